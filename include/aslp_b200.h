@@ -1,0 +1,228 @@
+/* aslp_b200.h -- C-ABI of libaslp_b200.so: the sm_100a backing for the aslp-nnet
+ * Component Propagate / Backpropagate / Update path and the aslp-parallel averaging.
+ *
+ * It replaces, for this path only, what src/aslp-cudamatrix offers the reference:
+ * the 257 `extern "C" cudaF_*` launchers (src/aslp-cudamatrix/cu-kernels-ansi.h:32-401),
+ * cuBLAS behind CuMatrixBase::AddMatMat (src/aslp-cudamatrix/cu-matrix.cc:1027-1062,
+ * cublas-wrappers.h:28-38) and CuDevice::Malloc/Free (cu-device.h:54-59) -- re-cut
+ * coarser: ONE symbol per fused operation.
+ *
+ * Conventions (all functions):
+ *   - plain C symbols, raw DEVICE pointers + {rows, cols, stride} in ELEMENTS (like
+ *     MatrixDim, src/aslp-cudamatrix/cu-matrixdim.h:51-55), scalars by value;
+ *   - row-major fp32 matrices; row stride (ld*) must be a multiple of 4 floats and base
+ *     pointers 16-byte aligned (what CuMatrix's pitched allocation gives the reference);
+ *   - every call takes an explicit stream (a cudaStream_t passed as void*), is
+ *     asynchronous, never allocates behind the caller's back (workspaces are explicit),
+ *     returns 0 on success like ctcStatus_t (src/warp-ctc/include/ctc.h:16-22) and
+ *     never throws; aslp_last_error() gives the text for a non-zero status;
+ *   - there is NO CPU path: without a CUDA device every compute call fails.
+ */
+#ifndef ASLP_B200_H_
+#define ASLP_B200_H_
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* aslp_stream_t; /* cudaStream_t */
+
+enum {
+  ASLP_STATUS_SUCCESS = 0,
+  ASLP_STATUS_MEMOPS_FAILED = 1,
+  ASLP_STATUS_INVALID_VALUE = 2,
+  ASLP_STATUS_EXECUTION_FAILED = 3,
+  ASLP_STATUS_UNKNOWN_ERROR = 4
+};
+
+/* ---- runtime: device, memory, streams (replaces CuDevice, cu-device.h:40-170) ---- */
+const char* aslp_last_error(void);
+unsigned long long aslp_launch_count(void);       /* kernels launched by this library so far */
+int aslp_device_count(int* n);
+int aslp_set_device(int dev);                     /* CuDevice::SelectGpuId */
+int aslp_malloc(void** dptr, size_t bytes);       /* CuDevice::Malloc (cu-device.h:54) */
+int aslp_free(void* dptr);                        /* CuDevice::Free   (cu-device.h:59) */
+int aslp_malloc_host(void** hptr, size_t bytes);  /* pinned staging for CopyFromMat/CopyToMat */
+int aslp_free_host(void* hptr);
+int aslp_memset(aslp_stream_t s, void* dptr, int value, size_t bytes);
+int aslp_memcpy_h2d(aslp_stream_t s, void* dst, const void* src, size_t bytes);
+int aslp_memcpy_d2h(aslp_stream_t s, void* dst, const void* src, size_t bytes);
+int aslp_memcpy_d2d(aslp_stream_t s, void* dst, const void* src, size_t bytes);
+/* strided 2-D copies, widths/pitches in BYTES (CuMatrix::CopyFromMat, cu-matrix.cc:236-330) */
+int aslp_memcpy2d_h2d(aslp_stream_t s, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height);
+int aslp_memcpy2d_d2h(aslp_stream_t s, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height);
+int aslp_memcpy2d_d2d(aslp_stream_t s, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height);
+int aslp_stream_create(aslp_stream_t* s);
+int aslp_stream_destroy(aslp_stream_t s);
+int aslp_stream_sync(aslp_stream_t s);
+int aslp_device_sync(void);
+
+/* ---- dense contraction: CuMatrixBase::AddMatMat (cu-matrix.cc:1027-1062) ----
+ * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C  (+ bias[n] broadcast over rows)
+ * then, if clip > 0, C = min(max(C, -clip), clip)  (ApplyFloor/ApplyCeiling on *_corr_,
+ * src/aslp-nnet/nnet-blstm-projected-streams-lc.h:1002-1017 fused into the epilogue).
+ * trans_a: A is stored [K,M]; trans_b: B is stored [N,K] (Kaldi kTrans).
+ * precision: ASLP_GEMM_3XTF32 = fp32-grade split-TF32 (3 tcgen05 MMAs per k-step),
+ *            ASLP_GEMM_TF32   = single-pass TF32 (looser bound),
+ *            ASLP_GEMM_FP32   = CUDA-core fp32 FMA (exact-order-free fp32; small/odd shapes).
+ * workspace: used only for split-K; aslp_gemm_workspace_bytes() gives the size (may be 0). */
+enum { ASLP_GEMM_3XTF32 = 0, ASLP_GEMM_TF32 = 1, ASLP_GEMM_FP32 = 2 };
+size_t aslp_gemm_workspace_bytes(int M, int N, int K);
+int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
+              float alpha, const float* A, int lda, const float* B, int ldb,
+              float beta, float* C, int ldc, const float* bias, float clip,
+              int precision, void* workspace, size_t workspace_bytes);
+
+/* ---- pointwise / reductions (cu-kernels.cu:1802-1858, 700-760, 416-437, 1346-1505) ---- */
+enum { ASLP_ACT_SIGMOID = 0, ASLP_ACT_TANH = 1, ASLP_ACT_RELU = 2 };
+/* Sigmoid/Tanh/ReLU::PropagateFnc (src/aslp-nnet/nnet-activation.h:153-199,276-298) */
+int aslp_act_fwd(aslp_stream_t s, int kind, float* out, int ldo, const float* in, int ldi, int rows, int cols);
+/* BackpropagateFnc: sigmoid y(1-y)e, tanh (1-y^2)e use the OUTPUT y; relu uses the INPUT x (x>0 ? e : 0) */
+int aslp_act_bwd(aslp_stream_t s, int kind, float* in_diff, int ldd, const float* y_or_x, int ldy,
+                 const float* out_diff, int lde, int rows, int cols);
+/* Softmax::PropagateFnc, ApplySoftMaxPerRow (nnet-activation.h:49-52; kaldi-vector.cc:852-859) */
+int aslp_softmax_rows(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int cols);
+/* dst = alpha*src + beta*dst elementwise (AddMat / CopyFromMat / Scale; cu-kernels.cu:584) */
+int aslp_axpby(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, int rows, int cols, float alpha, float beta);
+/* dst[r,c] = alpha*vec[c] + beta*dst[r,c]  (AddVecToRows, cu-kernels.cu:700) */
+int aslp_add_vec_to_rows(aslp_stream_t s, float* dst, int ldd, int rows, int cols, const float* vec, float alpha, float beta);
+/* vec[c] = alpha * sum_r mat[r,c] + beta*vec[c], then optional clip (CuVector::AddRowSumMat, cu-vector.cc:1145-1166) */
+int aslp_col_sum(aslp_stream_t s, float* vec, const float* mat, int ldm, int rows, int cols, float alpha, float beta, float clip);
+/* vec[c] = alpha * sum_r a[r,c]*b[r,c] + beta*vec[c], optional clip (AddDiagMatMat(kTrans,kNoTrans), cu-kernels.cu:992; peephole grads) */
+int aslp_col_dot(aslp_stream_t s, float* vec, const float* a, int lda, const float* b, int ldb, int rows, int cols, float alpha, float beta, float clip);
+/* clamp to [lo, hi] (ApplyFloor + ApplyCeiling) */
+int aslp_clamp(aslp_stream_t s, float* dst, int ldd, int rows, int cols, float lo, float hi);
+/* cu::RegularizeL1 (src/aslp-cudamatrix/cu-math.cc:37-77) */
+int aslp_regularize_l1(aslp_stream_t s, float* w, int ldw, float* grad, int ldg, int rows, int cols, float l1, float lr);
+/* AffineTransform max-norm renormalisation of rows (nnet-affine-transform.h:232-243) */
+int aslp_max_norm_rows(aslp_stream_t s, float* w, int ldw, int rows, int cols, float max_norm);
+/* transpose: dst[c,r] = src[r,c] */
+int aslp_transpose(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, int rows, int cols);
+/* sum of all elements / finite check (Nnet::Check, Xent asserts): out[0]=sum (double), out[1]=#non-finite */
+int aslp_sum_check(aslp_stream_t s, const float* m, int ldm, int rows, int cols, double* out2_dev);
+
+/* ---- Xent::Eval (src/aslp-nnet/nnet-loss.cc:63-156), one pass ----
+ * sparse one-target-per-frame form: tgt_idx[r] in [0,cols), tgt_w[r] = posterior weight.
+ * frame_w[r] = frame mask.  diff = (y - t) * (frame_w * sum_k t).
+ * stats_dev[5] (double, ACCUMULATED into): cross-entropy, entropy, likelihood, correct, frames. */
+int aslp_xent_sparse(aslp_stream_t s, float* diff, int ldd, const float* y, int ldy, int rows, int cols,
+                     const int* tgt_idx, const float* tgt_w, const float* frame_w, double* stats_dev);
+/* dense-target form (Posterior with several pdfs per frame, PosteriorToMatrix) */
+int aslp_xent_dense(aslp_stream_t s, float* diff, int ldd, const float* y, int ldy, const float* tgt, int ldt,
+                    int rows, int cols, const float* frame_w, double* stats_dev);
+/* row arg-max (FindRowMaxId, cu-kernels.cu:2141): first maximal index */
+int aslp_row_argmax(aslp_stream_t s, int* idx, const float* m, int ldm, int rows, int cols);
+
+/* ---- Splice (src/aslp-nnet/nnet-various.h:139-175; cu-math.cc:153-166) ---- */
+int aslp_splice_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int dim,
+                    const int* offsets_dev, int n_offsets);
+/* reference's backward: in_diff[t] = sum_c out_diff[clamp(t+off[c]), c-th block] (quirk kept) */
+int aslp_splice_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* out_diff, int ldo, int rows, int dim,
+                    const int* offsets_dev, int n_offsets);
+
+/* ---- RowConvolution (src/aslp-nnet/nnet-row-convolution.cc:90-169) ----
+ * stream-interleaved rows t*S+s; w is [dim, future+1]; seq_len_dev int[S]. */
+int aslp_rowconv_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int T, int S, int dim,
+                     const float* w, int ldw, int future, const int* seq_len_dev);
+int aslp_rowconv_bwd(aslp_stream_t s, float* in_diff, int ldd, float* w_diff, int ldwd,
+                     const float* in, int ldi, const float* out_diff, int ldo, int T, int S, int dim,
+                     const float* w, int ldw, int future, const int* seq_len_dev);
+
+/* ---- BatchNormalization (src/aslp-nnet/nnet-batch-normalization.h:139-284) ----
+ * train fwd: batch mean / inv-std (var_floor), xhat kept for backward, out = xhat*scale+shift,
+ * fp64 running sums acc_mean += sum x, acc_var += sum x^2 (:217-219). */
+int aslp_bn_fwd_train(aslp_stream_t s, float* out, int ldo, float* xhat, int ldx, const float* in, int ldi,
+                      int rows, int cols, const float* scale, const float* shift, float var_floor,
+                      float* mean, float* inv_std, double* acc_mean, double* acc_var);
+/* eval fwd with given mean / inv_std (FeedforwardFnc global-stats branch :167-174) */
+int aslp_bn_fwd_eval(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int cols,
+                     const float* scale, const float* shift, const float* mean, const float* inv_std);
+/* bwd: dscale = mmt*dscale + sum xhat*dy; dshift = mmt*dshift + sum dy; in_diff per :236-277 */
+int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int ldi, const float* xhat, int ldx,
+                const float* out_diff, int ldo, int rows, int cols, const float* scale,
+                const float* mean, const float* inv_std, float momentum, float* dscale, float* dshift);
+
+/* ---- CompactFsmn memory block (src/aslp-nnet/nnet-cfsmn-component.h:169-264) ----
+ * fwd : out[t,d] = in[t,d] + sum_{c=0}^{P+F} coef[c,d] * in[t+c-P, d]        (zero outside [0,T))
+ * bwd : in_diff[t,d] = out_diff[t,d] + sum_c coef[P+F-c, d] * out_diff[t+c-F, d]
+ * grad: coef_corr[c,d] = sum_t in[t+c-P,d] * out_diff[t,d]  (beta = 0, :224), then optional clip. */
+int aslp_fsmn_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int T, int D,
+                  const float* coef, int ldc, int past, int future);
+int aslp_fsmn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* out_diff, int ldo, int T, int D,
+                  const float* coef, int ldc, int past, int future);
+int aslp_fsmn_coef_grad(aslp_stream_t s, float* coef_corr, int ldc, const float* in, int ldi,
+                        const float* out_diff, int ldo, int T, int D, int past, int future, float clip);
+
+/* ---- LSTM family recurrence: one persistent launch walks all T steps ----
+ * Lstm (nnet-recurrent-component.cc:235-480), LstmProjectedStreams (nnet-lstm-projected-streams.h:313-617),
+ * BLstm / BLstmProjectedStreams (nnet-blstm-projected-streams.h:468-), BLstmProjectedStreamsLC
+ * (nnet-blstm-projected-streams-lc.h:503-1082).  Buffers keep the reference layout:
+ * [(T+2)*S, 7C+R] rows t*S+s, columns [g i f o c h m r]; row block 0 / T+1 are the boundary states.
+ * Before fwd the caller has put x*W_x^T + bias into the gifo columns of rows [S,(T+1)S) (one GEMM).
+ * Before bwd the caller has put out_diff into the r (or m if R==0) columns of dbuf rows [S,(T+1)S). */
+typedef struct {
+  int T, S, C, R;            /* R == 0: no projection, the recurrent input is m and w_r is [4C, C] */
+  int reverse;               /* 0: t = 1..T reading t-1;  1: t = T..1 reading t+1 */
+  float* buf;  int ldb;      /* forward activations  [(T+2)S, 7C+R] */
+  float* dbuf; int lddb;     /* backward derivatives [(T+2)S, 7C+R] (bwd only; NULL for fwd) */
+  const float* w_r;  int ldwr;   /* [4C, R or C] */
+  const float* w_rm; int ldwrm;  /* [R, C], NULL if R == 0 */
+  const float* peep_i; const float* peep_f; const float* peep_o; /* [C] each */
+  const int* seq_len_dev;    /* int[S] or NULL: fwd zeroes row t of a stream when t > len (blstm-projected-streams.h:654-657) */
+  float cell_clip;           /* 50 (ApplyFloor(-50)/ApplyCeiling(50)) */
+} aslp_lstm_dir_t;
+size_t aslp_lstm_workspace_bytes(int T, int S, int C, int R, int ndirs, int backward);
+int aslp_lstm_seq_fwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* workspace, size_t workspace_bytes);
+int aslp_lstm_seq_bwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* workspace, size_t workspace_bytes);
+
+/* ---- GruStreams recurrence (src/aslp-nnet/nnet-gru-streams.h:238-441) ----
+ * buf [(T+2)S, 5H] columns [z r m g h]; before fwd rows [S,(T+1)S) hold x*W_zrm_x^T + bias in [z r m]. */
+typedef struct {
+  int T, S, H;
+  float* buf;  int ldb;
+  float* dbuf; int lddb;      /* bwd only: [(T+2)S, 5H] with out_diff preloaded into the h columns */
+  const float* w_zr_h; int ldwzr;   /* [2H, H] */
+  const float* w_m_g;  int ldwmg;   /* [H, H] */
+} aslp_gru_t;
+int aslp_gru_seq_fwd(aslp_stream_t s, const aslp_gru_t* g, void* workspace, size_t workspace_bytes);
+int aslp_gru_seq_bwd(aslp_stream_t s, const aslp_gru_t* g, void* workspace, size_t workspace_bytes);
+
+/* ---- Eesen-style CTC on probabilities (src/aslp-nnet/ctc-loss.cc:115-227; cu-kernels.cu:3276-3534) ----
+ * probs [T*S, K] stream-interleaved softmax outputs; labels_dev int[S, 2*Lmax+1] expanded with blanks
+ * and padded with -1 (ctc-loss.cc:133-150); frames per stream in seq_len_dev.
+ * Outputs: pzx_dev[S] = log p(z|x); diff [T*S, K] = gradient w.r.t. the pre-softmax activations. */
+size_t aslp_ctc_eesen_workspace_bytes(int T, int S, int K, int Lexp_max);
+int aslp_ctc_eesen(aslp_stream_t s, float* diff, int ldd, const float* probs, int ldp, int T, int S, int K,
+                   const int* labels_dev, int Lexp_max, const int* seq_len_dev, float* pzx_dev,
+                   void* workspace, size_t workspace_bytes);
+
+/* ---- aslp-parallel averaging kernels (src/aslp-parallel/{bsp,bmuf,sod}-worker.cc, optimizer.h) ----
+ * All operate on ONE packed fp32 arena of n elements (UpdatableComponent::GetGpuParams order). */
+/* BSP pre-scale: buf = w * factor (bsp-worker.cc:41-47) */
+int aslp_sync_scale(aslp_stream_t s, float* dst, const float* w, size_t n, float factor);
+/* BMUF: g = w - w_prev (bmuf-worker.cc:46-50) */
+int aslp_sync_diff(aslp_stream_t s, float* g, const float* a, const float* b, size_t n);
+/* BMUF filter after the sum-allreduce of g (bmuf-worker.cc:55-66):
+ *   delta = mom*delta_prev + (1-mom)*lr*g ; w = w_prev + delta ; w_prev = w ; delta_prev = delta */
+int aslp_sync_bmuf_apply(aslp_stream_t s, float* w, float* w_prev, float* delta_prev, const float* g_sum,
+                         size_t n, float momentum, float learn_rate);
+/* SOD optimizers applied to the summed difference g = w_prev - w (sod-worker.cc:46-60; optimizer.h:21-170) */
+enum { ASLP_OPT_SGD = 0, ASLP_OPT_MOMENTUM = 1, ASLP_OPT_ADAGRAD = 2, ASLP_OPT_RMSPROP = 3, ASLP_OPT_ADADELTA = 4, ASLP_OPT_ADAM = 5 };
+int aslp_sync_sod_apply(aslp_stream_t s, int opt, float* w, const float* g, float* state1, float* state2,
+                        size_t n, float lr, float p1, float p2, float eps, int step);
+
+/* NCCL communicator owned by the library (replaces MpiNode, src/aslp-parallel/mpi-node.h:18-101) */
+typedef struct aslp_comm* aslp_comm_t;
+int aslp_comm_unique_id(char id_out[128]);                       /* rank 0, then shipped by the launcher */
+int aslp_comm_init(aslp_comm_t* c, const char id[128], int nranks, int rank);
+int aslp_comm_destroy(aslp_comm_t c);
+int aslp_comm_rank(aslp_comm_t c, int* rank, int* nranks);
+int aslp_comm_allreduce_sum_f32(aslp_comm_t c, aslp_stream_t s, float* buf, size_t n);   /* MpiNode::AllReduce (mpi-node.h:69-73) */
+int aslp_comm_allreduce_sum_f64(aslp_comm_t c, aslp_stream_t s, double* buf, size_t n);  /* ReduceAccStat (mpi-node.h:76-91) */
+int aslp_comm_allreduce_sum_i32(aslp_comm_t c, aslp_stream_t s, int* buf, size_t n);
+int aslp_comm_barrier(aslp_comm_t c, aslp_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASLP_B200_H_ */

@@ -1,0 +1,73 @@
+// Shared device/host helpers for libaslp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/aslp_b200.h"
+
+// ---- launch accounting (bench.py reports gpu_launches from this counter) ----
+extern unsigned long long g_aslp_launches;
+#define ASLP_COUNT_LAUNCH() (++g_aslp_launches)
+
+#define ASLP_CHECK_LAUNCH()                                   \
+  do {                                                        \
+    ASLP_COUNT_LAUNCH();                                      \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if (e__ != cudaSuccess) { aslp_set_last_error(e__, __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; } \
+  } while (0)
+
+#define ASLP_CUDA(call)                                       \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) { aslp_set_last_error(e__, __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; } \
+  } while (0)
+
+#define ASLP_REQUIRE(cond)                                    \
+  do { if (!(cond)) { aslp_set_last_error_msg("invalid argument: " #cond, __FILE__, __LINE__); return ASLP_STATUS_INVALID_VALUE; } } while (0)
+
+void aslp_set_last_error(cudaError_t e, const char* file, int line);
+void aslp_set_last_error_msg(const char* msg, const char* file, int line);
+
+static inline int aslp_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+int aslp_num_sms();
+
+// ---- device math with the reference's formulas (matrix/kaldi-vector.cc:885-936) ----
+__device__ __forceinline__ float ref_sigmoid(float x) {
+  // x>0: 1/(1+exp(-x)); else exp(x)/(exp(x)+1)  -- overflow-safe split used by the CPU path
+  if (x > 0.0f) return 1.0f / (1.0f + expf(-x));
+  float ex = expf(x);
+  return ex / (ex + 1.0f);
+}
+__device__ __forceinline__ float ref_tanh(float x) {
+  if (x > 0.0f) { float ie = expf(-x); return -1.0f + 2.0f / (1.0f + ie * ie); }
+  float ie = expf(x);
+  return 1.0f - 2.0f / (1.0f + ie * ie);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit accesses (read-once / write-once data: bypass L1 allocation)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}

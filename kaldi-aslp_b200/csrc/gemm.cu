@@ -1,0 +1,506 @@
+// Dense contractions for the aslp-nnet path: CuMatrixBase::AddMatMat
+// (src/aslp-cudamatrix/cu-matrix.cc:1027-1062 -> cublasSgemm, cublas-wrappers.h:28-38) replaced by a
+// hand-written sm_100a kernel: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ->
+// tcgen05.mma kind::tf32 with the fp32 accumulator in TMEM -> tcgen05.ld epilogue
+// (alpha/beta/bias/clip fused).  fp32 operands stay fp32 in HBM; the tensor core reads them as
+// TF32.  The default precision is a 3-pass split (a = hi + lo; hi*hi + lo*hi + hi*lo) that
+// restores fp32-grade products so the reference's 1e-4 parity bound holds.
+//
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  : epilogue (TMEM lane quarter = warp_id % 4)
+//   warps 6..9  : hi/lo splitter (3xTF32 only)
+#include "common.cuh"
+#include <cuda.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;           // BK floats = 128 B = one swizzle row
+constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB per operand tile
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();   // turn a protocol bug into an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct EpiParams {
+  float* C; int ldc;
+  int M, N, K;
+  float alpha, beta;
+  const float* bias;
+  float clip;
+  float* partial;      // split-K: [splits][M][ldp] raw accumulators, else NULL
+  int ldp;
+  int kb_per_split;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <bool A_MN, bool B_MN, int PASSES>
+__global__ void __launch_bounds__(PASSES == 1 ? 192 : 320, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p) {
+  constexpr int STAGES = (PASSES == 1) ? 6 : 3;
+  constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B wants 1024 B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // barriers live after the stage buffers
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar  = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 128);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + TILE_BYTES;
+        mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
+        if (!A_MN) {
+          tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);              // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, full_bar(s), m0 + 32 * j, kb * BK);  // box {32 m, 32 k}
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmB, full_bar(s), kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, full_bar(s), n0 + 32 * j, kb * BK);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=F32, a=b=TF32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(PASSES == 1 ? full_bar(s) : split_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + TILE_BYTES;
+        // K-major : rows of 128 B, 8-row groups 1024 B apart; one MMA (K=8) = 32 B along the row
+        // MN-major: 4 boxes of [32 k][128 B]; LBO = box stride 4096 B, SBO = 8 k-rows = 1024 B; one MMA = 8 k-rows
+        const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+        const uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t da = make_desc(sa + k * a_step, a_lbo, 1024u);
+          const uint64_t db = make_desc(sb + k * b_step, b_lbo, 1024u);
+          const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+          if (PASSES == 1) {
+            tc_mma_tf32(tmem_base, da, db, idesc, acc);
+          } else {
+            const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, 1024u);
+            const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, 1024u);
+            tc_mma_tf32(tmem_base, da_lo, db, idesc, acc);     // small terms first
+            tc_mma_tf32(tmem_base, da, db_lo, idesc, 1u);
+            tc_mma_tf32(tmem_base, da, db, idesc, 1u);
+          }
+        }
+        tc_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      tc_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue =====================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                               // TMEM lane quarter this warp may read
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const bool has_work = kb_end > kb_begin;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int nb = n0 + c * 32;
+      // tcgen05.ld is .sync.aligned: keep the warp convergent across iterations (no early continue)
+      if (row_ok && nb < p.N) {
+      if (p.partial != nullptr) {
+        float* dst = p.partial + ((size_t)blockIdx.z * p.M + row) * p.ldp + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (nb + j < p.N) {   // ldp is padded to a multiple of 4, so a float4 never crosses the row end
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (!has_work) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        }
+      } else {
+        float* dst = p.C + (size_t)row * p.ldc + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (nb + j + 3 < p.N) {
+            float4 o;
+            o.x = p.alpha * __uint_as_float(v[j]);     o.y = p.alpha * __uint_as_float(v[j + 1]);
+            o.z = p.alpha * __uint_as_float(v[j + 2]); o.w = p.alpha * __uint_as_float(v[j + 3]);
+            if (p.beta != 0.f) {
+              const float4 old = *reinterpret_cast<const float4*>(dst + j);
+              o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+            }
+            if (p.bias != nullptr) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (p.clip > 0.f) {
+              o.x = fminf(fmaxf(o.x, -p.clip), p.clip); o.y = fminf(fmaxf(o.y, -p.clip), p.clip);
+              o.z = fminf(fmaxf(o.z, -p.clip), p.clip); o.w = fminf(fmaxf(o.w, -p.clip), p.clip);
+            }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          } else {
+            for (int jj = j; jj < j + 4 && nb + jj < p.N; ++jj) {
+              float o = p.alpha * __uint_as_float(v[jj]);
+              if (p.beta != 0.f) o += p.beta * dst[jj];
+              if (p.bias != nullptr) o += p.bias[nb + jj];
+              if (p.clip > 0.f) o = fminf(fmaxf(o, -p.clip), p.clip);
+              dst[jj] = o;
+            }
+          }
+        }
+      }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== hi/lo splitter (3xTF32) =====================
+    if (PASSES == 3) {
+      const int t = threadIdx.x - 192;            // 0..127
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        float4* hi4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES);                   // A then B, 32 KB
+        float4* lo4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * TILE_BYTES);  // A_lo then B_lo
+#pragma unroll 4
+        for (int i = 0; i < (2 * TILE_BYTES / 16) / 128; ++i) {
+          const int idx = t + i * 128;
+          float4 x = hi4[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+          hi4[idx] = h;
+          lo4[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(split_bar(s));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem_base) : "memory");
+  }
+}
+
+// split-K second phase: C = alpha * sum_z partial[z] + beta*C + bias, clip
+__global__ void splitk_reduce_kernel(float* C, int ldc, const float* partial, int ldp, int splits, int M, int N,
+                                     float alpha, float beta, const float* bias, float clip) {
+  const int n4 = (N + 3) / 4;
+  const long long total = (long long)M * n4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / n4), c = (int)(i % n4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)z * M + r) * ldp + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+    float* dst = C + (size_t)r * ldc + c;
+    for (int j = 0; j < 4 && c + j < N; ++j) {
+      float v = alpha * o[j];
+      if (beta != 0.f) v += beta * dst[j];
+      if (bias != nullptr) v += bias[c + j];
+      if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+      dst[j] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CUDA-core fp32 GEMM (odd shapes / exact fp32)
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_fp32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
+                                                        int ldc, const float* __restrict__ bias, float clip) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int i = threadIdx.x; i < TM * TK; i += 256) {
+      int mm, kk;
+      if (TA) { mm = i % TM; kk = i / TM; } else { kk = i % TK; mm = i / TK; }
+      const int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < M && k < K) v = TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+      As[kk][mm] = v;
+    }
+    for (int i = threadIdx.x; i < TN * TK; i += 256) {
+      int nn, kk;
+      if (TB) { kk = i % TK; nn = i / TK; } else { nn = i % TN; kk = i / TN; }
+      const int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < N && k < K) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (beta != 0.f) v += beta * C[(size_t)m * ldc + n];
+      if (bias != nullptr) v += bias[n];
+      if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+      C[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// operand stored row-major [outer_extent rows][inner_extent cols], row stride ld floats
+bool make_tmap(CUtensorMap* tm, const float* base, int inner_extent, int outer_extent, int ld, int box_inner, int box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner_extent, (cuuint64_t)outer_extent};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <bool A_MN, bool B_MN, int PASSES>
+int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int splits) {
+  constexpr int STAGES = (PASSES == 1) ? 6 : 3;
+  constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * (3 * STAGES + 1) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASLP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  dim3 grid(aslp_div_up(p.N, BN), aslp_div_up(p.M, BM), splits);
+  gemm_tf32_kernel<A_MN, B_MN, PASSES><<<grid, PASSES == 1 ? 192 : 320, SMEM, st>>>(ta, tb, p);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
+int pick_splits(int M, int N, int K) {
+  const int tiles = aslp_div_up(M, BM) * aslp_div_up(N, BN);
+  const int num_kb = aslp_div_up(K, BK);
+  const int sms = aslp_num_sms();
+  if (tiles >= sms / 2 || num_kb < 16) return 1;
+  int splits = sms / tiles;
+  if (splits > num_kb / 8) splits = num_kb / 8;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  // make every split non-empty
+  const int per = aslp_div_up(num_kb, splits);
+  return aslp_div_up(num_kb, per);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t aslp_gemm_workspace_bytes(int M, int N, int K) {
+  const int splits = pick_splits(M, N, K);
+  if (splits <= 1) return 0;
+  const size_t ldp = ((size_t)N + 3) / 4 * 4;
+  return (size_t)splits * M * ldp * sizeof(float);
+}
+
+int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
+              void* workspace, size_t workspace_bytes) {
+  cudaStream_t st = (cudaStream_t)s;
+  ASLP_REQUIRE(M >= 0 && N >= 0 && K >= 0);
+  if (M == 0 || N == 0) return 0;
+  ASLP_REQUIRE(A != nullptr && B != nullptr && C != nullptr);
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
+                       (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && (bias == nullptr || (uintptr_t)bias % 16 == 0);
+  const bool tiny = (long long)M * N * K < (1ll << 18) || K == 0;
+  if (precision == ASLP_GEMM_FP32 || !aligned || tiny) {
+    dim3 grid(aslp_div_up(N, 64), aslp_div_up(M, 64));
+    if (!trans_a && !trans_b) gemm_fp32_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip);
+    else if (!trans_a && trans_b) gemm_fp32_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip);
+    else if (trans_a && !trans_b) gemm_fp32_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip);
+    else gemm_fp32_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip);
+    ASLP_CHECK_LAUNCH();
+    return 0;
+  }
+  // op(A)[M,K]: !trans_a -> stored [M][K] (K-major) ; trans_a -> stored [K][M] (M-major)
+  // op(B)[K,N]:  trans_b -> stored [N][K] (K-major) ; !trans_b -> stored [K][N] (N-major)
+  const bool a_mn = trans_a != 0, b_mn = trans_b == 0;
+  CUtensorMap ta, tb;
+  bool ok = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK) : make_tmap(&ta, A, K, M, lda, BK, BM);
+  ok = ok && (b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK) : make_tmap(&tb, B, K, N, ldb, BK, BN));
+  if (!ok) { aslp_set_last_error_msg("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; }
+
+  int splits = pick_splits(M, N, K);
+  const size_t ldp = ((size_t)N + 3) / 4 * 4;
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * ldp * sizeof(float))) splits = 1;
+  const int num_kb = aslp_div_up(K, BK);
+  EpiParams p;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.bias = bias; p.clip = clip;
+  p.partial = splits > 1 ? (float*)workspace : nullptr;
+  p.ldp = (int)ldp;
+  p.kb_per_split = aslp_div_up(num_kb, splits);
+  const bool one_pass = precision == ASLP_GEMM_TF32;
+  int rc;
+#define ASLP_DISPATCH(AM, BMN)                                             \
+  rc = one_pass ? launch_tc<AM, BMN, 1>(st, ta, tb, p, splits) : launch_tc<AM, BMN, 3>(st, ta, tb, p, splits)
+  if (!a_mn && !b_mn) { ASLP_DISPATCH(false, false); }
+  else if (!a_mn && b_mn) { ASLP_DISPATCH(false, true); }
+  else if (a_mn && !b_mn) { ASLP_DISPATCH(true, false); }
+  else { ASLP_DISPATCH(true, true); }
+#undef ASLP_DISPATCH
+  if (rc != 0) return rc;
+  if (splits > 1) {
+    const long long total = (long long)M * ((N + 3) / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > aslp_num_sms() * 8) blocks = aslp_num_sms() * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(C, ldc, (const float*)workspace, (int)ldp, splits, M, N, alpha, beta, bias, clip);
+    ASLP_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // extern "C"

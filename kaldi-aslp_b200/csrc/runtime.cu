@@ -1,0 +1,91 @@
+// Runtime plumbing of libaslp_b200.so: device selection, memory, streams, error text.
+// Replaces CuDevice (src/aslp-cudamatrix/cu-device.h:40-170) for the hot path.
+#include "common.cuh"
+#include <stdio.h>
+#include <string.h>
+
+unsigned long long g_aslp_launches = 0;
+static thread_local char g_err[512] = "";
+
+void aslp_set_last_error(cudaError_t e, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+}
+void aslp_set_last_error_msg(const char* msg, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "%s at %s:%d", msg, file, line);
+}
+
+int aslp_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+extern "C" {
+
+const char* aslp_last_error(void) { return g_err; }
+unsigned long long aslp_launch_count(void) { return g_aslp_launches; }
+
+int aslp_device_count(int* n) { ASLP_CUDA(cudaGetDeviceCount(n)); return 0; }
+int aslp_set_device(int dev) { ASLP_CUDA(cudaSetDevice(dev)); return 0; }
+int aslp_malloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) { aslp_set_last_error(e, __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
+  return 0;
+}
+int aslp_free(void* p) { ASLP_CUDA(cudaFree(p)); return 0; }
+int aslp_malloc_host(void** p, size_t bytes) {
+  cudaError_t e = cudaMallocHost(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) { aslp_set_last_error(e, __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
+  return 0;
+}
+int aslp_free_host(void* p) { ASLP_CUDA(cudaFreeHost(p)); return 0; }
+int aslp_memset(aslp_stream_t s, void* d, int v, size_t n) { ASLP_CUDA(cudaMemsetAsync(d, v, n, (cudaStream_t)s)); return 0; }
+int aslp_memcpy_h2d(aslp_stream_t s, void* d, const void* h, size_t n) { ASLP_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s)); return 0; }
+int aslp_memcpy_d2h(aslp_stream_t s, void* h, const void* d, size_t n) { ASLP_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s)); return 0; }
+int aslp_memcpy_d2d(aslp_stream_t s, void* d, const void* src, size_t n) { ASLP_CUDA(cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)s)); return 0; }
+int aslp_memcpy2d_h2d(aslp_stream_t s, void* d, size_t dp, const void* h, size_t sp, size_t w, size_t ht) {
+  if (w == 0 || ht == 0) return 0;
+  ASLP_CUDA(cudaMemcpy2DAsync(d, dp, h, sp, w, ht, cudaMemcpyHostToDevice, (cudaStream_t)s)); return 0; }
+int aslp_memcpy2d_d2h(aslp_stream_t s, void* h, size_t dp, const void* d, size_t sp, size_t w, size_t ht) {
+  if (w == 0 || ht == 0) return 0;
+  ASLP_CUDA(cudaMemcpy2DAsync(h, dp, d, sp, w, ht, cudaMemcpyDeviceToHost, (cudaStream_t)s)); return 0; }
+int aslp_memcpy2d_d2d(aslp_stream_t s, void* d, size_t dp, const void* src, size_t sp, size_t w, size_t ht) {
+  if (w == 0 || ht == 0) return 0;
+  ASLP_CUDA(cudaMemcpy2DAsync(d, dp, src, sp, w, ht, cudaMemcpyDeviceToDevice, (cudaStream_t)s)); return 0; }
+int aslp_stream_create(aslp_stream_t* s) { cudaStream_t st; ASLP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = (aslp_stream_t)st; return 0; }
+int aslp_stream_destroy(aslp_stream_t s) { ASLP_CUDA(cudaStreamDestroy((cudaStream_t)s)); return 0; }
+int aslp_stream_sync(aslp_stream_t s) { ASLP_CUDA(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
+int aslp_device_sync(void) { ASLP_CUDA(cudaDeviceSynchronize()); return 0; }
+
+}  // extern "C"
+
+// ---- per-(device, stream) scratch arena (see scratch.cuh) ----
+#include "scratch.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
+namespace {
+struct ScratchBuf { void* ptr; size_t bytes; };
+std::map<std::pair<int, cudaStream_t>, ScratchBuf> g_scratch;
+std::mutex g_scratch_mu;
+}
+void* aslp_scratch(cudaStream_t stream, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ScratchBuf& b = g_scratch[std::make_pair(dev, stream)];
+  const size_t want = bytes + ASLP_SCRATCH_RESERVED;
+  if (b.ptr == nullptr || b.bytes < want) {
+    if (b.ptr != nullptr) { cudaStreamSynchronize(stream); cudaFree(b.ptr); b.ptr = nullptr; }
+    size_t cap = want < (8u << 20) ? (8u << 20) : want * 2;
+    if (cudaMalloc(&b.ptr, cap) != cudaSuccess) { b.ptr = nullptr; b.bytes = 0; return nullptr; }
+    cudaMemsetAsync(b.ptr, 0, ASLP_SCRATCH_RESERVED, stream);
+    b.bytes = cap;
+  }
+  return static_cast<char*>(b.ptr) + ASLP_SCRATCH_RESERVED;
+}
