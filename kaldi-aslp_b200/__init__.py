@@ -76,6 +76,8 @@ def parse_header(path):
 def _bind(lib, header):
     decls = parse_header(header)
     for name, (restype, argtypes) in decls.items():
+        if os.environ.get("ASLP_B200_ALLOW_MISSING") and not hasattr(lib, name):
+            continue                     # bring-up only; the CPU test suite checks every symbol is exported
         fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes

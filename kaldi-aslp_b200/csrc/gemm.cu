@@ -18,7 +18,7 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;           // BK floats = 128 B = one swizzle row
 constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB per operand tile
-constexpr uint32_t SPIN_LIMIT = 1u << 22;
+constexpr uint32_t SPIN_LIMIT = 1u << 18;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
