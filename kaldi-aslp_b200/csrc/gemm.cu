@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include "scratch.cuh"
 
 namespace {
 
@@ -76,13 +78,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
 
 // UMMA shared-memory descriptor (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B -- the ONLY legal shared-memory layout for
+// MN-major 32-bit (tf32) operands: 32-byte chunks swizzled inside the 128 B row, atom = 4 k-rows x 128 B
+// (cutlass/gemm/collective/builders/sm100_common.inl:92; TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -175,20 +180,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + TILE_BYTES;
-        // K-major : rows of 128 B, 8-row groups 1024 B apart; one MMA (K=8) = 32 B along the row
-        // MN-major: 4 boxes of [32 k][128 B]; LBO = box stride 4096 B, SBO = 8 k-rows = 1024 B; one MMA = 8 k-rows
+        // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA (K=8) = 32 B along the row
+        // MN-major: 4 boxes of [32 k][128 B]; LBO = box stride 4096 B; swizzle atom = 4 k-rows -> SBO = 512 B;
+        //           one MMA consumes 8 k-rows = 1024 B
         const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+        const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+        const uint32_t a_lay = A_MN ? 1u : 2u, b_lay = B_MN ? 1u : 2u;
         const uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t da = make_desc(sa + k * a_step, a_lbo, 1024u);
-          const uint64_t db = make_desc(sb + k * b_step, b_lbo, 1024u);
+          const uint64_t da = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
+          const uint64_t db = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
           const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
           if (PASSES == 1) {
             tc_mma_tf32(tmem_base, da, db, idesc, acc);
           } else {
-            const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, 1024u);
-            const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, 1024u);
+            const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, b_sbo, b_lay);
             tc_mma_tf32(tmem_base, da_lo, db, idesc, acc);     // small terms first
             tc_mma_tf32(tmem_base, da, db_lo, idesc, 1u);
             tc_mma_tf32(tmem_base, da, db, idesc, 1u);
@@ -393,7 +401,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // operand stored row-major [outer_extent rows][inner_extent cols], row stride ld floats
-bool make_tmap(CUtensorMap* tm, const float* base, int inner_extent, int outer_extent, int ld, int box_inner, int box_outer) {
+bool make_tmap(CUtensorMap* tm, const float* base, int inner_extent, int outer_extent, int ld, int box_inner, int box_outer, bool mn_major) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return false;
   cuuint64_t dims[2] = {(cuuint64_t)inner_extent, (cuuint64_t)outer_extent};
@@ -401,7 +409,8 @@ bool make_tmap(CUtensorMap* tm, const float* base, int inner_extent, int outer_e
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -468,15 +477,23 @@ int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, fl
   }
   // op(A)[M,K]: !trans_a -> stored [M][K] (K-major) ; trans_a -> stored [K][M] (M-major)
   // op(B)[K,N]:  trans_b -> stored [N][K] (K-major) ; !trans_b -> stored [K][N] (N-major)
-  const bool a_mn = trans_a != 0, b_mn = trans_b == 0;
+  bool a_mn = trans_a != 0, b_mn = trans_b == 0;
+  static const bool via_transpose = getenv("ASLP_GEMM_MN_TRANSPOSE") != nullptr;   // bring-up switch: K-major only
+  if (via_transpose && (a_mn || b_mn)) {
+    const size_t lda_t = ((size_t)K + 3) / 4 * 4, ldb_t = lda_t;
+    float* scr = (float*)aslp_scratch(st, ((a_mn ? (size_t)M * lda_t : 0) + (b_mn ? (size_t)N * ldb_t : 0)) * sizeof(float));
+    if (scr == nullptr) { aslp_set_last_error_msg("scratch allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
+    if (a_mn) { int rc = aslp_transpose(s, scr, (int)lda_t, A, lda, K, M); if (rc) return rc; A = scr; lda = (int)lda_t; scr += (size_t)M * lda_t; a_mn = false; }
+    if (b_mn) { int rc = aslp_transpose(s, scr, (int)ldb_t, B, ldb, K, N); if (rc) return rc; B = scr; ldb = (int)ldb_t; b_mn = false; }
+  }
   CUtensorMap ta, tb;
-  bool ok = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK) : make_tmap(&ta, A, K, M, lda, BK, BM);
-  ok = ok && (b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK) : make_tmap(&tb, B, K, N, ldb, BK, BN));
+  bool ok = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK, true) : make_tmap(&ta, A, K, M, lda, BK, BM, false);
+  ok = ok && (b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK, true) : make_tmap(&tb, B, K, N, ldb, BK, BN, false));
   if (!ok) { aslp_set_last_error_msg("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; }
 
   int splits = pick_splits(M, N, K);
   const size_t ldp = ((size_t)N + 3) / 4 * 4;
-  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * ldp * sizeof(float))) splits = 1;
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * ldp * sizeof(float))) splits = 1;   // caller gave no room: single pass
   const int num_kb = aslp_div_up(K, BK);
   EpiParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.bias = bias; p.clip = clip;

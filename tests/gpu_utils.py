@@ -50,9 +50,17 @@ class DMat:
         return self.t[: self.rows, : self.cols].cpu().numpy()
 
 
+_KEEP = []   # device tensors handed to the C-ABI by raw pointer must outlive the asynchronous kernels
+
+
 def dvec(arr, dtype=np.float32):
     a = np.ascontiguousarray(arr, dtype)
-    return torch.from_numpy(a).cuda()
+    t = torch.from_numpy(a).cuda()
+    _KEEP.append(t)
+    if len(_KEEP) > 256:
+        torch.cuda.synchronize()
+        del _KEEP[:128]
+    return t
 
 
 def ptr(t):

@@ -107,7 +107,10 @@ def test_ctc_cfg3_geometry_many_utts_warp_path():
     sel = list(range(0, mb, 97))
     c2, g2 = CO.cost_and_grad(acts[:, sel, :], [labels[i] for i in sel], [T] * len(sel))
     assert np.allclose(costs[sel], c2, rtol=1e-4, atol=1e-5)
-    assert np.abs(grads[:, sel, :] - g2).max() < 1e-4
+    # fp32 log-space: alpha+beta-logZ is a difference of numbers of magnitude |cost| ~ 1e3 whose ulp is 6e-5, so
+    # posteriors (and the reference's own) carry ~4 ulp(|cost|) of absolute error; 1e-4 holds for short T (above)
+    tol = max(1e-4, 4 * float(np.spacing(np.float32(np.abs(c2).max()))))
+    assert np.abs(grads[:, sel, :] - g2).max() < tol
     # size-independent property: every gradient row sums to ~0 (softmax - posterior, both sum to 1)
     assert np.abs(grads.sum(axis=2)).max() < 2e-4
 

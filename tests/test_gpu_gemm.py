@@ -9,9 +9,9 @@ pytestmark = pytest.mark.gpu
 
 # tolerance: relative to max|C| of the fp32 oracle.
 #   3xTF32 (default): fp32-grade, the north_star's 1e-4 bound (we assert 2e-5)
-#   TF32 single pass: stated looser bound 2e-3 (10-bit mantissa operands)
+#   TF32 single pass: stated looser bound 5e-3 (10-bit mantissa operands, truncated)
 #   FP32 CUDA cores : 2e-5
-TOL = {0: 2e-5, 1: 2e-3, 2: 2e-5}
+TOL = {0: 2e-5, 1: 5e-3, 2: 2e-5}
 
 SHAPES = [
     # (M, N, K)

@@ -1,0 +1,117 @@
+"""Quick device-time probe of the hot kernels at BASELINE cfg3 geometry (CUDA events, warm-up, median).
+Development aid only; bench.py is the judged measurement."""
+import ctypes
+import json
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, __file__.rsplit("/tools/", 1)[0])
+import kaldi_aslp_b200 as K  # noqa: E402
+
+P = ctypes.c_void_p
+L = K.cuda_lib()
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def stream():
+    return P(torch.cuda.current_stream().cuda_stream)
+
+
+def probe_gemm(M, N, Kd, ta, tb, prec):
+    A = torch.randn((Kd, M) if ta else (M, Kd), device="cuda")
+    B = torch.randn((N, Kd) if tb else (Kd, N), device="cuda")
+    C = torch.zeros((M, N), device="cuda")
+    wsb = L.aslp_gemm_workspace_bytes(M, N, Kd)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device="cuda")
+
+    def fn():
+        K.check(L.aslp_gemm(stream(), int(ta), int(tb), M, N, Kd, 1.0, P(A.data_ptr()), A.shape[1], P(B.data_ptr()), B.shape[1],
+                            0.0, P(C.data_ptr()), N, P(0), 0.0, prec, P(ws.data_ptr()), wsb))
+    ms = timeit(fn)
+    return {"op": "gemm", "M": M, "N": N, "K": Kd, "ta": ta, "tb": tb, "prec": prec, "ms": ms, "tflops": 2.0 * M * N * Kd / ms / 1e9}
+
+
+def probe_lstm(T, S, C, R, ndirs, bwd):
+    W = 7 * C + R
+    arr = (K.LstmDir * ndirs)()
+    keep = []
+    for d in range(ndirs):
+        buf = torch.randn(((T + 2) * S, W), device="cuda") * 0.1
+        dbuf = torch.randn(((T + 2) * S, W), device="cuda") * 0.1
+        Rr = R if R > 0 else C
+        w_r = torch.randn((4 * C, Rr), device="cuda") * (0.5 / np.sqrt(Rr))
+        w_rm = torch.randn((max(R, 1), C), device="cuda") * (0.5 / np.sqrt(C))
+        pe = [torch.randn(C, device="cuda") * 0.1 for _ in range(3)]
+        a = arr[d]
+        a.T, a.S, a.C, a.R, a.reverse = T, S, C, R, d
+        a.buf, a.ldb, a.dbuf, a.lddb = buf.data_ptr(), W, dbuf.data_ptr(), W
+        a.w_r, a.ldwr = w_r.data_ptr(), Rr
+        a.w_rm, a.ldwrm = (w_rm.data_ptr(), C) if R > 0 else (None, 0)
+        a.peep_i, a.peep_f, a.peep_o = pe[0].data_ptr(), pe[1].data_ptr(), pe[2].data_ptr()
+        a.seq_len_dev = None
+        a.cell_clip = 50.0
+        keep.append((buf, dbuf, w_r, w_rm, pe))
+    wsb = L.aslp_lstm_workspace_bytes(T, S, C, R, ndirs, int(bwd))
+    ws = torch.empty(wsb + 256, dtype=torch.uint8, device="cuda")
+    f = L.aslp_lstm_seq_bwd if bwd else L.aslp_lstm_seq_fwd
+
+    def fn():
+        K.check(f(stream(), ctypes.byref(arr), ndirs, P(ws.data_ptr()), wsb))
+    ms = timeit(fn, iters=5, warm=2)
+    return {"op": "lstm_bwd" if bwd else "lstm_fwd", "T": T, "S": S, "C": C, "R": R, "ndirs": ndirs, "ms": ms, "us_per_step": 1e3 * ms / T}
+
+
+def probe_ctc(T, mb, Kc, Lab):
+    rng = np.random.default_rng(0)
+    acts = torch.randn((T, mb, Kc), device="cuda")
+    grads = torch.zeros_like(acts)
+    flat = np.ascontiguousarray(rng.integers(1, Kc, size=mb * Lab), np.int32)
+    llen = np.full(mb, Lab, np.int32)
+    ilen = np.full(mb, T, np.int32)
+    costs = np.zeros(mb, np.float32)
+    info = K.CtcComputeInfo(1, torch.cuda.current_stream().cuda_stream)
+    size = ctypes.c_size_t(0)
+    L.get_workspace_size(llen.ctypes.data, ilen.ctypes.data, Kc, mb, info, ctypes.addressof(size))
+    ws = torch.empty(size.value + 256, dtype=torch.uint8, device="cuda")
+
+    def fn():
+        grads.zero_()
+        rc = L.compute_ctc_loss(P(acts.data_ptr()), P(grads.data_ptr()), flat.ctypes.data, llen.ctypes.data, ilen.ctypes.data,
+                                Kc, mb, costs.ctypes.data, P(ws.data_ptr()), info)
+        assert rc == 0
+    ms = timeit(fn, iters=5, warm=2)
+    return {"op": "ctc", "T": T, "mb": mb, "K": Kc, "L": Lab, "ms": ms, "utts_per_s": mb / ms * 1e3}
+
+
+if __name__ == "__main__":
+    out = []
+    for spec in [(16000, 1280, 640, False, True), (16000, 1280, 40, False, True), (16000, 640, 1280, False, False),
+                 (1280, 640, 16000, True, False), (320, 320, 16000, True, False), (16000, 72, 640, False, True),
+                 (8192, 8192, 8192, False, True)]:
+        for prec in (0, 1):
+            try:
+                out.append(probe_gemm(*spec, prec))
+            except Exception as e:  # noqa: BLE001
+                out.append({"op": "gemm", "spec": spec, "prec": prec, "error": str(e)[:200]})
+            print(json.dumps(out[-1]), flush=True)
+    for bwd in (False, True):
+        out.append(probe_lstm(1000, 16, 320, 320, 2, bwd)); print(json.dumps(out[-1]), flush=True)
+        out.append(probe_lstm(200, 100, 512, 0, 1, bwd)); print(json.dumps(out[-1]), flush=True)
+    out.append(probe_ctc(1000, 16, 72, 100)); print(json.dumps(out[-1]), flush=True)
+    out.append(probe_ctc(1000, 2048, 72, 100)); print(json.dumps(out[-1]), flush=True)
