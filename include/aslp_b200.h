@@ -45,6 +45,7 @@ int aslp_free(void* dptr);                        /* CuDevice::Free   (cu-device
 int aslp_malloc_host(void** hptr, size_t bytes);  /* pinned staging for CopyFromMat/CopyToMat */
 int aslp_free_host(void* hptr);
 int aslp_memset(aslp_stream_t s, void* dptr, int value, size_t bytes);
+int aslp_memset2d(aslp_stream_t s, void* dptr, size_t pitch, int value, size_t width, size_t height);   /* strided views, bytes */
 int aslp_memcpy_h2d(aslp_stream_t s, void* dst, const void* src, size_t bytes);
 int aslp_memcpy_d2h(aslp_stream_t s, void* dst, const void* src, size_t bytes);
 int aslp_memcpy_d2d(aslp_stream_t s, void* dst, const void* src, size_t bytes);
@@ -184,6 +185,7 @@ typedef struct {
   const float* w_zr_h; int ldwzr;   /* [2H, H] */
   const float* w_m_g;  int ldwmg;   /* [H, H] */
 } aslp_gru_t;
+size_t aslp_gru_workspace_bytes(int T, int S, int H, int backward);
 int aslp_gru_seq_fwd(aslp_stream_t s, const aslp_gru_t* g, void* workspace, size_t workspace_bytes);
 int aslp_gru_seq_bwd(aslp_stream_t s, const aslp_gru_t* g, void* workspace, size_t workspace_bytes);
 
@@ -210,6 +212,17 @@ int aslp_sync_bmuf_apply(aslp_stream_t s, float* w, float* w_prev, float* delta_
 enum { ASLP_OPT_SGD = 0, ASLP_OPT_MOMENTUM = 1, ASLP_OPT_ADAGRAD = 2, ASLP_OPT_RMSPROP = 3, ASLP_OPT_ADADELTA = 4, ASLP_OPT_ADAM = 5 };
 int aslp_sync_sod_apply(aslp_stream_t s, int opt, float* w, const float* g, float* state1, float* state2,
                         size_t n, float lr, float p1, float p2, float eps, int step);
+
+/* multi-tensor forms: parameters stay in the components' own tensors (UpdatableComponent::GetGpuParams views, element
+ * counts including row padding); `table_dev` is a DEVICE array of {ptr, offset into the packed arena, n}.  One launch each. */
+typedef struct { float* ptr; size_t offset; size_t n; } aslp_tensor_ref_t;
+int aslp_sync_pack(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, float factor);           /* arena = w * factor (BSP) */
+int aslp_sync_pack_diff(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, const float* w_prev_arena, float sign);  /* arena = sign*(w - w_prev) */
+int aslp_sync_unpack(aslp_stream_t s, const float* arena, const aslp_tensor_ref_t* table_dev, int ntensors);                 /* w = arena */
+int aslp_sync_bmuf_apply_packed(aslp_stream_t s, const aslp_tensor_ref_t* table_dev, int ntensors, float* w_prev_arena, float* delta_prev_arena,
+                                const float* g_sum_arena, float momentum, float learn_rate);
+int aslp_sync_sod_apply_packed(aslp_stream_t s, int opt, const aslp_tensor_ref_t* table_dev, int ntensors, const float* g_sum_arena, float* state1,
+                               float* state2, float* w_prev_arena, float lr, float p1, float p2, float eps, int step);
 
 /* NCCL communicator owned by the library (replaces MpiNode, src/aslp-parallel/mpi-node.h:18-101) */
 typedef struct aslp_comm* aslp_comm_t;

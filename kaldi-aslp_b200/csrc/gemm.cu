@@ -431,17 +431,22 @@ int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, con
   return 0;
 }
 
+// Split-K policy.  (a) fill the chip: aim for ~2 CTAs per SM when the output has few tiles (wgrad shapes);
+// (b) bound the length of one TMEM accumulation chain to 32 k-blocks (K = 1024): the tensor core's fp32
+// accumulate truncates, so its error grows with the chain length, while the split partials are summed with
+// IEEE round-to-nearest adds in the reduce kernel.  Large square GEMMs (many tiles) are left unsplit.
 int pick_splits(int M, int N, int K) {
   const int tiles = aslp_div_up(M, BM) * aslp_div_up(N, BN);
   const int num_kb = aslp_div_up(K, BK);
   const int sms = aslp_num_sms();
-  if (tiles >= sms / 2 || num_kb < 16) return 1;
-  int splits = sms / tiles;
-  if (splits > num_kb / 8) splits = num_kb / 8;
+  if (tiles >= sms || num_kb < 16) return 1;
+  int splits = aslp_div_up(2 * sms, tiles);
+  const int by_chain = aslp_div_up(num_kb, 32);
+  if (by_chain > splits) splits = by_chain;
+  if (splits > num_kb / 4) splits = num_kb / 4;
   if (splits > 32) splits = 32;
   if (splits < 1) splits = 1;
-  // make every split non-empty
-  const int per = aslp_div_up(num_kb, splits);
+  const int per = aslp_div_up(num_kb, splits);     // make every split non-empty
   return aslp_div_up(num_kb, per);
 }
 

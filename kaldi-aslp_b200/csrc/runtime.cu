@@ -45,6 +45,9 @@ int aslp_malloc_host(void** p, size_t bytes) {
 }
 int aslp_free_host(void* p) { ASLP_CUDA(cudaFreeHost(p)); return 0; }
 int aslp_memset(aslp_stream_t s, void* d, int v, size_t n) { ASLP_CUDA(cudaMemsetAsync(d, v, n, (cudaStream_t)s)); return 0; }
+int aslp_memset2d(aslp_stream_t s, void* d, size_t pitch, int v, size_t w, size_t h) {
+  if (w == 0 || h == 0) return 0;
+  ASLP_CUDA(cudaMemset2DAsync(d, pitch, v, w, h, (cudaStream_t)s)); return 0; }
 int aslp_memcpy_h2d(aslp_stream_t s, void* d, const void* h, size_t n) { ASLP_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s)); return 0; }
 int aslp_memcpy_d2h(aslp_stream_t s, void* h, const void* d, size_t n) { ASLP_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s)); return 0; }
 int aslp_memcpy_d2d(aslp_stream_t s, void* d, const void* src, size_t n) { ASLP_CUDA(cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)s)); return 0; }

@@ -61,6 +61,70 @@ __global__ void sod_kernel(int opt, float* w, const float* g, float* s1, float* 
   }
 }
 
+// ---- multi-tensor forms: the model's parameter tensors stay where the components own them (GetGpuParams views);
+// a device table {ptr, arena offset, n} lets ONE launch gather / scatter all of them against a packed arena.
+// blockIdx.y = tensor, blockIdx.x strides over its elements.
+enum { MT_PACK_SCALE = 0, MT_PACK_DIFF = 1, MT_UNPACK = 2, MT_BMUF = 3, MT_SOD = 4 };
+struct MtArgs {
+  const aslp_tensor_ref_t* table;
+  float* arena;            // PACK_*: destination; UNPACK: source; BMUF/SOD: the all-reduced g
+  float* w_prev;           // arena-shaped
+  float* s1; float* s2;    // BMUF: s1 = delta_prev ; SOD: optimizer states
+  float a, b, p1, p2, eps; // PACK_SCALE: a = factor; PACK_DIFF: a = sign; BMUF: a = momentum, b = learn rate; SOD: a = lr
+  int opt, step;
+};
+template <int MODE>
+__global__ void multi_tensor_kernel(MtArgs A) {
+  const aslp_tensor_ref_t t = A.table[blockIdx.y];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < t.n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = t.offset + i;
+    if (MODE == MT_PACK_SCALE) A.arena[j] = t.ptr[i] * A.a;
+    else if (MODE == MT_PACK_DIFF) A.arena[j] = A.a * (t.ptr[i] - A.w_prev[j]);
+    else if (MODE == MT_UNPACK) t.ptr[i] = A.arena[j];
+    else if (MODE == MT_BMUF) {
+      const float delta = A.a * A.s1[j] + (1.0f - A.a) * A.b * A.arena[j];
+      const float nw = A.w_prev[j] + delta;
+      t.ptr[i] = nw; A.w_prev[j] = nw; A.s1[j] = delta;
+    }
+  }
+}
+// SOD: apply the optimizer to the scattered weights with arena-shaped g / states, then w_prev = w (sod-worker.cc:55-59)
+__global__ void multi_tensor_sod_kernel(MtArgs A) {
+  const aslp_tensor_ref_t t = A.table[blockIdx.y];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < t.n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = t.offset + i;
+    const float gi = A.arena[j], lr = A.a, p1 = A.p1, p2 = A.p2, eps = A.eps;
+    float wi = t.ptr[i];
+    switch (A.opt) {
+      case ASLP_OPT_SGD: wi -= lr * gi; break;
+      case ASLP_OPT_MOMENTUM: { const float v = p1 * A.s1[j] + lr * gi; A.s1[j] = v; wi -= v; } break;
+      case ASLP_OPT_ADAGRAD: { const float a = A.s1[j] + gi * gi; A.s1[j] = a; wi -= lr * gi * (1.0f / sqrtf(fmaxf(a, eps))); } break;
+      case ASLP_OPT_RMSPROP: { const float a = 0.9f * A.s1[j] + 0.1f * gi * gi; A.s1[j] = a; wi -= lr * gi * (1.0f / sqrtf(fmaxf(a, eps))); } break;
+      case ASLP_OPT_ADADELTA: {
+        const float a = p1 * A.s1[j] + (1.0f - p1) * gi * gi;
+        const float upd = (1.0f / sqrtf(fmaxf(a, eps))) * sqrtf(fmaxf(A.s2[j], eps)) * gi;
+        A.s1[j] = a; wi -= upd; A.s2[j] = p1 * A.s2[j] + (1.0f - p1) * upd * upd;
+      } break;
+      case ASLP_OPT_ADAM: {
+        const float m = p1 * A.s1[j] + (1.0f - p1) * gi, v = p2 * A.s2[j] + (1.0f - p2) * gi * gi;
+        A.s1[j] = m; A.s2[j] = v;
+        const float c1 = 1.0f / (1.0f - powf(p1, (float)A.step)), c2 = 1.0f / (1.0f - powf(p2, (float)A.step));
+        wi -= lr * c1 * m * (1.0f / sqrtf(fmaxf(v * c2, eps)));
+      } break;
+    }
+    t.ptr[i] = wi;
+    A.w_prev[j] = wi;
+  }
+}
+template <int MODE>
+int launch_mt(aslp_stream_t s, const MtArgs& A, int ntensors) {
+  if (ntensors == 0) return 0;
+  dim3 grid(aslp_num_sms() * 2 / (ntensors < 8 ? 1 : 4) + 1, ntensors);
+  multi_tensor_kernel<MODE><<<grid, 256, 0, (cudaStream_t)s>>>(A);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
 #define ASLP_NCCL(call)                                                                              \
   do {                                                                                               \
     ncclResult_t r__ = (call);                                                                       \
@@ -94,6 +158,36 @@ int aslp_sync_sod_apply(aslp_stream_t s, int opt, float* w, const float* g, floa
   if (n == 0) return 0;
   ASLP_REQUIRE(opt >= ASLP_OPT_SGD && opt <= ASLP_OPT_ADAM);
   sod_kernel<<<blocks_for(n * 4), 256, 0, (cudaStream_t)s>>>(opt, w, g, state1, state2, n, lr, p1, p2, eps, step);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
+int aslp_sync_pack(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, float factor) {
+  MtArgs A = {}; A.table = table_dev; A.arena = arena; A.a = factor;
+  return launch_mt<MT_PACK_SCALE>(s, A, ntensors);
+}
+int aslp_sync_pack_diff(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, const float* w_prev_arena, float sign) {
+  MtArgs A = {}; A.table = table_dev; A.arena = arena; A.w_prev = const_cast<float*>(w_prev_arena); A.a = sign;
+  return launch_mt<MT_PACK_DIFF>(s, A, ntensors);
+}
+int aslp_sync_unpack(aslp_stream_t s, const float* arena, const aslp_tensor_ref_t* table_dev, int ntensors) {
+  MtArgs A = {}; A.table = table_dev; A.arena = const_cast<float*>(arena);
+  return launch_mt<MT_UNPACK>(s, A, ntensors);
+}
+int aslp_sync_bmuf_apply_packed(aslp_stream_t s, const aslp_tensor_ref_t* table_dev, int ntensors, float* w_prev_arena, float* delta_prev_arena,
+                                const float* g_sum_arena, float momentum, float learn_rate) {
+  MtArgs A = {}; A.table = table_dev; A.arena = const_cast<float*>(g_sum_arena); A.w_prev = w_prev_arena; A.s1 = delta_prev_arena;
+  A.a = momentum; A.b = learn_rate;
+  return launch_mt<MT_BMUF>(s, A, ntensors);
+}
+int aslp_sync_sod_apply_packed(aslp_stream_t s, int opt, const aslp_tensor_ref_t* table_dev, int ntensors, const float* g_sum_arena, float* state1,
+                               float* state2, float* w_prev_arena, float lr, float p1, float p2, float eps, int step) {
+  ASLP_REQUIRE(opt >= ASLP_OPT_SGD && opt <= ASLP_OPT_ADAM);
+  if (ntensors == 0) return 0;
+  MtArgs A = {}; A.table = table_dev; A.arena = const_cast<float*>(g_sum_arena); A.w_prev = w_prev_arena; A.s1 = state1; A.s2 = state2;
+  A.a = lr; A.p1 = p1; A.p2 = p2; A.eps = eps; A.opt = opt; A.step = step;
+  dim3 grid(aslp_num_sms() / 2 + 1, ntensors);
+  multi_tensor_sod_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(A);
   ASLP_CHECK_LAUNCH();
   return 0;
 }

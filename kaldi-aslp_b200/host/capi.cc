@@ -1,0 +1,214 @@
+// capi.cc -- C handle API of include/aslp_nnet_c.h over the C++ host layer.  Exceptions stop here.
+#include <cstring>
+#include "../../include/aslp_nnet_c.h"
+#include "cu-workspace.h"
+#include "nnet-loss.h"
+#include "nnet-nnet.h"
+#include "parallel.h"
+
+using namespace kaldi;
+using namespace kaldi::aslp_nnet;
+
+static thread_local std::string g_err;
+
+#define CAPI_BEGIN try {
+#define CAPI_END                                                   \
+  return 0;                                                        \
+  } catch (const std::exception& e) { g_err = e.what(); return 1; } \
+  catch (...) { g_err = "unknown exception"; return 1; }
+
+static Nnet* N(aslp_nnet_t n) { if (n == nullptr) KALDI_ERR << "null Nnet handle"; return static_cast<Nnet*>(n); }
+
+static void CopyOut(const std::string& s, char* buf, size_t bytes) {
+  if (buf == nullptr || bytes == 0) return;
+  const size_t k = std::min(bytes - 1, s.size());
+  memcpy(buf, s.data(), k);
+  buf[k] = '\0';
+}
+
+// reusable device staging for host inputs / outputs
+static CuMatrix g_in, g_out, g_diff, g_indiff, g_loss_diff;
+
+extern "C" {
+
+const char* aslp_nnet_last_error(void) { return g_err.c_str(); }
+int aslp_nnet_select_device(int dev) { CAPI_BEGIN CuSelectDevice(dev); CAPI_END }
+int aslp_nnet_srand(int seed) { srand(seed); return 0; }
+int aslp_nnet_set_gemm_precision(int precision) { SetGemmPrecision(precision); return 0; }
+int aslp_nnet_device_sync(void) { CAPI_BEGIN CuSync(); CAPI_END }
+unsigned long long aslp_nnet_launch_count(void) { return aslp_launch_count(); }
+
+int aslp_nnet_init(const char* proto_file, aslp_nnet_t* out) { CAPI_BEGIN Nnet* n = new Nnet(); try { n->Init(proto_file); } catch (...) { delete n; throw; } *out = n; CAPI_END }
+int aslp_nnet_read(const char* model_file, aslp_nnet_t* out) { CAPI_BEGIN Nnet* n = new Nnet(); try { n->Read(model_file); } catch (...) { delete n; throw; } *out = n; CAPI_END }
+int aslp_nnet_write(aslp_nnet_t n, const char* file, int binary) { CAPI_BEGIN N(n)->Write(file, binary != 0); CAPI_END }
+int aslp_nnet_destroy(aslp_nnet_t n) { CAPI_BEGIN delete static_cast<Nnet*>(n); CAPI_END }
+int aslp_nnet_input_dim(aslp_nnet_t n, int* dim) { CAPI_BEGIN *dim = N(n)->InputDim(); CAPI_END }
+int aslp_nnet_output_dim(aslp_nnet_t n, int* dim) { CAPI_BEGIN *dim = N(n)->OutputDim(); CAPI_END }
+int aslp_nnet_num_components(aslp_nnet_t n, int* count) { CAPI_BEGIN *count = N(n)->NumComponents(); CAPI_END }
+int aslp_nnet_num_params(aslp_nnet_t n, int* count) { CAPI_BEGIN *count = N(n)->NumParams(); CAPI_END }
+int aslp_nnet_info(aslp_nnet_t n, char* buf, size_t bytes) { CAPI_BEGIN CopyOut(N(n)->Info(), buf, bytes); CAPI_END }
+int aslp_nnet_get_params(aslp_nnet_t n, float* host_out, int count) {
+  CAPI_BEGIN
+  Vector<BaseFloat> p;
+  N(n)->GetParams(&p);
+  if (p.Dim() != count) KALDI_ERR << "GetParams: the net has " << p.Dim() << " parameters, buffer holds " << count;
+  memcpy(host_out, p.Data(), sizeof(float) * count);
+  CAPI_END
+}
+int aslp_nnet_set_train_options(aslp_nnet_t n, float lr, float mmt, float l2, float l1) {
+  CAPI_BEGIN
+  NnetTrainOptions o; o.learn_rate = lr; o.momentum = mmt; o.l2_penalty = l2; o.l1_penalty = l1;
+  N(n)->SetTrainOptions(o);
+  CAPI_END
+}
+int aslp_nnet_set_seq_lengths(aslp_nnet_t n, const int* lengths, int count) { CAPI_BEGIN N(n)->SetSeqLengths(std::vector<int32>(lengths, lengths + count)); CAPI_END }
+int aslp_nnet_reset_streams(aslp_nnet_t n, const int* flags, int count) { CAPI_BEGIN N(n)->ResetLstmStreams(std::vector<int32>(flags, flags + count)); CAPI_END }
+int aslp_nnet_set_chunk_size(aslp_nnet_t n, int chunk_size) { CAPI_BEGIN N(n)->SetChunkSize(chunk_size); CAPI_END }
+
+int aslp_nnet_propagate(aslp_nnet_t n, const float* host_in, int rows, int cols, float* host_out) {
+  CAPI_BEGIN
+  g_in.Resize(rows, cols, kUndefined);
+  g_in.CopyFromHost(host_in, cols);
+  N(n)->Propagate(g_in, &g_out);
+  if (host_out != nullptr) g_out.CopyToHost(host_out, g_out.NumCols());
+  CuSync();
+  CAPI_END
+}
+int aslp_nnet_feedforward(aslp_nnet_t n, const float* host_in, int rows, int cols, float* host_out) {
+  CAPI_BEGIN
+  g_in.Resize(rows, cols, kUndefined);
+  g_in.CopyFromHost(host_in, cols);
+  N(n)->Feedforward(g_in, &g_out);
+  if (host_out != nullptr) g_out.CopyToHost(host_out, g_out.NumCols());
+  CuSync();
+  CAPI_END
+}
+int aslp_nnet_backpropagate(aslp_nnet_t n, const float* host_out_diff, int rows, int cols, float* host_in_diff) {
+  CAPI_BEGIN
+  g_diff.Resize(rows, cols, kUndefined);
+  g_diff.CopyFromHost(host_out_diff, cols);
+  N(n)->Backpropagate(g_diff, &g_indiff);
+  if (host_in_diff != nullptr) g_indiff.CopyToHost(host_in_diff, g_indiff.NumCols());
+  CuSync();
+  CAPI_END
+}
+static void CopyBuf(const CuMatrix& m, float* host_out, int rows, int cols) {
+  if (m.NumRows() != rows || m.NumCols() != cols) KALDI_ERR << "buffer is " << m.NumRows() << " x " << m.NumCols() << ", asked for " << rows << " x " << cols;
+  m.CopyToHost(host_out, cols);
+  CuSync();
+}
+int aslp_nnet_component_output(aslp_nnet_t n, int c, float* host_out, int rows, int cols) { CAPI_BEGIN CopyBuf(N(n)->PropagateBuffer().at(c), host_out, rows, cols); CAPI_END }
+int aslp_nnet_component_out_diff(aslp_nnet_t n, int c, float* host_out, int rows, int cols) { CAPI_BEGIN CopyBuf(N(n)->BackpropagateBuffer().at(c), host_out, rows, cols); CAPI_END }
+
+int aslp_xent_create(aslp_xent_t* out) { CAPI_BEGIN *out = new Xent(); CAPI_END }
+int aslp_xent_destroy(aslp_xent_t x) { CAPI_BEGIN delete static_cast<Xent*>(x); CAPI_END }
+int aslp_xent_report(aslp_xent_t x, char* buf, size_t bytes, double stats5[5]) {
+  CAPI_BEGIN
+  Xent* xe = static_cast<Xent*>(x);
+  CopyOut(xe->Report(), buf, bytes);
+  if (stats5 != nullptr) { stats5[0] = xe->AvgLoss(); stats5[1] = xe->Frames(); stats5[2] = xe->Correct(); stats5[3] = 0; stats5[4] = 0; }
+  CAPI_END
+}
+int aslp_warpctc_create(aslp_warpctc_t* out) { CAPI_BEGIN *out = new WarpCtc(); CAPI_END }
+int aslp_warpctc_destroy(aslp_warpctc_t c) { CAPI_BEGIN delete static_cast<WarpCtc*>(c); CAPI_END }
+int aslp_warpctc_report(aslp_warpctc_t c, char* buf, size_t bytes) { CAPI_BEGIN CopyOut(static_cast<WarpCtc*>(c)->Report(), buf, bytes); CAPI_END }
+
+static const CuMatrixBase& StageFeatures(const float* features, int on_device, int rows, int cols, CuSubMatrix* view) {
+  if (on_device) { *view = CuSubMatrix(const_cast<float*>(features), rows, cols, (cols + 3) / 4 * 4); return *view; }
+  g_in.Resize(rows, cols, kUndefined);
+  g_in.CopyFromHost(features, cols);
+  return g_in;
+}
+
+int aslp_train_step_xent(aslp_nnet_t n, aslp_xent_t x, const float* features, int on_device, int rows, int cols, const int* targets,
+                         const float* frame_mask) {
+  CAPI_BEGIN
+  CuSubMatrix view(nullptr, 0, 0, 0);
+  const CuMatrixBase& in = StageFeatures(features, on_device, rows, cols, &view);
+  N(n)->Propagate(in, &g_out);
+  Posterior post(rows);
+  Vector<BaseFloat> fw(rows);
+  for (int r = 0; r < rows; ++r) { post[r].push_back(std::make_pair(targets[r], 1.0f)); fw(r) = frame_mask ? frame_mask[r] : 1.0f; }
+  static_cast<Xent*>(x)->Eval(fw, g_out, post, &g_loss_diff);
+  N(n)->Backpropagate(g_loss_diff, NULL);
+  CAPI_END
+}
+
+int aslp_train_step_ctc(aslp_nnet_t n, aslp_warpctc_t c, const float* features, int on_device, int rows, int cols, const int* frame_num_utt,
+                        int nseq, const int* flat_labels, const int* label_lengths, float norm_learn_rate, int with_error_rate, float* costs_out) {
+  CAPI_BEGIN
+  Nnet* net = N(n);
+  WarpCtc* ctc = static_cast<WarpCtc*>(c);
+  std::vector<int32> lens(frame_num_utt, frame_num_utt + nseq);
+  std::vector<std::vector<int32>> labels(nseq);
+  std::vector<std::string> keys(nseq);
+  int off = 0, valid_frames = 0;
+  for (int s = 0; s < nseq; ++s) {
+    labels[s].assign(flat_labels + off, flat_labels + off + label_lengths[s]);
+    off += label_lengths[s];
+    keys[s] = "utt" + ToString(s);
+    valid_frames += lens[s];
+  }
+  net->SetSeqLengths(lens);                                           // aslp-nnet-train-warp-ctc-streams.cc:175
+  if (norm_learn_rate > 0.0f) {                                       // :177-178 learn_rate = norm_lr / valid frames
+    NnetTrainOptions o = net->GetTrainOptions();
+    o.learn_rate = norm_learn_rate / valid_frames;
+    net->SetTrainOptions(o);
+  }
+  CuSubMatrix view(nullptr, 0, 0, 0);
+  const CuMatrixBase& in = StageFeatures(features, on_device, rows, cols, &view);
+  net->Propagate(in, &g_out);                                         // :182
+  ctc->Eval(keys, lens, g_out, labels, &g_loss_diff);                 // :187
+  if (with_error_rate) ctc->ErrorRate(lens, g_out, labels);           // :190
+  net->Backpropagate(g_loss_diff, NULL);                              // :194
+  if (costs_out != nullptr) memcpy(costs_out, ctc->LastCosts().data(), sizeof(float) * nseq);
+  CAPI_END
+}
+
+int aslp_nnet_upload(const float* host, int rows, int cols, float** device_out, int* stride_out) {
+  CAPI_BEGIN
+  const int stride = (cols + 3) / 4 * 4;
+  void* p = nullptr;
+  CuStream();
+  ASLP_OK(aslp_malloc(&p, sizeof(float) * (static_cast<size_t>(rows) * stride + 4)));
+  ASLP_OK(aslp_memset(CuStream(), p, 0, sizeof(float) * (static_cast<size_t>(rows) * stride + 4)));
+  ASLP_OK(aslp_memcpy2d_h2d(CuStream(), p, sizeof(float) * stride, host, sizeof(float) * cols, sizeof(float) * cols, rows));
+  CuSync();
+  *device_out = static_cast<float*>(p);
+  if (stride_out) *stride_out = stride;
+  CAPI_END
+}
+int aslp_nnet_free_device(float* p) { CAPI_BEGIN ASLP_OK(aslp_free(p)); CAPI_END }
+
+int aslp_worker_create(const char* type, const char nccl_id[128], int nranks, int rank, float bmuf_momentum, float bmuf_learn_rate,
+                       const char* sod_solver, aslp_worker_t* out) {
+  CAPI_BEGIN
+  const std::string t(type);
+  IWorker* w = nullptr;
+  if (t == "bsp") w = new BspWorker(nccl_id, nranks, rank);
+  else if (t == "bmuf") w = new BmufWorker(nccl_id, nranks, rank, bmuf_momentum, bmuf_learn_rate);
+  else if (t == "sod") { OptimizerOption o; if (sod_solver && *sod_solver) o.solver = sod_solver; w = new SodWorker(nccl_id, nranks, rank, o); }
+  else KALDI_ERR << "Unsupported worker type: " << t << " (bsp | bmuf | sod; the async easgd/asgd/masgd servers are not built, DESIGN.md)";
+  *out = w;
+  CAPI_END
+}
+int aslp_worker_init_param(aslp_worker_t w, aslp_nnet_t n) {
+  CAPI_BEGIN
+  std::vector<std::pair<BaseFloat*, int>> params;
+  N(n)->GetGpuParams(&params);
+  static_cast<IWorker*>(w)->InitParam(params);
+  CAPI_END
+}
+int aslp_worker_synchronize(aslp_worker_t w, int num_frames, int* keep_going) { CAPI_BEGIN const bool k = static_cast<IWorker*>(w)->Synchronize(num_frames); if (keep_going) *keep_going = k ? 1 : 0; CAPI_END }
+int aslp_worker_stop(aslp_worker_t w) { CAPI_BEGIN static_cast<IWorker*>(w)->Stop(); CAPI_END }
+int aslp_worker_reduce_acc_stat(aslp_worker_t w, aslp_nnet_t n) {
+  CAPI_BEGIN
+  std::vector<double*> acc;
+  std::vector<std::pair<double*, int>> data;
+  N(n)->GetAccStats(&acc, &data);
+  static_cast<IWorker*>(w)->ReduceAccStat(acc, data);
+  CAPI_END
+}
+int aslp_worker_destroy(aslp_worker_t w) { CAPI_BEGIN delete static_cast<IWorker*>(w); CAPI_END }
+
+}  // extern "C"

@@ -1,0 +1,369 @@
+#include "matrix.h"
+#include <cstring>
+
+namespace kaldi {
+
+static aslp_stream_t g_stream = nullptr;
+static bool g_stream_made = false;
+
+void CuSelectDevice(int dev) {
+  if (g_stream_made) KALDI_ERR << "CuSelectDevice must be called before the first device operation";
+  ASLP_OK(aslp_set_device(dev));
+}
+aslp_stream_t CuStream() {
+  if (!g_stream_made) {
+    int n = 0;
+    if (aslp_device_count(&n) != 0 || n <= 0)
+      KALDI_ERR << "No CUDA device: this build has no CPU path (the reference's --use-gpu=no branch is the oracle, not the product)";
+    ASLP_OK(aslp_stream_create(&g_stream));
+    g_stream_made = true;
+  }
+  return g_stream;
+}
+void CuSync() { ASLP_OK(aslp_stream_sync(CuStream())); }
+
+// ------------------------------------------------------------------ host containers
+template <typename Real> static const char* MatTok() { return sizeof(Real) == 4 ? "FM" : "DM"; }
+template <typename Real> static const char* VecTok() { return sizeof(Real) == 4 ? "FV" : "DV"; }
+
+template <typename Real>
+void Vector<Real>::Write(std::ostream& os, bool binary) const {
+  if (binary) {
+    WriteToken(os, binary, VecTok<Real>());
+    WriteBasicType(os, binary, static_cast<int32>(Dim()));
+    os.write(reinterpret_cast<const char*>(d_.data()), sizeof(Real) * d_.size());
+  } else {
+    os << " [ ";
+    for (Real v : d_) os << v << " ";
+    os << "]\n";
+  }
+  if (!os.good()) KALDI_ERR << "Failed to write vector to stream";
+}
+
+template <typename Real>
+void Vector<Real>::Read(std::istream& is, bool binary) {
+  if (binary) {
+    std::string tok;
+    ReadToken(is, binary, &tok);
+    int32 dim = 0;
+    ReadBasicType(is, binary, &dim);
+    if (dim < 0) KALDI_ERR << "Vector::Read, negative dimension";
+    d_.resize(dim);
+    if (tok == VecTok<Real>()) {
+      is.read(reinterpret_cast<char*>(d_.data()), sizeof(Real) * dim);
+    } else if (tok == "FV") {
+      std::vector<float> tmp(dim); is.read(reinterpret_cast<char*>(tmp.data()), 4 * dim);
+      for (int32 i = 0; i < dim; ++i) d_[i] = static_cast<Real>(tmp[i]);
+    } else if (tok == "DV") {
+      std::vector<double> tmp(dim); is.read(reinterpret_cast<char*>(tmp.data()), 8 * dim);
+      for (int32 i = 0; i < dim; ++i) d_[i] = static_cast<Real>(tmp[i]);
+    } else {
+      KALDI_ERR << "Vector::Read, expected token FV or DV, got " << tok;
+    }
+  } else {
+    std::string s;
+    is >> s;
+    if (s != "[") KALDI_ERR << "Vector::Read, expected \"[\" but got " << s;
+    d_.clear();
+    while (true) {
+      is >> std::ws;
+      const int c = is.peek();
+      if (c == ']') { is.get(); break; }
+      if (c == EOF) KALDI_ERR << "Vector::Read, EOF while reading vector";
+      std::string item;
+      is >> item;
+      d_.push_back(static_cast<Real>(strtod(item.c_str(), nullptr)));   // handles nan / inf spellings of the stream writer
+    }
+    if (is.peek() == '\r') is.get();
+    if (is.peek() == '\n') is.get();
+  }
+  if (is.fail()) KALDI_ERR << "Failed to read vector from stream";
+}
+
+template <typename Real>
+void Matrix<Real>::Write(std::ostream& os, bool binary) const {
+  if (binary) {
+    WriteToken(os, binary, MatTok<Real>());
+    WriteBasicType(os, binary, r_);
+    WriteBasicType(os, binary, c_);
+    os.write(reinterpret_cast<const char*>(d_.data()), sizeof(Real) * d_.size());
+  } else if (c_ == 0) {
+    os << " [ ]\n";
+  } else {
+    os << " [";
+    for (int32 i = 0; i < r_; ++i) {
+      os << "\n  ";
+      for (int32 j = 0; j < c_; ++j) os << (*this)(i, j) << " ";
+    }
+    os << "]\n";
+  }
+  if (!os.good()) KALDI_ERR << "Failed to write matrix to stream";
+}
+
+template <typename Real>
+void Matrix<Real>::Read(std::istream& is, bool binary) {
+  if (binary) {
+    std::string tok;
+    ReadToken(is, binary, &tok);
+    int32 rows = 0, cols = 0;
+    ReadBasicType(is, binary, &rows);
+    ReadBasicType(is, binary, &cols);
+    if (rows < 0 || cols < 0) KALDI_ERR << "Matrix::Read, negative dimension";
+    Resize(rows, cols, kUndefined);
+    const size_t n = static_cast<size_t>(rows) * cols;
+    if (tok == MatTok<Real>()) {
+      is.read(reinterpret_cast<char*>(d_.data()), sizeof(Real) * n);
+    } else if (tok == "FM") {
+      std::vector<float> tmp(n); is.read(reinterpret_cast<char*>(tmp.data()), 4 * n);
+      for (size_t i = 0; i < n; ++i) d_[i] = static_cast<Real>(tmp[i]);
+    } else if (tok == "DM") {
+      std::vector<double> tmp(n); is.read(reinterpret_cast<char*>(tmp.data()), 8 * n);
+      for (size_t i = 0; i < n; ++i) d_[i] = static_cast<Real>(tmp[i]);
+    } else {
+      KALDI_ERR << "Matrix::Read, expected token FM or DM, got " << tok << " (compressed matrices are not on this path)";
+    }
+  } else {
+    std::string s;
+    is >> s;
+    if (s != "[") KALDI_ERR << "Matrix::Read, expected \"[\" but got " << s;
+    std::vector<std::vector<Real>> rows;
+    std::vector<Real> cur;
+    while (true) {
+      const int c = is.peek();
+      if (c == EOF) KALDI_ERR << "Matrix::Read, EOF while reading matrix";
+      if (c == ']') { is.get(); if (!cur.empty()) rows.push_back(cur); break; }
+      if (c == '\n' || c == ';') { is.get(); if (!cur.empty()) { rows.push_back(cur); cur.clear(); } continue; }
+      if (isspace(c)) { is.get(); continue; }
+      std::string item;
+      is >> item;
+      if (!item.empty() && item.back() == ']') {          // "1.0]" glued
+        item.pop_back();
+        if (!item.empty()) cur.push_back(static_cast<Real>(strtod(item.c_str(), nullptr)));
+        if (!cur.empty()) rows.push_back(cur);
+        break;
+      }
+      cur.push_back(static_cast<Real>(strtod(item.c_str(), nullptr)));
+    }
+    if (is.peek() == '\r') is.get();
+    if (is.peek() == '\n') is.get();
+    const int32 nr = static_cast<int32>(rows.size()), nc = nr ? static_cast<int32>(rows[0].size()) : 0;
+    Resize(nr, nc, kUndefined);
+    for (int32 i = 0; i < nr; ++i) {
+      if (static_cast<int32>(rows[i].size()) != nc) KALDI_ERR << "Matrix::Read, rows of different length";
+      for (int32 j = 0; j < nc; ++j) (*this)(i, j) = rows[i][j];
+    }
+  }
+  if (is.fail()) KALDI_ERR << "Failed to read matrix from stream";
+}
+
+template class Vector<float>;
+template class Vector<double>;
+template class Matrix<float>;
+template class Matrix<double>;
+
+// ------------------------------------------------------------------ device matrix
+CuSubMatrix CuMatrixBase::RowRange(int32 r0, int32 n) const {
+  KALDI_ASSERT(r0 >= 0 && n >= 0 && r0 + n <= rows_);
+  return CuSubMatrix(data_ + static_cast<size_t>(r0) * stride_, n, cols_, stride_);
+}
+CuSubMatrix CuMatrixBase::ColRange(int32 c0, int32 n) const {
+  KALDI_ASSERT(c0 >= 0 && n >= 0 && c0 + n <= cols_);
+  return CuSubMatrix(data_ + c0, rows_, n, stride_);
+}
+CuSubMatrix CuMatrixBase::Range(int32 r0, int32 nr, int32 c0, int32 nc) const {
+  KALDI_ASSERT(r0 >= 0 && nr >= 0 && r0 + nr <= rows_ && c0 >= 0 && nc >= 0 && c0 + nc <= cols_);
+  return CuSubMatrix(data_ + static_cast<size_t>(r0) * stride_ + c0, nr, nc, stride_);
+}
+void CuMatrixBase::SetZero() {
+  if (rows_ == 0 || cols_ == 0) return;
+  if (cols_ == stride_) { ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(float) * static_cast<size_t>(rows_) * stride_)); return; }
+  ASLP_OK(aslp_memset2d(CuStream(), data_, sizeof(float) * stride_, 0, sizeof(float) * cols_, rows_));
+}
+void CuMatrixBase::CopyFromMat(const CuMatrixBase& src) {
+  KALDI_ASSERT(src.NumRows() == rows_ && src.NumCols() == cols_);
+  ASLP_OK(aslp_memcpy2d_d2d(CuStream(), data_, sizeof(float) * stride_, src.Data(), sizeof(float) * src.Stride(), sizeof(float) * cols_, rows_));
+}
+void CuMatrixBase::CopyFromMat(const Matrix<float>& src) {
+  KALDI_ASSERT(src.NumRows() == rows_ && src.NumCols() == cols_);
+  CopyFromHost(src.Data(), src.Stride());
+  CuSync();   // the host matrix may be a temporary
+}
+void CuMatrixBase::CopyFromHost(const float* src, int32 src_stride) {
+  ASLP_OK(aslp_memcpy2d_h2d(CuStream(), data_, sizeof(float) * stride_, src, sizeof(float) * src_stride, sizeof(float) * cols_, rows_));
+}
+void CuMatrixBase::CopyToMat(Matrix<float>* dst) const {
+  if (dst->NumRows() != rows_ || dst->NumCols() != cols_) dst->Resize(rows_, cols_, kUndefined);
+  CopyToHost(dst->Data(), dst->Stride());
+  CuSync();
+}
+void CuMatrixBase::CopyToHost(float* dst, int32 dst_stride) const {
+  ASLP_OK(aslp_memcpy2d_d2h(CuStream(), dst, sizeof(float) * dst_stride, data_, sizeof(float) * stride_, sizeof(float) * cols_, rows_));
+}
+void CuMatrixBase::AddMat(float alpha, const CuMatrixBase& A) {
+  KALDI_ASSERT(A.NumRows() == rows_ && A.NumCols() == cols_);
+  ASLP_OK(aslp_axpby(CuStream(), data_, stride_, A.Data(), A.Stride(), rows_, cols_, alpha, 1.0f));
+}
+void CuMatrixBase::Scale(float alpha) {
+  ASLP_OK(aslp_axpby(CuStream(), data_, stride_, data_, stride_, rows_, cols_, alpha, 0.0f));
+}
+double CuMatrixBase::Sum() const {
+  static double* dev2 = nullptr;
+  if (dev2 == nullptr) ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&dev2), 2 * sizeof(double)));
+  ASLP_OK(aslp_sum_check(CuStream(), data_, stride_, rows_, cols_, dev2));
+  double h[2];
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), h, dev2, sizeof(h)));
+  CuSync();
+  return h[1] > 0 ? std::nan("") : h[0];
+}
+
+CuMatrix::~CuMatrix() { if (data_ != nullptr) aslp_free(data_); }
+void CuMatrix::Resize(int32 rows, int32 cols, MatrixResizeType t) {
+  KALDI_ASSERT(rows >= 0 && cols >= 0);
+  const int32 stride = (cols + 3) / 4 * 4;
+  const size_t need = static_cast<size_t>(rows) * stride;
+  if (need > cap_) {
+    KALDI_ASSERT(t != kCopyData);
+    CuStream();                                   // make sure the device is up before the first allocation
+    if (data_ != nullptr) { CuSync(); aslp_free(data_); data_ = nullptr; }
+    void* p = nullptr;
+    ASLP_OK(aslp_malloc(&p, sizeof(float) * (need + 4)));
+    data_ = static_cast<float*>(p);
+    cap_ = need;
+  }
+  rows_ = rows; cols_ = cols; stride_ = stride;
+  if (t == kSetZero && need > 0) ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(float) * need));
+}
+void CuMatrix::Swap(CuMatrix* o) {
+  std::swap(data_, o->data_); std::swap(rows_, o->rows_); std::swap(cols_, o->cols_); std::swap(stride_, o->stride_); std::swap(cap_, o->cap_);
+}
+void CuMatrix::Read(std::istream& is, bool binary) {
+  Matrix<float> tmp;
+  tmp.Read(is, binary);
+  *this = tmp;
+}
+void CuMatrix::Write(std::ostream& os, bool binary) const {
+  Matrix<float> tmp;
+  CopyToMat(&tmp);
+  tmp.Write(os, binary);
+}
+
+// ------------------------------------------------------------------ device vectors
+template <typename Real> CuVectorT<Real>::~CuVectorT() { if (data_ != nullptr) aslp_free(data_); }
+template <typename Real>
+void CuVectorT<Real>::Resize(int32 dim, MatrixResizeType t) {
+  if (static_cast<size_t>(dim) > cap_) {
+    CuStream();
+    if (data_ != nullptr) { CuSync(); aslp_free(data_); data_ = nullptr; }
+    void* p = nullptr;
+    ASLP_OK(aslp_malloc(&p, sizeof(Real) * (dim + 4)));
+    data_ = static_cast<Real*>(p);
+    cap_ = dim;
+    ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(Real) * (dim + 4)));   // pad lanes read by 128-bit loads stay finite
+  }
+  dim_ = dim;
+  if (t == kSetZero) SetZero();
+}
+template <typename Real> void CuVectorT<Real>::SetZero() { if (dim_ > 0) ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(Real) * dim_)); }
+template <typename Real> void CuVectorT<Real>::Set(Real v) {
+  Vector<Real> h(dim_);
+  for (int32 i = 0; i < dim_; ++i) h(i) = v;
+  CopyFromVec(h);
+}
+template <typename Real> void CuVectorT<Real>::CopyToVec(Vector<Real>* dst) const {
+  if (dst->Dim() != dim_) dst->Resize(dim_, kUndefined);
+  if (dim_ > 0) ASLP_OK(aslp_memcpy_d2h(CuStream(), dst->Data(), data_, sizeof(Real) * dim_));
+  CuSync();
+}
+template <typename Real> void CuVectorT<Real>::CopyFromVec(const Vector<Real>& src) {
+  KALDI_ASSERT(src.Dim() == dim_);
+  if (dim_ > 0) ASLP_OK(aslp_memcpy_h2d(CuStream(), data_, src.Data(), sizeof(Real) * dim_));
+  CuSync();
+}
+template <typename Real> CuVectorT<Real>& CuVectorT<Real>::operator=(const CuVectorT& o) {
+  if (this == &o) return *this;
+  Resize(o.dim_, kUndefined);
+  if (dim_ > 0) ASLP_OK(aslp_memcpy_d2d(CuStream(), data_, o.data_, sizeof(Real) * dim_));
+  return *this;
+}
+template <typename Real> CuVectorT<Real>& CuVectorT<Real>::operator=(const Vector<Real>& o) {
+  Resize(o.Dim(), kUndefined);
+  CopyFromVec(o);
+  return *this;
+}
+template <typename Real> void CuVectorT<Real>::Read(std::istream& is, bool binary) { Vector<Real> t; t.Read(is, binary); *this = t; }
+template <typename Real> void CuVectorT<Real>::Write(std::ostream& os, bool binary) const { Vector<Real> t; CopyToVec(&t); t.Write(os, binary); }
+template class CuVectorT<float>;
+template class CuVectorT<double>;
+
+CuArrayInt::~CuArrayInt() { if (data_ != nullptr) aslp_free(data_); }
+CuArrayInt& CuArrayInt::operator=(const std::vector<int32>& v) {
+  std::vector<int32> copy(v);   // v may alias host_
+  if (copy.size() > cap_) {
+    CuStream();
+    if (data_ != nullptr) { CuSync(); aslp_free(data_); data_ = nullptr; }
+    void* p = nullptr;
+    ASLP_OK(aslp_malloc(&p, sizeof(int32) * (copy.size() + 4)));
+    data_ = static_cast<int32*>(p);
+    cap_ = copy.size();
+  }
+  host_.swap(copy);
+  dim_ = static_cast<int32>(host_.size());
+  if (dim_ > 0) { ASLP_OK(aslp_memcpy_h2d(CuStream(), data_, host_.data(), sizeof(int32) * dim_)); CuSync(); }
+  return *this;
+}
+
+// MomentStatistics (src/aslp-nnet/nnet-utils.h): mean / stddev / skewness / kurtosis summary used by Info()
+static std::string Moments(const std::vector<float>& v) {
+  if (v.empty()) return " ( empty )";
+  double mean = 0;
+  for (float x : v) mean += x;
+  mean /= v.size();
+  double m2 = 0, m3 = 0, m4 = 0, mn = v[0], mx = v[0];
+  for (float x : v) { const double d = x - mean; m2 += d * d; m3 += d * d * d; m4 += d * d * d * d; if (x < mn) mn = x; if (x > mx) mx = x; }
+  m2 /= v.size(); m3 /= v.size(); m4 /= v.size();
+  std::ostringstream os;
+  os << " ( min " << mn << ", max " << mx << ", mean " << mean << ", variance " << m2
+     << ", skewness " << (m2 > 0 ? m3 / pow(m2, 1.5) : 0.0) << ", kurtosis " << (m2 > 0 ? m4 / (m2 * m2) - 3.0 : 0.0) << " ) ";
+  return os.str();
+}
+std::string MomentStatistics(const CuMatrixBase& m) {
+  Matrix<float> h;
+  m.CopyToMat(&h);
+  return Moments(std::vector<float>(h.Data(), h.Data() + static_cast<size_t>(h.NumRows()) * h.NumCols()));
+}
+std::string MomentStatistics(const CuVector& v) {
+  Vector<float> h;
+  v.CopyToVec(&h);
+  return Moments(std::vector<float>(h.Data(), h.Data() + h.Dim()));
+}
+
+}  // namespace kaldi
+
+// ------------------------------------------------------------------ shared workspace, GEMM precision
+#include "cu-workspace.h"
+#include <cstring>
+namespace kaldi {
+static void* g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+void* CuWorkspace(size_t bytes) {
+  if (bytes > g_ws_bytes) {
+    CuStream();
+    if (g_ws != nullptr) { CuSync(); aslp_free(g_ws); g_ws = nullptr; }
+    const size_t cap = bytes + bytes / 4 + (1u << 20);
+    ASLP_OK(aslp_malloc(&g_ws, cap));
+    g_ws_bytes = cap;
+  }
+  return g_ws;
+}
+static int g_gemm_precision = -1;
+int GemmPrecision() {
+  if (g_gemm_precision < 0) {
+    const char* e = getenv("ASLP_GEMM_PRECISION");
+    g_gemm_precision = ASLP_GEMM_3XTF32;
+    if (e != nullptr && strcmp(e, "tf32") == 0) g_gemm_precision = ASLP_GEMM_TF32;
+    if (e != nullptr && strcmp(e, "fp32") == 0) g_gemm_precision = ASLP_GEMM_FP32;
+  }
+  return g_gemm_precision;
+}
+void SetGemmPrecision(int p) { g_gemm_precision = p; }
+}  // namespace kaldi

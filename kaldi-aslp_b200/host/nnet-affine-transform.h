@@ -1,0 +1,148 @@
+// nnet-affine-transform.h -- AffineTransform and LinearTransform over the tcgen05 GEMM.
+// Reference: src/aslp-nnet/nnet-affine-transform.h:186-245, nnet-linear-transform.h:126-158.
+//   fwd   : out = in W^T + bias            one GEMM, bias fused in the epilogue
+//   bwd   : in_diff = out_diff W           one GEMM
+//   update: W_corr = mmt W_corr + diff^T in (momentum as the GEMM's beta), bias_corr column sum,
+//           optional L2 / L1 / max-norm, W -= lr W_corr
+#ifndef ASLP_HOST_NNET_AFFINE_TRANSFORM_H_
+#define ASLP_HOST_NNET_AFFINE_TRANSFORM_H_
+#include "cu-workspace.h"
+#include "nnet-component.h"
+
+namespace kaldi {
+namespace aslp_nnet {
+
+class AffineTransform : public UpdatableComponent {
+ public:
+  AffineTransform(int32 dim_in, int32 dim_out, bool has_bias = true)
+      : UpdatableComponent(dim_in, dim_out), has_bias_(has_bias), linearity_(dim_out, dim_in), bias_(has_bias ? dim_out : 0),
+        linearity_corr_(dim_out, dim_in), bias_corr_(has_bias ? dim_out : 0), learn_rate_coef_(1.0f), bias_learn_rate_coef_(1.0f), max_norm_(0.0f) {}
+  Component* Copy() const { return new AffineTransform(*this); }
+  ComponentType GetType() const { return has_bias_ ? kAffineTransform : kLinearTransform; }
+
+  void InitData(std::istream& is) {
+    float bias_mean = -2.0f, bias_range = 2.0f, param_stddev = 0.1f, norm_init_scale = 1.0f;
+    bool gauss_init = true;
+    std::string token;
+    while (!is.eof()) {      // same keys as nnet-affine-transform.h:70-84 (<NormInit> switches to Glorot-uniform)
+      ReadToken(is, false, &token);
+      if (token == "<NormInit>") { ReadBasicType(is, false, &norm_init_scale); gauss_init = false; }
+      else if (token == "<ParamStddev>") ReadBasicType(is, false, &param_stddev);
+      else if (token == "<BiasMean>") ReadBasicType(is, false, &bias_mean);
+      else if (token == "<BiasRange>") ReadBasicType(is, false, &bias_range);
+      else if (token == "<LearnRateCoef>") ReadBasicType(is, false, &learn_rate_coef_);
+      else if (token == "<BiasLearnRateCoef>") ReadBasicType(is, false, &bias_learn_rate_coef_);
+      else if (token == "<MaxNorm>") ReadBasicType(is, false, &max_norm_);
+      else KALDI_ERR << "Unknown token " << token << ", a typo in config? (ParamStddev|BiasMean|BiasRange|LearnRateCoef|BiasLearnRateCoef)";
+      is >> std::ws;
+    }
+    if (!gauss_init) {
+      const float scale = norm_init_scale * sqrt(6.0 / (output_dim_ + input_dim_));
+      InitMatParam(&linearity_, scale);
+      if (has_bias_) InitVecParam(&bias_, scale);
+    } else {
+      Matrix<BaseFloat> mat(output_dim_, input_dim_);
+      for (int32 r = 0; r < output_dim_; r++)
+        for (int32 c = 0; c < input_dim_; c++) mat(r, c) = param_stddev * RandGauss();
+      linearity_ = mat;
+      if (has_bias_) {
+        Vector<BaseFloat> vec(output_dim_);
+        for (int32 i = 0; i < output_dim_; i++) vec(i) = bias_mean + (RandUniform() - 0.5) * bias_range;
+        bias_ = vec;
+      }
+    }
+  }
+
+  void ReadData(std::istream& is, bool binary) {
+    if ('<' == Peek(is, binary)) {
+      ExpectToken(is, binary, "<LearnRateCoef>"); ReadBasicType(is, binary, &learn_rate_coef_);
+      if (has_bias_) { ExpectToken(is, binary, "<BiasLearnRateCoef>"); ReadBasicType(is, binary, &bias_learn_rate_coef_); }
+    }
+    if (has_bias_ && '<' == Peek(is, binary)) { ExpectToken(is, binary, "<MaxNorm>"); ReadBasicType(is, binary, &max_norm_); }
+    if (has_bias_ && '<' == Peek(is, binary)) { float tmp; ExpectToken(is, binary, "<ClipGradient>"); ReadBasicType(is, binary, &tmp); }
+    linearity_.Read(is, binary);
+    if (has_bias_) bias_.Read(is, binary);
+    KALDI_ASSERT(linearity_.NumRows() == output_dim_ && linearity_.NumCols() == input_dim_);
+    KALDI_ASSERT(!has_bias_ || bias_.Dim() == output_dim_);
+    linearity_corr_.Resize(output_dim_, input_dim_, kSetZero);
+    if (has_bias_) bias_corr_.Resize(output_dim_, kSetZero);
+  }
+  void WriteData(std::ostream& os, bool binary) const {
+    WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
+    if (has_bias_) {
+      WriteToken(os, binary, "<BiasLearnRateCoef>"); WriteBasicType(os, binary, bias_learn_rate_coef_);
+      WriteToken(os, binary, "<MaxNorm>"); WriteBasicType(os, binary, max_norm_);
+    }
+    linearity_.Write(os, binary);
+    if (has_bias_) bias_.Write(os, binary);
+  }
+
+  int32 NumParams() const { return linearity_.NumRows() * linearity_.NumCols() + bias_.Dim(); }
+  void GetParams(Vector<BaseFloat>* wei_copy) const {
+    wei_copy->Resize(NumParams());
+    CopyRowsToVec(linearity_, wei_copy->Data());
+    if (has_bias_) { Vector<float> b; bias_.CopyToVec(&b); for (int32 i = 0; i < b.Dim(); ++i) (*wei_copy)(linearity_.NumRows() * linearity_.NumCols() + i) = b(i); }
+  }
+  void GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* params) {
+    params->clear();
+    params->push_back(std::make_pair(linearity_.Data(), linearity_.NumRows() * linearity_.Stride()));
+    if (has_bias_) params->push_back(std::make_pair(bias_.Data(), bias_.Dim()));
+  }
+  std::string Info() const { return std::string("\n  linearity") + MomentStatistics(linearity_) + (has_bias_ ? "\n  bias" + MomentStatistics(bias_) : ""); }
+  std::string InfoGradient() const {
+    return std::string("\n  linearity_grad") + MomentStatistics(linearity_corr_) + ", lr-coef " + ToString(learn_rate_coef_) + ", max-norm " + ToString(max_norm_) +
+           (has_bias_ ? "\n  bias_grad" + MomentStatistics(bias_corr_) + ", lr-coef " + ToString(bias_learn_rate_coef_) : "");
+  }
+
+  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+    ASLP_OK(aslp_gemm(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
+                      0.0f, out->Data(), out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+  }
+  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+    ASLP_OK(aslp_gemm(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
+                      linearity_.Stride(), 0.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+  }
+  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+    aslp_stream_t st = CuStream();
+    const BaseFloat lr = opts_.learn_rate * learn_rate_coef_, lr_bias = opts_.learn_rate * bias_learn_rate_coef_;
+    const BaseFloat mmt = opts_.momentum, l2 = opts_.l2_penalty, l1 = opts_.l1_penalty;
+    const int32 num_frames = input.NumRows();
+    const size_t wsb = aslp_gemm_workspace_bytes(output_dim_, input_dim_, num_frames);
+    ASLP_OK(aslp_gemm(st, 1, 0, output_dim_, input_dim_, num_frames, 1.0f, diff.Data(), diff.Stride(), input.Data(), input.Stride(), mmt,
+                      linearity_corr_.Data(), linearity_corr_.Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
+    if (has_bias_) ASLP_OK(aslp_col_sum(st, bias_corr_.Data(), diff.Data(), diff.Stride(), num_frames, output_dim_, 1.0f, mmt, 0.0f));
+    // (LinearTransform regularises with the bare learn rate, nnet-linear-transform.h:140-155)
+    const BaseFloat lr_reg = has_bias_ ? lr : opts_.learn_rate;
+    if (l2 != 0.0) linearity_.Scale(1.0f - lr_reg * l2 * num_frames);                // W += (-lr*l2*N) * W
+    if (l1 != 0.0) ASLP_OK(aslp_regularize_l1(st, linearity_.Data(), linearity_.Stride(), linearity_corr_.Data(), linearity_corr_.Stride(),
+                                              output_dim_, input_dim_, lr_reg * l1 * num_frames, lr_reg));
+    linearity_.AddMat(-lr, linearity_corr_);
+    if (has_bias_) ASLP_OK(aslp_axpby(st, bias_.Data(), (output_dim_ + 3) / 4 * 4, bias_corr_.Data(), (output_dim_ + 3) / 4 * 4, 1, output_dim_, -lr_bias, 1.0f));
+    if (max_norm_ > 0.0) ASLP_OK(aslp_max_norm_rows(st, linearity_.Data(), linearity_.Stride(), output_dim_, input_dim_, max_norm_));
+  }
+
+  const CuVector& GetBias() const { return bias_; }
+  void SetBias(const CuVector& bias) { KALDI_ASSERT(bias.Dim() == bias_.Dim()); bias_ = bias; }
+  const CuMatrix& GetLinearity() const { return linearity_; }
+  void SetLinearity(const CuMatrixBase& l) { KALDI_ASSERT(l.NumRows() == linearity_.NumRows() && l.NumCols() == linearity_.NumCols()); linearity_.CopyFromMat(l); }
+  const CuVector& GetBiasCorr() const { return bias_corr_; }
+  const CuMatrix& GetLinearityCorr() const { return linearity_corr_; }
+
+ protected:
+  bool has_bias_;
+  CuMatrix linearity_;
+  CuVector bias_;
+  CuMatrix linearity_corr_;
+  CuVector bias_corr_;
+  BaseFloat learn_rate_coef_, bias_learn_rate_coef_, max_norm_;
+};
+
+class LinearTransform : public AffineTransform {
+ public:
+  LinearTransform(int32 dim_in, int32 dim_out) : AffineTransform(dim_in, dim_out, false) {}
+  Component* Copy() const { return new LinearTransform(*this); }
+};
+
+}  // namespace aslp_nnet
+}  // namespace kaldi
+#endif

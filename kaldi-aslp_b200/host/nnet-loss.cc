@@ -1,0 +1,265 @@
+#include "nnet-loss.h"
+#include <algorithm>
+#include "../../include/ctc.h"
+#include "cu-workspace.h"
+
+namespace kaldi {
+namespace aslp_nnet {
+
+// ------------------------------------------------------------------ Xent
+Xent::Xent() : stats_dev_(nullptr), frames_(0), correct_(0), loss_(0), entropy_(0), likelyhood_(0), frames_progress_(0) {
+  for (double& b : base_) b = 0;
+}
+Xent::~Xent() { if (stats_dev_ != nullptr) aslp_free(stats_dev_); }
+
+static void EnsureStats(double** p) {
+  if (*p == nullptr) {
+    ASLP_OK(aslp_malloc(reinterpret_cast<void**>(p), 5 * sizeof(double)));
+    ASLP_OK(aslp_memset(CuStream(), *p, 0, 5 * sizeof(double)));
+  }
+}
+
+void Xent::Fetch() {
+  if (stats_dev_ == nullptr) return;
+  double h[5];
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), h, stats_dev_, sizeof(h)));
+  CuSync();
+  loss_ = h[0]; entropy_ = h[1]; likelyhood_ = h[2]; correct_ = h[3]; frames_ = h[4];
+}
+
+void Xent::Progress(double num_frames) {
+  static const int32 progress_step = 3600 * 100;   // 1h of frames (nnet-loss.cc:137)
+  frames_progress_ += num_frames;
+  if (frames_progress_ > progress_step) {
+    Fetch();
+    const double df = frames_ - base_[4];
+    KALDI_LOG << "ProgressLoss[last " << static_cast<int>(df / 100 / 3600) << "h of " << static_cast<int>(frames_ / 100 / 3600) << "h]: "
+              << (likelyhood_ - base_[2]) / df << " (Likelyhood) " << ((loss_ - base_[0]) - (entropy_ - base_[1])) / df << " (Xent)";
+    base_[0] = loss_; base_[1] = entropy_; base_[2] = likelyhood_; base_[3] = correct_; base_[4] = frames_;
+    frames_progress_ = 0;
+  }
+}
+
+void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const CuMatrixBase& targets, CuMatrix* diff) {
+  KALDI_ASSERT(net_out.NumCols() == targets.NumCols() && net_out.NumRows() == targets.NumRows());
+  KALDI_ASSERT(net_out.NumRows() == frame_weights.Dim());
+  KALDI_ASSERT(KALDI_ISFINITE(frame_weights.Sum()));
+  EnsureStats(&stats_dev_);
+  frame_w_dev_ = frame_weights;
+  diff->Resize(net_out.NumRows(), net_out.NumCols(), kUndefined);
+  ASLP_OK(aslp_xent_dense(CuStream(), diff->Data(), diff->Stride(), net_out.Data(), net_out.Stride(), targets.Data(), targets.Stride(),
+                          net_out.NumRows(), net_out.NumCols(), frame_w_dev_.Data(), stats_dev_));
+  Progress(frame_weights.Sum());
+}
+
+void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff) {
+  const int32 num_frames = net_out.NumRows(), num_pdf = net_out.NumCols();
+  KALDI_ASSERT(num_frames == static_cast<int32>(post.size()));
+  KALDI_ASSERT(num_frames == frame_weights.Dim());
+  bool sparse = true;
+  for (const auto& f : post) if (f.size() > 1) { sparse = false; break; }
+  if (!sparse) {                                   // PosteriorToMatrix (nnet-utils.h) then the dense path
+    Matrix<BaseFloat> m(num_frames, num_pdf);
+    for (int32 t = 0; t < num_frames; ++t)
+      for (const auto& pr : post[t]) {
+        if (pr.first >= num_pdf) KALDI_ERR << "Posterior has pdf-id " << pr.first << " but the net has " << num_pdf << " outputs";
+        m(t, pr.first) += pr.second;
+      }
+    tgt_mat_ = m;
+    Eval(frame_weights, net_out, tgt_mat_, diff);
+    return;
+  }
+  EnsureStats(&stats_dev_);
+  std::vector<int32> idx(num_frames, 0);
+  Vector<BaseFloat> w(num_frames);
+  double nf = 0;
+  for (int32 t = 0; t < num_frames; ++t) {
+    if (!post[t].empty()) {
+      if (post[t][0].first >= num_pdf) KALDI_ERR << "Posterior has pdf-id " << post[t][0].first << " but the net has " << num_pdf << " outputs";
+      idx[t] = post[t][0].first;
+      w(t) = post[t][0].second;
+    }
+    nf += frame_weights(t) * w(t);
+  }
+  KALDI_ASSERT(nf >= 0.0);
+  tgt_idx_dev_ = idx;
+  tgt_w_dev_ = w;
+  frame_w_dev_ = frame_weights;
+  diff->Resize(num_frames, num_pdf, kUndefined);
+  ASLP_OK(aslp_xent_sparse(CuStream(), diff->Data(), diff->Stride(), net_out.Data(), net_out.Stride(), num_frames, num_pdf, tgt_idx_dev_.Data(),
+                           tgt_w_dev_.Data(), frame_w_dev_.Data(), stats_dev_));
+  Progress(nf);
+}
+
+void Xent::Eval(const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff) {
+  Vector<BaseFloat> ones(static_cast<int32>(post.size()));
+  for (int32 i = 0; i < ones.Dim(); ++i) ones(i) = 1.0f;
+  Eval(ones, net_out, post, diff);
+}
+
+BaseFloat Xent::AvgLoss() { Fetch(); return (loss_ - entropy_) / frames_; }
+
+std::string Xent::Report() {         // line formats the schedulers grep (nnet-loss.cc:175-200)
+  Fetch();
+  std::ostringstream oss;
+  if (0 == frames_) {
+    oss << "AvgLoss: " << 0.0 << " (Xent), " << "Likelyhood: " << 0.0 << " " << "Frame: " << 0 << std::endl;
+    oss << "FRAME_ACCURACY >> " << 0.0 << "% <<" << std::endl;
+  } else {
+    oss << "AvgLoss: " << (loss_ - entropy_) / frames_ << " (Xent), " << "Likelyhood: " << (likelyhood_) / frames_ << " " << "Frame: " << frames_ << std::endl;
+    if (correct_ >= 0.0) oss << "FRAME_ACCURACY >> " << 100.0 * correct_ / frames_ << "% <<" << std::endl;
+  }
+  return oss.str();
+}
+
+// ------------------------------------------------------------------ WarpCtc
+WarpCtc::WarpCtc()
+    : frames_(0), sequences_num_(0), ref_num_(0), error_num_(0), frames_progress_(0), ref_num_progress_(0), error_num_progress_(0),
+      sequences_progress_(0), obj_progress_(0.0), report_step_(100), obj_(0), loss_sum_(0), loss_square_sum_(0), loss_sum_bak_(0),
+      loss_square_sum_bak_(0), normal_num_(0), stat_period_(500) {}
+
+void WarpCtc::SetUseGpu(bool use_gpu) {
+  if (!use_gpu) KALDI_ERR << "WarpCtc: this build has no CPU path (--use-gpu=no is the reference oracle, not the product)";
+}
+
+void WarpCtc::Eval(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
+                   const std::vector<std::vector<int32>>& labels, CuMatrix* diff) {
+  KALDI_ASSERT(diff != NULL);
+  // the C API wants activations with row stride == alphabet size (include/ctc.h)
+  if (net_out.Stride() != net_out.NumCols())
+    KALDI_ERR << "WarpCtc: the output dimension (" << net_out.NumCols() << ") must be a multiple of 4 so that rows are dense, as on the reference CPU path";
+  diff->Resize(net_out.NumRows(), net_out.NumCols(), kSetZero);      // rows past an utterance's end stay zero
+  const int minibatch = static_cast<int>(frame_num_utt.size());
+  KALDI_ASSERT(minibatch > 0 && net_out.NumRows() % minibatch == 0);
+  std::vector<int> flat_labels, label_lengths;
+  for (int i = 0; i < minibatch; i++) {
+    const std::vector<int>& l = labels[i];
+    for (size_t j = 0; j < l.size(); j++) KALDI_ASSERT(l[j] < net_out.NumCols());
+    flat_labels.insert(flat_labels.end(), l.begin(), l.end());
+    label_lengths.push_back(static_cast<int>(l.size()));
+  }
+  if (flat_labels.empty()) flat_labels.push_back(0);
+  const int alphabet_size = net_out.NumCols();
+  costs_.assign(minibatch, 0);
+  ctcComputeInfo info;
+  info.loc = CTC_GPU;
+  info.stream = reinterpret_cast<CUstream>(CuStream());
+  size_t bytes = 0;
+  if (get_workspace_size(label_lengths.data(), frame_num_utt.data(), alphabet_size, minibatch, info, &bytes) != CTC_STATUS_SUCCESS)
+    KALDI_ERR << "Error in get_workspace_size";
+  void* ws = CuWorkspace(bytes);               // persistent workspace: no per-minibatch malloc/free
+  const ctcStatus_t rc = compute_ctc_loss(net_out.Data(), diff->Data(), flat_labels.data(), label_lengths.data(), frame_num_utt.data(),
+                                          alphabet_size, minibatch, costs_.data(), ws, info);
+  if (rc != CTC_STATUS_SUCCESS) KALDI_ERR << "Error: compute_ctc_loss, stat = " << ctcGetStatusString(rc);
+  StatAndAverageLossCheck(utt, frame_num_utt, costs_, diff);          // WARP_CTC_GRAD_CHECK == WARP_CTC_AVG_LOSS_CHECK (warp-ctc.h:25)
+  ASLP_OK(aslp_clamp(CuStream(), diff->Data(), diff->Stride(), diff->NumRows(), diff->NumCols(), -1.0f, 1.0f));
+  if (sequences_progress_ >= report_step_) {
+    KALDI_LOG << "Progress " << sequences_num_ << " sequences (" << frames_ / (100.0 * 3600) << "Hr):"
+              << " Obj(log[Pzx]) = " << obj_progress_ / sequences_progress_ << " Obj(frame) = " << obj_progress_ / frames_progress_
+              << " TokenAcc = " << 100.0 * (1.0 - error_num_progress_ / ref_num_progress_) << " %";
+    sequences_progress_ = 0; frames_progress_ = 0; obj_progress_ = 0.0; error_num_progress_ = 0; ref_num_progress_ = 0;
+  }
+}
+
+// running mean / sigma of the per-frame loss over a sliding window of stat_period_ utterances; an utterance whose
+// loss is non-finite, outside 6 sigma, or outside (0, 3000) has its diff rows zeroed (warp-ctc.cc:288-365)
+void WarpCtc::StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
+                                      const std::vector<float>& pzx_host, CuMatrix* diff) {
+  const int32 num_sequence = static_cast<int32>(frame_num_utt.size());
+  for (int s = 0; s < num_sequence; s++) {
+    const double loss_per_frame = pzx_host[s] / frame_num_utt[s];
+    if (normal_num_ < stat_period_ / 2) {
+      normal_num_++;
+      loss_sum_ += loss_per_frame; loss_sum_bak_ += loss_per_frame;
+      loss_square_sum_ += loss_per_frame * loss_per_frame; loss_square_sum_bak_ += loss_per_frame * loss_per_frame;
+      obj_ += pzx_host[s]; obj_progress_ += pzx_host[s];
+    } else {
+      const double mean = loss_sum_ / normal_num_, sigma = sqrt(loss_square_sum_ / normal_num_);
+      if (KALDI_ISFINITE(pzx_host[s]) && (loss_per_frame >= (mean - 6 * sigma) && loss_per_frame <= (mean + 6 * sigma)) &&
+          (pzx_host[s] > 0 && pzx_host[s] < 3000)) {
+        normal_num_++;
+        loss_sum_ += loss_per_frame;
+        loss_square_sum_ += loss_per_frame * loss_per_frame;
+        obj_ += pzx_host[s]; obj_progress_ += pzx_host[s];
+        if (normal_num_ == stat_period_) {
+          loss_sum_ -= loss_sum_bak_; loss_square_sum_ -= loss_square_sum_bak_;
+          loss_sum_bak_ = loss_sum_; loss_square_sum_bak_ = loss_square_sum_;
+          normal_num_ = stat_period_ / 2;
+        }
+      } else {
+        KALDI_WARN << "Sequences " << utt[s] << " obj is abnormal(sum " << pzx_host[s] << " per_frame " << loss_per_frame << " mean "
+                   << loss_sum_ / normal_num_ << " sigma " << loss_square_sum_ / normal_num_ << "), drop it's diff and stat";
+        // rows t*num_sequence + s, t < frames: one strided zero fill instead of a host loop of per-row SetZero
+        ASLP_OK(aslp_memset2d(CuStream(), diff->Data() + static_cast<size_t>(s) * diff->Stride(), sizeof(float) * diff->Stride() * num_sequence, 0,
+                              sizeof(float) * diff->NumCols(), frame_num_utt[s]));
+      }
+    }
+    frames_ += frame_num_utt[s];
+    frames_progress_ += frame_num_utt[s];
+  }
+  const double grad_sum = diff->Sum();
+  if (!KALDI_ISFINITE(grad_sum)) {
+    KALDI_WARN << "DIFF FINITE: nan or inf ocurred in the diff, ignore";
+    diff->SetZero();
+  }
+  sequences_progress_ += num_sequence;
+  sequences_num_ += num_sequence;
+}
+
+int32 LevenshteinEditDistance(const std::vector<int32>& ref, const std::vector<int32>& hyp, int32* ins, int32* del, int32* sub) {
+  // standard DP with operation counts (util/edit-distance-inl.h); ties prefer substitution, then deletion, then insertion
+  struct Cell { int32 ins, del, sub, total; };
+  const size_t R = ref.size(), Hn = hyp.size();
+  std::vector<Cell> prev(R + 1), cur(R + 1);
+  for (size_t i = 0; i <= R; ++i) prev[i] = Cell{0, static_cast<int32>(i), 0, static_cast<int32>(i)};
+  for (size_t j = 1; j <= Hn; ++j) {
+    cur[0] = Cell{prev[0].ins + 1, prev[0].del, prev[0].sub, prev[0].total + 1};
+    for (size_t i = 1; i <= R; ++i) {
+      const int32 s = prev[i - 1].total + (ref[i - 1] == hyp[j - 1] ? 0 : 1);
+      const int32 d = cur[i - 1].total + 1, in = prev[i].total + 1;
+      if (s <= d && s <= in) { cur[i] = prev[i - 1]; if (ref[i - 1] != hyp[j - 1]) cur[i].sub++; cur[i].total = s; }
+      else if (d <= in) { cur[i] = cur[i - 1]; cur[i].del++; cur[i].total = d; }
+      else { cur[i] = prev[i]; cur[i].ins++; cur[i].total = in; }
+    }
+    prev.swap(cur);
+  }
+  if (ins) *ins = prev[R].ins;
+  if (del) *del = prev[R].del;
+  if (sub) *sub = prev[R].sub;
+  return prev[R].total;
+}
+
+// greedy decode: per-frame arg-max -> collapse repeats -> drop blank (0) -> edit distance (warp-ctc.cc:487-526)
+void WarpCtc::ErrorRate(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label) {
+  const int32 rows = net_out.NumRows();
+  int32* idx_dev = static_cast<int32*>(CuWorkspace(sizeof(int32) * (rows + 4)));
+  ASLP_OK(aslp_row_argmax(CuStream(), idx_dev, net_out.Data(), net_out.Stride(), rows, net_out.NumCols()));
+  std::vector<int32> data(rows);
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), data.data(), idx_dev, sizeof(int32) * rows));
+  CuSync();
+  const int32 num_seq = static_cast<int32>(frame_num_utt.size());
+  for (int32 s = 0; s < num_seq; s++) {
+    const int32 num_frame = frame_num_utt[s];
+    std::vector<int32> hyp;
+    int32 last = -1;
+    for (int32 f = 0; f < num_frame; f++) {
+      const int32 v = data[f * num_seq + s];
+      if (f == 0 || v != last) { if (v != 0) hyp.push_back(v); }
+      last = v;
+    }
+    int32 ins, del, sub;
+    const int32 err = LevenshteinEditDistance(label[s], hyp, &ins, &del, &sub);
+    error_num_ += err; ref_num_ += static_cast<int32>(label[s].size());
+    error_num_progress_ += err; ref_num_progress_ += static_cast<int32>(label[s].size());
+  }
+}
+
+std::string WarpCtc::Report() {
+  std::ostringstream oss;
+  oss << " Obj(log[Pzx]) = " << obj_ / sequences_num_ << " Obj(frame) = " << obj_ / frames_ << " TOKEN_ACCURACY >> "
+      << 100.0 * (1.0 - error_num_ / ref_num_) << " % <<";
+  return oss.str();
+}
+
+}  // namespace aslp_nnet
+}  // namespace kaldi

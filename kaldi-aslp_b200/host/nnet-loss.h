@@ -1,0 +1,74 @@
+// nnet-loss.h -- Xent (src/aslp-nnet/nnet-loss.{h,cc}:63-200) and WarpCtc (src/aslp-nnet/warp-ctc.{h,cc}) with the
+// reference's method names, report line formats and host-side bookkeeping (bit-exact counters, the 6-sigma loss
+// guard state machine, greedy token error rate), over the fused Xent kernel and the CTC kernels of libaslp_b200.
+#ifndef ASLP_HOST_NNET_LOSS_H_
+#define ASLP_HOST_NNET_LOSS_H_
+#include "matrix.h"
+
+namespace kaldi {
+
+// hmm/posterior.h: per frame a list of (pdf-id, weight)
+typedef std::vector<std::vector<std::pair<int32, BaseFloat>>> Posterior;
+
+namespace aslp_nnet {
+
+class Xent {
+ public:
+  Xent();
+  ~Xent();
+  // dense targets (soft labels)
+  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const CuMatrixBase& targets, CuMatrix* diff);
+  // posterior targets: one fused sparse pass when every frame has at most one pdf, dense otherwise
+  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff);
+  void Eval(const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff);
+  std::string Report();
+  BaseFloat AvgLoss();
+  double Frames() { Fetch(); return frames_; }
+  double Correct() { Fetch(); return correct_; }
+ private:
+  void Fetch();                 // device accumulators -> host (synchronises)
+  void Progress(double num_frames);
+  double* stats_dev_;           // [ce, entropy, likelihood, correct, frames] accumulated on the device
+  double frames_, correct_, loss_, entropy_, likelyhood_;
+  double frames_progress_, base_[5];
+  CuMatrix tgt_mat_;
+  CuVector frame_w_dev_, tgt_w_dev_;
+  CuArrayInt tgt_idx_dev_;
+};
+
+class WarpCtc {
+ public:
+  WarpCtc();
+  // CTC training over multiple sequences; net_out rows are stream-interleaved (t * num_seq + s). diff receives
+  // d(loss)/d(activation) clipped to [-1, 1] after the average-loss guard (warp-ctc.cc:33-286)
+  void Eval(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
+            const std::vector<std::vector<int32>>& labels, CuMatrix* diff);
+  void ErrorRate(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label);
+  void SetReportStep(int32 report_step) { report_step_ = report_step; }
+  std::string Report();
+  float NumErrorTokens() const { return error_num_; }
+  int32 NumRefTokens() const { return ref_num_; }
+  void SetUseGpu(bool use_gpu);       // only true is served: there is no CPU path
+  const std::vector<float>& LastCosts() const { return costs_; }
+ private:
+  void StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
+                               const std::vector<float>& pzx_host, CuMatrix* diff);
+  int32 frames_, sequences_num_, ref_num_;
+  float error_num_;
+  int32 frames_progress_, ref_num_progress_;
+  float error_num_progress_;
+  int32 sequences_progress_;
+  double obj_progress_;
+  int32 report_step_;
+  double obj_;
+  double loss_sum_, loss_square_sum_, loss_sum_bak_, loss_square_sum_bak_;
+  int32 normal_num_, stat_period_;
+  std::vector<float> costs_;
+  CuArrayInt maxid_;
+};
+
+int32 LevenshteinEditDistance(const std::vector<int32>& ref, const std::vector<int32>& hyp, int32* ins, int32* del, int32* sub);
+
+}  // namespace aslp_nnet
+}  // namespace kaldi
+#endif

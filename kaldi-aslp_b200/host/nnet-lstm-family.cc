@@ -1,0 +1,290 @@
+#include "nnet-lstm-family.h"
+#include "cu-workspace.h"
+
+namespace kaldi {
+namespace aslp_nnet {
+
+LstmFamily::LstmFamily(int32 input_dim, int32 output_dim, const Traits& tr)
+    : UpdatableComponent(input_dim, output_dim), tr_(tr), ncell_(0), nrecur_(0), nstream_(0), chunk_size_(0),
+      clip_gradient_(0.0f), d_(tr.ndirs), per_utt_reset_(false) {
+  // Lstm: ncell = OutputDim; BLstm: OutputDim/2; projected: nrecur = OutputDim (1 dir) or OutputDim/2 (2 dirs)
+  if (tr_.projected) nrecur_ = output_dim / tr_.ndirs;
+  else ncell_ = output_dim / tr_.ndirs;
+}
+
+void LstmFamily::AllocCorr() {
+  for (Dir& d : d_) {
+    d.w_gifo_x_corr.Resize(4 * ncell_, input_dim_, kSetZero);
+    d.w_gifo_r_corr.Resize(4 * ncell_, RecDim(), kSetZero);
+    d.bias_corr.Resize(4 * ncell_, kSetZero);
+    d.peep_i_corr.Resize(ncell_, kSetZero);
+    d.peep_f_corr.Resize(ncell_, kSetZero);
+    d.peep_o_corr.Resize(ncell_, kSetZero);
+    if (tr_.projected) d.w_r_m_corr.Resize(nrecur_, ncell_, kSetZero);
+  }
+}
+
+void LstmFamily::InitData(std::istream& is) {
+  float param_scale = 0.02f;
+  ProtoOptions po(tr_.has_celldim_token ? "(CellDim|ClipGradient|ParamScale)" : "(ClipGradient|ParamScale)");
+  if (tr_.has_celldim_token) po.Int("<CellDim>", &ncell_);
+  po.Float("<ClipGradient>", &clip_gradient_);
+  po.Float("<ParamScale>", &param_scale);
+  po.Parse(is);
+  KALDI_ASSERT(ncell_ > 0);
+  // the reference's order: all matrices (per direction x, r, [rm]), then the biases, then the peepholes
+  for (Dir& d : d_) {
+    d.w_gifo_x.Resize(4 * ncell_, input_dim_, kUndefined);
+    d.w_gifo_r.Resize(4 * ncell_, RecDim(), kUndefined);
+    InitMatParam(&d.w_gifo_x, param_scale);
+    InitMatParam(&d.w_gifo_r, param_scale);
+    if (tr_.projected) { d.w_r_m.Resize(nrecur_, ncell_, kUndefined); InitMatParam(&d.w_r_m, param_scale); }
+  }
+  for (Dir& d : d_) { d.bias.Resize(4 * ncell_, kUndefined); InitVecParam(&d.bias, param_scale); }
+  for (Dir& d : d_) {
+    d.peep_i.Resize(ncell_, kUndefined); d.peep_f.Resize(ncell_, kUndefined); d.peep_o.Resize(ncell_, kUndefined);
+    InitVecParam(&d.peep_i, param_scale); InitVecParam(&d.peep_f, param_scale); InitVecParam(&d.peep_o, param_scale);
+  }
+  AllocCorr();
+  KALDI_ASSERT(clip_gradient_ >= 0.0);
+}
+
+void LstmFamily::ReadData(std::istream& is, bool binary) {
+  if (tr_.has_celldim_token) { ExpectToken(is, binary, "<CellDim>"); ReadBasicType(is, binary, &ncell_); }
+  ExpectToken(is, binary, "<ClipGradient>");
+  ReadBasicType(is, binary, &clip_gradient_);
+  for (Dir& d : d_) {
+    d.w_gifo_x.Read(is, binary);
+    d.w_gifo_r.Read(is, binary);
+    d.bias.Read(is, binary);
+    d.peep_i.Read(is, binary);
+    d.peep_f.Read(is, binary);
+    d.peep_o.Read(is, binary);
+    if (tr_.projected) d.w_r_m.Read(is, binary);
+    KALDI_ASSERT(d.w_gifo_x.NumRows() == 4 * ncell_ && d.w_gifo_x.NumCols() == input_dim_);
+    KALDI_ASSERT(d.w_gifo_r.NumRows() == 4 * ncell_ && d.w_gifo_r.NumCols() == RecDim());
+  }
+  AllocCorr();    // momentum buffers are not part of the file: zeroed on read
+}
+
+void LstmFamily::WriteData(std::ostream& os, bool binary) const {
+  if (tr_.has_celldim_token) { WriteToken(os, binary, "<CellDim>"); WriteBasicType(os, binary, ncell_); }
+  WriteToken(os, binary, "<ClipGradient>");
+  WriteBasicType(os, binary, clip_gradient_);
+  for (const Dir& d : d_) {
+    d.w_gifo_x.Write(os, binary);
+    d.w_gifo_r.Write(os, binary);
+    d.bias.Write(os, binary);
+    d.peep_i.Write(os, binary);
+    d.peep_f.Write(os, binary);
+    d.peep_o.Write(os, binary);
+    if (tr_.projected) d.w_r_m.Write(os, binary);
+  }
+}
+
+int32 LstmFamily::NumParams() const {
+  const Dir& d = d_[0];
+  int32 n = d.w_gifo_x.NumRows() * d.w_gifo_x.NumCols() + d.w_gifo_r.NumRows() * d.w_gifo_r.NumCols() + d.bias.Dim() + 3 * ncell_;
+  if (tr_.projected) n += d.w_r_m.NumRows() * d.w_r_m.NumCols();
+  return tr_.ndirs * n;
+}
+
+void LstmFamily::GetParams(Vector<BaseFloat>* wei_copy) const {
+  wei_copy->Resize(NumParams());
+  float* p = wei_copy->Data();
+  auto vec = [&](const CuVector& v) { Vector<float> h; v.CopyToVec(&h); for (int32 i = 0; i < h.Dim(); ++i) *p++ = h(i); };
+  auto mat = [&](const CuMatrix& m) { CopyRowsToVec(m, p); p += static_cast<size_t>(m.NumRows()) * m.NumCols(); };
+  for (const Dir& d : d_) {
+    mat(d.w_gifo_x); mat(d.w_gifo_r); vec(d.bias); vec(d.peep_i); vec(d.peep_f); vec(d.peep_o);
+    if (tr_.projected) mat(d.w_r_m);
+  }
+}
+
+void LstmFamily::GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* params) {
+  params->clear();
+  for (Dir& d : d_) {
+    params->push_back(std::make_pair(d.w_gifo_x.Data(), d.w_gifo_x.NumRows() * d.w_gifo_x.Stride()));
+    params->push_back(std::make_pair(d.w_gifo_r.Data(), d.w_gifo_r.NumRows() * d.w_gifo_r.Stride()));
+    params->push_back(std::make_pair(d.bias.Data(), d.bias.Dim()));
+    params->push_back(std::make_pair(d.peep_i.Data(), d.peep_i.Dim()));
+    params->push_back(std::make_pair(d.peep_f.Data(), d.peep_f.Dim()));
+    params->push_back(std::make_pair(d.peep_o.Data(), d.peep_o.Dim()));
+    if (tr_.projected) params->push_back(std::make_pair(d.w_r_m.Data(), d.w_r_m.NumRows() * d.w_r_m.Stride()));
+  }
+}
+
+std::string LstmFamily::Info() const {
+  std::string s;
+  const char* tag[2] = {"f_", "b_"};
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    const Dir& d = d_[i];
+    const std::string pre = tr_.ndirs == 2 ? tag[i] : "";
+    s += "\n  " + pre + "w_gifo_x_  " + MomentStatistics(d.w_gifo_x) + "\n  " + pre + "w_gifo_r_  " + MomentStatistics(d.w_gifo_r) +
+         "\n  " + pre + "bias_  " + MomentStatistics(d.bias) + "\n  " + pre + "peephole_i_c_  " + MomentStatistics(d.peep_i) +
+         "\n  " + pre + "peephole_f_c_  " + MomentStatistics(d.peep_f) + "\n  " + pre + "peephole_o_c_  " + MomentStatistics(d.peep_o);
+    if (tr_.projected) s += "\n  " + pre + "w_r_m_  " + MomentStatistics(d.w_r_m);
+  }
+  return s;
+}
+std::string LstmFamily::InfoGradient() const {
+  std::string s;
+  const char* tag[2] = {"f_", "b_"};
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    const Dir& d = d_[i];
+    const std::string pre = tr_.ndirs == 2 ? tag[i] : "";
+    s += "\n  " + pre + "w_gifo_x_corr_  " + MomentStatistics(d.w_gifo_x_corr) + "\n  " + pre + "w_gifo_r_corr_  " + MomentStatistics(d.w_gifo_r_corr) +
+         "\n  " + pre + "bias_corr_  " + MomentStatistics(d.bias_corr);
+    if (tr_.projected) s += "\n  " + pre + "w_r_m_corr_  " + MomentStatistics(d.w_r_m_corr);
+  }
+  return s;
+}
+
+void LstmFamily::ResetLstmStreams(const std::vector<int32>& stream_reset_flag) {
+  if (!tr_.carry_state) return;
+  if (nstream_ == 0) {
+    nstream_ = static_cast<int32>(stream_reset_flag.size());
+    prev_state_.Resize(nstream_, Width(), kSetZero);
+    KALDI_LOG << "Running training with " << nstream_ << " streams.";
+  }
+  KALDI_ASSERT(prev_state_.NumRows() == static_cast<int32>(stream_reset_flag.size()));
+  for (size_t s = 0; s < stream_reset_flag.size(); ++s)
+    if (stream_reset_flag[s] == 1) prev_state_.RowRange(static_cast<int32>(s), 1).SetZero();
+}
+
+void LstmFamily::SetSeqLengths(const std::vector<int32>& sequence_lengths) {
+  if (tr_.use_seq_lengths) {
+    sequence_lengths_ = sequence_lengths;
+    seq_len_dev_ = sequence_lengths;
+    nstream_ = static_cast<int32>(sequence_lengths.size());
+  } else {
+    // whole-sentence training through a state-carrying component: streams restart from zero (lc.h:497-501)
+    nstream_ = static_cast<int32>(sequence_lengths.size());
+    prev_state_.Resize(nstream_, Width(), kSetZero);
+  }
+}
+
+void LstmFamily::FillDirArgs(void* arr_v, int T, int S, bool bwd) {
+  aslp_lstm_dir_t* arr = static_cast<aslp_lstm_dir_t*>(arr_v);
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    Dir& d = d_[i];
+    aslp_lstm_dir_t& a = arr[i];
+    a.T = T; a.S = S; a.C = ncell_; a.R = tr_.projected ? nrecur_ : 0;
+    a.reverse = i;                                  // direction 0 walks t = 1..T, direction 1 walks t = T..1
+    a.buf = d.prop.Data(); a.ldb = d.prop.Stride();
+    a.dbuf = bwd ? d.back.Data() : nullptr; a.lddb = bwd ? d.back.Stride() : 0;
+    a.w_r = d.w_gifo_r.Data(); a.ldwr = d.w_gifo_r.Stride();
+    a.w_rm = tr_.projected ? d.w_r_m.Data() : nullptr; a.ldwrm = tr_.projected ? d.w_r_m.Stride() : 0;
+    a.peep_i = d.peep_i.Data(); a.peep_f = d.peep_f.Data(); a.peep_o = d.peep_o.Data();
+    a.seq_len_dev = (tr_.use_seq_lengths && i == 1) ? seq_len_dev_.Data() : nullptr;
+    a.cell_clip = 50.0f;
+  }
+}
+
+void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  if (nstream_ == 0) {
+    if (tr_.use_seq_lengths) KALDI_ERR << "SetSeqLengths must be called before Propagate for " << TypeToMarker(GetType());
+    per_utt_reset_ = true;          // nnet-forward: one stream, state reset per utterance
+    nstream_ = 1;
+    prev_state_.Resize(nstream_, Width(), kSetZero);
+    KALDI_LOG << "Running nnet-forward with per-utterance LSTM-state reset";
+  }
+  if (per_utt_reset_ && tr_.carry_state) prev_state_.SetZero();
+  KALDI_ASSERT(nstream_ > 0 && in.NumRows() % nstream_ == 0);
+  const int32 S = nstream_, T = in.NumRows() / S, C = ncell_, W = Width();
+  aslp_stream_t st = CuStream();
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    Dir& d = d_[i];
+    // rows [S,(T+1)S) are fully overwritten (GEMM -> gifo, kernel -> the rest); only the boundary blocks need zeroing
+    d.prop.Resize((T + 2) * S, W, kUndefined);
+    d.prop.RowRange(0, S).SetZero();
+    d.prop.RowRange((T + 1) * S, S).SetZero();
+    if (i == 0 && tr_.carry_state) d.prop.RowRange(0, S).CopyFromMat(prev_state_);
+    // x -> g,i,f,o for the whole chunk, bias fused in the epilogue (lc.h:552-555, :632-645)
+    CuSubMatrix gifo = d.prop.Range(S, T * S, 0, 4 * C);
+    ASLP_OK(aslp_gemm(st, 0, 1, T * S, 4 * C, input_dim_, 1.0f, in.Data(), in.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(), 0.0f,
+                      gifo.Data(), gifo.Stride(), d.bias.Data(), 0.0f, GemmPrecision(), nullptr, 0));
+  }
+  aslp_lstm_dir_t args[2];
+  FillDirArgs(args, T, S, false);
+  const size_t wsb = aslp_lstm_workspace_bytes(T, S, C, tr_.projected ? nrecur_ : 0, tr_.ndirs, 0);
+  ASLP_OK(aslp_lstm_seq_fwd(st, args, tr_.ndirs, CuWorkspace(wsb), wsb));
+  if (tr_.carry_state) {
+    const int32 row = tr_.lc ? chunk_size_ : T;      // lc.h:629 vs nnet-lstm-projected-streams.h:432
+    KALDI_ASSERT(row >= 0 && row <= T);
+    prev_state_.CopyFromMat(d_[0].prop.RowRange(row * S, S));
+  }
+  const int32 O = OutPerDir(), col = tr_.projected ? 7 * C : 6 * C;
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    CuSubMatrix dst = out->ColRange(i * O, O);
+    dst.CopyFromMat(d_[i].prop.Range(S, T * S, col, O));
+  }
+}
+
+void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  const int32 S = nstream_, T = in.NumRows() / S, C = ncell_, W = Width();
+  const int32 O = OutPerDir(), ocol = tr_.projected ? 7 * C : 6 * C;
+  aslp_stream_t st = CuStream();
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    Dir& d = d_[i];
+    d.back.Resize((T + 2) * S, W, kUndefined);
+    d.back.RowRange(0, S).SetZero();
+    d.back.RowRange((T + 1) * S, S).SetZero();
+    CuSubMatrix od = d.back.Range(S, T * S, ocol, O);
+    od.CopyFromMat(out_diff.ColRange(i * O, O));
+  }
+  aslp_lstm_dir_t args[2];
+  FillDirArgs(args, T, S, true);
+  const size_t wsb = aslp_lstm_workspace_bytes(T, S, C, tr_.projected ? nrecur_ : 0, tr_.ndirs, 1);
+  ASLP_OK(aslp_lstm_seq_bwd(st, args, tr_.ndirs, CuWorkspace(wsb), wsb));
+
+  const float mmt = opts_.momentum, clip = clip_gradient_;
+  const int prec = GemmPrecision();
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    Dir& d = d_[i];
+    CuSubMatrix dgifo = d.back.Range(S, T * S, 0, 4 * C);
+    // g,i,f,o -> x (lc.h:963-965): second direction accumulates
+    ASLP_OK(aslp_gemm(st, 0, 0, T * S, input_dim_, 4 * C, 1.0f, dgifo.Data(), dgifo.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(),
+                      i == 0 ? 0.0f : 1.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, prec, nullptr, 0));
+  }
+  for (int i = 0; i < tr_.ndirs; ++i) {
+    Dir& d = d_[i];
+    // rows of the forward buffers that held the recurrent input / previous cell of each step:
+    // direction 0 read t-1 (rows [0,T*S)), direction 1 read t+1 (rows [2S,(T+2)S))   (lc.h:981-1000 vs :1022-1040)
+    const int32 prev0 = i == 0 ? 0 : 2 * S;
+    CuSubMatrix dgifo = d.back.Range(S, T * S, 0, 4 * C);
+    const size_t gws = 64u << 20;
+    void* ws = CuWorkspace(gws);
+    ASLP_OK(aslp_gemm(st, 1, 0, 4 * C, input_dim_, T * S, 1.0f, dgifo.Data(), dgifo.Stride(), in.Data(), in.Stride(), mmt,
+                      d.w_gifo_x_corr.Data(), d.w_gifo_x_corr.Stride(), nullptr, clip, prec, ws, gws));
+    CuSubMatrix rec_prev = d.prop.Range(prev0, T * S, ocol, RecDim());
+    ASLP_OK(aslp_gemm(st, 1, 0, 4 * C, RecDim(), T * S, 1.0f, dgifo.Data(), dgifo.Stride(), rec_prev.Data(), rec_prev.Stride(), mmt,
+                      d.w_gifo_r_corr.Data(), d.w_gifo_r_corr.Stride(), nullptr, clip, prec, ws, gws));
+    ASLP_OK(aslp_col_sum(st, d.bias_corr.Data(), dgifo.Data(), dgifo.Stride(), T * S, 4 * C, 1.0f, mmt, clip));
+    CuSubMatrix c_prev = d.prop.Range(prev0, T * S, 4 * C, C), c_cur = d.prop.Range(S, T * S, 4 * C, C);
+    CuSubMatrix di = d.back.Range(S, T * S, C, C), df = d.back.Range(S, T * S, 2 * C, C), d_out = d.back.Range(S, T * S, 3 * C, C);
+    ASLP_OK(aslp_col_dot(st, d.peep_i_corr.Data(), di.Data(), di.Stride(), c_prev.Data(), c_prev.Stride(), T * S, C, 1.0f, mmt, clip));
+    ASLP_OK(aslp_col_dot(st, d.peep_f_corr.Data(), df.Data(), df.Stride(), c_prev.Data(), c_prev.Stride(), T * S, C, 1.0f, mmt, clip));
+    ASLP_OK(aslp_col_dot(st, d.peep_o_corr.Data(), d_out.Data(), d_out.Stride(), c_cur.Data(), c_cur.Stride(), T * S, C, 1.0f, mmt, clip));
+    if (tr_.projected) {
+      CuSubMatrix dr = d.back.Range(S, T * S, 7 * C, nrecur_), ym = d.prop.Range(S, T * S, 6 * C, C);
+      ASLP_OK(aslp_gemm(st, 1, 0, nrecur_, C, T * S, 1.0f, dr.Data(), dr.Stride(), ym.Data(), ym.Stride(), mmt,
+                        d.w_r_m_corr.Data(), d.w_r_m_corr.Stride(), nullptr, clip, prec, ws, gws));
+    }
+  }
+}
+
+void LstmFamily::Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  // plain -lr * corr: no per-component coefficient, no L2 (lc.h:1085-1110)
+  const float lr = opts_.learn_rate;
+  aslp_stream_t st = CuStream();
+  auto mat = [&](CuMatrix& w, const CuMatrix& c) { ASLP_OK(aslp_axpby(st, w.Data(), w.Stride(), c.Data(), c.Stride(), w.NumRows(), w.NumCols(), -lr, 1.0f)); };
+  auto vec = [&](CuVector& w, const CuVector& c) { ASLP_OK(aslp_axpby(st, w.Data(), (w.Dim() + 3) / 4 * 4, c.Data(), (c.Dim() + 3) / 4 * 4, 1, w.Dim(), -lr, 1.0f)); };
+  for (Dir& d : d_) {
+    mat(d.w_gifo_x, d.w_gifo_x_corr); mat(d.w_gifo_r, d.w_gifo_r_corr); vec(d.bias, d.bias_corr);
+    vec(d.peep_i, d.peep_i_corr); vec(d.peep_f, d.peep_f_corr); vec(d.peep_o, d.peep_o_corr);
+    if (tr_.projected) mat(d.w_r_m, d.w_r_m_corr);
+  }
+}
+
+}  // namespace aslp_nnet
+}  // namespace kaldi

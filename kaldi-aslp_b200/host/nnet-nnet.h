@@ -1,0 +1,85 @@
+// nnet-nnet.h -- the Nnet graph executor, public API as src/aslp-nnet/nnet-nnet.h:38-174.
+// Buffers input_buf_/output_buf_/input_diff_buf_/output_diff_buf_ per component as in the reference
+// (nnet-nnet.cc:70-154), with Update() applied right after each component's Backpropagate (:126-129).
+#ifndef ASLP_HOST_NNET_NNET_H_
+#define ASLP_HOST_NNET_NNET_H_
+#include "nnet-component.h"
+
+namespace kaldi {
+namespace aslp_nnet {
+
+class Nnet {
+ public:
+  Nnet() {}
+  Nnet(const Nnet& other);
+  Nnet& operator=(const Nnet& other);
+  ~Nnet();
+
+  void Propagate(const CuMatrixBase& in, CuMatrix* out);
+  void Propagate(const std::vector<const CuMatrixBase*>& in, std::vector<CuMatrix*>* out);
+  void Backpropagate(const CuMatrixBase& out_diff, CuMatrix* in_diff);
+  void Backpropagate(const std::vector<const CuMatrixBase*>& out_diff, std::vector<CuMatrix*>* in_diff);
+  void Feedforward(const CuMatrixBase& in, CuMatrix* out);
+  void Feedforward(const std::vector<const CuMatrixBase*>& in, std::vector<CuMatrix*>* out);
+  void GetComponentTime();
+
+  int32 InputDim() const;
+  int32 OutputDim() const;
+  int32 NumInput() const { return static_cast<int32>(input_.size()); }
+  int32 NumOutput() const { return static_cast<int32>(output_.size()); }
+  int32 NumComponents() const { return static_cast<int32>(components_.size()); }
+  const Component& GetComponent(int32 c) const;
+  Component& GetComponent(int32 c);
+  void SetComponent(int32 c, Component* component);
+  void AppendComponent(Component* dynamically_allocated_comp);
+  void AppendNnet(const Nnet& nnet_to_append);
+  void RemoveComponent(int32 c);
+  void RemoveLastComponent() { RemoveComponent(NumComponents() - 1); }
+
+  // per-component buffers of the last Propagate / Backpropagate (the reference's public accessors return the legacy,
+  // never-filled propagate_buf_; these return the live ones so parity tests can compare layer by layer)
+  const std::vector<CuMatrix>& PropagateBuffer() const { return output_buf_; }
+  const std::vector<CuMatrix>& BackpropagateBuffer() const { return output_diff_buf_; }   // d(loss)/d(output of component c)
+
+  int32 NumParams() const;
+  void GetParams(Vector<BaseFloat>* wei_copy) const;
+  void GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* params);
+  void GetAccStats(std::vector<double*>* acc_params, std::vector<std::pair<double*, int>>* data_params);
+
+  void ResetLstmStreams(const std::vector<int32>& stream_reset_flag);
+  void SetSeqLengths(const std::vector<int32>& sequence_lengths);
+  void SetChunkSize(int chunk_size);
+
+  void Init(const std::string& config_file);
+  void Read(const std::string& file);
+  void Read(std::istream& in, bool binary);
+  void Write(const std::string& file, bool binary) const;
+  void Write(std::ostream& out, bool binary) const;
+  void WriteStandard(const std::string& file, bool binary) const;
+  void WriteStandard(std::ostream& out, bool binary) const;
+
+  std::string Info() const;
+  std::string InfoGradient() const;
+  std::string InfoPropagate() const;
+  std::string InfoBackPropagate() const;
+  void Check() const;
+  void Destroy();
+
+  void SetTrainOptions(const NnetTrainOptions& opts);
+  const NnetTrainOptions& GetTrainOptions() const { return opts_; }
+  void AutoComplete();
+  void AssignComponentId(std::vector<Component*>& components);
+  void SortComponent(std::vector<Component*>& components);
+
+ private:
+  void InitInputOutput();
+  std::vector<Component*> components_;
+  std::vector<int32> input_, output_;
+  std::vector<std::pair<std::string, BaseFloat>> propagate_time_, back_propagate_time_;
+  std::vector<CuMatrix> input_buf_, output_buf_, input_diff_buf_, output_diff_buf_;
+  NnetTrainOptions opts_;
+};
+
+}  // namespace aslp_nnet
+}  // namespace kaldi
+#endif

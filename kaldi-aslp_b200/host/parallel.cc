@@ -1,0 +1,123 @@
+#include "parallel.h"
+
+namespace kaldi {
+
+NcclNode::NcclNode(const char nccl_id[128], int nranks, int rank) : comm_(nullptr), rank_(rank), nranks_(nranks) {
+  CuStream();      // device selected + stream before the communicator is created
+  ASLP_OK(aslp_comm_init(&comm_, nccl_id, nranks, rank));
+}
+NcclNode::~NcclNode() { if (comm_ != nullptr) aslp_comm_destroy(comm_); }
+void NcclNode::Barrier() { ASLP_OK(aslp_comm_barrier(comm_, CuStream())); }
+
+void NcclNode::AllReduce(int* host_data, int n) {
+  static int* dev = nullptr; static int cap = 0;
+  if (n > cap) { if (dev) aslp_free(dev); ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&dev), sizeof(int) * (n + 4))); cap = n; }
+  ASLP_OK(aslp_memcpy_h2d(CuStream(), dev, host_data, sizeof(int) * n));
+  ASLP_OK(aslp_comm_allreduce_sum_i32(comm_, CuStream(), dev, n));
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), host_data, dev, sizeof(int) * n));
+  CuSync();
+}
+void NcclNode::AllReduceDevice(float* dev, size_t n) { ASLP_OK(aslp_comm_allreduce_sum_f32(comm_, CuStream(), dev, n)); }
+
+void NcclNode::ReduceAccStat(const std::vector<double*>& acc_params, const std::vector<std::pair<double*, int>>& data_params) {
+  Barrier();
+  if (!acc_params.empty()) {
+    const int n = static_cast<int>(acc_params.size());
+    double* dev = nullptr;
+    ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&dev), sizeof(double) * n));
+    std::vector<double> h(n);
+    for (int i = 0; i < n; ++i) h[i] = *acc_params[i];
+    ASLP_OK(aslp_memcpy_h2d(CuStream(), dev, h.data(), sizeof(double) * n));
+    ASLP_OK(aslp_comm_allreduce_sum_f64(comm_, CuStream(), dev, n));
+    ASLP_OK(aslp_memcpy_d2h(CuStream(), h.data(), dev, sizeof(double) * n));
+    CuSync();
+    for (int i = 0; i < n; ++i) *acc_params[i] = h[i];
+    aslp_free(dev);
+  }
+  for (const auto& p : data_params) ASLP_OK(aslp_comm_allreduce_sum_f64(comm_, CuStream(), p.first, p.second));   // already device-resident
+  CuSync();
+}
+
+IWorker::~IWorker() { if (table_dev_ != nullptr) aslp_free(table_dev_); }
+
+void IWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
+  std::vector<aslp_tensor_ref_t> table(params.size());
+  size_t off = 0;
+  for (size_t i = 0; i < params.size(); ++i) {
+    table[i].ptr = params[i].first;
+    table[i].offset = off;
+    table[i].n = static_cast<size_t>(params[i].second);
+    off += (table[i].n + 3) / 4 * 4;          // keep every tensor 16-byte aligned inside the arena
+  }
+  ntensors_ = static_cast<int>(params.size());
+  total_ = off;
+  if (table_dev_ != nullptr) aslp_free(table_dev_);
+  ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&table_dev_), sizeof(aslp_tensor_ref_t) * (table.size() + 1)));
+  ASLP_OK(aslp_memcpy_h2d(CuStream(), table_dev_, table.data(), sizeof(aslp_tensor_ref_t) * table.size()));
+  CuSync();
+  arena_.Resize(static_cast<int32>(total_), kSetZero);
+}
+
+bool IWorker::AllFinished(int num_worker_samples, int* num_all) {
+  *num_all = num_worker_samples;
+  AllReduce(num_all, 1);
+  if (*num_all <= 0) { KALDI_LOG << "All worker finished their data"; return true; }
+  return false;
+}
+
+// frame-weighted MODEL average (bsp-worker.cc:33-58): w <- sum_r (frames_r / frames_all) * w_r
+bool BspWorker::Synchronize(int num_worker_samples) {
+  int num_all = 0;
+  if (AllFinished(num_worker_samples, &num_all)) return false;
+  const float factor = static_cast<float>(num_worker_samples) / num_all;
+  KALDI_ASSERT(factor >= 0.0 && factor <= 1.0);
+  ASLP_OK(aslp_sync_pack(CuStream(), arena_.Data(), table_dev_, ntensors_, factor));
+  AllReduceDevice(arena_.Data(), total_);
+  ASLP_OK(aslp_sync_unpack(CuStream(), arena_.Data(), table_dev_, ntensors_));
+  return true;
+}
+
+void BmufWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
+  IWorker::InitParam(params);
+  w_prev_.Resize(static_cast<int32>(total_), kSetZero);
+  delta_prev_.Resize(static_cast<int32>(total_), kSetZero);
+  ASLP_OK(aslp_sync_pack(CuStream(), w_prev_.Data(), table_dev_, ntensors_, 1.0f));      // prev = initial model
+}
+// block-wise model-update filtering (bmuf-worker.cc:37-68): G = SUM_r (w_r - w_prev);
+// delta = mom * delta_prev + (1 - mom) * lr * G ; w = w_prev + delta ; w_prev = w ; delta_prev = delta
+bool BmufWorker::Synchronize(int num_worker_samples) {
+  int num_all = 0;
+  if (AllFinished(num_worker_samples, &num_all)) return false;
+  ASLP_OK(aslp_sync_pack_diff(CuStream(), arena_.Data(), table_dev_, ntensors_, w_prev_.Data(), 1.0f));
+  AllReduceDevice(arena_.Data(), total_);
+  ASLP_OK(aslp_sync_bmuf_apply_packed(CuStream(), table_dev_, ntensors_, w_prev_.Data(), delta_prev_.Data(), arena_.Data(), momentum_, learn_rate_));
+  return true;
+}
+
+void SodWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
+  IWorker::InitParam(params);
+  w_prev_.Resize(static_cast<int32>(total_), kSetZero);
+  s1_.Resize(static_cast<int32>(total_), kSetZero);
+  s2_.Resize(static_cast<int32>(total_), kSetZero);
+  ASLP_OK(aslp_sync_pack(CuStream(), w_prev_.Data(), table_dev_, ntensors_, 1.0f));
+}
+// "synchronously optimise the difference" (sod-worker.cc:37-61): G = SUM_r (w_prev - w_r) fed to the chosen optimizer
+bool SodWorker::Synchronize(int num_worker_samples) {
+  int num_all = 0;
+  if (AllFinished(num_worker_samples, &num_all)) return false;
+  ASLP_OK(aslp_sync_pack_diff(CuStream(), arena_.Data(), table_dev_, ntensors_, w_prev_.Data(), -1.0f));
+  AllReduceDevice(arena_.Data(), total_);
+  int opt; float lr = config_.lr, p1 = 0.f, p2 = 0.f;
+  if (config_.solver == "sgd") { opt = ASLP_OPT_SGD; }
+  else if (config_.solver == "momentum") { opt = ASLP_OPT_MOMENTUM; p1 = config_.momentum; }
+  else if (config_.solver == "adagrad") { opt = ASLP_OPT_ADAGRAD; lr = config_.adagrad_lr; }
+  else if (config_.solver == "rmsprop") { opt = ASLP_OPT_RMSPROP; lr = config_.rmsprop_lr; }
+  else if (config_.solver == "adadelta") { opt = ASLP_OPT_ADADELTA; p1 = config_.adadelta_gamma; }
+  else if (config_.solver == "adam") { opt = ASLP_OPT_ADAM; lr = config_.adam_lr; p1 = config_.adam_beta1; p2 = config_.adam_beta2; }
+  else { KALDI_ERR << "Unknown solver type " << config_.solver; return false; }
+  ASLP_OK(aslp_sync_sod_apply_packed(CuStream(), opt, table_dev_, ntensors_, arena_.Data(), s1_.Data(), s2_.Data(), w_prev_.Data(), lr, p1, p2, 1e-8f, step_));
+  ++step_;
+  return true;
+}
+
+}  // namespace kaldi

@@ -1,0 +1,95 @@
+// parallel.h -- the aslp-parallel worker interface over NCCL (NVLink 5 / NVSwitch) instead of host-staged MPI.
+// Reference: src/aslp-parallel/itf.h:27-36 (IWorker), mpi-node.h:18-101 (MpiNode), bsp-worker.{h,cc},
+// bmuf-worker.{h,cc}, sod-worker.{h,cc}, optimizer.h:172-232 (OptimizerOption).
+// The parameter tensors stay in the components (non-owning GetGpuParams views, as in the reference); each
+// Synchronize is: one int allreduce (frame count / termination protocol), ONE multi-tensor pack kernel, ONE
+// ncclAllReduce of the packed arena, ONE multi-tensor apply kernel -- versus 44 x (scale, D2H, MPI_Allreduce, H2D).
+#ifndef ASLP_HOST_PARALLEL_H_
+#define ASLP_HOST_PARALLEL_H_
+#include "matrix.h"
+#include "parse-options.h"
+
+namespace kaldi {
+
+// replaces MpiNode: owns the communicator (ctor/dtor owned MPI_Init/Finalize there)
+class NcclNode {
+ public:
+  NcclNode(const char nccl_id[128], int nranks, int rank);
+  virtual ~NcclNode();
+  int Rank() const { return rank_; }
+  int NumNodes() const { return nranks_; }
+  bool IsMainNode() const { return rank_ == 0; }
+  void Barrier();
+  void AllReduce(int* host_data, int n);                          // in-place SUM of host ints (mpi-node.h:69-73)
+  void AllReduceDevice(float* dev, size_t n);
+  // BatchNorm statistics at the end of an epoch: frame counters (host doubles) and the device fp64 running sums
+  void ReduceAccStat(const std::vector<double*>& acc_params, const std::vector<std::pair<double*, int>>& data_params);
+ protected:
+  aslp_comm_t comm_;
+  int rank_, nranks_;
+};
+
+class IWorker : public NcclNode {
+ public:
+  IWorker(const char id[128], int nranks, int rank) : NcclNode(id, nranks, rank), table_dev_(nullptr), total_(0) {}
+  virtual ~IWorker();
+  virtual void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
+  virtual bool Synchronize(int num_worker_samples) = 0;   // false when every rank is out of data
+  // a rank that has finished its shard keeps answering with zero frames so collectives stay matched (bsp-worker.cc:60-65)
+  virtual void Stop() { KALDI_LOG << "Worker " << Rank() << "finished, waitting for others"; while (Synchronize(0)) {} }
+ protected:
+  bool AllFinished(int num_worker_samples, int* num_all);
+  aslp_tensor_ref_t* table_dev_;
+  int ntensors_;
+  size_t total_;            // packed arena length
+  CuVector arena_;          // the all-reduce buffer
+};
+
+class BspWorker : public IWorker {
+ public:
+  BspWorker(const char id[128], int nranks, int rank) : IWorker(id, nranks, rank) {}
+  bool Synchronize(int num_worker_samples);
+};
+
+class BmufWorker : public IWorker {
+ public:
+  BmufWorker(const char id[128], int nranks, int rank, float momentum = 0.9f, float learn_rate = 1.0f)
+      : IWorker(id, nranks, rank), momentum_(momentum), learn_rate_(learn_rate) {}
+  void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
+  bool Synchronize(int num_worker_samples);
+ private:
+  float momentum_, learn_rate_;
+  CuVector w_prev_, delta_prev_;
+};
+
+struct OptimizerOption {
+  std::string solver;
+  float lr, momentum, adagrad_lr, rmsprop_lr, adam_lr, adadelta_gamma, adam_beta1, adam_beta2;
+  OptimizerOption() : solver("momentum"), lr(0.01f), momentum(0.9f), adagrad_lr(0.01f), rmsprop_lr(0.001f), adam_lr(0.001f),
+                      adadelta_gamma(0.95f), adam_beta1(0.9f), adam_beta2(0.999f) {}
+  void Register(OptionsItf* opts) {
+    opts->Register("solver", &solver, "Optimizer solver(sgd | momentum | adagrad | adadelta | rmsprop | adam)");
+    opts->Register("lr", &lr, "learning rate for (sgd | momentum) optimizer");
+    opts->Register("sgd-momentum", &momentum, "momentum for (momentum) optimizer");
+    opts->Register("adagrad-lr", &adagrad_lr, "learning rate for (adagrad) optimizer");
+    opts->Register("rmsprop-lr", &rmsprop_lr, "learning rate for (rmsprop) optimizer");
+    opts->Register("adam-lr", &adam_lr, "learning rate for (adam) optimizer");
+    opts->Register("adadelta-gamma", &adadelta_gamma, "update factor for (adadelta) optimizer");
+    opts->Register("adam-beta1", &adam_beta1, "update mean factor for (adam) optimizer");
+    opts->Register("adam-beta2", &adam_beta2, "update variance factor for (adam) optimizer");
+  }
+};
+
+class SodWorker : public IWorker {
+ public:
+  SodWorker(const char id[128], int nranks, int rank, const OptimizerOption& config) : IWorker(id, nranks, rank), config_(config), step_(1) {}
+  void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
+  bool Synchronize(int num_worker_samples);
+ private:
+  OptimizerOption config_;
+  int step_;
+  CuVector w_prev_, s1_, s2_;
+};
+
+}  // namespace kaldi
+#endif

@@ -112,7 +112,8 @@ def test_ctc_cfg3_geometry_many_utts_warp_path():
     tol = max(1e-4, 4 * float(np.spacing(np.float32(np.abs(c2).max()))))
     assert np.abs(grads[:, sel, :] - g2).max() < tol
     # size-independent property: every gradient row sums to ~0 (softmax - posterior, both sum to 1)
-    assert np.abs(grads.sum(axis=2)).max() < 2e-4
+    # (up to the same fp32 log-space resolution: a few ulp(|cost|))
+    assert np.abs(grads.sum(axis=2)).max() < 16 * float(np.spacing(np.float32(costs.max())))
 
 
 def test_ctc_cpu_location_is_refused():

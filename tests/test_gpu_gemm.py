@@ -74,10 +74,14 @@ def test_gemm_epilogue_alpha_beta_bias_clip(prec):
 @pytest.mark.parametrize("prec", [0, 1])
 def test_gemm_wgrad_split_k(prec):
     # chunk weight gradient: [4C, D] = DGIFO^T [4C, T*S] * X [T*S, D] with momentum and clip (lc.h:981-1017)
+    # long contractions: the bound is the north_star's 1e-4 (fp32-grade path), the TF32 bound otherwise
+    tol = 1e-4 if prec == 0 else TOL[prec]
     err, _, _, _ = run_gemm(1280, 640, 4000, True, False, prec, alpha=1.0, beta=0.9, clip=50.0)
-    assert err < TOL[prec]
+    assert err < tol, err
     err, _, _, _ = run_gemm(320, 40, 4000, True, False, prec, alpha=1.0, beta=0.9)
-    assert err < TOL[prec]
+    assert err < tol, err
+    err, _, _, _ = run_gemm(1280, 640, 16000, True, False, prec, alpha=1.0, beta=0.9)      # cfg3 chunk wgrad, full K
+    assert err < tol, err
 
 
 def test_gemm_padded_strides_do_not_leak():

@@ -16,6 +16,7 @@ rm -f gpurun_out/summary.txt
 run pointwise tests/test_gpu_pointwise.py
 run ctc tests/test_gpu_ctc.py
 run lstm tests/test_gpu_lstm.py
+run nnet_golden tests/test_gpu_nnet_golden.py
 run gemm_fp32 tests/test_gpu_gemm.py -k "all_layouts and fp32"
 run gemm_nt_tf32 tests/test_gpu_gemm.py -k "all_layouts and NT and -tf32"
 run gemm_nt_3x tests/test_gpu_gemm.py -k "all_layouts and NT and x3tf32"
@@ -23,8 +24,6 @@ run gemm_nn tests/test_gpu_gemm.py -k "all_layouts and NN and tf32"
 run gemm_tn tests/test_gpu_gemm.py -k "all_layouts and TN and tf32"
 run gemm_tt tests/test_gpu_gemm.py -k "all_layouts and TT and tf32"
 run gemm_rest tests/test_gpu_gemm.py -k "not all_layouts"
-# if MN-major still fails natively, see whether the K-major-via-transpose route is sound
-ASLP_GEMM_MN_TRANSPOSE=1 run gemm_mn_via_transpose tests/test_gpu_gemm.py -k "(NN or TN or TT) and tf32 or split_k"
 timeout -s KILL 600 python tools/perf_probe.py > gpurun_out/perf_probe.jsonl 2> gpurun_out/perf_probe.err
 echo "perf_probe exit=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; cat gpurun_out/perf_probe.jsonl
