@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing measurement of the aslp-nnet training hot path on B200.
+
+Workload (BASELINE.json configs[2], the configuration the headline metric is quoted on; SURVEY.md 8d cfg 3):
+  3 x <BLstmProjectedStreamsLC> (CellDim 320, OutputDim 640) -> <AffineTransform> 640->72 -> <Softmax>, warp-ctc CTC,
+  one minibatch = 16 utterances x exactly 1000 frames of 40-dim N(0,1) features, 100 labels each, momentum 0.9,
+  learn_rate = norm_lr / valid frames (aslp-nnet-train-warp-ctc-streams.cc:175-198).  A "step" is one such minibatch:
+  Propagate -> WarpCtc::Eval -> Backpropagate (weight update inside), i.e. the reference trainer's loop body.
+Metric: train frames/sec (valid, unmasked frames), whole job over N GPUs.
+  value : features already resident in HBM when the timed region starts (device-timed, CUDA events on the compute stream)
+  e2e   : the same step through the host C API with HOST (pinned) feature buffers: H2D of the features and D2H of the
+          per-utterance costs inside the timed region
+N > 1 (torchrun, one process per GPU): every rank owns a model replica and its own utterance shard (weak scaling);
+  a BMUF worker (momentum 1 - 1/N, learn rate 1) synchronises over NCCL every --sync-period frames
+  (aslp-nnet-train-lc-blstm-streams-worker.cc:341-347).  Time = max over ranks.
+--impl reference: the reference's own CPU path (oracle/_ref/ref_driver, the unmodified reference classes compiled with
+  HAVE_CUDA=0) on a bounded sample of the same workload, all host threads for BLAS.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S, T, D, K, L = 16, 1000, 40, 72, 100
+C_CELL, OUT = 320, 640
+MOMENTUM, NORM_LR = 0.9, 0.016            # learn_rate = 0.016 / 16000 valid frames = 1e-6
+SYNC_PERIOD = 25600
+PROTO = """<NnetProto>
+<BLstmProjectedStreamsLC> <InputDim> 40 <OutputDim> 640 <CellDim> 320 <ParamScale> 0.01 <ClipGradient> 5
+<BLstmProjectedStreamsLC> <InputDim> 640 <OutputDim> 640 <CellDim> 320 <ParamScale> 0.01 <ClipGradient> 5
+<BLstmProjectedStreamsLC> <InputDim> 640 <OutputDim> 640 <CellDim> 320 <ParamScale> 0.01 <ClipGradient> 5
+<AffineTransform> <InputDim> 640 <OutputDim> 72 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.04
+<Softmax> <InputDim> 72 <OutputDim> 72
+</NnetProto>
+"""
+METRIC = "train frames/sec (LC-BLSTM-CTC)"
+UNIT = "frames/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "cfg3: 3x BLstmProjectedStreamsLC(cell 320, out 640) + Affine 640->72 + Softmax, warp-ctc CTC; "
+                    "minibatch 16 utts x 1000 frames x 40-dim, 100 labels/utt, K=72",
+        "frames_per_step_per_gpu": S * T,
+        "parallelism": "dp%d-bmuf(sync-period %d frames)" % (n_gpus, SYNC_PERIOD) if n_gpus > 1 else "single",
+        "l2_policy": "working set per step (6 LSTM buffers of 184 MB + exchange workspaces) >> 126 MB L2; no explicit flush needed",
+    }
+
+
+def make_data(rank, t_frames=T):
+    rng = np.random.default_rng(1000 + rank)
+    feats = rng.standard_normal((t_frames * S, D)).astype(np.float32)
+    n_lab = max(1, min(L, t_frames // 4))
+    labels = []
+    for _ in range(S):
+        lab = list(rng.integers(1, K, size=n_lab))
+        if n_lab >= 4:                                   # forced repeats as src/warp-ctc/tests/test.h:38-53
+            lab[n_lab // 2] = lab[n_lab // 2 + 1]
+            lab[n_lab // 4] = lab[n_lab // 4 + 1]
+        labels.append([int(v) for v in lab])
+    return feats, labels
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line) via NVML."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:          # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:      # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref)."""
+    if rank != 0:
+        return None
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    cores = os.cpu_count() or 1
+    t_sample = 200                                  # frames per utterance in one reference step (bounded sample: 1/5 of T)
+    cfg = workload_config(args.gpus)
+    line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg}
+    if not os.path.exists(drv):
+        line["unavailable"] = "oracle/_ref/ref_driver is not built (run __graft_entry__.build() where /root/reference exists)"
+        return line
+    from oracle import kaldi_io
+    feats, labels = make_data(0, t_sample)
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "proto.txt"), "w").write(PROTO)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS=str(cores))
+        subprocess.check_call([drv, "init", "proto.txt", "model.bin", "777", "1"], cwd=td, env=env, stderr=subprocess.DEVNULL)
+        kaldi_io.write_mat(os.path.join(td, "input.mat"), feats)
+        with open(os.path.join(td, "labels.txt"), "w") as f:
+            for l in labels:
+                f.write(" ".join(map(str, l)) + "\n")
+        with open(os.path.join(td, "spec.txt"), "w") as f:
+            f.write("input input.mat\nloss ctc\nlabels labels.txt\nseq_lengths %s\nmomentum %g\nnorm_learn_rate %g\niters %d\nwarmup %d\n"
+                    % (",".join([str(t_sample)] * S), MOMENTUM, NORM_LR * t_sample / T, args.steps + args.warmup, args.warmup))
+        out = subprocess.check_output([drv, "bench", "model.bin", "spec.txt"], cwd=td, env=env, stderr=subprocess.DEVNULL)
+    r = json.loads(out.decode().strip().splitlines()[-1])
+    fps = r["frames_per_sec"]
+    sample = "%d steps of 16 utts x %d frames (1/%d of the minibatch length), OpenBLAS threads=%d" % (args.steps, t_sample, T // t_sample, cores)
+    line.update({"value": fps, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps),
+                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return line
+
+
+def cpu_baseline_leg():
+    """Bounded CPU sample for our arm's JSON line (rank 0, N=1): one warm-up + one timed reference step at T=50."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    cores = os.cpu_count() or 1
+    if not os.path.exists(drv):
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "unavailable: oracle/_ref not built"}
+
+    class A:
+        gpus, steps, warmup = 1, 2, 1
+    r = run_reference(A, 0, 1)
+    cb = r["cpu_baseline"]
+    return cb
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return 0
+
+    import torch            # plumbing: rendezvous for N > 1; imported first so that its bundled NCCL is the one loaded
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    from kaldi_aslp_b200 import cuda_lib, nnet as NN
+    NN.select_device(local_rank)
+    NN.set_gemm_precision({"3xtf32": 0, "tf32": 1, "fp32": 2}[args.precision])
+    lib = cuda_lib()
+
+    with tempfile.TemporaryDirectory() as td:
+        proto = os.path.join(td, "proto.txt")
+        open(proto, "w").write(PROTO)
+        NN.srand(777)                       # same initial model on every rank, random-init weights of the named architecture
+        net = NN.Nnet.init(proto)
+    net.set_train_options(learn_rate=0.0, momentum=MOMENTUM)
+    ctc = NN.WarpCtc()
+    feats, labels = make_data(rank)
+    flat = (np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in labels])), np.ascontiguousarray([len(l) for l in labels], np.int32))
+    lens = [T] * S
+    dev_ptr, _ = NN.upload(feats)
+    # pinned host copy for the end-to-end leg
+    hp = ctypes.c_void_p()
+    from kaldi_aslp_b200 import host_lib
+    assert host_lib().aslp_nnet_pinned_alloc(ctypes.byref(hp), feats.nbytes) == 0
+    pinned = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_float)), shape=feats.shape)
+    pinned[:] = feats
+
+    worker = None
+    if world > 1:
+        ids = [NN.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        worker = NN.Worker("bmuf", ids[0], world, rank, bmuf_momentum=1.0 - 1.0 / world, bmuf_learn_rate=1.0)
+        worker.init_param(net)
+
+    state = {"since_sync": 0}
+
+    def step(on_device):
+        if on_device:
+            costs = NN.train_step_ctc(net, ctc, dev_ptr, lens, None, norm_learn_rate=NORM_LR, on_device=True, rows=T * S, cols=D, flat=flat)
+        else:
+            costs = NN.train_step_ctc(net, ctc, pinned, lens, None, norm_learn_rate=NORM_LR, flat=flat)
+        state["since_sync"] += S * T
+        if worker is not None and state["since_sync"] > SYNC_PERIOD:
+            worker.synchronize(state["since_sync"])
+            state["since_sync"] = 0
+        return costs
+
+    def barrier():
+        NN.device_sync()
+        if world > 1:
+            dist.barrier()
+
+    def timed(on_device, profile=False):
+        barrier()
+        l0 = NN.launch_count()
+        if profile:
+            lib.aslp_lstm_profile(1)
+        host_lib().aslp_nnet_event_record(0)
+        last = None
+        for _ in range(args.steps):
+            last = step(on_device)
+        host_lib().aslp_nnet_event_record(1)
+        ms = ctypes.c_float(0)
+        assert host_lib().aslp_nnet_event_elapsed_ms(0, 1, ctypes.byref(ms)) == 0
+        NN.device_sync()
+        launches = NN.launch_count() - l0
+        t = torch.tensor([ms.value], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, last
+
+    for _ in range(max(3, args.warmup)):
+        step(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches, costs = timed(True, profile=True)
+    fwd_ms, bwd_ms = ctypes.c_double(0), ctypes.c_double(0)
+    nf, nb = ctypes.c_int(0), ctypes.c_int(0)
+    lib.aslp_lstm_profile_read(ctypes.byref(fwd_ms), ctypes.byref(nf), ctypes.byref(bwd_ms), ctypes.byref(nb))
+    lib.aslp_lstm_profile(0)
+    step(False)                                   # warm the host path
+    ms_e2e, _, _ = timed(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        frames = S * T * args.steps * world
+        hbm_peak, tf_peak, peak_src = measured_peaks()
+        # dominant kernel: the persistent LSTM backward recurrence.  Algorithmic work per launch: per step and
+        # direction 2*S*(4C*R + R*C) flop for the two recurrent contractions, T steps, 2 directions.
+        flop_per_launch = 2.0 * S * (4 * C_CELL * C_CELL + C_CELL * C_CELL) * T * 2
+        bwd_avg_ms = bwd_ms.value / max(1, nb.value)
+        fwd_avg_ms = fwd_ms.value / max(1, nf.value)
+        ach = flop_per_launch / (bwd_avg_ms * 1e-3) / 1e12 if bwd_avg_ms > 0 else 0.0
+        step_ms = ms_dev / args.steps
+        line = {
+            "metric": METRIC, "value": frames / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else ("f32 (GEMMs: 3xTF32 split, fp32-grade)" if args.precision == "3xtf32" else "f32 (GEMMs: TF32)"),
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(feats.nbytes), "d2h_bytes_per_step": int(4 * S)},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {
+                "kernel": "lstm_bwd_kernel (persistent BPTT recurrence, both directions, one launch per layer)",
+                "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak if tf_peak else None,
+                "traffic": None, "peak_source": peak_src,
+                "note": "latency-bound per-step contractions [S=16 x 1280 x 320] (SURVEY 8d reports them separately); share of step: "
+                        "lstm_bwd %.1f%%, lstm_fwd %.1f%%" % (100 * bwd_ms.value / ms_dev, 100 * fwd_ms.value / ms_dev),
+                "avg_launch_ms": {"lstm_bwd": bwd_avg_ms, "lstm_fwd": fwd_avg_ms},
+            },
+            "loss": {"mean_ctc_cost_last_step": float(np.mean(costs))},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

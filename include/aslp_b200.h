@@ -57,6 +57,9 @@ int aslp_stream_create(aslp_stream_t* s);
 int aslp_stream_destroy(aslp_stream_t s);
 int aslp_stream_sync(aslp_stream_t s);
 int aslp_device_sync(void);
+/* CUDA events: *event is created on first use; elapsed synchronises on `b` */
+int aslp_event_record(aslp_stream_t s, void** event);
+int aslp_event_elapsed_ms(void* a, void* b, float* ms);
 
 /* ---- dense contraction: CuMatrixBase::AddMatMat (cu-matrix.cc:1027-1062) ----
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C  (+ bias[n] broadcast over rows)
@@ -175,6 +178,9 @@ typedef struct {
 size_t aslp_lstm_workspace_bytes(int T, int S, int C, int R, int ndirs, int backward);
 int aslp_lstm_seq_fwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* workspace, size_t workspace_bytes);
 int aslp_lstm_seq_bwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* workspace, size_t workspace_bytes);
+/* measurement aid: CUDA-event timing of the persistent launches on their own stream (enable, run, read totals in ms) */
+int aslp_lstm_profile(int enable);
+int aslp_lstm_profile_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches);
 
 /* ---- GruStreams recurrence (src/aslp-nnet/nnet-gru-streams.h:238-441) ----
  * buf [(T+2)S, 5H] columns [z r m g h]; before fwd rows [S,(T+1)S) hold x*W_zrm_x^T + bias in [z r m]. */

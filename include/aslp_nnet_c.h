@@ -21,7 +21,12 @@ int aslp_nnet_select_device(int dev);                 /* CuDevice::Instantiate()
 int aslp_nnet_srand(int seed);                        /* std::srand(seed) before Nnet::Init (aslp-nnet-init.cc:55) */
 int aslp_nnet_set_gemm_precision(int precision);      /* ASLP_GEMM_3XTF32 (default) / ASLP_GEMM_TF32 / ASLP_GEMM_FP32 */
 int aslp_nnet_device_sync(void);
-unsigned long long aslp_nnet_launch_count(void);      /* kernels launched so far by libaslp_b200 in this process */
+unsigned long long aslp_nnet_launch_count(void);
+/* CUDA events on the host layer's compute stream (the stream every kernel of this library is launched on) */
+int aslp_nnet_event_record(int slot);                 /* slot in [0, 16) */
+int aslp_nnet_event_elapsed_ms(int slot_a, int slot_b, float* ms);   /* synchronises on slot_b */
+int aslp_nnet_pinned_alloc(void** host_ptr, size_t bytes);
+int aslp_nnet_pinned_free(void* host_ptr);      /* kernels launched so far by libaslp_b200 in this process */
 
 int aslp_nnet_init(const char* proto_file, aslp_nnet_t* out);            /* Nnet::Init  (nnet-nnet.cc:561-603) */
 int aslp_nnet_read(const char* model_file, aslp_nnet_t* out);            /* Nnet::Read  (nnet-nnet.cc:606-636) */

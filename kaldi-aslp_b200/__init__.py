@@ -68,7 +68,7 @@ def parse_header(path):
                     continue
                 toks = a.replace("const", "").split()
                 ty = " ".join(toks[:-1]) if len(toks) > 1 else toks[0]
-                argtypes.append(_CTYPE[ty])
+                argtypes.append(_CTYPE[ty] if ty in _CTYPE else ctypes.c_void_p)      # opaque handle typedefs (*_t)
         out[name] = (restype, argtypes)
     return out
 

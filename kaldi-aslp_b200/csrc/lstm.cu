@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "scratch.cuh"
 #include "recur.cuh"
+#include <vector>
 
 namespace {
 
@@ -400,6 +401,12 @@ int init_exchange(cudaStream_t st, const Plan& P, bool bwd) {
   return 0;
 }
 
+// optional per-launch device timing of the persistent kernels (bench.py's roofline object): CUDA events on the
+// launching stream around the cooperative launch only; resolved lazily in aslp_lstm_profile_read().
+struct ProfRec { cudaEvent_t a, b; bool bwd; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
 int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_t ws_bytes, bool bwd) {
   cudaStream_t st = (cudaStream_t)s;
   ASLP_REQUIRE(ndirs == 1 || ndirs == 2);
@@ -418,8 +425,11 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
   ASLP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   void* args[] = {(void*)&P.L};
   // cooperative launch: guarantees all CTAs are co-resident (the polling exchange needs that)
+  ProfRec rec;
+  if (g_prof_on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); rec.bwd = bwd; cudaEventRecord(rec.a, st); }
   ASLP_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(P.L.nblk * ndirs), dim3(NT), args, P.smem, st));
   ASLP_COUNT_LAUNCH();
+  if (g_prof_on) { cudaEventRecord(rec.b, st); g_prof.push_back(rec); }
   return 0;
 }
 
@@ -429,6 +439,23 @@ extern "C" {
 
 size_t aslp_lstm_workspace_bytes(int T, int S, int C, int R, int ndirs, int backward) {
   return (size_t)ndirs * ws_per_dir(T, S, C, R, backward != 0);
+}
+int aslp_lstm_profile(int enable) {
+  g_prof_on = enable != 0;
+  for (ProfRec& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  return 0;
+}
+int aslp_lstm_profile_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches) {
+  double f = 0, b = 0; int nf = 0, nb = 0;
+  for (ProfRec& r : g_prof) {
+    ASLP_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    ASLP_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.bwd) { b += ms; ++nb; } else { f += ms; ++nf; }
+  }
+  if (fwd_ms) *fwd_ms = f; if (fwd_launches) *fwd_launches = nf; if (bwd_ms) *bwd_ms = b; if (bwd_launches) *bwd_launches = nb;
+  return 0;
 }
 int aslp_lstm_seq_fwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* workspace, size_t workspace_bytes) {
   return run(s, dirs, ndirs, workspace, workspace_bytes, false);

@@ -64,6 +64,16 @@ int aslp_stream_create(aslp_stream_t* s) { cudaStream_t st; ASLP_CUDA(cudaStream
 int aslp_stream_destroy(aslp_stream_t s) { ASLP_CUDA(cudaStreamDestroy((cudaStream_t)s)); return 0; }
 int aslp_stream_sync(aslp_stream_t s) { ASLP_CUDA(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
 int aslp_device_sync(void) { ASLP_CUDA(cudaDeviceSynchronize()); return 0; }
+int aslp_event_record(aslp_stream_t s, void** event) {
+  if (*event == nullptr) { cudaEvent_t e; ASLP_CUDA(cudaEventCreate(&e)); *event = (void*)e; }
+  ASLP_CUDA(cudaEventRecord((cudaEvent_t)*event, (cudaStream_t)s));
+  return 0;
+}
+int aslp_event_elapsed_ms(void* a, void* b, float* ms) {
+  ASLP_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+  ASLP_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return 0;
+}
 
 }  // extern "C"
 

@@ -37,6 +37,21 @@ int aslp_nnet_srand(int seed) { srand(seed); return 0; }
 int aslp_nnet_set_gemm_precision(int precision) { SetGemmPrecision(precision); return 0; }
 int aslp_nnet_device_sync(void) { CAPI_BEGIN CuSync(); CAPI_END }
 unsigned long long aslp_nnet_launch_count(void) { return aslp_launch_count(); }
+static void* g_events[16] = {nullptr};
+int aslp_nnet_event_record(int slot) {
+  CAPI_BEGIN
+  if (slot < 0 || slot >= 16) KALDI_ERR << "event slot out of range";
+  ASLP_OK(aslp_event_record(CuStream(), &g_events[slot]));
+  CAPI_END
+}
+int aslp_nnet_event_elapsed_ms(int a, int b, float* ms) {
+  CAPI_BEGIN
+  if (a < 0 || a >= 16 || b < 0 || b >= 16 || !g_events[a] || !g_events[b]) KALDI_ERR << "event slot not recorded";
+  ASLP_OK(aslp_event_elapsed_ms(g_events[a], g_events[b], ms));
+  CAPI_END
+}
+int aslp_nnet_pinned_alloc(void** host_ptr, size_t bytes) { CAPI_BEGIN CuStream(); ASLP_OK(aslp_malloc_host(host_ptr, bytes)); CAPI_END }
+int aslp_nnet_pinned_free(void* host_ptr) { CAPI_BEGIN ASLP_OK(aslp_free_host(host_ptr)); CAPI_END }
 
 int aslp_nnet_init(const char* proto_file, aslp_nnet_t* out) { CAPI_BEGIN Nnet* n = new Nnet(); try { n->Init(proto_file); } catch (...) { delete n; throw; } *out = n; CAPI_END }
 int aslp_nnet_read(const char* model_file, aslp_nnet_t* out) { CAPI_BEGIN Nnet* n = new Nnet(); try { n->Read(model_file); } catch (...) { delete n; throw; } *out = n; CAPI_END }

@@ -107,6 +107,7 @@ int main(int argc, char** argv) {
     ReadMat(sp["input"], &in_h);
     const std::string loss = sp.count("loss") ? sp["loss"] : "none";
     const int iters = sp.count("iters") ? atoi(sp["iters"].c_str()) : 1;
+    const int warmup = sp.count("warmup") ? atoi(sp["warmup"].c_str()) : 0;      // bench: untimed leading iterations
     const bool dump_comp = sp.count("dump_components") && atoi(sp["dump_components"].c_str()) != 0;
     const float norm_lr = sp.count("norm_learn_rate") ? atof(sp["norm_learn_rate"].c_str()) : 0.0f;
     std::vector<int32> seq_lengths = sp.count("seq_lengths") ? Ints(sp["seq_lengths"]) : std::vector<int32>();
@@ -139,6 +140,7 @@ int main(int argc, char** argv) {
     Timer timer;
     double frames_done = 0;
     for (int it = 0; it < iters; ++it) {
+      if (bench && it == warmup) { timer.Reset(); frames_done = 0; }
       if (!seq_lengths.empty()) {
         nnet.SetSeqLengths(seq_lengths);
         for (int c = 0; c < nnet.NumComponents(); ++c)
@@ -182,7 +184,7 @@ int main(int argc, char** argv) {
     }
     const double el = timer.Elapsed();
     if (bench) {
-      std::cout << "{\"impl\": \"reference-cpu\", \"iters\": " << iters << ", \"frames\": " << frames_done << ", \"seconds\": " << el
+      std::cout << "{\"impl\": \"reference-cpu\", \"iters\": " << (iters - warmup) << ", \"frames\": " << frames_done << ", \"seconds\": " << el
                 << ", \"frames_per_sec\": " << frames_done / el << "}" << std::endl;
     } else {
       std::ofstream rep((outdir + "/report.txt").c_str());

@@ -101,6 +101,14 @@ def probe_ctc(T, mb, Kc, Lab):
 
 if __name__ == "__main__":
     out = []
+    if len(sys.argv) > 1 and sys.argv[1] == "lstm":      # single launches for an ncu capture
+        orig = timeit
+        def timeit(fn, iters=1, warm=0):                  # noqa: F811
+            return orig(fn, iters=1, warm=0)
+        globals()["timeit"] = timeit
+        print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, False)), flush=True)
+        print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, True)), flush=True)
+        sys.exit(0)
     for spec in [(16000, 1280, 640, False, True), (16000, 1280, 40, False, True), (16000, 640, 1280, False, False),
                  (1280, 640, 16000, True, False), (320, 320, 16000, True, False), (16000, 72, 640, False, True),
                  (8192, 8192, 8192, False, True)]:
