@@ -26,7 +26,7 @@ unsigned long long aslp_nnet_launch_count(void);
 int aslp_nnet_event_record(int slot);                 /* slot in [0, 16) */
 int aslp_nnet_event_elapsed_ms(int slot_a, int slot_b, float* ms);   /* synchronises on slot_b */
 int aslp_nnet_pinned_alloc(void** host_ptr, size_t bytes);
-int aslp_nnet_pinned_free(void* host_ptr);      /* kernels launched so far by libaslp_b200 in this process */
+int aslp_nnet_pinned_free(void* host_ptr);
 
 int aslp_nnet_init(const char* proto_file, aslp_nnet_t* out);            /* Nnet::Init  (nnet-nnet.cc:561-603) */
 int aslp_nnet_read(const char* model_file, aslp_nnet_t* out);            /* Nnet::Read  (nnet-nnet.cc:606-636) */

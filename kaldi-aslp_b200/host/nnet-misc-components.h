@@ -53,8 +53,10 @@ class BatchNormalization : public UpdatableComponent {
   void WriteData(std::ostream& os, bool binary) const {
     WriteToken(os, binary, "<NumAccFrames>");
     WriteBasicType(os, binary, num_acc_frames_);
-    acc_means_.Write(os, binary);
-    acc_vars_.Write(os, binary);
+    // quirk kept for byte compatibility: the reference's CuVector<Real>::Write goes through a Vector<BaseFloat>
+    // (src/aslp-cudamatrix/cu-vector.cc:851-855), so the fp64 running sums land on disk as "FV"; Read promotes them back
+    WriteAsFloat(acc_means_, os, binary);
+    WriteAsFloat(acc_vars_, os, binary);
     shift_.Write(os, binary);
     scale_.Write(os, binary);
   }
@@ -112,6 +114,13 @@ class BatchNormalization : public UpdatableComponent {
   }
 
  private:
+  static void WriteAsFloat(const CuVectorD& v, std::ostream& os, bool binary) {
+    Vector<double> d;
+    v.CopyToVec(&d);
+    Vector<float> f(d.Dim());
+    for (int32 i = 0; i < d.Dim(); ++i) f(i) = static_cast<float>(d(i));
+    f.Write(os, binary);
+  }
   void AllocWork() {
     mean_vec_.Resize(output_dim_, kSetZero);
     var_vec_.Resize(output_dim_); var_vec_.Set(1.0f);
