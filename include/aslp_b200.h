@@ -181,6 +181,9 @@ int aslp_lstm_seq_bwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, v
 /* measurement aid: CUDA-event timing of the persistent launches on their own stream (enable, run, read totals in ms) */
 int aslp_lstm_profile(int enable);
 int aslp_lstm_profile_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches);
+/* development aid: when dev_buf != NULL (long long[grid][8], device) thread 0 of every CTA accumulates clock64 ticks spent
+ * {waiting for its CTA, in its own exchange poll, waiting for the CTA's polls, in the work units, [fwd: contraction, reduce, unit prologue]} over the launch */
+int aslp_lstm_debug_timing(long long* dev_buf);
 
 /* ---- GruStreams recurrence (src/aslp-nnet/nnet-gru-streams.h:238-441) ----
  * buf [(T+2)S, 5H] columns [z r m g h]; before fwd rows [S,(T+1)S) hold x*W_zrm_x^T + bias in [z r m]. */

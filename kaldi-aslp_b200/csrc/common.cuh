@@ -32,16 +32,17 @@ static inline int aslp_div_up(long long a, long long b) { return (int)((a + b - 
 int aslp_num_sms();
 
 // ---- device math with the reference's formulas (matrix/kaldi-vector.cc:885-936) ----
+// Branch-free forms of the reference's overflow-safe split (x > 0: 1/(1+exp(-x)), else exp(x)/(exp(x)+1)); both
+// branches share e = exp(-|x|) and the denominator, so selecting the numerator gives the SAME bits without divergence.
 __device__ __forceinline__ float ref_sigmoid(float x) {
-  // x>0: 1/(1+exp(-x)); else exp(x)/(exp(x)+1)  -- overflow-safe split used by the CPU path
-  if (x > 0.0f) return 1.0f / (1.0f + expf(-x));
-  float ex = expf(x);
-  return ex / (ex + 1.0f);
+  const float e = expf(-fabsf(x));
+  return (x > 0.0f ? 1.0f : e) / (1.0f + e);
 }
+// x > 0: -1 + 2/(1+exp(-x)^2), else 1 - 2/(1+exp(x)^2): the two are exact negations of each other at equal |x|
 __device__ __forceinline__ float ref_tanh(float x) {
-  if (x > 0.0f) { float ie = expf(-x); return -1.0f + 2.0f / (1.0f + ie * ie); }
-  float ie = expf(x);
-  return 1.0f - 2.0f / (1.0f + ie * ie);
+  const float ie = expf(-fabsf(x));
+  const float v = -1.0f + 2.0f / (1.0f + ie * ie);
+  return x > 0.0f ? v : -v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(NT, 1) gru_fwd_kernel(GruDev D) {
     for (int grp = 0; grp < ngroups; ++grp) {
       const int s0 = grp * SG, sg = min(SG, SX - s0), nchunks = (min(SG, S - s0) + 15) / 16;
       __syncthreads();
-      stage_poll(xT, SP, D.xa + (size_t)(t - 1) * H * SX, H, SX, s0, sg >> 2);
+      stage_poll<8>(xT, SP, D.xa + (size_t)(t - 1) * H * SX, H, SX, s0, sg >> 2);
       __syncthreads();
       const int npair = (nh + 1) >> 1;
       for (int u = warp; u < npair * nchunks; u += NW) {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NT, 1) gru_fwd_kernel(GruDev D) {
         }
       }
       __syncthreads();
-      stage_poll(xT, SP, D.xb + (size_t)t * H * SX, H, SX, s0, sg >> 2);
+      stage_poll<8>(xT, SP, D.xb + (size_t)t * H * SX, H, SX, s0, sg >> 2);
       __syncthreads();
       const int nquad = (nh + 3) >> 2;
       for (int u = warp; u < nquad * nchunks; u += NW) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NT, 1) gru_bwd_kernel(GruDev D) {
     for (int grp = 0; grp < ngroups; ++grp) {
       const int s0 = grp * SG, sg = min(SG, SX - s0), nchunks = (min(SG, S - s0) + 15) / 16;
       __syncthreads();
-      stage_poll(xT, SP, D.xa + (size_t)(t + 1) * 2 * H * SX, 2 * H, SX, s0, sg >> 2);
+      stage_poll<16>(xT, SP, D.xa + (size_t)(t + 1) * 2 * H * SX, 2 * H, SX, s0, sg >> 2);
       __syncthreads();
       for (int u = warp; u < nquad * nchunks; u += NW) {
         const int qd = u / nchunks, ch = u - qd * nchunks;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT, 1) gru_bwd_kernel(GruDev D) {
         }
       }
       __syncthreads();
-      stage_poll(xT, SP, D.xb + (size_t)t * H * SX, H, SX, s0, sg >> 2);
+      stage_poll<8>(xT, SP, D.xb + (size_t)t * H * SX, H, SX, s0, sg >> 2);
       __syncthreads();
       for (int u = warp; u < nquad * nchunks; u += NW) {
         const int qd = u / nchunks, ch = u - qd * nchunks;

@@ -20,6 +20,8 @@
 #include "scratch.cuh"
 #include "recur.cuh"
 #include <vector>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -45,7 +47,10 @@ struct Launch {
   int ndirs, nblk;           // CTAs per direction
   int SG;                    // streams staged per group (multiple of 16)
   int SP;                    // staging stride in floats (SG + 4: conflict-free 128-bit reads)
+  int pgroups, SGP;          // tensor-core form: parallel stream groups per direction and streams per group
+  long long* timing;         // debug: per-CTA clock64 totals [nCTA][4] = {wait for CTA, own poll, wait for CTA's polls, units}; or NULL
 };
+#define RECUR_TICK(var) const long long var = (L.timing != nullptr && threadIdx.x == 0) ? clock64() : 0
 
 // ---------------------------------------------------------------- forward
 __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
   __syncthreads();
 
   const int ngroups = (S + SG - 1) / SG;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float* xrec = (R > 0) ? D.xb : D.xa;            // what feeds the gates: r (projected) or m
   const int my_s_in_chunk = lane_stream(lane);
 
@@ -102,9 +108,13 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
       const int sg = min(SG, SX - s0);                   // staged streams (multiple of 4)
       const int nchunks = (min(SG, S - s0) + 15) / 16;
       // ---------------- phase A: gates + cell update for own cells
+      RECUR_TICK(k0);
       __syncthreads();                                   // previous readers of xT are done
-      stage_poll(xT, SP, xrec + (size_t)tp * Rr * SX, Rr, SX, s0, sg >> 2);
+      RECUR_TICK(k1);
+      stage_poll<8>(xT, SP, xrec + (size_t)tp * Rr * SX, Rr, SX, s0, sg >> 2);
+      RECUR_TICK(k2);
       __syncthreads();
+      RECUR_TICK(k3);
       for (int u = warp; u < nc * nchunks; u += NW) {
         const int cl = u / nchunks, ch = u - cl * nchunks;
         const int s = s0 + ch * 16 + my_s_in_chunk;
@@ -116,8 +126,12 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
           for (int g = 0; g < 4; ++g) pre[g] = D.buf[row * D.ldb + g * C + c0 + cl];   // x*W_x^T + bias (issued early)
         }
         float acc[4][16], sum[4];
+        RECUR_TICK(u0);
         unit_dot<4>(acc, wA + (size_t)cl * 4 * Rr, Rr, Rr, xT, SP, ch * 16, lane);
+        RECUR_TICK(u1);
         unit_reduce<4>(acc, sum, lane);
+        RECUR_TICK(u2);
+        if (L.timing != nullptr && threadIdx.x == 0) { tacc[4] += u1 - u0; tacc[5] += u2 - u1; tacc[6] += u0 - k3; }
         if (active) {
           const float cprev = cst[cl * SXs + s];
           float yg = pre[0] + sum[0];
@@ -137,10 +151,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
           st_pub(D.xa + ((size_t)t * C + c0 + cl) * SX + s, ym);   // publish m(t): the store is the flag
         }
       }
+      if (L.timing != nullptr && threadIdx.x == 0) {
+        const long long k4 = clock64();
+        tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3;
+      }
       // ---------------- phase B: r(t) = m(t) W_rm^T for own projection rows
       if (R > 0) {
         __syncthreads();
-        stage_poll(xT, SP, D.xa + (size_t)t * C * SX, C, SX, s0, sg >> 2);
+        stage_poll<8>(xT, SP, D.xa + (size_t)t * C * SX, C, SX, s0, sg >> 2);
         __syncthreads();
         const int nru = (nr + 3) >> 2;
         for (int u = warp; u < nru * nchunks; u += NW) {
@@ -164,6 +182,8 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
       }
     }
   }
+  if (L.timing != nullptr && threadIdx.x == 0)
+    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
 }
 
 // ---------------------------------------------------------------- backward (BPTT, reference "version 1")
@@ -211,6 +231,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
   __syncthreads();
 
   const int ngroups = (S + SG - 1) / SG;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int my_s_in_chunk = lane_stream(lane);
   const int ocol = (R > 0) ? 7 * C : 6 * C;          // where out_diff was preloaded in dbuf (r or m columns)
 
@@ -224,9 +245,13 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
       const int sg = min(SG, SX - s0);
       const int nchunks = (min(SG, S - s0) + 15) / 16;
       // ---------------- stage dgifo(tn)  [4C][streams]
+      RECUR_TICK(k0);
       __syncthreads();
-      stage_poll(xT, SP, D.xa + (size_t)tn * G4 * SX, G4, SX, s0, sg >> 2);
+      RECUR_TICK(k1);
+      stage_poll<20>(xT, SP, D.xa + (size_t)tn * G4 * SX, G4, SX, s0, sg >> 2);
+      RECUR_TICK(k2);
       __syncthreads();
+      RECUR_TICK(k3);
       if (R > 0) {
         // phase B1: d_r(t) for own projection rows
         const int nru = (nr + 3) >> 2;
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
           }
         }
         __syncthreads();
-        stage_poll(xT, SP, D.xb + (size_t)t * R * SX, R, SX, s0, sg >> 2);
+        stage_poll<8>(xT, SP, D.xb + (size_t)t * R * SX, R, SX, s0, sg >> 2);
         __syncthreads();
       }
       // ---------------- d_m(t) for own cells, then the cell derivative chain
@@ -311,12 +336,20 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
           }
         }
       }
+      if (L.timing != nullptr && threadIdx.x == 0) {
+        const long long k4 = clock64();
+        tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3;
+      }
     }
   }
+  if (L.timing != nullptr && threadIdx.x == 0)
+    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
 }
 
+#include "lstm_mma.cuh"
+
 // ---------------------------------------------------------------- host side
-struct Plan { Launch L; size_t smem; size_t ws_bytes; };
+struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; };
 
 size_t ws_per_dir(int T, int S, int C, int R, bool bwd) {
   const size_t SX = (size_t)(S + 3) / 4 * 4;
@@ -324,8 +357,67 @@ size_t ws_per_dir(int T, int S, int C, int R, bool bwd) {
   return ((size_t)(T + 2) * da * SX + (size_t)(T + 2) * R * SX) * sizeof(float);
 }
 
+void fill_dir(DirDev& D, const aslp_lstm_dir_t& a) {
+  D.T = a.T; D.S = a.S; D.C = a.C; D.R = a.R; D.Rr = a.R > 0 ? a.R : a.C; D.reverse = a.reverse;
+  D.buf = a.buf; D.ldb = a.ldb; D.dbuf = a.dbuf; D.lddb = a.lddb;
+  D.w_r = a.w_r; D.ldwr = a.ldwr; D.w_rm = a.w_rm; D.ldwrm = a.ldwrm;
+  D.peep_i = a.peep_i; D.peep_f = a.peep_f; D.peep_o = a.peep_o; D.seq_len = a.seq_len_dev; D.clip = a.cell_clip;
+  D.SX = (a.S + 3) / 4 * 4;
+}
+
+// tensor-core form: pick the largest number of parallel stream groups whose per-CTA weight slice still fits the
+// register budget (more groups = fewer CTAs per chain = more cells per CTA, but proportionally less exchange traffic)
+int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
+  Launch& L = P->L;
+  P->mma = false;
+  L.ndirs = ndirs;
+  const int C = dirs[0].C, S = dirs[0].S;
+  for (int i = 0; i < ndirs; ++i)
+    if (dirs[i].R != 0 || dirs[i].C != C || dirs[i].S != S || C % 8 != 0) return ASLP_STATUS_INVALID_VALUE;
+  const int sms = aslp_num_sms();
+  for (int pg = (S + 7) / 8; pg >= 1; --pg) {
+    int SGP = (S + pg - 1) / pg;
+    SGP = SGP <= 8 ? 8 : (SGP + 15) / 16 * 16;
+    if ((pg - 1) * SGP >= S) continue;                    // would leave a group without streams
+    int nblk = sms / (ndirs * pg);
+    if (nblk < 1) continue;
+    if (nblk > C) nblk = C;
+    int cb = (C + nblk - 1) / nblk;
+    // fill the last 16-row MMA tile (fwd: 4 rows per cell, bwd: 1): same work per CTA, fewer CTAs in the exchange
+    cb = bwd ? (cb + 15) / 16 * 16 : (cb + 3) / 4 * 4;
+    if (cb > C) cb = C;
+    nblk = (C + cb - 1) / cb;
+    MmaChoice mc;
+    if (!mma_fits(C, cb, bwd, &mc)) continue;
+    int SG = SGP;
+    while (SG > 16 && (cb * SG > NT || mma_smem_floats(C, cb, SG, SGP, bwd) * sizeof(float) > 220 * 1024)) SG -= 16;
+    if (cb * SG > NT || mma_smem_floats(C, cb, SG, SGP, bwd) * sizeof(float) > 220 * 1024) continue;
+    L.nblk = nblk; L.pgroups = pg; L.SGP = SGP; L.SG = SG; L.SP = SG == 8 ? 8 : SG + 8;
+    size_t need_ws = 0;
+    char* wsp = (char*)ws;
+    for (int i = 0; i < ndirs; ++i) {
+      DirDev& D = L.d[i];
+      fill_dir(D, dirs[i]);
+      D.cb = cb; D.rb = 0;
+      const size_t da = bwd ? 4 * (size_t)C : (size_t)C;
+      D.xa = (float*)(wsp + need_ws);
+      need_ws += (size_t)(D.T + 2) * da * D.SX * sizeof(float);
+      D.xb = nullptr;
+    }
+    if (ws == nullptr || ws_bytes < need_ws) { aslp_set_last_error_msg("LSTM workspace too small", __FILE__, __LINE__); return ASLP_STATUS_INVALID_VALUE; }
+    P->smem = mma_smem_floats(C, cb, SG, SGP, bwd) * sizeof(float);
+    P->ws_bytes = need_ws;
+    P->mc = mc;
+    P->mma = true;
+    return 0;
+  }
+  return ASLP_STATUS_INVALID_VALUE;
+}
+
 int make_plan(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
+  P->mma = false;
+  L.pgroups = 1; L.SGP = 0;
   L.ndirs = ndirs;
   const int sms = aslp_num_sms();
   int nblk = sms / ndirs;
@@ -405,6 +497,7 @@ int init_exchange(cudaStream_t st, const Plan& P, bool bwd) {
 // launching stream around the cooperative launch only; resolved lazily in aslp_lstm_profile_read().
 struct ProfRec { cudaEvent_t a, b; bool bwd; };
 bool g_prof_on = false;
+long long* g_timing = nullptr;     // device buffer for the per-CTA phase clocks (debug hook), [grid][8]
 std::vector<ProfRec> g_prof;
 
 int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_t ws_bytes, bool bwd) {
@@ -417,17 +510,27 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
     ASLP_REQUIRE(!bwd || dirs[i].dbuf != nullptr);
   }
   Plan P;
-  int rc = make_plan(dirs, ndirs, bwd, ws, ws_bytes, &P);
+  // ASLP_LSTM_KERNEL=simt forces the SIMT contraction (tests run both forms); default: tensor-core form when it applies
+  const char* force = std::getenv("ASLP_LSTM_KERNEL");
+  const bool want_mma = !(force != nullptr && std::strcmp(force, "simt") == 0);
+  int rc = want_mma ? make_plan_mma(dirs, ndirs, bwd, ws, ws_bytes, &P) : ASLP_STATUS_INVALID_VALUE;
+  if (rc != 0) rc = make_plan(dirs, ndirs, bwd, ws, ws_bytes, &P);
   if (rc != 0) return rc;
+  if (force != nullptr && std::strcmp(force, "mma") == 0 && !P.mma) {
+    aslp_set_last_error_msg("ASLP_LSTM_KERNEL=mma but the tensor-core recurrence does not apply to this shape", __FILE__, __LINE__);
+    return ASLP_STATUS_INVALID_VALUE;
+  }
   rc = init_exchange(st, P, bwd);
   if (rc != 0) return rc;
-  void* kfn = bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel;
+  void* kfn = P.mma ? mma_pick_kernel(P.mc, bwd) : (bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel);
+  if (kfn == nullptr) { aslp_set_last_error_msg("no tensor-core recurrence kernel for this shape", __FILE__, __LINE__); return ASLP_STATUS_UNKNOWN_ERROR; }
   ASLP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+  P.L.timing = g_timing;
   void* args[] = {(void*)&P.L};
   // cooperative launch: guarantees all CTAs are co-resident (the polling exchange needs that)
   ProfRec rec;
   if (g_prof_on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); rec.bwd = bwd; cudaEventRecord(rec.a, st); }
-  ASLP_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(P.L.nblk * ndirs), dim3(NT), args, P.smem, st));
+  ASLP_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(P.L.nblk * P.L.pgroups * ndirs), dim3(NT), args, P.smem, st));
   ASLP_COUNT_LAUNCH();
   if (g_prof_on) { cudaEventRecord(rec.b, st); g_prof.push_back(rec); }
   return 0;
@@ -446,6 +549,7 @@ int aslp_lstm_profile(int enable) {
   g_prof.clear();
   return 0;
 }
+int aslp_lstm_debug_timing(long long* dev_buf) { g_timing = dev_buf; return 0; }
 int aslp_lstm_profile_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches) {
   double f = 0, b = 0; int nf = 0, nb = 0;
   for (ProfRec& r : g_prof) {

@@ -1,0 +1,499 @@
+// lstm_mma.cuh -- tensor-core form of the persistent LSTM recurrence (included by lstm.cu inside its anonymous
+// namespace, after DirDev / Launch).  Same exchange protocol and buffer layout as the SIMT kernels in lstm.cu; what
+// changes is the partitioning and the per-step contraction:
+//   * the streams of a minibatch are independent, so they are split into `pgroups` parallel stream groups; a CHAIN is
+//     (direction, stream group) and owns nblk CTAs that partition the cells.  A CTA therefore gathers only its
+//     group's columns of the exchange vector each step: the all-gather volume through L2 -- what bounded the first
+//     versions of this kernel (every CTA re-reading the full [dim][S] vector, 2.6 MB fwd / 10.5 MB bwd per step at
+//     cfg3) -- drops by the number of groups;
+//   * the CTA's slice of the recurrent weights lives in REGISTERS for the whole sequence as fp32 values in
+//     mma.m16n8k8 A-fragment layout (rows of the slice = M); 8 streams are the N dimension; the contraction dimension
+//     is split over the 8 warps.  Operands are split into tf32 hi/lo halves on the fly (3xTF32: lo*hi + hi*lo + hi*hi,
+//     fp32-grade).  The 8 partial tiles meet in shared memory and one thread per (cell, stream) finishes the sum and
+//     runs the whole cell update in registers;
+//   * the non-recurrent inputs of the NEXT step (x*W_x^T + bias forward; the forward activations backward) are
+//     prefetched before the exchange wait, so no HBM latency sits on the recurrent chain.
+// tcgen05 does not fit here: a CTA owns 8..48 output rows and 8 streams, and the chain is latency-bound, so the
+// warp-level mma.sync with register-resident operands is the shortest path from "exchange landed" to "next value
+// published".  Only the single-exchange form is handled (R == 0: plain LSTM, or the folded projection W_gifo_r W_r_m).
+#pragma once
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 4 ? 1 : (MT_ >= 2 ? 2 : 4); };   // k-interleaved accumulator sets
+
+// part_w[stream][NPP] = Wslice[MT_*16 rows, k-slice of this warp] * X[k-slice, streams]   (8 streams per n-tile)
+// wa: A fragments (a0: row g, k tig; a1: row g+8, k tig; a2: row g, k tig+4; a3: row g+8, k tig+4), fp32.
+// Several independent accumulators per m-tile (hi*hi apart from the two cross terms, and k-interleaved) keep the
+// dependent-MMA chains short: the chain, not the issue rate, is what a single step waits for.
+template <int MT_, int KT_>
+__device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], const float* xT, int SP, int kbase, int Kdim,
+                                             int ntiles, float* part_w, int lane) {
+  constexpr int NPP = MT_ * 16 + 4;
+  constexpr int AK = MmaAcc<MT_>::K;
+  const int g = lane >> 2, tig = lane & 3;
+  for (int nt = 0; nt < ntiles; ++nt) {
+    float acc[MT_][AK][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+      for (int a = 0; a < AK; ++a)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { acc[mt][a][h][0] = acc[mt][a][h][1] = acc[mt][a][h][2] = acc[mt][a][h][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < KT_; ++kt) {
+      {
+        // no branch on the warp's real k-tile count: tiles past it carry zero weights and re-read the last valid rows, so
+        // the loads of the whole unrolled loop can be hoisted ahead of the first MMA
+        const float* xp = xT + (size_t)(min(kbase + kt * 8, Kdim - 8) + tig) * SP + nt * 8 + g;
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(xp[0], bh0, bl0);
+        split_tf32(xp[4 * SP], bh1, bl1);
+#pragma unroll
+        for (int mt = 0; mt < MT_; ++mt) {
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_tf32(wa[mt][kt][q], ah[q], al[q]);
+          mma_tf32(acc[mt][kt % AK][1], al, bh0, bh1);
+          mma_tf32(acc[mt][kt % AK][1], ah, bl0, bl1);
+          mma_tf32(acc[mt][kt % AK][0], ah, bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt) {
+      float c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo = 0.f, hi = 0.f;
+#pragma unroll
+        for (int a = 0; a < AK; ++a) { lo += acc[mt][a][1][q]; hi += acc[mt][a][0][q]; }
+        c[q] = lo + hi;                                  // small terms first
+      }
+      // c0: (row g, stream 2tig)  c1: (g, 2tig+1)  c2: (g+8, 2tig)  c3: (g+8, 2tig+1); stored stream-major
+      float* p0 = part_w + (size_t)(nt * 8 + 2 * tig) * NPP + mt * 16 + g;
+      p0[0] = c[0]; p0[NPP] = c[1]; p0[8] = c[2]; p0[NPP + 8] = c[3];
+    }
+  }
+}
+
+// Same contraction with the A fragments read from shared memory in fragment order ws[kt][mt][q][lane] (conflict-free
+// 32-word rows) instead of registers: the backward slice (K = 4C) needs 80+ registers per thread at cfg3, which together
+// with the accumulators pushed the kernel into spills whose reloads sat on the recurrent chain.  kt runs over ktp tiles
+// (a multiple of 4, zero-filled past the warp's real count).
+template <int MT_, int KTP_>     // KTP_ > 0: compile-time tile count (fully unrolled, loads hoisted); 0: run-time ktp
+__device__ __forceinline__ void mma_contract_ws(const float* ws, int ktp, const float* xT, int SP, int kbase, int Kdim,
+                                                int ntiles, float* part_w, int lane) {
+  constexpr int NPP = MT_ * 16 + 4;
+  constexpr int AK = 4;
+  const int g = lane >> 2, tig = lane & 3;
+  for (int nt = 0; nt < ntiles; ++nt) {
+    float acc[MT_][AK][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+      for (int a = 0; a < AK; ++a)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { acc[mt][a][h][0] = acc[mt][a][h][1] = acc[mt][a][h][2] = acc[mt][a][h][3] = 0.f; }
+    const int kend = KTP_ > 0 ? KTP_ : ktp;
+#pragma unroll (KTP_ > 0 ? KTP_ / AK : 1)
+    for (int kb = 0; kb < kend; kb += AK) {
+#pragma unroll
+      for (int a = 0; a < AK; ++a) {
+        const int kt = kb + a;
+        const float* xp = xT + (size_t)(min(kbase + kt * 8, Kdim - 8) + tig) * SP + nt * 8 + g;
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(xp[0], bh0, bl0);
+        split_tf32(xp[4 * SP], bh1, bl1);
+#pragma unroll
+        for (int mt = 0; mt < MT_; ++mt) {
+          const float* wp = ws + ((size_t)(kt * MT_ + mt) * 4) * 32 + lane;
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_tf32(wp[q * 32], ah[q], al[q]);
+          mma_tf32(acc[mt][a][1], al, bh0, bh1);
+          mma_tf32(acc[mt][a][1], ah, bl0, bl1);
+          mma_tf32(acc[mt][a][0], ah, bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt) {
+      float c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo = 0.f, hi = 0.f;
+#pragma unroll
+        for (int a = 0; a < AK; ++a) { lo += acc[mt][a][1][q]; hi += acc[mt][a][0][q]; }
+        c[q] = lo + hi;
+      }
+      float* p0 = part_w + (size_t)(nt * 8 + 2 * tig) * NPP + mt * 16 + g;
+      p0[0] = c[0]; p0[NPP] = c[1]; p0[8] = c[2]; p0[NPP + 8] = c[3];
+    }
+  }
+}
+
+struct MmaCta {
+  int dir, pg, blk;         // chain = (dir, pg); blk = cell block inside the chain
+  int sbeg, send;           // streams of this chain
+};
+__device__ __forceinline__ MmaCta mma_cta(const Launch& L) {
+  MmaCta c;
+  const int per_dir = L.nblk * L.pgroups;
+  c.dir = blockIdx.x / per_dir;
+  const int rem = blockIdx.x - c.dir * per_dir;
+  c.pg = rem / L.nblk;
+  c.blk = rem - c.pg * L.nblk;
+  c.sbeg = c.pg * L.SGP;
+  c.send = min(L.d[c.dir].S, c.sbeg + L.SGP);
+  return c;
+}
+
+// ---------------------------------------------------------------- forward
+template <int MT_, int KT_>
+__global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
+  extern __shared__ float smem[];
+  const MmaCta cta = mma_cta(L);
+  const DirDev& D = L.d[cta.dir];
+  const int T = D.T, S = D.S, C = D.C, SX = D.SX;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SP = L.SP, SG = L.SG;
+  constexpr int NPP = MT_ * 16 + 4;
+  const int K = C;
+  const int c0 = cta.blk * D.cb, nc = max(0, min(D.cb, C - c0));
+  if (nc == 0 || cta.sbeg >= S) return;                  // nobody waits on a CTA that owns no cells / no streams
+
+  float* xT = smem;                                      // [K][SP]       m(t-1) of this chain's streams, stream-minor
+  float* part = xT + (size_t)K * SP;                     // [NW][SG][NPP] per-warp partial gate sums
+  float* cst = part + (size_t)NW * SG * NPP;             // [cb][SGP]     c(t-1)
+  float* pst = cst + (size_t)D.cb * L.SGP;               // [3][cb]       peepholes
+
+  // ---- one-time: weight slice -> A fragments (row n of the slice = cell n/4, gate n%4)
+  const int ktiles = K >> 3, ktw = (ktiles + NW - 1) / NW;
+  const int kt0 = warp * ktw, nkt = max(0, min(ktw, ktiles - kt0));
+  float wa[MT_][KT_][4];
+  {
+    const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+      for (int kt = 0; kt < KT_; ++kt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = mt * 16 + g + (q & 1) * 8, cl = n >> 2, gate = n & 3;
+          const int k = (kt0 + kt) * 8 + tig + (q >> 1) * 4;
+          wa[mt][kt][q] = (kt < nkt && cl < nc) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + k] : 0.f;
+        }
+  }
+  const int slot0 = D.reverse ? T + 1 : 0;
+  for (int i = threadIdx.x; i < D.cb * L.SGP; i += NT) {
+    const int cl = i / L.SGP, s = cta.sbeg + (i - cl * L.SGP);
+    cst[i] = (cl < nc && s < cta.send) ? D.buf[((size_t)slot0 * S + s) * D.ldb + 4 * C + c0 + cl] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 3 * D.cb; i += NT) {
+    const int which = i / D.cb, cl = i - which * D.cb;
+    const float* p = which == 0 ? D.peep_i : (which == 1 ? D.peep_f : D.peep_o);
+    pst[i] = (cl < nc) ? p[c0 + cl] : 0.f;
+  }
+  for (int i = threadIdx.x; i < K * SP; i += NT) xT[i] = 0.f;
+  __syncthreads();
+
+  // ---- the (cell, stream-in-group) item this thread finishes every step
+  const int s_local = threadIdx.x % SG, cl = threadIdx.x / SG;
+  const bool owner = cl < nc;
+  const int ngroups = (cta.send - cta.sbeg + SG - 1) / SG;         // sequential staging groups inside the chain
+  const int nitems = T * ngroups;
+  const int reverse = D.reverse, ldb = D.ldb;
+  const float clip = D.clip;
+  const int* seq_len = D.seq_len;
+  float* const buf = D.buf;
+  float* const xa = D.xa;
+  const float pi = owner ? pst[cl] : 0.f, pf = owner ? pst[D.cb + cl] : 0.f, po = owner ? pst[2 * D.cb + cl] : 0.f;
+  // step-invariant staging share when the chain has one staging group (the common case)
+  const int sg4_0 = (min(cta.sbeg + SG, SX) - cta.sbeg) >> 2;
+  constexpr int SB = (KT_ + 1) / 2;                               // items per thread when a group is 8 streams wide
+  const StageDesc sd = stage_prepare<SB>(K, SX, SP, cta.sbeg, sg4_0);
+  const bool hoisted = (ngroups == 1) && sd.fast;
+  const size_t slot = (size_t)K * SX;
+  auto item_row = [&](int it, int& t, int& s0) {
+    if (ngroups == 1) { t = reverse ? T - it : 1 + it; s0 = cta.sbeg; return; }
+    const int step = it / ngroups, grp = it - step * ngroups;
+    t = reverse ? T - step : 1 + step;
+    s0 = cta.sbeg + grp * SG;
+  };
+  // x*W_x^T + bias of a future item: pulled into L2 two items ahead (no register, no scoreboard), read into registers
+  // right after the exchange wait of its own step, consumed after the contraction
+  auto pre_ptr = [&](int it) -> const float* {
+    int t, s0; item_row(it, t, s0);
+    const int s = s0 + s_local;
+    return (owner && it < nitems && s < cta.send) ? buf + ((size_t)t * S + s) * ldb + c0 + cl : nullptr;
+  };
+  auto warm = [&](int it) {
+    const float* p = pre_ptr(it);
+    if (p != nullptr) { prefetch_l2(p); prefetch_l2(p + C); prefetch_l2(p + 2 * C); prefetch_l2(p + 3 * C); }
+  };
+  warm(0); warm(1);
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? T + 1 : 0) * slot);
+
+  for (int it = 0; it < nitems; ++it) {
+    int t, s0; item_row(it, t, s0);
+    const int tp = reverse ? t + 1 : t - 1;
+    const int nstr = min(SG, cta.send - s0);             // streams of this staging group
+    RECUR_TICK(k0);
+    long long* dbg = (L.timing != nullptr && threadIdx.x == 0) ? &tacc[5] : nullptr;
+    if (hoisted) stage_complete<SB>(sd, xT, xa + (size_t)tp * slot, dbg);     // copies were issued at the end of the previous step
+    else stage_poll<8>(xT, SP, xa + (size_t)tp * slot, K, SX, s0, (min(s0 + SG, SX) - s0) >> 2, dbg);
+    float pre[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const float* p = pre_ptr(it);
+      if (p != nullptr) { pre[0] = p[0]; pre[1] = p[C]; pre[2] = p[2 * C]; pre[3] = p[3 * C]; }
+    }
+    RECUR_TICK(k1);
+    __syncthreads();
+    RECUR_TICK(k2);
+    mma_contract<MT_, KT_>(wa, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
+    RECUR_TICK(k3);
+    __syncthreads();
+    RECUR_TICK(k4);
+    const int s = s0 + s_local;
+    if (owner && s_local < nstr) {
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const float4 p = *reinterpret_cast<const float4*>(part + ((size_t)w * SG + s_local) * NPP + cl * 4);
+        sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+      }
+      const size_t row = (size_t)t * S + s;
+      const int ci = cl * L.SGP + (s - cta.sbeg);
+      const float cprev = cst[ci];
+      float yg = pre[0] + sum.x;
+      float yi = pre[1] + sum.y + cprev * pi;
+      float yf = pre[2] + sum.z + cprev * pf;
+      float yo = pre[3] + sum.w;
+      yi = ref_sigmoid(yi); yf = ref_sigmoid(yf); yg = ref_tanh(yg);
+      float yc = yg * yi + cprev * yf;
+      yc = fminf(fmaxf(yc, -clip), clip);
+      float yh = ref_tanh(yc);
+      yo = ref_sigmoid(yo + yc * po);
+      float ym = yh * yo;
+      if (seq_len != nullptr && t > seq_len[s]) { yg = yi = yf = yo = yc = yh = ym = 0.f; }
+      st_pub(xa + ((size_t)t * C + c0 + cl) * SX + s, ym);       // publish m(t) first: it is what the other SMs wait for
+      if (L.timing != nullptr && threadIdx.x == 0) tacc[7] += clock64() - k4;
+      float* o = buf + row * ldb + c0 + cl;
+      o[0] = yg; o[C] = yi; o[2 * C] = yf; o[3 * C] = yo; o[4 * C] = yc; o[5 * C] = yh; o[6 * C] = ym;
+      cst[ci] = yc;
+    }
+    // next step's exchange copies: after the bookkeeping stores (about one store-to-L2 latency after the publish, so
+    // the first round usually finds the data), before the prefetch address arithmetic; xT is free (contraction done)
+    if (hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    warm(it + 2);
+    if (L.timing != nullptr && threadIdx.x == 0) {
+      const long long k5 = clock64();
+      tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3; tacc[4] += k5 - k4;
+    }
+  }
+  if (L.timing != nullptr && threadIdx.x == 0)
+    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
+}
+
+// ---------------------------------------------------------------- backward (R == 0 form)
+// KT_ only sizes the staging share here (the weights live in shared memory)
+template <int MT_, int KT_>
+__global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
+  extern __shared__ float smem[];
+  const MmaCta cta = mma_cta(L);
+  const DirDev& D = L.d[cta.dir];
+  const int T = D.T, S = D.S, C = D.C, SX = D.SX;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SP = L.SP, SG = L.SG;
+  constexpr int NPP = MT_ * 16 + 4;
+  const int K = 4 * C;
+  const int c0 = cta.blk * D.cb, nc = max(0, min(D.cb, C - c0));
+  if (nc == 0 || cta.sbeg >= S) return;
+
+  float* xT = smem;                                      // [4C][SP]      dgifo(successor step) of this chain's streams
+  float* part = xT + (size_t)K * SP;                     // [NW][SG][NPP]
+  float* st = part + (size_t)NW * SG * NPP;              // [3][cb][SGP]  d_c, d_i, d_f of the successor step
+  float* pst = st + (size_t)3 * D.cb * L.SGP;            // [3][cb]
+  // ---- weight slice: column c0+n of W (d_m[c] = sum_q dgifo[q] W[q][c]); row n of the slice = own cell n.
+  // Stored per warp in A-fragment order [kt][mt][q][lane] (a0: row g, k tig; a1: row g+8; a2: k tig+4; a3: both)
+  const int ktiles = K >> 3, ktw = (ktiles + NW - 1) / NW;
+  const int ktp = (ktw + 3) & ~3;
+  const int kt0 = warp * ktw, nkt = max(0, min(ktw, ktiles - kt0));
+  float* wsm = pst + ((3 * D.cb + 3) & ~3);              // [NW][ktp][MT_][4][32]
+  float* ws = wsm + (size_t)warp * ktp * MT_ * 128;
+  {
+    const int g = lane >> 2, tig = lane & 3;
+    for (int kt = 0; kt < ktp; ++kt)
+#pragma unroll
+      for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = mt * 16 + g + (q & 1) * 8;
+          const int k = (kt0 + kt) * 8 + tig + (q >> 1) * 4;
+          ws[((size_t)(kt * MT_ + mt) * 4 + q) * 32 + lane] = (kt < nkt && n < nc) ? D.w_r[(size_t)k * D.ldwr + c0 + n] : 0.f;
+        }
+  }
+  for (int i = threadIdx.x; i < 3 * D.cb * L.SGP; i += NT) st[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * D.cb; i += NT) {
+    const int which = i / D.cb, cl = i - which * D.cb;
+    const float* p = which == 0 ? D.peep_i : (which == 1 ? D.peep_f : D.peep_o);
+    pst[i] = (cl < nc) ? p[c0 + cl] : 0.f;
+  }
+  for (int i = threadIdx.x; i < K * SP; i += NT) xT[i] = 0.f;
+  __syncthreads();
+
+  const int s_local = threadIdx.x % SG, cl = threadIdx.x / SG;
+  const bool owner = cl < nc;
+  const int cc = c0 + (owner ? cl : 0);
+  const int ngroups = (cta.send - cta.sbeg + SG - 1) / SG;
+  const int nitems = T * ngroups;
+  const int plane = D.cb * L.SGP;
+  const int reverse = D.reverse, ldb = D.ldb, lddb = D.lddb;
+  float* const buf = D.buf;
+  float* const dbuf = D.dbuf;
+  float* const xa = D.xa;
+  const float pi = owner ? pst[cl] : 0.f, pf = owner ? pst[D.cb + cl] : 0.f, po = owner ? pst[2 * D.cb + cl] : 0.f;
+  const int sg4_0 = (min(cta.sbeg + SG, SX) - cta.sbeg) >> 2;
+  constexpr int SB = (KT_ + 1) / 2;
+  const StageDesc sd = stage_prepare<SB>(K, SX, SP, cta.sbeg, sg4_0);
+  const bool hoisted = (ngroups == 1) && sd.fast;
+  const size_t slot = (size_t)K * SX;
+  // backward visits time in the opposite order of the forward pass of this direction
+  auto item_row = [&](int it, int& t, int& s0) {
+    if (ngroups == 1) { t = reverse ? 1 + it : T - it; s0 = cta.sbeg; return; }
+    const int step = it / ngroups, grp = it - step * ngroups;
+    t = reverse ? 1 + step : T - step;
+    s0 = cta.sbeg + grp * SG;
+  };
+  // forward activations of a future item: into L2 two items ahead, into registers after the exchange wait of their step
+  auto warm = [&](int it) {
+    if (!owner || it >= nitems) return;
+    int t, s0; item_row(it, t, s0);
+    const int s = s0 + s_local;
+    if (s >= cta.send) return;
+    const int tn = reverse ? t - 1 : t + 1, tp = reverse ? t + 1 : t - 1;
+    const float* y = buf + ((size_t)t * S + s) * ldb + cc;
+    prefetch_l2(y); prefetch_l2(y + C); prefetch_l2(y + 2 * C); prefetch_l2(y + 3 * C); prefetch_l2(y + 5 * C);
+    prefetch_l2(buf + ((size_t)tp * S + s) * ldb + 4 * C + cc);
+    prefetch_l2(buf + ((size_t)tn * S + s) * ldb + 2 * C + cc);
+    prefetch_l2(dbuf + ((size_t)t * S + s) * lddb + 6 * C + cc);
+  };
+  warm(0); warm(1);
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? 0 : T + 1) * slot);
+
+  for (int it = 0; it < nitems; ++it) {
+    int t, s0; item_row(it, t, s0);
+    const int tn = reverse ? t - 1 : t + 1, tp = reverse ? t + 1 : t - 1;
+    const int nstr = min(SG, cta.send - s0);
+    const int s = s0 + s_local;
+    RECUR_TICK(k0);
+    long long* dbg = (L.timing != nullptr && threadIdx.x == 0) ? &tacc[5] : nullptr;
+    if (hoisted) stage_complete<SB>(sd, xT, xa + (size_t)tn * slot, dbg);
+    else stage_poll<20>(xT, SP, xa + (size_t)tn * slot, K, SX, s0, (min(s0 + SG, SX) - s0) >> 2, dbg);
+    float yv[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // g, i, f, o, h at t ; c at the forward predecessor ; f at the successor
+    float od = 0.f;                                      // out_diff share of d_m (preloaded in the m columns of dbuf)
+    if (owner && s_local < nstr) {
+      const float* y = buf + ((size_t)t * S + s) * ldb + cc;
+      yv[0] = y[0]; yv[1] = y[C]; yv[2] = y[2 * C]; yv[3] = y[3 * C]; yv[4] = y[5 * C];
+      yv[5] = buf[((size_t)tp * S + s) * ldb + 4 * C + cc];
+      yv[6] = buf[((size_t)tn * S + s) * ldb + 2 * C + cc];
+      od = dbuf[((size_t)t * S + s) * lddb + 6 * C + cc];
+    }
+    RECUR_TICK(k1);
+    __syncthreads();
+    RECUR_TICK(k2);
+    constexpr int KTP = KT_ <= 32 ? ((KT_ + 3) & ~3) : 0;     // exact tile count known at compile time up to 32 tiles per warp
+    if (KTP > 0 && ktp == KTP) mma_contract_ws<MT_, KTP>(ws, ktp, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
+    else mma_contract_ws<MT_, 0>(ws, ktp, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
+    RECUR_TICK(k3);
+    __syncthreads();
+    RECUR_TICK(k4);
+    if (owner && s_local < nstr) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sum += part[((size_t)w * SG + s_local) * NPP + cl];
+      const size_t row = (size_t)t * S + s;
+      const int si = cl * L.SGP + (s - cta.sbeg);
+      const float yg = yv[0], yi = yv[1], yf = yv[2], yo = yv[3], yh = yv[4], c_prev = yv[5], yf_next = yv[6];
+      const float dm = sum + od;
+      const float dc_n = st[si], di_n = st[plane + si], df_n = st[2 * plane + si];
+      float dh = dm * yo;  dh = (1.0f - yh * yh) * dh;                 // DiffTanh(y_h, d_h)
+      float dout = dm * yh;  dout = yo * (1.0f - yo) * dout;           // DiffSigmoid(y_o, d_o)
+      const float dc = dh + dc_n * yf_next + di_n * pi + df_n * pf + dout * po;
+      float df = dc * c_prev;  df = yf * (1.0f - yf) * df;
+      float di = dc * yg;      di = yi * (1.0f - yi) * di;
+      float dg = dc * yi;      dg = (1.0f - yg * yg) * dg;
+      float* x = xa + ((size_t)t * K + cc) * SX + s;                   // publish dgifo(t) first
+      st_pub(x, dg); st_pub(x + (size_t)C * SX, di); st_pub(x + (size_t)2 * C * SX, df); st_pub(x + (size_t)3 * C * SX, dout);
+      if (L.timing != nullptr && threadIdx.x == 0) tacc[7] += clock64() - k4;
+      float* d = dbuf + row * lddb + cc;
+      d[0] = dg; d[C] = di; d[2 * C] = df; d[3 * C] = dout; d[4 * C] = dc; d[5 * C] = dh; d[6 * C] = dm;
+      st[si] = dc; st[plane + si] = di; st[2 * plane + si] = df;
+    }
+    if (hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    warm(it + 2);
+    if (L.timing != nullptr && threadIdx.x == 0) {
+      const long long k5 = clock64();
+      tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3; tacc[4] += k5 - k4;
+    }
+  }
+  if (L.timing != nullptr && threadIdx.x == 0)
+    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
+}
+
+// ---------------------------------------------------------------- planning + dispatch
+struct MmaChoice { int mt, kt; };
+
+inline int mma_rows(int cb, bool bwd) { return bwd ? cb : 4 * cb; }          // rows of the per-CTA weight slice
+inline int mma_kdim(int C, bool bwd) { return bwd ? 4 * C : C; }
+inline size_t mma_smem_floats(int C, int cb, int SG, int SGP, bool bwd) {
+  const int SP = SG == 8 ? 8 : SG + 8;
+  const size_t mt = (size_t)(mma_rows(cb, bwd) + 15) / 16;
+  size_t fl = (size_t)mma_kdim(C, bwd) * SP + (size_t)NW * SG * (mt * 16 + 4) + (size_t)(bwd ? 3 : 1) * cb * SGP + 3 * (size_t)cb;
+  if (bwd) {                                             // weight fragments in shared memory
+    const size_t ktw = ((size_t)mma_kdim(C, bwd) / 8 + NW - 1) / NW, ktp = (ktw + 3) & ~(size_t)3;
+    fl += 4 + (size_t)NW * ktp * mt * 128;
+  }
+  return fl;
+}
+// register budget: MT*KT A fragments of 4 fp32 each
+inline bool mma_fits(int C, int cb, bool bwd, MmaChoice* ch) {
+  const int mt = (mma_rows(cb, bwd) + 15) / 16;
+  const int kt = ((mma_kdim(C, bwd) / 8) + NW - 1) / NW;
+  if (bwd) { if (!(mt <= 2 && kt <= 64)) return false; }   // weights in shared memory: only the capacity check of the planner limits K
+  else     { if (!(mt <= 4 && kt <= 16 && mt * (kt <= 2 ? 2 : kt <= 5 ? 5 : kt <= 8 ? 8 : kt <= 12 ? 12 : 16) <= 30)) return false; }
+  ch->mt = mt; ch->kt = kt;
+  return true;
+}
+
+template <int MT_, int KT_> inline void* mma_fwd_ptr() { return (void*)lstm_fwd_mma_kernel<MT_, KT_>; }
+template <int MT_, int KT_> inline void* mma_bwd_ptr() { return (void*)lstm_bwd_mma_kernel<MT_, KT_>; }
+
+inline void* mma_pick_kernel(const MmaChoice& c, bool bwd) {
+  if (bwd) {                                             // KT_ = staging share bound (items per thread = KT_/2 at 8 streams)
+    if (c.mt == 1) { if (c.kt <= 8) return mma_bwd_ptr<1, 8>(); if (c.kt <= 20) return mma_bwd_ptr<1, 20>(); if (c.kt <= 32) return mma_bwd_ptr<1, 32>(); return mma_bwd_ptr<1, 64>(); }
+    if (c.kt <= 8) return mma_bwd_ptr<2, 8>(); if (c.kt <= 20) return mma_bwd_ptr<2, 20>(); if (c.kt <= 32) return mma_bwd_ptr<2, 32>(); return mma_bwd_ptr<2, 64>();
+  }
+#define ASLP_FWD_ROW(MTv)                                        \
+  if (c.mt == MTv) {                                             \
+    if (c.kt <= 2) return mma_fwd_ptr<MTv, 2>();                 \
+    if (c.kt <= 5) return mma_fwd_ptr<MTv, 5>();                 \
+    if (MTv * 8 <= 30 && c.kt <= 8) return mma_fwd_ptr<MTv, (MTv * 8 <= 30 ? 8 : 2)>();     \
+    if (MTv * 12 <= 30 && c.kt <= 12) return mma_fwd_ptr<MTv, (MTv * 12 <= 30 ? 12 : 2)>();  \
+    if (MTv * 16 <= 30 && c.kt <= 16) return mma_fwd_ptr<MTv, (MTv * 16 <= 30 ? 16 : 2)>();  \
+  }
+  ASLP_FWD_ROW(1) ASLP_FWD_ROW(2) ASLP_FWD_ROW(3) ASLP_FWD_ROW(4)
+#undef ASLP_FWD_ROW
+  return nullptr;
+}

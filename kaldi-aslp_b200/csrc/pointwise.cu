@@ -202,16 +202,35 @@ __global__ void col_reduce_partial_kernel(float* partial, const float* a, int ld
     *reinterpret_cast<float4*>(dst) = acc;
   }
 }
-__global__ void col_reduce_final_kernel(float* vec, const float* partial, int chunks, int cols, float alpha, float beta, float clip) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// 32 columns x 8 chunk-lanes per block: each thread sums every 8th partial row with 4 independent accumulators (the
+// one-thread-per-column form was a serial chain of `chunks` dependent L2 loads), fixed order -> deterministic
+__global__ void __launch_bounds__(256) col_reduce_final_kernel(float* vec, const float* partial, int chunks, int cols, float alpha, float beta, float clip) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   const int ldp = ((cols + 3) >> 2) << 2;
-  float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += partial[(size_t)k * ldp + c];
-  float v = alpha * s;
-  if (beta != 0.f) v += beta * vec[c];
-  if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
-  vec[c] = v;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < cols) {
+    int k = kl;
+    for (; k + 24 < chunks; k += 32) {
+      s0 += partial[(size_t)k * ldp + c];
+      s1 += partial[(size_t)(k + 8) * ldp + c];
+      s2 += partial[(size_t)(k + 16) * ldp + c];
+      s3 += partial[(size_t)(k + 24) * ldp + c];
+    }
+    for (; k < chunks; k += 8) s0 += partial[(size_t)k * ldp + c];
+  }
+  red[kl][cl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (kl == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][cl];
+    float v = alpha * s;
+    if (beta != 0.f) v += beta * vec[c];
+    if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+    vec[c] = v;
+  }
 }
 
 int col_reduce(cudaStream_t st, bool dot, float* vec, const float* a, int lda, const float* b, int ldb, int rows, int cols,
@@ -230,7 +249,7 @@ int col_reduce(cudaStream_t st, bool dot, float* vec, const float* a, int lda, c
   if (dot) col_reduce_partial_kernel<true><<<grid, 256, 0, st>>>(partial, a, lda, b, ldb, rows, cols, rows_per_chunk);
   else col_reduce_partial_kernel<false><<<grid, 256, 0, st>>>(partial, a, lda, b, ldb, rows, cols, rows_per_chunk);
   ASLP_CHECK_LAUNCH();
-  col_reduce_final_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(vec, partial, chunks, cols, alpha, beta, clip);
+  col_reduce_final_kernel<<<aslp_div_up(cols, 32), 256, 0, st>>>(vec, partial, chunks, cols, alpha, beta, clip);
   ASLP_CHECK_LAUNCH();
   return 0;
 }

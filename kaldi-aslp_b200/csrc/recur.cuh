@@ -26,33 +26,140 @@ __device__ __forceinline__ void st_pub(float* p, float v) {
 }
 
 // stage X[k][s0 .. s0+SG) (global, stream-minor, stride SX) into xT[k][SP]; polls until produced.
-// All loads of a batch are issued before any is checked, so one L2 round trip covers the batch.
-__device__ __forceinline__ void stage_poll(float* xT, int SP, const float* g, int K, int SX, int s0, int sg4) {
-  constexpr int BATCH = 8;
+// The copies are cp.async.cg (L2 -> shared memory, no registers, no L1), so a thread can have its whole share of the
+// exchange vector in flight at once; it then inspects what landed in shared memory and re-issues only the items that
+// still show the sentinel.  A round therefore costs ONE L2 round trip however many items it covers (checking item by
+// item with register loads serialised a round trip per item once the producers were done, and the registers the
+// in-flight data needed collided with the register-resident weights of the tensor-core form).
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int BATCH>
+__device__ __forceinline__ void stage_poll(float* xT, int SP, const float* g, int K, int SX, int s0, int sg4,
+                                           long long* dbg = nullptr) {   // dbg (timing builds): [0] += rounds, [1] += first-round ticks
+  static_assert(BATCH <= 32, "pending mask is 32 bits");
   const int total = K * sg4;
-  for (int base = 0; base < total; base += NT * BATCH) {
-    float4 v[BATCH];
-    const float* src[BATCH];
-    int dst[BATCH];
+  if (NT % sg4 == 0) {
+    // a thread's items are a constant stride apart (same stream quad, every (NT/sg4)-th row): no per-item address state
+    const int kstep = NT / sg4;
+    const size_t sstride = (size_t)kstep * SX;
+    const int dstride = kstep * SP;
+    for (int base = 0; base < total; base += NT * BATCH) {
+      const int i0 = base + threadIdx.x;
+      const int k0 = i0 / sg4, q = i0 - k0 * sg4;
+      const float* src0 = g + (size_t)k0 * SX + s0 + q * 4;
+      float* dst0 = xT + k0 * SP + q * 4;
+      unsigned pending = 0;
 #pragma unroll
-    for (int j = 0; j < BATCH; ++j) {
-      const int i = base + j * NT + threadIdx.x;
-      const int ii = i < total ? i : 0;
-      const int k = ii / sg4, q = ii - k * sg4;
-      src[j] = g + (size_t)k * SX + s0 + q * 4;
-      dst[j] = i < total ? k * SP + q * 4 : -1;
-      if (dst[j] >= 0) v[j] = ld_vol4(src[j]);
-    }
+      for (int j = 0; j < BATCH; ++j)
+        if (i0 + j * NT < total) { cp_async16(dst0 + j * dstride, src0 + j * sstride); pending |= 1u << j; }
+      unsigned rounds = 0;
+      const long long tq0 = dbg != nullptr ? clock64() : 0;
+      while (pending != 0) {
+        cp_async_wait_all();
+        if (dbg != nullptr) { if (rounds == 0) dbg[1] += clock64() - tq0; dbg[0] += 1; }
+        unsigned still = 0;
 #pragma unroll
-    for (int j = 0; j < BATCH; ++j) {
-      if (dst[j] >= 0) {
-        unsigned n = 0;
-        while (has_sentinel(v[j])) { v[j] = ld_vol4(src[j]); if (++n > POLL_LIMIT) __trap(); }
-        *reinterpret_cast<float4*>(xT + dst[j]) = v[j];
+        for (int j = 0; j < BATCH; ++j) {
+          if ((pending >> j) & 1u) {
+            const float4 v = *reinterpret_cast<const float4*>(dst0 + j * dstride);
+            if (has_sentinel(v)) { still |= 1u << j; cp_async16(dst0 + j * dstride, src0 + j * sstride); }
+          }
+        }
+        pending = still;
+        if (++rounds > POLL_LIMIT) __trap();
       }
     }
+    return;
+  }
+  // generic (odd-sized last stream group): one item at a time per thread
+  for (int i = threadIdx.x; i < total; i += NT) {
+    const int k = i / sg4, q = i - k * sg4;
+    const float* src = g + (size_t)k * SX + s0 + q * 4;
+    float4 v = ld_vol4(src);
+    unsigned rounds = 0;
+    while (has_sentinel(v)) { v = ld_vol4(src); if (++rounds > POLL_LIMIT) __trap(); }
+    *reinterpret_cast<float4*>(xT + k * SP + q * 4) = v;
   }
 }
+
+// ---- hoisted form: everything about a thread's share of a staging pass that does not change from step to step
+// (the integer divisions and 64-bit address arithmetic of stage_poll cost ~200 instructions per warp per step)
+struct StageDesc {
+  unsigned src_off, dst_off;     // floats: first item inside a time slot [K][SX] / inside xT
+  unsigned sstride, dstride;     // floats between consecutive items of this thread
+  unsigned mask;                 // bit j = item j exists
+  bool fast;                     // false: shape needs the generic stage_poll
+};
+template <int BATCH>
+__device__ __forceinline__ StageDesc stage_prepare(int K, int SX, int SP, int s0, int sg4) {
+  StageDesc d;
+  const int total = K * sg4;
+  d.fast = (sg4 > 0) && (NT % sg4 == 0) && (total <= NT * BATCH);
+  d.src_off = d.dst_off = d.sstride = d.dstride = d.mask = 0;
+  if (!d.fast) return d;
+  const int kstep = NT / sg4;
+  const int i0 = threadIdx.x;
+  const int k0 = i0 / sg4, q = i0 - k0 * sg4;
+  d.src_off = (unsigned)(k0 * SX + s0 + q * 4);
+  d.dst_off = (unsigned)(k0 * SP + q * 4);
+  d.sstride = (unsigned)(kstep * SX);
+  d.dstride = (unsigned)(kstep * SP);
+#pragma unroll
+  for (int j = 0; j < BATCH; ++j)
+    if (i0 + j * NT < total) d.mask |= 1u << j;
+  if (d.mask == 0) { d.src_off = 0; d.dst_off = 0; }      // a thread without a share still inspects a valid address
+  return d;
+}
+// issue / complete halves of a hoisted staging pass, so that work which does not depend on the exchange (the stores
+// of the step just finished) can sit between them while the copies are in flight
+template <int BATCH>
+__device__ __forceinline__ void stage_issue(const StageDesc& d, float* xT, const float* g) {
+  const float* src0 = g + d.src_off;
+  float* dst0 = xT + d.dst_off;
+#pragma unroll
+  for (int j = 0; j < BATCH; ++j)
+    if ((d.mask >> j) & 1u) cp_async16(dst0 + j * d.dstride, src0 + (size_t)j * d.sstride);
+}
+__device__ __forceinline__ unsigned sentinel_in(const float4& v) {
+  // 0xFFFFFFFF is the largest unsigned word: one max-reduction instead of four compares
+  const unsigned m = max(max(__float_as_uint(v.x), __float_as_uint(v.y)), max(__float_as_uint(v.z), __float_as_uint(v.w)));
+  return m == SENTINEL ? 1u : 0u;
+}
+template <int BATCH>
+__device__ __forceinline__ void stage_complete(const StageDesc& d, float* xT, const float* g, long long* dbg = nullptr) {
+  const float* src0 = g + d.src_off;
+  float* dst0 = xT + d.dst_off;
+  unsigned rounds = 0;
+  const long long tq0 = dbg != nullptr ? clock64() : 0;
+  for (;;) {
+    cp_async_wait_all();
+    if (dbg != nullptr) { if (rounds == 0) dbg[1] += clock64() - tq0; dbg[0] += 1; }
+    // branch-free inspection: all loads first, one mask out
+    unsigned still = 0;
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const bool live = (d.mask >> j) & 1u;
+      const float4 v = *reinterpret_cast<const float4*>(live ? dst0 + j * d.dstride : dst0);
+      still |= (live ? sentinel_in(v) : 0u) << j;
+    }
+    if (still == 0) break;
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j)
+      if ((still >> j) & 1u) cp_async16(dst0 + j * d.dstride, src0 + (size_t)j * d.sstride);
+    if (++rounds > POLL_LIMIT) __trap();
+  }
+}
+template <int BATCH>
+__device__ __forceinline__ void stage_poll_desc(const StageDesc& d, float* xT, const float* g, long long* dbg = nullptr) {
+  stage_issue<BATCH>(d, xT, g);
+  stage_complete<BATCH>(d, xT, g, dbg);
+}
+// fire-and-forget: pull a line into L2 without tying up a register or a scoreboard
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // acc[r][j] = sum_k w[r][k] * xT[k][sc + j],  lanes stride k.  w rows are ldw apart in smem.
 template <int NR>

@@ -163,17 +163,30 @@ void LstmFamily::SetSeqLengths(const std::vector<int32>& sequence_lengths) {
   }
 }
 
+bool LstmFamily::FoldProjection() const {
+  if (!tr_.projected) return false;
+  // ASLP_LSTM_FOLD_PROJECTION=0/1 forces the choice (tests run both); by default fold unless it would more than
+  // double the recurrent FMAs per step (4C*C folded vs 4C*R + R*C)
+  const char* env = std::getenv("ASLP_LSTM_FOLD_PROJECTION");
+  if (env != nullptr && env[0] != '\0') return env[0] != '0';
+  return ncell_ <= 2 * nrecur_;
+}
+
 void LstmFamily::FillDirArgs(void* arr_v, int T, int S, bool bwd) {
   aslp_lstm_dir_t* arr = static_cast<aslp_lstm_dir_t*>(arr_v);
+  const bool fold = FoldProjection();
   for (int i = 0; i < tr_.ndirs; ++i) {
     Dir& d = d_[i];
     aslp_lstm_dir_t& a = arr[i];
-    a.T = T; a.S = S; a.C = ncell_; a.R = tr_.projected ? nrecur_ : 0;
+    a.T = T; a.S = S; a.C = ncell_; a.R = (tr_.projected && !fold) ? nrecur_ : 0;
     a.reverse = i;                                  // direction 0 walks t = 1..T, direction 1 walks t = T..1
     a.buf = d.prop.Data(); a.ldb = d.prop.Stride();
     a.dbuf = bwd ? d.back.Data() : nullptr; a.lddb = bwd ? d.back.Stride() : 0;
-    a.w_r = d.w_gifo_r.Data(); a.ldwr = d.w_gifo_r.Stride();
-    a.w_rm = tr_.projected ? d.w_r_m.Data() : nullptr; a.ldwrm = tr_.projected ? d.w_r_m.Stride() : 0;
+    if (fold) { a.w_r = d.w_fused.Data(); a.ldwr = d.w_fused.Stride(); a.w_rm = nullptr; a.ldwrm = 0; }
+    else {
+      a.w_r = d.w_gifo_r.Data(); a.ldwr = d.w_gifo_r.Stride();
+      a.w_rm = tr_.projected ? d.w_r_m.Data() : nullptr; a.ldwrm = tr_.projected ? d.w_r_m.Stride() : 0;
+    }
     a.peep_i = d.peep_i.Data(); a.peep_f = d.peep_f.Data(); a.peep_o = d.peep_o.Data();
     a.seq_len_dev = (tr_.use_seq_lengths && i == 1) ? seq_len_dev_.Data() : nullptr;
     a.cell_clip = 50.0f;
@@ -204,10 +217,35 @@ void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
     ASLP_OK(aslp_gemm(st, 0, 1, T * S, 4 * C, input_dim_, 1.0f, in.Data(), in.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(), 0.0f,
                       gifo.Data(), gifo.Stride(), d.bias.Data(), 0.0f, GemmPrecision(), nullptr, 0));
   }
+  const bool fold = FoldProjection();
+  if (fold) {
+    for (Dir& d : d_) {
+      d.w_fused.Resize(4 * C, C, kUndefined);
+      ASLP_OK(aslp_gemm(st, 0, 0, 4 * C, C, nrecur_, 1.0f, d.w_gifo_r.Data(), d.w_gifo_r.Stride(), d.w_r_m.Data(), d.w_r_m.Stride(), 0.0f,
+                        d.w_fused.Data(), d.w_fused.Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+    }
+    if (tr_.carry_state) {
+      // the carried r(0) was projected with the W_r_m of the PREVIOUS minibatch (the weights have been updated since), so
+      // the first step cannot go through W': feed r(0) W_gifo_r^T into the first step's pre-activations and hide m(0)
+      Dir& d = d_[0];
+      CuSubMatrix r0 = d.prop.Range(0, S, 7 * C, nrecur_), gifo1 = d.prop.Range(S, S, 0, 4 * C), m0 = d.prop.Range(0, S, 6 * C, C);
+      ASLP_OK(aslp_gemm(st, 0, 1, S, 4 * C, nrecur_, 1.0f, r0.Data(), r0.Stride(), d.w_gifo_r.Data(), d.w_gifo_r.Stride(), 1.0f,
+                        gifo1.Data(), gifo1.Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+      m0.SetZero();
+    }
+  }
   aslp_lstm_dir_t args[2];
   FillDirArgs(args, T, S, false);
-  const size_t wsb = aslp_lstm_workspace_bytes(T, S, C, tr_.projected ? nrecur_ : 0, tr_.ndirs, 0);
+  const size_t wsb = aslp_lstm_workspace_bytes(T, S, C, (tr_.projected && !fold) ? nrecur_ : 0, tr_.ndirs, 0);
   ASLP_OK(aslp_lstm_seq_fwd(st, args, tr_.ndirs, CuWorkspace(wsb), wsb));
+  if (fold) {
+    // r(t) = m(t) W_r_m^T for the whole chunk at once
+    for (Dir& d : d_) {
+      CuSubMatrix ym = d.prop.Range(S, T * S, 6 * C, C), yr = d.prop.Range(S, T * S, 7 * C, nrecur_);
+      ASLP_OK(aslp_gemm(st, 0, 1, T * S, nrecur_, C, 1.0f, ym.Data(), ym.Stride(), d.w_r_m.Data(), d.w_r_m.Stride(), 0.0f,
+                        yr.Data(), yr.Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+    }
+  }
   if (tr_.carry_state) {
     const int32 row = tr_.lc ? chunk_size_ : T;      // lc.h:629 vs nnet-lstm-projected-streams.h:432
     KALDI_ASSERT(row >= 0 && row <= T);
@@ -232,13 +270,32 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
     CuSubMatrix od = d.back.Range(S, T * S, ocol, O);
     od.CopyFromMat(out_diff.ColRange(i * O, O));
   }
+  const bool fold = FoldProjection();
+  const int prec = GemmPrecision();
+  if (fold) {
+    // the out_diff share of d_m for every step: out_diff_r W_r_m, placed where the kernel expects out_diff (m columns)
+    for (Dir& d : d_) {
+      CuSubMatrix od = d.back.Range(S, T * S, 7 * C, nrecur_), odm = d.back.Range(S, T * S, 6 * C, C);
+      ASLP_OK(aslp_gemm(st, 0, 0, T * S, C, nrecur_, 1.0f, od.Data(), od.Stride(), d.w_r_m.Data(), d.w_r_m.Stride(), 0.0f,
+                        odm.Data(), odm.Stride(), nullptr, 0.0f, prec, nullptr, 0));
+    }
+  }
   aslp_lstm_dir_t args[2];
   FillDirArgs(args, T, S, true);
-  const size_t wsb = aslp_lstm_workspace_bytes(T, S, C, tr_.projected ? nrecur_ : 0, tr_.ndirs, 1);
+  const size_t wsb = aslp_lstm_workspace_bytes(T, S, C, (tr_.projected && !fold) ? nrecur_ : 0, tr_.ndirs, 1);
   ASLP_OK(aslp_lstm_seq_bwd(st, args, tr_.ndirs, CuWorkspace(wsb), wsb));
+  if (fold) {
+    // d_r(t) = out_diff(t) + dgifo(successor of t) W_gifo_r: direction 0's successor is t+1, direction 1's is t-1;
+    // the boundary blocks of the derivative buffer are zero
+    for (int i = 0; i < tr_.ndirs; ++i) {
+      Dir& d = d_[i];
+      CuSubMatrix dg_next = d.back.Range(i == 0 ? 2 * S : 0, T * S, 0, 4 * C), dr = d.back.Range(S, T * S, 7 * C, nrecur_);
+      ASLP_OK(aslp_gemm(st, 0, 0, T * S, nrecur_, 4 * C, 1.0f, dg_next.Data(), dg_next.Stride(), d.w_gifo_r.Data(), d.w_gifo_r.Stride(), 1.0f,
+                        dr.Data(), dr.Stride(), nullptr, 0.0f, prec, nullptr, 0));
+    }
+  }
 
   const float mmt = opts_.momentum, clip = clip_gradient_;
-  const int prec = GemmPrecision();
   for (int i = 0; i < tr_.ndirs; ++i) {
     Dir& d = d_[i];
     CuSubMatrix dgifo = d.back.Range(S, T * S, 0, 4 * C);

@@ -9,6 +9,9 @@
 //                                                                     from row chunk_size (:629), backward from zero
 // Per minibatch: 1 tcgen05 GEMM (+bias) per direction for x*W_x^T, ONE persistent launch for all T steps of all
 // directions, then the chunk wgrad GEMMs with momentum and clip fused in their epilogues.
+// Projected variants fold the projection into the recurrence (W' = W_gifo_r W_r_m, gates(t) += W' m(t-1)), which
+// halves the number of cross-SM exchanges per time step; r(t) = W_r_m m(t) and d_r(t) = out_diff + W_gifo_r^T dgifo(t+1)
+// then come from bulk GEMMs over the whole chunk (same sums as lc.h:664-668 / :872-884, re-associated).
 #ifndef ASLP_HOST_NNET_LSTM_FAMILY_H_
 #define ASLP_HOST_NNET_LSTM_FAMILY_H_
 #include "nnet-component.h"
@@ -60,12 +63,14 @@ class LstmFamily : public UpdatableComponent {
     CuMatrix w_gifo_x_corr, w_gifo_r_corr, w_r_m_corr;
     CuVector bias_corr, peep_i_corr, peep_f_corr, peep_o_corr;
     CuMatrix prop, back;
+    CuMatrix w_fused;      // W_gifo_r * W_r_m [4C, C]: the projection folded into the recurrence (rebuilt every Propagate)
   };
   void AllocCorr();
   int32 Width() const { return 7 * ncell_ + nrecur_; }
   int32 RecDim() const { return tr_.projected ? nrecur_ : ncell_; }   // recurrent input dim of W_gifo_r
   int32 OutPerDir() const { return tr_.projected ? nrecur_ : ncell_; }
   void FillDirArgs(void* arr, int T, int S, bool bwd);
+  bool FoldProjection() const;          // run the recurrence on m(t-1) through W_gifo_r*W_r_m, r(t) / d_r(t) by bulk GEMMs
 
   Traits tr_;
   int32 ncell_, nrecur_, nstream_, chunk_size_;

@@ -123,8 +123,15 @@ def run_case(T, S, C, R, ndirs, seed=0, with_state=True, seq_len=None, reverse_f
     (10, 8, 400, 16, 1),      # several cells per CTA (cb = 3), one projection row per CTA
     (10, 8, 64, 600, 1),      # several projection rows per CTA (rb = 5)
     (6, 16, 512, 0, 1),       # cfg2 cell count, no projection, cb = 4
+    (30, 16, 320, 0, 2),      # cfg3 with the projection folded away: what the trainer launches (tensor-core form)
+    (25, 40, 64, 0, 2),       # tensor-core form, several 16-stream chunks, ragged last chunk
+    (8, 100, 512, 0, 1),      # cfg2 geometry: stream groups + chunks
+    (9, 5, 24, 0, 2),         # tensor-core form, fewer streams than one chunk, C not a multiple of 16
 ])
-def test_lstm_fwd_bwd_parity(T, S, C, R, ndirs):
+@pytest.mark.parametrize("kernel", ["auto", "simt"])
+def test_lstm_fwd_bwd_parity(T, S, C, R, ndirs, kernel, monkeypatch):
+    # "auto" picks the mma.sync tensor-core recurrence whenever R == 0 and the shape fits, "simt" forces the FFMA form
+    monkeypatch.setenv("ASLP_LSTM_KERNEL", kernel)
     errs, berrs = run_case(T, S, C, R, ndirs)
     assert max(errs) < RTOL, errs
     assert max(berrs) < RTOL, berrs

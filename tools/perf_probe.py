@@ -101,6 +101,14 @@ def probe_ctc(T, mb, Kc, Lab):
 
 if __name__ == "__main__":
     out = []
+    if len(sys.argv) > 1 and sys.argv[1] == "lstm0":     # single launches (folded form, what the trainer runs) for an ncu capture
+        orig = timeit
+        def timeit(fn, iters=1, warm=0):                  # noqa: F811
+            return orig(fn, iters=1, warm=0)
+        globals()["timeit"] = timeit
+        print(json.dumps(probe_lstm(1000, 16, 320, 0, 2, False)), flush=True)
+        print(json.dumps(probe_lstm(1000, 16, 320, 0, 2, True)), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "lstm":      # single launches for an ncu capture
         orig = timeit
         def timeit(fn, iters=1, warm=0):                  # noqa: F811
@@ -108,6 +116,31 @@ if __name__ == "__main__":
         globals()["timeit"] = timeit
         print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, False)), flush=True)
         print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, True)), flush=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "timing":    # per-phase clock64 breakdown of the recurrence kernels
+        tb = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+        for R in (0,):
+            for bwd in (False, True):
+                tb.zero_()
+                L.aslp_lstm_debug_timing(P(tb.data_ptr()))
+                orig = timeit
+                r = probe_lstm(1000, 16, 320, R, 2, bwd)
+                L.aslp_lstm_debug_timing(P(0))
+                torch.cuda.synchronize()
+                t = tb.cpu().numpy().astype(np.float64)
+                used = t[t.sum(1) > 0] / 1000.0          # last launch only (buffer is overwritten); cycles per step
+                r["cycles_per_step_mean"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish"], used.mean(0).round(0).tolist()))
+                r["cycles_per_step_max"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish"], used.max(0).round(0).tolist()))
+                r["cycles_per_step_min"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish"], used.min(0).round(0).tolist()))
+                r["ctas"] = int(used.shape[0])
+                print(json.dumps(r), flush=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "recur":     # recurrence + CTC only
+        for bwd in (False, True):
+            print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, bwd)), flush=True)    # two-step projected form
+            print(json.dumps(probe_lstm(1000, 16, 320, 0, 2, bwd)), flush=True)      # what the folded form launches
+            print(json.dumps(probe_lstm(200, 100, 512, 0, 1, bwd)), flush=True)
+        print(json.dumps(probe_ctc(1000, 16, 72, 100)), flush=True)
         sys.exit(0)
     for spec in [(16000, 1280, 640, False, True), (16000, 1280, 40, False, True), (16000, 640, 1280, False, False),
                  (1280, 640, 16000, True, False), (320, 320, 16000, True, False), (16000, 72, 640, False, True),
