@@ -4,14 +4,16 @@
 // cost_and_grad :369-428, log_plus (detail/ctc_helper.h:55-68).  The reference's GPU path
 // (gpu_ctc_kernels.h) is not followed: it does not compile for sm_70+.
 //
-// Three launches per minibatch, labels uploaded once:
-//   1. ctc_softmax_kernel : warp per (t, n) row, probabilities into the workspace (HBM-bound);
-//   2. ctc_dp_kernel      : one thread group per utterance (a single warp when the minibatch is
-//                           large enough to fill the chip, a wider CTA when it is latency-bound):
-//                           alpha sweep (rows spilled to the workspace), beta sweep with the
-//                           per-label log-sum of alpha*beta, exactly the reference's valid-state
-//                           window (start/end, s_inc/e_inc) and in-place beta semantics;
-//   3. ctc_grad_kernel    : pointwise grad = p - exp(out - log p - logZ) (HBM-bound).
+// Four launches per minibatch, labels uploaded once:
+//   0. ctc_csr_kernel     : per utterance, the states of every label (for the per-label sums of pass 3);
+//   1. ctc_softmax_kernel : warp per (t, n) row: probabilities and the per-state log-probabilities lp[n][t][i]
+//                           into the workspace (HBM-bound);
+//   2. ctc_sweep_kernel   : the alpha sweep and the beta sweep of an utterance are two CTAs running concurrently; one
+//                           state per thread, one barrier per time step, lp rows prefetched a step ahead -- the
+//                           recurrence is latency-bound, so nothing that is not recurrent stays in the loop.  Exactly
+//                           the reference's valid-state window (start/end, s_inc/e_inc) and in-place beta semantics;
+//   3. ctc_grad_kernel    : warp per (t, n) row: per-label log-sum of alpha*beta and grad = p - exp(sum - log p - logZ)
+//                           (HBM-bound).
 #include "common.cuh"
 #include "../../include/ctc.h"
 #include <string.h>
@@ -25,8 +27,34 @@ __device__ __forceinline__ float log_plus(float p1, float p2) {
   return log1pf(expf(-fabsf(p1 - p2))) + fmaxf(p1, p2);
 }
 
-// ---- 1. softmax of every valid (t, n) row
-__global__ void ctc_softmax_kernel(float* probs, const float* acts, const int* in_len, int K, int mb, int maxT) {
+// ---- 0. per-utterance CSR of the non-blank states of every label (ascending state order: the reference's accumulation order)
+__global__ void ctc_csr_kernel(int* cls_start_all, int* cls_list_all, const int* flat_labels, const int* label_off,
+                               const int* label_len, int K, int maxS) {
+  const int n = blockIdx.x, L = label_len[n];
+  const int* labels = flat_labels + label_off[n];
+  int* cls_start = cls_start_all + (size_t)n * (K + 1);
+  int* cls_list = cls_list_all + (size_t)n * maxS;
+  extern __shared__ int cnt[];                         // [K+1]
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) cnt[k] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) atomicAdd(&cnt[labels[i] + 1], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) for (int k = 0; k < K; ++k) cnt[k + 1] += cnt[k];
+  __syncthreads();
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) cls_start[k] = cnt[k];
+  // position of state (2i+1) among equal labels = number of earlier equal labels
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const int l = labels[i];
+    int rank = 0;
+    for (int j = 0; j < i; ++j) rank += (labels[j] == l);
+    cls_list[cnt[l] + rank] = 2 * i + 1;
+  }
+}
+
+// ---- 1. softmax of every valid (t, n) row, plus the per-state log-probabilities lp[n][t][i] = log p[t][lab_n(i)] that
+// the two sweeps consume (contiguous, prefetchable rows instead of a dependent gather on the recurrent chain)
+__global__ void ctc_softmax_kernel(float* probs, float* lp_all, const float* acts, const int* in_len, const int* flat_labels,
+                                   const int* label_off, const int* label_len, int K, int mb, int maxT, int maxS) {
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long rows = (long long)maxT * mb;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
@@ -41,6 +69,11 @@ __global__ void ctc_softmax_kernel(float* probs, const float* acts, const int* i
     for (int k = lane; k < K; k += 32) den += expf(x[k] - mx);
     den = warp_sum(den);
     for (int k = lane; k < K; k += 32) p[k] = expf(x[k] - mx) / den;
+    __syncwarp();                                      // the row just written is re-read by other lanes below
+    const int L = label_len[n], S = 2 * L + 1;
+    const int* labels = flat_labels + label_off[n];
+    float* lp = lp_all + ((size_t)n * maxT + t) * maxS;
+    for (int i = lane; i < S; i += 32) lp[i] = logf(p[(i & 1) ? labels[i >> 1] : 0]);
   }
 }
 
@@ -59,30 +92,30 @@ __device__ __forceinline__ float block_log_plus(float v, float* red) {
   return r;
 }
 
-// ---- 2. alpha / beta dynamic programme, one block of G threads per utterance
+// ---- 2. the two sweeps, each its own CTA (blockIdx.y = 0: alpha, 1: beta) so that they run concurrently.  One
+// __syncthreads per time step (double-buffered rows in shared memory), lp rows prefetched one step ahead; the
+// reference's valid-state window (start/end, s_inc/e_inc) and its in-place beta semantics (states outside the window
+// keep their previous value) are reproduced exactly.  alpha rows go to alphas_ws; beta rows, masked to the window,
+// to betas_ws; the per-label sums and the gradient are a separate, fully parallel pass.
 template <int G>
-__global__ void __launch_bounds__(G) ctc_dp_kernel(float* grads_out /* receives per-label log-sums */, const float* probs,
-                                                   float* alphas_ws, float* costs_dev, int* valid_dev, const int* flat_labels,
-                                                   const int* label_off, const int* label_len, const int* in_len, int K, int mb,
-                                                   int maxT, int maxS) {
+__global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float* alphas_ws, float* betas_ws, float* costs_dev,
+                                                      int* valid_dev, const int* flat_labels, const int* label_off,
+                                                      const int* label_len, const int* in_len, int maxT, int maxS) {
   extern __shared__ int smem_i[];
   const int n = blockIdx.x;
+  const bool is_beta = blockIdx.y == 1;
   const int T = in_len[n], L = label_len[n], S = 2 * L + 1;
   const int tid = threadIdx.x;
   int* lab = smem_i;                      // [maxS] labels with blanks
   int* s_inc = lab + maxS;                // [maxS]
   int* e_inc = s_inc + maxS;              // [maxS]
-  int* cls_start = e_inc + maxS;          // [K+1] CSR of non-blank states per label
-  int* cls_list = cls_start + K + 1;      // [maxS]
-  float* a_prev = reinterpret_cast<float*>(cls_list + maxS);   // [maxS]
-  float* a_cur = a_prev + maxS;           // [maxS]
-  float* ab = a_cur + maxS;               // [maxS] alpha+beta of the current frame
-  float* red = ab + maxS;                 // [32]
+  float* rowA = reinterpret_cast<float*>(e_inc + maxS);   // [maxS + 2]
+  float* rowB = rowA + maxS + 2;          // [maxS + 2]
+  float* red = rowB + maxS + 2;           // [32]
   __shared__ int sh_repeats;
 
   const int* labels = flat_labels + label_off[n];
-  // ---- setup (cpu_ctc.h:119-155), sequential on one thread: O(L)
-  if (tid == 0) {
+  if (tid == 0) {                         // cpu_ctc.h:119-155, sequential: O(L)
     int e_counter = 0, s_counter = 0, repeats = 0;
     s_inc[s_counter++] = 1;
     for (int i = 1; i < L; ++i) {
@@ -97,163 +130,173 @@ __global__ void __launch_bounds__(G) ctc_dp_kernel(float* grads_out /* receives 
     }
     e_inc[e_counter++] = 1;
     sh_repeats = repeats;
-    for (int i = 0; i < L; ++i) { lab[2 * i] = 0; lab[2 * i + 1] = labels[i]; }
-    lab[S - 1] = 0;
-    // CSR: states of each non-blank label in ascending state order (the reference's accumulation order)
-    for (int k = 0; k <= K; ++k) cls_start[k] = 0;
-    for (int i = 0; i < L; ++i) cls_start[labels[i] + 1]++;
-    for (int k = 0; k < K; ++k) cls_start[k + 1] += cls_start[k];
   }
+  for (int i = tid; i < S; i += G) lab[i] = (i & 1) ? labels[i >> 1] : 0;
   __syncthreads();
-  // parallel CSR fill: position of state (2i+1) among equal labels = number of earlier equal labels
-  for (int i = tid; i < L; i += G) {
-    const int l = labels[i];
-    int rank = 0;
-    for (int j = 0; j < i; ++j) rank += (labels[j] == l);
-    cls_list[cls_start[l] + rank] = 2 * i + 1;
-  }
   const int repeats = sh_repeats;
-  __syncthreads();
-
   if (L + repeats > T) {                  // cpu_ctc.h:193-195: cost 0, gradient untouched
-    if (tid == 0) { costs_dev[n] = 0.f; valid_dev[n] = 0; }
+    if (tid == 0 && !is_beta) { costs_dev[n] = 0.f; valid_dev[n] = 0; }
+    return;
+  }
+  const float* lp = lp_all + (size_t)n * maxT * maxS;
+  constexpr int MAXI = 4;                 // states per thread (S <= 4 G), kept in registers
+  float* prev = rowA;
+  float* cur = rowB;
+
+  if (!is_beta) {
+    // ---- alpha sweep (cpu_ctc.h:217-262)
+    float* alphas = alphas_ws + (size_t)n * maxT * maxS;
+    int start = (((S / 2) + repeats - T) < 0) ? 0 : 1;
+    int end = S > 1 ? 2 : 1;
+    float lpn[MAXI];
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[i] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) {
+      const int i = j * G + tid;
+      if (i < S) {
+        const float v = (i >= start && i < end) ? lpn[j] : neg_inf();
+        prev[i] = v;
+        alphas[i] = v;
+      }
+    }
+    if (T > 1) {
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)maxS + i] : 0.f; }
+    }
+    __syncthreads();
+    for (int t = 1; t < T; ++t) {
+      const int remain = (S / 2) + repeats - (T - t);
+      if (remain >= 0) start += s_inc[remain];
+      if (t <= (S / 2) + repeats) end += e_inc[t - 1];
+      float lpc[MAXI];
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) lpc[j] = lpn[j];
+      if (t + 1 < T) {
+#pragma unroll
+        for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(t + 1) * maxS + i] : 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) {
+        const int i = j * G + tid;
+        if (i < S) {
+          float v = neg_inf();
+          if (i >= start && i < end) {
+            if (i == 0) {
+              v = prev[0] + lpc[j];
+            } else {
+              float prev_sum = log_plus(prev[i], prev[i - 1]);
+              const int li = lab[i];
+              if (li != 0 && i != 1 && li != lab[i - 2]) prev_sum = log_plus(prev_sum, prev[i - 2]);
+              v = prev_sum + lpc[j];
+            }
+          }
+          cur[i] = v;
+          alphas[(size_t)t * maxS + i] = v;
+        }
+      }
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
+    // log-likelihood over the final window (the reference sums in ascending i; the block reduction is a tree over the same terms)
+    float ll = neg_inf();
+    for (int i = tid; i < S; i += G) if (i >= start && i < end) ll = log_plus(ll, prev[i]);
+    const float loglike = block_log_plus<G>(ll, red);
+    if (tid == 0) { costs_dev[n] = -loglike; valid_dev[n] = 1; }
     return;
   }
 
-  float* alphas = alphas_ws + (size_t)n * maxT * maxS;
-  const size_t fstride = (size_t)mb * K;                 // floats between consecutive frames of one utterance
-  const float* pr = probs + (size_t)n * K;
-
-  // ---- alpha sweep (cpu_ctc.h:217-262)
-  int start = (((S / 2) + repeats - T) < 0) ? 0 : 1;
-  int end = S > 1 ? 2 : 1;
-  for (int i = tid; i < S; i += G) {
-    const float v = (i >= start && i < end) ? logf(pr[lab[i]]) : neg_inf();
-    a_prev[i] = v;
-    alphas[i] = v;
+  // ---- beta sweep (cpu_ctc.h:269-367)
+  float* betas_out = betas_ws + (size_t)n * maxT * maxS;
+  int start = S > 1 ? (S - 2) : 0;
+  int end = (T > (S / 2) + repeats) ? S : S - 1;
+  float lpn[MAXI];
+#pragma unroll
+  for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(T - 1) * maxS + i] : 0.f; }
+#pragma unroll
+  for (int j = 0; j < MAXI; ++j) {
+    const int i = j * G + tid;
+    if (i < S) {
+      const float v = (i >= start && i < end) ? lpn[j] : neg_inf();
+      prev[i] = v;
+      betas_out[(size_t)(T - 1) * maxS + i] = v;
+    }
+  }
+  if (tid < 2) { prev[S + tid] = neg_inf(); cur[S + tid] = neg_inf(); }   // guards for the i+1 / i+2 reads
+  if (T > 1) {
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(T - 2) * maxS + i] : 0.f; }
   }
   __syncthreads();
-  for (int t = 1; t < T; ++t) {
+  for (int t = T - 2; t >= 0; --t) {
     const int remain = (S / 2) + repeats - (T - t);
-    if (remain >= 0) start += s_inc[remain];
-    if (t <= (S / 2) + repeats) end += e_inc[t - 1];
-    const float* p = pr + (size_t)t * fstride;
-    for (int i = tid; i < S; i += G) {
-      float v = neg_inf();
-      if (i >= start && i < end) {
-        if (i == 0) {
-          v = a_prev[0] + logf(p[0]);
-        } else {
-          float prev_sum = log_plus(a_prev[i], a_prev[i - 1]);
+    if (remain >= -1) start -= s_inc[remain + 1];
+    if (t < (S / 2) + repeats) end -= e_inc[t];
+    const int endloop = (end == S) ? end - 1 : end;
+    float lpc[MAXI];
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) lpc[j] = lpn[j];
+    if (t > 0) {
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(t - 1) * maxS + i] : 0.f; }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) {
+      const int i = j * G + tid;
+      if (i < S) {
+        const bool in_loop = i >= start && i < endloop;
+        const bool in_last = end == S && i == S - 1;
+        float v = prev[i];                               // outside the window the reference leaves the old value in place
+        if (in_loop) {
+          float next_sum = log_plus(prev[i], prev[i + 1]);
           const int li = lab[i];
-          if (li != 0 && i != 1 && li != lab[i - 2]) prev_sum = log_plus(prev_sum, a_prev[i - 2]);
-          v = prev_sum + logf(p[li]);
+          if (li != 0 && i != (S - 2) && li != lab[i + 2]) next_sum = log_plus(next_sum, prev[i + 2]);
+          v = next_sum + lpc[j];
+        } else if (in_last) {
+          v = prev[S - 1] + lpc[j];
         }
-      }
-      a_cur[i] = v;
-      alphas[(size_t)t * maxS + i] = v;
-    }
-    __syncthreads();
-    float* tmp = a_prev; a_prev = a_cur; a_cur = tmp;
-  }
-  // log-likelihood over the final window (sequential order of the reference is ascending i; the
-  // block reduction uses a tree -- same terms)
-  float ll = neg_inf();
-  for (int i = tid; i < S; i += G) if (i >= start && i < end) ll = log_plus(ll, a_prev[i]);
-  const float loglike = block_log_plus<G>(ll, red);
-  if (tid == 0) { costs_dev[n] = -loglike; valid_dev[n] = 1; }
-
-  // ---- beta sweep + per-label log-sums (cpu_ctc.h:269-367); beta lives in a_cur, in-place semantics kept
-  float* betas = a_cur;
-  __syncthreads();
-  for (int i = tid; i < S; i += G) betas[i] = neg_inf();
-  __syncthreads();
-  start = S > 1 ? (S - 2) : 0;
-  end = (T > (S / 2) + repeats) ? S : S - 1;
-  for (int t = T - 1; t >= 0; --t) {
-    const float* p = pr + (size_t)t * fstride;
-    const float* al = alphas + (size_t)t * maxS;
-    if (t == T - 1) {
-      for (int i = tid; i < S; i += G) {
-        float v = neg_inf();
-        if (i >= start && i < end) {
-          const float b = logf(p[lab[i]]);
-          betas[i] = b;
-          v = al[i] + b;
-        }
-        ab[i] = v;
-      }
-    } else {
-      const int remain = (S / 2) + repeats - (T - t);
-      if (remain >= -1) start -= s_inc[remain + 1];
-      if (t < (S / 2) + repeats) end -= e_inc[t];
-      const int endloop = (end == S) ? end - 1 : end;
-      // read the old betas first, then write: reproduces the reference's ascending in-place update
-      constexpr int MAXI = 8;             // states per thread per pass, kept in registers
-      for (int base = 0; base < S; base += G * MAXI) {
-        float nb[MAXI];
-#pragma unroll
-        for (int j = 0; j < MAXI; ++j) {
-          const int i = base + j * G + tid;
-          float v = 0.f;
-          if (i < S) {
-            if (i >= start && i < endloop) {
-              float next_sum = log_plus(betas[i], betas[i + 1]);
-              const int li = lab[i];
-              if (li != 0 && i != (S - 2) && li != lab[i + 2]) next_sum = log_plus(next_sum, betas[i + 2]);
-              v = next_sum + logf(p[li]);
-            } else if (end == S && i == S - 1) {
-              v = betas[S - 1] + logf(p[0]);
-            }
-          }
-          nb[j] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < MAXI; ++j) {
-          const int i = base + j * G + tid;
-          if (i < S) {
-            const bool in_win = (i >= start && i < endloop) || (end == S && i == S - 1);
-            if (in_win) betas[i] = nb[j];
-            ab[i] = in_win ? al[i] + nb[j] : neg_inf();
-          }
-        }
-        __syncthreads();
+        cur[i] = v;
+        betas_out[(size_t)t * maxS + i] = (in_loop || in_last) ? v : neg_inf();
       }
     }
     __syncthreads();
-    // per-label log-sum of alpha*beta.  blank (label 0): all even states, block-parallel
-    float bl = neg_inf();
-    for (int i = 2 * tid; i < S; i += 2 * G) bl = log_plus(ab[i], bl);
-    const float blank_sum = block_log_plus<G>(bl, red);
-    float* out = grads_out + (size_t)n * K + (size_t)t * fstride;
-    for (int k = tid; k < K; k += G) {
-      float o = (k == 0) ? blank_sum : neg_inf();
-      for (int q = cls_start[k]; q < cls_start[k + 1]; ++q) o = log_plus(ab[cls_list[q]], o);
-      out[k] = o;
-    }
-    __syncthreads();
+    float* tmp = prev; prev = cur; cur = tmp;
   }
 }
 
-// ---- 3. grad = p - exp(out - log p - logZ), with the reference's guards (cpu_ctc.h:296-307)
-__global__ void ctc_grad_kernel(float* grads, const float* probs, const float* costs_dev, const int* valid_dev,
-                                const int* in_len, int K, int mb, int maxT) {
-  const long long total = (long long)maxT * mb * K;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / K;
+// ---- 3. per-label log-sums of alpha*beta and grad = p - exp(sum - log p - logZ), with the reference's guards
+// (cpu_ctc.h:296-307); warp per (t, n) row
+__global__ void ctc_grad_kernel(float* grads, const float* probs, const float* alphas_ws, const float* betas_ws,
+                                const float* costs_dev, const int* valid_dev, const int* in_len, const int* label_len,
+                                const int* cls_start_all, const int* cls_list_all, int K, int mb, int maxT, int maxS) {
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long rows = (long long)maxT * mb;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
     const int n = (int)(row % mb), t = (int)(row / mb);
     if (t >= in_len[n] || !valid_dev[n]) continue;
-    const float p = probs[i], o = grads[i];
+    const int S = 2 * label_len[n] + 1;
+    const float* al = alphas_ws + ((size_t)n * maxT + t) * maxS;
+    const float* be = betas_ws + ((size_t)n * maxT + t) * maxS;
+    const int* cls_start = cls_start_all + (size_t)n * (K + 1);
+    const int* cls_list = cls_list_all + (size_t)n * maxS;
+    // blank: all even states, lanes stride then tree
+    float bl = neg_inf();
+    for (int i = 2 * lane; i < S; i += 64) bl = log_plus(al[i] + be[i], bl);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bl = log_plus(bl, __shfl_xor_sync(0xffffffffu, bl, o));
     const float log_partition = -costs_dev[n];
-    float g;
-    if (o == 0.0f || o == -INFINITY || p == 0.0f) g = p;
-    else g = p - expf(o - logf(p) - log_partition);
-    grads[i] = g;
+    const float* p = probs + row * K;
+    float* g = grads + row * K;
+    for (int k = lane; k < K; k += 32) {
+      float o = (k == 0) ? bl : neg_inf();
+      for (int q = cls_start[k]; q < cls_start[k + 1]; ++q) { const int i = cls_list[q]; o = log_plus(al[i] + be[i], o); }
+      const float pk = p[k];
+      g[k] = (o == 0.0f || o == -INFINITY || pk == 0.0f) ? pk : pk - expf(o - logf(pk) - log_partition);
+    }
   }
 }
 
-struct Sizes { size_t alphas, probs, costs, valid, meta, total; int maxT, maxL, maxS, sumL; };
+struct Sizes { size_t alphas, betas, lp, probs, costs, valid, meta, csr, total; int maxT, maxL, maxS, sumL; };
 Sizes ctc_sizes(const int* label_lengths, const int* input_lengths, int K, int mb) {
   Sizes z; memset(&z, 0, sizeof(z));
   for (int i = 0; i < mb; ++i) {
@@ -267,16 +310,19 @@ Sizes ctc_sizes(const int* label_lengths, const int* input_lengths, int K, int m
   z.probs = al((size_t)mb * z.maxT * K * sizeof(float));
   z.costs = al((size_t)mb * sizeof(float));
   z.valid = al((size_t)mb * sizeof(int));
+  z.betas = z.alphas;
+  z.lp = z.alphas;
   z.meta = al((size_t)(3 * mb + z.sumL + 4) * sizeof(int));
-  z.total = z.alphas + z.probs + z.costs + z.valid + z.meta;
+  z.csr = al(((size_t)mb * (K + 1) + (size_t)mb * z.maxS) * sizeof(int));
+  z.total = z.alphas + z.betas + z.lp + z.probs + z.costs + z.valid + z.meta + z.csr;
   return z;
 }
 
 template <int G>
-int launch_dp(cudaStream_t st, int mb, size_t smem, float* grads, const float* probs, float* alphas, float* costs, int* valid,
-              const int* flat, const int* off, const int* llen, const int* ilen, int K, int maxT, int maxS) {
-  ASLP_CUDA(cudaFuncSetAttribute(ctc_dp_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ctc_dp_kernel<G><<<mb, G, smem, st>>>(grads, probs, alphas, costs, valid, flat, off, llen, ilen, K, mb, maxT, maxS);
+int launch_sweep(cudaStream_t st, int mb, size_t smem, const float* lp, float* alphas, float* betas, float* costs, int* valid,
+                 const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS) {
+  ASLP_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_sweep_kernel<G><<<dim3(mb, 2), G, smem, st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS);
   ASLP_CHECK_LAUNCH();
   return 0;
 }
@@ -316,11 +362,15 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
   const int K = alphabet_size, mb = minibatch;
   const Sizes z = ctc_sizes(label_lengths, input_lengths, K, mb);
   char* ws = (char*)workspace;
-  float* alphas = (float*)ws;
-  float* probs = (float*)(ws + z.alphas);
-  float* costs_dev = (float*)(ws + z.alphas + z.probs);
-  int* valid_dev = (int*)(ws + z.alphas + z.probs + z.costs);
-  int* meta = (int*)(ws + z.alphas + z.probs + z.costs + z.valid);
+  float* alphas = (float*)ws;                      ws += z.alphas;
+  float* betas = (float*)ws;                       ws += z.betas;
+  float* lp = (float*)ws;                          ws += z.lp;
+  float* probs = (float*)ws;                       ws += z.probs;
+  float* costs_dev = (float*)ws;                   ws += z.costs;
+  int* valid_dev = (int*)ws;                       ws += z.valid;
+  int* meta = (int*)ws;                            ws += z.meta;
+  int* cls_start = (int*)ws;
+  int* cls_list = cls_start + (size_t)mb * (K + 1);
   // host staging of the label metadata: [label_len mb][in_len mb][label_off mb][flat sumL]
   static thread_local int* hmeta = nullptr; static thread_local size_t hmeta_cap = 0;
   const size_t nmeta = (size_t)3 * mb + z.sumL;
@@ -344,33 +394,43 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
   if (cudaMemcpyAsync(meta, hmeta, nmeta * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) return CTC_STATUS_MEMOPS_FAILED;
   const int* d_llen = meta; const int* d_ilen = meta + mb; const int* d_off = meta + 2 * mb; const int* d_flat = meta + 3 * mb;
 
+  if (z.maxS > 4 * 1024) return CTC_STATUS_INVALID_VALUE;          // more than 2047 labels in one utterance
   {
-    const long long rows = (long long)z.maxT * mb;
-    int blocks = (int)((rows + 7) / 8);
-    if (blocks > aslp_num_sms() * 16) blocks = aslp_num_sms() * 16;
-    if (blocks < 1) blocks = 1;
-    ctc_softmax_kernel<<<blocks, 256, 0, st>>>(probs, activations, d_ilen, K, mb, z.maxT);
+    ctc_csr_kernel<<<mb, 128, (K + 1) * sizeof(int), st>>>(cls_start, cls_list, d_flat, d_off, d_llen, K, z.maxS);
+    ++g_aslp_launches;
+    if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+  }
+  const long long rows = (long long)z.maxT * mb;
+  int row_blocks = (int)((rows + 7) / 8);
+  if (row_blocks > aslp_num_sms() * 16) row_blocks = aslp_num_sms() * 16;
+  if (row_blocks < 1) row_blocks = 1;
+  {
+    ctc_softmax_kernel<<<row_blocks, 256, 0, st>>>(probs, lp, activations, d_ilen, d_flat, d_off, d_llen, K, mb, z.maxT, z.maxS);
     ++g_aslp_launches;
     if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
   }
   {
-    const size_t smem = ((size_t)5 * z.maxS + K + 1) * sizeof(int) + ((size_t)3 * z.maxS + 32) * sizeof(float);
+    const size_t smem = ((size_t)3 * z.maxS) * sizeof(int) + ((size_t)2 * (z.maxS + 2) + 32) * sizeof(float);
     if (smem > 220 * 1024) return CTC_STATUS_INVALID_VALUE;
-    // group width: one warp per utterance once the minibatch alone fills the chip, wider when latency-bound
+    // one state per thread where possible (the sweep is latency-bound: a step is two log-sum-exps and one barrier);
+    // a single warp per sweep once the minibatch alone fills the chip
     int G = 32;
-    if (mb < aslp_num_sms() * 8) { G = 64; while (G < z.maxS && G < 256) G <<= 1; }
+    if (2 * mb < aslp_num_sms() * 8) { G = 64; while (G < z.maxS && G < 1024) G <<= 1; }
+    while (4 * G < z.maxS) G <<= 1;
     int rc;
-    if (G == 32) rc = launch_dp<32>(st, mb, smem, gradients, probs, alphas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, K, z.maxT, z.maxS);
-    else if (G == 64) rc = launch_dp<64>(st, mb, smem, gradients, probs, alphas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, K, z.maxT, z.maxS);
-    else if (G == 128) rc = launch_dp<128>(st, mb, smem, gradients, probs, alphas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, K, z.maxT, z.maxS);
-    else rc = launch_dp<256>(st, mb, smem, gradients, probs, alphas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, K, z.maxT, z.maxS);
+    switch (G) {
+      case 32: rc = launch_sweep<32>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+      case 64: rc = launch_sweep<64>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+      case 128: rc = launch_sweep<128>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+      case 256: rc = launch_sweep<256>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+      case 512: rc = launch_sweep<512>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+      default: rc = launch_sweep<1024>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+    }
     if (rc != 0) return CTC_STATUS_EXECUTION_FAILED;
   }
   {
-    const long long total = (long long)z.maxT * mb * K;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > aslp_num_sms() * 16) blocks = aslp_num_sms() * 16;
-    ctc_grad_kernel<<<blocks, 256, 0, st>>>(gradients, probs, costs_dev, valid_dev, d_ilen, K, mb, z.maxT);
+    ctc_grad_kernel<<<row_blocks, 256, 0, st>>>(gradients, probs, alphas, betas, costs_dev, valid_dev, d_ilen, d_llen, cls_start, cls_list,
+                                                K, mb, z.maxT, z.maxS);
     ++g_aslp_launches;
     if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
   }

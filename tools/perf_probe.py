@@ -117,6 +117,11 @@ if __name__ == "__main__":
         print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, False)), flush=True)
         print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, True)), flush=True)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ctc":
+        print(json.dumps(probe_ctc(1000, 16, 72, 100)), flush=True)
+        print(json.dumps(probe_ctc(1000, 256, 72, 100)), flush=True)
+        print(json.dumps(probe_ctc(1000, 2048, 72, 100)), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "timing":    # per-phase clock64 breakdown of the recurrence kernels
         tb = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
         for R in (0,):
