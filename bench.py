@@ -279,12 +279,20 @@ def main():
     if rank == 0:
         frames = S * T * args.steps * world
         hbm_peak, tf_peak, peak_src = measured_peaks()
-        # dominant kernel: the persistent LSTM backward recurrence.  Algorithmic work per launch: per step and
-        # direction 2*S*(4C*R + R*C) flop for the two recurrent contractions, T steps, 2 directions.
+        # dominant kernel: the persistent LSTM backward recurrence (one launch per layer, both directions).  It fuses the
+        # per-step recurrent contraction with the cell derivative chain, so what it MUST move is the pointwise traffic of
+        # 22*C*4 bytes per (frame, direction) backward; the contraction flops are reported next to it.
+        bytes_per_launch = 22.0 * C_CELL * 4 * (S * T) * 2
         flop_per_launch = 2.0 * S * (4 * C_CELL * C_CELL + C_CELL * C_CELL) * T * 2
         bwd_avg_ms = bwd_ms.value / max(1, nb.value)
         fwd_avg_ms = fwd_ms.value / max(1, nf.value)
-        ach = flop_per_launch / (bwd_avg_ms * 1e-3) / 1e12 if bwd_avg_ms > 0 else 0.0
+        ach = bytes_per_launch / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
+        ach_tf = flop_per_launch / (bwd_avg_ms * 1e-3) / 1e12 if bwd_avg_ms > 0 else 0.0
+        traffic = None
+        try:                                       # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["lstm_bwd_mma_kernel"]["dram_bytes_per_launch"]
+        except Exception:  # noqa: BLE001
+            pass
         step_ms = ms_dev / args.steps
         line = {
             "metric": METRIC, "value": frames / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -295,11 +303,14 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {
-                "kernel": "lstm_bwd_kernel (persistent BPTT recurrence, both directions, one launch per layer)",
-                "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak if tf_peak else None,
-                "traffic": None, "peak_source": peak_src,
-                "note": "latency-bound per-step contractions [S=16 x 1280 x 320] (SURVEY 8d reports them separately); share of step: "
-                        "lstm_bwd %.1f%%, lstm_fwd %.1f%%" % (100 * bwd_ms.value / ms_dev, 100 * fwd_ms.value / ms_dev),
+                "kernel": "lstm_bwd_mma_kernel (persistent BPTT recurrence of one layer, both directions, all T steps in one launch)",
+                "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak if hbm_peak else None,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "note": "the kernel is bound by neither pipe but by the T-step dependent chain (exchange through L2 + legacy-MMA "
+                        "latency per step, see DESIGN.md); its recurrent contractions run at %.2f TFLOP/s (%.3f%% of the %.0f TFLOP/s "
+                        "bf16 peak); share of the step: lstm_bwd %.1f%%, lstm_fwd %.1f%%"
+                        % (ach_tf, 100 * ach_tf / tf_peak if tf_peak else 0.0, tf_peak, 100 * bwd_ms.value / ms_dev, 100 * fwd_ms.value / ms_dev),
                 "avg_launch_ms": {"lstm_bwd": bwd_avg_ms, "lstm_fwd": fwd_avg_ms},
             },
             "loss": {"mean_ctc_cost_last_step": float(np.mean(costs))},

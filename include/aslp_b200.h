@@ -84,6 +84,9 @@ int aslp_act_fwd(aslp_stream_t s, int kind, float* out, int ldo, const float* in
 /* BackpropagateFnc: sigmoid y(1-y)e, tanh (1-y^2)e use the OUTPUT y; relu uses the INPUT x (x>0 ? e : 0) */
 int aslp_act_bwd(aslp_stream_t s, int kind, float* in_diff, int ldd, const float* y_or_x, int ldy,
                  const float* out_diff, int lde, int rows, int cols);
+/* CuMatrixBase::CopyRows (cu-matrix.cc:2055-2080; kernel cu-kernels.cu:1090-1110): dst[r,:] = src[idx[r],:], idx < 0 -> zero row.
+ * The frame shuffle of MatrixRandomizer::Randomize (src/aslp-nnet/nnet-randomizer.cc:75-90). */
+int aslp_copy_rows(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, const int* idx_dev, int rows, int cols);
 /* Softmax::PropagateFnc, ApplySoftMaxPerRow (nnet-activation.h:49-52; kaldi-vector.cc:852-859) */
 int aslp_softmax_rows(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int cols);
 /* dst = alpha*src + beta*dst elementwise (AddMat / CopyFromMat / Scale; cu-kernels.cu:584) */

@@ -1,0 +1,81 @@
+// aslp-nnet-train-frame -- frame-shuffled minibatch training, same command line, bookkeeping and log lines as
+// src/aslp-nnetbin/aslp-nnet-train-frame.cc:22-153.  --use-gpu=no is refused: this build has no CPU path.
+#include "nnet-nnet.h"
+#include "nnet-loss.h"
+#include "nnet-randomizer.h"
+#include "nnet-trnopts.h"
+#include "parse-options.h"
+#include "table.h"
+
+int main(int argc, char* argv[]) {
+  using namespace kaldi;
+  using namespace kaldi::aslp_nnet;
+  try {
+    const char* usage =
+        "Perform one iteration of Neural Network training by mini-batch Stochastic Gradient Descent.\n"
+        "Usage:  aslp-nnet-train-frame [options] <feature-rspecifier> <targets-rspecifier> <model-in> [<model-out>]\n"
+        "e.g.: \n"
+        " aslp-nnet-train-frame scp:feature.scp ark:posterior.ark nnet.init nnet.iter1\n";
+    ParseOptions po(usage);
+    NnetTrainOptions trn_opts;
+    trn_opts.Register(&po);
+    NnetDataRandomizerOptions rnd_opts;
+    rnd_opts.Register(&po);
+    bool binary = true, crossvalidate = false, randomize = true;
+    po.Register("binary", &binary, "Write output in binary mode");
+    po.Register("cross-validate", &crossvalidate, "Perform cross-validation (don't backpropagate)");
+    po.Register("randomize", &randomize, "Perform the frame-level shuffling within the Cache::");
+    std::string objective_function = "xent";
+    po.Register("objective-function", &objective_function, "Objective function : xent|mse");
+    std::string use_gpu = "yes";
+    po.Register("use-gpu", &use_gpu, "yes|no|optional, only has effect if compiled with CUDA");
+    double dropout_retention = 0.0;
+    po.Register("dropout-retention", &dropout_retention, "number between 0..1, saying how many neurons to preserve (0.0 will keep original value");
+    int32 report_period = -1;
+    po.Register("report-period", &report_period, "Number of frames for one report log, default(-1, no report)");
+    int32 gpu_id = -1;
+    po.Register("gpu-id", &gpu_id, "selected gpu id, if negative then select automaticly");
+    po.Read(argc, argv);
+    if (po.NumArgs() != 4 - (crossvalidate ? 1 : 0)) { po.PrintUsage(); return 1; }
+    const std::string feature_rspecifier = po.GetArg(1), targets_rspecifier = po.GetArg(2), model_filename = po.GetArg(3);
+    std::string target_model_filename;
+    if (!crossvalidate) target_model_filename = po.GetArg(4);
+    if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
+    if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));
+    if (objective_function != "xent") KALDI_ERR << "Unsupported objective function: " << objective_function;
+    if (dropout_retention > 0.0) KALDI_ERR << "--dropout-retention: Dropout is not part of this build";
+
+    Nnet nnet;
+    nnet.Read(model_filename);
+    nnet.SetTrainOptions(trn_opts);
+    Xent loss;
+    Timer time;
+    long long total_frames = 0, report_frames = 0;
+    KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
+    FrameDataReader reader(feature_rspecifier, targets_rspecifier, rnd_opts);
+    const CuMatrixBase* nnet_in = nullptr;
+    const Posterior* nnet_tgt = nullptr;
+    CuMatrix nnet_out, obj_diff;
+    while (!reader.Done()) {
+      if (!reader.ReadData(&nnet_in, &nnet_tgt)) continue;
+      if (!crossvalidate) nnet.Propagate(*nnet_in, &nnet_out);
+      else nnet.Feedforward(*nnet_in, &nnet_out);
+      loss.Eval(nnet_out, *nnet_tgt, &obj_diff);
+      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      total_frames += nnet_in->NumRows();
+      report_frames += nnet_in->NumRows();
+      if (report_period > 0 && report_frames >= report_period) {
+        KALDI_LOG << loss.Report();
+        report_frames -= report_period;
+      }
+    }
+    if (!crossvalidate) nnet.Write(target_model_filename, binary);
+    KALDI_LOG << "[" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", " << (randomize ? "RANDOMIZED" : "NOT-RANDOMIZED") << ", "
+              << time.Elapsed() / 60 << " min, fps" << total_frames / time.Elapsed() << "]";
+    KALDI_LOG << loss.Report();
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << e.what();
+    return -1;
+  }
+}

@@ -254,6 +254,21 @@ int col_reduce(cudaStream_t st, bool dot, float* vec, const float* a, int lda, c
   return 0;
 }
 
+// dst[r, :] = src[idx[r], :]  (idx < 0 -> zeros), 128-bit lanes along the row
+__global__ void copy_rows_kernel(float* dst, int ldd, const float* src, int lds, const int* idx, int rows, int cols) {
+  const int c4 = (cols + 3) >> 2;
+  const long long total = (long long)rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), q = (int)(i - (long long)r * c4);
+    const int sr = idx[r];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sr >= 0) v = *reinterpret_cast<const float4*>(src + (size_t)sr * lds + q * 4);
+    float* d = dst + (size_t)r * ldd + q * 4;
+    if (q * 4 + 3 < cols) *reinterpret_cast<float4*>(d) = v;
+    else { const float t[4] = {v.x, v.y, v.z, v.w}; for (int j = 0; q * 4 + j < cols; ++j) d[j] = t[j]; }
+  }
+}
+
 // 32x32 tiled transpose through shared memory (coalesced both ways)
 __global__ void transpose_kernel(float* dst, int ldd, const float* src, int lds, int rows, int cols) {
   __shared__ float tile[32][33];
@@ -283,6 +298,14 @@ __global__ void sum_check_kernel(const float* m, int ldm, int rows, int cols, do
 }  // namespace
 
 extern "C" {
+
+int aslp_copy_rows(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, const int* idx_dev, int rows, int cols) {
+  if (rows == 0 || cols == 0) return 0;
+  ASLP_REQUIRE(ldd % 4 == 0 && lds % 4 == 0 && idx_dev != nullptr);
+  copy_rows_kernel<<<ew_blocks(rows, cols), 256, 0, (cudaStream_t)s>>>(dst, ldd, src, lds, idx_dev, rows, cols);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
 
 int aslp_act_fwd(aslp_stream_t s, int kind, float* out, int ldo, const float* in, int ldi, int rows, int cols) {
   if (rows == 0 || cols == 0) return 0;

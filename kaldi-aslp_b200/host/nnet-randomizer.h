@@ -1,0 +1,187 @@
+// nnet-randomizer.h -- frame-level shuffling for the frame trainers, same options, capacity rules and shuffle order
+// as src/aslp-nnet/nnet-randomizer.{h,cc}, plus FrameDataReader (src/aslp-nnet/data-reader.cc:34-182, single
+// feature / single target form).  The frame matrix stays on the device; the shuffle is one row-gather launch.
+#ifndef ASLP_HOST_NNET_RANDOMIZER_H_
+#define ASLP_HOST_NNET_RANDOMIZER_H_
+#include <cstdlib>
+#include "matrix.h"
+#include "nnet-loss.h"
+#include "parse-options.h"
+#include "table.h"
+
+namespace kaldi {
+namespace aslp_nnet {
+
+struct NnetDataRandomizerOptions {
+  int32 randomizer_size, randomizer_seed, minibatch_size;
+  NnetDataRandomizerOptions() : randomizer_size(32768), randomizer_seed(777), minibatch_size(256) {}
+  void Register(OptionsItf* opts) {
+    opts->Register("randomizer-size", &randomizer_size, "Capacity of randomizer, length of concatenated utterances which are used for frame-level shuffling (in frames, affects memory consumption, max 8000000).");
+    opts->Register("randomizer-seed", &randomizer_seed, "Seed value for srand, sets fixed order of frame-level shuffling");
+    opts->Register("minibatch-size", &minibatch_size, "Size of a minibatch.");
+  }
+};
+
+class RandomizerMask {
+ public:
+  RandomizerMask() {}
+  void Init(const NnetDataRandomizerOptions& conf) {
+    KALDI_LOG << "Seeding by srand with : " << conf.randomizer_seed;
+    srand(conf.randomizer_seed);
+  }
+  // the reference calls std::random_shuffle(begin, end) (nnet-randomizer.cc:41), which libstdc++ implements as
+  // "for i = 1..n-1: swap(v[i], v[rand() % (i+1)])" on the C library's rand(); restated so that the frame order is
+  // the same as the reference trainer's for the same --randomizer-seed
+  const std::vector<int32>& Generate(int32 mask_size) {
+    mask_.resize(mask_size);
+    for (int32 i = 0; i < mask_size; ++i) mask_[i] = i;
+    for (int32 i = 1; i < mask_size; ++i) {
+      const int32 j = std::rand() % (i + 1);
+      if (i != j) std::swap(mask_[i], mask_[j]);
+    }
+    return mask_;
+  }
+ private:
+  std::vector<int32> mask_;
+};
+
+class MatrixRandomizer {
+ public:
+  MatrixRandomizer() : data_begin_(0), data_end_(0) {}
+  void Init(const NnetDataRandomizerOptions& conf) { conf_ = conf; }
+  void AddData(const CuMatrixBase& m) {
+    if (data_.NumCols() == 0) data_.Resize(conf_.randomizer_size, m.NumCols());
+    if (data_begin_ > 0) {
+      KALDI_ASSERT(data_begin_ <= data_end_);
+      const int32 leftover = data_end_ - data_begin_;
+      KALDI_ASSERT(leftover < data_begin_);
+      if (leftover > 0) data_.RowRange(0, leftover).CopyFromMat(data_.RowRange(data_begin_, leftover));
+      data_begin_ = 0; data_end_ = leftover;
+      data_.RowRange(leftover, data_.NumRows() - leftover).SetZero();
+    }
+    if (data_.NumRows() < data_end_ + m.NumRows()) {
+      CuMatrix aux(data_);
+      data_.Resize(data_end_ + m.NumRows() + 1000, data_.NumCols());
+      data_.RowRange(0, aux.NumRows()).CopyFromMat(aux);
+    }
+    data_.RowRange(data_end_, m.NumRows()).CopyFromMat(m);
+    data_end_ += m.NumRows();
+  }
+  bool IsFull() const { return data_begin_ == 0 && data_end_ > conf_.randomizer_size; }
+  int32 NumFrames() const { return data_end_; }
+  void Randomize(const std::vector<int32>& mask) {
+    KALDI_ASSERT(data_begin_ == 0 && data_end_ > 0 && data_end_ == static_cast<int32>(mask.size()));
+    data_aux_ = data_;
+    mask_dev_ = mask;
+    ASLP_OK(aslp_copy_rows(CuStream(), data_.Data(), data_.Stride(), data_aux_.Data(), data_aux_.Stride(), mask_dev_.Data(),
+                           static_cast<int>(mask.size()), data_.NumCols()));
+  }
+  bool Done() const { return data_end_ - data_begin_ < conf_.minibatch_size; }
+  void Next() { data_begin_ += conf_.minibatch_size; }
+  const CuMatrixBase& Value() {
+    KALDI_ASSERT(data_end_ - data_begin_ >= conf_.minibatch_size);
+    minibatch_.Resize(conf_.minibatch_size, data_.NumCols(), kUndefined);
+    minibatch_.CopyFromMat(data_.RowRange(data_begin_, conf_.minibatch_size));
+    return minibatch_;
+  }
+ private:
+  CuMatrix data_, data_aux_, minibatch_;
+  CuArrayInt mask_dev_;
+  int32 data_begin_, data_end_;
+  NnetDataRandomizerOptions conf_;
+};
+
+template <typename T>
+class StdVectorRandomizer {
+ public:
+  StdVectorRandomizer() : data_begin_(0), data_end_(0) {}
+  void Init(const NnetDataRandomizerOptions& conf) { conf_ = conf; }
+  void AddData(const std::vector<T>& v) {
+    if (data_.size() == 0) data_.resize(conf_.randomizer_size);
+    if (data_begin_ > 0) {
+      KALDI_ASSERT(data_begin_ <= data_end_);
+      const int32 leftover = data_end_ - data_begin_;
+      KALDI_ASSERT(leftover < data_begin_);
+      if (leftover > 0) std::copy(data_.begin() + data_begin_, data_.begin() + data_begin_ + leftover, data_.begin());
+      data_begin_ = 0; data_end_ = leftover;
+    }
+    if (data_.size() < data_end_ + v.size()) data_.resize(data_end_ + v.size() + 1000);
+    std::copy(v.begin(), v.end(), data_.begin() + data_end_);
+    data_end_ += static_cast<int32>(v.size());
+  }
+  bool IsFull() const { return data_begin_ == 0 && data_end_ > conf_.randomizer_size; }
+  int32 NumFrames() const { return data_end_; }
+  void Randomize(const std::vector<int32>& mask) {
+    KALDI_ASSERT(data_begin_ == 0 && data_end_ > 0 && data_end_ == static_cast<int32>(mask.size()));
+    std::vector<T> aux(data_);
+    for (size_t i = 0; i < mask.size(); ++i) data_.at(i) = aux.at(mask.at(i));
+  }
+  bool Done() const { return data_end_ - data_begin_ < conf_.minibatch_size; }
+  void Next() { data_begin_ += conf_.minibatch_size; }
+  const std::vector<T>& Value() {
+    KALDI_ASSERT(data_end_ - data_begin_ >= conf_.minibatch_size);
+    minibatch_.assign(data_.begin() + data_begin_, data_.begin() + data_begin_ + conf_.minibatch_size);
+    return minibatch_;
+  }
+ private:
+  std::vector<T> data_, minibatch_;
+  int32 data_begin_, data_end_;
+  NnetDataRandomizerOptions conf_;
+};
+typedef StdVectorRandomizer<std::vector<std::pair<int32, BaseFloat>>> PosteriorRandomizer;
+
+// features + frame targets -> shuffled minibatches (data-reader.cc:62-182)
+class FrameDataReader {
+ public:
+  FrameDataReader(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const NnetDataRandomizerOptions& rand_opts)
+      : feature_reader_(feature_rspecifier), targets_reader_(targets_rspecifier), read_done_(false) {
+    feature_randomizer_.Init(rand_opts);
+    targets_randomizer_.Init(rand_opts);
+    randomizer_mask_.Init(rand_opts);
+  }
+  bool Done() { return read_done_ && feature_randomizer_.Done(); }
+  bool ReadData(const CuMatrixBase** feat, const Posterior** targets) {
+    if (Done()) KALDI_ERR << "Already read done";
+    if (feature_randomizer_.Done()) FillRandomizer();
+    if (!Done()) {                         // even after a refill there may be less than one minibatch left
+      *feat = &feature_randomizer_.Value();
+      feature_randomizer_.Next();
+      *targets = &targets_randomizer_.Value();
+      targets_randomizer_.Next();
+      return true;
+    }
+    return false;
+  }
+ private:
+  void FillRandomizer() {
+    while (true) {
+      if (feature_randomizer_.IsFull()) break;
+      if (feature_reader_.Done()) { read_done_ = true; break; }
+      const std::string utt = feature_reader_.Key();
+      if (!targets_reader_.HasKey(utt)) {
+        KALDI_WARN << utt << ", missing targets";
+      } else {
+        const Matrix<BaseFloat>& mat = feature_reader_.Value();
+        const Posterior& targets = targets_reader_.Value(utt);
+        if (static_cast<int32>(targets.size()) != mat.NumRows()) KALDI_ERR << "feature and target dim must match";
+        CuMatrix dev; dev = mat;
+        feature_randomizer_.AddData(dev);
+        targets_randomizer_.AddData(targets);
+      }
+      feature_reader_.Next();
+    }
+    const std::vector<int32>& mask = randomizer_mask_.Generate(feature_randomizer_.NumFrames());
+    feature_randomizer_.Randomize(mask);
+    targets_randomizer_.Randomize(mask);
+  }
+  SequentialBaseFloatMatrixReader feature_reader_;
+  RandomAccessPosteriorReader targets_reader_;
+  MatrixRandomizer feature_randomizer_;
+  PosteriorRandomizer targets_randomizer_;
+  RandomizerMask randomizer_mask_;
+  bool read_done_;
+};
+
+}  // namespace aslp_nnet
+}  // namespace kaldi
+#endif

@@ -1,4 +1,9 @@
 #include "parallel.h"
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <thread>
 
 namespace kaldi {
 
@@ -118,6 +123,35 @@ bool SodWorker::Synchronize(int num_worker_samples) {
   ASLP_OK(aslp_sync_sod_apply_packed(CuStream(), opt, table_dev_, ntensors_, arena_.Data(), s1_.Data(), s2_.Data(), w_prev_.Data(), lr, p1, p2, 1e-8f, step_));
   ++step_;
   return true;
+}
+
+WorkerBootstrap::WorkerBootstrap() : rank(0), nranks(1) {
+  std::memset(id, 0, sizeof(id));
+  auto env_int = [](const char* a, const char* b, int dflt) {
+    const char* v = std::getenv(a);
+    if (v == nullptr) v = std::getenv(b);
+    return v != nullptr ? std::atoi(v) : dflt;
+  };
+  rank = env_int("RANK", "OMPI_COMM_WORLD_RANK", 0);
+  nranks = env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", 1);
+  KALDI_ASSERT(nranks >= 1 && rank >= 0 && rank < nranks);
+  const char* file = std::getenv("ASLP_NCCL_ID_FILE");
+  if (nranks > 1 && file == nullptr) KALDI_ERR << "WORLD_SIZE > 1 needs ASLP_NCCL_ID_FILE (a path every rank can reach) to pass the NCCL id";
+  if (rank == 0) {
+    ASLP_OK(aslp_comm_unique_id(id));
+    if (file != nullptr) {
+      const std::string tmp = std::string(file) + ".tmp";
+      { std::ofstream os(tmp, std::ios::binary); os.write(id, sizeof(id)); if (!os.good()) KALDI_ERR << "Cannot write " << tmp; }
+      if (std::rename(tmp.c_str(), file) != 0) KALDI_ERR << "Cannot publish " << file;
+    }
+  } else {
+    for (int tries = 0;; ++tries) {
+      std::ifstream is(file, std::ios::binary);
+      if (is.good()) { is.read(id, sizeof(id)); if (is.gcount() == static_cast<std::streamsize>(sizeof(id))) break; }
+      if (tries > 1200) KALDI_ERR << "Timed out waiting for " << file;
+      std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+  }
 }
 
 }  // namespace kaldi

@@ -62,6 +62,15 @@ class BmufWorker : public IWorker {
   CuVector w_prev_, delta_prev_;
 };
 
+// Process-launch bootstrap for the worker mains (what mpirun + MPI_Init did in the reference): rank and world size
+// from RANK / WORLD_SIZE (torchrun's variables; OMPI_COMM_WORLD_RANK / _SIZE are honoured too), the ncclUniqueId
+// through a file named by ASLP_NCCL_ID_FILE (rank 0 writes it atomically, the others wait for it).
+struct WorkerBootstrap {
+  char id[128];
+  int rank, nranks;
+  WorkerBootstrap();
+};
+
 struct OptimizerOption {
   std::string solver;
   float lr, momentum, adagrad_lr, rmsprop_lr, adam_lr, adadelta_gamma, adam_beta1, adam_beta2;

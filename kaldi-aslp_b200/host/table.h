@@ -1,0 +1,196 @@
+// table.h -- the slice of Kaldi's table I/O the trainer mains use (src/util/kaldi-table.h, kaldi-holder.h):
+//   SequentialBaseFloatMatrixReader   "ark:file", "scp:file" (entries "key path" or "key path:offset")
+//   RandomAccessPosteriorReader       Posterior archives  (src/hmm/posterior.cc:29-99 on-disk format)
+//   RandomAccessInt32VectorReader     std::vector<int32> archives (CTC label sequences)
+//   BaseFloatMatrixWriter             "ark:file", "ark,t:file"
+// Option letters after the type ("ark,s,cs:") are accepted and ignored; piped commands ("cmd |") and "-" are not
+// supported here (the recipes' feature pipes run upstream of the trainers).
+#ifndef ASLP_HOST_TABLE_H_
+#define ASLP_HOST_TABLE_H_
+#include <fstream>
+#include <map>
+#include <memory>
+#include "base.h"
+#include "io.h"
+#include "matrix.h"
+#include "nnet-loss.h"
+
+namespace kaldi {
+
+struct TableSpec { bool scp; bool text; std::string file; };
+inline TableSpec ParseSpecifier(const std::string& spec) {
+  const size_t colon = spec.find(':');
+  if (colon == std::string::npos) KALDI_ERR << "Invalid table specifier " << spec;
+  std::vector<std::string> opts;
+  SplitStringToVector(spec.substr(0, colon), ",", true, &opts);
+  TableSpec t{false, false, spec.substr(colon + 1)};
+  bool have_type = false;
+  for (const std::string& o : opts) {
+    if (o == "ark") have_type = true;
+    else if (o == "scp") { t.scp = true; have_type = true; }
+    else if (o == "t") t.text = true;
+  }
+  if (!have_type) KALDI_ERR << "Invalid table specifier " << spec << " (expected ark: or scp:)";
+  if (t.file.empty() || t.file == "-" || t.file.back() == '|') KALDI_ERR << "Unsupported table source '" << t.file << "' (files only)";
+  return t;
+}
+
+// reads the next whitespace-terminated key of an archive; false at end of file
+inline bool ReadArchiveKey(std::istream& is, std::string* key) {
+  key->clear();
+  is >> *key;
+  if (is.eof() && key->empty()) return false;
+  if (is.fail()) return false;
+  const int c = is.get();                       // the single separator after the key
+  if (c != ' ' && c != '\t' && c != '\n') KALDI_ERR << "Invalid archive: expected space after key " << *key;
+  return true;
+}
+inline bool ReadBinaryFlag(std::istream& is) {   // consumes "\0B" if present
+  if (is.peek() == '\0') { is.get(); if (is.get() != 'B') KALDI_ERR << "Invalid binary header in archive"; return true; }
+  return false;
+}
+
+struct MatrixHolder {
+  typedef Matrix<BaseFloat> T;
+  static void Read(std::istream& is, T* v) { const bool b = ReadBinaryFlag(is); v->Read(is, b); }
+};
+struct Int32VectorHolder {
+  typedef std::vector<int32> T;
+  static void Read(std::istream& is, T* v) {
+    const bool b = ReadBinaryFlag(is);
+    if (b) { ReadIntegerVector(is, true, v); return; }
+    std::string line;                           // text form: integers up to end of line
+    std::getline(is, line);
+    if (!SplitStringToIntegers(line, " \t\r", true, v)) KALDI_ERR << "Invalid integer vector line: " << line;
+  }
+};
+struct PosteriorHolder {
+  typedef Posterior T;
+  // src/hmm/posterior.cc:57-99
+  static void Read(std::istream& is, T* post) {
+    const bool b = ReadBinaryFlag(is);
+    post->clear();
+    if (b) {
+      int32 sz; ReadBasicType(is, true, &sz);
+      if (sz < 0 || sz > 10000000) KALDI_ERR << "Reading posterior: got negative or improbably large size " << sz;
+      post->resize(sz);
+      for (auto& fr : *post) {
+        int32 sz2; ReadBasicType(is, true, &sz2);
+        if (sz2 < 0) KALDI_ERR << "Reading posteriors: got negative size";
+        fr.resize(sz2);
+        for (auto& pr : fr) { ReadBasicType(is, true, &pr.first); ReadBasicType(is, true, &pr.second); }
+      }
+      return;
+    }
+    std::string line;
+    std::getline(is, line);
+    std::vector<std::string> tok;
+    SplitStringToVector(line, " \t\r", true, &tok);
+    size_t i = 0;
+    while (i < tok.size()) {
+      if (tok[i] != "[") KALDI_ERR << "Invalid posterior line (expected '['): " << line;
+      ++i;
+      std::vector<std::pair<int32, BaseFloat>> fr;
+      while (i < tok.size() && tok[i] != "]") {
+        if (i + 1 >= tok.size()) KALDI_ERR << "Invalid posterior line: " << line;
+        int32 id;
+        if (!ConvertStringToInteger(tok[i], &id)) KALDI_ERR << "Invalid posterior line: " << line;
+        fr.push_back(std::make_pair(id, static_cast<BaseFloat>(std::atof(tok[i + 1].c_str()))));
+        i += 2;
+      }
+      if (i >= tok.size()) KALDI_ERR << "Invalid posterior line (missing ']'): " << line;
+      ++i;
+      post->push_back(fr);
+    }
+  }
+};
+
+template <class Holder>
+class SequentialTableReader {
+ public:
+  typedef typename Holder::T T;
+  explicit SequentialTableReader(const std::string& rspecifier) : spec_(ParseSpecifier(rspecifier)), done_(false) {
+    main_.open(spec_.file, std::ios::in | std::ios::binary);
+    if (!main_.is_open()) KALDI_ERR << "Cannot open " << spec_.file;
+    Next();
+  }
+  bool Done() const { return done_; }
+  const std::string& Key() const { return key_; }
+  const T& Value() const { return value_; }
+  void Next() {
+    if (!spec_.scp) {
+      if (!ReadArchiveKey(main_, &key_)) { done_ = true; return; }
+      Holder::Read(main_, &value_);
+      return;
+    }
+    std::string line;
+    while (std::getline(main_, line)) {
+      std::vector<std::string> f;
+      SplitStringToVector(line, " \t\r", true, &f);
+      if (f.empty()) continue;
+      if (f.size() != 2) KALDI_ERR << "Invalid scp line: " << line;
+      key_ = f[0];
+      std::string path = f[1];
+      long long off = -1;
+      const size_t c = path.rfind(':');
+      if (c != std::string::npos && c + 1 < path.size() && path.find_first_not_of("0123456789", c + 1) == std::string::npos) {
+        off = std::atoll(path.c_str() + c + 1);
+        path = path.substr(0, c);
+      }
+      std::ifstream obj(path, std::ios::in | std::ios::binary);
+      if (!obj.is_open()) KALDI_ERR << "Cannot open " << path << " (scp entry " << key_ << ")";
+      if (off >= 0) obj.seekg(off);
+      Holder::Read(obj, &value_);
+      return;
+    }
+    done_ = true;
+  }
+ private:
+  TableSpec spec_;
+  std::ifstream main_;
+  bool done_;
+  std::string key_;
+  T value_;
+};
+
+// whole table in memory: the trainers look targets up by utterance key in feature order
+template <class Holder>
+class RandomAccessTableReader {
+ public:
+  typedef typename Holder::T T;
+  explicit RandomAccessTableReader(const std::string& rspecifier) {
+    for (SequentialTableReader<Holder> r(rspecifier); !r.Done(); r.Next()) map_[r.Key()] = r.Value();
+  }
+  bool HasKey(const std::string& k) const { return map_.count(k) != 0; }
+  const T& Value(const std::string& k) const {
+    auto it = map_.find(k);
+    if (it == map_.end()) KALDI_ERR << "Value() called for key " << k << " which is not in the table";
+    return it->second;
+  }
+ private:
+  std::map<std::string, T> map_;
+};
+
+typedef SequentialTableReader<MatrixHolder> SequentialBaseFloatMatrixReader;
+typedef RandomAccessTableReader<PosteriorHolder> RandomAccessPosteriorReader;
+typedef RandomAccessTableReader<Int32VectorHolder> RandomAccessInt32VectorReader;
+
+class BaseFloatMatrixWriter {
+ public:
+  explicit BaseFloatMatrixWriter(const std::string& wspecifier) : spec_(ParseSpecifier(wspecifier)) {
+    if (spec_.scp) KALDI_ERR << "scp output is not supported: " << wspecifier;
+    os_.open(spec_.file, std::ios::out | std::ios::binary);
+    if (!os_.is_open()) KALDI_ERR << "Cannot open " << spec_.file << " for writing";
+  }
+  void Write(const std::string& key, const Matrix<BaseFloat>& m) {
+    os_ << key << ' ';
+    if (!spec_.text) { os_.put('\0'); os_.put('B'); }
+    m.Write(os_, !spec_.text);
+  }
+ private:
+  TableSpec spec_;
+  std::ofstream os_;
+};
+
+}  // namespace kaldi
+#endif

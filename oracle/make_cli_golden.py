@@ -1,0 +1,104 @@
+"""Trainer-level golden fixtures (tests/golden/cli_*): tiny synthetic ark inputs plus the model and log the UNMODIFIED
+reference CPU trainers (oracle/_ref/aslp-nnet-init, aslp-nnet-train-frame, aslp-nnet-train-warp-ctc-streams, built by
+oracle/Makefile) write for them with --use-gpu=no.  The GPU tests run OUR binaries (kaldi-aslp_b200/build/bin) with the
+same command lines and compare.  Run in the build container: `python oracle/make_cli_golden.py`.  TEST INFRASTRUCTURE ONLY."""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(HERE, "_ref")
+GOLD = os.path.join(ROOT, "tests", "golden")
+ENV = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+
+
+def write_feats_ark(path, utts):
+    with open(path, "wb") as f:
+        for key, m in utts:
+            m = np.ascontiguousarray(m, np.float32)
+            f.write(key.encode() + b" \0BFM " + b"\x04" + struct.pack("<i", m.shape[0]) + b"\x04" + struct.pack("<i", m.shape[1]) + m.tobytes())
+
+
+def write_post_ark(path, utts):
+    with open(path, "w") as f:
+        for key, ids in utts:
+            f.write(key + " " + " ".join("[ %d 1 ]" % i for i in ids) + "\n")
+
+
+def write_int_ark(path, utts):
+    with open(path, "w") as f:
+        for key, ids in utts:
+            f.write(key + " " + " ".join(str(i) for i in ids) + "\n")
+
+
+def run(cmd, log):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=ENV)
+    open(log, "w").write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("%s failed:\n%s" % (" ".join(cmd), r.stdout))
+
+
+def frame_case():
+    d = os.path.join(GOLD, "cli_frame")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(11)
+    open(os.path.join(d, "proto.txt"), "w").write(
+        "<NnetProto>\n"
+        "<AffineTransform> <InputDim> 20 <OutputDim> 32 <BiasMean> -1.0 <BiasRange> 2.0 <ParamStddev> 0.2\n"
+        "<Sigmoid> <InputDim> 32 <OutputDim> 32\n"
+        "<AffineTransform> <InputDim> 32 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.2\n"
+        "<Softmax> <InputDim> 8 <OutputDim> 8\n"
+        "</NnetProto>\n")
+    feats, post = [], []
+    for u in range(7):
+        n = int(rng.integers(40, 90))
+        feats.append(("utt%02d" % u, rng.standard_normal((n, 20)).astype(np.float32)))
+        post.append(("utt%02d" % u, rng.integers(0, 8, size=n).tolist()))
+    post = post[:5] + post[6:]                       # utt05 has no targets: must be skipped with a warning
+    write_feats_ark(os.path.join(d, "feats.ark"), feats)
+    write_post_ark(os.path.join(d, "post.ark"), post)
+    run([os.path.join(REF, "aslp-nnet-init"), "--seed=777", "--binary=true", os.path.join(d, "proto.txt"), os.path.join(d, "init.nnet")],
+        os.path.join(d, "ref_init.log"))
+    args = ["--use-gpu=no", "--minibatch-size=32", "--randomizer-size=200", "--randomizer-seed=777", "--learn-rate=0.02", "--momentum=0.9",
+            "--l2-penalty=0.0001", "ark:" + os.path.join(d, "feats.ark"), "ark:" + os.path.join(d, "post.ark"),
+            os.path.join(d, "init.nnet"), os.path.join(d, "ref_out.nnet")]
+    run([os.path.join(REF, "aslp-nnet-train-frame")] + args, os.path.join(d, "ref_train.log"))
+    open(os.path.join(d, "args.txt"), "w").write("--minibatch-size=32 --randomizer-size=200 --randomizer-seed=777 --learn-rate=0.02 --momentum=0.9 --l2-penalty=0.0001\n")
+
+
+def ctc_case():
+    d = os.path.join(GOLD, "cli_ctc")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(12)
+    open(os.path.join(d, "proto.txt"), "w").write(
+        "<NnetProto>\n"
+        "<BLstmProjectedStreams> <InputDim> 12 <OutputDim> 16 <CellDim> 8 <ClipGradient> 5 <ParamScale> 0.2\n"
+        "<AffineTransform> <InputDim> 16 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3\n"
+        "<Softmax> <InputDim> 8 <OutputDim> 8\n"
+        "</NnetProto>\n")
+    feats, labs = [], []
+    for u in range(7):
+        n = int(rng.integers(20, 40))
+        feats.append(("utt%02d" % u, rng.standard_normal((n, 12)).astype(np.float32)))
+        labs.append(("utt%02d" % u, rng.integers(1, 8, size=int(rng.integers(3, 8))).tolist()))
+    write_feats_ark(os.path.join(d, "feats.ark"), feats)
+    write_int_ark(os.path.join(d, "labels.ark"), labs)
+    run([os.path.join(REF, "aslp-nnet-init"), "--seed=777", "--binary=true", os.path.join(d, "proto.txt"), os.path.join(d, "init.nnet")],
+        os.path.join(d, "ref_init.log"))
+    flags = "--num-stream=3 --learn-rate=0.05 --momentum=0.9 --report-period=2 --report-step=2"
+    args = ["--use-gpu=no"] + flags.split() + ["ark:" + os.path.join(d, "feats.ark"), "ark:" + os.path.join(d, "labels.ark"),
+                                                os.path.join(d, "init.nnet"), os.path.join(d, "ref_out.nnet")]
+    run([os.path.join(REF, "aslp-nnet-train-warp-ctc-streams")] + args, os.path.join(d, "ref_train.log"))
+    open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
+
+
+if __name__ == "__main__":
+    frame_case()
+    ctc_case()
+    for c in ("cli_frame", "cli_ctc"):
+        d = os.path.join(GOLD, c)
+        print(c, sorted(os.listdir(d)), sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d)), "bytes")
