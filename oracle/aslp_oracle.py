@@ -442,3 +442,122 @@ def sod_optimize(opt, w, g, s1, s2, lr, p1, p2, step, floor=1e-8):
     else:
         raise ValueError(opt)
     return w.astype(F), s1.astype(F), s2.astype(F)
+
+
+# ---------------------------------------------------------------- Eesen CTC on probabilities (PARITY UNPINNED: the
+# reference implementation is GPU-only and has no tests; this follows the kernel sources line by line and the GPU tests
+# additionally cross-check it against warp-ctc, whose CPU path is pinned by its own known-answer tests)
+_LZ, _LINF, _EXPLIM, _FMAX = F(-1e30), F(1e30), F(88.722839), F(3.4028235e38)
+
+
+def _add_ab(a, b):      # ctc-utils.h:60-65
+    return _LZ if (a == _LZ or b == _LZ) else F(a + b)
+
+
+def _sub_ab(a, b):      # ctc-utils.h:67-73
+    if a == _LZ:
+        return _LZ
+    if b == _LZ:
+        return _LINF
+    return F(a - b)
+
+
+def _exp_a(a):          # ctc-utils.h:41-47
+    if a <= _LZ:
+        return F(0)
+    if a >= _EXPLIM:
+        return _FMAX
+    return F(np.exp(F(a)))
+
+
+def _log_a_plus_b(a, b):   # ctc-utils.h:76-82
+    if b < a:
+        return _add_ab(a, F(np.log(F(1) + _exp_a(_sub_ab(b, a)))))
+    return _add_ab(b, F(np.log(F(1) + _exp_a(_sub_ab(a, b)))))
+
+
+def ctc_eesen(probs, labels, seq_len, T, S):
+    """Ctc::EvalParallel (src/aslp-nnet/ctc-loss.cc:115-189) with the kernels _compute_ctc_alpha/beta/error_multiple_sequence
+    (src/aslp-cudamatrix/cu-kernels.cu:3276-3315, 3391-3451, 3512-3534).  probs [T*S, K] stream-interleaved softmax outputs.
+    Returns (pzx[S] = log p(z|x), diff [T*S, K] w.r.t. the pre-softmax activations, before the +-1 clip)."""
+    probs = np.asarray(probs, F)
+    K = probs.shape[1]
+    Lmax = max(len(l) for l in labels)
+    E = 2 * Lmax + 1
+    lab = -np.ones((S, E), np.int64)
+    for s, l in enumerate(labels):
+        for i, c in enumerate(l):
+            lab[s, 2 * i] = 0
+            lab[s, 2 * i + 1] = c
+        lab[s, 2 * len(l)] = 0
+    with np.errstate(divide="ignore"):
+        logp = np.log(probs).astype(F)
+    alpha = np.full((T * S, E), _LZ, F)
+    beta = np.full((T * S, E), _LZ, F)
+    for t in range(T):
+        for s in range(S):
+            if t >= seq_len[s]:
+                continue
+            r, rp = t * S + s, (t - 1) * S + s
+            for j in range(E):
+                c = lab[s, j]
+                if c == -1:
+                    continue
+                lp = logp[r, c]
+                if t == 0:
+                    alpha[r, j] = lp if j < 2 else _LZ
+                elif j > 1:
+                    tmp = _log_a_plus_b(alpha[rp, j - 1], alpha[rp, j])
+                    if not (j % 2 == 0 or lab[s, j - 2] == c):
+                        tmp = _log_a_plus_b(alpha[rp, j - 2], tmp)
+                    alpha[r, j] = _add_ab(lp, tmp)
+                elif j == 1:
+                    alpha[r, j] = _add_ab(lp, _log_a_plus_b(alpha[rp, 0], alpha[rp, 1]))
+                else:
+                    alpha[r, j] = _add_ab(lp, alpha[rp, 0])
+    for t in range(T - 1, -1, -1):
+        for s in range(S):
+            if t >= seq_len[s]:
+                continue
+            r, rn = t * S + s, (t + 1) * S + s
+            ll = 2 * len(labels[s]) + 1
+            for j in range(E):
+                c = lab[s, j]
+                if c == -1:
+                    continue
+                lp = logp[r, c]
+                if t == seq_len[s] - 1:
+                    beta[r, j] = lp if j > ll - 3 else _LZ
+                elif j < ll - 2:
+                    tmp = _log_a_plus_b(beta[rn, j + 1], beta[rn, j])
+                    if not (j % 2 == 0 or lab[s, j + 2] == c):
+                        tmp = _log_a_plus_b(beta[rn, j + 2], tmp)
+                    beta[r, j] = _add_ab(lp, tmp)
+                elif j == ll - 2:
+                    beta[r, j] = _add_ab(lp, _log_a_plus_b(beta[rn, j + 1], beta[rn, j]))
+                else:
+                    beta[r, j] = _add_ab(lp, beta[rn, j])
+    pzx = np.zeros(S, F)
+    for s in range(S):
+        ll = 2 * len(labels[s]) + 1
+        r = (seq_len[s] - 1) * S + s
+        t1, t2 = np.float64(alpha[r, ll - 1]), np.float64(alpha[r, ll - 2])      # LogAPlusB<double>: -1e30 is no sentinel there
+        hi, lo = (t1, t2) if t1 > t2 else (t2, t1)
+        pzx[s] = F(hi + np.log1p(np.exp(lo - hi)))
+    err = np.zeros((T * S, K), F)
+    for r in range(T * S):
+        s, t = r % S, r // S
+        if t >= seq_len[s]:
+            continue
+        for k in range(K):
+            e = _LZ
+            for j in range(E):
+                if lab[s, j] == k:
+                    e = _log_a_plus_b(e, _add_ab(alpha[r, j], beta[r, j]))
+            y = probs[r, k]
+            val = _exp_a(_sub_ab(e, _add_ab(pzx[s], _LZ if y == 0 else F(2) * F(np.log(y)))))
+            err[r, k] = F(-1.0) * val
+    err = (err * probs).astype(F)                                   # ctc_err_.MulElements(net_out)
+    row_sum = err.sum(axis=1, dtype=F)
+    diff = (err - probs * row_sum[:, None]).astype(F)
+    return pzx, diff

@@ -285,3 +285,19 @@ def test_sync_kernels():
         sync()
         ww, ws1, ws2 = O.sod_optimize(name, w[2], gg, s1, s2, 0.01, p1, 0.999, 3)
         assert np.allclose(dw.cpu().numpy(), ww, rtol=2e-5, atol=1e-6), name
+
+
+@pytest.mark.parametrize("rows,cols,nsrc", [(37, 40, 50), (256, 441, 300), (5, 3, 9)])
+def test_copy_rows_is_an_exact_gather(rows, cols, nsrc):
+    """CuMatrixBase::CopyRows / cu::Randomize (the frame shuffle of MatrixRandomizer): dst[r] = src[idx[r]], idx < 0 -> zeros."""
+    from tests.gpu_utils import DMat, P, dvec, lib, ok, stream, sync
+    rng = np.random.default_rng(rows + cols)
+    src = rng.standard_normal((nsrc, cols)).astype(np.float32)
+    idx = rng.integers(0, nsrc, size=rows).astype(np.int32)
+    idx[rows // 2] = -1
+    S, D = DMat(src), DMat(rows=rows, cols=cols, fill=3.0)
+    ok(lib().aslp_copy_rows(stream(), D.ptr, D.ld, S.ptr, S.ld, P(dvec(idx, np.int32).data_ptr()), rows, cols))
+    sync()
+    want = src[np.maximum(idx, 0)]
+    want[idx < 0] = 0
+    assert np.array_equal(D.np(), want)               # pure data movement: bit-exact
