@@ -60,6 +60,7 @@ int aslp_device_sync(void);
 /* CUDA events: *event is created on first use; elapsed synchronises on `b` */
 int aslp_event_record(aslp_stream_t s, void** event);
 int aslp_event_elapsed_ms(void* a, void* b, float* ms);
+int aslp_stream_wait_event(aslp_stream_t s, void* event);   /* later work on s starts after `event` (recorded on another stream) */
 
 /* ---- dense contraction: CuMatrixBase::AddMatMat (cu-matrix.cc:1027-1062) ----
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C  (+ bias[n] broadcast over rows)
@@ -184,7 +185,7 @@ int aslp_lstm_seq_bwd(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, v
 /* measurement aid: CUDA-event timing of the persistent launches on their own stream (enable, run, read totals in ms) */
 int aslp_lstm_profile(int enable);
 int aslp_lstm_profile_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches);
-/* development aid: when dev_buf != NULL (long long[grid][8], device) thread 0 of every CTA accumulates clock64 ticks spent
+/* development aid: when dev_buf != NULL (long long[grid][12], device) thread 0 of every CTA accumulates clock64 ticks spent
  * {waiting for its CTA, in its own exchange poll, waiting for the CTA's polls, in the work units, [fwd: contraction, reduce, unit prologue]} over the launch */
 int aslp_lstm_debug_timing(long long* dev_buf);
 

@@ -48,7 +48,7 @@ struct Launch {
   int SG;                    // streams staged per group (multiple of 16)
   int SP;                    // staging stride in floats (SG + 4: conflict-free 128-bit reads)
   int pgroups, SGP;          // tensor-core form: parallel stream groups per direction and streams per group
-  long long* timing;         // debug: per-CTA clock64 totals [nCTA][4] = {wait for CTA, own poll, wait for CTA's polls, units}; or NULL
+  long long* timing;         // debug: per-CTA clock64 totals [nCTA][12] = {wait for CTA, own poll, wait for CTA's polls, units}; or NULL
 };
 #define RECUR_TICK(var) const long long var = (L.timing != nullptr && threadIdx.x == 0) ? clock64() : 0
 
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(Launch L) {
     }
   }
   if (L.timing != nullptr && threadIdx.x == 0)
-    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
+    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 12 + q] = tacc[q];
 }
 
 // ---------------------------------------------------------------- backward (BPTT, reference "version 1")
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
     }
   }
   if (L.timing != nullptr && threadIdx.x == 0)
-    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
+    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 12 + q] = tacc[q];
 }
 
 #include "lstm_mma.cuh"

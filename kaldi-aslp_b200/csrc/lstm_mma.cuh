@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
     if (p != nullptr) { prefetch_l2(p); prefetch_l2(p + C); prefetch_l2(p + 2 * C); prefetch_l2(p + 3 * C); }
   };
   warm(0); warm(1);
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? T + 1 : 0) * slot);
 
   for (int it = 0; it < nitems; ++it) {
@@ -294,15 +294,18 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
     }
     // next step's exchange copies: after the bookkeeping stores (about one store-to-L2 latency after the publish, so
     // the first round usually finds the data), before the prefetch address arithmetic; xT is free (contraction done)
+    RECUR_TICK(e0);
     if (hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    RECUR_TICK(e1);
     warm(it + 2);
+    if (L.timing != nullptr && threadIdx.x == 0) { tacc[8] += e0 - k4; tacc[9] += e1 - e0; tacc[10] += clock64() - e1; }
     if (L.timing != nullptr && threadIdx.x == 0) {
       const long long k5 = clock64();
       tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3; tacc[4] += k5 - k4;
     }
   }
   if (L.timing != nullptr && threadIdx.x == 0)
-    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
+    for (int q = 0; q < 12; ++q) L.timing[(size_t)blockIdx.x * 12 + q] = tacc[q];
 }
 
 // ---------------------------------------------------------------- backward (R == 0 form)
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
     prefetch_l2(dbuf + ((size_t)t * S + s) * lddb + 6 * C + cc);
   };
   warm(0); warm(1);
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? 0 : T + 1) * slot);
 
   for (int it = 0; it < nitems; ++it) {
@@ -441,15 +444,18 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
       d[0] = dg; d[C] = di; d[2 * C] = df; d[3 * C] = dout; d[4 * C] = dc; d[5 * C] = dh; d[6 * C] = dm;
       st[si] = dc; st[plane + si] = di; st[2 * plane + si] = df;
     }
+    RECUR_TICK(e0);
     if (hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    RECUR_TICK(e1);
     warm(it + 2);
+    if (L.timing != nullptr && threadIdx.x == 0) { tacc[8] += e0 - k4; tacc[9] += e1 - e0; tacc[10] += clock64() - e1; }
     if (L.timing != nullptr && threadIdx.x == 0) {
       const long long k5 = clock64();
       tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3; tacc[4] += k5 - k4;
     }
   }
   if (L.timing != nullptr && threadIdx.x == 0)
-    for (int q = 0; q < 8; ++q) L.timing[(size_t)blockIdx.x * 8 + q] = tacc[q];
+    for (int q = 0; q < 12; ++q) L.timing[(size_t)blockIdx.x * 12 + q] = tacc[q];
 }
 
 // ---------------------------------------------------------------- planning + dispatch

@@ -69,6 +69,11 @@ int aslp_event_record(aslp_stream_t s, void** event) {
   ASLP_CUDA(cudaEventRecord((cudaEvent_t)*event, (cudaStream_t)s));
   return 0;
 }
+int aslp_stream_wait_event(aslp_stream_t s, void* event) {
+  ASLP_REQUIRE(event != nullptr);
+  ASLP_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)event, 0));
+  return 0;
+}
 int aslp_event_elapsed_ms(void* a, void* b, float* ms) {
   ASLP_CUDA(cudaEventSynchronize((cudaEvent_t)b));
   ASLP_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));

@@ -3,8 +3,13 @@
 
 namespace kaldi {
 
-static aslp_stream_t g_stream = nullptr;
+static aslp_stream_t g_stream = nullptr;       // compute stream
+static aslp_stream_t g_side = nullptr;         // side stream (lazily created)
+static aslp_stream_t g_current = nullptr;      // what CuStream() hands out (compute stream unless inside a CuStreamScope)
 static bool g_stream_made = false;
+static bool g_side_pending = false;
+static void* g_ev_fork = nullptr;
+static void* g_ev_join = nullptr;
 
 void CuSelectDevice(int dev) {
   if (g_stream_made) KALDI_ERR << "CuSelectDevice must be called before the first device operation";
@@ -16,11 +21,41 @@ aslp_stream_t CuStream() {
     if (aslp_device_count(&n) != 0 || n <= 0)
       KALDI_ERR << "No CUDA device: this build has no CPU path (the reference's --use-gpu=no branch is the oracle, not the product)";
     ASLP_OK(aslp_stream_create(&g_stream));
+    g_current = g_stream;
     g_stream_made = true;
   }
-  return g_stream;
+  return g_current;
 }
-void CuSync() { ASLP_OK(aslp_stream_sync(CuStream())); }
+aslp_stream_t CuSideStream() {
+  CuStream();
+  if (g_side == nullptr) ASLP_OK(aslp_stream_create(&g_side));
+  return g_side;
+}
+bool CuAsyncEnabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ASLP_ASYNC_WGRAD"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+void CuFork() {
+  CuSideStream();
+  ASLP_OK(aslp_event_record(g_stream, &g_ev_fork));
+  ASLP_OK(aslp_stream_wait_event(g_side, g_ev_fork));
+  g_side_pending = true;
+}
+void CuJoin() {
+  if (!g_side_pending) return;
+  ASLP_OK(aslp_event_record(g_side, &g_ev_join));
+  ASLP_OK(aslp_stream_wait_event(g_stream, g_ev_join));
+  g_side_pending = false;
+}
+CuStreamScope::CuStreamScope(aslp_stream_t s) { CuStream(); saved_ = g_current; g_current = s; }
+CuStreamScope::~CuStreamScope() { g_current = saved_; }
+void CuSync() {
+  CuStream();
+  if (g_side != nullptr) ASLP_OK(aslp_stream_sync(g_side));
+  g_side_pending = false;
+  ASLP_OK(aslp_stream_sync(g_stream));
+}
 
 // ------------------------------------------------------------------ host containers
 template <typename Real> static const char* MatTok() { return sizeof(Real) == 4 ? "FM" : "DM"; }
@@ -343,17 +378,18 @@ std::string MomentStatistics(const CuVector& v) {
 #include "cu-workspace.h"
 #include <cstring>
 namespace kaldi {
-static void* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
+// one workspace per stream: [0] compute stream, [1] side stream
+static void* g_ws[2] = {nullptr, nullptr};
+static size_t g_ws_bytes[2] = {0, 0};
 void* CuWorkspace(size_t bytes) {
-  if (bytes > g_ws_bytes) {
-    CuStream();
-    if (g_ws != nullptr) { CuSync(); aslp_free(g_ws); g_ws = nullptr; }
+  const int w = (CuStream() == g_stream) ? 0 : 1;
+  if (bytes > g_ws_bytes[w]) {
+    if (g_ws[w] != nullptr) { CuSync(); aslp_free(g_ws[w]); g_ws[w] = nullptr; }
     const size_t cap = bytes + bytes / 4 + (1u << 20);
-    ASLP_OK(aslp_malloc(&g_ws, cap));
-    g_ws_bytes = cap;
+    ASLP_OK(aslp_malloc(&g_ws[w], cap));
+    g_ws_bytes[w] = cap;
   }
-  return g_ws;
+  return g_ws[w];
 }
 static int g_gemm_precision = -1;
 int GemmPrecision() {

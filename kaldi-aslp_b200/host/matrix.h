@@ -16,7 +16,23 @@ typedef enum { kNoTrans = 0, kTrans = 1 } MatrixTransposeType;
 
 aslp_stream_t CuStream();          // the process-wide compute stream (created on first use, device already selected)
 void CuSelectDevice(int dev);      // CuDevice::SelectGpuId equivalent; must precede the first CuStream()
-void CuSync();
+void CuSync();                     // waits for the compute stream AND the side stream
+// Side stream for work that is off the critical path of a pass (the weight-gradient GEMMs and the update of a layer
+// overlap the backward recurrence of the layer below).  CuFork(): later side-stream work starts after everything issued
+// so far on the compute stream.  CuStreamScope(CuSideStream()): every device call of this library inside the scope goes to
+// the side stream (CuStream() returns it, CuWorkspace() hands out the side stream's own workspace).  CuJoin(): the
+// compute stream waits for the side stream; a no-op when nothing was forked.  ASLP_ASYNC_WGRAD=0 disables the overlap.
+aslp_stream_t CuSideStream();
+bool CuAsyncEnabled();
+void CuFork();
+void CuJoin();
+class CuStreamScope {
+ public:
+  explicit CuStreamScope(aslp_stream_t s);
+  ~CuStreamScope();
+ private:
+  aslp_stream_t saved_;
+};
 
 template <typename Real>
 class Vector {

@@ -1,5 +1,6 @@
 #include "nnet-lstm-family.h"
 #include "cu-workspace.h"
+#include <memory>
 
 namespace kaldi {
 namespace aslp_nnet {
@@ -303,6 +304,14 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
     ASLP_OK(aslp_gemm(st, 0, 0, T * S, input_dim_, 4 * C, 1.0f, dgifo.Data(), dgifo.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(),
                       i == 0 ? 0.0f : 1.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, prec, nullptr, 0));
   }
+  // Everything below (weight gradients, then Update) is off the critical path of the backward pass: nothing downstream reads
+  // these weights or corr buffers before the next Propagate.  It goes to the side stream so that it overlaps the backward
+  // recurrence of the layer below, which is latency-bound and leaves most SMs idle (Nnet::Backpropagate joins at its end).
+  async_tail_ = CuAsyncEnabled();
+  if (async_tail_) CuFork();
+  std::unique_ptr<CuStreamScope> side_scope;
+  if (async_tail_) side_scope.reset(new CuStreamScope(CuSideStream()));
+  st = CuStream();
   for (int i = 0; i < tr_.ndirs; ++i) {
     Dir& d = d_[i];
     // rows of the forward buffers that held the recurrent input / previous cell of each step:
@@ -333,6 +342,8 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
 void LstmFamily::Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
   // plain -lr * corr: no per-component coefficient, no L2 (lc.h:1085-1110)
   const float lr = opts_.learn_rate;
+  std::unique_ptr<CuStreamScope> side_scope;
+  if (async_tail_) side_scope.reset(new CuStreamScope(CuSideStream()));     // stays behind this component's weight-gradient GEMMs
   aslp_stream_t st = CuStream();
   auto mat = [&](CuMatrix& w, const CuMatrix& c) { ASLP_OK(aslp_axpby(st, w.Data(), w.Stride(), c.Data(), c.Stride(), w.NumRows(), w.NumCols(), -lr, 1.0f)); };
   auto vec = [&](CuVector& w, const CuVector& c) { ASLP_OK(aslp_axpby(st, w.Data(), (w.Dim() + 3) / 4 * 4, c.Data(), (c.Dim() + 3) / 4 * 4, 1, w.Dim(), -lr, 1.0f)); };

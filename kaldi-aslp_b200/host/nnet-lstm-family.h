@@ -79,6 +79,7 @@ class LstmFamily : public UpdatableComponent {
   CuMatrix prev_state_;                 // [S, 7C+R] forward-direction carried state
   std::vector<int32> sequence_lengths_;
   CuArrayInt seq_len_dev_;
+  bool async_tail_ = false;             // the last BackpropagateFnc put its weight gradients on the side stream
   bool per_utt_reset_;                  // nnet-forward mode: 1 stream, state reset every call (the reference's function-local static)
 };
 

@@ -101,6 +101,7 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase*>& out_diff, std::
       }
     }
   }
+  CuJoin();      // weight gradients / updates that ran on the side stream are complete before anyone reads the weights
   if (NULL == in_diff) return;
   for (size_t i = 0; i < input_.size(); i++)
     if ((*in_diff)[i] != NULL) *((*in_diff)[i]) = input_diff_buf_[input_[i]];

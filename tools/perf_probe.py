@@ -123,7 +123,7 @@ if __name__ == "__main__":
         print(json.dumps(probe_ctc(1000, 2048, 72, 100)), flush=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "timing":    # per-phase clock64 breakdown of the recurrence kernels
-        tb = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+        tb = torch.zeros((148, 12), dtype=torch.int64, device="cuda")
         for R in (0,):
             for bwd in (False, True):
                 tb.zero_()
@@ -134,9 +134,9 @@ if __name__ == "__main__":
                 torch.cuda.synchronize()
                 t = tb.cpu().numpy().astype(np.float64)
                 used = t[t.sum(1) > 0] / 1000.0          # last launch only (buffer is overwritten); cycles per step
-                r["cycles_per_step_mean"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish"], used.mean(0).round(0).tolist()))
-                r["cycles_per_step_max"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish"], used.max(0).round(0).tolist()))
-                r["cycles_per_step_min"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish"], used.min(0).round(0).tolist()))
+                r["cycles_per_step_mean"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish", "fin_to_stores", "issue", "warm", "x11"], used.mean(0).round(0).tolist()))
+                r["cycles_per_step_max"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish", "fin_to_stores", "issue", "warm", "x11"], used.max(0).round(0).tolist()))
+                r["cycles_per_step_min"] = dict(zip(["poll", "sync1", "contract", "sync2", "finish", "rounds", "first_round", "to_publish", "fin_to_stores", "issue", "warm", "x11"], used.min(0).round(0).tolist()))
                 r["ctas"] = int(used.shape[0])
                 print(json.dumps(r), flush=True)
         sys.exit(0)
