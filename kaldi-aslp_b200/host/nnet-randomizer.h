@@ -182,6 +182,109 @@ class FrameDataReader {
   bool read_done_;
 };
 
+
+// multi-stream truncated-BPTT batches with target delay (data-reader.h:49-98, data-reader.cc:184-341)
+struct SequenceDataReaderOptions {
+  int32 batch_size, num_stream, drop_len, skip_width, targets_delay, length_tolerance;
+  double frame_limit;
+  SequenceDataReaderOptions() : batch_size(20), num_stream(100), drop_len(0), skip_width(1), targets_delay(5), length_tolerance(5), frame_limit(100000) {}
+  void Register(OptionsItf* opts) {
+    opts->Register("batch-size", &batch_size, "--LSTM-- BPTT batch_size");
+    opts->Register("num-stream", &num_stream, "--LSTM-- BPTT multistream training");
+    opts->Register("drop-len", &drop_len, "if Sentence frame length greater than drop_len,then drop it, default(0, no drop)");
+    opts->Register("skip-width", &skip_width, "num of frame for one skip(default 1, no skip)");
+    opts->Register("targets-delay", &targets_delay, "--LSTM-- BPTT targets delay");
+    opts->Register("length-tolerance", &length_tolerance, "Allowed length difference of features/targets (frames),for the whole utterance training");
+    opts->Register("frame-limit", &frame_limit, "Max number of frames to be processed for whole utterance training");
+  }
+};
+
+class SequenceDataReader {
+ public:
+  SequenceDataReader(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const SequenceDataReaderOptions& opts)
+      : opts_(opts), read_done_(false), feature_reader_(feature_rspecifier), target_reader_(targets_rspecifier),
+        curt_(opts.num_stream, 0), lent_(opts.num_stream, 0), new_utt_flags_(opts.num_stream, 0), keys_(opts.num_stream),
+        feats_(opts.num_stream), targets_(opts.num_stream) {}
+  bool Done() { return read_done_ && feature_reader_.Done(); }
+  const std::vector<int32>& GetNewUttFlags() const { return new_utt_flags_; }
+  // feat is left untouched once every stream is exhausted (the reference's FillBatchBuff skips the copy, data-reader.cc:297-322:
+  // the trainer then runs one more minibatch on the previous features with an all-zero mask -- kept)
+  void ReadData(CuMatrix* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
+    if (Done()) KALDI_ERR << "Already read done!";
+    AddNewUtt();
+    FillBatchBuff(feat, target, frame_mask);
+  }
+ private:
+  void AddNewUtt() {
+    for (int32 s = 0; s < opts_.num_stream; s++) {
+      if (curt_[s] < lent_[s]) { new_utt_flags_[s] = 0; continue; }
+      while (!feature_reader_.Done()) {
+        const std::string key = feature_reader_.Key();
+        const Matrix<BaseFloat>& mat = feature_reader_.Value();
+        if (opts_.drop_len > 0 && mat.NumRows() > opts_.drop_len) { KALDI_WARN << key << ", too long, droped"; feature_reader_.Next(); continue; }
+        if (!target_reader_.HasKey(key)) { KALDI_WARN << key << ", missing targets"; feature_reader_.Next(); continue; }
+        const Posterior& target = target_reader_.Value(key);
+        if (mat.NumRows() != static_cast<int32>(target.size())) {
+          KALDI_WARN << key << ", length miss-match between feats and targers, skip";
+          feature_reader_.Next();
+          continue;
+        }
+        if (opts_.skip_width > 1) {
+          const int32 skip_len = (mat.NumRows() - 1) / opts_.skip_width + 1;
+          feats_[s].Resize(skip_len, mat.NumCols());
+          targets_[s].assign(skip_len, Posterior::value_type());
+          for (int32 i = 0; i < skip_len; i++) {
+            std::copy(mat.RowData(i * opts_.skip_width), mat.RowData(i * opts_.skip_width) + mat.NumCols(), feats_[s].RowData(i));
+            targets_[s][i] = target[i * opts_.skip_width];
+          }
+        } else {
+          feats_[s] = mat;
+          targets_[s] = target;
+        }
+        keys_[s] = key;
+        curt_[s] = 0;
+        lent_[s] = feats_[s].NumRows();
+        new_utt_flags_[s] = 1;
+        feature_reader_.Next();
+        break;
+      }
+    }
+  }
+  void FillBatchBuff(CuMatrix* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
+    const int32 num_stream = opts_.num_stream, batch_size = opts_.batch_size, delay = opts_.targets_delay;
+    for (int32 s = 0; s < num_stream; s++) {
+      if (curt_[s] < lent_[s]) { read_done_ = false; break; }
+      read_done_ = true;
+    }
+    const int32 feat_dim = feats_[0].NumCols();
+    host_.Resize(batch_size * num_stream, feat_dim, kSetZero);
+    target->assign(batch_size * num_stream, Posterior::value_type());
+    frame_mask->Resize(batch_size * num_stream);
+    if (read_done_) return;
+    for (int32 t = 0; t < batch_size; t++) {
+      for (int32 s = 0; s < num_stream; s++) {
+        const int32 row = t * num_stream + s;
+        if (lent_[s] == 0) { curt_[s]++; continue; }      // a stream that never received an utterance (the reference indexes [-1] here)
+        if (curt_[s] < lent_[s]) { (*frame_mask)(row) = 1; (*target)[row] = targets_[s][curt_[s]]; }
+        else { (*frame_mask)(row) = 0; (*target)[row] = targets_[s][lent_[s] - 1]; }
+        const int32 src = (curt_[s] + delay < lent_[s]) ? curt_[s] + delay : lent_[s] - 1;    // shifted by the target delay, padded with the last frame
+        std::copy(feats_[s].RowData(src), feats_[s].RowData(src) + feat_dim, host_.RowData(row));
+        curt_[s]++;
+      }
+    }
+    *feat = host_;
+  }
+  SequenceDataReaderOptions opts_;
+  bool read_done_;
+  SequentialBaseFloatMatrixReader feature_reader_;
+  RandomAccessPosteriorReader target_reader_;
+  std::vector<int32> curt_, lent_, new_utt_flags_;
+  std::vector<std::string> keys_;
+  std::vector<Matrix<BaseFloat>> feats_;
+  std::vector<Posterior> targets_;
+  Matrix<BaseFloat> host_;
+};
+
 }  // namespace aslp_nnet
 }  // namespace kaldi
 #endif

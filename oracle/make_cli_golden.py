@@ -124,10 +124,38 @@ def lc_case():
     open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
 
 
+def lstm_case():
+    d = os.path.join(GOLD, "cli_lstm")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(14)
+    open(os.path.join(d, "proto.txt"), "w").write(
+        "<NnetProto>\n"
+        "<Lstm> <InputDim> 12 <OutputDim> 16 <ClipGradient> 5 <ParamScale> 0.2\n"
+        "<LstmProjectedStreams> <InputDim> 16 <OutputDim> 8 <CellDim> 16 <ClipGradient> 5 <ParamScale> 0.2\n"
+        "<AffineTransform> <InputDim> 8 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3\n"
+        "<Softmax> <InputDim> 8 <OutputDim> 8\n"
+        "</NnetProto>\n")
+    feats, post = [], []
+    for u in range(7):
+        n = int(rng.integers(9, 30))
+        feats.append(("utt%02d" % u, rng.standard_normal((n, 12)).astype(np.float32)))
+        post.append(("utt%02d" % u, rng.integers(0, 8, size=n).tolist()))
+    write_feats_ark(os.path.join(d, "feats.ark"), feats)
+    write_post_ark(os.path.join(d, "post.ark"), post)
+    run([os.path.join(REF, "aslp-nnet-init"), "--seed=777", "--binary=true", os.path.join(d, "proto.txt"), os.path.join(d, "init.nnet")],
+        os.path.join(d, "ref_init.log"))
+    flags = "--batch-size=5 --num-stream=3 --targets-delay=2 --learn-rate=0.02 --momentum=0.9 --report-period=2"
+    args = ["--use-gpu=no"] + flags.split() + ["ark:" + os.path.join(d, "feats.ark"), "ark:" + os.path.join(d, "post.ark"),
+                                                os.path.join(d, "init.nnet"), os.path.join(d, "ref_out.nnet")]
+    run([os.path.join(REF, "aslp-nnet-train-lstm-streams")] + args, os.path.join(d, "ref_train.log"))
+    open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
+
+
 if __name__ == "__main__":
     frame_case()
     ctc_case()
     lc_case()
-    for c in ("cli_frame", "cli_ctc", "cli_lc"):
+    lstm_case()
+    for c in ("cli_frame", "cli_ctc", "cli_lc", "cli_lstm"):
         d = os.path.join(GOLD, c)
         print(c, sorted(os.listdir(d)), sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d)), "bytes")
