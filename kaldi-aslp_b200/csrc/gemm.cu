@@ -6,7 +6,10 @@
 // TF32.  The default precision is a 3-pass split (a = hi + lo; hi*hi + lo*hi + hi*lo) that
 // restores fp32-grade products so the reference's 1e-4 parity bound holds.
 //
-//   warp 0      : TMA producer (one elected lane)
+// Persistent: one CTA per SM walks the (split, tile) work items; TWO TMEM accumulators (2 x 128 columns) so that the
+// epilogue of one tile (TMEM -> registers -> HBM) overlaps the main loop of the next.
+//
+//   warp 0      : TMA producer (one elected lane), runs ahead across tile boundaries
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane)
 //   warps 2..5  : epilogue (TMEM lane quarter = warp_id % 4)
 //   warps 6..9  : hi/lo splitter (3xTF32 only)
@@ -100,6 +103,7 @@ struct EpiParams {
   float* partial;      // split-K: [splits][M][ldp] raw accumulators, else NULL
   int ldp;
   int kb_per_split;
+  int tiles_m, tiles_n, splits;   // persistent scheduling: work item = (split z, tile row, tile column), z slowest
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -116,14 +120,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto full_bar  = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto split_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (3 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+  // two TMEM accumulators (2 x 128 columns): the epilogue of one tile overlaps the main loop of the next
+  auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int num_items = tiles_mn * p.splits;
+  // item -> (z, m0, n0, k-block range); consecutive items walk the tile columns of one row, so CTAs running at the same
+  // time share the A rows in L2
+  auto item_coords = [&](int item, int& z, int& m0, int& n0, int& kb_begin, int& kb_end) {
+    z = item / tiles_mn;
+    const int t = item - z * tiles_mn;
+    const int tm = t / p.tiles_n;
+    m0 = tm * BM; n0 = (t - tm * p.tiles_n) * BN;
+    kb_begin = z * p.kb_per_split;
+    kb_end = min(num_kb, kb_begin + p.kb_per_split);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -131,12 +146,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(empty_bar(s), 1);
       mbar_init(split_bar(s), 128);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 128 fp32 accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(tmem_slot)) : "memory");
+  if (warp == 1) {   // TMEM: 2 x 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -148,24 +163,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint32_t sb = sa + TILE_BYTES;
-        mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
-        if (!A_MN) {
-          tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);              // box {32 k, 128 rows}
-        } else {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int z, m0, n0, kb_begin, kb_end;
+        item_coords(item, z, m0, n0, kb_begin, kb_end);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + TILE_BYTES;
+          mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);              // box {32 k, 128 rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, full_bar(s), m0 + 32 * j, kb * BK);  // box {32 m, 32 k}
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmB, full_bar(s), kb * BK, n0);
-        } else {
+            for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, full_bar(s), m0 + 32 * j, kb * BK);  // box {32 m, 32 k}
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, full_bar(s), kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, full_bar(s), n0 + 32 * j, kb * BK);
+            for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, full_bar(s), n0 + 32 * j, kb * BK);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -174,123 +193,146 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=F32, a=b=TF32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA (K=8) = 32 B along the row
+      // MN-major: 4 boxes of [32 k][128 B]; LBO = box stride 4096 B; swizzle atom = 4 k-rows -> SBO = 512 B;
+      //           one MMA consumes 8 k-rows = 1024 B
+      const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+      const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+      const uint32_t a_lay = A_MN ? 1u : 2u, b_lay = B_MN ? 1u : 2u;
+      const uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
       int s = 0; uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(PASSES == 1 ? full_bar(s) : split_bar(s), ph);
+      int acc_idx = 0; uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int z, m0, n0, kb_begin, kb_end;
+        item_coords(item, z, m0, n0, kb_begin, kb_end);
+        mbar_wait(tmem_empty_bar(acc_idx), acc_ph ^ 1u);      // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint32_t sb = sa + TILE_BYTES;
-        // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA (K=8) = 32 B along the row
-        // MN-major: 4 boxes of [32 k][128 B]; LBO = box stride 4096 B; swizzle atom = 4 k-rows -> SBO = 512 B;
-        //           one MMA consumes 8 k-rows = 1024 B
-        const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
-        const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
-        const uint32_t a_lay = A_MN ? 1u : 2u, b_lay = B_MN ? 1u : 2u;
-        const uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc_idx * BN);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(PASSES == 1 ? full_bar(s) : split_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t da = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
-          const uint64_t db = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
-          const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
-          if (PASSES == 1) {
-            tc_mma_tf32(tmem_base, da, db, idesc, acc);
-          } else {
-            const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, b_sbo, b_lay);
-            tc_mma_tf32(tmem_base, da_lo, db, idesc, acc);     // small terms first
-            tc_mma_tf32(tmem_base, da, db_lo, idesc, 1u);
-            tc_mma_tf32(tmem_base, da, db, idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t da = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t db = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
+            const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+            if (PASSES == 1) {
+              tc_mma_tf32(tmem_d, da, db, idesc, acc);
+            } else {
+              const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, a_sbo, a_lay);
+              const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, b_sbo, b_lay);
+              tc_mma_tf32(tmem_d, da_lo, db, idesc, acc);     // small terms first
+              tc_mma_tf32(tmem_d, da, db_lo, idesc, 1u);
+              tc_mma_tf32(tmem_d, da, db, idesc, 1u);
+            }
           }
+          tc_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        tc_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        tc_commit(tmem_full_bar(acc_idx));    // accumulator complete (fires at once for an empty k range)
+        if (++acc_idx == 2) { acc_idx = 0; acc_ph ^= 1u; }
       }
-      tc_commit(tmem_full_bar);             // accumulator complete
     }
   } else if (warp < 6) {
     // ===================== epilogue =====================
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int q = warp & 3;                               // TMEM lane quarter this warp may read
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const bool has_work = kb_end > kb_begin;
+    int acc_idx = 0; uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int z, m0, n0, kb_begin, kb_end;
+      item_coords(item, z, m0, n0, kb_begin, kb_end);
+      mbar_wait(tmem_full_bar(acc_idx), acc_ph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool has_work = kb_end > kb_begin;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int nb = n0 + c * 32;
-      // tcgen05.ld is .sync.aligned: keep the warp convergent across iterations (no early continue)
-      if (row_ok && nb < p.N) {
-      if (p.partial != nullptr) {
-        float* dst = p.partial + ((size_t)blockIdx.z * p.M + row) * p.ldp + nb;
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_idx * BN + c * 32), v);
+        const int nb = n0 + c * 32;
+        // tcgen05.ld is .sync.aligned: keep the warp convergent across iterations (no early continue)
+        if (row_ok && nb < p.N) {
+        if (p.partial != nullptr) {
+          float* dst = p.partial + ((size_t)z * p.M + row) * p.ldp + nb;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (nb + j < p.N) {   // ldp is padded to a multiple of 4, so a float4 never crosses the row end
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (!has_work) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(dst + j) = o;
-          }
-        }
-      } else {
-        float* dst = p.C + (size_t)row * p.ldc + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (nb + j + 3 < p.N) {
-            float4 o;
-            o.x = p.alpha * __uint_as_float(v[j]);     o.y = p.alpha * __uint_as_float(v[j + 1]);
-            o.z = p.alpha * __uint_as_float(v[j + 2]); o.w = p.alpha * __uint_as_float(v[j + 3]);
-            if (p.beta != 0.f) {
-              const float4 old = *reinterpret_cast<const float4*>(dst + j);
-              o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
-            }
-            if (p.bias != nullptr) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (p.clip > 0.f) {
-              o.x = fminf(fmaxf(o.x, -p.clip), p.clip); o.y = fminf(fmaxf(o.y, -p.clip), p.clip);
-              o.z = fminf(fmaxf(o.z, -p.clip), p.clip); o.w = fminf(fmaxf(o.w, -p.clip), p.clip);
-            }
-            *reinterpret_cast<float4*>(dst + j) = o;
-          } else {
-            for (int jj = j; jj < j + 4 && nb + jj < p.N; ++jj) {
-              float o = p.alpha * __uint_as_float(v[jj]);
-              if (p.beta != 0.f) o += p.beta * dst[jj];
-              if (p.bias != nullptr) o += p.bias[nb + jj];
-              if (p.clip > 0.f) o = fminf(fmaxf(o, -p.clip), p.clip);
-              dst[jj] = o;
+          for (int j = 0; j < 32; j += 4) {
+            if (nb + j < p.N) {   // ldp is padded to a multiple of 4, so a float4 never crosses the row end
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (!has_work) o = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(dst + j) = o;
             }
           }
+        } else {
+          float* dst = p.C + (size_t)row * p.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (nb + j + 3 < p.N) {
+              float4 o;
+              o.x = p.alpha * __uint_as_float(v[j]);     o.y = p.alpha * __uint_as_float(v[j + 1]);
+              o.z = p.alpha * __uint_as_float(v[j + 2]); o.w = p.alpha * __uint_as_float(v[j + 3]);
+              if (p.beta != 0.f) {
+                const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+              }
+              if (p.bias != nullptr) {
+                const float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (p.clip > 0.f) {
+                o.x = fminf(fmaxf(o.x, -p.clip), p.clip); o.y = fminf(fmaxf(o.y, -p.clip), p.clip);
+                o.z = fminf(fmaxf(o.z, -p.clip), p.clip); o.w = fminf(fmaxf(o.w, -p.clip), p.clip);
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            } else {
+              for (int jj = j; jj < j + 4 && nb + jj < p.N; ++jj) {
+                float o = p.alpha * __uint_as_float(v[jj]);
+                if (p.beta != 0.f) o += p.beta * dst[jj];
+                if (p.bias != nullptr) o += p.bias[nb + jj];
+                if (p.clip > 0.f) o = fminf(fmaxf(o, -p.clip), p.clip);
+                dst[jj] = o;
+              }
+            }
+          }
         }
+        }
+        __syncwarp();
       }
-      }
-      __syncwarp();
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside tc_ld32): hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar(acc_idx));
+      if (++acc_idx == 2) { acc_idx = 0; acc_ph ^= 1u; }
     }
   } else {
     // ===================== hi/lo splitter (3xTF32) =====================
     if (PASSES == 3) {
       const int t = threadIdx.x - 192;            // 0..127
       int s = 0; uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(full_bar(s), ph);
-        float4* hi4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES);                   // A then B, 32 KB
-        float4* lo4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * TILE_BYTES);  // A_lo then B_lo
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int z, m0, n0, kb_begin, kb_end;
+        item_coords(item, z, m0, n0, kb_begin, kb_end);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          float4* hi4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES);                   // A then B, 32 KB
+          float4* lo4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * TILE_BYTES);  // A_lo then B_lo
 #pragma unroll 4
-        for (int i = 0; i < (2 * TILE_BYTES / 16) / 128; ++i) {
-          const int idx = t + i * 128;
-          float4 x = hi4[idx];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-          hi4[idx] = h;
-          lo4[idx] = l;
+          for (int i = 0; i < (2 * TILE_BYTES / 16) / 128; ++i) {
+            const int idx = t + i * 128;
+            // the tensor core reads a TF32 operand as the top 19 bits of the fp32 word, so the raw tile already IS the
+            // "hi" operand; only the residual has to be written (one third less shared-memory traffic per stage)
+            const float4 x = hi4[idx];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            lo4[idx] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+          mbar_arrive(split_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(split_bar(s));
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   }
@@ -299,7 +341,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem_base) : "memory");
   }
 }
 
@@ -416,16 +458,20 @@ bool make_tmap(CUtensorMap* tm, const float* base, int inner_extent, int outer_e
 }
 
 template <bool A_MN, bool B_MN, int PASSES>
-int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int splits) {
+int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p_in, int splits) {
   constexpr int STAGES = (PASSES == 1) ? 6 : 3;
   constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * (3 * STAGES + 1) + 16;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * (3 * STAGES + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     ASLP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  dim3 grid(aslp_div_up(p.N, BN), aslp_div_up(p.M, BM), splits);
+  EpiParams p = p_in;
+  p.tiles_m = aslp_div_up(p.M, BM); p.tiles_n = aslp_div_up(p.N, BN); p.splits = splits;
+  // persistent: one CTA per SM walks the (split, tile) work items with a stride of the grid size
+  const long long items = (long long)p.tiles_m * p.tiles_n * splits;
+  const int grid = (int)(items < aslp_num_sms() ? items : aslp_num_sms());
   gemm_tf32_kernel<A_MN, B_MN, PASSES><<<grid, PASSES == 1 ? 192 : 320, SMEM, st>>>(ta, tb, p);
   ASLP_CHECK_LAUNCH();
   return 0;
