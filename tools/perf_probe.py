@@ -117,6 +117,21 @@ if __name__ == "__main__":
         print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, False)), flush=True)
         print(json.dumps(probe_lstm(1000, 16, 320, 320, 2, True)), flush=True)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gemm1":     # one large 3xTF32 and one TF32 GEMM for an ncu capture
+        orig = timeit
+        def timeit(fn, iters=1, warm=0):                  # noqa: F811
+            return orig(fn, iters=1, warm=0)
+        globals()["timeit"] = timeit
+        print(json.dumps(probe_gemm(16000, 1280, 640, False, True, 0)), flush=True)
+        print(json.dumps(probe_gemm(16000, 1280, 640, False, True, 1)), flush=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ctc1":
+        orig = timeit
+        def timeit(fn, iters=1, warm=0):                  # noqa: F811
+            return orig(fn, iters=1, warm=0)
+        globals()["timeit"] = timeit
+        print(json.dumps(probe_ctc(1000, 16, 72, 100)), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ctc":
         print(json.dumps(probe_ctc(1000, 16, 72, 100)), flush=True)
         print(json.dumps(probe_ctc(1000, 256, 72, 100)), flush=True)
