@@ -73,6 +73,16 @@ int aslp_train_step_xent(aslp_nnet_t n, aslp_xent_t x, const float* features, in
 int aslp_train_step_ctc(aslp_nnet_t n, aslp_warpctc_t c, const float* features, int features_on_device, int rows, int cols,
                         const int* frame_num_utt, int nseq, const int* flat_labels, const int* label_lengths,
                         float norm_learn_rate, int with_error_rate, float* costs_out);
+/* Eesen-style CTC (kaldi::aslp_nnet::Ctc, src/aslp-nnet/ctc-loss.{h,cc}); the loop body of aslp-nnet-train-ctc-streams.cc:160-205:
+ * SetSeqLengths, learn-rate normalisation, Propagate, Ctc::EvalParallel, ErrorRateMSeq (optional), Backpropagate.
+ * obj_out[nseq] receives -log p(z|x) per sequence. */
+typedef void* aslp_eesenctc_t;
+int aslp_eesenctc_create(aslp_eesenctc_t* out);
+int aslp_eesenctc_destroy(aslp_eesenctc_t c);
+int aslp_eesenctc_report(aslp_eesenctc_t c, char* buf, size_t buf_bytes);
+int aslp_train_step_ctc_eesen(aslp_nnet_t n, aslp_eesenctc_t c, const float* features, int features_on_device, int rows, int cols,
+                              const int* frame_num_utt, int nseq, const int* flat_labels, const int* label_lengths,
+                              float norm_learn_rate, int with_error_rate, float* obj_out);
 /* pinned host staging + device upload helpers for the bench (aslp_malloc_host / CuMatrix with padded stride) */
 int aslp_nnet_upload(const float* host, int rows, int cols, float** device_out, int* stride_out);
 int aslp_nnet_free_device(float* device_ptr);

@@ -90,8 +90,8 @@ def build_host(verbose=False):
     bjobs = []
     for s in sorted(glob.glob(os.path.join(BIN_SRC, "*.cc"))):
         exe = os.path.join(BIN_OUT, os.path.basename(s)[:-3])
-        if _newer(s, exe, hdrs + [LIB_HOST]):
-            bjobs.append(["g++", *CXX_FLAGS, s, "-o", exe, "-L", HERE, "-laslp_nnet", "-laslp_b200",
+        if _newer(s, exe, hdrs + glob.glob(os.path.join(BIN_SRC, "*.h")) + [LIB_HOST]):
+            bjobs.append(["g++", *CXX_FLAGS, "-I", BIN_SRC, s, "-o", exe, "-L", HERE, "-laslp_nnet", "-laslp_b200",
                           "-Wl,-rpath,$ORIGIN/../..", "-L/usr/local/cuda/lib64", "-lcudart",
                           "-Wl,-rpath,/usr/local/cuda/lib64", "-lpthread"])
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:

@@ -180,6 +180,42 @@ int aslp_train_step_ctc(aslp_nnet_t n, aslp_warpctc_t c, const float* features, 
   CAPI_END
 }
 
+int aslp_eesenctc_create(aslp_eesenctc_t* out) { CAPI_BEGIN *out = new Ctc(); CAPI_END }
+int aslp_eesenctc_destroy(aslp_eesenctc_t c) { CAPI_BEGIN delete static_cast<Ctc*>(c); CAPI_END }
+int aslp_eesenctc_report(aslp_eesenctc_t c, char* buf, size_t bytes) { CAPI_BEGIN CopyOut(static_cast<Ctc*>(c)->Report(), buf, bytes); CAPI_END }
+
+int aslp_train_step_ctc_eesen(aslp_nnet_t n, aslp_eesenctc_t c, const float* features, int on_device, int rows, int cols,
+                              const int* frame_num_utt, int nseq, const int* flat_labels, const int* label_lengths, float norm_learn_rate,
+                              int with_error_rate, float* obj_out) {
+  CAPI_BEGIN
+  Nnet* net = N(n);
+  Ctc* ctc = static_cast<Ctc*>(c);
+  std::vector<int32> lens(frame_num_utt, frame_num_utt + nseq);
+  std::vector<std::vector<int32>> labels(nseq);
+  std::vector<std::string> keys(nseq);
+  int off = 0, valid_frames = 0;
+  for (int s = 0; s < nseq; ++s) {
+    labels[s].assign(flat_labels + off, flat_labels + off + label_lengths[s]);
+    off += label_lengths[s];
+    keys[s] = "utt" + ToString(s);
+    valid_frames += lens[s];
+  }
+  net->SetSeqLengths(lens);
+  if (norm_learn_rate > 0.0f) {
+    NnetTrainOptions o = net->GetTrainOptions();
+    o.learn_rate = norm_learn_rate / valid_frames;
+    net->SetTrainOptions(o);
+  }
+  CuSubMatrix view(nullptr, 0, 0, 0);
+  const CuMatrixBase& in = StageFeatures(features, on_device, rows, cols, &view);
+  net->Propagate(in, &g_out);
+  ctc->EvalParallel(keys, lens, g_out, labels, &g_loss_diff);
+  if (with_error_rate) ctc->ErrorRateMSeq(lens, g_out, labels);
+  net->Backpropagate(g_loss_diff, NULL);
+  if (obj_out != nullptr) memcpy(obj_out, ctc->LastObj().data(), sizeof(float) * nseq);
+  CAPI_END
+}
+
 int aslp_nnet_upload(const float* host, int rows, int cols, float** device_out, int* stride_out) {
   CAPI_BEGIN
   const int stride = (cols + 3) / 4 * 4;

@@ -261,5 +261,136 @@ std::string WarpCtc::Report() {
   return oss.str();
 }
 
+
+// ------------------------------------------------------------------ Eesen CTC
+Ctc::Ctc()
+    : frames_(0), sequences_num_(0), ref_num_(0), error_num_(0), frames_progress_(0), ref_num_progress_(0), error_num_progress_(0),
+      sequences_progress_(0), obj_progress_(0.0), report_step_(100), obj_(0), loss_sum_(0), loss_square_sum_(0), loss_sum_bak_(0),
+      loss_square_sum_bak_(0), normal_num_(0), stat_period_(100) {}
+
+void Ctc::EvalParallel(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
+                       std::vector<std::vector<int32>>& label, CuMatrix* diff) {
+  KALDI_ASSERT(diff != NULL);
+  diff->Resize(net_out.NumRows(), net_out.NumCols(), kUndefined);      // the kernel writes every element
+  const int32 num_sequence = static_cast<int32>(frame_num_utt.size());
+  const int32 num_frames = net_out.NumRows();
+  KALDI_ASSERT(num_sequence > 0 && num_frames % num_sequence == 0);
+  const int32 num_frames_per_sequence = num_frames / num_sequence;
+  int32 max_label_len = 0;
+  for (int32 s = 0; s < num_sequence; s++) max_label_len = std::max<int32>(max_label_len, static_cast<int32>(label[s].size()));
+  // label expansion with blanks, padded with -1 (ctc-loss.cc:133-150)
+  const int32 exp_len_labels = 2 * max_label_len + 1;
+  std::vector<int32> label_expand(static_cast<size_t>(num_sequence) * exp_len_labels, -1);
+  for (int32 s = 0; s < num_sequence; s++) {
+    const std::vector<int32>& l = label[s];
+    for (size_t j = 0; j < l.size(); j++) {
+      if (l[j] >= net_out.NumCols()) KALDI_ERR << "label gt outdim " << l[j] << " " << net_out.NumCols();
+      label_expand[s * exp_len_labels + 2 * j] = 0;
+      label_expand[s * exp_len_labels + 2 * j + 1] = l[j];
+    }
+    label_expand[s * exp_len_labels + 2 * l.size()] = 0;
+  }
+  labels_dev_ = label_expand;
+  seq_len_dev_ = frame_num_utt;
+  pzx_dev_.Resize(num_sequence, kUndefined);
+  const size_t wsb = aslp_ctc_eesen_workspace_bytes(num_frames_per_sequence, num_sequence, net_out.NumCols(), exp_len_labels);
+  ASLP_OK(aslp_ctc_eesen(CuStream(), diff->Data(), diff->Stride(), net_out.Data(), net_out.Stride(), num_frames_per_sequence, num_sequence,
+                         net_out.NumCols(), labels_dev_.Data(), exp_len_labels, seq_len_dev_.Data(), pzx_dev_.Data(), CuWorkspace(wsb), wsb));
+  Vector<float> pzx_host;
+  pzx_dev_.CopyToVec(&pzx_host);
+  pzx_.resize(num_sequence);
+  for (int32 s = 0; s < num_sequence; s++) pzx_[s] = -pzx_host(s);                      // pzx.Scale(-1): the objective
+  StatAndAverageLossCheck(utt, frame_num_utt, pzx_, diff);
+  ASLP_OK(aslp_clamp(CuStream(), diff->Data(), diff->Stride(), diff->NumRows(), diff->NumCols(), -1.0f, 1.0f));
+  if (sequences_progress_ >= report_step_) {
+    KALDI_LOG << "Progress " << sequences_num_ << " sequences (" << frames_ / (100.0 * 3600) << "Hr):"
+              << " Obj(log[Pzx]) = " << obj_progress_ / sequences_progress_ << " Obj(frame) = " << obj_progress_ / frames_progress_
+              << " TokenAcc = " << 100.0 * (1.0 - error_num_progress_ / ref_num_progress_) << " %";
+    sequences_progress_ = 0; frames_progress_ = 0; obj_progress_ = 0.0; error_num_progress_ = 0; ref_num_progress_ = 0;
+  }
+}
+
+void Ctc::Eval(const CuMatrixBase& net_out, const std::vector<int32>& label, CuMatrix* diff) {
+  std::vector<std::string> utt(1, "utt");
+  std::vector<int32> frames(1, net_out.NumRows());
+  std::vector<std::vector<int32>> labels(1, label);
+  EvalParallel(utt, frames, net_out, labels, diff);
+}
+
+// ctc-loss.cc:229-296: unlike the warp-ctc variant the warm-up half of the window only takes finite losses in (0, 3000)
+void Ctc::StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
+                                  const std::vector<float>& pzx_host, CuMatrix* diff) {
+  const int32 num_sequence = static_cast<int32>(frame_num_utt.size());
+  for (int s = 0; s < num_sequence; s++) {
+    const double loss_per_frame = pzx_host[s] / frame_num_utt[s];
+    if (normal_num_ < stat_period_ / 2) {
+      if (KALDI_ISFINITE(pzx_host[s]) && pzx_host[s] > 0 && pzx_host[s] < 3000) {
+        normal_num_++;
+        loss_sum_ += loss_per_frame; loss_sum_bak_ += loss_per_frame;
+        loss_square_sum_ += loss_per_frame * loss_per_frame; loss_square_sum_bak_ += loss_per_frame * loss_per_frame;
+        obj_ += pzx_host[s]; obj_progress_ += pzx_host[s];
+      }
+    } else {
+      const double mean = loss_sum_ / normal_num_, sigma = sqrt(loss_square_sum_ / normal_num_);
+      if (KALDI_ISFINITE(pzx_host[s]) && (loss_per_frame >= (mean - 6 * sigma) && loss_per_frame <= (mean + 6 * sigma)) &&
+          (pzx_host[s] > 0 && pzx_host[s] < 3000)) {
+        normal_num_++;
+        loss_sum_ += loss_per_frame;
+        loss_square_sum_ += loss_per_frame * loss_per_frame;
+        obj_ += pzx_host[s]; obj_progress_ += pzx_host[s];
+        if (normal_num_ == stat_period_) {
+          loss_sum_ -= loss_sum_bak_; loss_square_sum_ -= loss_square_sum_bak_;
+          loss_sum_bak_ = loss_sum_; loss_square_sum_bak_ = loss_square_sum_;
+          normal_num_ = stat_period_ / 2;
+        }
+      } else {
+        KALDI_WARN << "Sequences " << utt[s] << " obj is abnormal(sum " << pzx_host[s] << " per_frame " << loss_per_frame << " mean "
+                   << loss_sum_ / normal_num_ << " sigma " << loss_square_sum_ / normal_num_ << "), drop it's diff and stat";
+        ASLP_OK(aslp_memset2d(CuStream(), diff->Data() + static_cast<size_t>(s) * diff->Stride(), sizeof(float) * diff->Stride() * num_sequence, 0,
+                              sizeof(float) * diff->NumCols(), frame_num_utt[s]));
+      }
+    }
+    frames_ += frame_num_utt[s];
+    frames_progress_ += frame_num_utt[s];
+  }
+  const double grad_sum = diff->Sum();
+  if (!KALDI_ISFINITE(grad_sum)) {
+    KALDI_WARN << "DIFF FINITE: nan or inf ocurred in the diff, ignore";
+    diff->SetZero();
+  }
+  sequences_progress_ += num_sequence;
+  sequences_num_ += num_sequence;
+}
+
+void Ctc::ErrorRateMSeq(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label) {
+  const int32 rows = net_out.NumRows();
+  int32* idx_dev = static_cast<int32*>(CuWorkspace(sizeof(int32) * (rows + 4)));
+  ASLP_OK(aslp_row_argmax(CuStream(), idx_dev, net_out.Data(), net_out.Stride(), rows, net_out.NumCols()));
+  std::vector<int32> data(rows);
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), data.data(), idx_dev, sizeof(int32) * rows));
+  CuSync();
+  const int32 num_seq = static_cast<int32>(frame_num_utt.size());
+  for (int32 s = 0; s < num_seq; s++) {
+    std::vector<int32> hyp;
+    int32 last = -1;
+    for (int32 f = 0; f < frame_num_utt[s]; f++) {          // greedy path, repetitions collapsed, blanks removed (ctc-loss.cc:385-424)
+      const int32 v = data[f * num_seq + s];
+      if (f == 0 || v != last) { if (v != 0) hyp.push_back(v); }
+      last = v;
+    }
+    int32 ins, del, sub;
+    const int32 err = LevenshteinEditDistance(label[s], hyp, &ins, &del, &sub);
+    error_num_ += err; ref_num_ += static_cast<int32>(label[s].size());
+    error_num_progress_ += err; ref_num_progress_ += static_cast<int32>(label[s].size());
+  }
+}
+
+std::string Ctc::Report() {
+  std::ostringstream oss;
+  oss << " Obj(log[Pzx]) = " << obj_ / sequences_num_ << " Obj(frame) = " << obj_ / frames_ << " TOKEN_ACCURACY >> "
+      << 100.0 * (1.0 - error_num_ / ref_num_) << " % <<";
+  return oss.str();
+}
+
 }  // namespace aslp_nnet
 }  // namespace kaldi

@@ -67,6 +67,41 @@ class WarpCtc {
   CuArrayInt maxid_;
 };
 
+// Eesen-style CTC on the softmax OUTPUTS (probabilities), errors back-propagated through the softmax
+// (src/aslp-nnet/ctc-loss.{h,cc}).  The reference computes it only on the GPU (2T+1 kernel launches per minibatch,
+// cu-kernels.cu:3276-3534); here one launch of aslp_ctc_eesen.  Statistics, the 6-sigma loss guard
+// (CTC_GRAD_CHECK == AVG_LOSS_CHECK, ctc-loss.h:36; window 100 utterances) and the report lines as in the reference.
+class Ctc {
+ public:
+  Ctc();
+  void EvalParallel(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
+                    std::vector<std::vector<int32>>& label, CuMatrix* diff);
+  // single sequence (ctc-loss.cc:33-113): the multi-sequence path with one stream
+  void Eval(const CuMatrixBase& net_out, const std::vector<int32>& label, CuMatrix* diff);
+  void ErrorRateMSeq(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label);
+  void SetReportStep(int32 report_step) { report_step_ = report_step; }
+  std::string Report();
+  float NumErrorTokens() const { return error_num_; }
+  int32 NumRefTokens() const { return ref_num_; }
+  const std::vector<float>& LastObj() const { return pzx_; }      // -log p(z|x) per sequence of the last call
+ private:
+  void StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
+                               const std::vector<float>& pzx_host, CuMatrix* diff);
+  int32 frames_, sequences_num_, ref_num_;
+  float error_num_;
+  int32 frames_progress_, ref_num_progress_;
+  float error_num_progress_;
+  int32 sequences_progress_;
+  double obj_progress_;
+  int32 report_step_;
+  double obj_;
+  double loss_sum_, loss_square_sum_, loss_sum_bak_, loss_square_sum_bak_;
+  int32 normal_num_, stat_period_;
+  std::vector<float> pzx_;
+  CuArrayInt labels_dev_, seq_len_dev_;
+  CuVector pzx_dev_;
+};
+
 int32 LevenshteinEditDistance(const std::vector<int32>& ref, const std::vector<int32>& hyp, int32* ins, int32* del, int32* sub);
 
 }  // namespace aslp_nnet

@@ -165,6 +165,32 @@ class WarpCtc:
         return buf.value.decode()
 
 
+class EesenCtc:
+    """kaldi::aslp_nnet::Ctc (src/aslp-nnet/ctc-loss.h): CTC on the softmax outputs, error back-propagated through the softmax."""
+
+    def __init__(self):
+        self.h = P()
+        _ck(host_lib().aslp_eesenctc_create(ctypes.byref(self.h)))
+
+    def report(self):
+        buf = ctypes.create_string_buffer(4096)
+        _ck(host_lib().aslp_eesenctc_report(self.h, buf, len(buf)))
+        return buf.value.decode()
+
+
+def train_step_ctc_eesen(nnet, ctc, feats, frame_num_utt, labels, norm_learn_rate=0.0, with_error_rate=False):
+    """Loop body of aslp-nnet-train-ctc-streams.cc.  Returns -log p(z|x) per sequence."""
+    lens = _i32(frame_num_utt)
+    fl = _i32(np.concatenate([np.asarray(l, np.int32) for l in labels]))
+    ll = _i32([len(l) for l in labels])
+    obj = np.zeros(lens.size, np.float32)
+    feats = _f32(feats)
+    rows, cols = feats.shape
+    _ck(host_lib().aslp_train_step_ctc_eesen(nnet.h, ctc.h, P(feats.ctypes.data), 0, rows, cols, lens.ctypes.data, lens.size, fl.ctypes.data,
+                                             ll.ctypes.data, float(norm_learn_rate), int(with_error_rate), obj.ctypes.data))
+    return obj
+
+
 def train_step_xent(nnet, xent, feats, targets, frame_mask=None, on_device=False, rows=None, cols=None):
     """Loop body of aslp-nnet-train-frame / -lstm-streams / -blstm-streams-lc (Propagate, Xent::Eval, Backpropagate)."""
     t = _i32(targets)

@@ -73,3 +73,53 @@ def test_eesen_and_warp_ctc_agree_on_cost_and_gradient():
     costs, grads = ctc_oracle.cost_and_grad(x.reshape(T, S, Kc), labels, lens)        # warp-ctc semantics (softmax inside)
     np.testing.assert_allclose(-pzx, costs, rtol=1e-4)
     assert np.max(np.abs(diff - grads.reshape(T * S, Kc))) <= 2e-4 * np.max(np.abs(grads))
+
+
+def test_eesen_ctc_host_class_through_the_net():
+    """kaldi::aslp_nnet::Ctc behind the trainer loop body: for the golden BLSTM-CTC net, the loss derivative that reaches the
+    Softmax component equals the restated Eesen error for the net's own outputs (clipped to +-1), the per-sequence objective
+    equals -log p(z|x), and the Softmax back-propagation is the reference's pass-through copy."""
+    import os
+    from kaldi_aslp_b200 import nnet as NN
+    from oracle import kaldi_io
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lc_blstm_ctc")
+    x = kaldi_io.read(os.path.join(d, "input.mat"))
+    labels = [list(map(int, l.split())) for l in open(os.path.join(d, "labels.txt"))]
+    S, T = 3, x.shape[0] // 3
+    net = NN.Nnet.read(os.path.join(d, "model.bin"))
+    net.set_train_options(0.0, 0.0, 0.0, 0.0)                 # learn rate 0: parameters untouched
+    ctc = NN.EesenCtc()
+    obj = NN.train_step_ctc_eesen(net, ctc, x, [T] * S, labels, with_error_rate=True)
+    ncomp = net.num_components
+    probs = net.component_output(ncomp - 1, T * S, 8)
+    got = net.component_out_diff(ncomp - 1, T * S, 8)
+    want_pzx, want_diff = O.ctc_eesen(probs, labels, [T] * S, T, S)
+    np.testing.assert_allclose(obj, -want_pzx, rtol=1e-5)
+    want_diff = np.clip(want_diff, -1.0, 1.0)
+    assert np.max(np.abs(got - want_diff)) <= 1e-4 * np.max(np.abs(want_diff))
+    rep = ctc.report()
+    assert "Obj(log[Pzx]) = " in rep and "TOKEN_ACCURACY" in rep
+    assert abs(float(rep.split("Obj(log[Pzx]) = ")[1].split()[0]) - float(np.mean(obj))) < 1e-3
+    net.close()
+
+
+def test_eesen_ctc_trainer_runs_and_learns(tmp_path):
+    """aslp-nnet-train-ctc-streams (no reference CPU build exists for it): two passes over the trainer-level CTC fixture; the
+    objective of the second pass must be lower than the first, the bookkeeping must match the warp-ctc trainer's."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "kaldi-aslp_b200", "build", "bin", "aslp-nnet-train-ctc-streams")
+    d = os.path.join(root, "tests", "golden", "cli_ctc")
+    objs = []
+    model = os.path.join(d, "init.nnet")
+    for it in range(2):
+        out = str(tmp_path / ("iter%d.nnet" % it))
+        r = subprocess.run([exe, "--num-stream=3", "--learn-rate=0.05", "--momentum=0.9", "ark:" + os.path.join(d, "feats.ark"),
+                            "ark:" + os.path.join(d, "labels.ark"), model, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:]
+        assert re.findall(r"Done (\d+) files, (\d+) with no targets", r.stdout)[-1] == ("7", "0")
+        objs.append(float(re.findall(r"Obj\(log\[Pzx\]\) = ([\d.eE+-]+)", r.stdout)[-1]))
+        model = out
+    assert objs[1] < objs[0], objs
