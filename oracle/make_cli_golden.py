@@ -151,11 +151,47 @@ def lstm_case():
     open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
 
 
+def fsmn_case():
+    d = os.path.join(GOLD, "cli_fsmn")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(15)
+    open(os.path.join(d, "proto.txt"), "w").write(
+        "<NnetProto>\n"
+        "<AffineTransform> <InputDim> 12 <OutputDim> 24 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.2\n"
+        "<ReLU> <InputDim> 24 <OutputDim> 24\n"
+        "<AffineTransform> <InputDim> 24 <OutputDim> 16 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.2\n"
+        "<CompactFsmn> <InputDim> 16 <OutputDim> 16 <PastContext> 4 <FutureContext> 3\n"
+        "<AffineTransform> <InputDim> 16 <OutputDim> 24 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.2\n"
+        "<ReLU> <InputDim> 24 <OutputDim> 24\n"
+        "<AffineTransform> <InputDim> 24 <OutputDim> 16 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.2\n"
+        "<CompactFsmn> <InputDim> 16 <OutputDim> 16 <PastContext> 4 <FutureContext> 3\n"
+        "<AffineTransform> <InputDim> 16 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3\n"
+        "<Softmax> <InputDim> 8 <OutputDim> 8\n"
+        "</NnetProto>\n")
+    feats, post = [], []
+    for u in range(6):
+        n = int(rng.integers(20, 60))
+        feats.append(("utt%02d" % u, rng.standard_normal((n, 12)).astype(np.float32)))
+        post.append(("utt%02d" % u, rng.integers(0, 8, size=n).tolist()))
+    post[2] = (post[2][0], post[2][1][:-3])          # 3 targets short: inside --length-tolerance=5, truncated to the minimum
+    post[4] = (post[4][0], post[4][1][:-9])          # 9 short: skipped, counted as other error
+    write_feats_ark(os.path.join(d, "feats.ark"), feats)
+    write_post_ark(os.path.join(d, "post.ark"), post)
+    run([os.path.join(REF, "aslp-nnet-init"), "--seed=777", "--binary=true", os.path.join(d, "proto.txt"), os.path.join(d, "init.nnet")],
+        os.path.join(d, "ref_init.log"))
+    flags = "--learn-rate=20.0 --momentum=0.5 --report-period=60"
+    args = ["--use-gpu=no"] + flags.split() + ["ark:" + os.path.join(d, "feats.ark"), "ark:" + os.path.join(d, "post.ark"),
+                                                os.path.join(d, "init.nnet"), os.path.join(d, "ref_out.nnet")]
+    run([os.path.join(REF, "aslp-nnet-train-perutt")] + args, os.path.join(d, "ref_train.log"))
+    open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
+
+
 if __name__ == "__main__":
     frame_case()
     ctc_case()
     lc_case()
     lstm_case()
-    for c in ("cli_frame", "cli_ctc", "cli_lc", "cli_lstm"):
+    fsmn_case()
+    for c in ("cli_frame", "cli_ctc", "cli_lc", "cli_lstm", "cli_fsmn"):
         d = os.path.join(GOLD, c)
         print(c, sorted(os.listdir(d)), sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d)), "bytes")
