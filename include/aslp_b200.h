@@ -121,6 +121,12 @@ int aslp_xent_dense(aslp_stream_t s, float* diff, int ldd, const float* y, int l
 /* row arg-max (FindRowMaxId, cu-kernels.cu:2141): first maximal index */
 int aslp_row_argmax(aslp_stream_t s, int* idx, const float* m, int ldm, int rows, int cols);
 
+/* ---- forwarder post-processing (src/aslp-nnetbin/aslp-nnet-forward.cc:184-207; nnet-pdf-prior.cc:73-86), one pass ----
+ * m = [log(m + log_add)] ; m[:,0] -= blank_shift (if > 0) ; m -= prior_scale * log_priors (if given).
+ * stats5_dev (float[5], overwritten): min / max of the input, min / max before the prior stage, #non-finite outputs. */
+int aslp_posterior_finalize(aslp_stream_t s, float* m, int ldm, int rows, int cols, int apply_log, float log_add, float blank_shift,
+                            const float* log_priors_dev, float prior_scale, float* stats5_dev);
+
 /* ---- Splice (src/aslp-nnet/nnet-various.h:139-175; cu-math.cc:153-166) ---- */
 int aslp_splice_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int dim,
                     const int* offsets_dev, int n_offsets);
@@ -137,8 +143,9 @@ int aslp_rowconv_bwd(aslp_stream_t s, float* in_diff, int ldd, float* w_diff, in
                      const float* w, int ldw, int future, const int* seq_len_dev);
 
 /* ---- BatchNormalization (src/aslp-nnet/nnet-batch-normalization.h:139-284) ----
- * train fwd: batch mean / inv-std (var_floor), xhat kept for backward, out = xhat*scale+shift,
- * fp64 running sums acc_mean += sum x, acc_var += sum x^2 (:217-219). */
+ * train fwd: batch mean / inv-std (var_floor), out = xhat*scale+shift, fp64 running sums acc_mean += sum x,
+ * acc_var += sum x^2 (:217-219).  xhat may be NULL (the backward recomputes it from in, mean, inv_std and ignores its
+ * xhat argument); when given it is filled for callers that want it. */
 int aslp_bn_fwd_train(aslp_stream_t s, float* out, int ldo, float* xhat, int ldx, const float* in, int ldi,
                       int rows, int cols, const float* scale, const float* shift, float var_floor,
                       float* mean, float* inv_std, double* acc_mean, double* acc_var);

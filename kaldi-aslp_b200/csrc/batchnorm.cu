@@ -1,7 +1,10 @@
 // BatchNormalization (src/aslp-nnet/nnet-batch-normalization.h:139-284): the reference spends ~12
 // elementwise launches forward and ~25 backward plus two fp32->fp64 matrix conversions; here the
-// forward is 2 column-statistics passes + 1 normalise pass and the backward 1 statistics pass +
-// 1 elementwise pass, all 128-bit, deterministic (two-phase column reductions, no atomics).
+// forward is ONE column-statistics pass (sum x, sum x^2 in double; the variance about the fp32 mean follows exactly from
+// them) + 1 normalise pass, and the backward 1 statistics pass + 1 elementwise pass; x-hat is recomputed from x, mean and
+// inv_std instead of being stored and re-read.  All 128-bit, deterministic (two-phase column reductions, no atomics).
+// HBM passes over the [rows, cols] matrix: forward 2 reads + 1 write (12 B/elem, 8 algorithmic), backward 4 reads + 1
+// write (20 B/elem, 16 algorithmic; the second read of a pass pair hits L2 when the minibatch fits it).
 #include "common.cuh"
 #include "scratch.cuh"
 
@@ -24,9 +27,8 @@ __device__ __forceinline__ void st4z(float* p, float4 v, int nv) {
   if (nv > 2) p[2] = v.z;
 }
 
-// MODE 0 (fwd pass 1): v0 = sum x (float order), v1 = sum (double)x, v2 = sum (double)fl(x*x)
-// MODE 1 (fwd pass 2): v0 = sum (x-mean)^2
-// MODE 2 (bwd)       : v0 = sum xhat*dy, v1 = sum dy, v2 = sum (x-mean)*dy, v3 = sum (x-mean)
+// MODE 0 (fwd): v0 = sum (double)x, v1 = sum (double)fl(x*x) (the reference's running sum), v2 = sum (double)x*(double)x
+// MODE 2 (bwd): v0 = sum xhat*dy, v1 = sum dy, v2 = sum (x-mean)*dy, v3 = sum (x-mean);  xhat = (x-mean)*inv_std (a = inv_std)
 // block = 256 threads = 32 column quads x 8 row lanes ; partial[chunk][v][colpad] in double
 template <int MODE>
 __global__ void bn_partial_kernel(double* partial, const float* x, int ldx, const float* a, int lda, const float* b, int ldb,
@@ -36,7 +38,7 @@ __global__ void bn_partial_kernel(double* partial, const float* x, int ldx, cons
   const int c = (blockIdx.x * 32 + cq) * 4;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
   const int colpad = ((cols + 3) >> 2) << 2;
-  constexpr int NV = (MODE == 0) ? 3 : (MODE == 1 ? 1 : 4);
+  constexpr int NV = (MODE == 0) ? 3 : 4;
   double acc[NV][4];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -44,25 +46,39 @@ __global__ void bn_partial_kernel(double* partial, const float* x, int ldx, cons
     for (int j = 0; j < 4; ++j) acc[v][j] = 0.0;
   if (c < cols) {
     const int nv = min(4, cols - c);
-    float mu[4] = {0.f, 0.f, 0.f, 0.f};
-    if (MODE != 0) { const float4 m4 = ld4z(mean + c, nv); mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; }
-    for (int r = r0 + rl; r < r1; r += 8) {
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, iv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE != 0) {
+      const float4 m4 = ld4z(mean + c, nv); mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+      const float4 i4 = ld4z(a + c, nv); iv[0] = i4.x; iv[1] = i4.y; iv[2] = i4.z; iv[3] = i4.w;
+    }
+    // two rows per iteration: twice the loads in flight per thread
+    for (int r = r0 + rl; r < r1; r += 16) {
+      const bool two = r + 8 < r1;
       const float4 x4 = ld4z(x + (size_t)r * ldx + c, nv);
-      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-      if (MODE == 0) {
+      const float4 y4 = two ? ld4z(x + (size_t)(r + 8) * ldx + c, nv) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = d4;
+      if (MODE == 2) {
+        d4 = ld4z(b + (size_t)r * ldb + c, nv);
+        if (two) e4 = ld4z(b + (size_t)(r + 8) * ldb + c, nv);
+      }
+      const float xv[2][4] = {{x4.x, x4.y, x4.z, x4.w}, {y4.x, y4.y, y4.z, y4.w}};
+      const float dv[2][4] = {{d4.x, d4.y, d4.z, d4.w}, {e4.x, e4.y, e4.z, e4.w}};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[0][j] += (double)xv[j]; acc[1][j] += (double)xv[j]; acc[2][j] += (double)(xv[j] * xv[j]); }
-      } else if (MODE == 1) {
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float d = xv[j] - mu[j]; acc[0][j] += (double)(d * d); }
-      } else {
-        const float4 h4 = ld4z(a + (size_t)r * lda + c, nv);   // xhat
-        const float4 d4 = ld4z(b + (size_t)r * ldb + c, nv);   // dy
-        const float hv[4] = {h4.x, h4.y, h4.z, h4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          for (int j = 0; j < 4; ++j) {
+            const double xd = (double)xv[u][j];
+            acc[0][j] += xd; acc[1][j] += (double)(xv[u][j] * xv[u][j]); acc[2][j] += xd * xd;
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float xm = xv[j] - mu[j];
-          acc[0][j] += (double)(hv[j] * dv[j]); acc[1][j] += (double)dv[j]; acc[2][j] += (double)(xm * dv[j]); acc[3][j] += (double)xm;
+          for (int j = 0; j < 4; ++j) {
+            const float xm = xv[u][j] - mu[j];
+            const float hv = xm * iv[j];
+            acc[0][j] += (double)(hv * dv[u][j]); acc[1][j] += (double)dv[u][j]; acc[2][j] += (double)(xm * dv[u][j]); acc[3][j] += (double)xm;
+          }
         }
       }
     }
@@ -90,19 +106,22 @@ __device__ __forceinline__ double sum_chunks(const double* partial, int chunks, 
   return s;
 }
 
-__global__ void bn_fwd_fin1_kernel(const double* partial, int chunks, int rows, int cols, float* mean, double* acc_mean, double* acc_var) {
+__global__ void bn_fwd_fin_kernel(const double* partial, int chunks, int rows, int cols, float var_floor, float* mean, float* inv_std,
+                                  double* acc_mean, double* acc_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const int colpad = ((cols + 3) >> 2) << 2;
-  mean[c] = (float)(sum_chunks(partial, chunks, 0, colpad, c) * (double)(1.0f / rows));     // AddRowSumMat(1/N, in)
-  if (acc_mean != nullptr) acc_mean[c] += sum_chunks(partial, chunks, 1, colpad, c);
-  if (acc_var != nullptr) acc_var[c] += sum_chunks(partial, chunks, 2, colpad, c);
-}
-__global__ void bn_fwd_fin2_kernel(const double* partial, int chunks, int rows, int cols, float var_floor, float* inv_std) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int colpad = ((cols + 3) >> 2) << 2;
-  float var = (float)(sum_chunks(partial, chunks, 0, colpad, c) * (double)(1.0f / rows));
+  const double s1 = sum_chunks(partial, chunks, 0, colpad, c), s2f = sum_chunks(partial, chunks, 1, colpad, c);
+  const double s2 = sum_chunks(partial, chunks, 2, colpad, c);
+  const float mu = (float)(s1 * (double)(1.0f / rows));                                     // AddRowSumMat(1/N, in)
+  mean[c] = mu;
+  if (acc_mean != nullptr) acc_mean[c] += s1;
+  if (acc_var != nullptr) acc_var[c] += s2f;
+  // (1/N) sum (x - mu)^2 about the ROUNDED fp32 mean, as the reference's second pass computes it, from the exact sums
+  const double m = (double)mu;
+  double ssq = s2 - 2.0 * m * s1 + (double)rows * m * m;
+  if (ssq < 0.0) ssq = 0.0;
+  float var = (float)(ssq * (double)(1.0f / rows));
   var += var_floor;                         // Add(var_floor); ApplyPow(0.5); InvertElements()
   inv_std[c] = 1.0f / sqrtf(var);
 }
@@ -192,11 +211,7 @@ int aslp_bn_fwd_train(aslp_stream_t s, float* out, int ldo, float* xhat, int ldx
   dim3 grid(p.col_blocks, p.chunks);
   bn_partial_kernel<0><<<grid, 256, 0, st>>>(partial, in, ldi, nullptr, 0, nullptr, 0, nullptr, rows, cols, p.rows_per_chunk);
   ASLP_CHECK_LAUNCH();
-  bn_fwd_fin1_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(partial, p.chunks, rows, cols, mean, acc_mean, acc_var);
-  ASLP_CHECK_LAUNCH();
-  bn_partial_kernel<1><<<grid, 256, 0, st>>>(partial, in, ldi, nullptr, 0, nullptr, 0, mean, rows, cols, p.rows_per_chunk);
-  ASLP_CHECK_LAUNCH();
-  bn_fwd_fin2_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(partial, p.chunks, rows, cols, var_floor, inv_std);
+  bn_fwd_fin_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(partial, p.chunks, rows, cols, var_floor, mean, inv_std, acc_mean, acc_var);
   ASLP_CHECK_LAUNCH();
   bn_normalize_kernel<<<ew_grid(rows, cols), 256, 0, st>>>(out, ldo, xhat, ldx, in, ldi, rows, cols, scale, shift, mean, inv_std);
   ASLP_CHECK_LAUNCH();
@@ -216,7 +231,8 @@ int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int l
                 int ldo, int rows, int cols, const float* scale, const float* mean, const float* inv_std, float momentum,
                 float* dscale, float* dshift) {
   if (rows == 0 || cols == 0) return 0;
-  ASLP_REQUIRE(ldi % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && (in_diff == nullptr || ldd % 4 == 0));
+  ASLP_REQUIRE(ldi % 4 == 0 && ldo % 4 == 0 && (in_diff == nullptr || ldd % 4 == 0));
+  (void)xhat; (void)ldx;
   cudaStream_t st = (cudaStream_t)s;
   const RedPlan p = plan_reduce(rows, cols);
   const size_t colpad = (size_t)(cols + 3) / 4 * 4;
@@ -225,7 +241,7 @@ int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int l
   float* dvar = (float*)((char*)partial + p.bytes);
   float* dmean = dvar + colpad;
   dim3 grid(p.col_blocks, p.chunks);
-  bn_partial_kernel<2><<<grid, 256, 0, st>>>(partial, in, ldi, xhat, ldx, out_diff, ldo, mean, rows, cols, p.rows_per_chunk);
+  bn_partial_kernel<2><<<grid, 256, 0, st>>>(partial, in, ldi, inv_std, 0, out_diff, ldo, mean, rows, cols, p.rows_per_chunk);   // xhat recomputed, not read
   ASLP_CHECK_LAUNCH();
   bn_bwd_fin_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(partial, p.chunks, rows, cols, scale, inv_std, momentum, dscale, dshift, dvar, dmean);
   ASLP_CHECK_LAUNCH();

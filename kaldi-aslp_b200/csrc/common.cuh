@@ -33,15 +33,29 @@ int aslp_num_sms();
 
 // ---- device math with the reference's formulas (matrix/kaldi-vector.cc:885-936) ----
 // Branch-free forms of the reference's overflow-safe split (x > 0: 1/(1+exp(-x)), else exp(x)/(exp(x)+1)); both
-// branches share e = exp(-|x|) and the denominator, so selecting the numerator gives the SAME bits without divergence.
+// branches share e = exp(-|x|) and the denominator, so selecting the numerator gives the SAME value without divergence.
+// exp and the division use the SFU forms (ex2.approx on x*log2(e), rcp.approx): ~2 ulp each, i.e. <= 3e-7 on outputs in
+// [0,1] -- far inside the 1e-4 parity bound -- and a third of the instructions of expf + IEEE division, which is what the
+// step time of the recurrent chains and the throughput of the Sigmoid/Tanh kernels are made of.
+// -DASLP_PRECISE_MATH restores expf and IEEE division.
+#ifdef ASLP_PRECISE_MATH
+__device__ __forceinline__ float aslp_exp(float x) { return expf(x); }
+__device__ __forceinline__ float aslp_div(float a, float b) { return a / b; }
+__device__ __forceinline__ float aslp_log1p_of_exp_neg(float d) { return log1pf(expf(-d)); }
+#else
+__device__ __forceinline__ float aslp_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float aslp_div(float a, float b) { return __fdividef(a, b); }
+// log(1 + exp(-d)), d >= 0: the argument of the log lies in (1, 2], where lg2.approx has an absolute error < 4e-7
+__device__ __forceinline__ float aslp_log1p_of_exp_neg(float d) { return __logf(1.0f + __expf(-d)); }
+#endif
 __device__ __forceinline__ float ref_sigmoid(float x) {
-  const float e = expf(-fabsf(x));
-  return (x > 0.0f ? 1.0f : e) / (1.0f + e);
+  const float e = aslp_exp(-fabsf(x));
+  return aslp_div(x > 0.0f ? 1.0f : e, 1.0f + e);
 }
 // x > 0: -1 + 2/(1+exp(-x)^2), else 1 - 2/(1+exp(x)^2): the two are exact negations of each other at equal |x|
 __device__ __forceinline__ float ref_tanh(float x) {
-  const float ie = expf(-fabsf(x));
-  const float v = -1.0f + 2.0f / (1.0f + ie * ie);
+  const float ie = aslp_exp(-fabsf(x));
+  const float v = -1.0f + aslp_div(2.0f, 1.0f + ie * ie);
   return x > 0.0f ? v : -v;
 }
 

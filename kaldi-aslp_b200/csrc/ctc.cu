@@ -24,7 +24,9 @@ __device__ __forceinline__ float neg_inf() { return -INFINITY; }
 __device__ __forceinline__ float log_plus(float p1, float p2) {
   if (p1 == neg_inf()) return p2;
   if (p2 == neg_inf()) return p1;
-  return log1pf(expf(-fabsf(p1 - p2))) + fmaxf(p1, p2);
+  // SFU forms (common.cuh): the absolute error (< 4e-7) is three orders below one ulp of the alpha / beta values this is
+  // added to on utterances of the BASELINE size (|alpha| ~ 3e3, ulp 2.4e-4); a fifth of the instructions of log1pf(expf())
+  return aslp_log1p_of_exp_neg(fabsf(p1 - p2)) + fmaxf(p1, p2);
 }
 
 // ---- 0. per-utterance CSR of the non-blank states of every label (ascending state order: the reference's accumulation order)

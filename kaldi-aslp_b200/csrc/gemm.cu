@@ -24,6 +24,9 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 32;           // BK floats = 128 B = one swizzle row
 constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB per operand tile
 constexpr uint32_t SPIN_LIMIT = 1u << 18;
+constexpr int STG_PITCH = 36;                        // epilogue staging tile pitch (floats)
+constexpr int BAR_REGION = 256;                      // mbarriers + the TMEM slot, after the stage buffers
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;    // one 32 x 32 chunk per epilogue warp
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +127,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tmem_full_bar  = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+  float* stage_base = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + BAR_REGION);   // [4 warps][32][STG_PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -244,60 +248,72 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       item_coords(item, z, m0, n0, kb_begin, kb_end);
       mbar_wait(tmem_full_bar(acc_idx), acc_ph);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
       const bool has_work = kb_end > kb_begin;
+      // Coalesced epilogue.  tcgen05.ld hands lane r the 32 columns of accumulator row r; storing that straight to HBM makes
+      // every store instruction touch 32 different rows (32 half-filled sectors, 32 LSU passes) and was what bounded the
+      // K <= 1280 shapes of this path.  The chunk goes through a padded per-warp staging tile instead (pitch 36 floats:
+      // conflict-free for 128-bit writes by row and 128-bit reads by row quarter), and is written out with 8 lanes covering
+      // 128 contiguous bytes of one row, 4 rows per instruction; beta reads of the old C are coalesced the same way.
+      float* stg = stage_base + (size_t)q * 32 * STG_PITCH;
+      const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_idx * BN + c * 32), v);
         const int nb = n0 + c * 32;
-        // tcgen05.ld is .sync.aligned: keep the warp convergent across iterations (no early continue)
-        if (row_ok && nb < p.N) {
-        if (p.partial != nullptr) {
-          float* dst = p.partial + ((size_t)z * p.M + row) * p.ldp + nb;
+        if (nb < p.N) {                         // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j < p.N) {   // ldp is padded to a multiple of 4, so a float4 never crosses the row end
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              if (!has_work) o = make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(dst + j) = o;
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          __syncwarp();
+          const int col = nb + sub_c;
+          const int nvalid = p.N - col;         // > 0: columns col .. col+3 that exist
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + sub_r;
+            const int row = m0 + q * 32 + rl;
+            if (row < p.M && nvalid > 0) {
+              float4 o = *reinterpret_cast<const float4*>(stg + rl * STG_PITCH + sub_c);
+              if (p.partial != nullptr) {
+                // ldp is padded to a multiple of 4, so a float4 never crosses the row end
+                if (!has_work) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(p.partial + ((size_t)z * p.M + row) * p.ldp + col) = o;
+              } else {
+                float* dst = p.C + (size_t)row * p.ldc + col;
+                o.x *= p.alpha; o.y *= p.alpha; o.z *= p.alpha; o.w *= p.alpha;
+                if (nvalid >= 4) {
+                  if (p.beta != 0.f) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst);
+                    o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                  }
+                  if (p.bias != nullptr) {
+                    const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                  }
+                  if (p.clip > 0.f) {
+                    o.x = fminf(fmaxf(o.x, -p.clip), p.clip); o.y = fminf(fmaxf(o.y, -p.clip), p.clip);
+                    o.z = fminf(fmaxf(o.z, -p.clip), p.clip); o.w = fminf(fmaxf(o.w, -p.clip), p.clip);
+                  }
+                  *reinterpret_cast<float4*>(dst) = o;
+                } else {
+                  const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int jj = 0; jj < 3; ++jj) {
+                    if (jj < nvalid) {
+                      float x = ov[jj];
+                      if (p.beta != 0.f) x += p.beta * dst[jj];
+                      if (p.bias != nullptr) x += p.bias[col + jj];
+                      if (p.clip > 0.f) x = fminf(fmaxf(x, -p.clip), p.clip);
+                      dst[jj] = x;
+                    }
+                  }
+                }
+              }
             }
           }
-        } else {
-          float* dst = p.C + (size_t)row * p.ldc + nb;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j + 3 < p.N) {
-              float4 o;
-              o.x = p.alpha * __uint_as_float(v[j]);     o.y = p.alpha * __uint_as_float(v[j + 1]);
-              o.z = p.alpha * __uint_as_float(v[j + 2]); o.w = p.alpha * __uint_as_float(v[j + 3]);
-              if (p.beta != 0.f) {
-                const float4 old = *reinterpret_cast<const float4*>(dst + j);
-                o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
-              }
-              if (p.bias != nullptr) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j);
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (p.clip > 0.f) {
-                o.x = fminf(fmaxf(o.x, -p.clip), p.clip); o.y = fminf(fmaxf(o.y, -p.clip), p.clip);
-                o.z = fminf(fmaxf(o.z, -p.clip), p.clip); o.w = fminf(fmaxf(o.w, -p.clip), p.clip);
-              }
-              *reinterpret_cast<float4*>(dst + j) = o;
-            } else {
-              for (int jj = j; jj < j + 4 && nb + jj < p.N; ++jj) {
-                float o = p.alpha * __uint_as_float(v[jj]);
-                if (p.beta != 0.f) o += p.beta * dst[jj];
-                if (p.bias != nullptr) o += p.bias[nb + jj];
-                if (p.clip > 0.f) o = fminf(fmaxf(o, -p.clip), p.clip);
-                dst[jj] = o;
-              }
-            }
-          }
+          __syncwarp();                         // the staging tile is rewritten by the next chunk
         }
-        }
-        __syncwarp();
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside tc_ld32): hand it back to the MMA warp
       tc_fence_before();
@@ -461,7 +477,8 @@ template <bool A_MN, bool B_MN, int PASSES>
 int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p_in, int splits) {
   constexpr int STAGES = (PASSES == 1) ? 6 : 3;
   constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * (3 * STAGES + 4) + 16;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + BAR_REGION + STG_BYTES;
+  static_assert(8 * (3 * STAGES + 4) + 16 <= BAR_REGION, "barrier region too small");
   static bool attr_set = false;
   if (!attr_set) {
     ASLP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

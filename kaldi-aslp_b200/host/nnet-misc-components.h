@@ -86,8 +86,7 @@ class BatchNormalization : public UpdatableComponent {
   void FeedforwardFnc(const CuMatrixBase& in, CuMatrixBase* out) {
     aslp_stream_t st = CuStream();
     if (num_acc_frames_ <= 0) {       // local statistics, nothing accumulated
-      xhat_.Resize(in.NumRows(), output_dim_, kUndefined);
-      ASLP_OK(aslp_bn_fwd_train(st, out->Data(), out->Stride(), xhat_.Data(), xhat_.Stride(), in.Data(), in.Stride(), in.NumRows(), output_dim_,
+      ASLP_OK(aslp_bn_fwd_train(st, out->Data(), out->Stride(), nullptr, 0, in.Data(), in.Stride(), in.NumRows(), output_dim_,
                                 scale_.Data(), shift_.Data(), var_floor_, mean_vec_.Data(), var_vec_.Data(), nullptr, nullptr));
     } else {
       ASLP_OK(aslp_bn_fwd_eval(st, out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), output_dim_, scale_.Data(), shift_.Data(),
@@ -96,14 +95,14 @@ class BatchNormalization : public UpdatableComponent {
   }
   void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
     if (!acc_cleaned_) { acc_cleaned_ = true; CleanAccs(); }      // running sums restart with the first training propagate (:178-181)
-    xhat_.Resize(in.NumRows(), output_dim_, kUndefined);
-    ASLP_OK(aslp_bn_fwd_train(CuStream(), out->Data(), out->Stride(), xhat_.Data(), xhat_.Stride(), in.Data(), in.Stride(), in.NumRows(), output_dim_,
+    // no x-hat buffer: the backward kernels recompute it from in, mean_vec_ and var_vec_ (= 1/std)
+    ASLP_OK(aslp_bn_fwd_train(CuStream(), out->Data(), out->Stride(), nullptr, 0, in.Data(), in.Stride(), in.NumRows(), output_dim_,
                               scale_.Data(), shift_.Data(), var_floor_, mean_vec_.Data(), var_vec_.Data(), acc_means_.Data(), acc_vars_.Data()));
     num_acc_frames_ += in.NumRows();
   }
   void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
-    ASLP_OK(aslp_bn_bwd(CuStream(), in_diff ? in_diff->Data() : nullptr, in_diff ? in_diff->Stride() : 0, in.Data(), in.Stride(), xhat_.Data(),
-                        xhat_.Stride(), out_diff.Data(), out_diff.Stride(), in.NumRows(), output_dim_, scale_.Data(), mean_vec_.Data(), var_vec_.Data(),
+    ASLP_OK(aslp_bn_bwd(CuStream(), in_diff ? in_diff->Data() : nullptr, in_diff ? in_diff->Stride() : 0, in.Data(), in.Stride(), nullptr,
+                        0, out_diff.Data(), out_diff.Stride(), in.NumRows(), output_dim_, scale_.Data(), mean_vec_.Data(), var_vec_.Data(),
                         opts_.momentum, dscale_.Data(), dshift_.Data()));
   }
   void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {       // plain -lr * d (no lr coefficient, :279-283)
@@ -127,7 +126,6 @@ class BatchNormalization : public UpdatableComponent {
     dscale_.Resize(output_dim_, kSetZero);
     dshift_.Resize(output_dim_, kSetZero);
   }
-  CuMatrix xhat_;
   CuVector mean_vec_, var_vec_, scale_, dscale_, shift_, dshift_;
   BaseFloat var_floor_;
   CuVectorD acc_means_, acc_vars_;

@@ -186,12 +186,41 @@ def fsmn_case():
     open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
 
 
+def forward_cases():
+    """Forwarders: the unmodified reference aslp-nnet-forward / aslp-nnet-forward-blstm-lc on the models the trainer cases
+    above wrote.  Each entry: (name, binary, model case, flags)."""
+    d = os.path.join(GOLD, "cli_fwd")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "counts.txt"), "w").write(" [ 30 10 0 25 5 40 20 15 ]\n")     # one empty class: floored prior
+    cases = [
+        ("frame_default", "aslp-nnet-forward", "cli_frame", ""),
+        ("frame_prior", "aslp-nnet-forward", "cli_frame", "--class-frame-counts=%s --prior-scale=0.8" % os.path.join(d, "counts.txt")),
+        ("frame_skip", "aslp-nnet-forward", "cli_frame", "--skip-width=3 --apply-log=false"),
+        ("lstm_shift", "aslp-nnet-forward", "cli_lstm", "--time-shift=2 --apply-log=false"),
+        ("ctc_blank", "aslp-nnet-forward", "cli_ctc", "--add-softmax=true --scale-blank=0.5"),
+        ("lc_chunks", "aslp-nnet-forward-blstm-lc", "cli_lc", "--chunk-size=8 --right-splice=3"),
+        ("lc_prior", "aslp-nnet-forward-blstm-lc", "cli_lc", "--chunk-size=8 --right-splice=3 --apply-log=false --no-softmax=true "
+         "--class-frame-counts=%s" % os.path.join(d, "counts.txt")),
+    ]
+    with open(os.path.join(d, "cases.txt"), "w") as f:
+        for name, exe, case, flags in cases:
+            src = os.path.join(GOLD, case)
+            out = os.path.join(d, name + ".ark")
+            run([os.path.join(REF, exe), "--use-gpu=no"] + flags.split() + [os.path.join(src, "ref_out.nnet"), "ark:" + os.path.join(src, "feats.ark"), "ark:" + out],
+                os.path.join(d, name + ".log"))
+            f.write("%s\t%s\t%s\t%s\n" % (name, exe, case, flags.replace(d + os.sep, "@GOLD@/")))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "forward":
+        forward_cases()
+        sys.exit(0)
     frame_case()
     ctc_case()
     lc_case()
     lstm_case()
     fsmn_case()
+    forward_cases()
     for c in ("cli_frame", "cli_ctc", "cli_lc", "cli_lstm", "cli_fsmn"):
         d = os.path.join(GOLD, c)
         print(c, sorted(os.listdir(d)), sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d)), "bytes")

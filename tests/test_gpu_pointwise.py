@@ -301,3 +301,32 @@ def test_copy_rows_is_an_exact_gather(rows, cols, nsrc):
     want = src[np.maximum(idx, 0)]
     want[idx < 0] = 0
     assert np.array_equal(D.np(), want)               # pure data movement: bit-exact
+
+
+@pytest.mark.parametrize("rows,cols,apply_log,blank,prior", [(300, 72, 1, 0.5, True), (64, 1500, 1, 0.0, False), (17, 7, 0, 0.0, True)])
+def test_posterior_finalize(rows, cols, apply_log, blank, prior):
+    """Forwarder tail in one pass (aslp-nnet-forward.cc:184-207): log(x + 1e-20), blank column shift, prior subtraction and
+    the min / max / non-finite statistics the warnings use."""
+    from tests.gpu_utils import DMat, dvec, lib, ok, ptr, stream, sync
+    import torch
+    rng = np.random.default_rng(21)
+    x = O.softmax_rows(rng.standard_normal((rows, cols)).astype(np.float32) * 3)
+    lp = np.log(rng.uniform(0.01, 1.0, cols)).astype(np.float32)
+    dx = DMat(x)
+    stats = torch.zeros(8, dtype=torch.float32, device="cuda")
+    ok(lib().aslp_posterior_finalize(stream(), dx.ptr, dx.ld, rows, cols, apply_log, 1e-20, blank, ptr(dvec(lp)) if prior else None, 0.8,
+                                     ptr(stats)))
+    sync()
+    want = x.copy()
+    if apply_log:
+        want = np.log(want + np.float32(1e-20)).astype(np.float32)
+    if blank > 0:
+        want[:, 0] -= np.float32(blank)
+    mid = want.copy()
+    if prior:
+        want = want + np.float32(-0.8) * lp[None, :]
+    assert np.abs(dx.np() - want).max() < 2e-6 * max(1.0, np.abs(want).max())
+    s = stats.cpu().numpy()
+    assert s[0] == x.min() and s[1] == x.max()
+    assert abs(s[2] - mid.min()) < 1e-5 * max(1.0, abs(mid.min())) and abs(s[3] - mid.max()) < 1e-5
+    assert s[4] == 0
