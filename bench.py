@@ -171,6 +171,59 @@ def cpu_baseline_leg():
     return cb
 
 
+
+def secondary_metrics(lib, torch):
+    """The other two quantities BASELINE.json's metric names, measured outside the timed region on rank 0: CTC forward-backward
+    utterances/s (cfg3 utterances through compute_ctc_loss, include/ctc.h) and the tensor-pipe fraction of the dominant GEMM
+    shape class of the step (x W_x^T of one layer: 16000 x 1280 x 640).  CUDA events on the launching stream, 3 warm-ups, median of 7."""
+    from kaldi_aslp_b200 import CtcComputeInfo
+    P = ctypes.c_void_p
+    st = torch.cuda.current_stream().cuda_stream
+
+    def med(fn, n=7):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    out = {}
+    rng = np.random.default_rng(0)
+    for mb in (S, 2048):
+        acts = torch.randn(T, mb, K, device="cuda")
+        grads = torch.zeros_like(acts)
+        flat = np.ascontiguousarray(rng.integers(1, K, size=mb * L), np.int32)
+        llen, ilen, costs = np.full(mb, L, np.int32), np.full(mb, T, np.int32), np.zeros(mb, np.float32)
+        info = CtcComputeInfo(1, st)
+        size = ctypes.c_size_t(0)
+        lib.get_workspace_size(llen.ctypes.data, ilen.ctypes.data, K, mb, info, ctypes.addressof(size))
+        ws = torch.empty(size.value + 256, dtype=torch.uint8, device="cuda")
+
+        def fn():
+            assert lib.compute_ctc_loss(P(acts.data_ptr()), P(grads.data_ptr()), flat.ctypes.data, llen.ctypes.data, ilen.ctypes.data,
+                                        K, mb, costs.ctypes.data, P(ws.data_ptr()), info) == 0
+        ms = med(fn)
+        per_utt = 2 * T * K * 4 + 2 * T * (2 * L + 1) * 4          # SURVEY 8(d): activations + gradients + alpha spill store/reload
+        out["ctc_%d_utts" % mb] = {"utts_per_s": mb / ms * 1e3, "ms": ms, "algorithmic_GBps": per_utt * mb / ms / 1e6}
+        del acts, grads, ws
+    M, N, Kd = S * T, 4 * C_CELL, 2 * C_CELL
+    A = torch.randn(M, Kd, device="cuda"); B = torch.randn(N, Kd, device="cuda"); Cm = torch.zeros(M, N, device="cuda")
+    hbm_peak, tf_peak, _ = measured_peaks()
+    for prec, name in ((0, "3xtf32"), (1, "tf32")):
+        def fn():
+            assert lib.aslp_gemm(P(st), 0, 1, M, N, Kd, 1.0, P(A.data_ptr()), Kd, P(B.data_ptr()), Kd, 0.0, P(Cm.data_ptr()), N, None, 0.0, prec, None, 0) == 0
+        ms = med(fn)
+        tf = 2.0 * M * N * Kd / ms / 1e9
+        issued = tf * (3 if prec == 0 else 1)
+        out["gemm_%dx%dx%d_%s" % (M, N, Kd, name)] = {
+            "useful_TFLOPs": tf, "ms": ms, "tensor_pipe_frac": issued / (tf_peak / 2.0) if tf_peak else None,
+            "peak": "TF32 dense = sustained bf16 / 2 = %.0f TFLOP/s; 3xTF32 issues 3 MMAs per useful one" % (tf_peak / 2.0)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -276,6 +329,25 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    sync_info = None
+    if worker is not None:                         # parameter averaging alone: NVLink bus bandwidth of one BMUF sync
+        barrier()
+        ts = []
+        for _ in range(5):
+            host_lib().aslp_nnet_event_record(0)
+            worker.synchronize(S * T)
+            host_lib().aslp_nnet_event_record(1)
+            ms = ctypes.c_float(0)
+            assert host_lib().aslp_nnet_event_elapsed_ms(0, 1, ctypes.byref(ms)) == 0
+            ts.append(ms.value)
+        t = torch.tensor([float(np.median(ts[1:]))], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nparams = net.num_params()
+        sync_info = {"ms_per_sync": float(t.item()), "params": int(nparams),
+                     "bus_GBps": 2.0 * (world - 1) / world * 4.0 * nparams / (float(t.item()) * 1e-3) / 1e9,
+                     "what": "pack + ONE ncclAllReduce(sum) of the fp32 arena + BMUF filter apply; bus bytes = 2(N-1)/N * 4P (SURVEY 8d)"}
+    secondary = secondary_metrics(lib, torch) if (rank == 0 and world == 1) else None
+
     if rank == 0:
         frames = S * T * args.steps * world
         hbm_peak, tf_peak, peak_src = measured_peaks()
@@ -315,6 +387,10 @@ def main():
             },
             "loss": {"mean_ctc_cost_last_step": float(np.mean(costs))},
         }
+        if secondary is not None:
+            line["secondary"] = secondary
+        if sync_info is not None:
+            line["sync"] = sync_info
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)

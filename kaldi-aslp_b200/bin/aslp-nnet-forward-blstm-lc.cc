@@ -1,7 +1,12 @@
 // aslp-nnet-forward-blstm-lc -- Feedforward of a latency-controlled BLSTM net, chunk by chunk with the forward state
 // carried across chunks, as src/aslp-nnetbin/aslp-nnet-forward-blstm-lc.cc:30-243: same flags, chunk arithmetic and log
-// lines.  Kept quirk: the [chunk+right_splice] input buffer is zeroed once per utterance, so the rows past the end of the
-// LAST chunk still hold the previous chunk's frames and feed the backward-direction chain (:160-170).
+// lines.  Two quirks of the reference are kept on purpose (its output depends on both):
+//  * batch_size = chunk_size + right_splice is evaluated BEFORE the command line is parsed (:50-52 vs :73), i.e. it is
+//    always 64 + 16 = 80 rows whatever --chunk-size / --right-splice say; the flags only move the chunk offsets, the copy
+//    length and the row the forward state is carried from.  With short utterances the backward-direction chain therefore
+//    sees every remaining frame, not right_splice of them (found by matching the reference archives to 1e-7).
+//  * the [80 x dim] input buffer is zeroed once per utterance, so rows past the frames of a chunk still hold what earlier
+//    chunks put there and feed the backward-direction chain (:160-170).
 #include "nnet-nnet.h"
 #include "nnet-pdf-prior.h"
 #include "parse-options.h"
@@ -34,9 +39,9 @@ int main(int argc, char* argv[]) {
     po.Register("use-gpu", &use_gpu, "yes|no|optional, only has effect if compiled with CUDA");
     int32 gpu_id = -1;
     po.Register("gpu-id", &gpu_id, "selected gpu id, if negative then select automaticly");
+    const int32 batch_size = chunk_size + right_splice;      // quirk: the DEFAULTS (64 + 16), taken before po.Read()
     po.Read(argc, argv);
     if (po.NumArgs() != 3) { po.PrintUsage(); return 1; }
-    const int32 batch_size = chunk_size + right_splice;
     const std::string model_filename = po.GetArg(1), feature_rspecifier = po.GetArg(2), feature_wspecifier = po.GetArg(3);
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
     if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));

@@ -51,33 +51,35 @@ __global__ void bn_partial_kernel(double* partial, const float* x, int ldx, cons
       const float4 m4 = ld4z(mean + c, nv); mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
       const float4 i4 = ld4z(a + c, nv); iv[0] = i4.x; iv[1] = i4.y; iv[2] = i4.z; iv[3] = i4.w;
     }
-    // two rows per iteration: twice the loads in flight per thread
-    for (int r = r0 + rl; r < r1; r += 16) {
-      const bool two = r + 8 < r1;
-      const float4 x4 = ld4z(x + (size_t)r * ldx + c, nv);
-      const float4 y4 = two ? ld4z(x + (size_t)(r + 8) * ldx + c, nv) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = d4;
-      if (MODE == 2) {
-        d4 = ld4z(b + (size_t)r * ldb + c, nv);
-        if (two) e4 = ld4z(b + (size_t)(r + 8) * ldb + c, nv);
+    // four rows per iteration, all loads issued before the first use
+    constexpr int U = 4;
+    for (int r = r0 + rl; r < r1; r += 8 * U) {
+      float4 x4[U], d4[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rr = r + 8 * u;
+        const bool live = rr < r1;
+        x4[u] = live ? ld4z(x + (size_t)rr * ldx + c, nv) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d4[u] = (MODE == 2 && live) ? ld4z(b + (size_t)rr * ldb + c, nv) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const float xv[2][4] = {{x4.x, x4.y, x4.z, x4.w}, {y4.x, y4.y, y4.z, y4.w}};
-      const float dv[2][4] = {{d4.x, d4.y, d4.z, d4.w}, {e4.x, e4.y, e4.z, e4.w}};
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !two) break;
-        if (MODE == 0) {
+      for (int u = 0; u < U; ++u) {
+        if (r + 8 * u < r1) {
+          const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+          const float dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+          if (MODE == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double xd = (double)xv[u][j];
-            acc[0][j] += xd; acc[1][j] += (double)(xv[u][j] * xv[u][j]); acc[2][j] += xd * xd;
-          }
-        } else {
+            for (int j = 0; j < 4; ++j) {
+              const double xd = (double)xv[j];
+              acc[0][j] += xd; acc[1][j] += (double)(xv[j] * xv[j]); acc[2][j] += xd * xd;
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xm = xv[u][j] - mu[j];
-            const float hv = xm * iv[j];
-            acc[0][j] += (double)(hv * dv[u][j]); acc[1][j] += (double)dv[u][j]; acc[2][j] += (double)(xm * dv[u][j]); acc[3][j] += (double)xm;
+            for (int j = 0; j < 4; ++j) {
+              const float xm = xv[j] - mu[j];
+              const float hv = xm * iv[j];
+              acc[0][j] += (double)(hv * dv[j]); acc[1][j] += (double)dv[j]; acc[2][j] += (double)(xm * dv[j]); acc[3][j] += (double)xm;
+            }
           }
         }
       }
@@ -100,19 +102,40 @@ __global__ void bn_partial_kernel(double* partial, const float* x, int ldx, cons
   }
 }
 
-__device__ __forceinline__ double sum_chunks(const double* partial, int chunks, int v, int colpad, int c) {
-  double s = 0.0;
-  for (int k = 0; k < chunks; ++k) s += partial[((size_t)k * MAXV + v) * colpad + c];
-  return s;
+// Finalize kernels: block = 32 columns x 8 chunk lanes.  Every lane sums each 8th chunk partial (independent loads), the 8
+// lanes of a column meet in shared memory in a fixed order (deterministic).  The one-thread-per-column form was a chain of
+// chunks x NV dependent L2 loads: 38-44 us for 74 chunks, longer than the statistics pass itself.
+template <int NVAL>
+__device__ __forceinline__ void sum_chunks_block(const double* partial, int chunks, int colpad, int c, bool col_ok, double (&out)[NVAL]) {
+  __shared__ double red[NVAL][8][33];
+  const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+  double s[NVAL];
+#pragma unroll
+  for (int v = 0; v < NVAL; ++v) s[v] = 0.0;
+  if (col_ok)
+    for (int k = kl; k < chunks; k += 8)
+#pragma unroll
+      for (int v = 0; v < NVAL; ++v) s[v] += partial[((size_t)k * MAXV + v) * colpad + c];
+#pragma unroll
+  for (int v = 0; v < NVAL; ++v) red[v][kl][cl] = s[v];
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < NVAL; ++v) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[v][j][cl];
+    out[v] = t;
+  }
 }
 
-__global__ void bn_fwd_fin_kernel(const double* partial, int chunks, int rows, int cols, float var_floor, float* mean, float* inv_std,
-                                  double* acc_mean, double* acc_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+__global__ void __launch_bounds__(256) bn_fwd_fin_kernel(const double* partial, int chunks, int rows, int cols, float var_floor, float* mean,
+                                                         float* inv_std, double* acc_mean, double* acc_var) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int colpad = ((cols + 3) >> 2) << 2;
-  const double s1 = sum_chunks(partial, chunks, 0, colpad, c), s2f = sum_chunks(partial, chunks, 1, colpad, c);
-  const double s2 = sum_chunks(partial, chunks, 2, colpad, c);
+  double sv[3];
+  sum_chunks_block<3>(partial, chunks, colpad, c, c < cols, sv);
+  if (c >= cols || (threadIdx.x >> 5) != 0) return;
+  const double s1 = sv[0], s2f = sv[1], s2 = sv[2];
   const float mu = (float)(s1 * (double)(1.0f / rows));                                     // AddRowSumMat(1/N, in)
   mean[c] = mu;
   if (acc_mean != nullptr) acc_mean[c] += s1;
@@ -143,15 +166,15 @@ __global__ void bn_normalize_kernel(float* out, int ldo, float* xhat, int ldh, c
 }
 
 // bwd finalize: dscale/dshift (momentum) and the per-column dvar, dmean used by the elementwise pass
-__global__ void bn_bwd_fin_kernel(const double* partial, int chunks, int rows, int cols, const float* scale, const float* inv_std,
-                                  float momentum, float* dscale, float* dshift, float* dvar_out, float* dmean_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+__global__ void __launch_bounds__(256) bn_bwd_fin_kernel(const double* partial, int chunks, int rows, int cols, const float* scale,
+                                                         const float* inv_std, float momentum, float* dscale, float* dshift,
+                                                         float* dvar_out, float* dmean_out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int colpad = ((cols + 3) >> 2) << 2;
-  const float s_hd = (float)sum_chunks(partial, chunks, 0, colpad, c);
-  const float s_d = (float)sum_chunks(partial, chunks, 1, colpad, c);
-  const float s_xd = (float)sum_chunks(partial, chunks, 2, colpad, c);
-  const float s_x = (float)sum_chunks(partial, chunks, 3, colpad, c);
+  double sv[4];
+  sum_chunks_block<4>(partial, chunks, colpad, c, c < cols, sv);
+  if (c >= cols || (threadIdx.x >> 5) != 0) return;
+  const float s_hd = (float)sv[0], s_d = (float)sv[1], s_xd = (float)sv[2], s_x = (float)sv[3];
   dscale[c] = momentum * dscale[c] + s_hd;
   dshift[c] = momentum * dshift[c] + s_d;
   const float iv = inv_std[c], sc = scale[c];
@@ -178,10 +201,15 @@ __global__ void bn_bwd_apply_kernel(float* din, int ldd, const float* in, int ld
 }
 
 struct RedPlan { int col_blocks, chunks, rows_per_chunk; size_t bytes; };
-RedPlan plan_reduce(int rows, int cols) {
+// one full wave of the statistics kernel: chunks = resident blocks (occupancy query: the kernels are register-limited to
+// 2-4 blocks per SM) / column blocks
+template <typename KernelT>
+RedPlan plan_reduce(KernelT kernel, int rows, int cols) {
   RedPlan p;
   p.col_blocks = aslp_div_up(cols, 128);
-  int chunks = aslp_div_up(aslp_num_sms() * 4, p.col_blocks);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  int chunks = (aslp_num_sms() * per_sm) / p.col_blocks;
   if (chunks > aslp_div_up(rows, 32)) chunks = aslp_div_up(rows, 32);
   if (chunks < 1) chunks = 1;
   p.rows_per_chunk = aslp_div_up(rows, chunks);
@@ -205,13 +233,13 @@ int aslp_bn_fwd_train(aslp_stream_t s, float* out, int ldo, float* xhat, int ldx
   if (rows == 0 || cols == 0) return 0;
   ASLP_REQUIRE(ldo % 4 == 0 && ldi % 4 == 0 && (xhat == nullptr || ldx % 4 == 0));
   cudaStream_t st = (cudaStream_t)s;
-  const RedPlan p = plan_reduce(rows, cols);
+  const RedPlan p = plan_reduce(bn_partial_kernel<0>, rows, cols);
   double* partial = (double*)aslp_scratch(st, p.bytes);
   if (partial == nullptr) { aslp_set_last_error_msg("scratch allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
   dim3 grid(p.col_blocks, p.chunks);
   bn_partial_kernel<0><<<grid, 256, 0, st>>>(partial, in, ldi, nullptr, 0, nullptr, 0, nullptr, rows, cols, p.rows_per_chunk);
   ASLP_CHECK_LAUNCH();
-  bn_fwd_fin_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(partial, p.chunks, rows, cols, var_floor, mean, inv_std, acc_mean, acc_var);
+  bn_fwd_fin_kernel<<<aslp_div_up(cols, 32), 256, 0, st>>>(partial, p.chunks, rows, cols, var_floor, mean, inv_std, acc_mean, acc_var);
   ASLP_CHECK_LAUNCH();
   bn_normalize_kernel<<<ew_grid(rows, cols), 256, 0, st>>>(out, ldo, xhat, ldx, in, ldi, rows, cols, scale, shift, mean, inv_std);
   ASLP_CHECK_LAUNCH();
@@ -234,7 +262,7 @@ int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int l
   ASLP_REQUIRE(ldi % 4 == 0 && ldo % 4 == 0 && (in_diff == nullptr || ldd % 4 == 0));
   (void)xhat; (void)ldx;
   cudaStream_t st = (cudaStream_t)s;
-  const RedPlan p = plan_reduce(rows, cols);
+  const RedPlan p = plan_reduce(bn_partial_kernel<2>, rows, cols);
   const size_t colpad = (size_t)(cols + 3) / 4 * 4;
   double* partial = (double*)aslp_scratch(st, p.bytes + 2 * colpad * sizeof(float));
   if (partial == nullptr) { aslp_set_last_error_msg("scratch allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
@@ -243,7 +271,7 @@ int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int l
   dim3 grid(p.col_blocks, p.chunks);
   bn_partial_kernel<2><<<grid, 256, 0, st>>>(partial, in, ldi, inv_std, 0, out_diff, ldo, mean, rows, cols, p.rows_per_chunk);   // xhat recomputed, not read
   ASLP_CHECK_LAUNCH();
-  bn_bwd_fin_kernel<<<aslp_div_up(cols, 256), 256, 0, st>>>(partial, p.chunks, rows, cols, scale, inv_std, momentum, dscale, dshift, dvar, dmean);
+  bn_bwd_fin_kernel<<<aslp_div_up(cols, 32), 256, 0, st>>>(partial, p.chunks, rows, cols, scale, inv_std, momentum, dscale, dshift, dvar, dmean);
   ASLP_CHECK_LAUNCH();
   if (in_diff != nullptr) {
     bn_bwd_apply_kernel<<<ew_grid(rows, cols), 256, 0, st>>>(in_diff, ldd, in, ldi, out_diff, ldo, rows, cols, scale, mean, inv_std, dvar, dmean);

@@ -21,8 +21,10 @@ __device__ __forceinline__ float4 f4_fma(float4 w, float4 x, float4 a) {
   return a;
 }
 // stage rows [t_first, t_first + nrows) x columns [d0, d0 + 128) of a [T, D] matrix into tile[nrows][128]; zero outside.
-// Items are float4, consecutive threads take consecutive quads of a row: every load is an independent coalesced 16-byte
-// access and a thread has all of its share in flight at once.
+// Items are 16-byte cp.async copies (zero-filled past the matrix edge through the src-size operand): no registers, no
+// scoreboard, so a thread has its whole share in flight at once -- with register loads the compiler kept ONE load
+// outstanding per thread and the staging loop cost 18 serial DRAM round trips (ncu: long_scoreboard 5.5 / issue).
+// The caller waits with stage_wait() before the barrier.
 __device__ __forceinline__ void stage_tile(float* tile, const float* x, int ldx, int T, int D, int t_first, int nrows, int d0,
                                            int row_rev_base) {   // row_rev_base >= 0: tile row r reads source row row_rev_base - r
   const int items = nrows * (COLS / 4);
@@ -30,15 +32,14 @@ __device__ __forceinline__ void stage_tile(float* tile, const float* x, int ldx,
     const int r = i >> 5, q = i & 31;
     const int t = row_rev_base >= 0 ? row_rev_base - r : t_first + r;
     const int d = d0 + q * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0 && t < T && d < D) {
-      const float* p = x + (size_t)t * ldx + d;
-      if (d + 3 < D) v = *reinterpret_cast<const float4*>(p);
-      else { v.x = p[0]; if (d + 1 < D) v.y = p[1]; if (d + 2 < D) v.z = p[2]; }
-    }
-    *reinterpret_cast<float4*>(tile + r * COLS + q * 4) = v;
+    const bool in = t >= 0 && t < T && d < D;
+    const float* src = in ? x + (size_t)t * ldx + d : x;
+    const int bytes = in ? min(4, D - d) * 4 : 0;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + r * COLS + q * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
   }
 }
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // y[t,d] = x[t,d] + sum_c w[c,d] * x[t + c - P, d],  w[c] = rev ? coef[C-1-c] : coef[c]
 // CTA = TT/TB warps; warp w owns outputs t0 + w*TB .. +TB-1 of 128 columns (lane = column quad).  Per tap: one 128-bit
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(TT / TB * 32) fsmn_filter_kernel(float* y, int
   const int d0 = blockIdx.x * COLS, t0 = blockIdx.y * TT;
   stage_tile(xs, x, ldx, T, D, t0 - P, nrows, d0, -1);
   stage_tile(cs, coef, ldc, C, D, 0, C, d0, rev ? C - 1 : -1);
+  stage_wait();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tb = warp * TB;
@@ -99,6 +101,7 @@ __global__ void fsmn_grad_partial_kernel(float* partial, const float* x, int ldx
   const int d0 = blockIdx.x * COLS, t0 = blockIdx.y * TT;
   stage_tile(xs, x, ldx, T, D, t0 - P, nrows, d0, -1);
   stage_tile(gs, g, ldg, T, D, t0, TT, d0, -1);
+  stage_wait();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = warp * TB;

@@ -294,7 +294,7 @@ int aslp_xent_sparse(aslp_stream_t s, float* diff, int ldd, const float* y, int 
   if (rows == 0) return 0;
   if (cols <= rowreg::MAX_COLS && rowreg::aligned16(diff, ldd) && rowreg::aligned16(y, ldy)) {
 #define ASLP_XENT_CALL(G, NV)                                                                                          \
-    rowreg::xent_reg_kernel<G, NV, false><<<rowreg::row_grid(rows, 8 * (32 / G), 8), 256, 0, (cudaStream_t)s>>>(       \
+    rowreg::xent_reg_kernel<G, NV, false><<<rowreg::row_grid(rowreg::xent_reg_kernel<G, NV, false>, rows, 8 * (32 / G)), 256, 0, (cudaStream_t)s>>>(       \
         diff, ldd, y, ldy, nullptr, 0, rows, cols, tgt_idx, tgt_w, frame_w, stats_dev)
     ROWREG_DISPATCH(cols, ASLP_XENT_CALL);
 #undef ASLP_XENT_CALL
@@ -312,7 +312,7 @@ int aslp_xent_dense(aslp_stream_t s, float* diff, int ldd, const float* y, int l
   if (rows == 0) return 0;
   if (cols <= 1024 && rowreg::aligned16(diff, ldd) && rowreg::aligned16(y, ldy) && rowreg::aligned16(tgt, ldt)) {
 #define ASLP_XENT_CALL(G, NV)                                                                                          \
-    rowreg::xent_reg_kernel<G, NV, true><<<rowreg::row_grid(rows, 8 * (32 / G), 4), 256, 0, (cudaStream_t)s>>>(        \
+    rowreg::xent_reg_kernel<G, NV, true><<<rowreg::row_grid(rowreg::xent_reg_kernel<G, NV, true>, rows, 8 * (32 / G)), 256, 0, (cudaStream_t)s>>>(        \
         diff, ldd, y, ldy, tgt, ldt, rows, cols, nullptr, nullptr, frame_w, stats_dev)
     if (cols <= 32) { ASLP_XENT_CALL(8, 1); } else if (cols <= 64) { ASLP_XENT_CALL(8, 2); } else if (cols <= 128) { ASLP_XENT_CALL(8, 4); }
     else if (cols <= 256) { ASLP_XENT_CALL(32, 2); } else if (cols <= 512) { ASLP_XENT_CALL(32, 4); } else { ASLP_XENT_CALL(32, 8); }

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
 #include "lstm_mma.cuh"
 
 // ---------------------------------------------------------------- host side
-struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; };
+struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; bool presplit; };
 
 size_t ws_per_dir(int T, int S, int C, int R, bool bwd) {
   const size_t SX = (size_t)(S + 3) / 4 * 4;
@@ -369,7 +369,7 @@ void fill_dir(DirDev& D, const aslp_lstm_dir_t& a) {
 // register budget (more groups = fewer CTAs per chain = more cells per CTA, but proportionally less exchange traffic)
 int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
-  P->mma = false;
+  P->mma = false; P->presplit = false;
   L.ndirs = ndirs;
   const int C = dirs[0].C, S = dirs[0].S;
   for (int i = 0; i < ndirs; ++i)
@@ -405,7 +405,11 @@ int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, si
       D.xb = nullptr;
     }
     if (ws == nullptr || ws_bytes < need_ws) { aslp_set_last_error_msg("LSTM workspace too small", __FILE__, __LINE__); return ASLP_STATUS_INVALID_VALUE; }
-    P->smem = mma_smem_floats(C, cb, SG, SGP, bwd) * sizeof(float);
+    // backward: fast contraction form (float4 fragment layout, immediate B addresses) when the shape allows
+    static const bool no_presplit = std::getenv("ASLP_LSTM_NO_PRESPLIT") != nullptr;
+    P->presplit = bwd && !no_presplit && mma_presplit_shape(C, SG, SGP) && mma_pick_kernel(mc, true, true) != nullptr &&
+                  mma_smem_floats(C, cb, SG, SGP, bwd, true) * sizeof(float) <= 224 * 1024;
+    P->smem = mma_smem_floats(C, cb, SG, SGP, bwd, P->presplit) * sizeof(float);
     P->ws_bytes = need_ws;
     P->mc = mc;
     P->mma = true;
@@ -416,7 +420,7 @@ int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, si
 
 int make_plan(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
-  P->mma = false;
+  P->mma = false; P->presplit = false;
   L.pgroups = 1; L.SGP = 0;
   L.ndirs = ndirs;
   const int sms = aslp_num_sms();
@@ -522,7 +526,7 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
   }
   rc = init_exchange(st, P, bwd);
   if (rc != 0) return rc;
-  void* kfn = P.mma ? mma_pick_kernel(P.mc, bwd) : (bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel);
+  void* kfn = P.mma ? mma_pick_kernel(P.mc, bwd, P.presplit) : (bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel);
   if (kfn == nullptr) { aslp_set_last_error_msg("no tensor-core recurrence kernel for this shape", __FILE__, __LINE__); return ASLP_STATUS_UNKNOWN_ERROR; }
   ASLP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   P.L.timing = g_timing;

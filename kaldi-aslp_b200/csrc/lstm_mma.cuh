@@ -28,12 +28,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 4 ? 1 : (MT_ >= 2 ? 2 : 4); };   // k-interleaved accumulator sets
+template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 2 ? 1 : 2; };   // k-interleaved accumulator sets
 
 // part_w[stream][NPP] = Wslice[MT_*16 rows, k-slice of this warp] * X[k-slice, streams]   (8 streams per n-tile)
 // wa: A fragments (a0: row g, k tig; a1: row g+8, k tig; a2: row g, k tig+4; a3: row g+8, k tig+4), fp32.
-// Several independent accumulators per m-tile (hi*hi apart from the two cross terms, and k-interleaved) keep the
-// dependent-MMA chains short: the chain, not the issue rate, is what a single step waits for.
+// The three products of a (m-tile, k-tile) -- lo*hi, hi*lo, hi*hi -- go to three independent accumulators, so an MMA never
+// waits for the one issued just before it (the two cross terms used to share one accumulator and ran back to back); the
+// next MMA into the same accumulator is a whole k-tile (3 * MT_ * K MMAs) later.  The chain, not the issue rate, is what
+// a single step waits for: the issue floor is 8 cycles per MMA per sub-partition (tools/micro/mma_rate.cu).
 template <int MT_, int KT_>
 __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], const float* xT, int SP, int kbase, int Kdim,
                                              int ntiles, float* part_w, int lane) {
@@ -41,13 +43,13 @@ __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], con
   constexpr int AK = MmaAcc<MT_>::K;
   const int g = lane >> 2, tig = lane & 3;
   for (int nt = 0; nt < ntiles; ++nt) {
-    float acc[MT_][AK][2][4];
+    float acc[MT_][AK][3][4];
 #pragma unroll
     for (int mt = 0; mt < MT_; ++mt)
 #pragma unroll
       for (int a = 0; a < AK; ++a)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { acc[mt][a][h][0] = acc[mt][a][h][1] = acc[mt][a][h][2] = acc[mt][a][h][3] = 0.f; }
+        for (int h = 0; h < 3; ++h) { acc[mt][a][h][0] = acc[mt][a][h][1] = acc[mt][a][h][2] = acc[mt][a][h][3] = 0.f; }
 #pragma unroll
     for (int kt = 0; kt < KT_; ++kt) {
       {
@@ -63,7 +65,7 @@ __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], con
 #pragma unroll
           for (int q = 0; q < 4; ++q) split_tf32(wa[mt][kt][q], ah[q], al[q]);
           mma_tf32(acc[mt][kt % AK][1], al, bh0, bh1);
-          mma_tf32(acc[mt][kt % AK][1], ah, bl0, bl1);
+          mma_tf32(acc[mt][kt % AK][2], ah, bl0, bl1);
           mma_tf32(acc[mt][kt % AK][0], ah, bh0, bh1);
         }
       }
@@ -75,7 +77,7 @@ __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], con
       for (int q = 0; q < 4; ++q) {
         float lo = 0.f, hi = 0.f;
 #pragma unroll
-        for (int a = 0; a < AK; ++a) { lo += acc[mt][a][1][q]; hi += acc[mt][a][0][q]; }
+        for (int a = 0; a < AK; ++a) { lo += acc[mt][a][1][q] + acc[mt][a][2][q]; hi += acc[mt][a][0][q]; }
         c[q] = lo + hi;                                  // small terms first
       }
       // c0: (row g, stream 2tig)  c1: (g, 2tig+1)  c2: (g+8, 2tig)  c3: (g+8, 2tig+1); stored stream-major
@@ -138,6 +140,58 @@ __device__ __forceinline__ void mma_contract_ws(const float* ws, int ktp, const 
       float* p0 = part_w + (size_t)(nt * 8 + 2 * tig) * NPP + mt * 16 + g;
       p0[0] = c[0]; p0[NPP] = c[1]; p0[8] = c[2]; p0[NPP + 8] = c[3];
     }
+  }
+}
+
+// Fast form of the backward contraction (what cfg3 runs).  Against mma_contract_ws: the A fragments of a (k-tile, m-tile)
+// are ONE 128-bit shared load per lane (layout [kt][mt][lane] float4) instead of four 32-bit loads; the three products of
+// a k-tile go to three independent accumulator sets, k-interleaved four ways, so no MMA waits for the one issued before
+// it; SP == 8 and an exact K split make the B addresses immediates (no per-tile integer arithmetic).  Measured before:
+// 22 cycles per MMA per sub-partition against an issue floor of 8 (tools/micro/mma_rate.cu).  The tf32 residual of the
+// weights is still taken on the fly: a second, pre-split copy in shared memory would double the A traffic
+// (8 warps x 20 tiles x 1 KB = 164 KB per step) and make the step shared-memory-bound at ~1600 cycles.
+// KTP_ k-tiles per warp (multiple of 4); xp0 = xT + (first k row of the warp + tig) * 8 + g.
+template <int MT_, int KTP_>
+__device__ __forceinline__ void mma_contract_fast(const float4* wfrag, const float* xp0, float* part_w, int lane) {
+  constexpr int NPP = MT_ * 16 + 4;
+  constexpr int AK = 4;
+  static_assert(KTP_ % AK == 0, "k-tiles per warp must be a multiple of 4");
+  const int g = lane >> 2, tig = lane & 3;
+  float hh[MT_][AK][4], lh[MT_][AK][4], hl[MT_][AK][4];
+#pragma unroll
+  for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+    for (int a = 0; a < AK; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { hh[mt][a][q] = 0.f; lh[mt][a][q] = 0.f; hl[mt][a][q] = 0.f; }
+#pragma unroll
+  for (int kt = 0; kt < KTP_; ++kt) {
+    const int a = kt % AK;
+    uint32_t bh0, bl0, bh1, bl1;
+    split_tf32(xp0[kt * 64], bh0, bl0);
+    split_tf32(xp0[kt * 64 + 32], bh1, bl1);
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt) {
+      const float4 w4 = wfrag[(kt * MT_ + mt) * 32 + lane];
+      uint32_t ah[4], al[4];
+      split_tf32(w4.x, ah[0], al[0]); split_tf32(w4.y, ah[1], al[1]); split_tf32(w4.z, ah[2], al[2]); split_tf32(w4.w, ah[3], al[3]);
+      mma_tf32(lh[mt][a], al, bh0, bh1);
+      mma_tf32(hl[mt][a], ah, bl0, bl1);
+      mma_tf32(hh[mt][a], ah, bh0, bh1);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT_; ++mt) {
+    float c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float lo = 0.f, hi = 0.f;
+#pragma unroll
+      for (int a = 0; a < AK; ++a) { lo += lh[mt][a][q] + hl[mt][a][q]; hi += hh[mt][a][q]; }
+      c[q] = lo + hi;                                    // small terms first
+    }
+    float* p0 = part_w + (size_t)(2 * tig) * NPP + mt * 16 + g;
+    p0[0] = c[0]; p0[NPP] = c[1]; p0[8] = c[2]; p0[NPP + 8] = c[3];
   }
 }
 
@@ -309,8 +363,9 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
 }
 
 // ---------------------------------------------------------------- backward (R == 0 form)
-// KT_ only sizes the staging share here (the weights live in shared memory)
-template <int MT_, int KT_>
+// KT_ only sizes the staging share here (the weights live in shared memory).  PS_: fast contraction form
+// (mma_contract_fast, float4 fragment layout); the planner turns it on when SP == 8 and K splits exactly over the warps.
+template <int MT_, int KT_, bool PS_>
 __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
   extern __shared__ float smem[];
   const MmaCta cta = mma_cta(L);
@@ -332,7 +387,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
   const int ktiles = K >> 3, ktw = (ktiles + NW - 1) / NW;
   const int ktp = (ktw + 3) & ~3;
   const int kt0 = warp * ktw, nkt = max(0, min(ktw, ktiles - kt0));
-  float* wsm = pst + ((3 * D.cb + 3) & ~3);              // [NW][ktp][MT_][4][32]
+  float* wsm = pst + ((3 * D.cb + 3) & ~3);              // [NW][ktp][MT_][4][32]  (PS_: [NW][ktp][MT_][32] float4)
   float* ws = wsm + (size_t)warp * ktp * MT_ * 128;
   {
     const int g = lane >> 2, tig = lane & 3;
@@ -343,7 +398,12 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
         for (int q = 0; q < 4; ++q) {
           const int n = mt * 16 + g + (q & 1) * 8;
           const int k = (kt0 + kt) * 8 + tig + (q >> 1) * 4;
-          ws[((size_t)(kt * MT_ + mt) * 4 + q) * 32 + lane] = (kt < nkt && n < nc) ? D.w_r[(size_t)k * D.ldwr + c0 + n] : 0.f;
+          const float wv = (kt < nkt && n < nc) ? D.w_r[(size_t)k * D.ldwr + c0 + n] : 0.f;
+          if (PS_) {
+            ws[((size_t)(kt * MT_ + mt) * 32 + lane) * 4 + q] = wv;
+          } else {
+            ws[((size_t)(kt * MT_ + mt) * 4 + q) * 32 + lane] = wv;
+          }
         }
   }
   for (int i = threadIdx.x; i < 3 * D.cb * L.SGP; i += NT) st[i] = 0.f;
@@ -417,6 +477,11 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
     __syncthreads();
     RECUR_TICK(k2);
     constexpr int KTP = KT_ <= 32 ? ((KT_ + 3) & ~3) : 0;     // exact tile count known at compile time up to 32 tiles per warp
+    if (PS_) {
+      constexpr int KTPS = KTP > 0 ? KTP : 4;
+      mma_contract_fast<MT_, KTPS>(reinterpret_cast<const float4*>(ws), xT + (size_t)(kt0 * 8 + (lane & 3)) * 8 + (lane >> 2),
+                                   part + (size_t)warp * SG * NPP, lane);
+    } else
     if (KTP > 0 && ktp == KTP) mma_contract_ws<MT_, KTP>(ws, ktp, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
     else mma_contract_ws<MT_, 0>(ws, ktp, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
     RECUR_TICK(k3);
@@ -463,13 +528,20 @@ struct MmaChoice { int mt, kt; };
 
 inline int mma_rows(int cb, bool bwd) { return bwd ? cb : 4 * cb; }          // rows of the per-CTA weight slice
 inline int mma_kdim(int C, bool bwd) { return bwd ? 4 * C : C; }
-inline size_t mma_smem_floats(int C, int cb, int SG, int SGP, bool bwd) {
+// fast contraction form applies: one staging group of 8 streams (SP == 8), K splits exactly into a multiple of 4 k-tiles per
+// warp, and a kernel with that compile-time tile count exists
+inline bool mma_presplit_shape(int C, int SG, int SGP) {
+  const int kt = (4 * C) / 8;
+  return SG == 8 && SGP == 8 && (4 * C) % (8 * NW) == 0 && (kt / NW) % 4 == 0 && (kt / NW == 8 || kt / NW == 20 || kt / NW == 32);
+}
+inline size_t mma_smem_floats(int C, int cb, int SG, int SGP, bool bwd, bool presplit = false) {
   const int SP = SG == 8 ? 8 : SG + 8;
   const size_t mt = (size_t)(mma_rows(cb, bwd) + 15) / 16;
   size_t fl = (size_t)mma_kdim(C, bwd) * SP + (size_t)NW * SG * (mt * 16 + 4) + (size_t)(bwd ? 3 : 1) * cb * SGP + 3 * (size_t)cb;
   if (bwd) {                                             // weight fragments in shared memory
     const size_t ktw = ((size_t)mma_kdim(C, bwd) / 8 + NW - 1) / NW, ktp = (ktw + 3) & ~(size_t)3;
     fl += 4 + (size_t)NW * ktp * mt * 128;
+    (void)presplit;
   }
   return fl;
 }
@@ -484,12 +556,17 @@ inline bool mma_fits(int C, int cb, bool bwd, MmaChoice* ch) {
 }
 
 template <int MT_, int KT_> inline void* mma_fwd_ptr() { return (void*)lstm_fwd_mma_kernel<MT_, KT_>; }
-template <int MT_, int KT_> inline void* mma_bwd_ptr() { return (void*)lstm_bwd_mma_kernel<MT_, KT_>; }
+template <int MT_, int KT_, bool PS_> inline void* mma_bwd_ptr() { return (void*)lstm_bwd_mma_kernel<MT_, KT_, PS_>; }
 
-inline void* mma_pick_kernel(const MmaChoice& c, bool bwd) {
+inline void* mma_pick_kernel(const MmaChoice& c, bool bwd, bool presplit = false) {
   if (bwd) {                                             // KT_ = staging share bound (items per thread = KT_/2 at 8 streams)
-    if (c.mt == 1) { if (c.kt <= 8) return mma_bwd_ptr<1, 8>(); if (c.kt <= 20) return mma_bwd_ptr<1, 20>(); if (c.kt <= 32) return mma_bwd_ptr<1, 32>(); return mma_bwd_ptr<1, 64>(); }
-    if (c.kt <= 8) return mma_bwd_ptr<2, 8>(); if (c.kt <= 20) return mma_bwd_ptr<2, 20>(); if (c.kt <= 32) return mma_bwd_ptr<2, 32>(); return mma_bwd_ptr<2, 64>();
+    if (presplit) {
+      if (c.mt == 1) { if (c.kt == 8) return mma_bwd_ptr<1, 8, true>(); if (c.kt == 20) return mma_bwd_ptr<1, 20, true>(); if (c.kt == 32) return mma_bwd_ptr<1, 32, true>(); }
+      else { if (c.kt == 8) return mma_bwd_ptr<2, 8, true>(); if (c.kt == 20) return mma_bwd_ptr<2, 20, true>(); if (c.kt == 32) return mma_bwd_ptr<2, 32, true>(); }
+      return nullptr;
+    }
+    if (c.mt == 1) { if (c.kt <= 8) return mma_bwd_ptr<1, 8, false>(); if (c.kt <= 20) return mma_bwd_ptr<1, 20, false>(); if (c.kt <= 32) return mma_bwd_ptr<1, 32, false>(); return mma_bwd_ptr<1, 64, false>(); }
+    if (c.kt <= 8) return mma_bwd_ptr<2, 8, false>(); if (c.kt <= 20) return mma_bwd_ptr<2, 20, false>(); if (c.kt <= 32) return mma_bwd_ptr<2, 32, false>(); return mma_bwd_ptr<2, 64, false>();
   }
 #define ASLP_FWD_ROW(MTv)                                        \
   if (c.mt == MTv) {                                             \

@@ -361,7 +361,7 @@ int aslp_softmax_rows(aslp_stream_t s, float* out, int ldo, const float* in, int
   if (cols <= rowreg::MAX_COLS && rowreg::aligned16(out, ldo) && rowreg::aligned16(in, ldi)) {
     // whole row in registers: one HBM read + one write, every load of a row in flight at once
 #define ASLP_SOFTMAX_CALL(G, NV)                                                                                      \
-    rowreg::softmax_reg_kernel<G, NV><<<rowreg::row_grid(rows, 8 * (32 / G), 8), 256, 0, (cudaStream_t)s>>>(out, ldo, in, ldi, rows, cols)
+    rowreg::softmax_reg_kernel<G, NV><<<rowreg::row_grid(rowreg::softmax_reg_kernel<G, NV>, rows, 8 * (32 / G)), 256, 0, (cudaStream_t)s>>>(out, ldo, in, ldi, rows, cols)
     ROWREG_DISPATCH(cols, ASLP_SOFTMAX_CALL);
 #undef ASLP_SOFTMAX_CALL
     ASLP_CHECK_LAUNCH();

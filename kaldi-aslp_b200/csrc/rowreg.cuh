@@ -58,7 +58,7 @@ __device__ __forceinline__ void store_row(const float (&v)[NV][4], float* row, i
 
 // ---- softmax (Softmax::PropagateFnc; kaldi-vector.cc:852-859: max, exp(x - max), scale by 1 / sum)
 template <int G, int NV>
-__global__ void __launch_bounds__(256) softmax_reg_kernel(float* out, int ldo, const float* in, int ldi, int rows, int cols) {
+__global__ void __launch_bounds__(256, NV >= 8 ? 2 : 3) softmax_reg_kernel(float* out, int ldo, const float* in, int ldi, int rows, int cols) {
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31, lg = lane % G, sub = lane / G;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
@@ -106,7 +106,7 @@ __device__ __forceinline__ void block_flush_stats(double* stats, double (&acc)[5
 }
 
 template <int G, int NV, bool DENSE>
-__global__ void __launch_bounds__(256) xent_reg_kernel(float* diff, int ldd, const float* y, int ldy, const float* tgt, int ldt,
+__global__ void __launch_bounds__(256, NV >= 8 ? 2 : 3) xent_reg_kernel(float* diff, int ldd, const float* y, int ldy, const float* tgt, int ldt,
                                                        int rows, int cols, const int* tgt_idx, const float* tgt_w,
                                                        const float* frame_w, double* stats) {
   constexpr int RPW = 32 / G;
@@ -189,9 +189,14 @@ __global__ void __launch_bounds__(256) xent_reg_kernel(float* diff, int ldd, con
 }
 
 inline bool aligned16(const void* p, int ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
-inline int row_grid(long long rows, int rows_per_block, int blocks_per_sm) {
+// persistent grid: as many blocks as are resident at once (queried per kernel), each walking rows with a grid stride;
+// a grid of several register-limited waves paid a launch / drain ramp per wave (ncu: 8 waves for the 1500-column softmax)
+template <typename KernelT>
+inline int row_grid(KernelT kernel, long long rows, int rows_per_block) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   long long b = (rows + rows_per_block - 1) / rows_per_block;
-  const long long cap = (long long)aslp_num_sms() * blocks_per_sm;
+  const long long cap = (long long)aslp_num_sms() * per_sm;
   if (b > cap) b = cap;
   return (int)(b < 1 ? 1 : b);
 }
