@@ -342,11 +342,20 @@ def main():
             ts.append(ms.value)
         t = torch.tensor([float(np.median(ts[1:]))], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        nparams = net.num_params()
+        nparams = net.num_params
         sync_info = {"ms_per_sync": float(t.item()), "params": int(nparams),
                      "bus_GBps": 2.0 * (world - 1) / world * 4.0 * nparams / (float(t.item()) * 1e-3) / 1e9,
                      "what": "pack + ONE ncclAllReduce(sum) of the fp32 arena + BMUF filter apply; bus bytes = 2(N-1)/N * 4P (SURVEY 8d)"}
     secondary = secondary_metrics(lib, torch) if (rank == 0 and world == 1) else None
+    if secondary is not None and args.precision == "3xtf32":
+        # the same step with single-pass TF32 chunk GEMMs (north_star's "stated looser bound" mode, parity bound 5e-3 in
+        # tests/test_gpu_gemm.py); informative only -- `value` above is the fp32-grade configuration
+        NN.set_gemm_precision(1)
+        for _ in range(3):
+            step(True)
+        ms_tf32, _, _ = timed(True)
+        NN.set_gemm_precision(0)
+        secondary["step_with_tf32_gemms"] = {"ms_per_step": ms_tf32 / args.steps, "frames_per_s": S * T * args.steps / (ms_tf32 * 1e-3)}
 
     if rank == 0:
         frames = S * T * args.steps * world

@@ -16,7 +16,7 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 INCLUDE = os.path.join(ROOT, "include")
-LIB_CUDA_PATH = os.path.join(HERE, "libaslp_b200.so")
+LIB_CUDA_PATH = os.environ.get("ASLP_B200_CUDA_LIB", os.path.join(HERE, "libaslp_b200.so"))     # override: A/B builds of one kernel (tools/)
 LIB_HOST_PATH = os.path.join(HERE, "libaslp_nnet.so")
 
 _CTYPE = {

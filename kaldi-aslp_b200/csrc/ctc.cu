@@ -17,16 +17,21 @@
 #include "common.cuh"
 #include "../../include/ctc.h"
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
 __device__ __forceinline__ float neg_inf() { return -INFINITY; }
+// log(exp(p1) + exp(p2)), ctc_helper.h:55-68.  Branch-free: with one argument at -inf the difference is -inf, exp gives 0 and
+// the result is exactly the other argument, as the reference's early returns; only both at -inf (inf - inf) needs the
+// select.  Without branches the independent states a thread owns overlap their SFU latencies.
 __device__ __forceinline__ float log_plus(float p1, float p2) {
-  if (p1 == neg_inf()) return p2;
-  if (p2 == neg_inf()) return p1;
+  const float m = fmaxf(p1, p2);
+  const float d = (m == neg_inf()) ? 0.f : fabsf(p1 - p2);
   // SFU forms (common.cuh): the absolute error (< 4e-7) is three orders below one ulp of the alpha / beta values this is
   // added to on utterances of the BASELINE size (|alpha| ~ 3e3, ulp 2.4e-4); a fifth of the instructions of log1pf(expf())
-  return aslp_log1p_of_exp_neg(fabsf(p1 - p2)) + fmaxf(p1, p2);
+  const float r = aslp_log1p_of_exp_neg(d) + m;
+  return (m == neg_inf()) ? neg_inf() : r;
 }
 
 // ---- 0. per-utterance CSR of the non-blank states of every label (ascending state order: the reference's accumulation order)
@@ -266,6 +271,160 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
   }
 }
 
+// ---- 2b. warp-per-sweep form (S <= 256 states): one warp walks the alpha sweep of an utterance, a second warp of the same
+// CTA its beta sweep.  Lane l owns the states j*32 + l (j < NS) in REGISTERS -- rows of lp / alpha / beta are read and
+// written as coalesced 128-byte lines -- and the neighbour states i-1, i-2 (alpha) / i+1, i+2 (beta) come by shuffle, so a
+// time step has no barrier and no shared-memory traffic, and up to 32 such CTAs are resident per SM.  lp rows are fetched
+// two steps ahead.  Same recurrences, window arithmetic and in-place beta semantics as ctc_sweep_kernel above
+// (cpu_ctc.h:217-262, :269-367).  Used once the minibatch alone fills the chip (see the dispatch in compute_ctc_loss).
+template <int NS>
+__global__ void __launch_bounds__(64) ctc_sweep_warp_kernel(const float* __restrict__ lp_all, float* __restrict__ alphas_ws,
+                                                            float* __restrict__ betas_ws, float* costs_dev, int* valid_dev,
+                                                            const int* flat_labels, const int* label_off, const int* label_len,
+                                                            const int* in_len, int maxT, int maxS) {
+  extern __shared__ int smem_i[];
+  const int n = blockIdx.x;
+  const int T = in_len[n], L = label_len[n], S = 2 * L + 1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool is_beta = (tid >> 5) == 1;
+  int* s_inc = smem_i;                    // [maxS]
+  int* e_inc = s_inc + maxS;              // [maxS]
+  __shared__ int sh_repeats;
+  const int* labels = flat_labels + label_off[n];
+  if (tid == 0) {                         // cpu_ctc.h:119-155, sequential: O(L)
+    int e_counter = 0, s_counter = 0, repeats = 0;
+    s_inc[s_counter++] = 1;
+    for (int i = 1; i < L; ++i) {
+      if (labels[i - 1] == labels[i]) {
+        s_inc[s_counter++] = 1; s_inc[s_counter++] = 1;
+        e_inc[e_counter++] = 1; e_inc[e_counter++] = 1;
+        ++repeats;
+      } else {
+        s_inc[s_counter++] = 2;
+        e_inc[e_counter++] = 2;
+      }
+    }
+    e_inc[e_counter++] = 1;
+    sh_repeats = repeats;
+  }
+  __syncthreads();
+  const int repeats = sh_repeats;
+  if (L + repeats > T) {                  // cpu_ctc.h:193-195: cost 0, gradient untouched
+    if (tid == 0) { costs_dev[n] = 0.f; valid_dev[n] = 0; }
+    return;
+  }
+  const float* lp = lp_all + (size_t)n * maxT * maxS;
+  // third-term flags: alpha may come from i-2 / beta from i+2 only across a blank between two DIFFERENT labels
+  bool skip_a[NS], skip_b[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int i = j * 32 + lane;
+    const bool odd = (i & 1) && i < S;
+    skip_a[j] = odd && i >= 3 && labels[i >> 1] != labels[(i >> 1) - 1];
+    skip_b[j] = odd && i + 2 < S && i != S - 2 && labels[i >> 1] != labels[(i >> 1) + 1];
+  }
+  float prev[NS], lp1[NS], lp2[NS];       // lp rows of the next step and the one after
+  auto load_row = [&](float (&dst)[NS], int t) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { const int i = j * 32 + lane; dst[j] = (t >= 0 && t < T && i < S) ? lp[(size_t)t * maxS + i] : 0.f; }
+  };
+
+  if (!is_beta) {
+    float* alphas = alphas_ws + (size_t)n * maxT * maxS;
+    int start = (((S / 2) + repeats - T) < 0) ? 0 : 1;
+    int end = S > 1 ? 2 : 1;
+    load_row(lp1, 0);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int i = j * 32 + lane;
+      prev[j] = (i < S && i >= start && i < end) ? lp1[j] : neg_inf();
+      if (i < S) alphas[i] = prev[j];
+    }
+    load_row(lp1, 1);
+    load_row(lp2, 2);
+    for (int t = 1; t < T; ++t) {
+      const int remain = (S / 2) + repeats - (T - t);
+      if (remain >= 0) start += s_inc[remain];
+      if (t <= (S / 2) + repeats) end += e_inc[t - 1];
+      float lpc[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) { lpc[j] = lp1[j]; lp1[j] = lp2[j]; }
+      load_row(lp2, t + 2);
+      float cur[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int i = j * 32 + lane;
+        const float a = prev[j];
+        const float u1 = __shfl_up_sync(0xffffffffu, a, 1), u2 = __shfl_up_sync(0xffffffffu, a, 2);
+        float w31 = neg_inf(), w30 = neg_inf();
+        if (j >= 1) { w31 = __shfl_sync(0xffffffffu, prev[j >= 1 ? j - 1 : 0], 31); w30 = __shfl_sync(0xffffffffu, prev[j >= 1 ? j - 1 : 0], 30); }
+        const float b = lane >= 1 ? u1 : w31;
+        const float c = lane >= 2 ? u2 : (lane == 1 ? w31 : w30);
+        // predicated, not branched: the NS states of a lane are independent chains that should overlap
+        const float s2 = log_plus(a, i == 0 ? neg_inf() : b);
+        const float s3 = log_plus(s2, skip_a[j] ? c : neg_inf());
+        const float v = (i < S && i >= start && i < end) ? s3 + lpc[j] : neg_inf();
+        cur[j] = v;
+        if (i < S) alphas[(size_t)t * maxS + i] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) prev[j] = cur[j];
+    }
+    float ll = neg_inf();
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { const int i = j * 32 + lane; if (i < S && i >= start && i < end) ll = log_plus(ll, prev[j]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll = log_plus(ll, __shfl_xor_sync(0xffffffffu, ll, o));
+    if (lane == 0) { costs_dev[n] = -ll; valid_dev[n] = 1; }
+    return;
+  }
+
+  // ---- beta sweep
+  float* betas_out = betas_ws + (size_t)n * maxT * maxS;
+  int start = S > 1 ? (S - 2) : 0;
+  int end = (T > (S / 2) + repeats) ? S : S - 1;
+  load_row(lp1, T - 1);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int i = j * 32 + lane;
+    prev[j] = (i < S && i >= start && i < end) ? lp1[j] : neg_inf();
+    if (i < S) betas_out[(size_t)(T - 1) * maxS + i] = prev[j];
+  }
+  load_row(lp1, T - 2);
+  load_row(lp2, T - 3);
+  for (int t = T - 2; t >= 0; --t) {
+    const int remain = (S / 2) + repeats - (T - t);
+    if (remain >= -1) start -= s_inc[remain + 1];
+    if (t < (S / 2) + repeats) end -= e_inc[t];
+    const int endloop = (end == S) ? end - 1 : end;
+    float lpc[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { lpc[j] = lp1[j]; lp1[j] = lp2[j]; }
+    load_row(lp2, t - 2);
+    float cur[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int i = j * 32 + lane;
+      const float a = prev[j];
+      const float d1 = __shfl_down_sync(0xffffffffu, a, 1), d2 = __shfl_down_sync(0xffffffffu, a, 2);
+      float w0 = neg_inf(), w1 = neg_inf();                    // states >= S hold -inf, so no guard on i+1 / i+2 is needed
+      if (j + 1 < NS) { w0 = __shfl_sync(0xffffffffu, prev[j + 1 < NS ? j + 1 : 0], 0); w1 = __shfl_sync(0xffffffffu, prev[j + 1 < NS ? j + 1 : 0], 1); }
+      const float n1 = lane <= 30 ? d1 : w0;
+      const float n2 = lane <= 29 ? d2 : (lane == 30 ? w0 : w1);
+      const bool in_loop = i < S && i >= start && i < endloop;
+      const bool in_last = end == S && i == S - 1;
+      // predicated: outside the window the reference leaves the old value in place; the last state only adds lp
+      const float s2 = log_plus(a, in_loop ? n1 : neg_inf());
+      const float s3 = log_plus(s2, (in_loop && skip_b[j]) ? n2 : neg_inf());
+      const float v = (in_loop || in_last) ? s3 + lpc[j] : a;
+      cur[j] = v;
+      if (i < S) betas_out[(size_t)t * maxS + i] = (in_loop || in_last) ? v : neg_inf();
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) prev[j] = cur[j];
+  }
+}
+
 // ---- 3. per-label log-sums of alpha*beta and grad = p - exp(sum - log p - logZ), with the reference's guards
 // (cpu_ctc.h:296-307); warp per (t, n) row
 __global__ void ctc_grad_kernel(float* grads, const float* probs, const float* alphas_ws, const float* betas_ws,
@@ -325,6 +484,14 @@ int launch_sweep(cudaStream_t st, int mb, size_t smem, const float* lp, float* a
                  const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS) {
   ASLP_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ctc_sweep_kernel<G><<<dim3(mb, 2), G, smem, st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int NS>
+int launch_sweep_warp(cudaStream_t st, int mb, const float* lp, float* alphas, float* betas, float* costs, int* valid,
+                      const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS) {
+  ctc_sweep_warp_kernel<NS><<<mb, 64, (size_t)2 * maxS * sizeof(int), st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS);
   ASLP_CHECK_LAUNCH();
   return 0;
 }
@@ -420,6 +587,22 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
     if (2 * mb < aslp_num_sms() * 8) { G = 64; while (G < z.maxS && G < 1024) G <<= 1; }
     while (4 * G < z.maxS) G <<= 1;
     int rc;
+    // Which sweep kernel: the CTA form (one state per thread) has the shorter step -- 0.53 ms against 0.90 ms for the 16
+    // utterances of a cfg3 minibatch -- and the warp-per-sweep form the higher throughput once the minibatch alone fills
+    // the chip (2048 utterances: 6.93 ms against 7.33 ms).  ASLP_CTC_SWEEP=warp|block forces one (the tests run both).
+    const char* sweep_env = getenv("ASLP_CTC_SWEEP");
+    const bool force_warp = sweep_env != nullptr && strcmp(sweep_env, "warp") == 0;
+    const bool force_block = sweep_env != nullptr && strcmp(sweep_env, "block") == 0;
+    const bool want_warp = z.maxS <= 256 && !force_block && (force_warp || mb >= aslp_num_sms() * 8);
+    if (want_warp) {
+      const int ns = (z.maxS + 31) / 32;
+#define ASLP_SWEEP_WARP(NSv) rc = launch_sweep_warp<NSv>(st, mb, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS)
+      switch (ns) {
+        case 1: ASLP_SWEEP_WARP(1); break; case 2: ASLP_SWEEP_WARP(2); break; case 3: ASLP_SWEEP_WARP(3); break; case 4: ASLP_SWEEP_WARP(4); break;
+        case 5: ASLP_SWEEP_WARP(5); break; case 6: ASLP_SWEEP_WARP(6); break; case 7: ASLP_SWEEP_WARP(7); break; default: ASLP_SWEEP_WARP(8); break;
+      }
+#undef ASLP_SWEEP_WARP
+    } else
     switch (G) {
       case 32: rc = launch_sweep<32>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
       case 64: rc = launch_sweep<64>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;

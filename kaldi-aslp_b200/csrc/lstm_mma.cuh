@@ -28,28 +28,42 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 2 ? 1 : 2; };   // k-interleaved accumulator sets
+// Accumulator scheme of the forward contraction.  ASLP_FWD_ACC3 = 1: three independent accumulators per (m-tile, slot) --
+// lo*hi, hi*lo, hi*hi never wait for each other -- with 1 (MT >= 2) or 2 k-interleave slots; 0: two accumulators (the cross
+// terms share one, issued with the hi*hi MMA between them) with 2 / 4 slots.  A/B-measured in one run on the cfg3 slice
+// (tools/gpu_ab_fwd.sh); the issue floor is 8 cycles per MMA per sub-partition (tools/micro/mma_rate.cu).
+#ifndef ASLP_FWD_ACC3
+#define ASLP_FWD_ACC3 1
+#endif
+#ifndef ASLP_ISSUE_EARLY
+#define ASLP_ISSUE_EARLY 0
+#endif
+#ifndef ASLP_WARM_AHEAD
+#define ASLP_WARM_AHEAD 2      // items ahead the non-recurrent operands are pulled into L2 (0: no prefetch)
+#endif
+#if ASLP_FWD_ACC3
+template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 2 ? 1 : 2; static constexpr int SETS = 3; };
+#else
+template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 4 ? 1 : (MT_ >= 2 ? 2 : 4); static constexpr int SETS = 2; };
+#endif
 
 // part_w[stream][NPP] = Wslice[MT_*16 rows, k-slice of this warp] * X[k-slice, streams]   (8 streams per n-tile)
 // wa: A fragments (a0: row g, k tig; a1: row g+8, k tig; a2: row g, k tig+4; a3: row g+8, k tig+4), fp32.
-// The three products of a (m-tile, k-tile) -- lo*hi, hi*lo, hi*hi -- go to three independent accumulators, so an MMA never
-// waits for the one issued just before it (the two cross terms used to share one accumulator and ran back to back); the
-// next MMA into the same accumulator is a whole k-tile (3 * MT_ * K MMAs) later.  The chain, not the issue rate, is what
-// a single step waits for: the issue floor is 8 cycles per MMA per sub-partition (tools/micro/mma_rate.cu).
 template <int MT_, int KT_>
 __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], const float* xT, int SP, int kbase, int Kdim,
                                              int ntiles, float* part_w, int lane) {
   constexpr int NPP = MT_ * 16 + 4;
   constexpr int AK = MmaAcc<MT_>::K;
+  constexpr int SETS = MmaAcc<MT_>::SETS;
   const int g = lane >> 2, tig = lane & 3;
   for (int nt = 0; nt < ntiles; ++nt) {
-    float acc[MT_][AK][3][4];
+    float acc[MT_][AK][SETS][4];
 #pragma unroll
     for (int mt = 0; mt < MT_; ++mt)
 #pragma unroll
       for (int a = 0; a < AK; ++a)
 #pragma unroll
-        for (int h = 0; h < 3; ++h) { acc[mt][a][h][0] = acc[mt][a][h][1] = acc[mt][a][h][2] = acc[mt][a][h][3] = 0.f; }
+        for (int h = 0; h < SETS; ++h) { acc[mt][a][h][0] = acc[mt][a][h][1] = acc[mt][a][h][2] = acc[mt][a][h][3] = 0.f; }
 #pragma unroll
     for (int kt = 0; kt < KT_; ++kt) {
       {
@@ -65,8 +79,8 @@ __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], con
 #pragma unroll
           for (int q = 0; q < 4; ++q) split_tf32(wa[mt][kt][q], ah[q], al[q]);
           mma_tf32(acc[mt][kt % AK][1], al, bh0, bh1);
-          mma_tf32(acc[mt][kt % AK][2], ah, bl0, bl1);
           mma_tf32(acc[mt][kt % AK][0], ah, bh0, bh1);
+          mma_tf32(acc[mt][kt % AK][SETS - 1], ah, bl0, bl1);
         }
       }
     }
@@ -77,7 +91,11 @@ __device__ __forceinline__ void mma_contract(const float (&wa)[MT_][KT_][4], con
       for (int q = 0; q < 4; ++q) {
         float lo = 0.f, hi = 0.f;
 #pragma unroll
-        for (int a = 0; a < AK; ++a) { lo += acc[mt][a][1][q] + acc[mt][a][2][q]; hi += acc[mt][a][0][q]; }
+        for (int a = 0; a < AK; ++a) {
+          lo += acc[mt][a][1][q];
+          if (SETS == 3) lo += acc[mt][a][2][q];
+          hi += acc[mt][a][0][q];
+        }
         c[q] = lo + hi;                                  // small terms first
       }
       // c0: (row g, stream 2tig)  c1: (g, 2tig+1)  c2: (g+8, 2tig)  c3: (g+8, 2tig+1); stored stream-major
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
     const float* p = pre_ptr(it);
     if (p != nullptr) { prefetch_l2(p); prefetch_l2(p + C); prefetch_l2(p + 2 * C); prefetch_l2(p + 3 * C); }
   };
-  warm(0); warm(1);
+  if (ASLP_WARM_AHEAD > 0) { for (int w = 0; w < ASLP_WARM_AHEAD; ++w) warm(w); }
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? T + 1 : 0) * slot);
 
@@ -342,16 +360,20 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
       if (seq_len != nullptr && t > seq_len[s]) { yg = yi = yf = yo = yc = yh = ym = 0.f; }
       st_pub(xa + ((size_t)t * C + c0 + cl) * SX + s, ym);       // publish m(t) first: it is what the other SMs wait for
       if (L.timing != nullptr && threadIdx.x == 0) tacc[7] += clock64() - k4;
+      if (ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
       float* o = buf + row * ldb + c0 + cl;
       o[0] = yg; o[C] = yi; o[2 * C] = yf; o[3 * C] = yo; o[4 * C] = yc; o[5 * C] = yh; o[6 * C] = ym;
       cst[ci] = yc;
+    } else if (ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) {
+      stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
     }
     // next step's exchange copies: after the bookkeeping stores (about one store-to-L2 latency after the publish, so
-    // the first round usually finds the data), before the prefetch address arithmetic; xT is free (contraction done)
+    // the first round usually finds the data), before the prefetch address arithmetic; xT is free (contraction done).
+    // ASLP_ISSUE_EARLY = 1 issues them right after the publish instead (A/B variant, tools/gpu_ab_fwd.sh).
     RECUR_TICK(e0);
-    if (hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    if (!ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
     RECUR_TICK(e1);
-    warm(it + 2);
+    if (ASLP_WARM_AHEAD > 0) warm(it + ASLP_WARM_AHEAD);
     if (L.timing != nullptr && threadIdx.x == 0) { tacc[8] += e0 - k4; tacc[9] += e1 - e0; tacc[10] += clock64() - e1; }
     if (L.timing != nullptr && threadIdx.x == 0) {
       const long long k5 = clock64();
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
     prefetch_l2(buf + ((size_t)tn * S + s) * ldb + 2 * C + cc);
     prefetch_l2(dbuf + ((size_t)t * S + s) * lddb + 6 * C + cc);
   };
-  warm(0); warm(1);
+  if (ASLP_WARM_AHEAD > 0) { for (int w = 0; w < ASLP_WARM_AHEAD; ++w) warm(w); }
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? 0 : T + 1) * slot);
 
@@ -505,14 +527,17 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_mma_kernel(Launch L) {
       float* x = xa + ((size_t)t * K + cc) * SX + s;                   // publish dgifo(t) first
       st_pub(x, dg); st_pub(x + (size_t)C * SX, di); st_pub(x + (size_t)2 * C * SX, df); st_pub(x + (size_t)3 * C * SX, dout);
       if (L.timing != nullptr && threadIdx.x == 0) tacc[7] += clock64() - k4;
+      if (ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
       float* d = dbuf + row * lddb + cc;
       d[0] = dg; d[C] = di; d[2 * C] = df; d[3 * C] = dout; d[4 * C] = dc; d[5 * C] = dh; d[6 * C] = dm;
       st[si] = dc; st[plane + si] = di; st[2 * plane + si] = df;
+    } else if (ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) {
+      stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
     }
     RECUR_TICK(e0);
-    if (hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    if (!ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
     RECUR_TICK(e1);
-    warm(it + 2);
+    if (ASLP_WARM_AHEAD > 0) warm(it + ASLP_WARM_AHEAD);
     if (L.timing != nullptr && threadIdx.x == 0) { tacc[8] += e0 - k4; tacc[9] += e1 - e0; tacc[10] += clock64() - e1; }
     if (L.timing != nullptr && threadIdx.x == 0) {
       const long long k5 = clock64();

@@ -10,6 +10,14 @@ from oracle import ctc_oracle as CO
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["warp", "block"])
+def sweep_form(request, monkeypatch):
+    """Every test runs with both alpha/beta sweep kernels: the warp-per-sweep form (default up to 256 states) and the
+    one-state-per-thread CTA form (ASLP_CTC_SWEEP=block, also what longer label sequences use)."""
+    monkeypatch.setenv("ASLP_CTC_SWEEP", request.param)
+    return request.param
+
+
 def gpu_ctc(acts, labels, ilen):
     import torch
     import kaldi_aslp_b200 as K
@@ -131,3 +139,30 @@ def test_ctc_cpu_location_is_refused():
     rc = L.compute_ctc_loss(a.ctypes.data, g.ctypes.data, lab.ctypes.data, ll.ctypes.data, il.ctypes.data, 5, 1,
                             c.ctypes.data, ws.ctypes.data, info)
     assert rc == 3      # CTC_STATUS_EXECUTION_FAILED: there is no CPU path
+
+
+def test_ctc_more_than_256_states_uses_block_form():
+    # 140 labels -> 281 states: past the warp form's 8 states per lane; must still match the oracle
+    rng = np.random.default_rng(5)
+    K, T, L, mb = 40, 330, 140, 3
+    acts = rng.standard_normal((T, mb, K)).astype(np.float32)
+    labels = [gen_labels(rng, K, L) for _ in range(mb)]
+    costs, grads = gpu_ctc(acts, labels, [T] * mb)
+    c2, g2 = CO.cost_and_grad(acts, labels, [T] * mb)
+    assert np.allclose(costs, c2, rtol=1e-4, atol=1e-5)
+    assert np.abs(grads - g2).max() < max(1e-4, 4 * float(np.spacing(np.float32(np.abs(c2).max()))))
+
+
+@pytest.mark.parametrize("L", [1, 2, 16, 17, 33, 64, 100, 127])
+def test_ctc_state_counts_around_lane_boundaries(L):
+    # 2L+1 states against the lanes x states-per-lane partition of the warp form (NS = 1 .. 8), with heavy label repeats
+    rng = np.random.default_rng(100 + L)
+    K, mb = 6, 4
+    T = 2 * L + 9
+    acts = rng.standard_normal((T, mb, K)).astype(np.float32)
+    labels = [[int(v) for v in rng.integers(1, 3, size=L)] for _ in range(mb)]      # two symbols: many repeats
+    ilen = [T, T - 3, T, max(1, T - 7)]
+    costs, grads = gpu_ctc(acts, labels, ilen)
+    c2, g2 = CO.cost_and_grad(acts, labels, ilen)
+    assert np.allclose(costs, c2, rtol=1e-4, atol=1e-5), (costs, c2)
+    assert np.abs(grads - g2).max() < 1e-4
