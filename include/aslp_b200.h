@@ -254,6 +254,11 @@ int aslp_comm_allreduce_sum_f32(aslp_comm_t c, aslp_stream_t s, float* buf, size
 int aslp_comm_allreduce_sum_f64(aslp_comm_t c, aslp_stream_t s, double* buf, size_t n);  /* ReduceAccStat (mpi-node.h:76-91) */
 int aslp_comm_allreduce_sum_i32(aslp_comm_t c, aslp_stream_t s, int* buf, size_t n);
 int aslp_comm_barrier(aslp_comm_t c, aslp_stream_t s);
+/* point-to-point exchange of a packed fp32 arena with one peer: the async parameter-server modes
+ * (MPI_Send / MPI_Recv / MPI_Sendrecv in easgd-worker.cc:49-56, easgd-server.cc:66-73, asgd-worker.cc:47-58, asgd-server.cc:82-99) */
+int aslp_comm_send_f32(aslp_comm_t c, aslp_stream_t s, const float* buf, size_t n, int peer);
+int aslp_comm_recv_f32(aslp_comm_t c, aslp_stream_t s, float* buf, size_t n, int peer);
+int aslp_comm_sendrecv_f32(aslp_comm_t c, aslp_stream_t s, const float* sendbuf, float* recvbuf, size_t n, int peer);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ typedef void* aslp_nnet_t;     /* kaldi::aslp_nnet::Nnet          (src/aslp-nnet
 typedef void* aslp_xent_t;     /* kaldi::aslp_nnet::Xent          (src/aslp-nnet/nnet-loss.h)          */
 typedef void* aslp_warpctc_t;  /* kaldi::aslp_nnet::WarpCtc       (src/aslp-nnet/warp-ctc.h:27-129)    */
 typedef void* aslp_worker_t;   /* kaldi::IWorker                  (src/aslp-parallel/itf.h:27-36)      */
+typedef void* aslp_server_t;   /* kaldi::IServer                  (src/aslp-parallel/itf.h:38-43)      */
 
 const char* aslp_nnet_last_error(void);
 int aslp_nnet_select_device(int dev);                 /* CuDevice::Instantiate().SelectGpuId (aslp-nnet-train-*.cc) */
@@ -96,6 +97,21 @@ int aslp_worker_synchronize(aslp_worker_t w, int num_frames, int* keep_going);  
 int aslp_worker_stop(aslp_worker_t w);                                            /* IWorker::Stop */
 int aslp_worker_reduce_acc_stat(aslp_worker_t w, aslp_nnet_t n);                  /* MpiNode::ReduceAccStat (mpi-node.h:76-91) */
 int aslp_worker_destroy(aslp_worker_t w);
+/* worker types also: "easgd" (bmuf_learn_rate carries alpha, easgd-worker.h:20), "asgd" / "masgd" (asgd-worker.cc); rank 0 is
+ * the server of these modes and creates an aslp_server_t instead of a worker.
+ * ---- async parameter servers (easgd-server.cc, asgd-server.cc, masgd-server.cc): rank 0, Run() returns when every worker
+ * has sent kMsgFinished.  The any-source message channel is loopback TCP on ASLP_CTRL_PORT (default MASTER_PORT + 1). */
+int aslp_server_create(const char* type, const char nccl_id[128], int nranks, float alpha, int sync_period, float momentum, aslp_server_t* out);
+int aslp_server_init_param(aslp_server_t s, aslp_nnet_t n);                       /* IServer::InitParam(GetGpuParams) */
+int aslp_server_run(aslp_server_t s);                                             /* IServer::Run */
+int aslp_server_destroy(aslp_server_t s);
+/* the control channel alone (host only; what replaces MPI_Recv(MPI_ANY_SOURCE, kTagMsg), itf.h:13-22) */
+int aslp_ctrl_server_create(int port, int nworkers, void** out);
+int aslp_ctrl_server_recv_any(void* server, int* worker_rank, int* msg_type);
+int aslp_ctrl_server_destroy(void* server);
+int aslp_ctrl_client_create(int port, int rank, void** out);
+int aslp_ctrl_client_send(void* client, int msg_type);
+int aslp_ctrl_client_destroy(void* client);
 
 #ifdef __cplusplus
 }

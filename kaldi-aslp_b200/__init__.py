@@ -22,7 +22,7 @@ LIB_HOST_PATH = os.path.join(HERE, "libaslp_nnet.so")
 _CTYPE = {
     "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
     "unsigned long long": ctypes.c_ulonglong, "aslp_stream_t": ctypes.c_void_p, "aslp_comm_t": ctypes.c_void_p,
-    "aslp_nnet_t": ctypes.c_void_p, "aslp_worker_t": ctypes.c_void_p, "long long": ctypes.c_longlong,
+    "aslp_nnet_t": ctypes.c_void_p, "aslp_worker_t": ctypes.c_void_p, "aslp_server_t": ctypes.c_void_p, "long long": ctypes.c_longlong,
     "ctcStatus_t": ctypes.c_int,
 }
 

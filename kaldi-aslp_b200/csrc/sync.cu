@@ -248,4 +248,29 @@ int aslp_comm_barrier(aslp_comm_t c, aslp_stream_t s) {
   return 0;
 }
 
+// point-to-point exchange of a packed arena with one peer (the async server modes: MPI_Send / MPI_Recv / MPI_Sendrecv of
+// easgd-worker.cc:49-56, asgd-worker.cc:47-58 -- one message for the whole model instead of one per tensor)
+int aslp_comm_send_f32(aslp_comm_t c, aslp_stream_t s, const float* buf, size_t n, int peer) {
+  ASLP_REQUIRE(c != nullptr && peer >= 0 && peer < c->nranks && peer != c->rank);
+  ASLP_NCCL(ncclSend(buf, n, ncclFloat32, peer, c->comm, (cudaStream_t)s));
+  ASLP_COUNT_LAUNCH();
+  return 0;
+}
+int aslp_comm_recv_f32(aslp_comm_t c, aslp_stream_t s, float* buf, size_t n, int peer) {
+  ASLP_REQUIRE(c != nullptr && peer >= 0 && peer < c->nranks && peer != c->rank);
+  ASLP_NCCL(ncclRecv(buf, n, ncclFloat32, peer, c->comm, (cudaStream_t)s));
+  ASLP_COUNT_LAUNCH();
+  return 0;
+}
+int aslp_comm_sendrecv_f32(aslp_comm_t c, aslp_stream_t s, const float* sendbuf, float* recvbuf, size_t n, int peer) {
+  ASLP_REQUIRE(c != nullptr && peer >= 0 && peer < c->nranks && peer != c->rank && sendbuf != recvbuf);
+  ASLP_NCCL(ncclGroupStart());
+  ncclResult_t r1 = ncclSend(sendbuf, n, ncclFloat32, peer, c->comm, (cudaStream_t)s);
+  ncclResult_t r2 = ncclRecv(recvbuf, n, ncclFloat32, peer, c->comm, (cudaStream_t)s);
+  ASLP_NCCL(ncclGroupEnd());
+  ASLP_NCCL(r1); ASLP_NCCL(r2);
+  ASLP_COUNT_LAUNCH();
+  return 0;
+}
+
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include "nnet-loss.h"
 #include "nnet-nnet.h"
 #include "parallel.h"
+#include "parallel-async.h"
 
 using namespace kaldi;
 using namespace kaldi::aslp_nnet;
@@ -239,7 +240,9 @@ int aslp_worker_create(const char* type, const char nccl_id[128], int nranks, in
   if (t == "bsp") w = new BspWorker(nccl_id, nranks, rank);
   else if (t == "bmuf") w = new BmufWorker(nccl_id, nranks, rank, bmuf_momentum, bmuf_learn_rate);
   else if (t == "sod") { OptimizerOption o; if (sod_solver && *sod_solver) o.solver = sod_solver; w = new SodWorker(nccl_id, nranks, rank, o); }
-  else KALDI_ERR << "Unsupported worker type: " << t << " (bsp | bmuf | sod; the async easgd/asgd/masgd servers are not built, DESIGN.md)";
+  else if (t == "easgd") w = new EasgdWorker(nccl_id, nranks, rank, bmuf_learn_rate);      // bmuf_learn_rate carries alpha
+  else if (t == "asgd" || t == "masgd") w = new AsgdWorker(nccl_id, nranks, rank);       // the MASGD worker is the ASGD worker
+  else KALDI_ERR << "Unsupported worker type: " << t << " (bsp | bmuf | sod | easgd | asgd | masgd)";
   *out = w;
   CAPI_END
 }
@@ -261,5 +264,34 @@ int aslp_worker_reduce_acc_stat(aslp_worker_t w, aslp_nnet_t n) {
   CAPI_END
 }
 int aslp_worker_destroy(aslp_worker_t w) { CAPI_BEGIN delete static_cast<IWorker*>(w); CAPI_END }
+
+int aslp_server_create(const char* type, const char nccl_id[128], int nranks, float alpha, int sync_period, float momentum, aslp_server_t* out) {
+  CAPI_BEGIN
+  const std::string t(type);
+  IServer* sv = nullptr;
+  if (t == "easgd") sv = new EasgdServer(nccl_id, nranks, alpha);
+  else if (t == "asgd") sv = new AsgdServer(nccl_id, nranks, alpha, sync_period, -1.0f);
+  else if (t == "masgd") sv = new AsgdServer(nccl_id, nranks, 1.0f, sync_period, momentum);
+  else KALDI_ERR << "Unsupported server type: " << t << " (easgd | asgd | masgd)";
+  *out = sv;
+  CAPI_END
+}
+int aslp_server_init_param(aslp_server_t sv, aslp_nnet_t n) {
+  CAPI_BEGIN
+  std::vector<std::pair<BaseFloat*, int>> params;
+  N(n)->GetGpuParams(&params);
+  static_cast<IServer*>(sv)->InitParam(params);
+  CAPI_END
+}
+int aslp_server_run(aslp_server_t sv) { CAPI_BEGIN static_cast<IServer*>(sv)->Run(); CAPI_END }
+int aslp_server_destroy(aslp_server_t sv) { CAPI_BEGIN delete static_cast<IServer*>(sv); CAPI_END }
+
+/* control channel alone (no GPU): the MPI_Recv(MPI_ANY_SOURCE) replacement of the async servers */
+int aslp_ctrl_server_create(int port, int nworkers, void** out) { CAPI_BEGIN *out = new CtrlServer(port, nworkers); CAPI_END }
+int aslp_ctrl_server_recv_any(void* sv, int* worker_rank, int* msg_type) { CAPI_BEGIN static_cast<CtrlServer*>(sv)->RecvAny(worker_rank, msg_type); CAPI_END }
+int aslp_ctrl_server_destroy(void* sv) { CAPI_BEGIN delete static_cast<CtrlServer*>(sv); CAPI_END }
+int aslp_ctrl_client_create(int port, int rank, void** out) { CAPI_BEGIN *out = new CtrlClient(port, rank); CAPI_END }
+int aslp_ctrl_client_send(void* c, int msg_type) { CAPI_BEGIN static_cast<CtrlClient*>(c)->Send(msg_type); CAPI_END }
+int aslp_ctrl_client_destroy(void* c) { CAPI_BEGIN delete static_cast<CtrlClient*>(c); CAPI_END }
 
 }  // extern "C"

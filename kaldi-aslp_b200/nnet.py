@@ -259,6 +259,26 @@ class Worker:
             self.h = None
 
 
+class Server:
+    """kaldi::IServer (src/aslp-parallel/itf.h:38-43): easgd | asgd | masgd parameter server on rank 0."""
+
+    def __init__(self, kind, nccl_id, nranks, alpha=0.5, sync_period=1000, momentum=0.9):
+        self.h = P()
+        idbuf = ctypes.create_string_buffer(bytes(nccl_id), 128)
+        _ck(host_lib().aslp_server_create(kind.encode(), idbuf, nranks, alpha, sync_period, momentum, ctypes.byref(self.h)))
+
+    def init_param(self, nnet):
+        _ck(host_lib().aslp_server_init_param(self.h, nnet.h))
+
+    def run(self):
+        _ck(host_lib().aslp_server_run(self.h))
+
+    def close(self):
+        if self.h:
+            host_lib().aslp_server_destroy(self.h)
+            self.h = None
+
+
 def nccl_unique_id():
     buf = ctypes.create_string_buffer(128)
     rc = cuda_lib().aslp_comm_unique_id(buf)

@@ -450,6 +450,34 @@ def sod_optimize(opt, w, g, s1, s2, lr, p1, p2, step, floor=1e-8):
 _LZ, _LINF, _EXPLIM, _FMAX = F(-1e30), F(1e30), F(88.722839), F(3.4028235e38)
 
 
+# ---------------------------------------------------------------- async parameter-server modes (aslp-parallel)
+# UNPINNED like the synchronous workers: the reference has no tests for them and needs MPI.  One call = what the server and
+# the worker do for ONE kMsgSynchronize, in the order the server receives the messages.
+
+def easgd_exchange(w_worker, w_server, alpha):
+    """easgd-worker.cc:58-62 and easgd-server.cc:78-83: both sides move towards the OTHER side's pre-update model."""
+    a = F(alpha)
+    new_worker = (a * w_server + (F(1) - a) * w_worker).astype(F)
+    new_server = (a * w_worker + (F(1) - a) * w_server).astype(F)
+    return new_worker, new_server
+
+
+def asgd_update(w_worker, w_prev_worker, w_server, alpha):
+    """asgd-worker.cc:40-44 + asgd-server.cc:88-92: delta = w - w_prev; server += alpha * delta; the worker restarts from
+    the server's new model (outside the periodic barrier)."""
+    delta = (w_worker - w_prev_worker).astype(F)
+    new_server = (w_server + F(alpha) * delta).astype(F)
+    return new_server.copy(), new_server
+
+
+def masgd_update(w_worker, w_prev_worker, w_server, diff_k, momentum):
+    """masgd-server.cc:121-123 (LMASGD): d_k = momentum * d_k + delta ; server += d_k."""
+    delta = (w_worker - w_prev_worker).astype(F)
+    d = (delta + F(momentum) * diff_k).astype(F)
+    new_server = (w_server + d).astype(F)
+    return new_server.copy(), new_server, d
+
+
 def _add_ab(a, b):      # ctc-utils.h:60-65
     return _LZ if (a == _LZ or b == _LZ) else F(a + b)
 
