@@ -7,7 +7,7 @@
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
 #include "nnet-trnopts.h"
-#include "parallel.h"
+#include "parallel-async.h"
 #include "parse-options.h"
 #include "table.h"
 
@@ -53,7 +53,9 @@ int main(int argc, char* argv[]) {
     po.Register("drop-len", &drop_len, "if Sentence frame length greater than drop_len,then drop it, default(0, no drop)");
     // worker extension
     std::string worker_type = "";
-    po.Register("worker-type", &worker_type, "Worker type(bsp | bmuf | sod); empty: single process");
+    po.Register("worker-type", &worker_type, "Worker type(bsp | bmuf | sod | easgd | asgd); empty: single process");
+    float alpha = 0.5f;
+    po.Register("alpha", &alpha, "Moving rate alpha for easgd worker");
     int32 sync_period = 25600;
     po.Register("sync-period", &sync_period, "number of frames for one sync with other workers");
     float bmuf_momentum = 0.9f, bmuf_learn_rate = 1.0f;
@@ -87,6 +89,8 @@ int main(int argc, char* argv[]) {
       if (worker_type == "bsp") worker.reset(new BspWorker(boot.id, boot.nranks, boot.rank));
       else if (worker_type == "bmuf") worker.reset(new BmufWorker(boot.id, boot.nranks, boot.rank, bmuf_momentum, bmuf_learn_rate));
       else if (worker_type == "sod") worker.reset(new SodWorker(boot.id, boot.nranks, boot.rank, optimizer_opts));
+      else if (worker_type == "easgd") worker.reset(new EasgdWorker(boot.id, boot.nranks, boot.rank, alpha));     // rank 0 runs aslp-nnet-train-server
+      else if (worker_type == "asgd") worker.reset(new AsgdWorker(boot.id, boot.nranks, boot.rank));
       else KALDI_ERR << "Unsupported worker type: " << worker_type;
       std::vector<std::pair<BaseFloat*, int>> params;
       nnet.GetGpuParams(&params);
@@ -206,9 +210,11 @@ int main(int argc, char* argv[]) {
       }
     }
     if (worker) {
-      if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);
-      while (worker->Synchronize(0)) {}
-      worker->Stop();
+      if (!worker->IsAsync()) {
+        if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);
+        while (worker->Synchronize(0)) {}
+      }
+      worker->Stop();         // async modes: kMsgFinished to the server, which writes the model
     }
     if (!crossvalidate && (!worker || worker->IsMainNode())) nnet.Write(target_model_filename, binary);
     KALDI_LOG << "Done " << num_done << " files, " << num_no_tgt_mat << " with no tgt_mats, " << num_other_error << " with other errors. "

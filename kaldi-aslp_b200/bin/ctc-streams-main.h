@@ -11,7 +11,7 @@
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
 #include "nnet-trnopts.h"
-#include "parallel.h"
+#include "parallel-async.h"
 #include "parse-options.h"
 #include "table.h"
 
@@ -48,7 +48,9 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     po.Register("use-gpu", &use_gpu, "yes|no|optional, only has effect if compiled with CUDA");
     // data-parallel extension (config 5)
     std::string worker_type = "";
-    po.Register("worker-type", &worker_type, "Data-parallel worker: bsp | bmuf (empty: single process)");
+    po.Register("worker-type", &worker_type, "Data-parallel worker: bsp | bmuf | easgd | asgd (empty: single process)");
+    float alpha = 0.5f;
+    po.Register("alpha", &alpha, "Moving rate alpha for easgd worker");
     int32 sync_period = 25600;
     po.Register("sync-period", &sync_period, "number of frames for one sync with other workers");
     float bmuf_momentum = 0.9f, bmuf_learn_rate = 1.0f;
@@ -75,6 +77,8 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
       WorkerBootstrap boot;
       if (worker_type == "bsp") worker.reset(new BspWorker(boot.id, boot.nranks, boot.rank));
       else if (worker_type == "bmuf") worker.reset(new BmufWorker(boot.id, boot.nranks, boot.rank, bmuf_momentum, bmuf_learn_rate));
+      else if (worker_type == "easgd") worker.reset(new EasgdWorker(boot.id, boot.nranks, boot.rank, alpha));     // rank 0 runs aslp-nnet-train-server
+      else if (worker_type == "asgd") worker.reset(new AsgdWorker(boot.id, boot.nranks, boot.rank));
       else KALDI_ERR << "Unsupported worker type: " << worker_type;
       std::vector<std::pair<BaseFloat*, int>> params;
       net.GetGpuParams(&params);
@@ -174,9 +178,11 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     }
     if (worker) {
       // last partial period, then zero-frame syncs until every rank is out of data (termination protocol)
-      if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);
-      while (worker->Synchronize(0)) {}
-      worker->Stop();
+      if (!worker->IsAsync()) {
+        if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);
+        while (worker->Synchronize(0)) {}
+      }
+      worker->Stop();         // async modes: kMsgFinished to the server, which writes the model
     }
     if (!crossvalidate) KALDI_LOG << net.InfoGradient();
     if (!crossvalidate && (!worker || worker->IsMainNode())) net.Write(target_model_filename, binary);

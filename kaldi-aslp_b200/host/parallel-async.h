@@ -62,6 +62,7 @@ class EasgdWorker : public IWorker {
   ~EasgdWorker();
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);        // always true (easgd-worker.cc:66)
+  bool IsAsync() const { return true; }
   void Stop();
  private:
   float alpha_;
@@ -83,6 +84,7 @@ class AsgdWorker : public IWorker {
   ~AsgdWorker();
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);
+  bool IsAsync() const { return true; }
   void Stop();
  private:
   CuVector w_prev_;

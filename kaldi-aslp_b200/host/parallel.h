@@ -35,6 +35,7 @@ class IWorker : public NcclNode {
   virtual ~IWorker();
   virtual void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   virtual bool Synchronize(int num_worker_samples) = 0;   // false when every rank is out of data
+  virtual bool IsAsync() const { return false; }          // true: a parameter-server worker (Synchronize never says "all done")
   // a rank that has finished its shard keeps answering with zero frames so collectives stay matched (bsp-worker.cc:60-65)
   virtual void Stop() { KALDI_LOG << "Worker " << Rank() << "finished, waitting for others"; while (Synchronize(0)) {} }
  protected:
