@@ -1,11 +1,13 @@
 // aslp-nnet-train-frame -- frame-shuffled minibatch training, same command line, bookkeeping and log lines as
 // src/aslp-nnetbin/aslp-nnet-train-frame.cc:22-153.  --use-gpu=no is refused: this build has no CPU path.
+// With --worker-type it is the worker of src/aslp-parallelbin/aslp-nnet-train-frame-worker.cc (bin/worker-opts.h).
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
 #include "nnet-trnopts.h"
 #include "parse-options.h"
 #include "table.h"
+#include "worker-opts.h"
 
 int main(int argc, char* argv[]) {
   using namespace kaldi;
@@ -35,6 +37,8 @@ int main(int argc, char* argv[]) {
     po.Register("report-period", &report_period, "Number of frames for one report log, default(-1, no report)");
     int32 gpu_id = -1;
     po.Register("gpu-id", &gpu_id, "selected gpu id, if negative then select automaticly");
+    WorkerOptions wopts;
+    wopts.Register(&po);
     po.Read(argc, argv);
     if (po.NumArgs() != 4 - (crossvalidate ? 1 : 0)) { po.PrintUsage(); return 1; }
     const std::string feature_rspecifier = po.GetArg(1), targets_rspecifier = po.GetArg(2), model_filename = po.GetArg(3);
@@ -42,12 +46,14 @@ int main(int argc, char* argv[]) {
     if (!crossvalidate) target_model_filename = po.GetArg(4);
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
     if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));
+    else wopts.SelectDevice();
     if (objective_function != "xent") KALDI_ERR << "Unsupported objective function: " << objective_function;
     if (dropout_retention > 0.0) KALDI_ERR << "--dropout-retention: Dropout is not part of this build";
 
     Nnet nnet;
     nnet.Read(model_filename);
     nnet.SetTrainOptions(trn_opts);
+    wopts.Create(&nnet, crossvalidate);
     Xent loss;
     Timer time;
     long long total_frames = 0, report_frames = 0;
@@ -64,12 +70,14 @@ int main(int argc, char* argv[]) {
       if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
       total_frames += nnet_in->NumRows();
       report_frames += nnet_in->NumRows();
+      wopts.Progress(nnet_in->NumRows());
       if (report_period > 0 && report_frames >= report_period) {
         KALDI_LOG << loss.Report();
         report_frames -= report_period;
       }
     }
-    if (!crossvalidate) nnet.Write(target_model_filename, binary);
+    wopts.Finish();
+    if (!crossvalidate && wopts.WritesModel()) nnet.Write(target_model_filename, binary);
     KALDI_LOG << "[" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", " << (randomize ? "RANDOMIZED" : "NOT-RANDOMIZED") << ", "
               << time.Elapsed() / 60 << " min, fps" << total_frames / time.Elapsed() << "]";
     KALDI_LOG << loss.Report();

@@ -7,6 +7,7 @@
 #include "nnet-trnopts.h"
 #include "parse-options.h"
 #include "table.h"
+#include "worker-opts.h"
 
 int main(int argc, char* argv[]) {
   using namespace kaldi;
@@ -42,6 +43,8 @@ int main(int argc, char* argv[]) {
     po.Register("report-period", &report_period, "Number of sentence for one report log, default(200)");
     int32 dump_interval = 0;
     po.Register("dump-interval", &dump_interval, "---LSTM--- num utts between model dumping [ 0 == disabled ]");
+    WorkerOptions wopts;       // --worker-type: the worker of src/aslp-parallelbin/aslp-nnet-train-lstm-stream-worker.cc
+    wopts.Register(&po);
     po.Read(argc, argv);
     if (po.NumArgs() != 4 - (crossvalidate ? 1 : 0)) { po.PrintUsage(); return 1; }
     const std::string feature_rspecifier = po.GetArg(1), targets_rspecifier = po.GetArg(2), model_filename = po.GetArg(3);
@@ -49,11 +52,13 @@ int main(int argc, char* argv[]) {
     if (!crossvalidate) target_model_filename = po.GetArg(4);
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
     if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));
+    else wopts.SelectDevice();
     if (objective_function != "xent") KALDI_ERR << "Unsupported objective function: " << objective_function;
 
     Nnet nnet;
     nnet.Read(model_filename);
     nnet.SetTrainOptions(trn_opts);
+    wopts.Create(&nnet, crossvalidate);
     long long total_frames = 0;
     int32 num_done = 0, num_sentence = 0;
     Xent loss;
@@ -74,6 +79,7 @@ int main(int argc, char* argv[]) {
       int frame_progress = 0;
       for (int32 i = 0; i < frame_mask.Dim(); i++) frame_progress += static_cast<int>(frame_mask(i));
       total_frames += frame_progress;
+      wopts.Progress(frame_progress);
       int num_done_progress = 0;
       for (size_t i = 0; i < new_utt_flags.size(); i++) num_done_progress += new_utt_flags[i];
       num_done += num_done_progress;
@@ -88,7 +94,8 @@ int main(int argc, char* argv[]) {
         nnet.Write(nnet_name, binary);
       }
     }
-    if (!crossvalidate) nnet.Write(target_model_filename, binary);
+    wopts.Finish();
+    if (!crossvalidate && wopts.WritesModel()) nnet.Write(target_model_filename, binary);
     KALDI_LOG << "Done " << num_done << " files, [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "
               << (randomize ? "RANDOMIZED" : "NOT-RANDOMIZED") << ", " << time.Elapsed() / 60 << " min, fps" << total_frames / time.Elapsed() << "]";
     KALDI_LOG << loss.Report();

@@ -1,0 +1,74 @@
+// worker-opts.h -- the data-parallel extension shared by the trainer mains: the flags of the reference worker mains
+// (src/aslp-parallelbin/aslp-nnet-train-frame-worker.cc:60-80, aslp-nnet-train-lstm-stream-worker.cc:70-95,
+// aslp-nnet-train-lc-blstm-streams-worker.cc:100-120: --worker-type, --alpha, --sync-period, --bmuf-momentum,
+// --bmuf-learn-rate, optimizer options), worker construction after the model is read, the per-minibatch frame counter with
+// its Synchronize, and the end-of-data protocol.  One rank per GPU (RANK / WORLD_SIZE / LOCAL_RANK, NCCL id through
+// ASLP_NCCL_ID_FILE); with an empty --worker-type a main is the plain single-process trainer.
+#ifndef ASLP_BIN_WORKER_OPTS_H_
+#define ASLP_BIN_WORKER_OPTS_H_
+#include <memory>
+#include "nnet-nnet.h"
+#include "parallel-async.h"
+#include "parse-options.h"
+
+namespace kaldi {
+
+struct WorkerOptions {
+  std::string worker_type;
+  float alpha, bmuf_momentum, bmuf_learn_rate;
+  int32 sync_period;
+  OptimizerOption optimizer_opts;
+  std::unique_ptr<IWorker> worker;
+  int32 frames_since_sync;
+  WorkerOptions() : alpha(0.5f), bmuf_momentum(0.9f), bmuf_learn_rate(1.0f), sync_period(25600), frames_since_sync(0) {}
+  void Register(ParseOptions* po) {
+    po->Register("worker-type", &worker_type, "Worker type(bsp | bmuf | sod | easgd | asgd); empty: single process");
+    po->Register("alpha", &alpha, "Moving rate alpha for easgd worker");
+    po->Register("sync-period", &sync_period, "number frames for every synchronization");
+    po->Register("bmuf-momentum", &bmuf_momentum, "bmuf block momentum");
+    po->Register("bmuf-learn-rate", &bmuf_learn_rate, "bmuf block learning rate");
+    optimizer_opts.Register(po);
+  }
+  // before the model is read: one GPU per rank
+  void SelectDevice() const {
+    if (worker_type.empty()) return;
+    if (const char* lr = std::getenv("LOCAL_RANK")) ASLP_OK(aslp_set_device(std::atoi(lr)));
+  }
+  void Create(aslp_nnet::Nnet* nnet, bool crossvalidate) {
+    if (worker_type.empty() || crossvalidate) return;
+    WorkerBootstrap boot;
+    if (worker_type == "bsp") worker.reset(new BspWorker(boot.id, boot.nranks, boot.rank));
+    else if (worker_type == "bmuf") worker.reset(new BmufWorker(boot.id, boot.nranks, boot.rank, bmuf_momentum, bmuf_learn_rate));
+    else if (worker_type == "sod") worker.reset(new SodWorker(boot.id, boot.nranks, boot.rank, optimizer_opts));
+    else if (worker_type == "easgd") worker.reset(new EasgdWorker(boot.id, boot.nranks, boot.rank, alpha));     // rank 0 runs aslp-nnet-train-server
+    else if (worker_type == "asgd") worker.reset(new AsgdWorker(boot.id, boot.nranks, boot.rank));
+    else KALDI_ERR << "Unsupported worker type: " << worker_type;
+    std::vector<std::pair<BaseFloat*, int>> params;
+    nnet->GetGpuParams(&params);
+    worker->InitParam(params);
+  }
+  // after every minibatch (frame-worker.cc:150-156)
+  void Progress(int32 frames) {
+    if (!worker) return;
+    frames_since_sync += frames;
+    if (frames_since_sync > sync_period) {
+      KALDI_LOG << "Worker " << worker->Rank() << " synchronize once";
+      worker->Synchronize(frames_since_sync);
+      frames_since_sync = 0;
+    }
+  }
+  // end of data: synchronous workers flush their last frames and answer zero-frame syncs until every rank is done
+  // (bsp-worker.cc:60-65); asynchronous ones tell the server they are finished
+  void Finish() {
+    if (!worker) return;
+    if (!worker->IsAsync()) {
+      if (frames_since_sync > 0) worker->Synchronize(frames_since_sync);
+      while (worker->Synchronize(0)) {}
+    }
+    worker->Stop();
+  }
+  bool WritesModel() const { return !worker || worker->IsMainNode(); }
+};
+
+}  // namespace kaldi
+#endif
