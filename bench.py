@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the CTC / GEMM / TF32-mode side measurements (profiling runs: keeps the launch list to the training steps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -346,7 +347,7 @@ def main():
         sync_info = {"ms_per_sync": float(t.item()), "params": int(nparams),
                      "bus_GBps": 2.0 * (world - 1) / world * 4.0 * nparams / (float(t.item()) * 1e-3) / 1e9,
                      "what": "pack + ONE ncclAllReduce(sum) of the fp32 arena + BMUF filter apply; bus bytes = 2(N-1)/N * 4P (SURVEY 8d)"}
-    secondary = secondary_metrics(lib, torch) if (rank == 0 and world == 1) else None
+    secondary = secondary_metrics(lib, torch) if (rank == 0 and world == 1 and not args.no_secondary) else None
     if secondary is not None and args.precision == "3xtf32":
         # the same step with single-pass TF32 chunk GEMMs (north_star's "stated looser bound" mode, parity bound 5e-3 in
         # tests/test_gpu_gemm.py); informative only -- `value` above is the fp32-grade configuration
