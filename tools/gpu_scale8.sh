@@ -1,10 +1,8 @@
 #!/bin/bash
+# weak-scaling bench lines at N = 2, 4, 8 on one 8-GPU box (BMUF over NCCL), as the driver launches them
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l > gpurun_out/ngpus.txt
-for n in 8 4; do
-  timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/bench_n$n.log 2>&1
-  echo "n=$n exit=$?"; tail -1 gpurun_out/bench_n$n.log | cut -c1-420
+for n in 2 4 8; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_n$n.log 2>&1
+  echo "n=$n exit=$?"; grep '^{' gpurun_out/bench_n$n.log | tail -1 | cut -c1-180
 done
-timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > gpurun_out/bench_ref_n8.log 2>&1
-echo "ref n=8 exit=$?"; tail -1 gpurun_out/bench_ref_n8.log | cut -c1-300
