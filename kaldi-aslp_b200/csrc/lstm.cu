@@ -347,9 +347,10 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
 }
 
 #include "lstm_mma.cuh"
+#include "lstm_bwd_t.cuh"
 
 // ---------------------------------------------------------------- host side
-struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; bool presplit; };
+struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; bool presplit; bool transposed; };
 
 size_t ws_per_dir(int T, int S, int C, int R, bool bwd) {
   const size_t SX = (size_t)(S + 3) / 4 * 4;
@@ -369,7 +370,7 @@ void fill_dir(DirDev& D, const aslp_lstm_dir_t& a) {
 // register budget (more groups = fewer CTAs per chain = more cells per CTA, but proportionally less exchange traffic)
 int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
-  P->mma = false; P->presplit = false;
+  P->mma = false; P->presplit = false; P->transposed = false;
   L.ndirs = ndirs;
   const int C = dirs[0].C, S = dirs[0].S;
   for (int i = 0; i < ndirs; ++i)
@@ -410,6 +411,15 @@ int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, si
     P->presplit = bwd && !no_presplit && mma_presplit_shape(C, SG, SGP) && mma_pick_kernel(mc, true, true) != nullptr &&
                   mma_smem_floats(C, cb, SG, SGP, bwd, true) * sizeof(float) <= 224 * 1024;
     P->smem = mma_smem_floats(C, cb, SG, SGP, bwd, P->presplit) * sizeof(float);
+    // backward, transposed form (lstm_bwd_t.cuh): one 16-row MMA tile per CTA of the chain, 8 streams per chain
+    {
+      const char* tenv = std::getenv("ASLP_LSTM_BWD_T");
+      const bool t_off = tenv != nullptr && tenv[0] == '0';
+      P->transposed = bwd && !t_off && cb == 16 && C % 16 == 0 && nblk == C / 16 && nblk <= 24 && SG == 8 && SGP == 8 &&
+                      bwd_t_smem_floats(nblk) * sizeof(float) <= 224 * 1024 &&
+                      bwd_t_exchange_floats(nblk, pg) <= (size_t)(dirs[0].T + 2) * 4 * C * L.d[0].SX;
+      if (P->transposed) { P->presplit = false; P->smem = bwd_t_smem_floats(nblk) * sizeof(float); }
+    }
     P->ws_bytes = need_ws;
     P->mc = mc;
     P->mma = true;
@@ -420,7 +430,7 @@ int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, si
 
 int make_plan(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
-  P->mma = false; P->presplit = false;
+  P->mma = false; P->presplit = false; P->transposed = false;
   L.pgroups = 1; L.SGP = 0;
   L.ndirs = ndirs;
   const int sms = aslp_num_sms();
@@ -524,9 +534,18 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
     aslp_set_last_error_msg("ASLP_LSTM_KERNEL=mma but the tensor-core recurrence does not apply to this shape", __FILE__, __LINE__);
     return ASLP_STATUS_INVALID_VALUE;
   }
-  rc = init_exchange(st, P, bwd);
-  if (rc != 0) return rc;
-  void* kfn = P.mma ? mma_pick_kernel(P.mc, bwd, P.presplit) : (bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel);
+  if (P.transposed) {
+    const size_t per_slot = bwd_t_exchange_floats(P.L.nblk, P.L.pgroups) / TR;
+    for (int i = 0; i < P.L.ndirs; ++i) {
+      xch_t_init_kernel<<<aslp_num_sms(), 256, 0, st>>>(P.L.d[i].xa, per_slot, per_slot * TR);
+      ASLP_CHECK_LAUNCH();
+    }
+  } else {
+    rc = init_exchange(st, P, bwd);
+    if (rc != 0) return rc;
+  }
+  void* kfn = P.transposed ? (void*)lstm_bwd_t_kernel
+                           : (P.mma ? mma_pick_kernel(P.mc, bwd, P.presplit) : (bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel));
   if (kfn == nullptr) { aslp_set_last_error_msg("no tensor-core recurrence kernel for this shape", __FILE__, __LINE__); return ASLP_STATUS_UNKNOWN_ERROR; }
   ASLP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   P.L.timing = g_timing;

@@ -1,0 +1,239 @@
+// lstm_bwd_t.cuh -- "transposed" backward recurrence (included by lstm.cu after lstm_mma.cuh; R == 0 / folded form).
+//
+// lstm_bwd_mma_kernel makes every CTA of a chain gather ALL 4C rows of dgifo(t+1) (40 KB at cfg3) and contract them with
+// its own 16 weight columns: 80 CTAs x 40 KB = 3.2 MB cross L2 per step, ~500 cycles at the L2-slice cap on top of the
+// round trip, and the gather needs 10 copy instructions per thread.  Here the contraction is turned around: a CTA
+// contracts its OWN 64 dgifo rows (4 gates x 16 cells, already in its shared memory) against the matching 64 ROWS of W'
+// for ALL C columns,
+//     z_j[c] = sum_{q in rows of CTA j} dgifo[q] W'[q][c]            (M = C: one 16-row MMA tile per consumer CTA, K = 64)
+// and publishes the C partial sums straight from the MMA accumulators; the owner of cell block b gathers the 20 partials
+// z_j[16 cells of b] (one contiguous 10 KB block, 2.5 copies per thread) and adds them in a fixed order.  Per step the
+// chain moves 0.8 MB read + 0.8 MB written instead of 3.2 + 0.16, the K split across warps and its shared-memory partial
+// reduction disappear (a warp owns whole m-tiles), and the B operand is 2 KB instead of 40.
+// Every partial block has ONE producer and ONE consumer, so the exchange is a ring of TR time slots that the consumer
+// re-arms with the sentinel after reading (a fence orders the re-arm before the consumer's next publish; a producer
+// overwrites a slot only TR-1 steps later, after it has consumed a publish of that consumer).  Same data-is-its-own-flag
+// protocol (NaN sentinel), same cell derivative chain and buffer layout as lstm_bwd_mma_kernel.
+#pragma once
+
+constexpr int TR = 4;                    // ring slots of the partial-sum exchange
+#ifndef ASLP_BWD_T_DELAY_NS
+#define ASLP_BWD_T_DELAY_NS 0
+#endif
+
+__device__ __forceinline__ void st_pub2(float* p, float a, float b) {
+  asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// shared memory: wT [nblk][8][32] float4 | Bsm [64][8] | Psm [nblk][16][8] | st [3][16][8] | pst [3][16]
+inline size_t bwd_t_smem_floats(int nblk) { return (size_t)nblk * 1024 + 512 + (size_t)nblk * 128 + 384 + 48; }
+// exchange floats per direction: [TR][pgroups][consumer][producer][16][8]
+inline size_t bwd_t_exchange_floats(int nblk, int pgroups) { return (size_t)TR * pgroups * nblk * nblk * 128; }
+
+static __global__ void xch_t_init_kernel(float* x, size_t per_slot, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = i < per_slot ? 0.f : __uint_as_float(SENTINEL);       // slot 0 = the zero derivative boundary, the rest armed
+}
+
+// z[c][s] = sum_k W'[own row k][c] * dgifo[k][s] for the NM m-tiles (16 columns c each) warp `warp` owns: warp, warp+8, ...
+// NM is a template parameter so that the loop has no branch: with a run-time "is this tile real" test inside, every
+// A-fragment load sat behind its branch right in front of the MMAs that use it (40 cycles per MMA instead of ~10).
+template <int NM>
+__device__ __forceinline__ void bwd_t_contract(const float4* wT, const float* Bsm, float* out, int nblk, int warp, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+  float hh[NM][4], lh[NM][4], hl[NM][4];
+#pragma unroll
+  for (int mi = 0; mi < NM; ++mi)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { hh[mi][q] = 0.f; lh[mi][q] = 0.f; hl[mi][q] = 0.f; }
+#pragma unroll
+  for (int kt = 0; kt < 8; ++kt) {
+    uint32_t bh0, bl0, bh1, bl1;
+    split_tf32(Bsm[(kt * 8 + tig) * 8 + g], bh0, bl0);
+    split_tf32(Bsm[(kt * 8 + tig + 4) * 8 + g], bh1, bl1);
+#pragma unroll
+    for (int mi = 0; mi < NM; ++mi) {
+      const float4 w4 = wT[((warp + 8 * mi) * 8 + kt) * 32 + lane];
+      uint32_t ah[4], al[4];
+      split_tf32(w4.x, ah[0], al[0]); split_tf32(w4.y, ah[1], al[1]); split_tf32(w4.z, ah[2], al[2]); split_tf32(w4.w, ah[3], al[3]);
+      mma_tf32(lh[mi], al, bh0, bh1);
+      mma_tf32(hl[mi], ah, bl0, bl1);
+      mma_tf32(hh[mi], ah, bh0, bh1);
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < NM; ++mi) {
+    float* dst = out + (size_t)(warp + 8 * mi) * nblk * 128;           // block of consumer CTA warp + 8 mi
+    // c0: (cell g, stream 2tig)  c1: (g, 2tig+1)  c2: (g+8, 2tig)  c3: (g+8, 2tig+1); small terms first
+    st_pub2(dst + g * 8 + 2 * tig, (lh[mi][0] + hl[mi][0]) + hh[mi][0], (lh[mi][1] + hl[mi][1]) + hh[mi][1]);
+    st_pub2(dst + (g + 8) * 8 + 2 * tig, (lh[mi][2] + hl[mi][2]) + hh[mi][2], (lh[mi][3] + hl[mi][3]) + hh[mi][3]);
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
+  extern __shared__ __align__(16) float smem[];
+  const MmaCta cta = mma_cta(L);
+  const DirDev& D = L.d[cta.dir];
+  const int T = D.T, S = D.S, C = D.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int nblk = L.nblk;                               // == C / 16: m-tile index == consumer CTA index
+  const int c0 = cta.blk * 16;
+  if (cta.sbeg >= S) return;                             // a chain without streams: all of its CTAs leave together
+
+  float4* wT = reinterpret_cast<float4*>(smem);          // A fragments of W'[own 64 rows][all C columns], transposed
+  float* Bsm = smem + (size_t)nblk * 1024;               // dgifo of the step just finished: [gate*16 + cell][stream]
+  float* Psm = Bsm + 512;                                // gathered partial sums [producer][cell][stream]
+  float* st = Psm + (size_t)nblk * 128;                  // d_c, d_i, d_f of the successor step [3][cell][stream]
+  float* pst = st + 384;                                 // peepholes [3][cell]
+
+  // ---- one-time: A fragments (a0: row g, k tig; a1: row g+8, k tig; a2: row g, k tig+4; a3: row g+8, k tig+4);
+  // row = cell column c of W' (m-tile mt covers cells mt*16 .. +15), k = gate*16 + own cell
+  for (int i = threadIdx.x; i < nblk * 256; i += NT) {
+    const int mt = i >> 8, kt = (i >> 5) & 7, ln = i & 31, gg = ln >> 2, tt = ln & 3;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = mt * 16 + gg + (q & 1) * 8;
+      const int k = kt * 8 + tt + (q >> 1) * 4, gate = k >> 4, cl = k & 15;
+      v[q] = (c < C && c0 + cl < C) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + c] : 0.f;
+    }
+    wT[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  for (int i = threadIdx.x; i < 384; i += NT) st[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += NT) Bsm[i] = 0.f;
+  for (int i = threadIdx.x; i < 48; i += NT) {
+    const int which = i >> 4, cl = i & 15;
+    const float* p = which == 0 ? D.peep_i : (which == 1 ? D.peep_f : D.peep_o);
+    pst[i] = (c0 + cl < C) ? p[c0 + cl] : 0.f;
+  }
+  __syncthreads();
+
+  // exchange addressing: block(slot, consumer, producer) of this chain
+  float* const X = D.xa;
+  const size_t slot_stride = (size_t)L.pgroups * nblk * nblk * 128;
+  const size_t chain_off = (size_t)cta.pg * nblk * nblk * 128;
+  auto own_block = [&](int slot) { return X + (size_t)slot * slot_stride + chain_off + (size_t)cta.blk * nblk * 128; };   // [producer][16][8]
+  const int items = nblk * 32;                           // float4 items of the own block
+  auto issue_gather = [&](int slot) {
+    const float* src = own_block(slot);
+    for (int i = threadIdx.x; i < items; i += NT) cp_async16(Psm + i * 4, src + i * 4);
+  };
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // debug phase clocks (aslp_lstm_debug_timing), thread 0
+  auto complete_gather = [&](int slot) {
+    const float* src = own_block(slot);
+    unsigned rounds = 0;
+    for (;;) {
+      cp_async_wait_all();
+      if (L.timing != nullptr && threadIdx.x == 0) tacc[5] += 1;
+      bool again = false;
+      for (int i = threadIdx.x; i < items; i += NT) {
+        const float4 v = *reinterpret_cast<const float4*>(Psm + i * 4);
+        if (sentinel_in(v)) { cp_async16(Psm + i * 4, src + i * 4); again = true; }
+      }
+      if (!again) break;
+      if (++rounds > POLL_LIMIT) __trap();
+    }
+  };
+
+  // ---- the (cell, stream) item a finishing thread owns
+  const bool fin = threadIdx.x < 128;
+  const int cl = (threadIdx.x >> 3) & 15, s_local = threadIdx.x & 7;
+  const int s = cta.sbeg + s_local;
+  const bool live = fin && s < cta.send && c0 + cl < C;
+  const int cc = c0 + cl;
+  const int reverse = D.reverse, ldb = D.ldb, lddb = D.lddb;
+  float* const buf = D.buf;
+  float* const dbuf = D.dbuf;
+  const float pi = fin ? pst[cl] : 0.f, pf = fin ? pst[16 + cl] : 0.f, po = fin ? pst[32 + cl] : 0.f;
+  auto row_t = [&](int it) { return reverse ? 1 + it : T - it; };      // backward visits time against the forward order
+  auto warm = [&](int it) {
+    if (!live || it >= T) return;
+    const int t = row_t(it), tn = reverse ? t - 1 : t + 1, tp = reverse ? t + 1 : t - 1;
+    const float* y = buf + ((size_t)t * S + s) * ldb + cc;
+    prefetch_l2(y); prefetch_l2(y + C); prefetch_l2(y + 2 * C); prefetch_l2(y + 3 * C); prefetch_l2(y + 5 * C);
+    prefetch_l2(buf + ((size_t)tp * S + s) * ldb + 4 * C + cc);
+    prefetch_l2(buf + ((size_t)tn * S + s) * ldb + 2 * C + cc);
+    prefetch_l2(dbuf + ((size_t)t * S + s) * lddb + 6 * C + cc);
+  };
+  warm(0); warm(1);
+  issue_gather(0);
+
+  for (int it = 0; it < T; ++it) {
+    const int slot = it % TR;
+    const int t = row_t(it), tn = reverse ? t - 1 : t + 1, tp = reverse ? t + 1 : t - 1;
+    RECUR_TICK(k0);
+    complete_gather(slot);
+    RECUR_TICK(k1);
+    float yv[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // g, i, f, o, h at t ; c at the forward predecessor ; f at the successor
+    float od = 0.f;                                      // out_diff share of d_m (preloaded in the m columns of dbuf)
+    if (live) {
+      const float* y = buf + ((size_t)t * S + s) * ldb + cc;
+      yv[0] = y[0]; yv[1] = y[C]; yv[2] = y[2 * C]; yv[3] = y[3 * C]; yv[4] = y[5 * C];
+      yv[5] = buf[((size_t)tp * S + s) * ldb + 4 * C + cc];
+      yv[6] = buf[((size_t)tn * S + s) * ldb + 2 * C + cc];
+      od = dbuf[((size_t)t * S + s) * lddb + 6 * C + cc];
+    }
+    __syncthreads();                                     // every thread's share of the gather is in Psm
+    RECUR_TICK(k2);
+    float dg = 0.f, di = 0.f, df = 0.f, dout = 0.f, dc = 0.f, dh = 0.f, dm = 0.f;
+    if (fin) {
+      if (live) {
+        float sum = 0.f;
+        for (int p = 0; p < nblk; ++p) sum += Psm[p * 128 + cl * 8 + s_local];      // fixed order: deterministic
+        const int si = cl * 8 + s_local;
+        const float yg = yv[0], yi = yv[1], yf = yv[2], yo = yv[3], yh = yv[4], c_prev = yv[5], yf_next = yv[6];
+        dm = sum + od;
+        const float dc_n = st[si], di_n = st[128 + si], df_n = st[256 + si];
+        dh = dm * yo;  dh = (1.0f - yh * yh) * dh;                       // DiffTanh(y_h, d_h)
+        dout = dm * yh;  dout = yo * (1.0f - yo) * dout;                 // DiffSigmoid(y_o, d_o)
+        dc = dh + dc_n * yf_next + di_n * pi + df_n * pf + dout * po;
+        df = dc * c_prev;  df = yf * (1.0f - yf) * df;
+        di = dc * yg;      di = yi * (1.0f - yi) * di;
+        dg = dc * yi;      dg = (1.0f - yg * yg) * dg;
+        st[si] = dc; st[128 + si] = di; st[256 + si] = df;
+      }
+      const int bi = cl * 8 + s_local;                   // B operand of this step's contraction (zeros for padding streams)
+      Bsm[bi] = dg; Bsm[128 + bi] = di; Bsm[256 + bi] = df; Bsm[384 + bi] = dout;
+    } else {
+      __threadfence();                                   // the re-arm stores of the previous step (below) precede this step's publish
+    }
+    RECUR_TICK(k3);
+    __syncthreads();                                     // Bsm complete, re-arm fenced
+    RECUR_TICK(k4);
+    if (it + 1 < T) {
+      // ---- contraction of the own 64 dgifo rows against all C columns, published straight from the accumulators
+      const int nslot = (it + 1) % TR;
+      float* out = X + (size_t)nslot * slot_stride + chain_off + (size_t)cta.blk * 128;      // + consumer * nblk * 128
+      const int nm = (nblk - warp + 7) >> 3;             // m-tiles of this warp (warp-uniform)
+      if (nm >= 3) bwd_t_contract<3>(wT, Bsm, out, nblk, warp, lane);
+      else if (nm == 2) bwd_t_contract<2>(wT, Bsm, out, nblk, warp, lane);
+      else if (nm == 1) bwd_t_contract<1>(wT, Bsm, out, nblk, warp, lane);
+    }
+    RECUR_TICK(k5);
+    // ---- off the chain: re-arm the slot consumed at the top of this step, start the next gather, and only then write the
+    // bookkeeping of this step (they overlap the gather's round trip).  The re-arm and the prefetch address arithmetic put
+    // about one store-to-L2 latency between the publish and the gather, so its first round usually finds the data.
+    if (!fin) {
+      float* blk = own_block(slot);
+      const float4 sent = make_float4(__uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL));
+      for (int i = threadIdx.x - 128; i < items; i += NT - 128) *reinterpret_cast<float4*>(blk + i * 4) = sent;
+    }
+    if (it + 1 < T) {
+      warm(it + 2);
+#if ASLP_BWD_T_DELAY_NS > 0
+      __nanosleep(ASLP_BWD_T_DELAY_NS);
+#endif
+      issue_gather((it + 1) % TR);                       // Psm is free: its readers passed the barrier above
+    }
+    if (live) {
+      float* d = dbuf + ((size_t)t * S + s) * lddb + cc;
+      d[0] = dg; d[C] = di; d[2 * C] = df; d[3 * C] = dout; d[4 * C] = dc; d[5 * C] = dh; d[6 * C] = dm;
+    }
+    if (L.timing != nullptr && threadIdx.x == 0) {
+      const long long k6 = clock64();
+      tacc[0] += k1 - k0; tacc[1] += k2 - k1; tacc[2] += k3 - k2; tacc[3] += k4 - k3; tacc[4] += k5 - k4; tacc[6] += k6 - k5;
+    }
+  }
+  if (L.timing != nullptr && threadIdx.x == 0)
+    for (int q = 0; q < 12; ++q) L.timing[(size_t)blockIdx.x * 12 + q] = tacc[q];
+}
