@@ -372,7 +372,7 @@ def main():
         ach_tf = flop_per_launch / (bwd_avg_ms * 1e-3) / 1e12 if bwd_avg_ms > 0 else 0.0
         traffic = None
         try:                                       # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["lstm_bwd_mma_kernel"]["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["lstm_bwd_t_kernel"]["dram_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             pass
         step_ms = ms_dev / args.steps
@@ -385,7 +385,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {
-                "kernel": "lstm_bwd_mma_kernel (persistent BPTT recurrence of one layer, both directions, all T steps in one launch)",
+                "kernel": "lstm_bwd_t_kernel (persistent BPTT recurrence of one layer, both directions, all T steps in one launch)",
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak if hbm_peak else None,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,

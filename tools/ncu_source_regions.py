@@ -1,6 +1,6 @@
 """Summarise the SASS-level warp-state samples of one kernel in an `ncu --set full --import-source on` report: share of
 samples before / inside / after the tensor-core contraction (delimited by the first and last HMMA), top stall reasons per
-region and the instructions that collect the most samples.  Usage: ncu_source_regions.py report.ncu-rep > profiles/..."""
+region and the instructions that collect the most samples.  Usage: ncu_source_regions.py report.ncu-rep [kernel-name-substring] > profiles/..."""
 import csv
 import io
 import subprocess
@@ -9,10 +9,16 @@ import sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+# a report with several kernels lists them one after the other, each behind its own "Kernel Name" row; argv[2] picks one
+want = sys.argv[2] if len(sys.argv) > 2 else ""
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = next((i for i in starts if want in rows[i][1]), starts[0])
+end = next((i for i in starts if i > pick), len(rows))
+rows = rows[pick:end]
 print(rows[0][1])
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) == len(hdr)]
 num = lambda r, k: int(r[ix[k]] or 0)
 tot = sum(num(r, "# Samples") for r in data)
 hm = [i for i, r in enumerate(data) if "HMMA" in r[ix["Source"]]]
