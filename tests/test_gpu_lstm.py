@@ -149,3 +149,20 @@ def test_lstm_long_sequence_stays_in_tolerance():
     errs, berrs = run_case(300, 16, 64, 64, 2, seed=3)
     assert max(errs) < RTOL, errs
     assert max(berrs) < 5 * RTOL, berrs
+
+
+@pytest.mark.parametrize("T,S,C,ndirs", [
+    (300, 16, 64, 2),      # many times around the 4-slot partial-sum ring, 4 CTAs per chain
+    (40, 12, 320, 2),      # cfg3 cell count, second stream group only half full (8 + 4 streams)
+    (33, 40, 128, 1),      # five stream groups, one direction
+    (7, 8, 384, 1),        # 24 CTAs per chain: three MMA tiles in every warp; T + 2 slots barely cover the ring
+])
+@pytest.mark.parametrize("form", ["transposed", "gather-all"])
+def test_backward_recurrence_forms(T, S, C, ndirs, form, monkeypatch):
+    """The two tensor-core backward kernels (lstm_bwd_t_kernel: partial d_m sums exchanged through a re-armed ring;
+    lstm_bwd_mma_kernel: every CTA gathers all of dgifo) against the oracle on shapes the transposed form covers."""
+    monkeypatch.setenv("ASLP_LSTM_KERNEL", "mma")
+    monkeypatch.setenv("ASLP_LSTM_BWD_T", "1" if form == "transposed" else "0")
+    errs, berrs = run_case(T, S, C, 0, ndirs, seed=11)
+    assert max(errs) < RTOL, errs
+    assert max(berrs) < (5 * RTOL if T >= 300 else RTOL), berrs
