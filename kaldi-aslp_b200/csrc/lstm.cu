@@ -350,12 +350,18 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_kernel(Launch L) {
 #include "lstm_bwd_t.cuh"
 
 // ---------------------------------------------------------------- host side
-struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; bool presplit; bool transposed; };
+struct Plan { Launch L; size_t smem; size_t ws_bytes; bool mma; MmaChoice mc; bool presplit; bool transposed; int tn_ns; };
 
 size_t ws_per_dir(int T, int S, int C, int R, bool bwd) {
   const size_t SX = (size_t)(S + 3) / 4 * 4;
   const size_t da = bwd ? 4 * (size_t)C : (size_t)C;
-  return ((size_t)(T + 2) * da * SX + (size_t)(T + 2) * R * SX) * sizeof(float);
+  size_t bytes = ((size_t)(T + 2) * da * SX + (size_t)(T + 2) * R * SX) * sizeof(float);
+  // transposed backward form: ring of TR slots x [chains][C/16][C/16][16][streams per chain]; chains x streams <= 2S + 8
+  if (bwd && R == 0 && C % 16 == 0) {
+    const size_t ring = (size_t)4 * (C / 16) * (C / 16) * 16 * (2 * (size_t)S + 8) * sizeof(float);
+    if (ring > bytes) bytes = ring;
+  }
+  return bytes;
 }
 
 void fill_dir(DirDev& D, const aslp_lstm_dir_t& a) {
@@ -370,7 +376,7 @@ void fill_dir(DirDev& D, const aslp_lstm_dir_t& a) {
 // register budget (more groups = fewer CTAs per chain = more cells per CTA, but proportionally less exchange traffic)
 int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
-  P->mma = false; P->presplit = false; P->transposed = false;
+  P->mma = false; P->presplit = false; P->transposed = false; P->tn_ns = 0;
   L.ndirs = ndirs;
   const int C = dirs[0].C, S = dirs[0].S;
   for (int i = 0; i < ndirs; ++i)
@@ -411,15 +417,6 @@ int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, si
     P->presplit = bwd && !no_presplit && mma_presplit_shape(C, SG, SGP) && mma_pick_kernel(mc, true, true) != nullptr &&
                   mma_smem_floats(C, cb, SG, SGP, bwd, true) * sizeof(float) <= 224 * 1024;
     P->smem = mma_smem_floats(C, cb, SG, SGP, bwd, P->presplit) * sizeof(float);
-    // backward, transposed form (lstm_bwd_t.cuh): one 16-row MMA tile per CTA of the chain, 8 streams per chain
-    {
-      const char* tenv = std::getenv("ASLP_LSTM_BWD_T");
-      const bool t_off = tenv != nullptr && tenv[0] == '0';
-      P->transposed = bwd && !t_off && cb == 16 && C % 16 == 0 && nblk == C / 16 && nblk <= 24 && SG == 8 && SGP == 8 &&
-                      bwd_t_smem_floats(nblk) * sizeof(float) <= 224 * 1024 &&
-                      bwd_t_exchange_floats(nblk, pg) <= (size_t)(dirs[0].T + 2) * 4 * C * L.d[0].SX;
-      if (P->transposed) { P->presplit = false; P->smem = bwd_t_smem_floats(nblk) * sizeof(float); }
-    }
     P->ws_bytes = need_ws;
     P->mc = mc;
     P->mma = true;
@@ -428,9 +425,49 @@ int make_plan_mma(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, si
   return ASLP_STATUS_INVALID_VALUE;
 }
 
+// transposed backward form (lstm_bwd_t.cuh): 16 cells per CTA (one MMA tile per consumer), nblk = C / 16 CTAs per chain, the
+// largest number of stream groups (chains) per direction that still fits the chip; a chain carries 8, 16, 24 or 32 streams
+int make_plan_bwd_t(const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_t ws_bytes, Plan* P) {
+  Launch& L = P->L;
+  P->mma = false; P->presplit = false; P->transposed = false; P->tn_ns = 0;
+  const char* tenv = std::getenv("ASLP_LSTM_BWD_T");
+  if (tenv != nullptr && tenv[0] == '0') return ASLP_STATUS_INVALID_VALUE;
+  const int C = dirs[0].C, S = dirs[0].S, T = dirs[0].T;
+  for (int i = 0; i < ndirs; ++i)
+    if (dirs[i].R != 0 || dirs[i].C != C || dirs[i].S != S || dirs[i].T != T) return ASLP_STATUS_INVALID_VALUE;
+  if (C % 16 != 0 || C / 16 > 32) return ASLP_STATUS_INVALID_VALUE;
+  const int nblk = C / 16, sms = aslp_num_sms();
+  const size_t per_dir = ws_per_dir(T, S, C, 0, true);
+  for (int pg = (S + 7) / 8; pg >= 1; --pg) {
+    const int SW = (((S + pg - 1) / pg) + 7) / 8 * 8;
+    if (SW > 32) break;                                  // fewer groups only make the chains wider
+    if ((pg - 1) * SW >= S) continue;                    // would leave a chain without streams
+    if (ndirs * pg * nblk > sms) continue;
+    const int ns = SW / 8;
+    if (ns == 1 && nblk > 24) continue;                  // the 8-stream kernel has at most three m-tiles per warp
+    const size_t smem = (ns == 1 ? bwd_t_smem_floats(nblk) : bwd_tn_smem_floats(nblk, ns)) * sizeof(float);
+    if (smem > 224 * 1024) continue;
+    const size_t ring = (size_t)TR * pg * nblk * nblk * 16 * SW * sizeof(float);
+    if (ring > per_dir) continue;
+    if (ws == nullptr || ws_bytes < per_dir * ndirs) { aslp_set_last_error_msg("LSTM workspace too small", __FILE__, __LINE__); return ASLP_STATUS_INVALID_VALUE; }
+    L.ndirs = ndirs; L.nblk = nblk; L.pgroups = pg; L.SGP = SW; L.SG = SW; L.SP = SW;
+    for (int i = 0; i < ndirs; ++i) {
+      DirDev& D = L.d[i];
+      fill_dir(D, dirs[i]);
+      D.cb = 16; D.rb = 0;
+      D.xa = (float*)((char*)ws + per_dir * i);
+      D.xb = nullptr;
+    }
+    P->smem = smem; P->ws_bytes = per_dir * ndirs; P->transposed = true; P->tn_ns = ns; P->mma = true;
+    P->mc.mt = 1; P->mc.kt = 8;
+    return 0;
+  }
+  return ASLP_STATUS_INVALID_VALUE;
+}
+
 int make_plan(const aslp_lstm_dir_t* dirs, int ndirs, bool bwd, void* ws, size_t ws_bytes, Plan* P) {
   Launch& L = P->L;
-  P->mma = false; P->presplit = false; P->transposed = false;
+  P->mma = false; P->presplit = false; P->transposed = false; P->tn_ns = 0;
   L.pgroups = 1; L.SGP = 0;
   L.ndirs = ndirs;
   const int sms = aslp_num_sms();
@@ -527,7 +564,8 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
   // ASLP_LSTM_KERNEL=simt forces the SIMT contraction (tests run both forms); default: tensor-core form when it applies
   const char* force = std::getenv("ASLP_LSTM_KERNEL");
   const bool want_mma = !(force != nullptr && std::strcmp(force, "simt") == 0);
-  int rc = want_mma ? make_plan_mma(dirs, ndirs, bwd, ws, ws_bytes, &P) : ASLP_STATUS_INVALID_VALUE;
+  int rc = (want_mma && bwd) ? make_plan_bwd_t(dirs, ndirs, ws, ws_bytes, &P) : ASLP_STATUS_INVALID_VALUE;
+  if (rc != 0) rc = want_mma ? make_plan_mma(dirs, ndirs, bwd, ws, ws_bytes, &P) : ASLP_STATUS_INVALID_VALUE;
   if (rc != 0) rc = make_plan(dirs, ndirs, bwd, ws, ws_bytes, &P);
   if (rc != 0) return rc;
   if (force != nullptr && std::strcmp(force, "mma") == 0 && !P.mma) {
@@ -535,7 +573,7 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
     return ASLP_STATUS_INVALID_VALUE;
   }
   if (P.transposed) {
-    const size_t per_slot = bwd_t_exchange_floats(P.L.nblk, P.L.pgroups) / TR;
+    const size_t per_slot = (size_t)P.L.pgroups * P.L.nblk * P.L.nblk * 16 * P.L.SGP;
     for (int i = 0; i < P.L.ndirs; ++i) {
       xch_t_init_kernel<<<aslp_num_sms(), 256, 0, st>>>(P.L.d[i].xa, per_slot, per_slot * TR);
       ASLP_CHECK_LAUNCH();
@@ -544,7 +582,8 @@ int run(aslp_stream_t s, const aslp_lstm_dir_t* dirs, int ndirs, void* ws, size_
     rc = init_exchange(st, P, bwd);
     if (rc != 0) return rc;
   }
-  void* kfn = P.transposed ? (void*)lstm_bwd_t_kernel
+  void* kfn = P.transposed ? (P.tn_ns == 1 ? (void*)lstm_bwd_t_kernel : P.tn_ns == 2 ? (void*)lstm_bwd_tn_kernel<2>
+                                              : P.tn_ns == 3 ? (void*)lstm_bwd_tn_kernel<3> : (void*)lstm_bwd_tn_kernel<4>)
                            : (P.mma ? mma_pick_kernel(P.mc, bwd, P.presplit) : (bwd ? (void*)lstm_bwd_kernel : (void*)lstm_fwd_kernel));
   if (kfn == nullptr) { aslp_set_last_error_msg("no tensor-core recurrence kernel for this shape", __FILE__, __LINE__); return ASLP_STATUS_UNKNOWN_ERROR; }
   ASLP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));

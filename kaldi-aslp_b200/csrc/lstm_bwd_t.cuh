@@ -237,3 +237,199 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   if (L.timing != nullptr && threadIdx.x == 0)
     for (int q = 0; q < 12; ++q) L.timing[(size_t)blockIdx.x * 12 + q] = tacc[q];
 }
+
+// ---------------------------------------------------------------- wide form: 8*NS streams per chain (NS = 2, 3, 4)
+// Same algorithm for minibatches with many streams (BASELINE cfg2: 100 streams, 512 cells): a chain of 8 streams per CTA
+// set would need more CTAs than the chip has, so a chain carries NS n-tiles of 8 streams.  The A fragment of an
+// (m-tile, k-tile) is loaded once and used for NS x 3 MMAs; every thread finishes 16 * 8NS / 256 (cell, stream) items; the
+// re-arm + fence is done by all threads after the finish (the 4 idle warps of the 8-stream form do not exist here).
+inline size_t bwd_tn_smem_floats(int nblk, int ns) { return (size_t)nblk * 1024 + 64 * 40 + (size_t)nblk * 128 * ns + 384 * ns + 48; }
+
+template <int NM, int NS>
+__device__ __forceinline__ void bwd_tn_contract(const float4* wT, const float* Bsm, float* out, int nblk, int warp, int lane) {
+  constexpr int SW = 8 * NS;                             // streams per chain = row length of an exchange block
+  constexpr int BP = (NS == 2 || NS == 4) ? SW + 8 : SW; // Bsm row pitch: 4 k rows x 8 streams of a fragment load hit 32 different banks
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll 1
+  for (int mi = 0; mi < NM; ++mi) {
+    const int mt = warp + 8 * mi;
+    float hh[NS][4], lh[NS][4], hl[NS][4];
+#pragma unroll
+    for (int nt = 0; nt < NS; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { hh[nt][q] = 0.f; lh[nt][q] = 0.f; hl[nt][q] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+      const float4 w4 = wT[(mt * 8 + kt) * 32 + lane];
+      uint32_t ah[4], al[4];
+      split_tf32(w4.x, ah[0], al[0]); split_tf32(w4.y, ah[1], al[1]); split_tf32(w4.z, ah[2], al[2]); split_tf32(w4.w, ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < NS; ++nt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Bsm[(kt * 8 + tig) * BP + nt * 8 + g], bh0, bl0);
+        split_tf32(Bsm[(kt * 8 + tig + 4) * BP + nt * 8 + g], bh1, bl1);
+        mma_tf32(lh[nt], al, bh0, bh1);
+        mma_tf32(hl[nt], ah, bl0, bl1);
+        mma_tf32(hh[nt], ah, bh0, bh1);
+      }
+    }
+    float* dst = out + (size_t)mt * nblk * 16 * SW;      // block of consumer CTA mt: [producer][16][SW]
+#pragma unroll
+    for (int nt = 0; nt < NS; ++nt) {
+      st_pub2(dst + g * SW + nt * 8 + 2 * tig, (lh[nt][0] + hl[nt][0]) + hh[nt][0], (lh[nt][1] + hl[nt][1]) + hh[nt][1]);
+      st_pub2(dst + (g + 8) * SW + nt * 8 + 2 * tig, (lh[nt][2] + hl[nt][2]) + hh[nt][2], (lh[nt][3] + hl[nt][3]) + hh[nt][3]);
+    }
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
+  constexpr int SW = 8 * NS;                             // streams per chain
+  constexpr int BP = (NS == 2 || NS == 4) ? SW + 8 : SW; // Bsm row pitch (see bwd_tn_contract)
+  constexpr int ITEMS = 16 * SW;                         // (cell, stream) items of a CTA
+  constexpr int IPT = (ITEMS + NT - 1) / NT;             // items per thread (1 or 2)
+  extern __shared__ __align__(16) float smem[];
+  const MmaCta cta = mma_cta(L);
+  const DirDev& D = L.d[cta.dir];
+  const int T = D.T, S = D.S, C = D.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = L.nblk;
+  const int c0 = cta.blk * 16;
+  if (cta.sbeg >= S) return;
+
+  float4* wT = reinterpret_cast<float4*>(smem);          // [nblk][8][32] float4
+  float* Bsm = smem + (size_t)nblk * 1024;               // [64][BP]
+  float* Psm = Bsm + 64 * 40;                            // [nblk][16][SW]
+  float* st = Psm + (size_t)nblk * 16 * SW;              // [3][16][SW]
+  float* pst = st + 3 * ITEMS;                           // [3][16]
+
+  for (int i = threadIdx.x; i < nblk * 256; i += NT) {
+    const int mt = i >> 8, kt = (i >> 5) & 7, ln = i & 31, gg = ln >> 2, tt = ln & 3;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = mt * 16 + gg + (q & 1) * 8;
+      const int k = kt * 8 + tt + (q >> 1) * 4, gate = k >> 4, cl = k & 15;
+      v[q] = (c < C && c0 + cl < C) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + c] : 0.f;
+    }
+    wT[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  for (int i = threadIdx.x; i < 3 * ITEMS; i += NT) st[i] = 0.f;
+  for (int i = threadIdx.x; i < 64 * BP; i += NT) Bsm[i] = 0.f;
+  for (int i = threadIdx.x; i < 48; i += NT) {
+    const int which = i >> 4, cl = i & 15;
+    const float* p = which == 0 ? D.peep_i : (which == 1 ? D.peep_f : D.peep_o);
+    pst[i] = (c0 + cl < C) ? p[c0 + cl] : 0.f;
+  }
+  __syncthreads();
+
+  float* const X = D.xa;
+  const size_t blk_floats = (size_t)16 * SW;             // one (consumer, producer) block
+  const size_t slot_stride = (size_t)L.pgroups * nblk * nblk * blk_floats;
+  const size_t chain_off = (size_t)cta.pg * nblk * nblk * blk_floats;
+  auto own_block = [&](int slot) { return X + (size_t)slot * slot_stride + chain_off + (size_t)cta.blk * nblk * blk_floats; };
+  const int items4 = nblk * 4 * SW;                      // float4 items of the own block
+  auto issue_gather = [&](int slot) {
+    const float* src = own_block(slot);
+    for (int i = threadIdx.x; i < items4; i += NT) cp_async16(Psm + i * 4, src + i * 4);
+  };
+  auto complete_gather = [&](int slot) {
+    const float* src = own_block(slot);
+    unsigned rounds = 0;
+    for (;;) {
+      cp_async_wait_all();
+      bool again = false;
+      for (int i = threadIdx.x; i < items4; i += NT) {
+        const float4 v = *reinterpret_cast<const float4*>(Psm + i * 4);
+        if (sentinel_in(v)) { cp_async16(Psm + i * 4, src + i * 4); again = true; }
+      }
+      if (!again) break;
+      if (++rounds > POLL_LIMIT) __trap();
+    }
+  };
+
+  const int reverse = D.reverse, ldb = D.ldb, lddb = D.lddb;
+  float* const buf = D.buf;
+  float* const dbuf = D.dbuf;
+  auto row_t = [&](int it) { return reverse ? 1 + it : T - it; };
+  issue_gather(0);
+
+  for (int it = 0; it < T; ++it) {
+    const int slot = it % TR;
+    const int t = row_t(it), tn = reverse ? t - 1 : t + 1, tp = reverse ? t + 1 : t - 1;
+    complete_gather(slot);
+    float yv[IPT][7], od[IPT];
+    bool live[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      const int item = threadIdx.x + r * NT, cl = item / SW, sl = item - cl * SW, s = cta.sbeg + sl;
+      live[r] = item < ITEMS && s < cta.send && c0 + cl < C;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) yv[r][q] = 0.f;
+      od[r] = 0.f;
+      if (live[r]) {
+        const int cc = c0 + cl;
+        const float* y = buf + ((size_t)t * S + s) * ldb + cc;
+        yv[r][0] = y[0]; yv[r][1] = y[C]; yv[r][2] = y[2 * C]; yv[r][3] = y[3 * C]; yv[r][4] = y[5 * C];
+        yv[r][5] = buf[((size_t)tp * S + s) * ldb + 4 * C + cc];
+        yv[r][6] = buf[((size_t)tn * S + s) * ldb + 2 * C + cc];
+        od[r] = dbuf[((size_t)t * S + s) * lddb + 6 * C + cc];
+      }
+    }
+    __syncthreads();                                     // every thread's share of the gather is in Psm
+    float dv[IPT][7];
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      const int item = threadIdx.x + r * NT;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) dv[r][q] = 0.f;
+      if (item < ITEMS) {
+        const int cl = item / SW;
+        if (live[r]) {
+          float sum = 0.f;
+          for (int p = 0; p < nblk; ++p) sum += Psm[(size_t)p * ITEMS + item];      // fixed order: deterministic
+          const float pi = pst[cl], pf = pst[16 + cl], po = pst[32 + cl];
+          const float yg = yv[r][0], yi = yv[r][1], yf = yv[r][2], yo = yv[r][3], yh = yv[r][4], c_prev = yv[r][5], yf_next = yv[r][6];
+          const float dm = sum + od[r];
+          const float dc_n = st[item], di_n = st[ITEMS + item], df_n = st[2 * ITEMS + item];
+          float dh = dm * yo;  dh = (1.0f - yh * yh) * dh;
+          float dout = dm * yh;  dout = yo * (1.0f - yo) * dout;
+          const float dc = dh + dc_n * yf_next + di_n * pi + df_n * pf + dout * po;
+          float df = dc * c_prev;  df = yf * (1.0f - yf) * df;
+          float di = dc * yg;      di = yi * (1.0f - yi) * di;
+          float dg = dc * yi;      dg = (1.0f - yg * yg) * dg;
+          st[item] = dc; st[ITEMS + item] = di; st[2 * ITEMS + item] = df;
+          dv[r][0] = dg; dv[r][1] = di; dv[r][2] = df; dv[r][3] = dout; dv[r][4] = dc; dv[r][5] = dh; dv[r][6] = dm;
+        }
+        const int sl = item - cl * SW;                   // B operand rows: gate * 16 + cell
+        Bsm[(0 * 16 + cl) * BP + sl] = dv[r][0]; Bsm[(1 * 16 + cl) * BP + sl] = dv[r][1];
+        Bsm[(2 * 16 + cl) * BP + sl] = dv[r][2]; Bsm[(3 * 16 + cl) * BP + sl] = dv[r][3];
+      }
+    }
+    {                                                    // re-arm the slot just consumed; visible before the next publish
+      float* blk = own_block(slot);
+      const float4 sent = make_float4(__uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL));
+      for (int i = threadIdx.x; i < items4; i += NT) *reinterpret_cast<float4*>(blk + i * 4) = sent;
+      __threadfence();
+    }
+    __syncthreads();                                     // Bsm complete, re-arm fenced
+    if (it + 1 < T) {
+      const int nslot = (it + 1) % TR;
+      float* out = X + (size_t)nslot * slot_stride + chain_off + (size_t)cta.blk * blk_floats;   // + consumer * nblk * blk_floats
+      const int nm = (nblk - warp + 7) >> 3;             // m-tiles of this warp (warp-uniform)
+      if (nm >= 4) bwd_tn_contract<4, NS>(wT, Bsm, out, nblk, warp, lane);
+      else if (nm == 3) bwd_tn_contract<3, NS>(wT, Bsm, out, nblk, warp, lane);
+      else if (nm == 2) bwd_tn_contract<2, NS>(wT, Bsm, out, nblk, warp, lane);
+      else if (nm == 1) bwd_tn_contract<1, NS>(wT, Bsm, out, nblk, warp, lane);
+      issue_gather(nslot);
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      if (live[r]) {
+        const int item = threadIdx.x + r * NT, cl = item / SW, sl = item - cl * SW;
+        float* d = dbuf + ((size_t)t * S + cta.sbeg + sl) * lddb + c0 + cl;
+        d[0] = dv[r][0]; d[C] = dv[r][1]; d[2 * C] = dv[r][2]; d[3 * C] = dv[r][3]; d[4 * C] = dv[r][4]; d[5 * C] = dv[r][5]; d[6 * C] = dv[r][6];
+      }
+    }
+  }
+}

@@ -1,0 +1,62 @@
+"""Device-resident training-step throughput of the BASELINE configs that bench.py does not time (cfg1 DNN, cfg2 LSTM, cfg4 FSMN;
+cfg3 is the bench line): one minibatch = Propagate + Xent + Backpropagate with all updates through the handle API, random-init
+weights of the named architecture, synthetic features, CUDA events, median of 7 after 3 warm-ups.  Informative only."""
+import ctypes
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+sys.path.insert(0, __file__.rsplit("/tools/", 1)[0])
+from kaldi_aslp_b200 import nnet as NN  # noqa: E402
+
+CFG = {
+    "cfg1 DNN 440-4x1024-1500, minibatch 256": dict(
+        proto="".join(["<AffineTransform> <InputDim> %d <OutputDim> 1024 <BiasMean> -2.0 <BiasRange> 4.0 <ParamStddev> 0.04\n<Sigmoid> <InputDim> 1024 <OutputDim> 1024\n" % d
+                       for d in (440, 1024, 1024, 1024)]) +
+        "<AffineTransform> <InputDim> 1024 <OutputDim> 1500 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.04\n<Softmax> <InputDim> 1500 <OutputDim> 1500\n",
+        rows=256, dim=440, K=1500, streams=None),
+    "cfg2 2x Lstm(512) + Affine 512->1500, T=20 x S=100": dict(
+        proto="<Lstm> <InputDim> 40 <OutputDim> 512 <ClipGradient> 5 <ParamScale> 0.01\n<Lstm> <InputDim> 512 <OutputDim> 512 <ClipGradient> 5 <ParamScale> 0.01\n"
+              "<AffineTransform> <InputDim> 512 <OutputDim> 1500 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.04\n<Softmax> <InputDim> 1500 <OutputDim> 1500\n",
+        rows=2000, dim=40, K=1500, streams=100),
+    "cfg4 FSMN 6 x (Affine 1024, ReLU, Affine 512, CompactFsmn 20/20), one 1000-frame utterance": dict(
+        proto="".join(["<AffineTransform> <InputDim> %d <OutputDim> 1024 <BiasMean> 0 <BiasRange> 0.1 <ParamStddev> 0.04\n<ReLU> <InputDim> 1024 <OutputDim> 1024\n"
+                       "<AffineTransform> <InputDim> 1024 <OutputDim> 512 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.04\n"
+                       "<CompactFsmn> <InputDim> 512 <OutputDim> 512 <PastContext> 20 <FutureContext> 20\n" % d for d in (440, 512, 512, 512, 512, 512)]) +
+        "<AffineTransform> <InputDim> 512 <OutputDim> 1500 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.04\n<Softmax> <InputDim> 1500 <OutputDim> 1500\n",
+        rows=1000, dim=440, K=1500, streams=None),
+}
+
+if __name__ == "__main__":
+    NN.select_device(0)
+    for name, c in CFG.items():
+        with tempfile.TemporaryDirectory() as td:
+            p = os.path.join(td, "proto.txt")
+            open(p, "w").write("<NnetProto>\n" + c["proto"] + "</NnetProto>\n")
+            NN.srand(777)
+            net = NN.Nnet.init(p)
+        net.set_train_options(learn_rate=1e-4, momentum=0.9)
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal((c["rows"], c["dim"])).astype(np.float32)
+        t = rng.integers(0, c["K"], size=c["rows"]).astype(np.int32)
+        if c["streams"]:
+            net.reset_streams([1] * c["streams"])
+        dev, _ = NN.upload(x)
+        xent = NN.Xent()
+
+        def step():
+            NN.train_step_xent(net, xent, dev, t, on_device=True, rows=c["rows"], cols=c["dim"])
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            NN.device_sync(); a.record(); step(); NN.device_sync(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        print(json.dumps({"config": name, "ms_per_minibatch": round(ms, 3), "frames_per_s": round(c["rows"] / ms * 1e3), "params": net.num_params}), flush=True)
