@@ -38,10 +38,72 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 #ifndef ASLP_ISSUE_EARLY
 #define ASLP_ISSUE_EARLY 0
 #endif
+#ifndef ASLP_FWD_FP16X3
+#define ASLP_FWD_FP16X3 1      // 1: forward contraction as fp16 hi/lo split (3 x m16n8k16 per 16 k); 0: 3xTF32 (6 x m16n8k8)
+#endif
 #ifndef ASLP_WARM_AHEAD
 #define ASLP_WARM_AHEAD 2      // items ahead the non-recurrent operands are pulled into L2 (0: no prefetch)
 #endif
 #if ASLP_FWD_ACC3
+// ---- fp16 two-term split (forward contraction, ASLP_FWD_FP16X3): x = h1 + h2 + O(2^-22 |x|) with h1, h2 fp16; the products
+// h*h are exact in the fp32 accumulator, so w1*m1 + w2*m1 + w1*m2 has the accuracy of 3xTF32 at HALF the MMA count (the
+// legacy m16n8k16.f16 issues at the same 8 cycles as m16n8k8.tf32, tools/micro/mma_rate.cu).  Only for BOUNDED operands:
+// the recurrent input m = o * tanh(c) lies in (-1, 1) and weights are O(1), so fp16 range is no issue and the absolute
+// representation error is <= 3e-8 (fp16 subnormal step / 2); the backward operand dgifo is unbounded below and stays tf32.
+#include <cuda_fp16.h>
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {      // two values -> packed halves (x0 low)
+  const __half a0 = __float2half_rn(x0), a1 = __float2half_rn(x1);
+  const __half b0 = __float2half_rn(x0 - __half2float(a0)), b1 = __float2half_rn(x1 - __half2float(a1));
+  const __half2 h = __halves2half2(a0, a1), l = __halves2half2(b0, b1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// part_w = Wslice * X with pre-split fp16 weight fragments wh / wl [MT_][KH_][4] (a0: row g, k 2tig..+1; a1: row g+8;
+// a2: row g, k 2tig+8..+9; a3: row g+8) and the m values split on the fly; KH_ 16-wide k tiles starting at row kbase
+template <int MT_, int KH_>
+__device__ __forceinline__ void mma_contract_h(const uint32_t (&wh)[MT_][KH_][4], const uint32_t (&wl)[MT_][KH_][4], const float* xT, int SP,
+                                               int kbase, int Kdim, int ntiles, float* part_w, int lane) {
+  constexpr int NPP = MT_ * 16 + 4;
+  const int g = lane >> 2, tig = lane & 3;
+  for (int nt = 0; nt < ntiles; ++nt) {
+    float acc[MT_][3][4];
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+      for (int h = 0; h < 3; ++h) { acc[mt][h][0] = acc[mt][h][1] = acc[mt][h][2] = acc[mt][h][3] = 0.f; }
+#pragma unroll
+    for (int kh = 0; kh < KH_; ++kh) {
+      // rows past the warp's share carry zero weights; clamp them onto valid (finite) rows
+      const int k0 = kbase + kh * 16 + 2 * tig;
+      const float* col = xT + nt * 8 + g;
+      const float x00 = col[(size_t)min(k0, Kdim - 1) * SP], x01 = col[(size_t)min(k0 + 1, Kdim - 1) * SP];
+      const float x10 = col[(size_t)min(k0 + 8, Kdim - 1) * SP], x11 = col[(size_t)min(k0 + 9, Kdim - 1) * SP];
+      uint32_t bh0, bl0, bh1, bl1;
+      split_h2(x00, x01, bh0, bl0);
+      split_h2(x10, x11, bh1, bl1);
+#pragma unroll
+      for (int mt = 0; mt < MT_; ++mt) {
+        mma_f16(acc[mt][1], wl[mt][kh], bh0, bh1);
+        mma_f16(acc[mt][2], wh[mt][kh], bl0, bl1);
+        mma_f16(acc[mt][0], wh[mt][kh], bh0, bh1);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt) {
+      float c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] = (acc[mt][1][q] + acc[mt][2][q]) + acc[mt][0][q];      // small terms first
+      float* p0 = part_w + (size_t)(nt * 8 + 2 * tig) * NPP + mt * 16 + g;
+      p0[0] = c[0]; p0[NPP] = c[1]; p0[8] = c[2]; p0[NPP + 8] = c[3];
+    }
+  }
+}
+
 template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 2 ? 1 : 2; static constexpr int SETS = 3; };
 #else
 template <int MT_> struct MmaAcc { static constexpr int K = MT_ >= 4 ? 1 : (MT_ >= 2 ? 2 : 4); static constexpr int SETS = 2; };
@@ -251,6 +313,28 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
   // ---- one-time: weight slice -> A fragments (row n of the slice = cell n/4, gate n%4)
   const int ktiles = K >> 3, ktw = (ktiles + NW - 1) / NW;
   const int kt0 = warp * ktw, nkt = max(0, min(ktw, ktiles - kt0));
+#if ASLP_FWD_FP16X3
+  constexpr int KH = (KT_ + 1) / 2;                      // 16-wide k tiles per warp
+  uint32_t wh[MT_][KH][4], wl[MT_][KH][4];
+  {
+    const int g = lane >> 2, tig = lane & 3;
+    const int kend = (kt0 + nkt) * 8;                     // end of this warp's k range
+#pragma unroll
+    for (int mt = 0; mt < MT_; ++mt)
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = mt * 16 + g + (q & 1) * 8, cl = n >> 2, gate = n & 3;
+          const int k = kt0 * 8 + kh * 16 + 2 * tig + (q >> 1) * 8;
+          const float* wrow = D.w_r + (size_t)(gate * C + c0 + cl) * D.ldwr;
+          const float w0 = (cl < nc && k < kend && k < K) ? wrow[k] : 0.f;
+          const float w1 = (cl < nc && k + 1 < kend && k + 1 < K) ? wrow[k + 1] : 0.f;
+          if (fabsf(w0) > 32768.f || fabsf(w1) > 32768.f) __trap();     // outside the fp16 split's range: an error, never a silent inf
+          split_h2(w0, w1, wh[mt][kh][q], wl[mt][kh][q]);
+        }
+  }
+#else
   float wa[MT_][KT_][4];
   {
     const int g = lane >> 2, tig = lane & 3;
@@ -265,6 +349,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
           wa[mt][kt][q] = (kt < nkt && cl < nc) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + k] : 0.f;
         }
   }
+#endif
   const int slot0 = D.reverse ? T + 1 : 0;
   for (int i = threadIdx.x; i < D.cb * L.SGP; i += NT) {
     const int cl = i / L.SGP, s = cta.sbeg + (i - cl * L.SGP);
@@ -332,7 +417,11 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
     RECUR_TICK(k1);
     __syncthreads();
     RECUR_TICK(k2);
+#if ASLP_FWD_FP16X3
+    mma_contract_h<MT_, KH>(wh, wl, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
+#else
     mma_contract<MT_, KT_>(wa, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
+#endif
     RECUR_TICK(k3);
     __syncthreads();
     RECUR_TICK(k4);
