@@ -20,13 +20,16 @@ constexpr int TR = 4;                    // ring slots of the partial-sum exchan
 #ifndef ASLP_BWD_T_DELAY_NS
 #define ASLP_BWD_T_DELAY_NS 0
 #endif
+#ifndef ASLP_BWD_T_FP16
+#define ASLP_BWD_T_FP16 1        // 1: fp16 two-term split with per-stream power-of-two scaling of dgifo (8-stream form); 0: 3xTF32
+#endif
 
 __device__ __forceinline__ void st_pub2(float* p, float a, float b) {
   asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory");
 }
 
 // shared memory: wT [nblk][8][32] float4 | Bsm [64][8] | Psm [nblk][16][8] | st [3][16][8] | pst [3][16]
-inline size_t bwd_t_smem_floats(int nblk) { return (size_t)nblk * 1024 + 512 + (size_t)nblk * 128 + 384 + 48; }
+inline size_t bwd_t_smem_floats(int nblk) { return (size_t)nblk * 1024 + 512 + (size_t)nblk * 128 + 384 + 48 + 32; }   // + column maxima [4][8]
 // exchange floats per direction: [TR][pgroups][consumer][producer][16][8]
 inline size_t bwd_t_exchange_floats(int nblk, int pgroups) { return (size_t)TR * pgroups * nblk * nblk * 128; }
 
@@ -70,6 +73,57 @@ __device__ __forceinline__ void bwd_t_contract(const float4* wT, const float* Bs
   }
 }
 
+// fp16 form of the contraction above.  dgifo has no lower bound, so every stream column of the B operand is first scaled
+// by a power of two that brings its largest magnitude (over the CTA's 64 rows; maxima left in cmx[4][8] by the finishing
+// warps) to [2^14, 2^15): exact, no fp16 overflow, and an element keeps >= 22 significant bits unless it is more than 2^24
+// below its column's maximum, where its contribution to the partial sum is below fp32 resolution of the dominant terms
+// anyway.  The accumulators are scaled back per stream column (exact) before they are published.  Half the MMAs of 3xTF32.
+__device__ __forceinline__ float pow2_scale(float mx, float& inv) {
+  const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu);
+  if (e == 0 || e == 255) { inv = 1.0f; return 1.0f; }     // zero / denormal column (or inf: nothing to save)
+  int se = 127 + 14 - (e - 127);
+  se = se < 1 ? 1 : (se > 253 ? 253 : se);
+  inv = __uint_as_float((unsigned)(254 - se) << 23);
+  return __uint_as_float((unsigned)se << 23);
+}
+template <int NM>
+__device__ __forceinline__ void bwd_t_contract_h(const uint4* wh, const uint4* wl, const float* Bsm, const float* cmx, float* out, int nblk,
+                                                 int warp, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+  auto colmax = [&](int s) { return fmaxf(fmaxf(cmx[s], cmx[8 + s]), fmaxf(cmx[16 + s], cmx[24 + s])); };
+  float inv_g, inv0, inv1;
+  const float sc_g = pow2_scale(colmax(g), inv_g);
+  pow2_scale(colmax(2 * tig), inv0);
+  pow2_scale(colmax(2 * tig + 1), inv1);
+  float hh[NM][4], lh[NM][4], hl[NM][4];
+#pragma unroll
+  for (int mi = 0; mi < NM; ++mi)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { hh[mi][q] = 0.f; lh[mi][q] = 0.f; hl[mi][q] = 0.f; }
+#pragma unroll
+  for (int kh = 0; kh < 4; ++kh) {
+    const float* col = Bsm + (kh * 16 + 2 * tig) * 8 + g;
+    uint32_t bh0, bl0, bh1, bl1;
+    split_h2(col[0] * sc_g, col[8] * sc_g, bh0, bl0);            // k = 2tig, 2tig+1
+    split_h2(col[64] * sc_g, col[72] * sc_g, bh1, bl1);          // k = 2tig+8, 2tig+9
+#pragma unroll
+    for (int mi = 0; mi < NM; ++mi) {
+      const uint4 h4 = wh[((warp + 8 * mi) * 4 + kh) * 32 + lane], l4 = wl[((warp + 8 * mi) * 4 + kh) * 32 + lane];
+      const uint32_t ah[4] = {h4.x, h4.y, h4.z, h4.w}, al[4] = {l4.x, l4.y, l4.z, l4.w};
+      mma_f16(lh[mi], al, bh0, bh1);
+      mma_f16(hl[mi], ah, bl0, bl1);
+      mma_f16(hh[mi], ah, bh0, bh1);
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < NM; ++mi) {
+    float* dst = out + (size_t)(warp + 8 * mi) * nblk * 128;
+    st_pub2(dst + g * 8 + 2 * tig, ((lh[mi][0] + hl[mi][0]) + hh[mi][0]) * inv0, ((lh[mi][1] + hl[mi][1]) + hh[mi][1]) * inv1);
+    st_pub2(dst + (g + 8) * 8 + 2 * tig, ((lh[mi][2] + hl[mi][2]) + hh[mi][2]) * inv0, ((lh[mi][3] + hl[mi][3]) + hh[mi][3]) * inv1);
+  }
+  (void)inv_g;
+}
+
 __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   extern __shared__ __align__(16) float smem[];
   const MmaCta cta = mma_cta(L);
@@ -85,9 +139,36 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   float* Psm = Bsm + 512;                                // gathered partial sums [producer][cell][stream]
   float* st = Psm + (size_t)nblk * 128;                  // d_c, d_i, d_f of the successor step [3][cell][stream]
   float* pst = st + 384;                                 // peepholes [3][cell]
+  float* cmx = pst + 48;                                 // per-warp column maxima of |dgifo| [4][8] (fp16 form)
 
   // ---- one-time: A fragments (a0: row g, k tig; a1: row g+8, k tig; a2: row g, k tig+4; a3: row g+8, k tig+4);
   // row = cell column c of W' (m-tile mt covers cells mt*16 .. +15), k = gate*16 + own cell
+#if ASLP_BWD_T_FP16
+  // m16n8k16 fragments, pre-split into fp16 halves: hi [nblk][4][32] uint4, then lo (same bytes as the tf32 layout);
+  // a0: row g, k 2tig..+1; a1: row g+8; a2: row g, k 2tig+8..+9; a3: row g+8
+  uint4* wTh = reinterpret_cast<uint4*>(smem);
+  uint4* wTl = wTh + (size_t)nblk * 128;
+  (void)wT;
+  for (int i = threadIdx.x; i < nblk * 128; i += NT) {
+    const int mt = i >> 7, kh = (i >> 5) & 3, ln = i & 31, gg = ln >> 2, tt = ln & 3;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = mt * 16 + gg + (q & 1) * 8;
+      float w[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = kh * 16 + 2 * tt + (q >> 1) * 8 + u, gate = k >> 4, cl = k & 15;
+        w[u] = (c < C && c0 + cl < C) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + c] : 0.f;
+        if (fabsf(w[u]) > 32768.f) __trap();             // outside the fp16 split's range: an error, never a silent inf
+      }
+      split_h2(w[0], w[1], hi[q], lo[q]);
+    }
+    wTh[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    wTl[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  for (int i = threadIdx.x; i < 32; i += NT) cmx[i] = 0.f;
+#else
   for (int i = threadIdx.x; i < nblk * 256; i += NT) {
     const int mt = i >> 8, kt = (i >> 5) & 7, ln = i & 31, gg = ln >> 2, tt = ln & 3;
     float v[4];
@@ -99,6 +180,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
     }
     wT[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
+#endif
   for (int i = threadIdx.x; i < 384; i += NT) st[i] = 0.f;
   for (int i = threadIdx.x; i < 512; i += NT) Bsm[i] = 0.f;
   for (int i = threadIdx.x; i < 48; i += NT) {
@@ -194,6 +276,13 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
       }
       const int bi = cl * 8 + s_local;                   // B operand of this step's contraction (zeros for padding streams)
       Bsm[bi] = dg; Bsm[128 + bi] = di; Bsm[256 + bi] = df; Bsm[384 + bi] = dout;
+#if ASLP_BWD_T_FP16
+      // largest |dgifo| of every stream column over this warp's four cells (lanes with equal lane & 7)
+      float m4 = fmaxf(fmaxf(fabsf(dg), fabsf(di)), fmaxf(fabsf(df), fabsf(dout)));
+      m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, 8));
+      m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, 16));
+      if (lane < 8) cmx[warp * 8 + lane] = m4;
+#endif
     } else {
       __threadfence();                                   // the re-arm stores of the previous step (below) precede this step's publish
     }
@@ -205,9 +294,15 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
       const int nslot = (it + 1) % TR;
       float* out = X + (size_t)nslot * slot_stride + chain_off + (size_t)cta.blk * 128;      // + consumer * nblk * 128
       const int nm = (nblk - warp + 7) >> 3;             // m-tiles of this warp (warp-uniform)
+#if ASLP_BWD_T_FP16
+      if (nm >= 3) bwd_t_contract_h<3>(wTh, wTl, Bsm, cmx, out, nblk, warp, lane);
+      else if (nm == 2) bwd_t_contract_h<2>(wTh, wTl, Bsm, cmx, out, nblk, warp, lane);
+      else if (nm == 1) bwd_t_contract_h<1>(wTh, wTl, Bsm, cmx, out, nblk, warp, lane);
+#else
       if (nm >= 3) bwd_t_contract<3>(wT, Bsm, out, nblk, warp, lane);
       else if (nm == 2) bwd_t_contract<2>(wT, Bsm, out, nblk, warp, lane);
       else if (nm == 1) bwd_t_contract<1>(wT, Bsm, out, nblk, warp, lane);
+#endif
     }
     RECUR_TICK(k5);
     // ---- off the chain: re-arm the slot consumed at the top of this step, start the next gather, and only then write the

@@ -1,0 +1,10 @@
+#!/bin/bash
+# A/B of the transposed backward's contraction form (product = fp16 scaled split, variant bwdtf32 = 3xTF32) plus the
+# LSTM / golden / full-size parity tests on the product library.
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+for i in 1 2; do
+  python tools/ab_probe.py "product"
+  ASLP_B200_CUDA_LIB=$PWD/kaldi-aslp_b200/libaslp_b200_bwdtf32.so python tools/ab_probe.py "bwdtf32"
+done 2>&1 | grep variant | tee gpurun_out/ab_bwd.jsonl
+timeout 900 python -m pytest tests/test_gpu_lstm.py tests/test_gpu_nnet_golden.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/ab_bwd_tests.log
