@@ -379,7 +379,7 @@ def main():
         line = {
             "metric": METRIC, "value": frames / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else ("f32 (chunk GEMMs and backward recurrence: 3xTF32 split; forward recurrence: fp16 hi/lo split; all fp32-grade, fp32 accumulate)" if args.precision == "3xtf32" else "f32 (GEMMs: TF32)"),
+            "dtype": "f32" if args.precision == "fp32" else ("f32 (chunk GEMMs: 3xTF32 split; recurrences: fp16 hi/lo split, backward operand scaled per stream by an exact power of two; all fp32-grade, fp32 accumulate)" if args.precision == "3xtf32" else "f32 (GEMMs: TF32)"),
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(feats.nbytes), "d2h_bytes_per_step": int(4 * S)},
             "gpu_launches": int(launches),

@@ -78,6 +78,30 @@ __device__ __forceinline__ void bwd_t_contract(const float4* wT, const float* Bs
 // warps) to [2^14, 2^15): exact, no fp16 overflow, and an element keeps >= 22 significant bits unless it is more than 2^24
 // below its column's maximum, where its contribution to the partial sum is below fp32 resolution of the dominant terms
 // anyway.  The accumulators are scaled back per stream column (exact) before they are published.  Half the MMAs of 3xTF32.
+// A fragments of W'[own 64 rows][all C columns] for m16n8k16, pre-split into fp16 halves: hi [nblk][4][32] uint4, then lo
+// (same bytes as the tf32 layout); a0: row g, k 2tig..+1; a1: row g+8; a2: row g, k 2tig+8..+9; a3: row g+8;
+// row = cell column c of W' (m-tile mt covers cells mt*16 .. +15), k = gate*16 + own cell
+__device__ __forceinline__ void bwd_t_fill_h(const DirDev& D, uint4* wTh, uint4* wTl, int nblk, int c0) {
+  const int C = D.C;
+  for (int i = threadIdx.x; i < nblk * 128; i += NT) {
+    const int mt = i >> 7, kh = (i >> 5) & 3, ln = i & 31, gg = ln >> 2, tt = ln & 3;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = mt * 16 + gg + (q & 1) * 8;
+      float w[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = kh * 16 + 2 * tt + (q >> 1) * 8 + u, gate = k >> 4, cl = k & 15;
+        w[u] = (c < C && c0 + cl < C) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + c] : 0.f;
+        if (fabsf(w[u]) > 32768.f) __trap();             // outside the fp16 split's range: an error, never a silent inf
+      }
+      split_h2(w[0], w[1], hi[q], lo[q]);
+    }
+    wTh[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    wTl[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
 __device__ __forceinline__ float pow2_scale(float mx, float& inv) {
   const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu);
   if (e == 0 || e == 255) { inv = 1.0f; return 1.0f; }     // zero / denormal column (or inf: nothing to save)
@@ -129,12 +153,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   const MmaCta cta = mma_cta(L);
   const DirDev& D = L.d[cta.dir];
   const int T = D.T, S = D.S, C = D.C;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = L.nblk;                               // == C / 16: m-tile index == consumer CTA index
   const int c0 = cta.blk * 16;
   if (cta.sbeg >= S) return;                             // a chain without streams: all of its CTAs leave together
 
+#if !ASLP_BWD_T_FP16
   float4* wT = reinterpret_cast<float4*>(smem);          // A fragments of W'[own 64 rows][all C columns], transposed
+#endif
   float* Bsm = smem + (size_t)nblk * 1024;               // dgifo of the step just finished: [gate*16 + cell][stream]
   float* Psm = Bsm + 512;                                // gathered partial sums [producer][cell][stream]
   float* st = Psm + (size_t)nblk * 128;                  // d_c, d_i, d_f of the successor step [3][cell][stream]
@@ -144,29 +170,9 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   // ---- one-time: A fragments (a0: row g, k tig; a1: row g+8, k tig; a2: row g, k tig+4; a3: row g+8, k tig+4);
   // row = cell column c of W' (m-tile mt covers cells mt*16 .. +15), k = gate*16 + own cell
 #if ASLP_BWD_T_FP16
-  // m16n8k16 fragments, pre-split into fp16 halves: hi [nblk][4][32] uint4, then lo (same bytes as the tf32 layout);
-  // a0: row g, k 2tig..+1; a1: row g+8; a2: row g, k 2tig+8..+9; a3: row g+8
   uint4* wTh = reinterpret_cast<uint4*>(smem);
   uint4* wTl = wTh + (size_t)nblk * 128;
-  (void)wT;
-  for (int i = threadIdx.x; i < nblk * 128; i += NT) {
-    const int mt = i >> 7, kh = (i >> 5) & 3, ln = i & 31, gg = ln >> 2, tt = ln & 3;
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = mt * 16 + gg + (q & 1) * 8;
-      float w[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int k = kh * 16 + 2 * tt + (q >> 1) * 8 + u, gate = k >> 4, cl = k & 15;
-        w[u] = (c < C && c0 + cl < C) ? D.w_r[(size_t)(gate * C + c0 + cl) * D.ldwr + c] : 0.f;
-        if (fabsf(w[u]) > 32768.f) __trap();             // outside the fp16 split's range: an error, never a silent inf
-      }
-      split_h2(w[0], w[1], hi[q], lo[q]);
-    }
-    wTh[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    wTl[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
+  bwd_t_fill_h(D, wTh, wTl, nblk, c0);
   for (int i = threadIdx.x; i < 32; i += NT) cmx[i] = 0.f;
 #else
   for (int i = threadIdx.x; i < nblk * 256; i += NT) {
@@ -338,12 +344,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
 // set would need more CTAs than the chip has, so a chain carries NS n-tiles of 8 streams.  The A fragment of an
 // (m-tile, k-tile) is loaded once and used for NS x 3 MMAs; every thread finishes 16 * 8NS / 256 (cell, stream) items; the
 // re-arm + fence is done by all threads after the finish (the 4 idle warps of the 8-stream form do not exist here).
-inline size_t bwd_tn_smem_floats(int nblk, int ns) { return (size_t)nblk * 1024 + 64 * 40 + (size_t)nblk * 128 * ns + 384 * ns + 48; }
+inline size_t bwd_tn_smem_floats(int nblk, int ns) { return (size_t)nblk * 1024 + 64 * 40 + (size_t)nblk * 128 * ns + 384 * ns + 48 + 64; }   // + column maxima [2][32]
+// Bsm row pitch: the rows one fragment load touches (tig, or 2 tig for the k16 shape) x 8 streams hit 32 different banks
+template <int NS> struct BwdTnPitch { static constexpr int value = ASLP_BWD_T_FP16 ? 8 * NS + 4 : ((NS == 2 || NS == 4) ? 8 * NS + 8 : 8 * NS); };
 
 template <int NM, int NS>
 __device__ __forceinline__ void bwd_tn_contract(const float4* wT, const float* Bsm, float* out, int nblk, int warp, int lane) {
   constexpr int SW = 8 * NS;                             // streams per chain = row length of an exchange block
-  constexpr int BP = (NS == 2 || NS == 4) ? SW + 8 : SW; // Bsm row pitch: 4 k rows x 8 streams of a fragment load hit 32 different banks
+  constexpr int BP = BwdTnPitch<NS>::value;
   const int g = lane >> 2, tig = lane & 3;
 #pragma unroll 1
   for (int mi = 0; mi < NM; ++mi) {
@@ -377,10 +385,61 @@ __device__ __forceinline__ void bwd_tn_contract(const float4* wT, const float* B
   }
 }
 
+// fp16 form (see bwd_t_contract_h): the B fragments of all NS n-tiles are scaled and split once per step and warp, then
+// every m-tile costs 2 fragment loads and 3 NS MMAs per 16 k.  cmx: bit patterns of the per-stream maxima of |dgifo|.
+template <int NM, int NS>
+__device__ __forceinline__ void bwd_tn_contract_h(const uint4* wh, const uint4* wl, const float* Bsm, const unsigned* cmx, float* out, int nblk,
+                                                  int warp, int lane) {
+  constexpr int SW = 8 * NS;
+  constexpr int BP = BwdTnPitch<NS>::value;
+  const int g = lane >> 2, tig = lane & 3;
+  uint32_t bh[NS][4][2], bl[NS][4][2];
+  float inv[NS][2];
+#pragma unroll
+  for (int nt = 0; nt < NS; ++nt) {
+    float unused;
+    const float sc = pow2_scale(__uint_as_float(cmx[nt * 8 + g]), unused);
+    pow2_scale(__uint_as_float(cmx[nt * 8 + 2 * tig]), inv[nt][0]);
+    pow2_scale(__uint_as_float(cmx[nt * 8 + 2 * tig + 1]), inv[nt][1]);
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const float* col = Bsm + (kh * 16 + 2 * tig) * BP + nt * 8 + g;
+      split_h2(col[0] * sc, col[BP] * sc, bh[nt][kh][0], bl[nt][kh][0]);
+      split_h2(col[8 * BP] * sc, col[9 * BP] * sc, bh[nt][kh][1], bl[nt][kh][1]);
+    }
+  }
+#pragma unroll 1
+  for (int mi = 0; mi < NM; ++mi) {
+    const int mt = warp + 8 * mi;
+    float hh[NS][4], lh[NS][4], hl[NS][4];
+#pragma unroll
+    for (int nt = 0; nt < NS; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { hh[nt][q] = 0.f; lh[nt][q] = 0.f; hl[nt][q] = 0.f; }
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const uint4 h4 = wh[(mt * 4 + kh) * 32 + lane], l4 = wl[(mt * 4 + kh) * 32 + lane];
+      const uint32_t ah[4] = {h4.x, h4.y, h4.z, h4.w}, al[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int nt = 0; nt < NS; ++nt) {
+        mma_f16(lh[nt], al, bh[nt][kh][0], bh[nt][kh][1]);
+        mma_f16(hl[nt], ah, bl[nt][kh][0], bl[nt][kh][1]);
+        mma_f16(hh[nt], ah, bh[nt][kh][0], bh[nt][kh][1]);
+      }
+    }
+    float* dst = out + (size_t)mt * nblk * 16 * SW;      // block of consumer CTA mt: [producer][16][SW]
+#pragma unroll
+    for (int nt = 0; nt < NS; ++nt) {
+      st_pub2(dst + g * SW + nt * 8 + 2 * tig, ((lh[nt][0] + hl[nt][0]) + hh[nt][0]) * inv[nt][0], ((lh[nt][1] + hl[nt][1]) + hh[nt][1]) * inv[nt][1]);
+      st_pub2(dst + (g + 8) * SW + nt * 8 + 2 * tig, ((lh[nt][2] + hl[nt][2]) + hh[nt][2]) * inv[nt][0], ((lh[nt][3] + hl[nt][3]) + hh[nt][3]) * inv[nt][1]);
+    }
+  }
+}
+
 template <int NS>
 __global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
   constexpr int SW = 8 * NS;                             // streams per chain
-  constexpr int BP = (NS == 2 || NS == 4) ? SW + 8 : SW; // Bsm row pitch (see bwd_tn_contract)
+  constexpr int BP = BwdTnPitch<NS>::value;
   constexpr int ITEMS = 16 * SW;                         // (cell, stream) items of a CTA
   constexpr int IPT = (ITEMS + NT - 1) / NT;             // items per thread (1 or 2)
   extern __shared__ __align__(16) float smem[];
@@ -392,12 +451,21 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
   const int c0 = cta.blk * 16;
   if (cta.sbeg >= S) return;
 
+#if !ASLP_BWD_T_FP16
   float4* wT = reinterpret_cast<float4*>(smem);          // [nblk][8][32] float4
+#endif
   float* Bsm = smem + (size_t)nblk * 1024;               // [64][BP]
   float* Psm = Bsm + 64 * 40;                            // [nblk][16][SW]
   float* st = Psm + (size_t)nblk * 16 * SW;              // [3][16][SW]
   float* pst = st + 3 * ITEMS;                           // [3][16]
+  unsigned* cmx = reinterpret_cast<unsigned*>(pst + 48); // per-stream maxima of |dgifo| (bit patterns), double-buffered [2][32] (fp16 form)
 
+#if ASLP_BWD_T_FP16
+  uint4* wTh = reinterpret_cast<uint4*>(smem);
+  uint4* wTl = wTh + (size_t)nblk * 128;
+  bwd_t_fill_h(D, wTh, wTl, nblk, c0);
+  for (int i = threadIdx.x; i < 64; i += NT) cmx[i] = 0u;
+#else
   for (int i = threadIdx.x; i < nblk * 256; i += NT) {
     const int mt = i >> 8, kt = (i >> 5) & 7, ln = i & 31, gg = ln >> 2, tt = ln & 3;
     float v[4];
@@ -409,6 +477,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
     }
     wT[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
+#endif
   for (int i = threadIdx.x; i < 3 * ITEMS; i += NT) st[i] = 0.f;
   for (int i = threadIdx.x; i < 64 * BP; i += NT) Bsm[i] = 0.f;
   for (int i = threadIdx.x; i < 48; i += NT) {
@@ -499,8 +568,15 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
         const int sl = item - cl * SW;                   // B operand rows: gate * 16 + cell
         Bsm[(0 * 16 + cl) * BP + sl] = dv[r][0]; Bsm[(1 * 16 + cl) * BP + sl] = dv[r][1];
         Bsm[(2 * 16 + cl) * BP + sl] = dv[r][2]; Bsm[(3 * 16 + cl) * BP + sl] = dv[r][3];
+#if ASLP_BWD_T_FP16
+        const float m4 = fmaxf(fmaxf(fabsf(dv[r][0]), fabsf(dv[r][1])), fmaxf(fabsf(dv[r][2]), fabsf(dv[r][3])));
+        if (m4 > 0.f) atomicMax(&cmx[(it & 1) * 32 + sl], __float_as_uint(m4));      // non-negative floats order like their bits
+#endif
       }
     }
+#if ASLP_BWD_T_FP16
+    if (threadIdx.x < 32) cmx[((it + 1) & 1) * 32 + threadIdx.x] = 0u;   // next step's maxima; its last readers passed the barrier above
+#endif
     {                                                    // re-arm the slot just consumed; visible before the next publish
       float* blk = own_block(slot);
       const float4 sent = make_float4(__uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL));
@@ -512,10 +588,18 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
       const int nslot = (it + 1) % TR;
       float* out = X + (size_t)nslot * slot_stride + chain_off + (size_t)cta.blk * blk_floats;   // + consumer * nblk * blk_floats
       const int nm = (nblk - warp + 7) >> 3;             // m-tiles of this warp (warp-uniform)
+#if ASLP_BWD_T_FP16
+      const unsigned* cm = cmx + (it & 1) * 32;
+      if (nm >= 4) bwd_tn_contract_h<4, NS>(wTh, wTl, Bsm, cm, out, nblk, warp, lane);
+      else if (nm == 3) bwd_tn_contract_h<3, NS>(wTh, wTl, Bsm, cm, out, nblk, warp, lane);
+      else if (nm == 2) bwd_tn_contract_h<2, NS>(wTh, wTl, Bsm, cm, out, nblk, warp, lane);
+      else if (nm == 1) bwd_tn_contract_h<1, NS>(wTh, wTl, Bsm, cm, out, nblk, warp, lane);
+#else
       if (nm >= 4) bwd_tn_contract<4, NS>(wT, Bsm, out, nblk, warp, lane);
       else if (nm == 3) bwd_tn_contract<3, NS>(wT, Bsm, out, nblk, warp, lane);
       else if (nm == 2) bwd_tn_contract<2, NS>(wT, Bsm, out, nblk, warp, lane);
       else if (nm == 1) bwd_tn_contract<1, NS>(wT, Bsm, out, nblk, warp, lane);
+#endif
       issue_gather(nslot);
     }
 #pragma unroll
