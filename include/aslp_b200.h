@@ -40,6 +40,7 @@ const char* aslp_last_error(void);
 unsigned long long aslp_launch_count(void);       /* kernels launched by this library so far */
 int aslp_device_count(int* n);
 int aslp_set_device(int dev);                     /* CuDevice::SelectGpuId */
+int aslp_get_device(int* dev);                    /* the calling thread's current device (helper threads inherit it explicitly) */
 int aslp_malloc(void** dptr, size_t bytes);       /* CuDevice::Malloc (cu-device.h:54) */
 int aslp_free(void* dptr);                        /* CuDevice::Free   (cu-device.h:59) */
 int aslp_malloc_host(void** hptr, size_t bytes);  /* pinned staging for CopyFromMat/CopyToMat */
@@ -61,6 +62,7 @@ int aslp_device_sync(void);
 int aslp_event_record(aslp_stream_t s, void** event);
 int aslp_event_elapsed_ms(void* a, void* b, float* ms);
 int aslp_stream_wait_event(aslp_stream_t s, void* event);   /* later work on s starts after `event` (recorded on another stream) */
+int aslp_event_sync(void* event);                           /* the host waits for `event` (a pinned staging slot is free again) */
 
 /* ---- dense contraction: CuMatrixBase::AddMatMat (cu-matrix.cc:1027-1062) ----
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C  (+ bias[n] broadcast over rows)

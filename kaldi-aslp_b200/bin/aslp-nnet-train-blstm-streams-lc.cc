@@ -3,6 +3,7 @@
 // repeated, mask 0 for the look-ahead rows) and log lines as src/aslp-nnetbin/aslp-nnet-train-blstm-streams-lc.cc:35-394.
 // With --worker-type it is the worker of src/aslp-parallelbin/aslp-nnet-train-lc-blstm-streams-worker.cc:176-330
 // (one process per GPU; that binary spells the look-ahead flag --right_splice: '-' and '_' are interchangeable here).
+#include "batch-feeder.h"
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
@@ -108,16 +109,25 @@ int main(int argc, char* argv[]) {
     std::vector<std::string> keys(num_stream);
     std::vector<Matrix<BaseFloat>> feats(num_stream);
     std::vector<Posterior> targets(num_stream);
-    std::vector<int32> curt(num_stream, 0), lent(num_stream, 0), new_utt_flags(num_stream, 0);
+    std::vector<int32> curt(num_stream, 0), lent(num_stream, 0);
     const int32 feat_dim = nnet.InputDim();
-    Vector<BaseFloat> frame_mask(batch_size * num_stream);
-    Matrix<BaseFloat> feat(batch_size * num_stream, feat_dim);
-    Posterior target(batch_size * num_stream);
-    CuMatrix feat_dev, feat_transf, nnet_out, obj_diff;
+    CuMatrix feat_dev, nnet_out, obj_diff;
 
-    while (1) {
+    // One chunk minibatch, built by the feeder thread with the reference's own stream bookkeeping (:185-268): streams whose
+    // utterance is used up take the next readable one, then batch_size rows per stream are packed into a page-locked slot.
+    struct LcBatch {
+      PinnedMatrix feat;
+      Vector<BaseFloat> frame_mask;
+      Posterior target;
+      std::vector<int32> new_utt_flags;
+      int32 num_no_tgt = 0, num_other_error = 0;
+    };
+    CuMatrix transf_in, transf_out;                 // the feeder thread's own device buffers (its stream)
+    auto fill = [&](LcBatch* b) -> bool {
+      b->new_utt_flags.assign(num_stream, 0);
+      b->num_no_tgt = 0; b->num_other_error = 0;
       for (int32 s = 0; s < num_stream; s++) {
-        if (curt[s] < lent[s]) { new_utt_flags[s] = 0; continue; }
+        if (curt[s] < lent[s]) { b->new_utt_flags[s] = 0; continue; }
         while (!feature_reader.Done()) {
           const std::string key = feature_reader.Key();
           const Matrix<BaseFloat>& mat = feature_reader.Value();
@@ -128,22 +138,22 @@ int main(int argc, char* argv[]) {
           }
           Matrix<BaseFloat> transformed;
           if (nnet_transf.NumComponents() > 0) {
-            feat_dev = mat;
-            nnet_transf.Feedforward(feat_dev, &feat_transf);
-            feat_transf.CopyToMat(&transformed);
+            transf_in = mat;
+            nnet_transf.Feedforward(transf_in, &transf_out);
+            transf_out.CopyToMat(&transformed);
           } else {
             transformed = mat;
           }
           if (!target_reader.HasKey(key)) {
             KALDI_WARN << key << ", missing targets";
-            num_no_tgt_mat++;
+            b->num_no_tgt++;
             feature_reader.Next();
             continue;
           }
           const Posterior& tgt = target_reader.Value(key);
           if (transformed.NumRows() != static_cast<int32>(tgt.size())) {
             KALDI_WARN << key << ", length miss-match between feats and targets, skip";
-            num_other_error++;
+            b->num_other_error++;
             feature_reader.Next();
             continue;
           }
@@ -152,44 +162,56 @@ int main(int argc, char* argv[]) {
           targets[s] = tgt;
           curt[s] = 0;
           lent[s] = feats[s].NumRows();
-          new_utt_flags[s] = 1;
+          b->new_utt_flags[s] = 1;
           feature_reader.Next();
           break;
         }
       }
       int done = 1;
       for (int32 s = 0; s < num_stream; s++) if (curt[s] < lent[s]) done = 0;
-      if (done) break;
+      if (done) return false;
 
+      b->frame_mask.Resize(batch_size * num_stream);
+      b->target.resize(batch_size * num_stream);
+      b->feat.Resize(batch_size * num_stream, feat_dim, kUndefined);
       for (int32 t = 0; t < batch_size; t++) {
         for (int32 s = 0; s < num_stream; s++) {
           const int32 row = t * num_stream + s;
           if (curt[s] < lent[s]) {
-            frame_mask(row) = (t >= chunk_size) ? 0.0f : 1.0f;
-            target[row] = targets[s][curt[s]];
-            std::copy(feats[s].RowData(curt[s]), feats[s].RowData(curt[s]) + feat_dim, feat.RowData(row));
+            b->frame_mask(row) = (t >= chunk_size) ? 0.0f : 1.0f;
+            b->target[row] = targets[s][curt[s]];
+            std::copy(feats[s].RowData(curt[s]), feats[s].RowData(curt[s]) + feat_dim, b->feat.RowData(row));
           } else {
-            frame_mask(row) = 0.0f;
-            if (lent[s] > 0) target[row] = targets[s][lent[s] - 1]; else target[row].clear();
-            std::fill(feat.RowData(row), feat.RowData(row) + feat_dim, 0.0f);      // zero frames, not the last frame (:261)
+            b->frame_mask(row) = 0.0f;
+            if (lent[s] > 0) b->target[row] = targets[s][lent[s] - 1]; else b->target[row].clear();
+            std::fill(b->feat.RowData(row), b->feat.RowData(row) + feat_dim, 0.0f);      // zero frames, not the last frame (:261)
           }
           curt[s]++;
         }
       }
       for (int32 s = 0; s < num_stream; s++) curt[s] = curt[s] - right_splice;
+      return true;
+    };
+    BatchFeeder<LcBatch> feeder(fill, /*attach_device=*/nnet_transf.NumComponents() > 0);
 
-      nnet.ResetLstmStreams(new_utt_flags);
-      feat_dev = feat;
+    while (LcBatch* b = feeder.Next()) {
+      num_no_tgt_mat += b->num_no_tgt;
+      num_other_error += b->num_other_error;
+      nnet.ResetLstmStreams(b->new_utt_flags);
+      feat_dev.Resize(b->feat.NumRows(), feat_dim, kUndefined);
+      feat_dev.CopyFromHost(b->feat.Data(), b->feat.Stride());           // asynchronous: the slot is page-locked
       if (!crossvalidate) nnet.Propagate(feat_dev, &nnet_out);
       else nnet.Feedforward(feat_dev, &nnet_out);
-      xent.Eval(frame_mask, nnet_out, target, &obj_diff);
-      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      xent.Eval(b->frame_mask, nnet_out, b->target, &obj_diff);
 
       int frame_progress = 0;
-      for (int32 i = 0; i < frame_mask.Dim(); i++) frame_progress += static_cast<int>(frame_mask(i));
-      total_frames += frame_progress;
+      for (int32 i = 0; i < b->frame_mask.Dim(); i++) frame_progress += static_cast<int>(b->frame_mask(i));
       int num_done_progress = 0;
-      for (size_t i = 0; i < new_utt_flags.size(); i++) num_done_progress += new_utt_flags[i];
+      for (size_t i = 0; i < b->new_utt_flags.size(); i++) num_done_progress += b->new_utt_flags[i];
+      feeder.Release(b);                              // Xent::Eval has uploaded mask and targets (pageable: staged at the call)
+      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+
+      total_frames += frame_progress;
       num_done += num_done_progress;
       num_sentence += num_done_progress;
       if (num_sentence >= report_period) {

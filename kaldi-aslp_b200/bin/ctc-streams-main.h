@@ -7,6 +7,7 @@
 // data-parallel job (one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK from the environment).
 #ifndef ASLP_BIN_CTC_STREAMS_MAIN_H_
 #define ASLP_BIN_CTC_STREAMS_MAIN_H_
+#include "batch-feeder.h"
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
@@ -93,23 +94,31 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     CuMatrix net_out, obj_diff;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
-    std::vector<Matrix<BaseFloat>> feats_utt(num_stream);
-    std::vector<std::vector<int32>> labels_utt(num_stream);
-    std::vector<std::string> key_utt(num_stream);
     const int32 feat_dim = net.InputDim();
     int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0, num_sentence = 0;
     int32 num_frames_since_sync = 0;
-    Matrix<BaseFloat> feat_mat_host;
     CuMatrix feat_mat_dev;
 
-    while (1) {
+    // One group of utterances, read / filtered / packed by the feeder thread exactly as the reference's loop does it
+    // (aslp-nnet-train-warp-ctc-streams.cc:116-175), into a page-locked slot.
+    struct CtcBatch {
+      PinnedMatrix feat;                              // stream-interleaved, zero padded to the longest utterance of the group
       std::vector<int32> frame_num_utt;
+      std::vector<std::string> keys;
+      std::vector<std::vector<int32>> labels;
+      int32 num_valid_frame = 0, num_no_tgt = 0;
+      bool last = false;                              // the feature reader was exhausted when the group closed
+    };
+    std::vector<Matrix<BaseFloat>> feats_utt(num_stream);
+    auto fill = [&](CtcBatch* b) -> bool {
+      b->frame_num_utt.clear(); b->keys.clear(); b->labels.clear();
+      b->num_valid_frame = 0; b->num_no_tgt = 0;
       int32 sequence_index = 0, max_frame_num = 0;
       for (; !feature_reader.Done(); feature_reader.Next()) {
         const std::string utt = feature_reader.Key();
         if (!targets_reader.HasKey(utt)) {
           KALDI_WARN << utt << ", missing targets";
-          num_no_tgt_mat++;
+          b->num_no_tgt++;
           continue;
         }
         const Matrix<BaseFloat>& raw_mat = feature_reader.Value();
@@ -117,7 +126,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
           KALDI_WARN << utt << ", too long, droped";
           continue;
         }
-        Matrix<BaseFloat> mat;
+        Matrix<BaseFloat>& mat = feats_utt[sequence_index];
         if (skip_width > 1) {
           const int32 skip_len = (raw_mat.NumRows() - 1) / skip_width + 1;
           mat.Resize(skip_len, raw_mat.NumCols());
@@ -127,41 +136,52 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
           mat = raw_mat;
         }
         if (max_frame_num < mat.NumRows()) max_frame_num = mat.NumRows();
-        feats_utt[sequence_index] = mat;
-        labels_utt[sequence_index] = targets_reader.Value(utt);
-        key_utt[sequence_index] = utt;
-        frame_num_utt.push_back(mat.NumRows());
+        b->labels.push_back(targets_reader.Value(utt));
+        b->keys.push_back(utt);
+        b->frame_num_utt.push_back(mat.NumRows());
         sequence_index++;
-        if (static_cast<int32>(frame_num_utt.size()) == num_stream || frame_num_utt.size() * max_frame_num > frame_limit) {
+        if (static_cast<int32>(b->frame_num_utt.size()) == num_stream || b->frame_num_utt.size() * max_frame_num > frame_limit) {
           feature_reader.Next();
           break;
         }
       }
-      const int32 cur_sequence_num = static_cast<int32>(frame_num_utt.size());
-      if (cur_sequence_num == 0) break;        // nothing left (the reference would assert inside Propagate here)
-      int32 num_valid_frame = 0;
-      // stream-interleaved, zero padded to the longest utterance of the group
-      feat_mat_host.Resize(cur_sequence_num * max_frame_num, feat_dim, kSetZero);
+      const int32 cur_sequence_num = static_cast<int32>(b->frame_num_utt.size());
+      b->last = feature_reader.Done();
+      if (cur_sequence_num == 0) return false;  // nothing left (the reference would assert inside Propagate here)
+      b->feat.Resize(cur_sequence_num * max_frame_num, feat_dim, kSetZero);
       for (int32 s = 0; s < cur_sequence_num; s++) {
         const Matrix<BaseFloat>& m = feats_utt[s];
         KALDI_ASSERT(m.NumCols() == feat_dim);
-        for (int32 r = 0; r < frame_num_utt[s]; r++)
-          std::copy(m.RowData(r), m.RowData(r) + feat_dim, feat_mat_host.RowData(r * cur_sequence_num + s));
-        num_valid_frame += frame_num_utt[s];
+        for (int32 r = 0; r < b->frame_num_utt[s]; r++)
+          std::copy(m.RowData(r), m.RowData(r) + feat_dim, b->feat.RowData(r * cur_sequence_num + s));
+        b->num_valid_frame += b->frame_num_utt[s];
       }
-      net.SetSeqLengths(frame_num_utt);
+      return true;
+    };
+    BatchFeeder<CtcBatch> feeder(fill, /*attach_device=*/false);
+
+    while (CtcBatch* b = feeder.Next()) {
+      const int32 cur_sequence_num = static_cast<int32>(b->frame_num_utt.size());
+      const int32 num_valid_frame = b->num_valid_frame, batch_rows = b->feat.NumRows();
+      num_no_tgt_mat += b->num_no_tgt;
+      net.SetSeqLengths(b->frame_num_utt);
       trn_opts.learn_rate = norm_lr / num_valid_frame;        // per-minibatch learn-rate normalisation (:177)
       net.SetTrainOptions(trn_opts);
-      feat_mat_dev = feat_mat_host;
+      feat_mat_dev.Resize(b->feat.NumRows(), feat_dim, kUndefined);
+      feat_mat_dev.CopyFromHost(b->feat.Data(), b->feat.Stride());      // asynchronous: the slot is page-locked
+      // the loss below needs this group's keys / lengths / labels after the slot has gone back to the feeder
+      const std::vector<int32> frame_num_utt = b->frame_num_utt;
+      const std::vector<std::string> keys = b->keys;
+      std::vector<std::vector<int32>> labels = b->labels;     // (the Eesen front end takes it non-const, as the reference does)
+      const bool last = b->last;
+      feeder.Release(b);
       if (!crossvalidate) net.Propagate(feat_mat_dev, &net_out);
       else net.Feedforward(feat_mat_dev, &net_out);
-      std::vector<std::string> keys(key_utt.begin(), key_utt.begin() + cur_sequence_num);
-      std::vector<std::vector<int32>> labels(labels_utt.begin(), labels_utt.begin() + cur_sequence_num);
       ctc.Eval(keys, frame_num_utt, net_out, labels, &obj_diff);
       ctc.ErrorRate(frame_num_utt, net_out, labels);
       if (!crossvalidate) net.Backpropagate(obj_diff, nullptr);
       num_done += cur_sequence_num;
-      total_frames += feat_mat_host.NumRows();
+      total_frames += batch_rows;
       num_sentence += cur_sequence_num;
       if (num_sentence >= report_period) {
         KALDI_LOG << ctc.Report();
@@ -174,7 +194,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
           num_frames_since_sync = 0;
         }
       }
-      if (feature_reader.Done()) break;
+      if (last) break;
     }
     if (worker) {
       // last partial period, then zero-frame syncs until every rank is out of data (termination protocol)

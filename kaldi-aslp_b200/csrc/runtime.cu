@@ -32,6 +32,7 @@ unsigned long long aslp_launch_count(void) { return g_aslp_launches; }
 
 int aslp_device_count(int* n) { ASLP_CUDA(cudaGetDeviceCount(n)); return 0; }
 int aslp_set_device(int dev) { ASLP_CUDA(cudaSetDevice(dev)); return 0; }
+int aslp_get_device(int* dev) { ASLP_CUDA(cudaGetDevice(dev)); return 0; }
 int aslp_malloc(void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
   if (e != cudaSuccess) { aslp_set_last_error(e, __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
@@ -78,6 +79,11 @@ int aslp_event_record(aslp_stream_t s, void** event) {
 int aslp_stream_wait_event(aslp_stream_t s, void* event) {
   ASLP_REQUIRE(event != nullptr);
   ASLP_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)event, 0));
+  return 0;
+}
+int aslp_event_sync(void* event) {
+  ASLP_REQUIRE(event != nullptr);
+  ASLP_CUDA(cudaEventSynchronize((cudaEvent_t)event));
   return 0;
 }
 int aslp_event_elapsed_ms(void* a, void* b, float* ms) {

@@ -5,7 +5,9 @@ namespace kaldi {
 
 static aslp_stream_t g_stream = nullptr;       // compute stream
 static aslp_stream_t g_side = nullptr;         // side stream (lazily created)
-static aslp_stream_t g_current = nullptr;      // what CuStream() hands out (compute stream unless inside a CuStreamScope)
+static thread_local aslp_stream_t t_current = nullptr;   // CuStreamScope / helper-thread override of what CuStream() hands out
+static thread_local bool t_helper = false;                // a thread that went through CuThreadAttach()
+static int g_device = 0;                                  // the device the compute stream was created on
 static bool g_stream_made = false;
 static bool g_side_pending = false;
 static void* g_ev_fork = nullptr;
@@ -20,11 +22,24 @@ aslp_stream_t CuStream() {
     int n = 0;
     if (aslp_device_count(&n) != 0 || n <= 0)
       KALDI_ERR << "No CUDA device: this build has no CPU path (the reference's --use-gpu=no branch is the oracle, not the product)";
+    ASLP_OK(aslp_get_device(&g_device));
     ASLP_OK(aslp_stream_create(&g_stream));
-    g_current = g_stream;
     g_stream_made = true;
   }
-  return g_current;
+  return t_current != nullptr ? t_current : g_stream;
+}
+void CuThreadAttach() {
+  KALDI_ASSERT(!t_helper && g_stream_made);
+  ASLP_OK(aslp_set_device(g_device));                     // the current device is per-thread state
+  ASLP_OK(aslp_stream_create(&t_current));
+  t_helper = true;
+}
+void CuThreadDetach() {
+  if (!t_helper) return;
+  aslp_stream_sync(t_current);
+  aslp_stream_destroy(t_current);
+  t_current = nullptr;
+  t_helper = false;
 }
 aslp_stream_t CuSideStream() {
   CuStream();
@@ -48,16 +63,31 @@ void CuJoin() {
   ASLP_OK(aslp_stream_wait_event(g_stream, g_ev_join));
   g_side_pending = false;
 }
-CuStreamScope::CuStreamScope(aslp_stream_t s) { CuStream(); saved_ = g_current; g_current = s; }
-CuStreamScope::~CuStreamScope() { g_current = saved_; }
+CuStreamScope::CuStreamScope(aslp_stream_t s) { CuStream(); saved_ = t_current; t_current = s; }
+CuStreamScope::~CuStreamScope() { t_current = saved_; }
 void CuSync() {
   CuStream();
+  if (t_helper) { ASLP_OK(aslp_stream_sync(t_current)); return; }     // a helper thread owns nothing but its stream
   if (g_side != nullptr) ASLP_OK(aslp_stream_sync(g_side));
   g_side_pending = false;
   ASLP_OK(aslp_stream_sync(g_stream));
 }
 
 // ------------------------------------------------------------------ host containers
+PinnedMatrix::~PinnedMatrix() { if (d_ != nullptr) aslp_free_host(d_); }
+void PinnedMatrix::Resize(int32 rows, int32 cols, MatrixResizeType t) {
+  const size_t n = static_cast<size_t>(rows) * cols;
+  if (n > cap_) {
+    if (d_ != nullptr) { ASLP_OK(aslp_free_host(d_)); d_ = nullptr; }
+    const size_t cap = n + n / 4 + 1024;
+    void* p = nullptr;
+    ASLP_OK(aslp_malloc_host(&p, cap * sizeof(float)));
+    d_ = static_cast<float*>(p);
+    cap_ = cap;
+  }
+  r_ = rows; c_ = cols;
+  if (t == kSetZero && n > 0) std::memset(d_, 0, n * sizeof(float));
+}
 template <typename Real> static const char* MatTok() { return sizeof(Real) == 4 ? "FM" : "DM"; }
 template <typename Real> static const char* VecTok() { return sizeof(Real) == 4 ? "FV" : "DV"; }
 
@@ -377,19 +407,26 @@ std::string MomentStatistics(const CuVector& v) {
 // ------------------------------------------------------------------ shared workspace, GEMM precision
 #include "cu-workspace.h"
 #include <cstring>
+#include <map>
+#include <mutex>
 namespace kaldi {
-// one workspace per stream: [0] compute stream, [1] side stream
-static void* g_ws[2] = {nullptr, nullptr};
-static size_t g_ws_bytes[2] = {0, 0};
+// one workspace per stream (compute stream, side stream, a helper thread's stream)
+namespace {
+struct Ws { void* p = nullptr; size_t bytes = 0; };
+std::map<aslp_stream_t, Ws> g_ws;
+std::mutex g_ws_mu;
+}
 void* CuWorkspace(size_t bytes) {
-  const int w = (CuStream() == g_stream) ? 0 : 1;
-  if (bytes > g_ws_bytes[w]) {
-    if (g_ws[w] != nullptr) { CuSync(); aslp_free(g_ws[w]); g_ws[w] = nullptr; }
+  const aslp_stream_t st = CuStream();
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  Ws& w = g_ws[st];
+  if (bytes > w.bytes) {
+    if (w.p != nullptr) { ASLP_OK(aslp_stream_sync(st)); aslp_free(w.p); w.p = nullptr; }    // its users ran on this stream
     const size_t cap = bytes + bytes / 4 + (1u << 20);
-    ASLP_OK(aslp_malloc(&g_ws[w], cap));
-    g_ws_bytes[w] = cap;
+    ASLP_OK(aslp_malloc(&w.p, cap));
+    w.bytes = cap;
   }
-  return g_ws[w];
+  return w.p;
 }
 static int g_gemm_precision = -1;
 int GemmPrecision() {

@@ -23,6 +23,11 @@ void CuSync();                     // waits for the compute stream AND the side 
 // the side stream (CuStream() returns it, CuWorkspace() hands out the side stream's own workspace).  CuJoin(): the
 // compute stream waits for the side stream; a no-op when nothing was forked.  ASLP_ASYNC_WGRAD=0 disables the overlap.
 aslp_stream_t CuSideStream();
+// Helper threads (the batch feeders of the trainer mains): CuThreadAttach() gives the calling thread the process's device
+// and a stream of its own; from then on every device call this library makes on that thread goes to that stream (with its own
+// workspace) and CuSync() waits for it alone.  CuThreadDetach() drains and destroys the stream.
+void CuThreadAttach();
+void CuThreadDetach();
 bool CuAsyncEnabled();
 void CuFork();
 void CuJoin();
@@ -75,6 +80,28 @@ class Matrix {
  private:
   int32 r_, c_;
   std::vector<Real> d_;
+};
+
+// page-locked host matrix (dense rows): the staging slots of the batch feeders, so that the H2D copy of a minibatch is a true
+// asynchronous DMA (CuMatrixBase::CopyFromHost) instead of a driver-staged pageable copy
+class PinnedMatrix {
+ public:
+  PinnedMatrix() : d_(nullptr), cap_(0), r_(0), c_(0) {}
+  ~PinnedMatrix();
+  PinnedMatrix(const PinnedMatrix&) = delete;
+  PinnedMatrix& operator=(const PinnedMatrix&) = delete;
+  void Resize(int32 rows, int32 cols, MatrixResizeType t = kSetZero);   // grows geometrically, never shrinks
+  int32 NumRows() const { return r_; }
+  int32 NumCols() const { return c_; }
+  int32 Stride() const { return c_; }
+  float* Data() { return d_; }
+  const float* Data() const { return d_; }
+  float* RowData(int32 r) { return d_ + static_cast<size_t>(r) * c_; }
+  const float* RowData(int32 r) const { return d_ + static_cast<size_t>(r) * c_; }
+ private:
+  float* d_;
+  size_t cap_;
+  int32 r_, c_;
 };
 
 class CuSubMatrix;
