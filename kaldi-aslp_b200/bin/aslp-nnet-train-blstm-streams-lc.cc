@@ -120,12 +120,10 @@ int main(int argc, char* argv[]) {
       Vector<BaseFloat> frame_mask;
       Posterior target;
       std::vector<int32> new_utt_flags;
-      int32 num_no_tgt = 0, num_other_error = 0;
     };
     CuMatrix transf_in, transf_out;                 // the feeder thread's own device buffers (its stream)
     auto fill = [&](LcBatch* b) -> bool {
       b->new_utt_flags.assign(num_stream, 0);
-      b->num_no_tgt = 0; b->num_other_error = 0;
       for (int32 s = 0; s < num_stream; s++) {
         if (curt[s] < lent[s]) { b->new_utt_flags[s] = 0; continue; }
         while (!feature_reader.Done()) {
@@ -146,14 +144,14 @@ int main(int argc, char* argv[]) {
           }
           if (!target_reader.HasKey(key)) {
             KALDI_WARN << key << ", missing targets";
-            b->num_no_tgt++;
+            num_no_tgt_mat++;                      // these two counters are the feeder thread's until feeder.Join()
             feature_reader.Next();
             continue;
           }
           const Posterior& tgt = target_reader.Value(key);
           if (transformed.NumRows() != static_cast<int32>(tgt.size())) {
             KALDI_WARN << key << ", length miss-match between feats and targets, skip";
-            b->num_other_error++;
+            num_other_error++;
             feature_reader.Next();
             continue;
           }
@@ -195,8 +193,6 @@ int main(int argc, char* argv[]) {
     BatchFeeder<LcBatch> feeder(fill, /*attach_device=*/nnet_transf.NumComponents() > 0);
 
     while (LcBatch* b = feeder.Next()) {
-      num_no_tgt_mat += b->num_no_tgt;
-      num_other_error += b->num_other_error;
       nnet.ResetLstmStreams(b->new_utt_flags);
       feat_dev.Resize(b->feat.NumRows(), feat_dim, kUndefined);
       feat_dev.CopyFromHost(b->feat.Data(), b->feat.Stride());           // asynchronous: the slot is page-locked
@@ -231,6 +227,7 @@ int main(int argc, char* argv[]) {
         nnet.Write(nnet_name, binary);
       }
     }
+    feeder.Join();
     if (worker) {
       if (!worker->IsAsync()) {
         if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);

@@ -2,6 +2,7 @@
 // line, length-tolerance rule, learn-rate quirk (learn_rate = norm_lr / 1024 for every utterance, :201) and log lines as
 // src/aslp-nnetbin/aslp-nnet-train-perutt.cc:30-300.  --frame-weights is not served (not on the BASELINE configs).
 #include <algorithm>
+#include "batch-feeder.h"
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
@@ -71,40 +72,56 @@ int main(int argc, char* argv[]) {
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0;
-    for (; !feature_reader.Done(); feature_reader.Next()) {
-      const std::string utt = feature_reader.Key();
-      if (!targets_reader.HasKey(utt)) {
-        KALDI_WARN << utt << ", missing targets";
-        num_no_tgt_mat++;
-        continue;
+    // One utterance per step, read / filtered / trimmed by the feeder thread as the reference's loop does it (:139-190)
+    struct UttBatch {
+      PinnedMatrix mat;
+      Posterior targets;
+      Vector<BaseFloat> weights;
+    };
+    auto fill = [&](UttBatch* b) -> bool {
+      for (; !feature_reader.Done(); feature_reader.Next()) {
+        const std::string utt = feature_reader.Key();
+        if (!targets_reader.HasKey(utt)) {
+          KALDI_WARN << utt << ", missing targets";
+          num_no_tgt_mat++;                         // the feeder thread's until feeder.Join()
+          continue;
+        }
+        const Matrix<BaseFloat>& full = feature_reader.Value();
+        b->targets = targets_reader.Value(utt);
+        // correct small length mismatch (:155-172)
+        const int32 lens[3] = {full.NumRows(), static_cast<int32>(b->targets.size()), full.NumRows()};
+        const int32 mn = *std::min_element(lens, lens + 3), mx = *std::max_element(lens, lens + 3);
+        if (mx - mn >= length_tolerance) {
+          KALDI_WARN << utt << ", length mismatch of targets " << b->targets.size() << " and features " << full.NumRows();
+          num_other_error++;
+          continue;
+        }
+        if (drop_len > 0 && mn > drop_len) {
+          KALDI_WARN << utt << ", length too long " << mn << " drop it";
+          continue;
+        }
+        b->mat.Resize(mn, full.NumCols(), kUndefined);
+        for (int32 r = 0; r < mn; r++) std::copy(full.RowData(r), full.RowData(r) + full.NumCols(), b->mat.RowData(r));
+        b->targets.resize(mn);
+        b->weights.Resize(mn);
+        for (int32 r = 0; r < mn; r++) b->weights(r) = 1.0f;
+        feature_reader.Next();
+        return true;
       }
-      const Matrix<BaseFloat>& full = feature_reader.Value();
-      Posterior targets = targets_reader.Value(utt);
-      // correct small length mismatch (:155-172)
-      const int32 lens[3] = {full.NumRows(), static_cast<int32>(targets.size()), full.NumRows()};
-      const int32 mn = *std::min_element(lens, lens + 3), mx = *std::max_element(lens, lens + 3);
-      if (mx - mn >= length_tolerance) {
-        KALDI_WARN << utt << ", length mismatch of targets " << targets.size() << " and features " << full.NumRows();
-        num_other_error++;
-        continue;
-      }
-      Matrix<BaseFloat> mat(mn, full.NumCols());
-      for (int32 r = 0; r < mn; r++) std::copy(full.RowData(r), full.RowData(r) + full.NumCols(), mat.RowData(r));
-      targets.resize(mn);
-      Vector<BaseFloat> weights(mn);
-      for (int32 r = 0; r < mn; r++) weights(r) = 1.0f;
-      if (drop_len > 0 && mat.NumRows() > drop_len) {
-        KALDI_WARN << utt << ", length too long " << mat.NumRows() << " drop it";
-        continue;
-      }
-      feats = mat;
+      return false;
+    };
+    BatchFeeder<UttBatch> feeder(fill, /*attach_device=*/false);
+    while (UttBatch* b = feeder.Next()) {
+      feats.Resize(b->mat.NumRows(), b->mat.NumCols(), kUndefined);
+      feats.CopyFromHost(b->mat.Data(), b->mat.Stride());      // asynchronous: the slot is page-locked
       const CuMatrixBase* net_in = &feats;
       if (nnet_transf.NumComponents() > 0) { nnet_transf.Feedforward(feats, &feats_transf); net_in = &feats_transf; }
       trn_opts.learn_rate = norm_lr / 1024.0;             // quirk (:201): a fixed divisor, not the utterance length
       nnet.SetTrainOptions(trn_opts);
       if (!crossvalidate) nnet.Propagate(*net_in, &nnet_out);
       else nnet.Feedforward(*net_in, &nnet_out);
-      xent.Eval(weights, nnet_out, targets, &obj_diff);
+      xent.Eval(b->weights, nnet_out, b->targets, &obj_diff);
+      feeder.Release(b);                                  // Xent::Eval has uploaded weights and targets
       if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
       num_done++;
       total_frames += net_in->NumRows();
@@ -114,6 +131,7 @@ int main(int argc, char* argv[]) {
         report_frames -= report_period;
       }
     }
+    feeder.Join();
     if (!crossvalidate) nnet.Write(target_model_filename, binary);
     KALDI_LOG << "Done " << num_done << " files, " << num_no_tgt_mat << " with no tgt_mats, " << num_other_error << " with other errors. "
               << "[" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", " << (randomize ? "RANDOMIZED" : "NOT-RANDOMIZED") << ", "

@@ -106,19 +106,19 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
       std::vector<int32> frame_num_utt;
       std::vector<std::string> keys;
       std::vector<std::vector<int32>> labels;
-      int32 num_valid_frame = 0, num_no_tgt = 0;
+      int32 num_valid_frame = 0;
       bool last = false;                              // the feature reader was exhausted when the group closed
     };
     std::vector<Matrix<BaseFloat>> feats_utt(num_stream);
     auto fill = [&](CtcBatch* b) -> bool {
       b->frame_num_utt.clear(); b->keys.clear(); b->labels.clear();
-      b->num_valid_frame = 0; b->num_no_tgt = 0;
+      b->num_valid_frame = 0;
       int32 sequence_index = 0, max_frame_num = 0;
       for (; !feature_reader.Done(); feature_reader.Next()) {
         const std::string utt = feature_reader.Key();
         if (!targets_reader.HasKey(utt)) {
           KALDI_WARN << utt << ", missing targets";
-          b->num_no_tgt++;
+          num_no_tgt_mat++;                          // owned by the feeder thread until feeder.Join()
           continue;
         }
         const Matrix<BaseFloat>& raw_mat = feature_reader.Value();
@@ -163,7 +163,6 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     while (CtcBatch* b = feeder.Next()) {
       const int32 cur_sequence_num = static_cast<int32>(b->frame_num_utt.size());
       const int32 num_valid_frame = b->num_valid_frame, batch_rows = b->feat.NumRows();
-      num_no_tgt_mat += b->num_no_tgt;
       net.SetSeqLengths(b->frame_num_utt);
       trn_opts.learn_rate = norm_lr / num_valid_frame;        // per-minibatch learn-rate normalisation (:177)
       net.SetTrainOptions(trn_opts);
@@ -196,6 +195,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
       }
       if (last) break;
     }
+    feeder.Join();
     if (worker) {
       // last partial period, then zero-frame syncs until every rank is out of data (termination protocol)
       if (!worker->IsAsync()) {

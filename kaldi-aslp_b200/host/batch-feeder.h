@@ -36,7 +36,10 @@ class BatchFeeder {
       thread_ = std::thread([this] { Run(); });
     }
   }
-  ~BatchFeeder() {
+  ~BatchFeeder() { Join(); }
+  // stops the feeder thread (after the fill() it may be in); what fill() wrote through captured references -- e.g. the
+  // skipped-utterance counters, which also count utterances skipped after the last delivered minibatch -- is then safe to read
+  void Join() {
     if (thread_.joinable()) {
       { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
       cv_.notify_all();

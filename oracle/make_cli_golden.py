@@ -187,7 +187,7 @@ def fsmn_case():
 
 
 def forward_cases():
-    """Forwarders: the unmodified reference aslp-nnet-forward / aslp-nnet-forward-blstm-lc on the models the trainer cases
+    """Forwarders: the unmodified reference aslp-nnet-forward / aslp-nnet-forward-blstm-lc / aslp-nnet-forward-skip on the models the trainer cases
     above wrote.  Each entry: (name, binary, model case, flags)."""
     d = os.path.join(GOLD, "cli_fwd")
     os.makedirs(d, exist_ok=True)
@@ -199,6 +199,9 @@ def forward_cases():
         ("lstm_shift", "aslp-nnet-forward", "cli_lstm", "--time-shift=2 --apply-log=false"),
         ("ctc_blank", "aslp-nnet-forward", "cli_ctc", "--add-softmax=true --scale-blank=0.5"),
         ("lc_chunks", "aslp-nnet-forward-blstm-lc", "cli_lc", "--chunk-size=8 --right-splice=3"),
+        ("skip_split3", "aslp-nnet-forward-skip", "cli_frame", "--skip-width=3"),
+        ("skip_lstm2", "aslp-nnet-forward-skip", "cli_lstm", "--skip-width=2 --apply-log=false --time-shift=1"),
+        ("skip_ctc4", "aslp-nnet-forward-skip", "cli_ctc", "--skip-width=4 --add-softmax=true --scale-blank=0.25"),
         ("lc_prior", "aslp-nnet-forward-blstm-lc", "cli_lc", "--chunk-size=8 --right-splice=3 --apply-log=false --no-softmax=true "
          "--class-frame-counts=%s" % os.path.join(d, "counts.txt")),
     ]
