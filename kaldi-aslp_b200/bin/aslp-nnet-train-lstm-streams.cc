@@ -1,6 +1,7 @@
 // aslp-nnet-train-lstm-streams -- multi-stream truncated-BPTT training of (projected) LSTMs with delayed targets, same
 // command line, batching (SequenceDataReader), bookkeeping and log lines as
 // src/aslp-nnetbin/aslp-nnet-train-lstm-streams.cc:24-240 (BASELINE config 2).
+#include "batch-feeder.h"
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
@@ -66,18 +67,35 @@ int main(int argc, char* argv[]) {
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     SequenceDataReader reader(feature_rspecifier, targets_rspecifier, read_opts);
     CuMatrix nnet_out, obj_diff, nnet_in;
-    Vector<BaseFloat> frame_mask;
-    Posterior nnet_tgt;
-    while (!reader.Done()) {
-      reader.ReadData(&nnet_in, &nnet_tgt, &frame_mask);
-      const std::vector<int32> new_utt_flags = reader.GetNewUttFlags();
+    // SequenceDataReader::ReadData on the feeder thread, into a page-locked slot (same stream bookkeeping, data-reader.cc:200-324)
+    struct SeqBatch {
+      PinnedMatrix feat;
+      bool has_feat = false;                          // false on the trailing all-masked minibatch: the previous features stay
+      Posterior tgt;
+      Vector<BaseFloat> frame_mask;
+      std::vector<int32> new_utt_flags;
+    };
+    auto fill = [&](SeqBatch* b) -> bool {
+      if (reader.Done()) return false;
+      b->has_feat = reader.ReadDataHost(&b->feat, &b->tgt, &b->frame_mask);
+      b->new_utt_flags = reader.GetNewUttFlags();
+      return true;
+    };
+    BatchFeeder<SeqBatch> feeder(fill, /*attach_device=*/false);
+    while (SeqBatch* b = feeder.Next()) {
+      const std::vector<int32> new_utt_flags = b->new_utt_flags;
       nnet.ResetLstmStreams(new_utt_flags);
+      if (b->has_feat) {
+        nnet_in.Resize(b->feat.NumRows(), b->feat.NumCols(), kUndefined);
+        nnet_in.CopyFromHost(b->feat.Data(), b->feat.Stride());       // asynchronous: the slot is page-locked
+      }
       if (!crossvalidate) nnet.Propagate(nnet_in, &nnet_out);
       else nnet.Feedforward(nnet_in, &nnet_out);
-      loss.Eval(frame_mask, nnet_out, nnet_tgt, &obj_diff);
-      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      loss.Eval(b->frame_mask, nnet_out, b->tgt, &obj_diff);
       int frame_progress = 0;
-      for (int32 i = 0; i < frame_mask.Dim(); i++) frame_progress += static_cast<int>(frame_mask(i));
+      for (int32 i = 0; i < b->frame_mask.Dim(); i++) frame_progress += static_cast<int>(b->frame_mask(i));
+      feeder.Release(b);                              // Xent::Eval has uploaded mask and targets
+      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
       total_frames += frame_progress;
       wopts.Progress(frame_progress);
       int num_done_progress = 0;
@@ -94,6 +112,7 @@ int main(int argc, char* argv[]) {
         nnet.Write(nnet_name, binary);
       }
     }
+    feeder.Join();
     wopts.Finish();
     if (!crossvalidate && wopts.WritesModel()) nnet.Write(target_model_filename, binary);
     KALDI_LOG << "Done " << num_done << " files, [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "

@@ -212,7 +212,14 @@ class SequenceDataReader {
   void ReadData(CuMatrix* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
     if (Done()) KALDI_ERR << "Already read done!";
     AddNewUtt();
-    FillBatchBuff(feat, target, frame_mask);
+    if (FillBatchBuff(&host_, target, frame_mask)) *feat = host_;
+  }
+  // the same minibatch into a page-locked host matrix (the batch feeder's slot); false: every stream is exhausted and
+  // `feat` was not written (the caller keeps its previous device matrix, as above)
+  bool ReadDataHost(PinnedMatrix* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
+    if (Done()) KALDI_ERR << "Already read done!";
+    AddNewUtt();
+    return FillBatchBuff(feat, target, frame_mask);
   }
  private:
   void AddNewUtt() {
@@ -250,17 +257,18 @@ class SequenceDataReader {
       }
     }
   }
-  void FillBatchBuff(CuMatrix* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
+  template <class HostMat>
+  bool FillBatchBuff(HostMat* host, Posterior* target, Vector<BaseFloat>* frame_mask) {
     const int32 num_stream = opts_.num_stream, batch_size = opts_.batch_size, delay = opts_.targets_delay;
     for (int32 s = 0; s < num_stream; s++) {
       if (curt_[s] < lent_[s]) { read_done_ = false; break; }
       read_done_ = true;
     }
     const int32 feat_dim = feats_[0].NumCols();
-    host_.Resize(batch_size * num_stream, feat_dim, kSetZero);
+    if (!read_done_) host->Resize(batch_size * num_stream, feat_dim, kSetZero);
     target->assign(batch_size * num_stream, Posterior::value_type());
     frame_mask->Resize(batch_size * num_stream);
-    if (read_done_) return;
+    if (read_done_) return false;
     for (int32 t = 0; t < batch_size; t++) {
       for (int32 s = 0; s < num_stream; s++) {
         const int32 row = t * num_stream + s;
@@ -268,11 +276,11 @@ class SequenceDataReader {
         if (curt_[s] < lent_[s]) { (*frame_mask)(row) = 1; (*target)[row] = targets_[s][curt_[s]]; }
         else { (*frame_mask)(row) = 0; (*target)[row] = targets_[s][lent_[s] - 1]; }
         const int32 src = (curt_[s] + delay < lent_[s]) ? curt_[s] + delay : lent_[s] - 1;    // shifted by the target delay, padded with the last frame
-        std::copy(feats_[s].RowData(src), feats_[s].RowData(src) + feat_dim, host_.RowData(row));
+        std::copy(feats_[s].RowData(src), feats_[s].RowData(src) + feat_dim, host->RowData(row));
         curt_[s]++;
       }
     }
-    *feat = host_;
+    return true;
   }
   SequenceDataReaderOptions opts_;
   bool read_done_;
