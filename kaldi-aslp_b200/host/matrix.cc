@@ -88,6 +88,22 @@ void PinnedMatrix::Resize(int32 rows, int32 cols, MatrixResizeType t) {
   r_ = rows; c_ = cols;
   if (t == kSetZero && n > 0) std::memset(d_, 0, n * sizeof(float));
 }
+void PinnedMatrix::AppendRows(const float* src, int32 rows, int32 cols) {
+  if (r_ == 0) c_ = cols;
+  KALDI_ASSERT(cols == c_);
+  const size_t have = static_cast<size_t>(r_) * c_, add = static_cast<size_t>(rows) * cols;
+  if (have + add > cap_) {
+    const size_t cap = (have + add) + (have + add) / 2 + 1024;
+    void* p = nullptr;
+    ASLP_OK(aslp_malloc_host(&p, cap * sizeof(float)));
+    if (have > 0) std::memcpy(p, d_, have * sizeof(float));
+    if (d_ != nullptr) ASLP_OK(aslp_free_host(d_));
+    d_ = static_cast<float*>(p);
+    cap_ = cap;
+  }
+  if (add > 0) std::memcpy(d_ + have, src, add * sizeof(float));
+  r_ += rows;
+}
 template <typename Real> static const char* MatTok() { return sizeof(Real) == 4 ? "FM" : "DM"; }
 template <typename Real> static const char* VecTok() { return sizeof(Real) == 4 ? "FV" : "DV"; }
 

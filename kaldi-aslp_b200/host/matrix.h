@@ -90,7 +90,8 @@ class PinnedMatrix {
   ~PinnedMatrix();
   PinnedMatrix(const PinnedMatrix&) = delete;
   PinnedMatrix& operator=(const PinnedMatrix&) = delete;
-  void Resize(int32 rows, int32 cols, MatrixResizeType t = kSetZero);   // grows geometrically, never shrinks
+  void Resize(int32 rows, int32 cols, MatrixResizeType t = kSetZero);   // grows geometrically, never shrinks; contents are NOT kept
+  void AppendRows(const float* src, int32 rows, int32 cols);            // keeps the contents (cols must match unless empty)
   int32 NumRows() const { return r_; }
   int32 NumCols() const { return c_; }
   int32 Stride() const { return c_; }

@@ -4,6 +4,7 @@
 #ifndef ASLP_HOST_NNET_RANDOMIZER_H_
 #define ASLP_HOST_NNET_RANDOMIZER_H_
 #include <cstdlib>
+#include "batch-feeder.h"
 #include "matrix.h"
 #include "nnet-loss.h"
 #include "parse-options.h"
@@ -134,7 +135,8 @@ typedef StdVectorRandomizer<std::vector<std::pair<int32, BaseFloat>>> PosteriorR
 class FrameDataReader {
  public:
   FrameDataReader(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const NnetDataRandomizerOptions& rand_opts)
-      : feature_reader_(feature_rspecifier), targets_reader_(targets_rspecifier), read_done_(false) {
+      : feature_reader_(feature_rspecifier), targets_reader_(targets_rspecifier), read_done_(false), conf_(rand_opts), sim_begin_(0),
+        sim_end_(0), sim_read_done_(false), feeder_([this](Block* b) { return FillBlock(b); }, /*attach_device=*/false) {
     feature_randomizer_.Init(rand_opts);
     targets_randomizer_.Init(rand_opts);
     randomizer_mask_.Init(rand_opts);
@@ -153,10 +155,24 @@ class FrameDataReader {
     return false;
   }
  private:
-  void FillRandomizer() {
+  // What one FillRandomizer call of the reference reads (data-reader.cc:118-160): the utterances up to the one that makes
+  // the randomizer full, or to the end of the table.  The feeder thread (batch-feeder.h) prepares the NEXT refill while the
+  // minibatches of the current one train: it replays the randomizer's begin / end arithmetic (which utterance closes a
+  // refill depends only on frame counts) and concatenates the utterances into one page-locked block, so a refill costs one
+  // H2D copy instead of one allocation + synchronous pageable copy per utterance.
+  struct Block {
+    PinnedMatrix feats;                    // rows of all utterances of the refill, in reading order
+    std::vector<int32> utt_rows;
+    std::vector<Posterior> targets;
+    bool read_done = false;
+  };
+  bool FillBlock(Block* b) {               // feeder thread
+    if (sim_read_done_) return false;
+    b->feats.Resize(0, 0, kUndefined);
+    b->utt_rows.clear(); b->targets.clear(); b->read_done = false;
     while (true) {
-      if (feature_randomizer_.IsFull()) break;
-      if (feature_reader_.Done()) { read_done_ = true; break; }
+      if (sim_begin_ == 0 && sim_end_ > conf_.randomizer_size) break;                       // MatrixRandomizer::IsFull
+      if (feature_reader_.Done()) { b->read_done = sim_read_done_ = true; break; }
       const std::string utt = feature_reader_.Key();
       if (!targets_reader_.HasKey(utt)) {
         KALDI_WARN << utt << ", missing targets";
@@ -164,12 +180,32 @@ class FrameDataReader {
         const Matrix<BaseFloat>& mat = feature_reader_.Value();
         const Posterior& targets = targets_reader_.Value(utt);
         if (static_cast<int32>(targets.size()) != mat.NumRows()) KALDI_ERR << "feature and target dim must match";
-        CuMatrix dev; dev = mat;
-        feature_randomizer_.AddData(dev);
-        targets_randomizer_.AddData(targets);
+        b->feats.AppendRows(mat.Data(), mat.NumRows(), mat.NumCols());
+        b->utt_rows.push_back(mat.NumRows());
+        b->targets.push_back(targets);
+        if (sim_begin_ > 0) { sim_end_ -= sim_begin_; sim_begin_ = 0; }                     // AddData: the leftover moves to the front
+        sim_end_ += mat.NumRows();
       }
       feature_reader_.Next();
     }
+    while (sim_end_ - sim_begin_ >= conf_.minibatch_size) sim_begin_ += conf_.minibatch_size;   // the minibatches of this refill
+    return true;
+  }
+  void FillRandomizer() {
+    Block* b = feeder_.Next();
+    KALDI_ASSERT(b != nullptr);
+    if (b->feats.NumRows() > 0) {
+      block_dev_.Resize(b->feats.NumRows(), b->feats.NumCols(), kUndefined);
+      block_dev_.CopyFromHost(b->feats.Data(), b->feats.Stride());                          // asynchronous: the block is page-locked
+    }
+    int32 row = 0;
+    for (size_t i = 0; i < b->utt_rows.size(); ++i) {                                       // the same AddData sequence as utterance by utterance
+      feature_randomizer_.AddData(block_dev_.RowRange(row, b->utt_rows[i]));
+      targets_randomizer_.AddData(b->targets[i]);
+      row += b->utt_rows[i];
+    }
+    if (b->read_done) read_done_ = true;
+    feeder_.Release(b);
     const std::vector<int32>& mask = randomizer_mask_.Generate(feature_randomizer_.NumFrames());
     feature_randomizer_.Randomize(mask);
     targets_randomizer_.Randomize(mask);
@@ -180,6 +216,11 @@ class FrameDataReader {
   PosteriorRandomizer targets_randomizer_;
   RandomizerMask randomizer_mask_;
   bool read_done_;
+  NnetDataRandomizerOptions conf_;
+  int32 sim_begin_, sim_end_;              // the feeder thread's replay of the randomizer's data_begin_ / data_end_
+  bool sim_read_done_;
+  CuMatrix block_dev_;
+  BatchFeeder<Block> feeder_;              // last member: its thread uses everything above
 };
 
 
