@@ -121,12 +121,12 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, threads=None):
     """The reference's own CPU implementation of the path on the host cores (oracle/_ref)."""
     if rank != 0:
         return None
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     t_sample = 200                                  # frames per utterance in one reference step (bounded sample: 1/5 of T)
     cfg = workload_config(args.gpus)
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -168,6 +168,13 @@ def cpu_baseline_leg():
         gpus, steps, warmup = 1, 2, 1
     r = run_reference(A, 0, 1)
     cb = r["cpu_baseline"]
+    # also with OPENBLAS_NUM_THREADS=1 (the reference's pointwise code and its warp-ctc call are single-threaded anyway)
+    class B:
+        gpus, steps, warmup = 1, 1, 1
+    try:
+        cb["single_thread"] = {"value": run_reference(B, 0, 1, threads=1)["cpu_baseline"]["value"], "unit": UNIT, "cores": 1}
+    except Exception as e:  # the baseline is a reported figure: never fail the bench line over it
+        cb["single_thread"] = {"value": None, "error": str(e)[:200]}
     return cb
 
 
