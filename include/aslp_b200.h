@@ -159,6 +159,24 @@ int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int l
                 const float* out_diff, int ldo, int rows, int cols, const float* scale,
                 const float* mean, const float* inv_std, float momentum, float* dscale, float* dshift);
 
+/* ---- ConvolutionalComponent / MaxPoolingComponent (src/aslp-nnet/nnet-convolutional-component.h:263-421,
+ * nnet-max-pooling-component.h:100-156) ----
+ * gather : patches[(b*num_patches + p)*ldp + s*patch_dim + d] = in[b*ldi + p*patch_step + s*patch_stride + d]
+ *          (replaces column_map + CopyCols; with this layout the per-patch AddMatMat loop is ONE aslp_gemm:
+ *          [rows*num_patches, filter_dim] x filters^T -> out viewed as [rows*num_patches, num_filters])
+ * scatter: in_diff[b, c] = sum over the patch positions that read column c, in ascending p (replaces ReverseIndexes /
+ *          RearrangeIndexes / AddCols); in_diff is overwritten
+ * maxpool fwd: out[b, q*S + j] = max(-1e20, max_{r<pool_size} in[b, (q*pool_step + r)*S + j]),  S = pool_stride
+ * maxpool bwd: in_diff[b, p*S + j] = (sum_q [in == out_q] * out_diff_q) / #pools containing patch p */
+int aslp_conv_gather_patches(aslp_stream_t s, float* patches, int ldp, const float* in, int ldi, int rows, int num_patches, int num_splice,
+                             int patch_dim, int patch_step, int patch_stride);
+int aslp_conv_scatter_patch_diffs(aslp_stream_t s, float* in_diff, int ldd, const float* patch_diffs, int ldp, int rows, int num_patches,
+                                  int num_splice, int patch_dim, int patch_step, int patch_stride);
+int aslp_maxpool_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int num_pools, int pool_size, int pool_step,
+                     int pool_stride);
+int aslp_maxpool_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int ldi, const float* out, int ldo, const float* out_diff,
+                     int ldod, int rows, int num_patches, int num_pools, int pool_size, int pool_step, int pool_stride);
+
 /* ---- CompactFsmn memory block (src/aslp-nnet/nnet-cfsmn-component.h:169-264) ----
  * fwd : out[t,d] = in[t,d] + sum_{c=0}^{P+F} coef[c,d] * in[t+c-P, d]        (zero outside [0,T))
  * bwd : in_diff[t,d] = out_diff[t,d] + sum_c coef[P+F-c, d] * out_diff[t+c-F, d]

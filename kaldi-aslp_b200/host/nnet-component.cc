@@ -2,6 +2,7 @@
 #include <algorithm>
 #include "nnet-activation.h"
 #include "nnet-affine-transform.h"
+#include "nnet-conv-pool.h"
 #include "nnet-gru-streams.h"
 #include "nnet-lstm-family.h"
 #include "nnet-misc-components.h"
@@ -32,6 +33,8 @@ const struct Component::key_value Component::kMarkerMap[] = {
     {Component::kBLstmProjectedStreamsLC, "<BLstmProjectedStreamsLC>"},
     {Component::kGruStreams, "<GruStreams>"},
     {Component::kCompactFsmn, "<CompactFsmn>"},
+    {Component::kConvolutionalComponent, "<ConvolutionalComponent>"},
+    {Component::kMaxPoolingComponent, "<MaxPoolingComponent>"},
 };
 static const int kNumMarkers = sizeof(Component::kMarkerMap) / sizeof(Component::kMarkerMap[0]);
 
@@ -74,6 +77,8 @@ Component* Component::NewComponentOfType(ComponentType t, int32 in, int32 out) {
     case kBLstmProjectedStreamsLC: return new BLstmProjectedStreamsLC(in, out);
     case kGruStreams: return new GruStreams(in, out);
     case kCompactFsmn: return new CompactFsmn(in, out);
+    case kConvolutionalComponent: return new ConvolutionalComponent(in, out);
+    case kMaxPoolingComponent: return new MaxPoolingComponent(in, out);
     default: KALDI_ERR << "Missing type: " << static_cast<int>(t);
   }
   return NULL;

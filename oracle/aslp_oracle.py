@@ -589,3 +589,84 @@ def ctc_eesen(probs, labels, seq_len, T, S):
     row_sum = err.sum(axis=1, dtype=F)
     diff = (err - probs * row_sum[:, None]).astype(F)
     return pzx, diff
+
+
+# ---------------------------------------------------------------- ConvolutionalComponent / MaxPoolingComponent
+def conv_column_map(in_dim, patch_dim, patch_step, patch_stride):
+    """column_map_ of ConvolutionalComponent::PropagateFnc, src/aslp-nnet/nnet-convolutional-component.h:289-297."""
+    num_splice = in_dim // patch_stride
+    num_patches = 1 + (patch_stride - patch_dim) // patch_step
+    return np.array([p * patch_step + s * patch_stride + d for p in range(num_patches) for s in range(num_splice) for d in range(patch_dim)],
+                    np.int64), num_patches, num_splice * patch_dim
+
+
+def conv_fwd(x, filters, bias, patch_dim, patch_step, patch_stride):
+    """CopyCols + per-patch AddVecToRows / AddMatMat (:298-306).  Returns (out, vectorized_feature_patches)."""
+    x = np.asarray(x, F)
+    cmap, npatch, fd = conv_column_map(x.shape[1], patch_dim, patch_step, patch_stride)
+    vec = x[:, cmap]
+    nf = filters.shape[0]
+    out = np.zeros((x.shape[0], npatch * nf), F)
+    for p in range(npatch):
+        out[:, p * nf:(p + 1) * nf] = bias[None, :] + vec[:, p * fd:(p + 1) * fd] @ filters.T
+    return out.astype(F), vec
+
+
+def conv_bwd(out_diff, filters, in_dim, patch_dim, patch_step, patch_stride):
+    """per-patch AddMatMat into feature_patch_diffs_, then AddCols over the rearranged reverse map (:377-400): every input
+    column adds its patch positions in ascending order of the forward index."""
+    out_diff = np.asarray(out_diff, F)
+    cmap, npatch, fd = conv_column_map(in_dim, patch_dim, patch_step, patch_stride)
+    nf = filters.shape[0]
+    pd = np.zeros((out_diff.shape[0], npatch * fd), F)
+    for p in range(npatch):
+        pd[:, p * fd:(p + 1) * fd] = out_diff[:, p * nf:(p + 1) * nf] @ filters
+    in_diff = np.zeros((out_diff.shape[0], in_dim), F)
+    for j, c in enumerate(cmap):                     # ascending j == the order of the AddCols passes for a given column
+        in_diff[:, c] = in_diff[:, c] + pd[:, j]
+    return in_diff, pd
+
+
+def conv_grads(out_diff, vec, num_filters):
+    """Update (:403-421): gradients summed over the patch positions."""
+    npatch = out_diff.shape[1] // num_filters
+    fd = vec.shape[1] // npatch
+    fg = np.zeros((num_filters, fd), np.float64)
+    bg = np.zeros(num_filters, np.float64)
+    for p in range(npatch):
+        dp = out_diff[:, p * num_filters:(p + 1) * num_filters].astype(np.float64)
+        fg += dp.T @ vec[:, p * fd:(p + 1) * fd].astype(np.float64)
+        bg += dp.sum(axis=0)
+    return fg.astype(F), bg.astype(F)
+
+
+def maxpool_fwd(x, pool_size, pool_step, pool_stride):
+    """MaxPoolingComponent::PropagateFnc, src/aslp-nnet/nnet-max-pooling-component.h:100-114."""
+    x = np.asarray(x, F)
+    num_patches = x.shape[1] // pool_stride
+    num_pools = 1 + (num_patches - pool_size) // pool_step
+    out = np.full((x.shape[0], num_pools * pool_stride), F(-1e20), F)
+    for q in range(num_pools):
+        for r in range(pool_size):
+            p = r + q * pool_step
+            out[:, q * pool_stride:(q + 1) * pool_stride] = np.maximum(out[:, q * pool_stride:(q + 1) * pool_stride],
+                                                                       x[:, p * pool_stride:(p + 1) * pool_stride])
+    return out
+
+
+def maxpool_bwd(x, out, out_diff, pool_size, pool_step, pool_stride):
+    """BackpropagateFnc (:116-156): equality mask per (pool, member), summed, scaled by 1 / #pools containing the patch."""
+    x, out, out_diff = np.asarray(x, F), np.asarray(out, F), np.asarray(out_diff, F)
+    num_patches = x.shape[1] // pool_stride
+    num_pools = 1 + (num_patches - pool_size) // pool_step
+    in_diff = np.zeros_like(x)
+    summands = [0] * num_patches
+    for q in range(num_pools):
+        for r in range(pool_size):
+            p = r + q * pool_step
+            sl_p, sl_q = slice(p * pool_stride, (p + 1) * pool_stride), slice(q * pool_stride, (q + 1) * pool_stride)
+            in_diff[:, sl_p] = in_diff[:, sl_p] + out_diff[:, sl_q] * (x[:, sl_p] == out[:, sl_q]).astype(F)
+            summands[p] += 1
+    for p in range(num_patches):
+        in_diff[:, p * pool_stride:(p + 1) * pool_stride] *= F(1.0 / summands[p])
+    return in_diff

@@ -157,6 +157,19 @@ def read_nnet(path):
         elif t == "RowConvolution":
             assert s.token() == "<FutureContext>"; c["future"] = s.int32()
             c["w"] = s.mat()
+        elif t == "ConvolutionalComponent":      # nnet-convolutional-component.h:199-221
+            assert s.token() == "<PatchDim>"; c["patch_dim"] = s.int32()
+            assert s.token() == "<PatchStep>"; c["patch_step"] = s.int32()
+            assert s.token() == "<PatchStride>"; c["patch_stride"] = s.int32()
+            assert s.token() == "<LearnRateCoef>"; c["lr_coef"] = s.float32()
+            assert s.token() == "<BiasLearnRateCoef>"; c["bias_lr_coef"] = s.float32()
+            assert s.token() == "<MaxNorm>"; c["max_norm"] = s.float32()
+            assert s.token() == "<Filters>"; c["filters"] = s.mat()
+            assert s.token() == "<Bias>"; c["bias"] = s.vec()
+        elif t == "MaxPoolingComponent":         # nnet-max-pooling-component.h:91-98
+            assert s.token() == "<PoolSize>"; c["pool_size"] = s.int32()
+            assert s.token() == "<PoolStep>"; c["pool_step"] = s.int32()
+            assert s.token() == "<PoolStride>"; c["pool_stride"] = s.int32()
         elif t in ("Softmax", "Sigmoid", "Tanh", "ReLU", "InputLayer", "OutputLayer"):
             pass
         else:

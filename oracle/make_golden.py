@@ -32,6 +32,21 @@ CASES = {
                "<AffineTransform> <InputDim> 20 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.2",
                "<Softmax> <InputDim> 8 <OutputDim> 8"],
         dim=12, rows=16, loss="xent", spec=dict(learn_rate=0.05, momentum=0.5, l2=0.001, l1=0.0005, iters=2)),
+    "cnn_xent": dict(           # Conv (8 patch positions x 8 filters, dense single-GEMM view) + overlapping max pooling
+        proto=["<ConvolutionalComponent> <InputDim> 33 <OutputDim> 64 <PatchDim> 4 <PatchStep> 1 <PatchStride> 11 <BiasMean> -0.5 <BiasRange> 1.0 <ParamStddev> 0.3",
+               "<MaxPoolingComponent> <InputDim> 64 <OutputDim> 24 <PoolSize> 4 <PoolStep> 2 <PoolStride> 8",
+               "<Sigmoid> <InputDim> 24 <OutputDim> 24",
+               "<AffineTransform> <InputDim> 24 <OutputDim> 5 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
+               "<Softmax> <InputDim> 5 <OutputDim> 5"],
+        dim=33, rows=20, loss="xent", spec=dict(learn_rate=0.1, momentum=0.9, iters=2, dump_components=1)),
+    "cnn_odd_maxnorm": dict(    # 7 x 5 = 35 output columns (not a multiple of 4: the per-patch form), max-norm, lr coefficients
+        proto=["<ConvolutionalComponent> <InputDim> 30 <OutputDim> 35 <PatchDim> 4 <PatchStep> 1 <PatchStride> 10 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.4 "
+               "<LearnRateCoef> 0.7 <BiasLearnRateCoef> 1.5 <MaxNorm> 0.9",
+               "<MaxPoolingComponent> <InputDim> 35 <OutputDim> 15 <PoolSize> 3 <PoolStep> 2 <PoolStride> 5",
+               "<Tanh> <InputDim> 15 <OutputDim> 15",
+               "<AffineTransform> <InputDim> 15 <OutputDim> 4 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
+               "<Softmax> <InputDim> 4 <OutputDim> 4"],
+        dim=30, rows=13, loss="xent", spec=dict(learn_rate=0.2, momentum=0.5, iters=3, dump_components=1)),
     "lstm_xent": dict(
         proto=["<Lstm> <InputDim> 10 <OutputDim> 16 <ClipGradient> 5 <ParamScale> 0.2",
                "<AffineTransform> <InputDim> 16 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
@@ -99,7 +114,10 @@ def main():
     if not os.path.exists(DRIVER):
         raise SystemExit("build oracle/_ref first: make -C oracle")
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    only = sys.argv[1:]                       # optional: regenerate just the named cases
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         d = os.path.join(GOLD, name)
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)

@@ -330,3 +330,56 @@ def test_posterior_finalize(rows, cols, apply_log, blank, prior):
     assert s[0] == x.min() and s[1] == x.max()
     assert abs(s[2] - mid.min()) < 1e-5 * max(1.0, abs(mid.min())) and abs(s[3] - mid.max()) < 1e-5
     assert s[4] == 0
+
+
+@pytest.mark.parametrize("rows,ns,stride,pd,step,nf", [(256, 11, 40, 9, 1, 128), (37, 3, 11, 4, 1, 6), (50, 2, 12, 4, 2, 5), (9, 1, 8, 8, 1, 3)])
+def test_conv_gather_gemm_scatter(rows, ns, stride, pd, step, nf):
+    """ConvolutionalComponent device side (nnet-convolutional-component.h:263-421): im2col into [frames*P, filter_dim], ONE GEMM
+    into the [frames, P*num_filters] output, and the inverse gather-sum; the first shape is the recipes' 40 x 11 input."""
+    from tests.gpu_utils import DMat, dvec, lib, ok, ptr, stream, sync
+    rng = np.random.default_rng(rows + nf)
+    in_dim = ns * stride
+    npatch, fd = 1 + (stride - pd) // step, ns * pd
+    x = rng.standard_normal((rows, in_dim)).astype(np.float32)
+    filt = (rng.standard_normal((nf, fd)) * 0.2).astype(np.float32)
+    bias = rng.standard_normal(nf).astype(np.float32)
+    want_out, want_vec = O.conv_fwd(x, filt, bias, pd, step, stride)
+    dx, dpat, dfilt = DMat(x), DMat(rows=rows * npatch, cols=fd), DMat(filt)
+    ok(lib().aslp_conv_gather_patches(stream(), dpat.ptr, dpat.ld, dx.ptr, dx.ld, rows, npatch, ns, pd, step, stride))
+    sync()
+    assert np.array_equal(dpat.np().reshape(rows, npatch * fd), want_vec)             # a pure gather: bit-exact
+    import torch
+    out = torch.zeros((rows * npatch, nf), dtype=torch.float32, device="cuda")       # dense view of [rows, P*nf]
+    db = dvec(bias)
+    ok(lib().aslp_gemm(stream(), 0, 1, rows * npatch, nf, fd, 1.0, dpat.ptr, dpat.ld, dfilt.ptr, dfilt.ld, 0.0, ptr(out), nf, ptr(db), 0.0, 0, None, 0))
+    sync()
+    got_out = out.cpu().numpy().reshape(rows, npatch * nf)
+    assert np.abs(got_out - want_out).max() < 1e-4 * max(1.0, np.abs(want_out).max())
+    od = (rng.standard_normal((rows, npatch * nf)) * 0.1).astype(np.float32)
+    want_in, want_pd = O.conv_bwd(od, filt, in_dim, pd, step, stride)
+    dpd = DMat(want_pd.reshape(rows * npatch, fd))
+    din = DMat(rows=rows, cols=in_dim, fill=7.0)                                       # overwritten, not accumulated
+    ok(lib().aslp_conv_scatter_patch_diffs(stream(), din.ptr, din.ld, dpd.ptr, dpd.ld, rows, npatch, ns, pd, step, stride))
+    sync()
+    assert np.array_equal(din.np(), want_in)                                           # same summation order: bit-exact
+
+
+@pytest.mark.parametrize("rows,patches,size,step,ps", [(256, 32, 4, 4, 128), (40, 8, 4, 2, 6), (13, 7, 3, 2, 5), (5, 4, 4, 1, 3)])
+def test_maxpool_fwd_bwd(rows, patches, size, step, ps):
+    """MaxPoolingComponent (nnet-max-pooling-component.h:100-156), overlapping pools and ties included."""
+    from tests.gpu_utils import DMat, lib, ok, stream, sync
+    rng = np.random.default_rng(rows * 7 + ps)
+    pools = 1 + (patches - size) // step
+    x = rng.standard_normal((rows, patches * ps)).astype(np.float32)
+    x[::3, :] = np.round(x[::3, :])                                                    # ties: several members equal the maximum
+    want = O.maxpool_fwd(x, size, step, ps)
+    dx, dout = DMat(x), DMat(rows=rows, cols=pools * ps)
+    ok(lib().aslp_maxpool_fwd(stream(), dout.ptr, dout.ld, dx.ptr, dx.ld, rows, pools, size, step, ps))
+    sync()
+    assert np.array_equal(dout.np(), want)
+    od = rng.standard_normal((rows, pools * ps)).astype(np.float32)
+    want_in = O.maxpool_bwd(x, want, od, size, step, ps)
+    dod, din = DMat(od), DMat(rows=rows, cols=patches * ps, fill=3.0)
+    ok(lib().aslp_maxpool_bwd(stream(), din.ptr, din.ld, dx.ptr, dx.ld, dout.ptr, dout.ld, dod.ptr, dod.ld, rows, patches, pools, size, step, ps))
+    sync()
+    assert np.array_equal(din.np(), want_in)
