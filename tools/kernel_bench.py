@@ -126,6 +126,36 @@ def cases():
                 (x, dy, dx, sc, mean, istd, ds, dsh))
     cs.append(Case("bn_bwd", "%dx%d" % (R, D), 16 * R * D, 12 * R * D, mk_bnb))
 
+    # ---- CNN front end of the CTC recipes (run_ctc_cnn_1dnn_2blstm.sh:67-68): 40 x 11 spliced input, 9-wide patches -> 32 positions x 128
+    # filters, pooled 4:1.  Algorithmic bytes: gather reads the input once and writes the patches; scatter reads the patch
+    # derivatives once and writes the input derivative; pooling reads / writes every operand once.
+    Rc, NSc, STc, PDc, NPc, NFc = 16384, 11, 40, 9, 32, 128
+    FDc = NSc * PDc
+    LDP = (FDc + 3) // 4 * 4
+    def mk_cg(i):
+        x = torch.randn(Rc, NSc * STc, **f32); pt = torch.empty(Rc * NPc, LDP, **f32)
+        return lambda: K.check(L.aslp_conv_gather_patches(stream(), p(pt), LDP, p(x), NSc * STc, Rc, NPc, NSc, PDc, 1, STc)), (x, pt)
+    cs.append(Case("conv_gather", "%dx%d->%dx%d" % (Rc, NSc * STc, Rc * NPc, FDc), 4 * Rc * (NSc * STc + NPc * FDc), 4 * Rc * (NSc * STc + NPc * LDP), mk_cg))
+
+    def mk_csc(i):
+        pt = torch.randn(Rc * NPc, LDP, **f32); d = torch.empty(Rc, NSc * STc, **f32)
+        return lambda: K.check(L.aslp_conv_scatter_patch_diffs(stream(), p(d), NSc * STc, p(pt), LDP, Rc, NPc, NSc, PDc, 1, STc)), (pt, d)
+    cs.append(Case("conv_scatter", "%dx%d->%dx%d" % (Rc * NPc, FDc, Rc, NSc * STc), 4 * Rc * (NSc * STc + NPc * FDc), 4 * Rc * (NSc * STc + NPc * LDP), mk_csc))
+
+    PSZ, NPO = 4, 8                                  # 32 positions -> 8 pools of 4, stride = 128 filters
+    def mk_mp(i):
+        x = torch.randn(Rc, NPc * NFc, **f32); o = torch.empty(Rc, NPO * NFc, **f32)
+        return lambda: K.check(L.aslp_maxpool_fwd(stream(), p(o), NPO * NFc, p(x), NPc * NFc, Rc, NPO, PSZ, PSZ, NFc)), (x, o)
+    cs.append(Case("maxpool_fwd", "%dx%d->%d" % (Rc, NPc * NFc, NPO * NFc), 4 * Rc * NFc * (NPc + NPO), 4 * Rc * NFc * (NPc + NPO), mk_mp))
+
+    def mk_mpb(i):
+        x = torch.randn(Rc, NPc * NFc, **f32); o = torch.empty(Rc, NPO * NFc, **f32); od = torch.randn(Rc, NPO * NFc, **f32)
+        d = torch.empty(Rc, NPc * NFc, **f32)
+        K.check(L.aslp_maxpool_fwd(stream(), p(o), NPO * NFc, p(x), NPc * NFc, Rc, NPO, PSZ, PSZ, NFc))
+        return (lambda: K.check(L.aslp_maxpool_bwd(stream(), p(d), NPc * NFc, p(x), NPc * NFc, p(o), NPO * NFc, p(od), NPO * NFc, Rc, NPc, NPO, PSZ, PSZ, NFc)),
+                (x, o, od, d))
+    cs.append(Case("maxpool_bwd", "%dx%d" % (Rc, NPc * NFc), 4 * Rc * NFc * (2 * NPc + 2 * NPO), 4 * Rc * NFc * (2 * NPc + 2 * NPO), mk_mpb))
+
     # ---- Splice: 40-dim, offsets -5..5 (cfg1 front end), one randomizer block of frames
     Rs, Ds, NO = 262144, 40, 11
     def mk_sp(i):
