@@ -194,6 +194,14 @@ class FrameDataReader {
   void FillRandomizer() {
     Block* b = feeder_.Next();
     KALDI_ASSERT(b != nullptr);
+    if (b->utt_rows.empty() && b->read_done) {
+      // The table ended exactly at the previous refill's boundary: nothing to add, and less than one minibatch is left over.
+      // The reference runs Randomize() here and dies on its data_begin_ == 0 assertion (nnet-randomizer.cc:70); this build
+      // ends the epoch instead (Done() is now true).
+      read_done_ = true;
+      feeder_.Release(b);
+      return;
+    }
     if (b->feats.NumRows() > 0) {
       block_dev_.Resize(b->feats.NumRows(), b->feats.NumCols(), kUndefined);
       block_dev_.CopyFromHost(b->feats.Data(), b->feats.Stride());                          // asynchronous: the block is page-locked
