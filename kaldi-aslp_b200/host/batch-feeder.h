@@ -26,9 +26,11 @@ template <class Batch>
 class BatchFeeder {
  public:
   typedef std::function<bool(Batch*)> FillFn;
-  // attach_device: the feeder thread launches device work of its own (a feature transform) and needs a stream
-  BatchFeeder(FillFn fill, bool attach_device)
-      : fill_(fill), attach_(attach_device), depth_(Depth()), done_(false), stop_(false) {
+  // attach_device: the feeder thread launches device work of its own (a feature transform) and needs a stream.
+  // track_copies = false: Release() hands the slot straight back (the consumer made no asynchronous device copy out of it;
+  // also what the host-only unit test of the hand-over logic uses, tests/test_cpu_batch_feeder.py)
+  BatchFeeder(FillFn fill, bool attach_device, bool track_copies = true)
+      : fill_(fill), attach_(attach_device), track_(track_copies), depth_(Depth()), done_(false), stop_(false) {
     const int n = depth_ > 0 ? depth_ : 1;
     for (int i = 0; i < n; ++i) slots_.emplace_back(new Slot());
     if (depth_ > 0) {
@@ -67,8 +69,10 @@ class BatchFeeder {
   // refilled only after that copy has completed on the device
   void Release(Batch* b) {
     Slot* s = FindSlot(b);
-    ASLP_OK(aslp_event_record(CuStream(), &s->copied));
-    s->pending = true;
+    if (track_) {
+      ASLP_OK(aslp_event_record(CuStream(), &s->copied));
+      s->pending = true;
+    }
     if (depth_ == 0) return;
     { std::lock_guard<std::mutex> lk(mu_); free_.push_back(s); }
     cv_.notify_all();
@@ -126,7 +130,7 @@ class BatchFeeder {
   }
 
   FillFn fill_;
-  bool attach_;
+  bool attach_, track_;
   int depth_;
   std::vector<std::unique_ptr<Slot>> slots_;
   std::deque<Slot*> free_, ready_;
