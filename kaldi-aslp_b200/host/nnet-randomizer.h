@@ -132,11 +132,26 @@ class StdVectorRandomizer {
 typedef StdVectorRandomizer<std::vector<std::pair<int32, BaseFloat>>> PosteriorRandomizer;
 
 // features + frame targets -> shuffled minibatches (data-reader.cc:62-182)
+// The begin / end arithmetic of MatrixRandomizer / StdVectorRandomizer without the data (nnet-randomizer.cc:60-134): which
+// utterance closes a refill depends only on frame counts, so the batch feeder can group the utterances of the NEXT refill
+// while the minibatches of the current one train.  tests/test_cpu_batch_feeder.py replays random tables against the real
+// StdVectorRandomizer.
+struct RandomizerReplay {
+  int32 begin, end, randomizer_size, minibatch_size;
+  RandomizerReplay(int32 randomizer_size_, int32 minibatch_size_) : begin(0), end(0), randomizer_size(randomizer_size_), minibatch_size(minibatch_size_) {}
+  bool IsFull() const { return begin == 0 && end > randomizer_size; }
+  void AddData(int32 rows) {
+    if (begin > 0) { end -= begin; begin = 0; }          // the leftover moves to the front
+    end += rows;
+  }
+  void ConsumeMinibatches() { while (end - begin >= minibatch_size) begin += minibatch_size; }     // Done() / Next() until used up
+};
+
 class FrameDataReader {
  public:
   FrameDataReader(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const NnetDataRandomizerOptions& rand_opts)
-      : feature_reader_(feature_rspecifier), targets_reader_(targets_rspecifier), read_done_(false), conf_(rand_opts), sim_begin_(0),
-        sim_end_(0), sim_read_done_(false), feeder_([this](Block* b) { return FillBlock(b); }, /*attach_device=*/false) {
+      : feature_reader_(feature_rspecifier), targets_reader_(targets_rspecifier), read_done_(false), sim_(rand_opts.randomizer_size, rand_opts.minibatch_size),
+        sim_read_done_(false), feeder_([this](Block* b) { return FillBlock(b); }, /*attach_device=*/false) {
     feature_randomizer_.Init(rand_opts);
     targets_randomizer_.Init(rand_opts);
     randomizer_mask_.Init(rand_opts);
@@ -171,7 +186,7 @@ class FrameDataReader {
     b->feats.Resize(0, 0, kUndefined);
     b->utt_rows.clear(); b->targets.clear(); b->read_done = false;
     while (true) {
-      if (sim_begin_ == 0 && sim_end_ > conf_.randomizer_size) break;                       // MatrixRandomizer::IsFull
+      if (sim_.IsFull()) break;
       if (feature_reader_.Done()) { b->read_done = sim_read_done_ = true; break; }
       const std::string utt = feature_reader_.Key();
       if (!targets_reader_.HasKey(utt)) {
@@ -183,12 +198,11 @@ class FrameDataReader {
         b->feats.AppendRows(mat.Data(), mat.NumRows(), mat.NumCols());
         b->utt_rows.push_back(mat.NumRows());
         b->targets.push_back(targets);
-        if (sim_begin_ > 0) { sim_end_ -= sim_begin_; sim_begin_ = 0; }                     // AddData: the leftover moves to the front
-        sim_end_ += mat.NumRows();
+        sim_.AddData(mat.NumRows());
       }
       feature_reader_.Next();
     }
-    while (sim_end_ - sim_begin_ >= conf_.minibatch_size) sim_begin_ += conf_.minibatch_size;   // the minibatches of this refill
+    sim_.ConsumeMinibatches();                 // the minibatches of this refill
     return true;
   }
   void FillRandomizer() {
@@ -224,8 +238,7 @@ class FrameDataReader {
   PosteriorRandomizer targets_randomizer_;
   RandomizerMask randomizer_mask_;
   bool read_done_;
-  NnetDataRandomizerOptions conf_;
-  int32 sim_begin_, sim_end_;              // the feeder thread's replay of the randomizer's data_begin_ / data_end_
+  RandomizerReplay sim_;                   // the feeder thread's replay of the randomizer's data_begin_ / data_end_
   bool sim_read_done_;
   CuMatrix block_dev_;
   BatchFeeder<Block> feeder_;              // last member: its thread uses everything above
