@@ -57,7 +57,7 @@ int main(int argc, char* argv[]) {
     int64 tot_t = 0;
     SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
     BaseFloatMatrixWriter feature_writer(feature_wspecifier);
-    CuMatrix feats, feats_transf, nnet_in, nnet_out, nnet_out_chunk;
+    CuMatrix<BaseFloat> feats, feats_transf, nnet_in, nnet_out, nnet_out_chunk;
     Matrix<BaseFloat> nnet_out_host;
     const int32 feat_dim = nnet.InputDim(), out_dim = nnet.OutputDim();
     Timer time;
@@ -70,7 +70,7 @@ int main(int argc, char* argv[]) {
       for (int32 r = 0; r < mat.NumRows(); r++) for (int32 c = 0; c < mat.NumCols(); c++) sum += mat.RowData(r)[c];
       if (!KALDI_ISFINITE(sum)) KALDI_ERR << "NaN or inf found in features for " << utt;
       feats = mat;
-      const CuMatrixBase* net_in = &feats;
+      const CuMatrixBase<BaseFloat>* net_in = &feats;
       if (nnet_transf.NumComponents() > 0) {
         nnet_transf.Feedforward(feats, &feats_transf);
         if (!KALDI_ISFINITE(feats_transf.Sum())) KALDI_ERR << "NaN or inf found in transformed-features for " << utt;

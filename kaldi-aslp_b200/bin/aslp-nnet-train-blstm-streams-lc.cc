@@ -111,7 +111,7 @@ int main(int argc, char* argv[]) {
     std::vector<Posterior> targets(num_stream);
     std::vector<int32> curt(num_stream, 0), lent(num_stream, 0);
     const int32 feat_dim = nnet.InputDim();
-    CuMatrix feat_dev, nnet_out, obj_diff;
+    CuMatrix<BaseFloat> feat_dev, nnet_out, obj_diff;
 
     // One chunk minibatch, built by the feeder thread with the reference's own stream bookkeeping (:185-268): streams whose
     // utterance is used up take the next readable one, then batch_size rows per stream are packed into a page-locked slot.
@@ -121,7 +121,7 @@ int main(int argc, char* argv[]) {
       Posterior target;
       std::vector<int32> new_utt_flags;
     };
-    CuMatrix transf_in, transf_out;                 // the feeder thread's own device buffers (its stream)
+    CuMatrix<BaseFloat> transf_in, transf_out;                 // the feeder thread's own device buffers (its stream)
     auto fill = [&](LcBatch* b) -> bool {
       b->new_utt_flags.assign(num_stream, 0);
       for (int32 s = 0; s < num_stream; s++) {

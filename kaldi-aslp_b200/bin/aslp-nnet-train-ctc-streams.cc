@@ -6,9 +6,9 @@ namespace {
 struct EesenCtcAdapter {
   kaldi::aslp_nnet::Ctc c;
   void SetReportStep(int s) { c.SetReportStep(s); }
-  void Eval(const std::vector<std::string>& k, const std::vector<kaldi::int32>& f, const kaldi::CuMatrixBase& o,
-            std::vector<std::vector<kaldi::int32>>& l, kaldi::CuMatrix* d) { c.EvalParallel(k, f, o, l, d); }
-  void ErrorRate(const std::vector<int>& f, const kaldi::CuMatrixBase& o, std::vector<std::vector<int>>& l) { c.ErrorRateMSeq(f, o, l); }
+  void Eval(const std::vector<std::string>& k, const std::vector<kaldi::int32>& f, const kaldi::CuMatrixBase<kaldi::BaseFloat>& o,
+            std::vector<std::vector<kaldi::int32>>& l, kaldi::CuMatrix<kaldi::BaseFloat>* d) { c.EvalParallel(k, f, o, l, d); }
+  void ErrorRate(const std::vector<int>& f, const kaldi::CuMatrixBase<kaldi::BaseFloat>& o, std::vector<std::vector<int>>& l) { c.ErrorRateMSeq(f, o, l); }
   std::string Report() { return c.Report(); }
 };
 }  // namespace

@@ -59,9 +59,9 @@ int main(int argc, char* argv[]) {
     long long total_frames = 0, report_frames = 0;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     FrameDataReader reader(feature_rspecifier, targets_rspecifier, rnd_opts);
-    const CuMatrixBase* nnet_in = nullptr;
+    const CuMatrixBase<BaseFloat>* nnet_in = nullptr;
     const Posterior* nnet_tgt = nullptr;
-    CuMatrix nnet_out, obj_diff;
+    CuMatrix<BaseFloat> nnet_out, obj_diff;
     while (!reader.Done()) {
       if (!reader.ReadData(&nnet_in, &nnet_tgt)) continue;
       if (!crossvalidate) nnet.Propagate(*nnet_in, &nnet_out);

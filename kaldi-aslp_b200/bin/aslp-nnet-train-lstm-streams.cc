@@ -66,7 +66,7 @@ int main(int argc, char* argv[]) {
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     SequenceDataReader reader(feature_rspecifier, targets_rspecifier, read_opts);
-    CuMatrix nnet_out, obj_diff, nnet_in;
+    CuMatrix<BaseFloat> nnet_out, obj_diff, nnet_in;
     // SequenceDataReader::ReadData on the feeder thread, into a page-locked slot (same stream bookkeeping, data-reader.cc:200-324)
     struct SeqBatch {
       PinnedMatrix feat;

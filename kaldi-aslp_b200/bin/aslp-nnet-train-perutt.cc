@@ -68,7 +68,7 @@ int main(int argc, char* argv[]) {
     SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
     RandomAccessPosteriorReader targets_reader(targets_rspecifier);
     Xent xent;
-    CuMatrix feats, feats_transf, nnet_out, obj_diff;
+    CuMatrix<BaseFloat> feats, feats_transf, nnet_out, obj_diff;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0;
@@ -114,7 +114,7 @@ int main(int argc, char* argv[]) {
     while (UttBatch* b = feeder.Next()) {
       feats.Resize(b->mat.NumRows(), b->mat.NumCols(), kUndefined);
       feats.CopyFromHost(b->mat.Data(), b->mat.Stride());      // asynchronous: the slot is page-locked
-      const CuMatrixBase* net_in = &feats;
+      const CuMatrixBase<BaseFloat>* net_in = &feats;
       if (nnet_transf.NumComponents() > 0) { nnet_transf.Feedforward(feats, &feats_transf); net_in = &feats_transf; }
       trn_opts.learn_rate = norm_lr / 1024.0;             // quirk (:201): a fixed divisor, not the utterance length
       nnet.SetTrainOptions(trn_opts);

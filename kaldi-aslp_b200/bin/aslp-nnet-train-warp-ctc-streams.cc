@@ -6,9 +6,9 @@ struct WarpCtcAdapter {
   kaldi::aslp_nnet::WarpCtc c;
   WarpCtcAdapter() { c.SetUseGpu(true); }
   void SetReportStep(int s) { c.SetReportStep(s); }
-  void Eval(const std::vector<std::string>& k, const std::vector<kaldi::int32>& f, const kaldi::CuMatrixBase& o,
-            std::vector<std::vector<kaldi::int32>>& l, kaldi::CuMatrix* d) { c.Eval(k, f, o, l, d); }
-  void ErrorRate(const std::vector<int>& f, const kaldi::CuMatrixBase& o, std::vector<std::vector<int>>& l) { c.ErrorRate(f, o, l); }
+  void Eval(const std::vector<std::string>& k, const std::vector<kaldi::int32>& f, const kaldi::CuMatrixBase<kaldi::BaseFloat>& o,
+            std::vector<std::vector<kaldi::int32>>& l, kaldi::CuMatrix<kaldi::BaseFloat>* d) { c.Eval(k, f, o, l, d); }
+  void ErrorRate(const std::vector<int>& f, const kaldi::CuMatrixBase<kaldi::BaseFloat>& o, std::vector<std::vector<int>>& l) { c.ErrorRate(f, o, l); }
   std::string Report() { return c.Report(); }
 };
 }  // namespace

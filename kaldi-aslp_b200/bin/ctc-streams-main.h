@@ -91,13 +91,13 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     RandomAccessInt32VectorReader targets_reader(targets_rspecifier);
     LossAdapter ctc;
     ctc.SetReportStep(report_step);
-    CuMatrix net_out, obj_diff;
+    CuMatrix<BaseFloat> net_out, obj_diff;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     const int32 feat_dim = net.InputDim();
     int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0, num_sentence = 0;
     int32 num_frames_since_sync = 0;
-    CuMatrix feat_mat_dev;
+    CuMatrix<BaseFloat> feat_mat_dev;
 
     // One group of utterances, read / filtered / packed by the feeder thread exactly as the reference's loop does it
     // (aslp-nnet-train-warp-ctc-streams.cc:116-175), into a page-locked slot.

@@ -65,7 +65,7 @@ inline int ForwardMain(int argc, char* argv[], bool split_skip) {
     int64 tot_t = 0;
     SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
     BaseFloatMatrixWriter feature_writer(feature_wspecifier);
-    CuMatrix feats, feats_transf, nnet_out, skip_feat, skip_out, tmp_out;
+    CuMatrix<BaseFloat> feats, feats_transf, nnet_out, skip_feat, skip_out, tmp_out;
     Matrix<BaseFloat> nnet_out_host;
     Timer time;
     int32 num_done = 0;
@@ -83,14 +83,14 @@ inline int ForwardMain(int argc, char* argv[], bool split_skip) {
       }
       if (!KALDI_ISFINITE(sum)) KALDI_ERR << "NaN or inf found in features for " << utt;
       feats = mat;
-      const CuMatrixBase* net_in = &feats;
+      const CuMatrixBase<BaseFloat>* net_in = &feats;
       if (nnet_transf.NumComponents() > 0) {
         nnet_transf.Feedforward(feats, &feats_transf);
         if (!KALDI_ISFINITE(feats_transf.Sum())) KALDI_ERR << "NaN or inf found in transformed-features for " << utt;
         net_in = &feats_transf;
       }
       std::vector<int32> frame_num_utt;
-      auto strided_rows = [&](CuMatrix* dst, int32 dst_row0, int32 dst_step, const CuMatrixBase& src, int32 src_row0, int32 src_step, int32 n) {
+      auto strided_rows = [&](CuMatrix<BaseFloat>* dst, int32 dst_row0, int32 dst_step, const CuMatrixBase<BaseFloat>& src, int32 src_row0, int32 src_step, int32 n) {
         // n rows: dst[dst_row0 + i*dst_step] = src[src_row0 + i*src_step] in ONE strided device copy
         ASLP_OK(aslp_memcpy2d_d2d(CuStream(), dst->Data() + static_cast<size_t>(dst_row0) * dst->Stride(), sizeof(float) * dst->Stride() * dst_step,
                                   src.Data() + static_cast<size_t>(src_row0) * src.Stride(), sizeof(float) * src.Stride() * src_step,

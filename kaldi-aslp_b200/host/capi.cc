@@ -28,7 +28,7 @@ static void CopyOut(const std::string& s, char* buf, size_t bytes) {
 }
 
 // reusable device staging for host inputs / outputs
-static CuMatrix g_in, g_out, g_diff, g_indiff, g_loss_diff;
+static CuMatrix<BaseFloat> g_in, g_out, g_diff, g_indiff, g_loss_diff;
 
 extern "C" {
 
@@ -108,7 +108,7 @@ int aslp_nnet_backpropagate(aslp_nnet_t n, const float* host_out_diff, int rows,
   CuSync();
   CAPI_END
 }
-static void CopyBuf(const CuMatrix& m, float* host_out, int rows, int cols) {
+static void CopyBuf(const CuMatrix<BaseFloat>& m, float* host_out, int rows, int cols) {
   if (m.NumRows() != rows || m.NumCols() != cols) KALDI_ERR << "buffer is " << m.NumRows() << " x " << m.NumCols() << ", asked for " << rows << " x " << cols;
   m.CopyToHost(host_out, cols);
   CuSync();
@@ -129,8 +129,8 @@ int aslp_warpctc_create(aslp_warpctc_t* out) { CAPI_BEGIN *out = new WarpCtc(); 
 int aslp_warpctc_destroy(aslp_warpctc_t c) { CAPI_BEGIN delete static_cast<WarpCtc*>(c); CAPI_END }
 int aslp_warpctc_report(aslp_warpctc_t c, char* buf, size_t bytes) { CAPI_BEGIN CopyOut(static_cast<WarpCtc*>(c)->Report(), buf, bytes); CAPI_END }
 
-static const CuMatrixBase& StageFeatures(const float* features, int on_device, int rows, int cols, CuSubMatrix* view) {
-  if (on_device) { *view = CuSubMatrix(const_cast<float*>(features), rows, cols, (cols + 3) / 4 * 4); return *view; }
+static const CuMatrixBase<BaseFloat>& StageFeatures(const float* features, int on_device, int rows, int cols, CuSubMatrix<BaseFloat>* view) {
+  if (on_device) { *view = CuSubMatrix<BaseFloat>(const_cast<float*>(features), rows, cols, (cols + 3) / 4 * 4); return *view; }
   g_in.Resize(rows, cols, kUndefined);
   g_in.CopyFromHost(features, cols);
   return g_in;
@@ -139,8 +139,8 @@ static const CuMatrixBase& StageFeatures(const float* features, int on_device, i
 int aslp_train_step_xent(aslp_nnet_t n, aslp_xent_t x, const float* features, int on_device, int rows, int cols, const int* targets,
                          const float* frame_mask) {
   CAPI_BEGIN
-  CuSubMatrix view(nullptr, 0, 0, 0);
-  const CuMatrixBase& in = StageFeatures(features, on_device, rows, cols, &view);
+  CuSubMatrix<BaseFloat> view(nullptr, 0, 0, 0);
+  const CuMatrixBase<BaseFloat>& in = StageFeatures(features, on_device, rows, cols, &view);
   N(n)->Propagate(in, &g_out);
   Posterior post(rows);
   Vector<BaseFloat> fw(rows);
@@ -171,8 +171,8 @@ int aslp_train_step_ctc(aslp_nnet_t n, aslp_warpctc_t c, const float* features, 
     o.learn_rate = norm_learn_rate / valid_frames;
     net->SetTrainOptions(o);
   }
-  CuSubMatrix view(nullptr, 0, 0, 0);
-  const CuMatrixBase& in = StageFeatures(features, on_device, rows, cols, &view);
+  CuSubMatrix<BaseFloat> view(nullptr, 0, 0, 0);
+  const CuMatrixBase<BaseFloat>& in = StageFeatures(features, on_device, rows, cols, &view);
   net->Propagate(in, &g_out);                                         // :182
   ctc->Eval(keys, lens, g_out, labels, &g_loss_diff);                 // :187
   if (with_error_rate) ctc->ErrorRate(lens, g_out, labels);           // :190
@@ -207,8 +207,8 @@ int aslp_train_step_ctc_eesen(aslp_nnet_t n, aslp_eesenctc_t c, const float* fea
     o.learn_rate = norm_learn_rate / valid_frames;
     net->SetTrainOptions(o);
   }
-  CuSubMatrix view(nullptr, 0, 0, 0);
-  const CuMatrixBase& in = StageFeatures(features, on_device, rows, cols, &view);
+  CuSubMatrix<BaseFloat> view(nullptr, 0, 0, 0);
+  const CuMatrixBase<BaseFloat>& in = StageFeatures(features, on_device, rows, cols, &view);
   net->Propagate(in, &g_out);
   ctc->EvalParallel(keys, lens, g_out, labels, &g_loss_diff);
   if (with_error_rate) ctc->ErrorRateMSeq(lens, g_out, labels);

@@ -243,51 +243,51 @@ template class Matrix<float>;
 template class Matrix<double>;
 
 // ------------------------------------------------------------------ device matrix
-CuSubMatrix CuMatrixBase::RowRange(int32 r0, int32 n) const {
+CuSubMatrix<float> CuMatrixBase<float>::RowRange(int32 r0, int32 n) const {
   KALDI_ASSERT(r0 >= 0 && n >= 0 && r0 + n <= rows_);
-  return CuSubMatrix(data_ + static_cast<size_t>(r0) * stride_, n, cols_, stride_);
+  return CuSubMatrix<float>(data_ + static_cast<size_t>(r0) * stride_, n, cols_, stride_);
 }
-CuSubMatrix CuMatrixBase::ColRange(int32 c0, int32 n) const {
+CuSubMatrix<float> CuMatrixBase<float>::ColRange(int32 c0, int32 n) const {
   KALDI_ASSERT(c0 >= 0 && n >= 0 && c0 + n <= cols_);
-  return CuSubMatrix(data_ + c0, rows_, n, stride_);
+  return CuSubMatrix<float>(data_ + c0, rows_, n, stride_);
 }
-CuSubMatrix CuMatrixBase::Range(int32 r0, int32 nr, int32 c0, int32 nc) const {
+CuSubMatrix<float> CuMatrixBase<float>::Range(int32 r0, int32 nr, int32 c0, int32 nc) const {
   KALDI_ASSERT(r0 >= 0 && nr >= 0 && r0 + nr <= rows_ && c0 >= 0 && nc >= 0 && c0 + nc <= cols_);
-  return CuSubMatrix(data_ + static_cast<size_t>(r0) * stride_ + c0, nr, nc, stride_);
+  return CuSubMatrix<float>(data_ + static_cast<size_t>(r0) * stride_ + c0, nr, nc, stride_);
 }
-void CuMatrixBase::SetZero() {
+void CuMatrixBase<float>::SetZero() {
   if (rows_ == 0 || cols_ == 0) return;
   if (cols_ == stride_) { ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(float) * static_cast<size_t>(rows_) * stride_)); return; }
   ASLP_OK(aslp_memset2d(CuStream(), data_, sizeof(float) * stride_, 0, sizeof(float) * cols_, rows_));
 }
-void CuMatrixBase::CopyFromMat(const CuMatrixBase& src) {
+void CuMatrixBase<float>::CopyFromMat(const CuMatrixBase<float>& src) {
   KALDI_ASSERT(src.NumRows() == rows_ && src.NumCols() == cols_);
   ASLP_OK(aslp_memcpy2d_d2d(CuStream(), data_, sizeof(float) * stride_, src.Data(), sizeof(float) * src.Stride(), sizeof(float) * cols_, rows_));
 }
-void CuMatrixBase::CopyFromMat(const Matrix<float>& src) {
+void CuMatrixBase<float>::CopyFromMat(const Matrix<float>& src) {
   KALDI_ASSERT(src.NumRows() == rows_ && src.NumCols() == cols_);
   CopyFromHost(src.Data(), src.Stride());
   CuSync();   // the host matrix may be a temporary
 }
-void CuMatrixBase::CopyFromHost(const float* src, int32 src_stride) {
+void CuMatrixBase<float>::CopyFromHost(const float* src, int32 src_stride) {
   ASLP_OK(aslp_memcpy2d_h2d(CuStream(), data_, sizeof(float) * stride_, src, sizeof(float) * src_stride, sizeof(float) * cols_, rows_));
 }
-void CuMatrixBase::CopyToMat(Matrix<float>* dst) const {
+void CuMatrixBase<float>::CopyToMat(Matrix<float>* dst) const {
   if (dst->NumRows() != rows_ || dst->NumCols() != cols_) dst->Resize(rows_, cols_, kUndefined);
   CopyToHost(dst->Data(), dst->Stride());
   CuSync();
 }
-void CuMatrixBase::CopyToHost(float* dst, int32 dst_stride) const {
+void CuMatrixBase<float>::CopyToHost(float* dst, int32 dst_stride) const {
   ASLP_OK(aslp_memcpy2d_d2h(CuStream(), dst, sizeof(float) * dst_stride, data_, sizeof(float) * stride_, sizeof(float) * cols_, rows_));
 }
-void CuMatrixBase::AddMat(float alpha, const CuMatrixBase& A) {
+void CuMatrixBase<float>::AddMat(float alpha, const CuMatrixBase<float>& A) {
   KALDI_ASSERT(A.NumRows() == rows_ && A.NumCols() == cols_);
   ASLP_OK(aslp_axpby(CuStream(), data_, stride_, A.Data(), A.Stride(), rows_, cols_, alpha, 1.0f));
 }
-void CuMatrixBase::Scale(float alpha) {
+void CuMatrixBase<float>::Scale(float alpha) {
   ASLP_OK(aslp_axpby(CuStream(), data_, stride_, data_, stride_, rows_, cols_, alpha, 0.0f));
 }
-double CuMatrixBase::Sum() const {
+double CuMatrixBase<float>::Sum() const {
   static double* dev2 = nullptr;
   if (dev2 == nullptr) ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&dev2), 2 * sizeof(double)));
   ASLP_OK(aslp_sum_check(CuStream(), data_, stride_, rows_, cols_, dev2));
@@ -297,8 +297,8 @@ double CuMatrixBase::Sum() const {
   return h[1] > 0 ? std::nan("") : h[0];
 }
 
-CuMatrix::~CuMatrix() { if (data_ != nullptr) aslp_free(data_); }
-void CuMatrix::Resize(int32 rows, int32 cols, MatrixResizeType t) {
+CuMatrix<float>::~CuMatrix() { if (data_ != nullptr) aslp_free(data_); }
+void CuMatrix<float>::Resize(int32 rows, int32 cols, MatrixResizeType t) {
   KALDI_ASSERT(rows >= 0 && cols >= 0);
   const int32 stride = (cols + 3) / 4 * 4;
   const size_t need = static_cast<size_t>(rows) * stride;
@@ -314,24 +314,24 @@ void CuMatrix::Resize(int32 rows, int32 cols, MatrixResizeType t) {
   rows_ = rows; cols_ = cols; stride_ = stride;
   if (t == kSetZero && need > 0) ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(float) * need));
 }
-void CuMatrix::Swap(CuMatrix* o) {
+void CuMatrix<float>::Swap(CuMatrix<float>* o) {
   std::swap(data_, o->data_); std::swap(rows_, o->rows_); std::swap(cols_, o->cols_); std::swap(stride_, o->stride_); std::swap(cap_, o->cap_);
 }
-void CuMatrix::Read(std::istream& is, bool binary) {
+void CuMatrix<float>::Read(std::istream& is, bool binary) {
   Matrix<float> tmp;
   tmp.Read(is, binary);
   *this = tmp;
 }
-void CuMatrix::Write(std::ostream& os, bool binary) const {
+void CuMatrix<float>::Write(std::ostream& os, bool binary) const {
   Matrix<float> tmp;
   CopyToMat(&tmp);
   tmp.Write(os, binary);
 }
 
 // ------------------------------------------------------------------ device vectors
-template <typename Real> CuVectorT<Real>::~CuVectorT() { if (data_ != nullptr) aslp_free(data_); }
+template <typename Real> CuVector<Real>::~CuVector() { if (data_ != nullptr) aslp_free(data_); }
 template <typename Real>
-void CuVectorT<Real>::Resize(int32 dim, MatrixResizeType t) {
+void CuVector<Real>::Resize(int32 dim, MatrixResizeType t) {
   if (static_cast<size_t>(dim) > cap_) {
     CuStream();
     if (data_ != nullptr) { CuSync(); aslp_free(data_); data_ = nullptr; }
@@ -344,37 +344,37 @@ void CuVectorT<Real>::Resize(int32 dim, MatrixResizeType t) {
   dim_ = dim;
   if (t == kSetZero) SetZero();
 }
-template <typename Real> void CuVectorT<Real>::SetZero() { if (dim_ > 0) ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(Real) * dim_)); }
-template <typename Real> void CuVectorT<Real>::Set(Real v) {
+template <typename Real> void CuVector<Real>::SetZero() { if (dim_ > 0) ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(Real) * dim_)); }
+template <typename Real> void CuVector<Real>::Set(Real v) {
   Vector<Real> h(dim_);
   for (int32 i = 0; i < dim_; ++i) h(i) = v;
   CopyFromVec(h);
 }
-template <typename Real> void CuVectorT<Real>::CopyToVec(Vector<Real>* dst) const {
+template <typename Real> void CuVector<Real>::CopyToVec(Vector<Real>* dst) const {
   if (dst->Dim() != dim_) dst->Resize(dim_, kUndefined);
   if (dim_ > 0) ASLP_OK(aslp_memcpy_d2h(CuStream(), dst->Data(), data_, sizeof(Real) * dim_));
   CuSync();
 }
-template <typename Real> void CuVectorT<Real>::CopyFromVec(const Vector<Real>& src) {
+template <typename Real> void CuVector<Real>::CopyFromVec(const Vector<Real>& src) {
   KALDI_ASSERT(src.Dim() == dim_);
   if (dim_ > 0) ASLP_OK(aslp_memcpy_h2d(CuStream(), data_, src.Data(), sizeof(Real) * dim_));
   CuSync();
 }
-template <typename Real> CuVectorT<Real>& CuVectorT<Real>::operator=(const CuVectorT& o) {
+template <typename Real> CuVector<Real>& CuVector<Real>::operator=(const CuVector& o) {
   if (this == &o) return *this;
   Resize(o.dim_, kUndefined);
   if (dim_ > 0) ASLP_OK(aslp_memcpy_d2d(CuStream(), data_, o.data_, sizeof(Real) * dim_));
   return *this;
 }
-template <typename Real> CuVectorT<Real>& CuVectorT<Real>::operator=(const Vector<Real>& o) {
+template <typename Real> CuVector<Real>& CuVector<Real>::operator=(const Vector<Real>& o) {
   Resize(o.Dim(), kUndefined);
   CopyFromVec(o);
   return *this;
 }
-template <typename Real> void CuVectorT<Real>::Read(std::istream& is, bool binary) { Vector<Real> t; t.Read(is, binary); *this = t; }
-template <typename Real> void CuVectorT<Real>::Write(std::ostream& os, bool binary) const { Vector<Real> t; CopyToVec(&t); t.Write(os, binary); }
-template class CuVectorT<float>;
-template class CuVectorT<double>;
+template <typename Real> void CuVector<Real>::Read(std::istream& is, bool binary) { Vector<Real> t; t.Read(is, binary); *this = t; }
+template <typename Real> void CuVector<Real>::Write(std::ostream& os, bool binary) const { Vector<Real> t; CopyToVec(&t); t.Write(os, binary); }
+template class CuVector<float>;
+template class CuVector<double>;
 
 CuArrayInt::~CuArrayInt() { if (data_ != nullptr) aslp_free(data_); }
 CuArrayInt& CuArrayInt::operator=(const std::vector<int32>& v) {
@@ -407,12 +407,12 @@ static std::string Moments(const std::vector<float>& v) {
      << ", skewness " << (m2 > 0 ? m3 / pow(m2, 1.5) : 0.0) << ", kurtosis " << (m2 > 0 ? m4 / (m2 * m2) - 3.0 : 0.0) << " ) ";
   return os.str();
 }
-std::string MomentStatistics(const CuMatrixBase& m) {
+std::string MomentStatistics(const CuMatrixBase<float>& m) {
   Matrix<float> h;
   m.CopyToMat(&h);
   return Moments(std::vector<float>(h.Data(), h.Data() + static_cast<size_t>(h.NumRows()) * h.NumCols()));
 }
-std::string MomentStatistics(const CuVector& v) {
+std::string MomentStatistics(const CuVector<float>& v) {
   Vector<float> h;
   v.CopyToVec(&h);
   return Moments(std::vector<float>(h.Data(), h.Data() + h.Dim()));

@@ -105,25 +105,32 @@ class PinnedMatrix {
   int32 r_, c_;
 };
 
-class CuSubMatrix;
+// The device classes are templates on the element type like the reference's (src/aslp-cudamatrix/cu-matrix.h:48, cu-vector.h), so that
+// code written against CuMatrix<BaseFloat> / CuSubMatrix<BaseFloat> / CuVector<BaseFloat> compiles unchanged; the path is fp32
+// (BaseFloat = float, -DKALDI_DOUBLEPRECISION=0), so only the float specialisations are defined (CuVector also for double: the
+// BatchNorm running sums).
+template <typename Real> class CuMatrixBase;
+template <typename Real> class CuSubMatrix;
+template <typename Real> class CuMatrix;
 
-class CuMatrixBase {
+template <>
+class CuMatrixBase<float> {
  public:
   float* Data() { return data_; }
   const float* Data() const { return data_; }
   int32 NumRows() const { return rows_; }
   int32 NumCols() const { return cols_; }
   int32 Stride() const { return stride_; }
-  CuSubMatrix RowRange(int32 r0, int32 n) const;
-  CuSubMatrix ColRange(int32 c0, int32 n) const;
-  CuSubMatrix Range(int32 r0, int32 nr, int32 c0, int32 nc) const;
+  CuSubMatrix<float> RowRange(int32 r0, int32 n) const;
+  CuSubMatrix<float> ColRange(int32 c0, int32 n) const;
+  CuSubMatrix<float> Range(int32 r0, int32 nr, int32 c0, int32 nc) const;
   void SetZero();
-  void CopyFromMat(const CuMatrixBase& src);                 // device -> device
+  void CopyFromMat(const CuMatrixBase<float>& src);                 // device -> device
   void CopyFromMat(const Matrix<float>& src);                // host -> device
   void CopyFromHost(const float* src, int32 src_stride);     // host (pinned or pageable) -> device, async
   void CopyToMat(Matrix<float>* dst) const;                  // device -> host (synchronises)
   void CopyToHost(float* dst, int32 dst_stride) const;       // async
-  void AddMat(float alpha, const CuMatrixBase& A);           // this += alpha * A
+  void AddMat(float alpha, const CuMatrixBase<float>& A);           // this += alpha * A
   void Scale(float alpha);
   double Sum() const;                                        // synchronises
  protected:
@@ -133,20 +140,22 @@ class CuMatrixBase {
   int32 rows_, cols_, stride_;
 };
 
-class CuSubMatrix : public CuMatrixBase {
+template <>
+class CuSubMatrix<float> : public CuMatrixBase<float> {
  public:
-  CuSubMatrix(float* d, int32 r, int32 c, int32 s) : CuMatrixBase(d, r, c, s) {}
+  CuSubMatrix(float* d, int32 r, int32 c, int32 s) : CuMatrixBase<float>(d, r, c, s) {}
 };
 
-class CuMatrix : public CuMatrixBase {
+template <>
+class CuMatrix<float> : public CuMatrixBase<float> {
  public:
   CuMatrix() : cap_(0) {}
   CuMatrix(int32 rows, int32 cols, MatrixResizeType t = kSetZero) : cap_(0) { Resize(rows, cols, t); }
-  CuMatrix(const CuMatrix& o) : CuMatrixBase(), cap_(0) { *this = o; }
-  explicit CuMatrix(const CuMatrixBase& o) : cap_(0) { Resize(o.NumRows(), o.NumCols(), kUndefined); CopyFromMat(o); }
+  CuMatrix(const CuMatrix& o) : CuMatrixBase<float>(), cap_(0) { *this = o; }
+  explicit CuMatrix(const CuMatrixBase<float>& o) : cap_(0) { Resize(o.NumRows(), o.NumCols(), kUndefined); CopyFromMat(o); }
   explicit CuMatrix(const Matrix<float>& o) : cap_(0) { *this = o; }
   CuMatrix& operator=(const CuMatrix& o) { if (this != &o) { Resize(o.NumRows(), o.NumCols(), kUndefined); CopyFromMat(o); } return *this; }
-  CuMatrix& operator=(const CuMatrixBase& o) { Resize(o.NumRows(), o.NumCols(), kUndefined); CopyFromMat(o); return *this; }
+  CuMatrix& operator=(const CuMatrixBase<float>& o) { Resize(o.NumRows(), o.NumCols(), kUndefined); CopyFromMat(o); return *this; }
   CuMatrix& operator=(const Matrix<float>& o) { Resize(o.NumRows(), o.NumCols(), kUndefined); CopyFromMat(o); return *this; }
   ~CuMatrix();
   // rows are 16-byte aligned (stride = cols rounded up to 4 floats), like the pitched allocation of the reference
@@ -159,14 +168,14 @@ class CuMatrix : public CuMatrixBase {
 };
 
 template <typename Real>
-class CuVectorT {
+class CuVector {
  public:
-  CuVectorT() : data_(nullptr), dim_(0), cap_(0) {}
-  explicit CuVectorT(int32 dim, MatrixResizeType t = kSetZero) : data_(nullptr), dim_(0), cap_(0) { Resize(dim, t); }
-  CuVectorT(const CuVectorT& o) : data_(nullptr), dim_(0), cap_(0) { *this = o; }
-  CuVectorT& operator=(const CuVectorT& o);
-  CuVectorT& operator=(const Vector<Real>& o);
-  ~CuVectorT();
+  CuVector() : data_(nullptr), dim_(0), cap_(0) {}
+  explicit CuVector(int32 dim, MatrixResizeType t = kSetZero) : data_(nullptr), dim_(0), cap_(0) { Resize(dim, t); }
+  CuVector(const CuVector& o) : data_(nullptr), dim_(0), cap_(0) { *this = o; }
+  CuVector& operator=(const CuVector& o);
+  CuVector& operator=(const Vector<Real>& o);
+  ~CuVector();
   void Resize(int32 dim, MatrixResizeType t = kSetZero);
   int32 Dim() const { return dim_; }
   Real* Data() { return data_; }
@@ -182,8 +191,6 @@ class CuVectorT {
   int32 dim_;
   size_t cap_;
 };
-typedef CuVectorT<float> CuVector;
-typedef CuVectorT<double> CuVectorD;
 
 // device int32 array (CuArray<int32>)
 class CuArrayInt {
@@ -203,8 +210,8 @@ class CuArrayInt {
   std::vector<int32> host_;
 };
 
-std::string MomentStatistics(const CuMatrixBase& m);
-std::string MomentStatistics(const CuVector& v);
+std::string MomentStatistics(const CuMatrixBase<float>& m);
+std::string MomentStatistics(const CuVector<float>& v);
 
 }  // namespace kaldi
 #endif

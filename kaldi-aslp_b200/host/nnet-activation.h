@@ -13,11 +13,11 @@ class Softmax : public Component {
   Softmax(int32 dim_in, int32 dim_out) : Component(dim_in, dim_out) {}
   Component* Copy() const { return new Softmax(*this); }
   ComponentType GetType() const { return kSoftmax; }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     ASLP_OK(aslp_softmax_rows(CuStream(), out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), in.NumCols()));
   }
   // the loss already delivers y - t: the backward pass is a copy (nnet-activation.h:51-59)
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     in_diff->CopyFromMat(out_diff);
   }
 };
@@ -28,11 +28,11 @@ class PointwiseActivation : public Component {
   PointwiseActivation(int32 dim_in, int32 dim_out) : Component(dim_in, dim_out) {}
   Component* Copy() const { return new PointwiseActivation(*this); }
   ComponentType GetType() const { return TYPE; }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     ASLP_OK(aslp_act_fwd(CuStream(), KIND, out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), in.NumCols()));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
-    const CuMatrixBase& ref = (KIND == ASLP_ACT_RELU) ? in : out;     // sigmoid/tanh use y, ReLU uses Heaviside(x)
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
+    const CuMatrixBase<BaseFloat>& ref = (KIND == ASLP_ACT_RELU) ? in : out;     // sigmoid/tanh use y, ReLU uses Heaviside(x)
     ASLP_OK(aslp_act_bwd(CuStream(), KIND, in_diff->Data(), in_diff->Stride(), ref.Data(), ref.Stride(), out_diff.Data(), out_diff.Stride(),
                          out_diff.NumRows(), out_diff.NumCols()));
   }
@@ -48,8 +48,8 @@ class CopyLayer : public Component {
   CopyLayer(int32 dim_in, int32 dim_out) : Component(dim_in, dim_out) {}
   Component* Copy() const { return new CopyLayer(*this); }
   ComponentType GetType() const { return TYPE; }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) { out->CopyFromMat(in); }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) { in_diff->CopyFromMat(out_diff); }
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) { out->CopyFromMat(in); }
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) { in_diff->CopyFromMat(out_diff); }
 };
 typedef CopyLayer<Component::kInputLayer> InputLayer;
 typedef CopyLayer<Component::kOutputLayer> OutputLayer;
@@ -62,10 +62,10 @@ class ScaleLayer : public Component {
   void InitData(std::istream& is) { ProtoOptions po("(Scale)"); po.Float("<Scale>", &scale_); po.Parse(is); }
   void ReadData(std::istream& is, bool binary) { ExpectToken(is, binary, "<Scale>"); ReadBasicType(is, binary, &scale_); }
   void WriteData(std::ostream& os, bool binary) const { WriteToken(os, binary, "<Scale>"); WriteBasicType(os, binary, scale_); }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     ASLP_OK(aslp_axpby(CuStream(), out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), in.NumCols(), scale_, 0.0f));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     ASLP_OK(aslp_axpby(CuStream(), in_diff->Data(), in_diff->Stride(), out_diff.Data(), out_diff.Stride(), out_diff.NumRows(), out_diff.NumCols(), scale_, 0.0f));
   }
  private:
@@ -122,10 +122,10 @@ class Splice : public Component {
     os << "]";
     return os.str();
   }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     ASLP_OK(aslp_splice_fwd(CuStream(), out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), input_dim_, frame_offsets_.Data(), frame_offsets_.Dim()));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     ASLP_OK(aslp_splice_bwd(CuStream(), in_diff->Data(), in_diff->Stride(), out_diff.Data(), out_diff.Stride(), in.NumRows(), input_dim_,
                             frame_offsets_.Data(), frame_offsets_.Dim()));
   }
@@ -156,18 +156,18 @@ class AddShift : public UpdatableComponent {
   int32 NumParams() const { return shift_data_.Dim(); }
   void GetParams(Vector<BaseFloat>* w) const { shift_data_.CopyToVec(w); }
   void GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* p) { p->clear(); p->push_back(std::make_pair(shift_data_.Data(), shift_data_.Dim())); }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     out->CopyFromMat(in);
     ASLP_OK(aslp_add_vec_to_rows(CuStream(), out->Data(), out->Stride(), out->NumRows(), out->NumCols(), shift_data_.Data(), 1.0f, 1.0f));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) { in_diff->CopyFromMat(out_diff); }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) { in_diff->CopyFromMat(out_diff); }
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     const float lr = opts_.learn_rate * learn_rate_coef_;
     if (lr == 0.0f) return;
     ASLP_OK(aslp_col_sum(CuStream(), shift_data_.Data(), diff.Data(), diff.Stride(), diff.NumRows(), diff.NumCols(), -lr, 1.0f, 0.0f));
   }
  private:
-  CuVector shift_data_;
+  CuVector<BaseFloat> shift_data_;
   float learn_rate_coef_;
 };
 
@@ -195,20 +195,20 @@ class Rescale : public UpdatableComponent {
   void GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* p) { p->clear(); p->push_back(std::make_pair(scale_data_.Data(), scale_data_.Dim())); }
   // y = x * diag(scale): the eval-mode BatchNorm kernel with mean 0, inv_std = scale, scale 1, shift 0 would do; a dedicated
   // helper keeps it one pass: out = in, then out *= scale per column via bn_fwd_eval(scale=scale, shift=0, mean=0, inv_std=1)
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) { Apply(in, out); }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) { Apply(out_diff, in_diff); }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) { Apply(in, out); }
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) { Apply(out_diff, in_diff); }
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     const float lr = opts_.learn_rate * learn_rate_coef_;
     if (lr == 0.0f) return;
     ASLP_OK(aslp_col_dot(CuStream(), scale_data_.Data(), input.Data(), input.Stride(), diff.Data(), diff.Stride(), diff.NumRows(), diff.NumCols(), -lr, 1.0f, 0.0f));
   }
  private:
-  void Apply(const CuMatrixBase& src, CuMatrixBase* dst) {
+  void Apply(const CuMatrixBase<BaseFloat>& src, CuMatrixBase<BaseFloat>* dst) {
     if (zeros_.Dim() != scale_data_.Dim()) { zeros_.Resize(scale_data_.Dim(), kSetZero); ones_.Resize(scale_data_.Dim()); ones_.Set(1.0f); }
     ASLP_OK(aslp_bn_fwd_eval(CuStream(), dst->Data(), dst->Stride(), src.Data(), src.Stride(), src.NumRows(), src.NumCols(), scale_data_.Data(),
                              zeros_.Data(), zeros_.Data(), ones_.Data()));
   }
-  CuVector scale_data_, zeros_, ones_;
+  CuVector<BaseFloat> scale_data_, zeros_, ones_;
   float learn_rate_coef_;
 };
 

@@ -94,15 +94,15 @@ class AffineTransform : public UpdatableComponent {
            (has_bias_ ? "\n  bias_grad" + MomentStatistics(bias_corr_) + ", lr-coef " + ToString(bias_learn_rate_coef_) : "");
   }
 
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     ASLP_OK(aslp_gemm(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
                       0.0f, out->Data(), out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), nullptr, 0));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     ASLP_OK(aslp_gemm(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
                       linearity_.Stride(), 0.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
   }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     aslp_stream_t st = CuStream();
     const BaseFloat lr = opts_.learn_rate * learn_rate_coef_, lr_bias = opts_.learn_rate * bias_learn_rate_coef_;
     const BaseFloat mmt = opts_.momentum, l2 = opts_.l2_penalty, l1 = opts_.l1_penalty;
@@ -121,19 +121,19 @@ class AffineTransform : public UpdatableComponent {
     if (max_norm_ > 0.0) ASLP_OK(aslp_max_norm_rows(st, linearity_.Data(), linearity_.Stride(), output_dim_, input_dim_, max_norm_));
   }
 
-  const CuVector& GetBias() const { return bias_; }
-  void SetBias(const CuVector& bias) { KALDI_ASSERT(bias.Dim() == bias_.Dim()); bias_ = bias; }
-  const CuMatrix& GetLinearity() const { return linearity_; }
-  void SetLinearity(const CuMatrixBase& l) { KALDI_ASSERT(l.NumRows() == linearity_.NumRows() && l.NumCols() == linearity_.NumCols()); linearity_.CopyFromMat(l); }
-  const CuVector& GetBiasCorr() const { return bias_corr_; }
-  const CuMatrix& GetLinearityCorr() const { return linearity_corr_; }
+  const CuVector<BaseFloat>& GetBias() const { return bias_; }
+  void SetBias(const CuVector<BaseFloat>& bias) { KALDI_ASSERT(bias.Dim() == bias_.Dim()); bias_ = bias; }
+  const CuMatrix<BaseFloat>& GetLinearity() const { return linearity_; }
+  void SetLinearity(const CuMatrixBase<BaseFloat>& l) { KALDI_ASSERT(l.NumRows() == linearity_.NumRows() && l.NumCols() == linearity_.NumCols()); linearity_.CopyFromMat(l); }
+  const CuVector<BaseFloat>& GetBiasCorr() const { return bias_corr_; }
+  const CuMatrix<BaseFloat>& GetLinearityCorr() const { return linearity_corr_; }
 
  protected:
   bool has_bias_;
-  CuMatrix linearity_;
-  CuVector bias_;
-  CuMatrix linearity_corr_;
-  CuVector bias_corr_;
+  CuMatrix<BaseFloat> linearity_;
+  CuVector<BaseFloat> bias_;
+  CuMatrix<BaseFloat> linearity_corr_;
+  CuVector<BaseFloat> bias_corr_;
   BaseFloat learn_rate_coef_, bias_learn_rate_coef_, max_norm_;
 };
 

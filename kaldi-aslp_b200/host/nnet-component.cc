@@ -166,21 +166,21 @@ void Component::WriteStandard(std::ostream& os, bool binary) const {
   this->WriteData(os, binary);
 }
 
-void Component::Feedforward(const CuMatrixBase& in, CuMatrix* out) {
+void Component::Feedforward(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out) {
   if (input_dim_ != in.NumCols())
     KALDI_ERR << "Non-matching dims! " << TypeToMarker(GetType()) << " input-dim : " << input_dim_ << " data : " << in.NumCols();
   out->Resize(in.NumRows(), output_dim_, kUndefined);
   FeedforwardFnc(in, out);
 }
 
-void Component::Propagate(const CuMatrixBase& in, CuMatrix* out) {
+void Component::Propagate(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out) {
   if (input_dim_ != in.NumCols())
     KALDI_ERR << "Non-matching dims! " << TypeToMarker(GetType()) << " input-dim : " << input_dim_ << " data : " << in.NumCols();
   out->Resize(in.NumRows(), output_dim_, kUndefined);
   PropagateFnc(in, out);
 }
 
-void Component::Backpropagate(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrix* in_diff) {
+void Component::Backpropagate(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrix<BaseFloat>* in_diff) {
   if (output_dim_ != out_diff.NumCols())
     KALDI_ERR << "Non-matching output dims, component:" << output_dim_ << " data:" << out_diff.NumCols();
   if (in_diff == NULL) return;     // only nested-nnet components back-propagate without a target, none are on this path
@@ -204,7 +204,7 @@ void ProtoOptions::Parse(std::istream& is) {
   }
 }
 
-void InitMatParam(CuMatrix* m, float scale) {
+void InitMatParam(CuMatrix<BaseFloat>* m, float scale) {
   Matrix<BaseFloat> h(m->NumRows(), m->NumCols());
   RandomState rs;                                        // MatrixBase::SetRandUniform (kaldi-matrix.cc:1190-1198)
   for (int32 r = 0; r < h.NumRows(); ++r)
@@ -216,12 +216,12 @@ void InitMatParam(CuMatrix* m, float scale) {
     }
   *m = h;
 }
-void InitVecParam(CuVector* v, float scale) {
+void InitVecParam(CuVector<BaseFloat>* v, float scale) {
   Vector<BaseFloat> tmp(v->Dim());
   for (int32 i = 0; i < tmp.Dim(); i++) tmp(i) = (RandUniform() - 0.5) * 2 * scale;
   *v = tmp;
 }
-void CopyRowsToVec(const CuMatrixBase& m, float* dst) {
+void CopyRowsToVec(const CuMatrixBase<BaseFloat>& m, float* dst) {
   Matrix<float> h;
   m.CopyToMat(&h);
   std::copy(h.Data(), h.Data() + static_cast<size_t>(h.NumRows()) * h.NumCols(), dst);

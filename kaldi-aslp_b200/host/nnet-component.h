@@ -52,9 +52,9 @@ class Component {
 
   // dim check, size `out` / `in_diff`, call the virtual (nnet-component.h:286-347).  The reference zeroes the
   // target first; here targets are sized without a memset and every *Fnc overwrites all of its output.
-  virtual void Feedforward(const CuMatrixBase& in, CuMatrix* out);
-  void Propagate(const CuMatrixBase& in, CuMatrix* out);
-  void Backpropagate(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrix* in_diff);
+  virtual void Feedforward(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out);
+  void Propagate(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out);
+  void Backpropagate(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrix<BaseFloat>* in_diff);
 
   static Component* Init(const std::string& conf_line);
   static Component* Read(std::istream& is, bool binary);
@@ -65,9 +65,9 @@ class Component {
   virtual std::string InfoGradient() const { return ""; }
 
  protected:
-  virtual void FeedforwardFnc(const CuMatrixBase& in, CuMatrixBase* out) { PropagateFnc(in, out); }
-  virtual void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) = 0;
-  virtual void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) = 0;
+  virtual void FeedforwardFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) { PropagateFnc(in, out); }
+  virtual void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) = 0;
+  virtual void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) = 0;
   virtual void InitData(std::istream& is) {}
   virtual void ReadData(std::istream& is, bool binary) {}
   virtual void WriteData(std::ostream& os, bool binary) const {}
@@ -90,7 +90,7 @@ class UpdatableComponent : public Component {
   // (device pointer, element count INCLUDING row padding) per parameter tensor; pointers stay valid for the life of
   // the component -- the arena/packing contract of the aslp-parallel workers (nnet-component.h:264; bsp-worker.cc:14-16)
   virtual void GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* params) = 0;
-  virtual void Update(const CuMatrixBase& input, const CuMatrixBase& diff) = 0;
+  virtual void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) = 0;
   virtual void SetTrainOptions(const NnetTrainOptions& opts) { opts_ = opts; }
   const NnetTrainOptions& GetTrainOptions() const { return opts_; }
   virtual void InitData(std::istream& is) = 0;
@@ -113,9 +113,9 @@ class ProtoOptions {
 };
 // uniform [-scale, scale] fills in the reference's element order and RNG streams
 // (InitMatParam: CuMatrix::SetRandUniform -> MatrixBase::SetRandUniform with a fresh RandomState; InitVecParam: global Rand())
-void InitMatParam(CuMatrix* m, float scale);
-void InitVecParam(CuVector* v, float scale);
-void CopyRowsToVec(const CuMatrixBase& m, float* dst);     // CopyRowsFromMat into a params super-vector (synchronises)
+void InitMatParam(CuMatrix<BaseFloat>* m, float scale);
+void InitVecParam(CuVector<BaseFloat>* v, float scale);
+void CopyRowsToVec(const CuMatrixBase<BaseFloat>& m, float* dst);     // CopyRowsFromMat into a params super-vector (synchronises)
 
 }  // namespace aslp_nnet
 }  // namespace kaldi

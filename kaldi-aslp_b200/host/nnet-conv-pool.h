@@ -105,7 +105,7 @@ class ConvolutionalComponent : public UpdatableComponent {
            ToString(max_norm_) + "\n  bias_grad" + MomentStatistics(bias_grad_) + ", lr-coef " + ToString(bias_learn_rate_coef_);
   }
 
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     const Geometry g = CheckGeometry();
     const int32 rows = in.NumRows();
     aslp_stream_t st = CuStream();
@@ -122,7 +122,7 @@ class ConvolutionalComponent : public UpdatableComponent {
                           bias_.Data(), 0.0f, GemmPrecision(), nullptr, 0));
     }
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     const Geometry g = CheckGeometry();
     const int32 rows = out_diff.NumRows();
     aslp_stream_t st = CuStream();
@@ -139,7 +139,7 @@ class ConvolutionalComponent : public UpdatableComponent {
     ASLP_OK(aslp_conv_scatter_patch_diffs(st, in_diff->Data(), in_diff->Stride(), patch_diffs_.Data(), patch_diffs_.Stride(), rows, g.num_patches,
                                           g.num_splice, patch_dim_, patch_step_, patch_stride_));
   }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     const Geometry g = CheckGeometry();
     const int32 rows = diff.NumRows();
     KALDI_ASSERT(patches_.NumRows() == rows * g.num_patches);           // the patches of the Propagate this diff belongs to
@@ -190,14 +190,14 @@ class ConvolutionalComponent : public UpdatableComponent {
   // the [frames, P*num_filters] matrix can be addressed as a row-major [frames*P, num_filters] one with 16-byte aligned rows
   static bool Dense(const Geometry& g, int32 stride) { return stride == g.num_patches * g.num_filters && g.num_filters % 4 == 0; }
   int32 patch_dim_, patch_step_, patch_stride_;
-  CuMatrix filters_;                           // row = vectorised rectangular filter [num_filters, filter_dim]
-  CuVector bias_;
-  CuMatrix filters_grad_;
-  CuVector bias_grad_;
+  CuMatrix<BaseFloat> filters_;                           // row = vectorised rectangular filter [num_filters, filter_dim]
+  CuVector<BaseFloat> bias_;
+  CuMatrix<BaseFloat> filters_grad_;
+  CuVector<BaseFloat> bias_grad_;
   BaseFloat learn_rate_coef_, bias_learn_rate_coef_, max_norm_;
-  CuMatrix patches_;                           // [frames * num_patches, filter_dim] of the last Propagate
-  CuMatrix patch_diffs_;
-  CuMatrix diff_patch_;                        // dense copy of one patch position's derivative columns (odd shapes only)
+  CuMatrix<BaseFloat> patches_;                           // [frames * num_patches, filter_dim] of the last Propagate
+  CuMatrix<BaseFloat> patch_diffs_;
+  CuMatrix<BaseFloat> diff_patch_;                        // dense copy of one patch position's derivative columns (odd shapes only)
 };
 
 class MaxPoolingComponent : public Component {
@@ -230,13 +230,13 @@ class MaxPoolingComponent : public Component {
     WriteToken(os, binary, "<PoolStep>"); WriteBasicType(os, binary, pool_step_);
     WriteToken(os, binary, "<PoolStride>"); WriteBasicType(os, binary, pool_stride_);
   }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     int32 num_patches, num_pools;
     PoolGeometry(&num_patches, &num_pools);
     KALDI_ASSERT(output_dim_ == num_pools * pool_stride_);
     ASLP_OK(aslp_maxpool_fwd(CuStream(), out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), num_pools, pool_size_, pool_step_, pool_stride_));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     int32 num_patches, num_pools;
     PoolGeometry(&num_patches, &num_pools);
     ASLP_OK(aslp_maxpool_bwd(CuStream(), in_diff->Data(), in_diff->Stride(), in.Data(), in.Stride(), out.Data(), out.Stride(), out_diff.Data(),

@@ -41,7 +41,7 @@ class GruStreams : public UpdatableComponent {
   void GetParams(Vector<BaseFloat>* w) const {
     w->Resize(NumParams());
     float* p = w->Data();
-    for (const CuMatrix* m : {&w_zrm_x_, &w_zr_h_, &w_m_g_}) { CopyRowsToVec(*m, p); p += static_cast<size_t>(m->NumRows()) * m->NumCols(); }
+    for (const CuMatrix<BaseFloat>* m : {&w_zrm_x_, &w_zr_h_, &w_m_g_}) { CopyRowsToVec(*m, p); p += static_cast<size_t>(m->NumRows()) * m->NumCols(); }
     Vector<float> b; bias_.CopyToVec(&b);
     for (int32 i = 0; i < b.Dim(); ++i) *p++ = b(i);
   }
@@ -68,7 +68,7 @@ class GruStreams : public UpdatableComponent {
   }
   void SetSeqLengths(const std::vector<int32>& l) { nstream_ = static_cast<int32>(l.size()); prev_state_.Resize(nstream_, 5 * output_dim_, kSetZero); }
 
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     if (nstream_ == 0) {
       per_utt_reset_ = true; nstream_ = 1;
       prev_state_.Resize(nstream_, 5 * output_dim_, kSetZero);
@@ -81,7 +81,7 @@ class GruStreams : public UpdatableComponent {
     prop_.Resize((T + 2) * S, 5 * H, kUndefined);
     prop_.RowRange(0, S).CopyFromMat(prev_state_);
     prop_.RowRange((T + 1) * S, S).SetZero();
-    CuSubMatrix zrm = prop_.Range(S, T * S, 0, 3 * H);
+    CuSubMatrix<BaseFloat> zrm = prop_.Range(S, T * S, 0, 3 * H);
     ASLP_OK(aslp_gemm(st, 0, 1, T * S, 3 * H, input_dim_, 1.0f, in.Data(), in.Stride(), w_zrm_x_.Data(), w_zrm_x_.Stride(), 0.0f, zrm.Data(), zrm.Stride(),
                       bias_.Data(), 0.0f, GemmPrecision(), nullptr, 0));
     aslp_gru_t g = MakeArgs(T, S, false);
@@ -90,20 +90,20 @@ class GruStreams : public UpdatableComponent {
     out->CopyFromMat(prop_.Range(S, T * S, 4 * H, H));
     prev_state_.CopyFromMat(prop_.RowRange(T * S, S));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     const int32 S = nstream_, T = in.NumRows() / S, H = output_dim_;
     aslp_stream_t st = CuStream();
     back_.Resize((T + 2) * S, 5 * H, kUndefined);
     back_.RowRange(0, S).SetZero();
     back_.RowRange((T + 1) * S, S).SetZero();
-    CuSubMatrix dh = back_.Range(S, T * S, 4 * H, H);
+    CuSubMatrix<BaseFloat> dh = back_.Range(S, T * S, 4 * H, H);
     dh.CopyFromMat(out_diff);
     aslp_gru_t g = MakeArgs(T, S, true);
     const size_t wsb = aslp_gru_workspace_bytes(T, S, H, 1);
     ASLP_OK(aslp_gru_seq_bwd(st, &g, CuWorkspace(wsb), wsb));
     const float mmt = opts_.momentum, clip = clip_gradient_;
     const int prec = GemmPrecision();
-    CuSubMatrix dzrm = back_.Range(S, T * S, 0, 3 * H), dzr = back_.Range(S, T * S, 0, 2 * H), dm = back_.Range(S, T * S, 2 * H, H);
+    CuSubMatrix<BaseFloat> dzrm = back_.Range(S, T * S, 0, 3 * H), dzr = back_.Range(S, T * S, 0, 2 * H), dm = back_.Range(S, T * S, 2 * H, H);
     ASLP_OK(aslp_gemm(st, 0, 0, T * S, input_dim_, 3 * H, 1.0f, dzrm.Data(), dzrm.Stride(), w_zrm_x_.Data(), w_zrm_x_.Stride(), 0.0f, in_diff->Data(),
                       in_diff->Stride(), nullptr, 0.0f, prec, nullptr, 0));
     const size_t gws = 64u << 20;
@@ -111,13 +111,13 @@ class GruStreams : public UpdatableComponent {
     ASLP_OK(aslp_gemm(st, 1, 0, 3 * H, input_dim_, T * S, 1.0f, dzrm.Data(), dzrm.Stride(), in.Data(), in.Stride(), mmt, w_zrm_x_corr_.Data(),
                       w_zrm_x_corr_.Stride(), nullptr, clip, prec, ws, gws));
     ASLP_OK(aslp_col_sum(st, bias_corr_.Data(), dzrm.Data(), dzrm.Stride(), T * S, 3 * H, 1.0f, mmt, clip));
-    CuSubMatrix h_prev = prop_.Range(0, T * S, 4 * H, H), yg = prop_.Range(S, T * S, 3 * H, H);
+    CuSubMatrix<BaseFloat> h_prev = prop_.Range(0, T * S, 4 * H, H), yg = prop_.Range(S, T * S, 3 * H, H);
     ASLP_OK(aslp_gemm(st, 1, 0, 2 * H, H, T * S, 1.0f, dzr.Data(), dzr.Stride(), h_prev.Data(), h_prev.Stride(), mmt, w_zr_h_corr_.Data(),
                       w_zr_h_corr_.Stride(), nullptr, clip, prec, ws, gws));
     ASLP_OK(aslp_gemm(st, 1, 0, H, H, T * S, 1.0f, dm.Data(), dm.Stride(), yg.Data(), yg.Stride(), mmt, w_m_g_corr_.Data(), w_m_g_corr_.Stride(),
                       nullptr, clip, prec, ws, gws));
   }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     const float lr = opts_.learn_rate;
     w_zrm_x_.AddMat(-lr, w_zrm_x_corr_); w_zr_h_.AddMat(-lr, w_zr_h_corr_); w_m_g_.AddMat(-lr, w_m_g_corr_);
     const int32 ld = (bias_.Dim() + 3) / 4 * 4;
@@ -142,9 +142,9 @@ class GruStreams : public UpdatableComponent {
   int32 nstream_;
   BaseFloat clip_gradient_;
   bool per_utt_reset_;
-  CuMatrix w_zrm_x_, w_zr_h_, w_m_g_, w_zrm_x_corr_, w_zr_h_corr_, w_m_g_corr_;
-  CuVector bias_, bias_corr_;
-  CuMatrix prop_, back_, prev_state_;
+  CuMatrix<BaseFloat> w_zrm_x_, w_zr_h_, w_m_g_, w_zrm_x_corr_, w_zr_h_corr_, w_m_g_corr_;
+  CuVector<BaseFloat> bias_, bias_corr_;
+  CuMatrix<BaseFloat> prop_, back_, prev_state_;
 };
 
 }  // namespace aslp_nnet

@@ -40,7 +40,7 @@ void Xent::Progress(double num_frames) {
   }
 }
 
-void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const CuMatrixBase& targets, CuMatrix* diff) {
+void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& targets, CuMatrix<BaseFloat>* diff) {
   KALDI_ASSERT(net_out.NumCols() == targets.NumCols() && net_out.NumRows() == targets.NumRows());
   KALDI_ASSERT(net_out.NumRows() == frame_weights.Dim());
   KALDI_ASSERT(KALDI_ISFINITE(frame_weights.Sum()));
@@ -52,7 +52,7 @@ void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_
   Progress(frame_weights.Sum());
 }
 
-void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff) {
+void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
   const int32 num_frames = net_out.NumRows(), num_pdf = net_out.NumCols();
   KALDI_ASSERT(num_frames == static_cast<int32>(post.size()));
   KALDI_ASSERT(num_frames == frame_weights.Dim());
@@ -91,7 +91,7 @@ void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_
   Progress(nf);
 }
 
-void Xent::Eval(const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff) {
+void Xent::Eval(const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
   Vector<BaseFloat> ones(static_cast<int32>(post.size()));
   for (int32 i = 0; i < ones.Dim(); ++i) ones(i) = 1.0f;
   Eval(ones, net_out, post, diff);
@@ -122,8 +122,8 @@ void WarpCtc::SetUseGpu(bool use_gpu) {
   if (!use_gpu) KALDI_ERR << "WarpCtc: this build has no CPU path (--use-gpu=no is the reference oracle, not the product)";
 }
 
-void WarpCtc::Eval(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
-                   const std::vector<std::vector<int32>>& labels, CuMatrix* diff) {
+void WarpCtc::Eval(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out,
+                   const std::vector<std::vector<int32>>& labels, CuMatrix<BaseFloat>* diff) {
   KALDI_ASSERT(diff != NULL);
   // the C API wants activations with row stride == alphabet size (include/ctc.h)
   if (net_out.Stride() != net_out.NumCols())
@@ -164,7 +164,7 @@ void WarpCtc::Eval(const std::vector<std::string>& utt, const std::vector<int32>
 // running mean / sigma of the per-frame loss over a sliding window of stat_period_ utterances; an utterance whose
 // loss is non-finite, outside 6 sigma, or outside (0, 3000) has its diff rows zeroed (warp-ctc.cc:288-365)
 void WarpCtc::StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
-                                      const std::vector<float>& pzx_host, CuMatrix* diff) {
+                                      const std::vector<float>& pzx_host, CuMatrix<BaseFloat>* diff) {
   const int32 num_sequence = static_cast<int32>(frame_num_utt.size());
   for (int s = 0; s < num_sequence; s++) {
     const double loss_per_frame = pzx_host[s] / frame_num_utt[s];
@@ -230,7 +230,7 @@ int32 LevenshteinEditDistance(const std::vector<int32>& ref, const std::vector<i
 }
 
 // greedy decode: per-frame arg-max -> collapse repeats -> drop blank (0) -> edit distance (warp-ctc.cc:487-526)
-void WarpCtc::ErrorRate(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label) {
+void WarpCtc::ErrorRate(const std::vector<int>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out, std::vector<std::vector<int>>& label) {
   const int32 rows = net_out.NumRows();
   int32* idx_dev = static_cast<int32*>(CuWorkspace(sizeof(int32) * (rows + 4)));
   ASLP_OK(aslp_row_argmax(CuStream(), idx_dev, net_out.Data(), net_out.Stride(), rows, net_out.NumCols()));
@@ -268,8 +268,8 @@ Ctc::Ctc()
       sequences_progress_(0), obj_progress_(0.0), report_step_(100), obj_(0), loss_sum_(0), loss_square_sum_(0), loss_sum_bak_(0),
       loss_square_sum_bak_(0), normal_num_(0), stat_period_(100) {}
 
-void Ctc::EvalParallel(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
-                       std::vector<std::vector<int32>>& label, CuMatrix* diff) {
+void Ctc::EvalParallel(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out,
+                       std::vector<std::vector<int32>>& label, CuMatrix<BaseFloat>* diff) {
   KALDI_ASSERT(diff != NULL);
   diff->Resize(net_out.NumRows(), net_out.NumCols(), kUndefined);      // the kernel writes every element
   const int32 num_sequence = static_cast<int32>(frame_num_utt.size());
@@ -310,7 +310,7 @@ void Ctc::EvalParallel(const std::vector<std::string>& utt, const std::vector<in
   }
 }
 
-void Ctc::Eval(const CuMatrixBase& net_out, const std::vector<int32>& label, CuMatrix* diff) {
+void Ctc::Eval(const CuMatrixBase<BaseFloat>& net_out, const std::vector<int32>& label, CuMatrix<BaseFloat>* diff) {
   std::vector<std::string> utt(1, "utt");
   std::vector<int32> frames(1, net_out.NumRows());
   std::vector<std::vector<int32>> labels(1, label);
@@ -319,7 +319,7 @@ void Ctc::Eval(const CuMatrixBase& net_out, const std::vector<int32>& label, CuM
 
 // ctc-loss.cc:229-296: unlike the warp-ctc variant the warm-up half of the window only takes finite losses in (0, 3000)
 void Ctc::StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
-                                  const std::vector<float>& pzx_host, CuMatrix* diff) {
+                                  const std::vector<float>& pzx_host, CuMatrix<BaseFloat>* diff) {
   const int32 num_sequence = static_cast<int32>(frame_num_utt.size());
   for (int s = 0; s < num_sequence; s++) {
     const double loss_per_frame = pzx_host[s] / frame_num_utt[s];
@@ -362,7 +362,7 @@ void Ctc::StatAndAverageLossCheck(const std::vector<std::string>& utt, const std
   sequences_num_ += num_sequence;
 }
 
-void Ctc::ErrorRateMSeq(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label) {
+void Ctc::ErrorRateMSeq(const std::vector<int>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out, std::vector<std::vector<int>>& label) {
   const int32 rows = net_out.NumRows();
   int32* idx_dev = static_cast<int32*>(CuWorkspace(sizeof(int32) * (rows + 4)));
   ASLP_OK(aslp_row_argmax(CuStream(), idx_dev, net_out.Data(), net_out.Stride(), rows, net_out.NumCols()));

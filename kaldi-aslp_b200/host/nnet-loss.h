@@ -17,10 +17,10 @@ class Xent {
   Xent();
   ~Xent();
   // dense targets (soft labels)
-  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const CuMatrixBase& targets, CuMatrix* diff);
+  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& targets, CuMatrix<BaseFloat>* diff);
   // posterior targets: one fused sparse pass when every frame has at most one pdf, dense otherwise
-  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff);
-  void Eval(const CuMatrixBase& net_out, const Posterior& post, CuMatrix* diff);
+  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff);
+  void Eval(const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff);
   std::string Report();
   BaseFloat AvgLoss();
   double Frames() { Fetch(); return frames_; }
@@ -31,8 +31,8 @@ class Xent {
   double* stats_dev_;           // [ce, entropy, likelihood, correct, frames] accumulated on the device
   double frames_, correct_, loss_, entropy_, likelyhood_;
   double frames_progress_, base_[5];
-  CuMatrix tgt_mat_;
-  CuVector frame_w_dev_, tgt_w_dev_;
+  CuMatrix<BaseFloat> tgt_mat_;
+  CuVector<BaseFloat> frame_w_dev_, tgt_w_dev_;
   CuArrayInt tgt_idx_dev_;
 };
 
@@ -41,9 +41,9 @@ class WarpCtc {
   WarpCtc();
   // CTC training over multiple sequences; net_out rows are stream-interleaved (t * num_seq + s). diff receives
   // d(loss)/d(activation) clipped to [-1, 1] after the average-loss guard (warp-ctc.cc:33-286)
-  void Eval(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
-            const std::vector<std::vector<int32>>& labels, CuMatrix* diff);
-  void ErrorRate(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label);
+  void Eval(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out,
+            const std::vector<std::vector<int32>>& labels, CuMatrix<BaseFloat>* diff);
+  void ErrorRate(const std::vector<int>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out, std::vector<std::vector<int>>& label);
   void SetReportStep(int32 report_step) { report_step_ = report_step; }
   std::string Report();
   float NumErrorTokens() const { return error_num_; }
@@ -52,7 +52,7 @@ class WarpCtc {
   const std::vector<float>& LastCosts() const { return costs_; }
  private:
   void StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
-                               const std::vector<float>& pzx_host, CuMatrix* diff);
+                               const std::vector<float>& pzx_host, CuMatrix<BaseFloat>* diff);
   int32 frames_, sequences_num_, ref_num_;
   float error_num_;
   int32 frames_progress_, ref_num_progress_;
@@ -74,11 +74,11 @@ class WarpCtc {
 class Ctc {
  public:
   Ctc();
-  void EvalParallel(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase& net_out,
-                    std::vector<std::vector<int32>>& label, CuMatrix* diff);
+  void EvalParallel(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out,
+                    std::vector<std::vector<int32>>& label, CuMatrix<BaseFloat>* diff);
   // single sequence (ctc-loss.cc:33-113): the multi-sequence path with one stream
-  void Eval(const CuMatrixBase& net_out, const std::vector<int32>& label, CuMatrix* diff);
-  void ErrorRateMSeq(const std::vector<int>& frame_num_utt, const CuMatrixBase& net_out, std::vector<std::vector<int>>& label);
+  void Eval(const CuMatrixBase<BaseFloat>& net_out, const std::vector<int32>& label, CuMatrix<BaseFloat>* diff);
+  void ErrorRateMSeq(const std::vector<int>& frame_num_utt, const CuMatrixBase<BaseFloat>& net_out, std::vector<std::vector<int>>& label);
   void SetReportStep(int32 report_step) { report_step_ = report_step; }
   std::string Report();
   float NumErrorTokens() const { return error_num_; }
@@ -86,7 +86,7 @@ class Ctc {
   const std::vector<float>& LastObj() const { return pzx_; }      // -log p(z|x) per sequence of the last call
  private:
   void StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
-                               const std::vector<float>& pzx_host, CuMatrix* diff);
+                               const std::vector<float>& pzx_host, CuMatrix<BaseFloat>* diff);
   int32 frames_, sequences_num_, ref_num_;
   float error_num_;
   int32 frames_progress_, ref_num_progress_;
@@ -99,7 +99,7 @@ class Ctc {
   int32 normal_num_, stat_period_;
   std::vector<float> pzx_;
   CuArrayInt labels_dev_, seq_len_dev_;
-  CuVector pzx_dev_;
+  CuVector<BaseFloat> pzx_dev_;
 };
 
 int32 LevenshteinEditDistance(const std::vector<int32>& ref, const std::vector<int32>& hyp, int32* ins, int32* del, int32* sub);

@@ -93,8 +93,8 @@ int32 LstmFamily::NumParams() const {
 void LstmFamily::GetParams(Vector<BaseFloat>* wei_copy) const {
   wei_copy->Resize(NumParams());
   float* p = wei_copy->Data();
-  auto vec = [&](const CuVector& v) { Vector<float> h; v.CopyToVec(&h); for (int32 i = 0; i < h.Dim(); ++i) *p++ = h(i); };
-  auto mat = [&](const CuMatrix& m) { CopyRowsToVec(m, p); p += static_cast<size_t>(m.NumRows()) * m.NumCols(); };
+  auto vec = [&](const CuVector<BaseFloat>& v) { Vector<float> h; v.CopyToVec(&h); for (int32 i = 0; i < h.Dim(); ++i) *p++ = h(i); };
+  auto mat = [&](const CuMatrix<BaseFloat>& m) { CopyRowsToVec(m, p); p += static_cast<size_t>(m.NumRows()) * m.NumCols(); };
   for (const Dir& d : d_) {
     mat(d.w_gifo_x); mat(d.w_gifo_r); vec(d.bias); vec(d.peep_i); vec(d.peep_f); vec(d.peep_o);
     if (tr_.projected) mat(d.w_r_m);
@@ -194,7 +194,7 @@ void LstmFamily::FillDirArgs(void* arr_v, int T, int S, bool bwd) {
   }
 }
 
-void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+void LstmFamily::PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
   if (nstream_ == 0) {
     if (tr_.use_seq_lengths) KALDI_ERR << "SetSeqLengths must be called before Propagate for " << TypeToMarker(GetType());
     per_utt_reset_ = true;          // nnet-forward: one stream, state reset per utterance
@@ -214,7 +214,7 @@ void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
     d.prop.RowRange((T + 1) * S, S).SetZero();
     if (i == 0 && tr_.carry_state) d.prop.RowRange(0, S).CopyFromMat(prev_state_);
     // x -> g,i,f,o for the whole chunk, bias fused in the epilogue (lc.h:552-555, :632-645)
-    CuSubMatrix gifo = d.prop.Range(S, T * S, 0, 4 * C);
+    CuSubMatrix<BaseFloat> gifo = d.prop.Range(S, T * S, 0, 4 * C);
     ASLP_OK(aslp_gemm(st, 0, 1, T * S, 4 * C, input_dim_, 1.0f, in.Data(), in.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(), 0.0f,
                       gifo.Data(), gifo.Stride(), d.bias.Data(), 0.0f, GemmPrecision(), nullptr, 0));
   }
@@ -229,7 +229,7 @@ void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
       // the carried r(0) was projected with the W_r_m of the PREVIOUS minibatch (the weights have been updated since), so
       // the first step cannot go through W': feed r(0) W_gifo_r^T into the first step's pre-activations and hide m(0)
       Dir& d = d_[0];
-      CuSubMatrix r0 = d.prop.Range(0, S, 7 * C, nrecur_), gifo1 = d.prop.Range(S, S, 0, 4 * C), m0 = d.prop.Range(0, S, 6 * C, C);
+      CuSubMatrix<BaseFloat> r0 = d.prop.Range(0, S, 7 * C, nrecur_), gifo1 = d.prop.Range(S, S, 0, 4 * C), m0 = d.prop.Range(0, S, 6 * C, C);
       ASLP_OK(aslp_gemm(st, 0, 1, S, 4 * C, nrecur_, 1.0f, r0.Data(), r0.Stride(), d.w_gifo_r.Data(), d.w_gifo_r.Stride(), 1.0f,
                         gifo1.Data(), gifo1.Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
       m0.SetZero();
@@ -242,7 +242,7 @@ void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
   if (fold) {
     // r(t) = m(t) W_r_m^T for the whole chunk at once
     for (Dir& d : d_) {
-      CuSubMatrix ym = d.prop.Range(S, T * S, 6 * C, C), yr = d.prop.Range(S, T * S, 7 * C, nrecur_);
+      CuSubMatrix<BaseFloat> ym = d.prop.Range(S, T * S, 6 * C, C), yr = d.prop.Range(S, T * S, 7 * C, nrecur_);
       ASLP_OK(aslp_gemm(st, 0, 1, T * S, nrecur_, C, 1.0f, ym.Data(), ym.Stride(), d.w_r_m.Data(), d.w_r_m.Stride(), 0.0f,
                         yr.Data(), yr.Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
     }
@@ -254,12 +254,12 @@ void LstmFamily::PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
   }
   const int32 O = OutPerDir(), col = tr_.projected ? 7 * C : 6 * C;
   for (int i = 0; i < tr_.ndirs; ++i) {
-    CuSubMatrix dst = out->ColRange(i * O, O);
+    CuSubMatrix<BaseFloat> dst = out->ColRange(i * O, O);
     dst.CopyFromMat(d_[i].prop.Range(S, T * S, col, O));
   }
 }
 
-void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+void LstmFamily::BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
   const int32 S = nstream_, T = in.NumRows() / S, C = ncell_, W = Width();
   const int32 O = OutPerDir(), ocol = tr_.projected ? 7 * C : 6 * C;
   aslp_stream_t st = CuStream();
@@ -268,7 +268,7 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
     d.back.Resize((T + 2) * S, W, kUndefined);
     d.back.RowRange(0, S).SetZero();
     d.back.RowRange((T + 1) * S, S).SetZero();
-    CuSubMatrix od = d.back.Range(S, T * S, ocol, O);
+    CuSubMatrix<BaseFloat> od = d.back.Range(S, T * S, ocol, O);
     od.CopyFromMat(out_diff.ColRange(i * O, O));
   }
   const bool fold = FoldProjection();
@@ -276,7 +276,7 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
   if (fold) {
     // the out_diff share of d_m for every step: out_diff_r W_r_m, placed where the kernel expects out_diff (m columns)
     for (Dir& d : d_) {
-      CuSubMatrix od = d.back.Range(S, T * S, 7 * C, nrecur_), odm = d.back.Range(S, T * S, 6 * C, C);
+      CuSubMatrix<BaseFloat> od = d.back.Range(S, T * S, 7 * C, nrecur_), odm = d.back.Range(S, T * S, 6 * C, C);
       ASLP_OK(aslp_gemm(st, 0, 0, T * S, C, nrecur_, 1.0f, od.Data(), od.Stride(), d.w_r_m.Data(), d.w_r_m.Stride(), 0.0f,
                         odm.Data(), odm.Stride(), nullptr, 0.0f, prec, nullptr, 0));
     }
@@ -290,7 +290,7 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
     // the boundary blocks of the derivative buffer are zero
     for (int i = 0; i < tr_.ndirs; ++i) {
       Dir& d = d_[i];
-      CuSubMatrix dg_next = d.back.Range(i == 0 ? 2 * S : 0, T * S, 0, 4 * C), dr = d.back.Range(S, T * S, 7 * C, nrecur_);
+      CuSubMatrix<BaseFloat> dg_next = d.back.Range(i == 0 ? 2 * S : 0, T * S, 0, 4 * C), dr = d.back.Range(S, T * S, 7 * C, nrecur_);
       ASLP_OK(aslp_gemm(st, 0, 0, T * S, nrecur_, 4 * C, 1.0f, dg_next.Data(), dg_next.Stride(), d.w_gifo_r.Data(), d.w_gifo_r.Stride(), 1.0f,
                         dr.Data(), dr.Stride(), nullptr, 0.0f, prec, nullptr, 0));
     }
@@ -299,7 +299,7 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
   const float mmt = opts_.momentum, clip = clip_gradient_;
   for (int i = 0; i < tr_.ndirs; ++i) {
     Dir& d = d_[i];
-    CuSubMatrix dgifo = d.back.Range(S, T * S, 0, 4 * C);
+    CuSubMatrix<BaseFloat> dgifo = d.back.Range(S, T * S, 0, 4 * C);
     // g,i,f,o -> x (lc.h:963-965): second direction accumulates
     ASLP_OK(aslp_gemm(st, 0, 0, T * S, input_dim_, 4 * C, 1.0f, dgifo.Data(), dgifo.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(),
                       i == 0 ? 0.0f : 1.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, prec, nullptr, 0));
@@ -317,36 +317,36 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& ou
     // rows of the forward buffers that held the recurrent input / previous cell of each step:
     // direction 0 read t-1 (rows [0,T*S)), direction 1 read t+1 (rows [2S,(T+2)S))   (lc.h:981-1000 vs :1022-1040)
     const int32 prev0 = i == 0 ? 0 : 2 * S;
-    CuSubMatrix dgifo = d.back.Range(S, T * S, 0, 4 * C);
+    CuSubMatrix<BaseFloat> dgifo = d.back.Range(S, T * S, 0, 4 * C);
     const size_t gws = 64u << 20;
     void* ws = CuWorkspace(gws);
     ASLP_OK(aslp_gemm(st, 1, 0, 4 * C, input_dim_, T * S, 1.0f, dgifo.Data(), dgifo.Stride(), in.Data(), in.Stride(), mmt,
                       d.w_gifo_x_corr.Data(), d.w_gifo_x_corr.Stride(), nullptr, clip, prec, ws, gws));
-    CuSubMatrix rec_prev = d.prop.Range(prev0, T * S, ocol, RecDim());
+    CuSubMatrix<BaseFloat> rec_prev = d.prop.Range(prev0, T * S, ocol, RecDim());
     ASLP_OK(aslp_gemm(st, 1, 0, 4 * C, RecDim(), T * S, 1.0f, dgifo.Data(), dgifo.Stride(), rec_prev.Data(), rec_prev.Stride(), mmt,
                       d.w_gifo_r_corr.Data(), d.w_gifo_r_corr.Stride(), nullptr, clip, prec, ws, gws));
     ASLP_OK(aslp_col_sum(st, d.bias_corr.Data(), dgifo.Data(), dgifo.Stride(), T * S, 4 * C, 1.0f, mmt, clip));
-    CuSubMatrix c_prev = d.prop.Range(prev0, T * S, 4 * C, C), c_cur = d.prop.Range(S, T * S, 4 * C, C);
-    CuSubMatrix di = d.back.Range(S, T * S, C, C), df = d.back.Range(S, T * S, 2 * C, C), d_out = d.back.Range(S, T * S, 3 * C, C);
+    CuSubMatrix<BaseFloat> c_prev = d.prop.Range(prev0, T * S, 4 * C, C), c_cur = d.prop.Range(S, T * S, 4 * C, C);
+    CuSubMatrix<BaseFloat> di = d.back.Range(S, T * S, C, C), df = d.back.Range(S, T * S, 2 * C, C), d_out = d.back.Range(S, T * S, 3 * C, C);
     ASLP_OK(aslp_col_dot(st, d.peep_i_corr.Data(), di.Data(), di.Stride(), c_prev.Data(), c_prev.Stride(), T * S, C, 1.0f, mmt, clip));
     ASLP_OK(aslp_col_dot(st, d.peep_f_corr.Data(), df.Data(), df.Stride(), c_prev.Data(), c_prev.Stride(), T * S, C, 1.0f, mmt, clip));
     ASLP_OK(aslp_col_dot(st, d.peep_o_corr.Data(), d_out.Data(), d_out.Stride(), c_cur.Data(), c_cur.Stride(), T * S, C, 1.0f, mmt, clip));
     if (tr_.projected) {
-      CuSubMatrix dr = d.back.Range(S, T * S, 7 * C, nrecur_), ym = d.prop.Range(S, T * S, 6 * C, C);
+      CuSubMatrix<BaseFloat> dr = d.back.Range(S, T * S, 7 * C, nrecur_), ym = d.prop.Range(S, T * S, 6 * C, C);
       ASLP_OK(aslp_gemm(st, 1, 0, nrecur_, C, T * S, 1.0f, dr.Data(), dr.Stride(), ym.Data(), ym.Stride(), mmt,
                         d.w_r_m_corr.Data(), d.w_r_m_corr.Stride(), nullptr, clip, prec, ws, gws));
     }
   }
 }
 
-void LstmFamily::Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+void LstmFamily::Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
   // plain -lr * corr: no per-component coefficient, no L2 (lc.h:1085-1110)
   const float lr = opts_.learn_rate;
   std::unique_ptr<CuStreamScope> side_scope;
   if (async_tail_) side_scope.reset(new CuStreamScope(CuSideStream()));     // stays behind this component's weight-gradient GEMMs
   aslp_stream_t st = CuStream();
-  auto mat = [&](CuMatrix& w, const CuMatrix& c) { ASLP_OK(aslp_axpby(st, w.Data(), w.Stride(), c.Data(), c.Stride(), w.NumRows(), w.NumCols(), -lr, 1.0f)); };
-  auto vec = [&](CuVector& w, const CuVector& c) { ASLP_OK(aslp_axpby(st, w.Data(), (w.Dim() + 3) / 4 * 4, c.Data(), (c.Dim() + 3) / 4 * 4, 1, w.Dim(), -lr, 1.0f)); };
+  auto mat = [&](CuMatrix<BaseFloat>& w, const CuMatrix<BaseFloat>& c) { ASLP_OK(aslp_axpby(st, w.Data(), w.Stride(), c.Data(), c.Stride(), w.NumRows(), w.NumCols(), -lr, 1.0f)); };
+  auto vec = [&](CuVector<BaseFloat>& w, const CuVector<BaseFloat>& c) { ASLP_OK(aslp_axpby(st, w.Data(), (w.Dim() + 3) / 4 * 4, c.Data(), (c.Dim() + 3) / 4 * 4, 1, w.Dim(), -lr, 1.0f)); };
   for (Dir& d : d_) {
     mat(d.w_gifo_x, d.w_gifo_x_corr); mat(d.w_gifo_r, d.w_gifo_r_corr); vec(d.bias, d.bias_corr);
     vec(d.peep_i, d.peep_i_corr); vec(d.peep_f, d.peep_f_corr); vec(d.peep_o, d.peep_o_corr);

@@ -48,22 +48,22 @@ class LstmFamily : public UpdatableComponent {
   void SetSeqLengths(const std::vector<int32>& sequence_lengths);
   void SetChunkSize(int32 chunk_size) { chunk_size_ = chunk_size; }
 
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out);
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff);
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff);
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out);
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff);
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff);
 
   // test / tooling access
-  const CuMatrix& PropagateBuf(int dir) const { return d_[dir].prop; }
-  const CuMatrix& BackpropagateBuf(int dir) const { return d_[dir].back; }
+  const CuMatrix<BaseFloat>& PropagateBuf(int dir) const { return d_[dir].prop; }
+  const CuMatrix<BaseFloat>& BackpropagateBuf(int dir) const { return d_[dir].back; }
 
  private:
   struct Dir {
-    CuMatrix w_gifo_x, w_gifo_r, w_r_m;
-    CuVector bias, peep_i, peep_f, peep_o;
-    CuMatrix w_gifo_x_corr, w_gifo_r_corr, w_r_m_corr;
-    CuVector bias_corr, peep_i_corr, peep_f_corr, peep_o_corr;
-    CuMatrix prop, back;
-    CuMatrix w_fused;      // W_gifo_r * W_r_m [4C, C]: the projection folded into the recurrence (rebuilt every Propagate)
+    CuMatrix<BaseFloat> w_gifo_x, w_gifo_r, w_r_m;
+    CuVector<BaseFloat> bias, peep_i, peep_f, peep_o;
+    CuMatrix<BaseFloat> w_gifo_x_corr, w_gifo_r_corr, w_r_m_corr;
+    CuVector<BaseFloat> bias_corr, peep_i_corr, peep_f_corr, peep_o_corr;
+    CuMatrix<BaseFloat> prop, back;
+    CuMatrix<BaseFloat> w_fused;      // W_gifo_r * W_r_m [4C, C]: the projection folded into the recurrence (rebuilt every Propagate)
   };
   void AllocCorr();
   int32 Width() const { return 7 * ncell_ + nrecur_; }
@@ -76,7 +76,7 @@ class LstmFamily : public UpdatableComponent {
   int32 ncell_, nrecur_, nstream_, chunk_size_;
   BaseFloat clip_gradient_;
   std::vector<Dir> d_;
-  CuMatrix prev_state_;                 // [S, 7C+R] forward-direction carried state
+  CuMatrix<BaseFloat> prev_state_;                 // [S, 7C+R] forward-direction carried state
   std::vector<int32> sequence_lengths_;
   CuArrayInt seq_len_dev_;
   bool async_tail_ = false;             // the last BackpropagateFnc put its weight gradients on the side stream

@@ -83,7 +83,7 @@ class BatchNormalization : public UpdatableComponent {
   std::string Info() const { return std::string("\n  batch_normaliztion"); }
   void CleanAccs() { acc_means_.SetZero(); acc_vars_.SetZero(); num_acc_frames_ = 0; }
 
-  void FeedforwardFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void FeedforwardFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     aslp_stream_t st = CuStream();
     if (num_acc_frames_ <= 0) {       // local statistics, nothing accumulated
       ASLP_OK(aslp_bn_fwd_train(st, out->Data(), out->Stride(), nullptr, 0, in.Data(), in.Stride(), in.NumRows(), output_dim_,
@@ -93,19 +93,19 @@ class BatchNormalization : public UpdatableComponent {
                                mean_vec_.Data(), var_vec_.Data()));
     }
   }
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     if (!acc_cleaned_) { acc_cleaned_ = true; CleanAccs(); }      // running sums restart with the first training propagate (:178-181)
     // no x-hat buffer: the backward kernels recompute it from in, mean_vec_ and var_vec_ (= 1/std)
     ASLP_OK(aslp_bn_fwd_train(CuStream(), out->Data(), out->Stride(), nullptr, 0, in.Data(), in.Stride(), in.NumRows(), output_dim_,
                               scale_.Data(), shift_.Data(), var_floor_, mean_vec_.Data(), var_vec_.Data(), acc_means_.Data(), acc_vars_.Data()));
     num_acc_frames_ += in.NumRows();
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     ASLP_OK(aslp_bn_bwd(CuStream(), in_diff ? in_diff->Data() : nullptr, in_diff ? in_diff->Stride() : 0, in.Data(), in.Stride(), nullptr,
                         0, out_diff.Data(), out_diff.Stride(), in.NumRows(), output_dim_, scale_.Data(), mean_vec_.Data(), var_vec_.Data(),
                         opts_.momentum, dscale_.Data(), dshift_.Data()));
   }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {       // plain -lr * d (no lr coefficient, :279-283)
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {       // plain -lr * d (no lr coefficient, :279-283)
     const BaseFloat lr = opts_.learn_rate;
     const int32 ld = (output_dim_ + 3) / 4 * 4;
     ASLP_OK(aslp_axpby(CuStream(), scale_.Data(), ld, dscale_.Data(), ld, 1, output_dim_, -lr, 1.0f));
@@ -113,7 +113,7 @@ class BatchNormalization : public UpdatableComponent {
   }
 
  private:
-  static void WriteAsFloat(const CuVectorD& v, std::ostream& os, bool binary) {
+  static void WriteAsFloat(const CuVector<double>& v, std::ostream& os, bool binary) {
     Vector<double> d;
     v.CopyToVec(&d);
     Vector<float> f(d.Dim());
@@ -126,9 +126,9 @@ class BatchNormalization : public UpdatableComponent {
     dscale_.Resize(output_dim_, kSetZero);
     dshift_.Resize(output_dim_, kSetZero);
   }
-  CuVector mean_vec_, var_vec_, scale_, dscale_, shift_, dshift_;
+  CuVector<BaseFloat> mean_vec_, var_vec_, scale_, dscale_, shift_, dshift_;
   BaseFloat var_floor_;
-  CuVectorD acc_means_, acc_vars_;
+  CuVector<double> acc_means_, acc_vars_;
   double num_acc_frames_;
   bool acc_cleaned_;
 };
@@ -183,13 +183,13 @@ class CompactFsmn : public UpdatableComponent {
   std::string Info() const { return std::string("\n  vec_coef") + MomentStatistics(vec_coef_); }
   std::string InfoGradient() const { return std::string("\n  vec_coef_grad") + MomentStatistics(vec_coef_corr_) + ", lr-coef " + ToString(learn_rate_coef_); }
 
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     KALDI_ASSERT(in.NumRows() <= max_frames_);             // the reference's hard limit (:38,174)
     KALDI_ASSERT(in.NumCols() == vec_coef_.NumCols());
     ASLP_OK(aslp_fsmn_fwd(CuStream(), out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), in.NumCols(), vec_coef_.Data(),
                           vec_coef_.Stride(), past_context_, future_context_));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     KALDI_ASSERT(in.NumRows() <= max_frames_);
     aslp_stream_t st = CuStream();
     ASLP_OK(aslp_fsmn_coef_grad(st, vec_coef_corr_.Data(), vec_coef_corr_.Stride(), in.Data(), in.Stride(), out_diff.Data(), out_diff.Stride(),
@@ -197,11 +197,11 @@ class CompactFsmn : public UpdatableComponent {
     ASLP_OK(aslp_fsmn_bwd(st, in_diff->Data(), in_diff->Stride(), out_diff.Data(), out_diff.Stride(), in.NumRows(), in.NumCols(), vec_coef_.Data(),
                           vec_coef_.Stride(), past_context_, future_context_));
   }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     vec_coef_.AddMat(-opts_.learn_rate * learn_rate_coef_, vec_coef_corr_);
   }
  private:
-  CuMatrix vec_coef_, vec_coef_corr_;
+  CuMatrix<BaseFloat> vec_coef_, vec_coef_corr_;
   int32 max_frames_;
   BaseFloat learn_rate_coef_;
   int32 past_context_, future_context_;
@@ -238,25 +238,25 @@ class RowConvolution : public UpdatableComponent {
   std::string InfoGradient() const { return std::string("  ") + "\n w_diff_ " + MomentStatistics(w_diff_) + "\n w_corr_ " + MomentStatistics(w_corr_); }
   void SetSeqLengths(const std::vector<int32>& sequence_lengths) { sequence_lengths_ = sequence_lengths; seq_len_dev_ = sequence_lengths; }
 
-  void PropagateFnc(const CuMatrixBase& in, CuMatrixBase* out) {
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     const int32 S = static_cast<int32>(sequence_lengths_.size());
     KALDI_ASSERT(S > 0 && in.NumRows() % S == 0);
     ASLP_OK(aslp_rowconv_fwd(CuStream(), out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows() / S, S, input_dim_, w_.Data(), w_.Stride(),
                              future_ctx_, seq_len_dev_.Data()));
   }
-  void BackpropagateFnc(const CuMatrixBase& in, const CuMatrixBase& out, const CuMatrixBase& out_diff, CuMatrixBase* in_diff) {
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     const int32 S = static_cast<int32>(sequence_lengths_.size());
     ASLP_OK(aslp_rowconv_bwd(CuStream(), in_diff->Data(), in_diff->Stride(), w_diff_.Data(), w_diff_.Stride(), in.Data(), in.Stride(), out_diff.Data(),
                              out_diff.Stride(), in.NumRows() / S, S, input_dim_, w_.Data(), w_.Stride(), future_ctx_, seq_len_dev_.Data()));
   }
-  void Update(const CuMatrixBase& input, const CuMatrixBase& diff) {     // w_corr = mmt*w_corr + w_diff ; w -= lr*w_corr (.cc:161-169)
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {     // w_corr = mmt*w_corr + w_diff ; w -= lr*w_corr (.cc:161-169)
     ASLP_OK(aslp_axpby(CuStream(), w_corr_.Data(), w_corr_.Stride(), w_diff_.Data(), w_diff_.Stride(), w_corr_.NumRows(), w_corr_.NumCols(), 1.0f, opts_.momentum));
     w_.AddMat(-opts_.learn_rate, w_corr_);
   }
  private:
   void AllocWork() { w_diff_.Resize(input_dim_, future_ctx_ + 1, kSetZero); w_corr_.Resize(input_dim_, future_ctx_ + 1, kSetZero); }
   int32 future_ctx_;
-  CuMatrix w_, w_diff_, w_corr_;
+  CuMatrix<BaseFloat> w_, w_diff_, w_corr_;
   std::vector<int32> sequence_lengths_;
   CuArrayInt seq_len_dev_;
 };

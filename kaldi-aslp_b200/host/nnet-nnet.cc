@@ -36,18 +36,18 @@ static bool DirectInput(const std::vector<Component*>& comps, int32 i) {
   return consumers == 1;
 }
 
-void Nnet::Propagate(const std::vector<const CuMatrixBase*>& in, std::vector<CuMatrix*>* out) {
+void Nnet::Propagate(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std::vector<CuMatrix<BaseFloat>*>* out) {
   KALDI_ASSERT(NULL != out);
   KALDI_ASSERT(in.size() == input_.size());
   const int32 num_frame = in[0]->NumRows();
   for (size_t i = 0; i < input_.size(); i++) {
-    CuMatrix& b = input_buf_[input_[i]];
+    CuMatrix<BaseFloat>& b = input_buf_[input_[i]];
     b.Resize(num_frame, components_[input_[i]]->InputDim(), kUndefined);
     b.CopyFromMat(*(in[i]));
   }
   for (int32 i = 0; i < NumComponents(); i++) {
     Component* c = components_[i];
-    const CuMatrixBase* src = &input_buf_[i];
+    const CuMatrixBase<BaseFloat>* src = &input_buf_[i];
     if (c->GetType() != Component::kInputLayer) {
       if (DirectInput(components_, i)) {
         src = &output_buf_[c->GetInput()[0]];
@@ -58,7 +58,7 @@ void Nnet::Propagate(const std::vector<const CuMatrixBase*>& in, std::vector<CuM
         input_buf_[i].Resize(num_frame, c->InputDim(), kSetZero);
         for (size_t j = 0; j < input_idx.size(); j++) {
           const int32 out_len = components_[input_idx[j]]->OutputDim();
-          CuSubMatrix dst = input_buf_[i].ColRange(offset[j], out_len);
+          CuSubMatrix<BaseFloat> dst = input_buf_[i].ColRange(offset[j], out_len);
           dst.AddMat(1.0, output_buf_[input_idx[j]]);
         }
       }
@@ -71,7 +71,7 @@ void Nnet::Propagate(const std::vector<const CuMatrixBase*>& in, std::vector<CuM
   for (size_t i = 0; i < output_.size(); i++) *((*out)[i]) = output_buf_[output_[i]];
 }
 
-void Nnet::Backpropagate(const std::vector<const CuMatrixBase*>& out_diff, std::vector<CuMatrix*>* in_diff) {
+void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_diff, std::vector<CuMatrix<BaseFloat>*>* in_diff) {
   KALDI_ASSERT(out_diff.size() == output_.size());
   const int32 num_frame = out_diff[0]->NumRows();
   std::vector<char> direct(NumComponents(), 0), fed_direct(NumComponents(), 0);
@@ -84,8 +84,8 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase*>& out_diff, std::
   for (size_t i = 0; i < output_.size(); i++) output_diff_buf_[output_[i]].CopyFromMat(*(out_diff[i]));
   for (int32 i = NumComponents() - 1; i >= 0; i--) {
     Component* c = components_[i];
-    const CuMatrixBase& cin = direct[i] ? static_cast<const CuMatrixBase&>(output_buf_[c->GetInput()[0]]) : input_buf_[i];
-    CuMatrix* target = direct[i] ? &output_diff_buf_[c->GetInput()[0]] : &input_diff_buf_[i];
+    const CuMatrixBase<BaseFloat>& cin = direct[i] ? static_cast<const CuMatrixBase<BaseFloat>&>(output_buf_[c->GetInput()[0]]) : input_buf_[i];
+    CuMatrix<BaseFloat>* target = direct[i] ? &output_diff_buf_[c->GetInput()[0]] : &input_diff_buf_[i];
     Timer tim;
     c->Backpropagate(cin, output_buf_[i], output_diff_buf_[i], target);
     if (c->IsUpdatable()) dynamic_cast<UpdatableComponent*>(c)->Update(cin, output_diff_buf_[i]);   // update inside backprop (:126-129)
@@ -107,18 +107,18 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase*>& out_diff, std::
     if ((*in_diff)[i] != NULL) *((*in_diff)[i]) = input_diff_buf_[input_[i]];
 }
 
-void Nnet::Feedforward(const std::vector<const CuMatrixBase*>& in, std::vector<CuMatrix*>* out) {
+void Nnet::Feedforward(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std::vector<CuMatrix<BaseFloat>*>* out) {
   KALDI_ASSERT(NULL != out);
   KALDI_ASSERT(in.size() == input_.size());
   const int32 num_frame = in[0]->NumRows();
   for (size_t i = 0; i < input_.size(); i++) {
-    CuMatrix& b = input_buf_[input_[i]];
+    CuMatrix<BaseFloat>& b = input_buf_[input_[i]];
     b.Resize(num_frame, components_[input_[i]]->InputDim(), kUndefined);
     b.CopyFromMat(*(in[i]));
   }
   for (int32 i = 0; i < NumComponents(); i++) {
     Component* c = components_[i];
-    const CuMatrixBase* src = &input_buf_[i];
+    const CuMatrixBase<BaseFloat>* src = &input_buf_[i];
     if (c->GetType() != Component::kInputLayer) {
       if (DirectInput(components_, i)) {
         src = &output_buf_[c->GetInput()[0]];
@@ -126,7 +126,7 @@ void Nnet::Feedforward(const std::vector<const CuMatrixBase*>& in, std::vector<C
         input_buf_[i].Resize(num_frame, c->InputDim(), kSetZero);
         for (size_t j = 0; j < c->GetInput().size(); j++) {
           const int32 s = c->GetInput()[j];
-          CuSubMatrix dst = input_buf_[i].ColRange(c->GetOffset()[j], components_[s]->OutputDim());
+          CuSubMatrix<BaseFloat> dst = input_buf_[i].ColRange(c->GetOffset()[j], components_[s]->OutputDim());
           dst.AddMat(1.0, output_buf_[s]);
         }
       }
@@ -136,27 +136,27 @@ void Nnet::Feedforward(const std::vector<const CuMatrixBase*>& in, std::vector<C
   for (size_t i = 0; i < output_.size(); i++) *((*out)[i]) = output_buf_[output_[i]];
 }
 
-void Nnet::Propagate(const CuMatrixBase& in, CuMatrix* out) {
+void Nnet::Propagate(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out) {
   KALDI_ASSERT(NULL != out);
   if (NumComponents() == 0) { (*out) = in; return; }
   KALDI_ASSERT(input_.size() == 1 && output_.size() == 1);
-  std::vector<const CuMatrixBase*> in_vec(1, &in);
-  std::vector<CuMatrix*> out_vec(1, out);
+  std::vector<const CuMatrixBase<BaseFloat>*> in_vec(1, &in);
+  std::vector<CuMatrix<BaseFloat>*> out_vec(1, out);
   Propagate(in_vec, &out_vec);
 }
-void Nnet::Backpropagate(const CuMatrixBase& out_diff, CuMatrix* in_diff) {
+void Nnet::Backpropagate(const CuMatrixBase<BaseFloat>& out_diff, CuMatrix<BaseFloat>* in_diff) {
   if (NumComponents() == 0) { if (in_diff) (*in_diff) = out_diff; return; }
   KALDI_ASSERT(input_.size() == 1 && output_.size() == 1);
-  std::vector<const CuMatrixBase*> od(1, &out_diff);
-  std::vector<CuMatrix*> id(1, in_diff);
+  std::vector<const CuMatrixBase<BaseFloat>*> od(1, &out_diff);
+  std::vector<CuMatrix<BaseFloat>*> id(1, in_diff);
   Backpropagate(od, &id);
 }
-void Nnet::Feedforward(const CuMatrixBase& in, CuMatrix* out) {
+void Nnet::Feedforward(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out) {
   KALDI_ASSERT(NULL != out);
   if (NumComponents() == 0) { (*out) = in; return; }
   KALDI_ASSERT(input_.size() == 1 && output_.size() == 1);
-  std::vector<const CuMatrixBase*> in_vec(1, &in);
-  std::vector<CuMatrix*> out_vec(1, out);
+  std::vector<const CuMatrixBase<BaseFloat>*> in_vec(1, &in);
+  std::vector<CuMatrix<BaseFloat>*> out_vec(1, out);
   Feedforward(in_vec, &out_vec);
 }
 

@@ -15,12 +15,12 @@ class Nnet {
   Nnet& operator=(const Nnet& other);
   ~Nnet();
 
-  void Propagate(const CuMatrixBase& in, CuMatrix* out);
-  void Propagate(const std::vector<const CuMatrixBase*>& in, std::vector<CuMatrix*>* out);
-  void Backpropagate(const CuMatrixBase& out_diff, CuMatrix* in_diff);
-  void Backpropagate(const std::vector<const CuMatrixBase*>& out_diff, std::vector<CuMatrix*>* in_diff);
-  void Feedforward(const CuMatrixBase& in, CuMatrix* out);
-  void Feedforward(const std::vector<const CuMatrixBase*>& in, std::vector<CuMatrix*>* out);
+  void Propagate(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out);
+  void Propagate(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std::vector<CuMatrix<BaseFloat>*>* out);
+  void Backpropagate(const CuMatrixBase<BaseFloat>& out_diff, CuMatrix<BaseFloat>* in_diff);
+  void Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_diff, std::vector<CuMatrix<BaseFloat>*>* in_diff);
+  void Feedforward(const CuMatrixBase<BaseFloat>& in, CuMatrix<BaseFloat>* out);
+  void Feedforward(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std::vector<CuMatrix<BaseFloat>*>* out);
   void GetComponentTime();
 
   int32 InputDim() const;
@@ -38,8 +38,8 @@ class Nnet {
 
   // per-component buffers of the last Propagate / Backpropagate (the reference's public accessors return the legacy,
   // never-filled propagate_buf_; these return the live ones so parity tests can compare layer by layer)
-  const std::vector<CuMatrix>& PropagateBuffer() const { return output_buf_; }
-  const std::vector<CuMatrix>& BackpropagateBuffer() const { return output_diff_buf_; }   // d(loss)/d(output of component c)
+  const std::vector<CuMatrix<BaseFloat>>& PropagateBuffer() const { return output_buf_; }
+  const std::vector<CuMatrix<BaseFloat>>& BackpropagateBuffer() const { return output_diff_buf_; }   // d(loss)/d(output of component c)
 
   int32 NumParams() const;
   void GetParams(Vector<BaseFloat>* wei_copy) const;
@@ -76,7 +76,7 @@ class Nnet {
   std::vector<Component*> components_;
   std::vector<int32> input_, output_;
   std::vector<std::pair<std::string, BaseFloat>> propagate_time_, back_propagate_time_;
-  std::vector<CuMatrix> input_buf_, output_buf_, input_diff_buf_, output_diff_buf_;
+  std::vector<CuMatrix<BaseFloat>> input_buf_, output_buf_, input_diff_buf_, output_diff_buf_;
   NnetTrainOptions opts_;
 };
 

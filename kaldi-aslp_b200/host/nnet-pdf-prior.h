@@ -66,13 +66,13 @@ class PdfPrior {
   }
  private:
   BaseFloat prior_scale_;
-  CuVector log_priors_;
+  CuVector<BaseFloat> log_priors_;
 };
 
 // The tail of the forwarders (aslp-nnet-forward.cc:184-216, -forward-blstm-lc.cc:178-199): log, blank scaling, prior
 // subtraction, the two "doesn't look like probabilities" warnings and the finiteness check, in one device pass.
 inline void FinalizePosteriors(const std::string& utt, bool apply_log, BaseFloat scale_blank, const std::string& class_frame_counts,
-                               const PdfPrior& pdf_prior, CuMatrix* nnet_out) {
+                               const PdfPrior& pdf_prior, CuMatrix<BaseFloat>* nnet_out) {
   static float* stats_dev = nullptr;
   if (stats_dev == nullptr) ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&stats_dev), 8 * sizeof(float)));
   const bool use_prior = class_frame_counts != "";

@@ -50,7 +50,7 @@ class MatrixRandomizer {
  public:
   MatrixRandomizer() : data_begin_(0), data_end_(0) {}
   void Init(const NnetDataRandomizerOptions& conf) { conf_ = conf; }
-  void AddData(const CuMatrixBase& m) {
+  void AddData(const CuMatrixBase<BaseFloat>& m) {
     if (data_.NumCols() == 0) data_.Resize(conf_.randomizer_size, m.NumCols());
     if (data_begin_ > 0) {
       KALDI_ASSERT(data_begin_ <= data_end_);
@@ -61,7 +61,7 @@ class MatrixRandomizer {
       data_.RowRange(leftover, data_.NumRows() - leftover).SetZero();
     }
     if (data_.NumRows() < data_end_ + m.NumRows()) {
-      CuMatrix aux(data_);
+      CuMatrix<BaseFloat> aux(data_);
       data_.Resize(data_end_ + m.NumRows() + 1000, data_.NumCols());
       data_.RowRange(0, aux.NumRows()).CopyFromMat(aux);
     }
@@ -79,14 +79,14 @@ class MatrixRandomizer {
   }
   bool Done() const { return data_end_ - data_begin_ < conf_.minibatch_size; }
   void Next() { data_begin_ += conf_.minibatch_size; }
-  const CuMatrixBase& Value() {
+  const CuMatrixBase<BaseFloat>& Value() {
     KALDI_ASSERT(data_end_ - data_begin_ >= conf_.minibatch_size);
     minibatch_.Resize(conf_.minibatch_size, data_.NumCols(), kUndefined);
     minibatch_.CopyFromMat(data_.RowRange(data_begin_, conf_.minibatch_size));
     return minibatch_;
   }
  private:
-  CuMatrix data_, data_aux_, minibatch_;
+  CuMatrix<BaseFloat> data_, data_aux_, minibatch_;
   CuArrayInt mask_dev_;
   int32 data_begin_, data_end_;
   NnetDataRandomizerOptions conf_;
@@ -157,7 +157,7 @@ class FrameDataReader {
     randomizer_mask_.Init(rand_opts);
   }
   bool Done() { return read_done_ && feature_randomizer_.Done(); }
-  bool ReadData(const CuMatrixBase** feat, const Posterior** targets) {
+  bool ReadData(const CuMatrixBase<BaseFloat>** feat, const Posterior** targets) {
     if (Done()) KALDI_ERR << "Already read done";
     if (feature_randomizer_.Done()) FillRandomizer();
     if (!Done()) {                         // even after a refill there may be less than one minibatch left
@@ -240,7 +240,7 @@ class FrameDataReader {
   bool read_done_;
   RandomizerReplay sim_;                   // the feeder thread's replay of the randomizer's data_begin_ / data_end_
   bool sim_read_done_;
-  CuMatrix block_dev_;
+  CuMatrix<BaseFloat> block_dev_;
   BatchFeeder<Block> feeder_;              // last member: its thread uses everything above
 };
 
@@ -271,7 +271,7 @@ class SequenceDataReader {
   const std::vector<int32>& GetNewUttFlags() const { return new_utt_flags_; }
   // feat is left untouched once every stream is exhausted (the reference's FillBatchBuff skips the copy, data-reader.cc:297-322:
   // the trainer then runs one more minibatch on the previous features with an all-zero mask -- kept)
-  void ReadData(CuMatrix* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
+  void ReadData(CuMatrix<BaseFloat>* feat, Posterior* target, Vector<BaseFloat>* frame_mask) {
     if (Done()) KALDI_ERR << "Already read done!";
     AddNewUtt();
     if (FillBatchBuff(&host_, target, frame_mask)) *feat = host_;

@@ -216,7 +216,7 @@ void AsgdServer::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params
   IServer::InitParam(params);
   if (momentum_ >= 0.0f) {
     diffs_.resize(NumNodes() - 1);
-    for (CuVector& d : diffs_) d.Resize(static_cast<int32>(total_), kSetZero);
+    for (CuVector<BaseFloat>& d : diffs_) d.Resize(static_cast<int32>(total_), kSetZero);
   }
 }
 void AsgdServer::SendModel(int worker_rank) {
@@ -264,7 +264,7 @@ void AsgdServer::Update(int worker_rank, int synchronized_count) {
   ASLP_OK(aslp_comm_recv_f32(comm_, CuStream(), worker_arena_.Data(), total_, worker_rank));
   const int32 ld = static_cast<int32>((total_ + 3) / 4 * 4), n = static_cast<int32>(total_);
   if (momentum_ >= 0.0f) {
-    CuVector& d = diffs_[worker_rank - 1];
+    CuVector<BaseFloat>& d = diffs_[worker_rank - 1];
     ASLP_OK(aslp_axpby(CuStream(), d.Data(), ld, worker_arena_.Data(), ld, 1, n, 1.0f, momentum_));
     ASLP_OK(aslp_axpby(CuStream(), server_arena_.Data(), ld, d.Data(), ld, 1, n, 1.0f, 1.0f));
   } else {

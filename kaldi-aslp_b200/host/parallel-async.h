@@ -52,7 +52,7 @@ class IServer : public NcclNode {             // itf.h:38-43
   aslp_tensor_ref_t* table_dev_;
   int ntensors_;
   size_t total_;
-  CuVector server_arena_, worker_arena_;
+  CuVector<BaseFloat> server_arena_, worker_arena_;
   CtrlServer* ctrl_;
 };
 
@@ -66,7 +66,7 @@ class EasgdWorker : public IWorker {
   void Stop();
  private:
   float alpha_;
-  CuVector server_arena_;
+  CuVector<BaseFloat> server_arena_;
   CtrlClient* ctrl_;
 };
 class EasgdServer : public IServer {
@@ -87,7 +87,7 @@ class AsgdWorker : public IWorker {
   bool IsAsync() const { return true; }
   void Stop();
  private:
-  CuVector w_prev_;
+  CuVector<BaseFloat> w_prev_;
   CtrlClient* ctrl_;
 };
 // ASGD server; momentum >= 0 turns it into the MASGD server (per-worker momentum buffers, no alpha)
@@ -103,7 +103,7 @@ class AsgdServer : public IServer {
   float alpha_;
   int sync_period_;
   float momentum_;
-  std::vector<CuVector> diffs_;       // MASGD: one per worker
+  std::vector<CuVector<BaseFloat>> diffs_;       // MASGD: one per worker
 };
 
 }  // namespace kaldi

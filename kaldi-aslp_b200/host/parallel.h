@@ -43,7 +43,7 @@ class IWorker : public NcclNode {
   aslp_tensor_ref_t* table_dev_;
   int ntensors_;
   size_t total_;            // packed arena length
-  CuVector arena_;          // the all-reduce buffer
+  CuVector<BaseFloat> arena_;          // the all-reduce buffer
 };
 
 class BspWorker : public IWorker {
@@ -60,7 +60,7 @@ class BmufWorker : public IWorker {
   bool Synchronize(int num_worker_samples);
  private:
   float momentum_, learn_rate_;
-  CuVector w_prev_, delta_prev_;
+  CuVector<BaseFloat> w_prev_, delta_prev_;
 };
 
 // Process-launch bootstrap for the worker mains (what mpirun + MPI_Init did in the reference): rank and world size
@@ -98,7 +98,7 @@ class SodWorker : public IWorker {
  private:
   OptimizerOption config_;
   int step_;
-  CuVector w_prev_, s1_, s2_;
+  CuVector<BaseFloat> w_prev_, s1_, s2_;
 };
 
 }  // namespace kaldi
