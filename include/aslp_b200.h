@@ -120,6 +120,10 @@ int aslp_xent_sparse(aslp_stream_t s, float* diff, int ldd, const float* y, int 
 /* dense-target form (Posterior with several pdfs per frame, PosteriorToMatrix) */
 int aslp_xent_dense(aslp_stream_t s, float* diff, int ldd, const float* y, int ldy, const float* tgt, int ldt,
                     int rows, int cols, const float* frame_w, double* stats_dev);
+/* Mse::Eval (src/aslp-nnet/nnet-loss.cc:205-258): diff = w (y - t), stats_dev[0] += 0.5 * sum w * diff^2 (the reference weights the
+ * squared, already weighted difference once more; kept).  stats_dev: one device double, never reset by the call. */
+int aslp_mse(aslp_stream_t s, float* diff, int ldd, const float* y, int ldy, const float* tgt, int ldt, int rows, int cols,
+             const float* frame_w, double* stats_dev);
 /* row arg-max (FindRowMaxId, cu-kernels.cu:2141): first maximal index */
 int aslp_row_argmax(aslp_stream_t s, int* idx, const float* m, int ldm, int rows, int cols);
 
@@ -187,6 +191,35 @@ int aslp_fsmn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* out_dif
                   const float* coef, int ldc, int past, int future);
 int aslp_fsmn_coef_grad(aslp_stream_t s, float* coef_corr, int ldc, const float* in, int ldi,
                         const float* out_diff, int ldo, int T, int D, int past, int future, float clip);
+
+/* ---- the smaller components of the zoo (csrc/zoo.cu) ----
+ * Dropout (src/aslp-nnet/nnet-activation.h:203-273): mask = (u < retention), out = in * mask / retention; the mask is kept (as
+ * 0/1 floats, like the reference's dropout_mask_) for the backward pass.  u comes from Philox-4x32-10 keyed by `seed`, counter =
+ * (element index / 4, call): the mask depends only on (seed, call, rows, cols), not on the launch geometry. */
+int aslp_dropout_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, float* mask, int ldm, int rows, int cols,
+                     float retention, unsigned long long seed, unsigned long long call);
+/* out = a * b * scale (MulElements + Scale: Dropout with a host-drawn mask, Dropout backward) */
+int aslp_mul_elements(aslp_stream_t s, float* out, int ldo, const float* a, int lda, const float* b, int ldb, int rows, int cols, float scale);
+/* BlockSoftmax backward of one block (nnet-activation.h:120-139): dst = src * (1 - sum over the block's columns of src) */
+int aslp_rows_one_minus_sum(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, int rows, int cols);
+/* PnormComponent / MaxoutComponent (nnet-activation.h:305-377; MatrixBase::GroupPnorm, GroupPnormDeriv, GroupMax, GroupMaxDeriv,
+ * MulRowsGroupMat, kaldi-matrix.cc:1071-1138, 2530-2558): in [rows, groups * group_size] -> out [rows, groups] */
+int aslp_group_pnorm_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int groups, int group_size, float p);
+int aslp_group_pnorm_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int ldi, const float* out, int ldo, const float* out_diff, int ldod,
+                         int rows, int groups, int group_size, float p);
+int aslp_group_max_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, int rows, int groups, int group_size);
+int aslp_group_max_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int ldi, const float* out, int ldo, const float* out_diff, int ldod,
+                       int rows, int groups, int group_size);
+/* LengthNormComponent (nnet-various.h:327-365): row_scales[r] = 1 / |x_r|_2, out = x * row_scales; backward = aslp_mul_rows_vec */
+int aslp_length_norm_fwd(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, float* row_scales, int rows, int cols);
+int aslp_mul_rows_vec(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, const float* v, int rows, int cols);
+/* CopyComponent (nnet-various.h:186-316, cu::Copy): out[r][c] = in[r][idx[c]] */
+int aslp_copy_cols(aslp_stream_t s, float* out, int ldo, const float* in, int ldi, const int* idx_dev, int rows, int cols_out);
+/* LstmCifgProjectedStreams (nnet-lstm-couple-if-projected-streams.h): rows [g | f | o] -> [g | -f | f | o] of a parameter matrix
+ * (i = 1 - f = sigmoid(-pre_f), so the four-gate recurrence serves the coupled cell), and the derivative columns
+ * [dg | di | df | do] -> [dg | df - di | do] for the three-gate weight gradients */
+int aslp_cifg_expand(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, int C, int cols);
+int aslp_cifg_compact(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, int rows, int C);
 
 /* ---- LSTM family recurrence: one persistent launch walks all T steps ----
  * Lstm (nnet-recurrent-component.cc:235-480), LstmProjectedStreams (nnet-lstm-projected-streams.h:313-617),

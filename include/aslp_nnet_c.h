@@ -55,6 +55,9 @@ int aslp_nnet_component_out_diff(aslp_nnet_t n, int component, float* host_out, 
 
 /* ---- losses ---- */
 int aslp_xent_create(aslp_xent_t* out);
+/* any frame-level objective behind the same handle: "xent" | "mse" | "multitask,<type>,<dim>,<weight>,..." (LossItf, nnet-loss.h:33-222;
+ * the --objective-function values of the trainer mains) */
+int aslp_loss_create(const char* objective, aslp_xent_t* out);
 int aslp_xent_destroy(aslp_xent_t x);
 int aslp_xent_report(aslp_xent_t x, char* buf, size_t buf_bytes, double stats5[5]);   /* Xent::Report; stats: avg-loss-numerator.. see .cc */
 int aslp_warpctc_create(aslp_warpctc_t* out);

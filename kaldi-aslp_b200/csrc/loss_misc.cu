@@ -287,6 +287,44 @@ __global__ void posterior_stats_decode_kernel(unsigned* stats) {
 
 }  // namespace
 
+
+// Mse::Eval (src/aslp-nnet/nnet-loss.cc:205-258): diff = w (y - t); loss += 0.5 * sum_rows w * diff^2 -- the reference squares the
+// ALREADY weighted difference and weights it again (w^3 (y - t)^2), kept.  One pass, warp per row, float4 when aligned; the loss
+// is accumulated in double on the device (stats_dev[0]), one atomic per block.
+__global__ void __launch_bounds__(256) mse_kernel(float* __restrict__ diff, int ldd, const float* __restrict__ y, int ldy, const float* __restrict__ t,
+                                                  int ldt, int rows, int cols, const float* __restrict__ w, double* stats, int vec4) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double acc = 0.0;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const float fw = w[r];
+    float part = 0.f;
+    if (vec4) {
+      for (int c = lane * 4; c < cols; c += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(y + (size_t)r * ldy + c), b = *reinterpret_cast<const float4*>(t + (size_t)r * ldt + c);
+        const float4 d = make_float4((a.x - b.x) * fw, (a.y - b.y) * fw, (a.z - b.z) * fw, (a.w - b.w) * fw);
+        *reinterpret_cast<float4*>(diff + (size_t)r * ldd + c) = d;
+        part += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) {
+        const float d = (y[(size_t)r * ldy + c] - t[(size_t)r * ldt + c]) * fw;
+        diff[(size_t)r * ldd + c] = d;
+        part += d * d;
+      }
+    }
+    acc += (double)(part * fw);
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double sh[8];
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += sh[i];
+    atomicAdd(stats, 0.5 * tot);
+  }
+}
+
 extern "C" {
 
 int aslp_xent_sparse(aslp_stream_t s, float* diff, int ldd, const float* y, int ldy, int rows, int cols, const int* tgt_idx,
@@ -323,6 +361,17 @@ int aslp_xent_dense(aslp_stream_t s, float* diff, int ldd, const float* y, int l
   int blocks = aslp_div_up(rows, 8);
   if (blocks > aslp_num_sms() * 8) blocks = aslp_num_sms() * 8;
   xent_kernel<true><<<blocks, 256, 0, (cudaStream_t)s>>>(diff, ldd, y, ldy, tgt, ldt, rows, cols, nullptr, nullptr, frame_w, stats_dev);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
+int aslp_mse(aslp_stream_t s, float* diff, int ldd, const float* y, int ldy, const float* tgt, int ldt, int rows, int cols,
+             const float* frame_w, double* stats_dev) {
+  if (rows == 0 || cols == 0) return 0;
+  const int vec4 = (cols % 4 == 0 && rowreg::aligned16(diff, ldd) && rowreg::aligned16(y, ldy) && rowreg::aligned16(tgt, ldt)) ? 1 : 0;
+  int blocks = aslp_div_up(rows, 8);
+  if (blocks > aslp_num_sms() * 8) blocks = aslp_num_sms() * 8;
+  mse_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(diff, ldd, y, ldy, tgt, ldt, rows, cols, frame_w, stats_dev, vec4);
   ASLP_CHECK_LAUNCH();
   return 0;
 }

@@ -116,13 +116,26 @@ static void CopyBuf(const CuMatrix<BaseFloat>& m, float* host_out, int rows, int
 int aslp_nnet_component_output(aslp_nnet_t n, int c, float* host_out, int rows, int cols) { CAPI_BEGIN CopyBuf(N(n)->PropagateBuffer().at(c), host_out, rows, cols); CAPI_END }
 int aslp_nnet_component_out_diff(aslp_nnet_t n, int c, float* host_out, int rows, int cols) { CAPI_BEGIN CopyBuf(N(n)->BackpropagateBuffer().at(c), host_out, rows, cols); CAPI_END }
 
-int aslp_xent_create(aslp_xent_t* out) { CAPI_BEGIN *out = new Xent(); CAPI_END }
-int aslp_xent_destroy(aslp_xent_t x) { CAPI_BEGIN delete static_cast<Xent*>(x); CAPI_END }
+// the frame-level objectives share one handle type: the handle is a LossItf* (Xent | Mse | MultiTaskLoss)
+int aslp_xent_create(aslp_xent_t* out) { CAPI_BEGIN *out = static_cast<LossItf*>(new Xent()); CAPI_END }
+int aslp_loss_create(const char* objective, aslp_xent_t* out) {
+  CAPI_BEGIN
+  const std::string obj(objective);
+  if (obj == "xent") *out = static_cast<LossItf*>(new Xent());
+  else if (obj == "mse") *out = static_cast<LossItf*>(new Mse());
+  else if (obj.compare(0, 9, "multitask") == 0) { MultiTaskLoss* m = new MultiTaskLoss(); m->InitFromString(obj); *out = static_cast<LossItf*>(m); }
+  else KALDI_ERR << "Unknown objective function code : " << obj;
+  CAPI_END
+}
+int aslp_xent_destroy(aslp_xent_t x) { CAPI_BEGIN delete static_cast<LossItf*>(x); CAPI_END }
 int aslp_xent_report(aslp_xent_t x, char* buf, size_t bytes, double stats5[5]) {
   CAPI_BEGIN
-  Xent* xe = static_cast<Xent*>(x);
-  CopyOut(xe->Report(), buf, bytes);
-  if (stats5 != nullptr) { stats5[0] = xe->AvgLoss(); stats5[1] = xe->Frames(); stats5[2] = xe->Correct(); stats5[3] = 0; stats5[4] = 0; }
+  LossItf* l = static_cast<LossItf*>(x);
+  CopyOut(l->Report(), buf, bytes);
+  if (stats5 != nullptr) {
+    Xent* xe = dynamic_cast<Xent*>(l);
+    stats5[0] = l->AvgLoss(); stats5[1] = xe ? xe->Frames() : 0; stats5[2] = xe ? xe->Correct() : 0; stats5[3] = 0; stats5[4] = 0;
+  }
   CAPI_END
 }
 int aslp_warpctc_create(aslp_warpctc_t* out) { CAPI_BEGIN *out = new WarpCtc(); CAPI_END }
@@ -145,7 +158,7 @@ int aslp_train_step_xent(aslp_nnet_t n, aslp_xent_t x, const float* features, in
   Posterior post(rows);
   Vector<BaseFloat> fw(rows);
   for (int r = 0; r < rows; ++r) { post[r].push_back(std::make_pair(targets[r], 1.0f)); fw(r) = frame_mask ? frame_mask[r] : 1.0f; }
-  static_cast<Xent*>(x)->Eval(fw, g_out, post, &g_loss_diff);
+  static_cast<LossItf*>(x)->Eval(fw, g_out, post, &g_loss_diff);
   N(n)->Backpropagate(g_loss_diff, NULL);
   CAPI_END
 }

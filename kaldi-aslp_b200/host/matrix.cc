@@ -108,14 +108,14 @@ template <typename Real> static const char* MatTok() { return sizeof(Real) == 4 
 template <typename Real> static const char* VecTok() { return sizeof(Real) == 4 ? "FV" : "DV"; }
 
 template <typename Real>
-void Vector<Real>::Write(std::ostream& os, bool binary) const {
+void VectorBase<Real>::Write(std::ostream& os, bool binary) const {
   if (binary) {
     WriteToken(os, binary, VecTok<Real>());
     WriteBasicType(os, binary, static_cast<int32>(Dim()));
-    os.write(reinterpret_cast<const char*>(d_.data()), sizeof(Real) * d_.size());
+    os.write(reinterpret_cast<const char*>(data_), sizeof(Real) * dim_);
   } else {
     os << " [ ";
-    for (Real v : d_) os << v << " ";
+    for (int32 i = 0; i < dim_; ++i) os << data_[i] << " ";
     os << "]\n";
   }
   if (!os.good()) KALDI_ERR << "Failed to write vector to stream";
@@ -158,16 +158,17 @@ void Vector<Real>::Read(std::istream& is, bool binary) {
     if (is.peek() == '\r') is.get();
     if (is.peek() == '\n') is.get();
   }
+  Sync();
   if (is.fail()) KALDI_ERR << "Failed to read vector from stream";
 }
 
 template <typename Real>
-void Matrix<Real>::Write(std::ostream& os, bool binary) const {
+void MatrixBase<Real>::Write(std::ostream& os, bool binary) const {
   if (binary) {
     WriteToken(os, binary, MatTok<Real>());
     WriteBasicType(os, binary, r_);
     WriteBasicType(os, binary, c_);
-    os.write(reinterpret_cast<const char*>(d_.data()), sizeof(Real) * d_.size());
+    for (int32 i = 0; i < r_; ++i) os.write(reinterpret_cast<const char*>(RowData(i)), sizeof(Real) * c_);
   } else if (c_ == 0) {
     os << " [ ]\n";
   } else {
@@ -237,6 +238,10 @@ void Matrix<Real>::Read(std::istream& is, bool binary) {
   if (is.fail()) KALDI_ERR << "Failed to read matrix from stream";
 }
 
+template class VectorBase<float>;
+template class VectorBase<double>;
+template class MatrixBase<float>;
+template class MatrixBase<double>;
 template class Vector<float>;
 template class Vector<double>;
 template class Matrix<float>;
@@ -355,7 +360,7 @@ template <typename Real> void CuVector<Real>::CopyToVec(Vector<Real>* dst) const
   if (dim_ > 0) ASLP_OK(aslp_memcpy_d2h(CuStream(), dst->Data(), data_, sizeof(Real) * dim_));
   CuSync();
 }
-template <typename Real> void CuVector<Real>::CopyFromVec(const Vector<Real>& src) {
+template <typename Real> void CuVector<Real>::CopyFromVec(const VectorBase<Real>& src) {
   KALDI_ASSERT(src.Dim() == dim_);
   if (dim_ > 0) ASLP_OK(aslp_memcpy_h2d(CuStream(), data_, src.Data(), sizeof(Real) * dim_));
   CuSync();
@@ -366,7 +371,7 @@ template <typename Real> CuVector<Real>& CuVector<Real>::operator=(const CuVecto
   if (dim_ > 0) ASLP_OK(aslp_memcpy_d2d(CuStream(), data_, o.data_, sizeof(Real) * dim_));
   return *this;
 }
-template <typename Real> CuVector<Real>& CuVector<Real>::operator=(const Vector<Real>& o) {
+template <typename Real> CuVector<Real>& CuVector<Real>::operator=(const VectorBase<Real>& o) {
   Resize(o.Dim(), kUndefined);
   CopyFromVec(o);
   return *this;

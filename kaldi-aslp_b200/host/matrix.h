@@ -39,46 +39,118 @@ class CuStreamScope {
   aslp_stream_t saved_;
 };
 
+// Host containers with the reference's class split (src/matrix/kaldi-vector.h, kaldi-matrix.h): VectorBase / SubVector /
+// Vector and MatrixBase / SubMatrix / Matrix, so that trainer code written against them (Matrix::Row(i).CopyFromVec(...),
+// Vector<BaseFloat> v(n, kSetZero), const VectorBase<BaseFloat>& arguments) compiles unchanged.  Dense rows (stride == cols).
 template <typename Real>
-class Vector {
+class VectorBase {
+ public:
+  int32 Dim() const { return dim_; }
+  Real* Data() { return data_; }
+  const Real* Data() const { return data_; }
+  Real& operator()(int32 i) { return data_[i]; }
+  Real operator()(int32 i) const { return data_[i]; }
+  Real Sum() const { double s = 0; for (int32 i = 0; i < dim_; ++i) s += data_[i]; return static_cast<Real>(s); }
+  void Set(Real v) { for (int32 i = 0; i < dim_; ++i) data_[i] = v; }
+  void SetZero() { Set(Real(0)); }
+  void Scale(Real a) { for (int32 i = 0; i < dim_; ++i) data_[i] *= a; }
+  void Add(Real a) { for (int32 i = 0; i < dim_; ++i) data_[i] += a; }
+  Real Max() const { Real m = dim_ ? data_[0] : Real(0); for (int32 i = 1; i < dim_; ++i) if (data_[i] > m) m = data_[i]; return m; }
+  Real Min() const { Real m = dim_ ? data_[0] : Real(0); for (int32 i = 1; i < dim_; ++i) if (data_[i] < m) m = data_[i]; return m; }
+  template <typename Other>
+  void CopyFromVec(const VectorBase<Other>& v) {
+    KALDI_ASSERT(v.Dim() == dim_);
+    for (int32 i = 0; i < dim_; ++i) data_[i] = static_cast<Real>(v(i));
+  }
+  void AddVec(Real alpha, const VectorBase<Real>& v) { KALDI_ASSERT(v.Dim() == dim_); for (int32 i = 0; i < dim_; ++i) data_[i] += alpha * v(i); }
+  void Write(std::ostream& os, bool binary) const;
+ protected:
+  VectorBase() : data_(nullptr), dim_(0) {}
+  VectorBase(Real* d, int32 n) : data_(d), dim_(n) {}
+  Real* data_;
+  int32 dim_;
+};
+
+template <typename Real>
+class SubVector : public VectorBase<Real> {
+ public:
+  SubVector(Real* d, int32 n) : VectorBase<Real>(d, n) {}
+  SubVector(const VectorBase<Real>& v, int32 origin, int32 n) : VectorBase<Real>(const_cast<Real*>(v.Data()) + origin, n) { KALDI_ASSERT(origin + n <= v.Dim()); }
+  SubVector(const SubVector& o) : VectorBase<Real>(o.data_, o.dim_) {}
+};
+
+template <typename Real>
+class Vector : public VectorBase<Real> {
  public:
   Vector() {}
-  explicit Vector(int32 dim) : d_(dim, Real(0)) {}
-  void Resize(int32 dim, MatrixResizeType t = kSetZero) { if (t == kSetZero) d_.assign(dim, Real(0)); else d_.resize(dim); }
-  int32 Dim() const { return static_cast<int32>(d_.size()); }
-  Real* Data() { return d_.data(); }
-  const Real* Data() const { return d_.data(); }
-  Real& operator()(int32 i) { return d_[i]; }
-  Real operator()(int32 i) const { return d_[i]; }
-  Real Sum() const { double s = 0; for (Real v : d_) s += v; return static_cast<Real>(s); }
+  explicit Vector(int32 dim, MatrixResizeType t = kSetZero) { Resize(dim, t); }
+  Vector(const Vector& o) : VectorBase<Real>(), d_(o.d_) { Sync(); }
+  explicit Vector(const VectorBase<Real>& o) : d_(o.Data(), o.Data() + o.Dim()) { Sync(); }
+  Vector& operator=(const Vector& o) { if (this != &o) { d_ = o.d_; Sync(); } return *this; }
+  Vector& operator=(const VectorBase<Real>& o) { if (this != &o) { d_.assign(o.Data(), o.Data() + o.Dim()); Sync(); } return *this; }
+  void Resize(int32 dim, MatrixResizeType t = kSetZero) { if (t == kSetZero) d_.assign(dim, Real(0)); else d_.resize(dim); Sync(); }
+  void Swap(Vector* o) { d_.swap(o->d_); Sync(); o->Sync(); }
   void Read(std::istream& is, bool binary);
-  void Write(std::ostream& os, bool binary) const;
  private:
+  void Sync() { this->data_ = d_.data(); this->dim_ = static_cast<int32>(d_.size()); }
   std::vector<Real> d_;
 };
 
 template <typename Real>
-class Matrix {
+class MatrixBase {
  public:
-  Matrix() : r_(0), c_(0) {}
-  Matrix(int32 rows, int32 cols) : r_(rows), c_(cols), d_(static_cast<size_t>(rows) * cols, Real(0)) {}
-  void Resize(int32 rows, int32 cols, MatrixResizeType t = kSetZero) {
-    r_ = rows; c_ = cols;
-    if (t == kSetZero) d_.assign(static_cast<size_t>(rows) * cols, Real(0)); else d_.resize(static_cast<size_t>(rows) * cols);
-  }
   int32 NumRows() const { return r_; }
   int32 NumCols() const { return c_; }
-  int32 Stride() const { return c_; }
-  Real* Data() { return d_.data(); }
-  const Real* Data() const { return d_.data(); }
-  Real* RowData(int32 r) { return d_.data() + static_cast<size_t>(r) * c_; }
-  const Real* RowData(int32 r) const { return d_.data() + static_cast<size_t>(r) * c_; }
-  Real& operator()(int32 r, int32 c) { return d_[static_cast<size_t>(r) * c_ + c]; }
-  Real operator()(int32 r, int32 c) const { return d_[static_cast<size_t>(r) * c_ + c]; }
-  void Read(std::istream& is, bool binary);
+  int32 Stride() const { return stride_; }
+  Real* Data() { return data_; }
+  const Real* Data() const { return data_; }
+  Real* RowData(int32 r) { return data_ + static_cast<size_t>(r) * stride_; }
+  const Real* RowData(int32 r) const { return data_ + static_cast<size_t>(r) * stride_; }
+  Real& operator()(int32 r, int32 c) { return data_[static_cast<size_t>(r) * stride_ + c]; }
+  Real operator()(int32 r, int32 c) const { return data_[static_cast<size_t>(r) * stride_ + c]; }
+  SubVector<Real> Row(int32 r) { KALDI_ASSERT(r >= 0 && r < r_); return SubVector<Real>(RowData(r), c_); }
+  const SubVector<Real> Row(int32 r) const { KALDI_ASSERT(r >= 0 && r < r_); return SubVector<Real>(const_cast<Real*>(RowData(r)), c_); }
+  void SetZero() { for (int32 r = 0; r < r_; ++r) for (int32 c = 0; c < c_; ++c) (*this)(r, c) = Real(0); }
+  void Set(Real v) { for (int32 r = 0; r < r_; ++r) for (int32 c = 0; c < c_; ++c) (*this)(r, c) = v; }
+  void Scale(Real a) { for (int32 r = 0; r < r_; ++r) for (int32 c = 0; c < c_; ++c) (*this)(r, c) *= a; }
+  Real Sum() const { double s = 0; for (int32 r = 0; r < r_; ++r) for (int32 c = 0; c < c_; ++c) s += (*this)(r, c); return static_cast<Real>(s); }
+  void CopyFromMat(const MatrixBase<Real>& m) {
+    KALDI_ASSERT(m.NumRows() == r_ && m.NumCols() == c_);
+    for (int32 r = 0; r < r_; ++r) for (int32 c = 0; c < c_; ++c) (*this)(r, c) = m(r, c);
+  }
+  void CopyRowFromVec(const VectorBase<Real>& v, int32 row) { Row(row).CopyFromVec(v); }
   void Write(std::ostream& os, bool binary) const;
+ protected:
+  MatrixBase() : data_(nullptr), r_(0), c_(0), stride_(0) {}
+  MatrixBase(Real* d, int32 r, int32 c, int32 s) : data_(d), r_(r), c_(c), stride_(s) {}
+  Real* data_;
+  int32 r_, c_, stride_;
+};
+
+template <typename Real>
+class SubMatrix : public MatrixBase<Real> {
+ public:
+  SubMatrix(const MatrixBase<Real>& m, int32 r0, int32 nr, int32 c0, int32 nc)
+      : MatrixBase<Real>(const_cast<Real*>(m.RowData(r0)) + c0, nr, nc, m.Stride()) { KALDI_ASSERT(r0 + nr <= m.NumRows() && c0 + nc <= m.NumCols()); }
+};
+
+template <typename Real>
+class Matrix : public MatrixBase<Real> {
+ public:
+  Matrix() {}
+  Matrix(int32 rows, int32 cols, MatrixResizeType t = kSetZero) { Resize(rows, cols, t); }
+  Matrix(const Matrix& o) : MatrixBase<Real>(), d_(o.d_) { Sync(o.r_, o.c_); }
+  explicit Matrix(const MatrixBase<Real>& o) { Resize(o.NumRows(), o.NumCols(), kUndefined); this->CopyFromMat(o); }
+  Matrix& operator=(const Matrix& o) { if (this != &o) { d_ = o.d_; Sync(o.r_, o.c_); } return *this; }
+  Matrix& operator=(const MatrixBase<Real>& o) { if (this != &o) { Resize(o.NumRows(), o.NumCols(), kUndefined); this->CopyFromMat(o); } return *this; }
+  void Resize(int32 rows, int32 cols, MatrixResizeType t = kSetZero) {
+    if (t == kSetZero) d_.assign(static_cast<size_t>(rows) * cols, Real(0)); else d_.resize(static_cast<size_t>(rows) * cols);
+    Sync(rows, cols);
+  }
+  void Swap(Matrix* o) { d_.swap(o->d_); const int32 r = this->r_, c = this->c_; Sync(o->r_, o->c_); o->Sync(r, c); }
+  void Read(std::istream& is, bool binary);
  private:
-  int32 r_, c_;
+  void Sync(int32 r, int32 c) { this->data_ = d_.data(); this->r_ = r; this->c_ = c; this->stride_ = c; }
   std::vector<Real> d_;
 };
 
@@ -174,7 +246,7 @@ class CuVector {
   explicit CuVector(int32 dim, MatrixResizeType t = kSetZero) : data_(nullptr), dim_(0), cap_(0) { Resize(dim, t); }
   CuVector(const CuVector& o) : data_(nullptr), dim_(0), cap_(0) { *this = o; }
   CuVector& operator=(const CuVector& o);
-  CuVector& operator=(const Vector<Real>& o);
+  CuVector& operator=(const VectorBase<Real>& o);
   ~CuVector();
   void Resize(int32 dim, MatrixResizeType t = kSetZero);
   int32 Dim() const { return dim_; }
@@ -183,7 +255,7 @@ class CuVector {
   void SetZero();
   void Set(Real v);
   void CopyToVec(Vector<Real>* dst) const;     // synchronises
-  void CopyFromVec(const Vector<Real>& src);
+  void CopyFromVec(const VectorBase<Real>& src);
   void Read(std::istream& is, bool binary);
   void Write(std::ostream& os, bool binary) const;
  private:

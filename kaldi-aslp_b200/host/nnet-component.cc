@@ -6,6 +6,7 @@
 #include "nnet-gru-streams.h"
 #include "nnet-lstm-family.h"
 #include "nnet-misc-components.h"
+#include "nnet-zoo-components.h"
 
 namespace kaldi {
 namespace aslp_nnet {
@@ -35,6 +36,13 @@ const struct Component::key_value Component::kMarkerMap[] = {
     {Component::kCompactFsmn, "<CompactFsmn>"},
     {Component::kConvolutionalComponent, "<ConvolutionalComponent>"},
     {Component::kMaxPoolingComponent, "<MaxPoolingComponent>"},
+    {Component::kBlockSoftmax, "<BlockSoftmax>"},
+    {Component::kDropout, "<Dropout>"},
+    {Component::kLengthNormComponent, "<LengthNormComponent>"},
+    {Component::kCopy, "<Copy>"},
+    {Component::kLstmCifgProjectedStreams, "<LstmCifgProjectedStreams>"},
+    {Component::kPnormComponent, "<Pnorm>"},
+    {Component::kPnormComponent, "<Maxout>"},      // the reference's table maps BOTH markers to the p-norm type (nnet-component.cc:79-80); kept
 };
 static const int kNumMarkers = sizeof(Component::kMarkerMap) / sizeof(Component::kMarkerMap[0]);
 
@@ -79,6 +87,13 @@ Component* Component::NewComponentOfType(ComponentType t, int32 in, int32 out) {
     case kCompactFsmn: return new CompactFsmn(in, out);
     case kConvolutionalComponent: return new ConvolutionalComponent(in, out);
     case kMaxPoolingComponent: return new MaxPoolingComponent(in, out);
+    case kBlockSoftmax: return new BlockSoftmax(in, out);
+    case kDropout: return new Dropout(in, out);
+    case kLengthNormComponent: return new LengthNormComponent(in, out);
+    case kCopy: return new CopyComponent(in, out);
+    case kLstmCifgProjectedStreams: return new LstmCifgProjectedStreams(in, out);
+    case kPnormComponent: return new PnormComponent(in, out);
+    case kMaxoutComponent: return new MaxoutComponent(in, out);
     default: KALDI_ERR << "Missing type: " << static_cast<int>(t);
   }
   return NULL;

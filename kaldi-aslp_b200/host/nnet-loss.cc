@@ -40,7 +40,7 @@ void Xent::Progress(double num_frames) {
   }
 }
 
-void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& targets, CuMatrix<BaseFloat>* diff) {
+void Xent::Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& targets, CuMatrix<BaseFloat>* diff) {
   KALDI_ASSERT(net_out.NumCols() == targets.NumCols() && net_out.NumRows() == targets.NumRows());
   KALDI_ASSERT(net_out.NumRows() == frame_weights.Dim());
   KALDI_ASSERT(KALDI_ISFINITE(frame_weights.Sum()));
@@ -52,20 +52,14 @@ void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseF
   Progress(frame_weights.Sum());
 }
 
-void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
+void Xent::Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
   const int32 num_frames = net_out.NumRows(), num_pdf = net_out.NumCols();
   KALDI_ASSERT(num_frames == static_cast<int32>(post.size()));
   KALDI_ASSERT(num_frames == frame_weights.Dim());
   bool sparse = true;
   for (const auto& f : post) if (f.size() > 1) { sparse = false; break; }
   if (!sparse) {                                   // PosteriorToMatrix (nnet-utils.h) then the dense path
-    Matrix<BaseFloat> m(num_frames, num_pdf);
-    for (int32 t = 0; t < num_frames; ++t)
-      for (const auto& pr : post[t]) {
-        if (pr.first >= num_pdf) KALDI_ERR << "Posterior has pdf-id " << pr.first << " but the net has " << num_pdf << " outputs";
-        m(t, pr.first) += pr.second;
-      }
-    tgt_mat_ = m;
+    PosteriorToMatrix(post, num_pdf, &tgt_mat_);
     Eval(frame_weights, net_out, tgt_mat_, diff);
     return;
   }
@@ -91,12 +85,6 @@ void Xent::Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseF
   Progress(nf);
 }
 
-void Xent::Eval(const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
-  Vector<BaseFloat> ones(static_cast<int32>(post.size()));
-  for (int32 i = 0; i < ones.Dim(); ++i) ones(i) = 1.0f;
-  Eval(ones, net_out, post, diff);
-}
-
 BaseFloat Xent::AvgLoss() { Fetch(); return (loss_ - entropy_) / frames_; }
 
 std::string Xent::Report() {         // line formats the schedulers grep (nnet-loss.cc:175-200)
@@ -110,6 +98,141 @@ std::string Xent::Report() {         // line formats the schedulers grep (nnet-l
     if (correct_ >= 0.0) oss << "FRAME_ACCURACY >> " << 100.0 * correct_ / frames_ << "% <<" << std::endl;
   }
   return oss.str();
+}
+
+void PosteriorToMatrix(const Posterior& post, int32 num_cols, CuMatrix<BaseFloat>* mat) {
+  const int32 num_rows = static_cast<int32>(post.size());
+  Matrix<BaseFloat> m(num_rows, num_cols);
+  for (int32 t = 0; t < num_rows; ++t)
+    for (const auto& pr : post[t]) {
+      if (pr.first >= num_cols) KALDI_ERR << "Out-of-bound Posterior element with index " << pr.first << ", higher than number of columns " << num_cols;
+      m(t, pr.first) += pr.second;
+    }
+  *mat = m;
+}
+
+// ------------------------------------------------------------------ Mse
+Mse::Mse() : loss_dev_(nullptr), frames_(0), frames_progress_(0), loss_base_(0), num_tgt_(0) {}
+Mse::~Mse() { if (loss_dev_ != nullptr) aslp_free(loss_dev_); }
+
+double Mse::Loss() {
+  if (loss_dev_ == nullptr) return 0.0;
+  double h = 0;
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), &h, loss_dev_, sizeof(h)));
+  CuSync();
+  return h;
+}
+
+void Mse::Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& target, CuMatrix<BaseFloat>* diff) {
+  KALDI_ASSERT(net_out.NumCols() == target.NumCols());
+  KALDI_ASSERT(net_out.NumRows() == target.NumRows());
+  KALDI_ASSERT(net_out.NumRows() == frame_weights.Dim());
+  KALDI_ASSERT(KALDI_ISFINITE(frame_weights.Sum()));
+  const int32 num_frames = frame_weights.Sum();           // truncated to an integer, as in the reference (nnet-loss.cc:219)
+  KALDI_ASSERT(num_frames >= 0.0);
+  if (loss_dev_ == nullptr) {
+    ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&loss_dev_), sizeof(double)));
+    ASLP_OK(aslp_memset(CuStream(), loss_dev_, 0, sizeof(double)));
+  }
+  frame_weights_ = frame_weights;
+  num_tgt_ = net_out.NumCols();
+  diff->Resize(net_out.NumRows(), net_out.NumCols(), kUndefined);
+  ASLP_OK(aslp_mse(CuStream(), diff->Data(), diff->Stride(), net_out.Data(), net_out.Stride(), target.Data(), target.Stride(), net_out.NumRows(),
+                   net_out.NumCols(), frame_weights_.Data(), loss_dev_));
+  frames_ += num_frames;
+  static const int32 progress_step = 3600 * 100;          // 1h
+  frames_progress_ += num_frames;
+  if (frames_progress_ > progress_step) {
+    const double loss = Loss();
+    KALDI_LOG << "ProgressLoss[last " << static_cast<int>(frames_progress_ / 100 / 3600) << "h of " << static_cast<int>(frames_ / 100 / 3600) << "h]: "
+              << (loss - loss_base_) / frames_progress_ << " (Mse)";
+    loss_base_ = loss;
+    frames_progress_ = 0;
+  }
+}
+
+void Mse::Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
+  KALDI_ASSERT(net_out.NumRows() == static_cast<int32>(post.size()));
+  PosteriorToMatrix(post, net_out.NumCols(), &tgt_mat_);
+  Eval(frame_weights, net_out, tgt_mat_, diff);
+}
+
+BaseFloat Mse::AvgLoss() { return Loss() / frames_; }
+
+std::string Mse::Report() {
+  const double loss = Loss();
+  const BaseFloat root_mean_square = sqrt(loss / frames_ / num_tgt_);
+  std::ostringstream oss;
+  oss << "AvgLoss: " << loss / frames_ << " (Mse), " << "[RMS " << root_mean_square << ", frames " << frames_ << "]" << std::endl;
+  return oss.str();
+}
+
+// ------------------------------------------------------------------ MultiTaskLoss
+MultiTaskLoss::~MultiTaskLoss() { for (LossItf* l : loss_vec_) delete l; }
+
+void MultiTaskLoss::InitFromString(const std::string& s) {
+  std::vector<std::string> v;
+  std::string cur;
+  for (char ch : s) { if (ch == ',' || ch == ':') { v.push_back(cur); cur.clear(); } else cur.push_back(ch); }
+  v.push_back(cur);
+  KALDI_ASSERT((v.size() - 1) % 3 == 0);     // triplets
+  KALDI_ASSERT(v[0] == "multitask");
+  for (size_t i = 1; i + 2 < v.size(); i += 3) {
+    if (v[i] == "xent") loss_vec_.push_back(new Xent());
+    else if (v[i] == "mse") loss_vec_.push_back(new Mse());
+    else KALDI_ERR << "Unknown objective function code : " << v[i];
+    char* end = nullptr;
+    const long dim = strtol(v[i + 1].c_str(), &end, 10);
+    if (end == v[i + 1].c_str() || *end != '\0') KALDI_ERR << "Cannot convert 'dim' " << v[i + 1] << " to integer!";
+    loss_dim_.push_back(static_cast<int32>(dim));
+    const double w = strtod(v[i + 2].c_str(), &end);
+    if (end == v[i + 2].c_str() || *end != '\0') KALDI_ERR << "Cannot convert 'weight' " << v[i + 2] << " to integer!";
+    KALDI_ASSERT(w >= 0.0);
+    loss_weights_.push_back(static_cast<BaseFloat>(w));
+  }
+  loss_dim_offset_.assign(loss_dim_.size() + 1, 0);
+  for (size_t i = 1; i <= loss_dim_.size(); i++) loss_dim_offset_[i] = loss_dim_offset_[i - 1] + loss_dim_[i - 1];
+  KALDI_ASSERT(loss_vec_.size() > 0);
+}
+
+void MultiTaskLoss::Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff) {
+  const int32 num_frames = net_out.NumRows(), num_output = net_out.NumCols();
+  KALDI_ASSERT(num_frames == static_cast<int32>(post.size()));
+  KALDI_ASSERT(num_output == loss_dim_offset_.back());
+  PosteriorToMatrix(post, num_output, &tgt_mat_);
+  diff->Resize(num_frames, num_output);
+  CuMatrix<BaseFloat> diff_aux;
+  for (size_t i = 0; i < loss_vec_.size(); i++) {
+    loss_vec_[i]->Eval(frame_weights, net_out.ColRange(loss_dim_offset_[i], loss_dim_[i]), tgt_mat_.ColRange(loss_dim_offset_[i], loss_dim_[i]), &diff_aux);
+    diff_aux.Scale(loss_weights_[i]);
+    diff->ColRange(loss_dim_offset_[i], loss_dim_[i]).CopyFromMat(diff_aux);
+  }
+}
+
+std::string MultiTaskLoss::Report() {
+  const BaseFloat overall_loss = AvgLoss();
+  std::ostringstream oss;
+  oss << "MultiTaskLoss, with " << loss_vec_.size() << " parallel loss functions." << std::endl;
+  for (size_t i = 0; i < loss_vec_.size(); i++) oss << "Loss " << i + 1 << ", " << loss_vec_[i]->Report() << std::endl;
+  oss << "Loss (OVERALL), " << "AvgLoss: " << overall_loss << " (MultiTaskLoss), " << "weights [ ";
+  for (BaseFloat w : loss_weights_) oss << w << " ";
+  oss << "], values [ ";
+  for (LossItf* l : loss_vec_) oss << l->AvgLoss() << " ";
+  oss << "]" << std::endl;
+  return oss.str();
+}
+
+BaseFloat MultiTaskLoss::AvgLoss() {
+  BaseFloat ans(0.0);
+  for (size_t i = 0; i < loss_vec_.size(); i++) {
+    BaseFloat val = loss_weights_[i] * loss_vec_[i]->AvgLoss();
+    if (!KALDI_ISFINITE(val)) {
+      KALDI_WARN << "Loss " << i + 1 << ", has bad objective function value '" << val << "', using 0.0 instead.";
+      val = 0.0;
+    }
+    ans += val;
+  }
+  return ans;
 }
 
 // ------------------------------------------------------------------ WarpCtc

@@ -12,15 +12,38 @@ typedef std::vector<std::vector<std::pair<int32, BaseFloat>>> Posterior;
 
 namespace aslp_nnet {
 
-class Xent {
+// common interface of the frame-level objectives (nnet-loss.h:33-71); the trainer mains hold a LossItf*
+class LossItf {
+ public:
+  LossItf() {}
+  virtual ~LossItf() {}
+  virtual void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& target,
+                    CuMatrix<BaseFloat>* diff) = 0;
+  virtual void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& target,
+                    CuMatrix<BaseFloat>* diff) = 0;
+  // without frame weights (all ones)
+  virtual void Eval(const CuMatrixBase<BaseFloat>& net_out, const Posterior& target, CuMatrix<BaseFloat>* diff) {
+    tmp_frame_weights_.Resize(static_cast<int32>(target.size()), kUndefined);
+    tmp_frame_weights_.Set(1.0f);
+    Eval(tmp_frame_weights_, net_out, target, diff);
+  }
+  virtual std::string Report() = 0;
+  virtual BaseFloat AvgLoss() = 0;
+ protected:
+  Vector<BaseFloat> tmp_frame_weights_;
+};
+
+void PosteriorToMatrix(const Posterior& post, int32 num_cols, CuMatrix<BaseFloat>* mat);      // nnet-utils.h:318-338
+
+class Xent : public LossItf {
  public:
   Xent();
   ~Xent();
+  using LossItf::Eval;
   // dense targets (soft labels)
-  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& targets, CuMatrix<BaseFloat>* diff);
+  void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& targets, CuMatrix<BaseFloat>* diff);
   // posterior targets: one fused sparse pass when every frame has at most one pdf, dense otherwise
-  void Eval(const Vector<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff);
-  void Eval(const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff);
+  void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& post, CuMatrix<BaseFloat>* diff);
   std::string Report();
   BaseFloat AvgLoss();
   double Frames() { Fetch(); return frames_; }
@@ -34,6 +57,46 @@ class Xent {
   CuMatrix<BaseFloat> tgt_mat_;
   CuVector<BaseFloat> frame_w_dev_, tgt_w_dev_;
   CuArrayInt tgt_idx_dev_;
+};
+
+// mean square error (nnet-loss.h:133-171, nnet-loss.cc:205-290): diff = w (y - t); one fused pass, the loss stays on the device
+// until a report asks for it
+class Mse : public LossItf {
+ public:
+  Mse();
+  ~Mse();
+  using LossItf::Eval;
+  void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& target, CuMatrix<BaseFloat>* diff);
+  void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& target, CuMatrix<BaseFloat>* diff);
+  std::string Report();
+  BaseFloat AvgLoss();
+ private:
+  double Loss();                // device accumulator -> host (synchronises)
+  double* loss_dev_;
+  double frames_, frames_progress_, loss_base_;
+  int32 num_tgt_;
+  CuVector<BaseFloat> frame_weights_;
+  CuMatrix<BaseFloat> tgt_mat_;
+};
+
+// 'multitask,<type1>,<dim1>,<weight1>,...,<typeN>,<dimN>,<weightN>' over column ranges of the output (nnet-loss.h:173-222)
+class MultiTaskLoss : public LossItf {
+ public:
+  MultiTaskLoss() {}
+  ~MultiTaskLoss();
+  using LossItf::Eval;
+  void InitFromString(const std::string& s);
+  void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const CuMatrixBase<BaseFloat>& target, CuMatrix<BaseFloat>* diff) {
+    KALDI_ERR << "This is not supposed to be called!";
+  }
+  void Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<BaseFloat>& net_out, const Posterior& target, CuMatrix<BaseFloat>* diff);
+  std::string Report();
+  BaseFloat AvgLoss();
+ private:
+  std::vector<LossItf*> loss_vec_;
+  std::vector<int32> loss_dim_, loss_dim_offset_;
+  std::vector<BaseFloat> loss_weights_;
+  CuMatrix<BaseFloat> tgt_mat_;
 };
 
 class WarpCtc {

@@ -304,6 +304,7 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMat
     ASLP_OK(aslp_gemm(st, 0, 0, T * S, input_dim_, 4 * C, 1.0f, dgifo.Data(), dgifo.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(),
                       i == 0 ? 0.0f : 1.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, prec, nullptr, 0));
   }
+  if (skip_wgrad_) { async_tail_ = false; return; }
   // Everything below (weight gradients, then Update) is off the critical path of the backward pass: nothing downstream reads
   // these weights or corr buffers before the next Propagate.  It goes to the side stream so that it overlaps the backward
   // recurrence of the layer below, which is latency-bound and leaves most SMs idle (Nnet::Backpropagate joins at its end).
@@ -352,6 +353,176 @@ void LstmFamily::Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase
     vec(d.peep_i, d.peep_i_corr); vec(d.peep_f, d.peep_f_corr); vec(d.peep_o, d.peep_o_corr);
     if (tr_.projected) mat(d.w_r_m, d.w_r_m_corr);
   }
+}
+
+
+// ------------------------------------------------------------------ LstmCifgProjectedStreams
+LstmCifgProjectedStreams::LstmCifgProjectedStreams(int32 input_dim, int32 output_dim)
+    : UpdatableComponent(input_dim, output_dim), ncell_(0), nrecur_(output_dim), clip_gradient_(0.0f),
+      engine_(input_dim, output_dim, LstmFamily::Traits{kLstmProjectedStreams, 1, true, true, true, false, false}) {
+  engine_.SetSkipWeightGradients(true);
+}
+
+void LstmCifgProjectedStreams::AllocCorr() {
+  w_gfo_x_corr_.Resize(3 * ncell_, input_dim_, kSetZero);
+  w_gfo_r_corr_.Resize(3 * ncell_, nrecur_, kSetZero);
+  bias_corr_.Resize(3 * ncell_, kSetZero);
+  peephole_f_c_corr_.Resize(ncell_, kSetZero);
+  peephole_o_c_corr_.Resize(ncell_, kSetZero);
+  w_r_m_corr_.Resize(nrecur_, ncell_, kSetZero);
+}
+
+void LstmCifgProjectedStreams::SizeEngine() {
+  engine_.ncell_ = ncell_;
+  engine_.clip_gradient_ = clip_gradient_;
+  LstmFamily::Dir& d = engine_.d_[0];
+  d.w_gifo_x.Resize(4 * ncell_, input_dim_, kUndefined);
+  d.w_gifo_r.Resize(4 * ncell_, nrecur_, kUndefined);
+  d.w_r_m.Resize(nrecur_, ncell_, kUndefined);
+  d.bias.Resize(4 * ncell_, kUndefined);
+  d.peep_i.Resize(ncell_, kUndefined); d.peep_f.Resize(ncell_, kUndefined); d.peep_o.Resize(ncell_, kUndefined);
+}
+
+void LstmCifgProjectedStreams::InitData(std::istream& is) {
+  float param_scale = 0.02f;
+  ProtoOptions po("(CellDim|ClipGradient|ParamScale)");
+  po.Int("<CellDim>", &ncell_);
+  po.Float("<ClipGradient>", &clip_gradient_);
+  po.Float("<ParamScale>", &param_scale);
+  po.Parse(is);
+  KALDI_ASSERT(ncell_ > 0);
+  w_gfo_x_.Resize(3 * ncell_, input_dim_, kUndefined);
+  w_gfo_r_.Resize(3 * ncell_, nrecur_, kUndefined);
+  w_r_m_.Resize(nrecur_, ncell_, kUndefined);
+  InitMatParam(&w_gfo_x_, param_scale);
+  InitMatParam(&w_gfo_r_, param_scale);
+  InitMatParam(&w_r_m_, param_scale);
+  bias_.Resize(3 * ncell_, kUndefined);
+  peephole_f_c_.Resize(ncell_, kUndefined);
+  peephole_o_c_.Resize(ncell_, kUndefined);
+  InitVecParam(&bias_, param_scale);
+  InitVecParam(&peephole_f_c_, param_scale);
+  InitVecParam(&peephole_o_c_, param_scale);
+  AllocCorr();
+  SizeEngine();
+  KALDI_ASSERT(clip_gradient_ >= 0.0);
+}
+
+void LstmCifgProjectedStreams::ReadData(std::istream& is, bool binary) {
+  ExpectToken(is, binary, "<CellDim>");
+  ReadBasicType(is, binary, &ncell_);
+  ExpectToken(is, binary, "<ClipGradient>");
+  ReadBasicType(is, binary, &clip_gradient_);
+  w_gfo_x_.Read(is, binary);
+  w_gfo_r_.Read(is, binary);
+  bias_.Read(is, binary);
+  peephole_f_c_.Read(is, binary);
+  peephole_o_c_.Read(is, binary);
+  w_r_m_.Read(is, binary);
+  KALDI_ASSERT(w_gfo_x_.NumRows() == 3 * ncell_ && w_gfo_x_.NumCols() == input_dim_);
+  KALDI_ASSERT(w_gfo_r_.NumRows() == 3 * ncell_ && w_gfo_r_.NumCols() == nrecur_);
+  AllocCorr();
+  SizeEngine();
+}
+
+void LstmCifgProjectedStreams::WriteData(std::ostream& os, bool binary) const {
+  WriteToken(os, binary, "<CellDim>");
+  WriteBasicType(os, binary, ncell_);
+  WriteToken(os, binary, "<ClipGradient>");
+  WriteBasicType(os, binary, clip_gradient_);
+  w_gfo_x_.Write(os, binary);
+  w_gfo_r_.Write(os, binary);
+  bias_.Write(os, binary);
+  peephole_f_c_.Write(os, binary);
+  peephole_o_c_.Write(os, binary);
+  w_r_m_.Write(os, binary);
+}
+
+int32 LstmCifgProjectedStreams::NumParams() const {
+  return w_gfo_x_.NumRows() * w_gfo_x_.NumCols() + w_gfo_r_.NumRows() * w_gfo_r_.NumCols() + bias_.Dim() + peephole_f_c_.Dim() + peephole_o_c_.Dim() +
+         w_r_m_.NumRows() * w_r_m_.NumCols();
+}
+
+void LstmCifgProjectedStreams::GetParams(Vector<BaseFloat>* wei_copy) const {
+  wei_copy->Resize(NumParams());
+  float* p = wei_copy->Data();
+  auto vec = [&](const CuVector<BaseFloat>& v) { Vector<float> h; v.CopyToVec(&h); for (int32 i = 0; i < h.Dim(); ++i) *p++ = h(i); };
+  auto mat = [&](const CuMatrix<BaseFloat>& m) { CopyRowsToVec(m, p); p += static_cast<size_t>(m.NumRows()) * m.NumCols(); };
+  mat(w_gfo_x_); mat(w_gfo_r_); vec(bias_); vec(peephole_f_c_); vec(peephole_o_c_); mat(w_r_m_);
+}
+
+void LstmCifgProjectedStreams::GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* params) {
+  params->clear();
+  params->push_back(std::make_pair(w_gfo_x_.Data(), w_gfo_x_.NumRows() * w_gfo_x_.Stride()));
+  params->push_back(std::make_pair(w_gfo_r_.Data(), w_gfo_r_.NumRows() * w_gfo_r_.Stride()));
+  params->push_back(std::make_pair(bias_.Data(), bias_.Dim()));
+  params->push_back(std::make_pair(peephole_f_c_.Data(), peephole_f_c_.Dim()));
+  params->push_back(std::make_pair(peephole_o_c_.Data(), peephole_o_c_.Dim()));
+  params->push_back(std::make_pair(w_r_m_.Data(), w_r_m_.NumRows() * w_r_m_.Stride()));
+}
+
+std::string LstmCifgProjectedStreams::Info() const {
+  return std::string("  ") + "\n  w_gfo_x_  " + MomentStatistics(w_gfo_x_) + "\n  w_gfo_r_  " + MomentStatistics(w_gfo_r_) + "\n  bias_  " + MomentStatistics(bias_) +
+         "\n  peephole_f_c_  " + MomentStatistics(peephole_f_c_) + "\n  peephole_o_c_  " + MomentStatistics(peephole_o_c_) + "\n  w_r_m_  " + MomentStatistics(w_r_m_);
+}
+std::string LstmCifgProjectedStreams::InfoGradient() const {
+  return std::string("  ") + "\n  Gradients:" + "\n  w_gfo_x_corr_  " + MomentStatistics(w_gfo_x_corr_) + "\n  w_gfo_r_corr_  " + MomentStatistics(w_gfo_r_corr_) +
+         "\n  bias_corr_  " + MomentStatistics(bias_corr_) + "\n  peephole_f_c_corr_  " + MomentStatistics(peephole_f_c_corr_) +
+         "\n  peephole_o_c_corr_  " + MomentStatistics(peephole_o_c_corr_) + "\n  w_r_m_corr_  " + MomentStatistics(w_r_m_corr_);
+}
+
+void LstmCifgProjectedStreams::PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
+  aslp_stream_t st = CuStream();
+  LstmFamily::Dir& d = engine_.d_[0];
+  const int32 C = ncell_;
+  // four-gate view of the three-gate parameters: rows [g | -f | f | o]
+  ASLP_OK(aslp_cifg_expand(st, d.w_gifo_x.Data(), d.w_gifo_x.Stride(), w_gfo_x_.Data(), w_gfo_x_.Stride(), C, input_dim_));
+  ASLP_OK(aslp_cifg_expand(st, d.w_gifo_r.Data(), d.w_gifo_r.Stride(), w_gfo_r_.Data(), w_gfo_r_.Stride(), C, nrecur_));
+  ASLP_OK(aslp_cifg_expand(st, d.bias.Data(), 1, bias_.Data(), 1, C, 1));
+  const int32 ldv = (C + 3) / 4 * 4;
+  ASLP_OK(aslp_axpby(st, d.peep_i.Data(), ldv, peephole_f_c_.Data(), ldv, 1, C, -1.0f, 0.0f));
+  ASLP_OK(aslp_axpby(st, d.peep_f.Data(), ldv, peephole_f_c_.Data(), ldv, 1, C, 1.0f, 0.0f));
+  ASLP_OK(aslp_axpby(st, d.peep_o.Data(), ldv, peephole_o_c_.Data(), ldv, 1, C, 1.0f, 0.0f));
+  d.w_r_m.CopyFromMat(w_r_m_);
+  engine_.PropagateFnc(in, out);
+}
+
+void LstmCifgProjectedStreams::BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff,
+                                                CuMatrixBase<BaseFloat>* in_diff) {
+  engine_.BackpropagateFnc(in, out, out_diff, in_diff);        // recurrence, d_r, in_diff = dgifo W4_x (= DGFO w_gfo_x_)
+  const int32 S = engine_.nstream_, T = in.NumRows() / S, C = ncell_;
+  const LstmFamily::Dir& d = engine_.d_[0];
+  aslp_stream_t st = CuStream();
+  const int prec = GemmPrecision();
+  const float mmt = opts_.momentum, clip = clip_gradient_;
+  dgfo_.Resize(T * S, 3 * C, kUndefined);
+  CuSubMatrix<BaseFloat> dgifo = d.back.Range(S, T * S, 0, 4 * C);
+  ASLP_OK(aslp_cifg_compact(st, dgfo_.Data(), dgfo_.Stride(), dgifo.Data(), dgifo.Stride(), T * S, C));
+  const size_t gws = 64u << 20;
+  void* ws = CuWorkspace(gws);
+  // nnet-lstm-couple-if-projected-streams.h:593-640: momentum as beta of the product, then the elementwise clip
+  ASLP_OK(aslp_gemm(st, 1, 0, 3 * C, input_dim_, T * S, 1.0f, dgfo_.Data(), dgfo_.Stride(), in.Data(), in.Stride(), mmt, w_gfo_x_corr_.Data(),
+                    w_gfo_x_corr_.Stride(), nullptr, clip, prec, ws, gws));
+  CuSubMatrix<BaseFloat> r_prev = d.prop.Range(0, T * S, 7 * C, nrecur_);
+  ASLP_OK(aslp_gemm(st, 1, 0, 3 * C, nrecur_, T * S, 1.0f, dgfo_.Data(), dgfo_.Stride(), r_prev.Data(), r_prev.Stride(), mmt, w_gfo_r_corr_.Data(),
+                    w_gfo_r_corr_.Stride(), nullptr, clip, prec, ws, gws));
+  ASLP_OK(aslp_col_sum(st, bias_corr_.Data(), dgfo_.Data(), dgfo_.Stride(), T * S, 3 * C, 1.0f, mmt, clip));
+  CuSubMatrix<BaseFloat> c_prev = d.prop.Range(0, T * S, 4 * C, C), c_cur = d.prop.Range(S, T * S, 4 * C, C);
+  CuSubMatrix<BaseFloat> df = dgfo_.ColRange(C, C), d_out = dgfo_.ColRange(2 * C, C);
+  ASLP_OK(aslp_col_dot(st, peephole_f_c_corr_.Data(), df.Data(), df.Stride(), c_prev.Data(), c_prev.Stride(), T * S, C, 1.0f, mmt, clip));
+  ASLP_OK(aslp_col_dot(st, peephole_o_c_corr_.Data(), d_out.Data(), d_out.Stride(), c_cur.Data(), c_cur.Stride(), T * S, C, 1.0f, mmt, clip));
+  CuSubMatrix<BaseFloat> dr = d.back.Range(S, T * S, 7 * C, nrecur_), ym = d.prop.Range(S, T * S, 6 * C, C);
+  ASLP_OK(aslp_gemm(st, 1, 0, nrecur_, C, T * S, 1.0f, dr.Data(), dr.Stride(), ym.Data(), ym.Stride(), mmt, w_r_m_corr_.Data(), w_r_m_corr_.Stride(),
+                    nullptr, clip, prec, ws, gws));
+}
+
+void LstmCifgProjectedStreams::Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
+  const float lr = opts_.learn_rate;
+  aslp_stream_t st = CuStream();
+  auto mat = [&](CuMatrix<BaseFloat>& w, const CuMatrix<BaseFloat>& c) { ASLP_OK(aslp_axpby(st, w.Data(), w.Stride(), c.Data(), c.Stride(), w.NumRows(), w.NumCols(), -lr, 1.0f)); };
+  auto vec = [&](CuVector<BaseFloat>& w, const CuVector<BaseFloat>& c) { ASLP_OK(aslp_axpby(st, w.Data(), (w.Dim() + 3) / 4 * 4, c.Data(), (c.Dim() + 3) / 4 * 4, 1, w.Dim(), -lr, 1.0f)); };
+  mat(w_gfo_x_, w_gfo_x_corr_); mat(w_gfo_r_, w_gfo_r_corr_); vec(bias_, bias_corr_);
+  vec(peephole_f_c_, peephole_f_c_corr_); vec(peephole_o_c_, peephole_o_c_corr_); mat(w_r_m_, w_r_m_corr_);
 }
 
 }  // namespace aslp_nnet

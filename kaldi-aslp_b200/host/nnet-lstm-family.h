@@ -52,11 +52,15 @@ class LstmFamily : public UpdatableComponent {
   void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff);
   void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff);
 
+  // the weight-gradient tail of BackpropagateFnc is skipped: the owner computes its own (LstmCifgProjectedStreams)
+  void SetSkipWeightGradients(bool v) { skip_wgrad_ = v; }
+
   // test / tooling access
   const CuMatrix<BaseFloat>& PropagateBuf(int dir) const { return d_[dir].prop; }
   const CuMatrix<BaseFloat>& BackpropagateBuf(int dir) const { return d_[dir].back; }
 
  private:
+  friend class LstmCifgProjectedStreams;
   struct Dir {
     CuMatrix<BaseFloat> w_gifo_x, w_gifo_r, w_r_m;
     CuVector<BaseFloat> bias, peep_i, peep_f, peep_o;
@@ -81,6 +85,7 @@ class LstmFamily : public UpdatableComponent {
   CuArrayInt seq_len_dev_;
   bool async_tail_ = false;             // the last BackpropagateFnc put its weight gradients on the side stream
   bool per_utt_reset_;                  // nnet-forward mode: 1 stream, state reset every call (the reference's function-local static)
+  bool skip_wgrad_ = false;
 };
 
 // thin named types so that factory / dynamic_cast code reads like the reference
@@ -97,6 +102,42 @@ ASLP_LSTM_TYPE(LstmProjectedStreams,    kLstmProjectedStreams,    1, true,  true
 ASLP_LSTM_TYPE(BLstmProjectedStreams,   kBLstmProjectedStreams,   2, true,  true,  false, false, true);
 ASLP_LSTM_TYPE(BLstmProjectedStreamsLC, kBLstmProjectedStreamsLC, 2, true,  true,  true,  true,  false);
 #undef ASLP_LSTM_TYPE
+
+
+// LstmCifgProjectedStreams (src/aslp-nnet/nnet-lstm-couple-if-projected-streams.h): projected LSTM whose input gate is coupled to the
+// forget gate, i = 1 - f, with three gate blocks [g f o] and two peepholes.  Since 1 - sigmoid(x) = sigmoid(-x), the coupled cell IS
+// the four-gate cell with W_i = -W_f, bias_i = -bias_f, peephole_i = -peephole_f: the component keeps the reference's three-gate
+// parameters (file format, GetParams / GetGpuParams order, gradients, clipping) and drives the persistent recurrence of LstmFamily
+// with the expanded four-gate view, rebuilt from the parameters at every Propagate.  The three-gate derivative the weight gradients
+// need is d_f(coupled) = d_f - d_i of the four-gate cell (nnet-lstm-couple-if-projected-streams.h:566-569).
+class LstmCifgProjectedStreams : public UpdatableComponent {
+ public:
+  LstmCifgProjectedStreams(int32 input_dim, int32 output_dim);
+  Component* Copy() const { return new LstmCifgProjectedStreams(*this); }
+  ComponentType GetType() const { return kLstmCifgProjectedStreams; }
+  void InitData(std::istream& is);
+  void ReadData(std::istream& is, bool binary);
+  void WriteData(std::ostream& os, bool binary) const;
+  int32 NumParams() const;
+  void GetParams(Vector<BaseFloat>* wei_copy) const;
+  void GetGpuParams(std::vector<std::pair<BaseFloat*, int>>* params);
+  std::string Info() const;
+  std::string InfoGradient() const;
+  void ResetLstmStreams(const std::vector<int32>& stream_reset_flag) { engine_.ResetLstmStreams(stream_reset_flag); }
+  void SetSeqLengths(const std::vector<int32>& sequence_lengths) { engine_.SetSeqLengths(sequence_lengths); }
+  void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out);
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff);
+  void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff);
+ private:
+  void SizeEngine();
+  void AllocCorr();
+  int32 ncell_, nrecur_;
+  BaseFloat clip_gradient_;
+  CuMatrix<BaseFloat> w_gfo_x_, w_gfo_r_, w_r_m_, w_gfo_x_corr_, w_gfo_r_corr_, w_r_m_corr_;
+  CuVector<BaseFloat> bias_, peephole_f_c_, peephole_o_c_, bias_corr_, peephole_f_c_corr_, peephole_o_c_corr_;
+  CuMatrix<BaseFloat> dgfo_;         // [T*S, 3C] three-gate derivatives of the last backward pass
+  LstmFamily engine_;                // four-gate recurrence (LstmProjectedStreams traits), weight gradients off
+};
 
 }  // namespace aslp_nnet
 }  // namespace kaldi

@@ -4,6 +4,7 @@
 #include "nnet-gru-streams.h"
 #include "nnet-lstm-family.h"
 #include "nnet-misc-components.h"
+#include "nnet-zoo-components.h"
 
 namespace kaldi {
 namespace aslp_nnet {
@@ -233,6 +234,7 @@ void Nnet::GetAccStats(std::vector<double*>* acc_params, std::vector<std::pair<d
 void Nnet::ResetLstmStreams(const std::vector<int32>& flags) {
   for (Component* c : components_) {
     if (LstmFamily* l = dynamic_cast<LstmFamily*>(c)) l->ResetLstmStreams(flags);      // no-op for the non-carrying types
+    else if (LstmCifgProjectedStreams* q = dynamic_cast<LstmCifgProjectedStreams*>(c)) q->ResetLstmStreams(flags);
     else if (GruStreams* g = dynamic_cast<GruStreams*>(c)) g->ResetLstmStreams(flags);
   }
 }
@@ -246,8 +248,20 @@ void Nnet::SetSeqLengths(const std::vector<int32>& lens) {
     if (LstmFamily* l = dynamic_cast<LstmFamily*>(c)) {
       if (strict && c->GetType() == Component::kBLstmProjectedStreamsLC) continue;
       l->SetSeqLengths(lens);
-    } else if (RowConvolution* r = dynamic_cast<RowConvolution*>(c)) r->SetSeqLengths(lens);
+    } else if (LstmCifgProjectedStreams* q = dynamic_cast<LstmCifgProjectedStreams*>(c)) q->SetSeqLengths(lens);
+    else if (RowConvolution* r = dynamic_cast<RowConvolution*>(c)) r->SetSeqLengths(lens);
     else if (GruStreams* g = dynamic_cast<GruStreams*>(c)) g->SetSeqLengths(lens);
+  }
+}
+// nnet-nnet.cc:454-464
+void Nnet::SetDropoutRetention(BaseFloat r) {
+  for (int32 c = 0; c < NumComponents(); c++) {
+    if (GetComponent(c).GetType() == Component::kDropout) {
+      Dropout& comp = dynamic_cast<Dropout&>(GetComponent(c));
+      const BaseFloat r_old = comp.GetDropoutRetention();
+      comp.SetDropoutRetention(r);
+      KALDI_LOG << "Setting dropout-retention in component " << c << " from " << r_old << " to " << r;
+    }
   }
 }
 void Nnet::SetChunkSize(int chunk_size) {

@@ -49,6 +49,7 @@ class Nnet {
   void ResetLstmStreams(const std::vector<int32>& stream_reset_flag);
   void SetSeqLengths(const std::vector<int32>& sequence_lengths);
   void SetChunkSize(int chunk_size);
+  void SetDropoutRetention(BaseFloat r);        // nnet-nnet.h:153
 
   void Init(const std::string& config_file);
   void Read(const std::string& file);

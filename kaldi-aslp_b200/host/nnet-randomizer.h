@@ -26,6 +26,7 @@ struct NnetDataRandomizerOptions {
 class RandomizerMask {
  public:
   RandomizerMask() {}
+  explicit RandomizerMask(const NnetDataRandomizerOptions& conf) { Init(conf); }      // nnet-randomizer.h:74
   void Init(const NnetDataRandomizerOptions& conf) {
     KALDI_LOG << "Seeding by srand with : " << conf.randomizer_seed;
     srand(conf.randomizer_seed);
@@ -49,6 +50,7 @@ class RandomizerMask {
 class MatrixRandomizer {
  public:
   MatrixRandomizer() : data_begin_(0), data_end_(0) {}
+  explicit MatrixRandomizer(const NnetDataRandomizerOptions& conf) : data_begin_(0), data_end_(0) { Init(conf); }
   void Init(const NnetDataRandomizerOptions& conf) { conf_ = conf; }
   void AddData(const CuMatrixBase<BaseFloat>& m) {
     if (data_.NumCols() == 0) data_.Resize(conf_.randomizer_size, m.NumCols());
@@ -96,6 +98,7 @@ template <typename T>
 class StdVectorRandomizer {
  public:
   StdVectorRandomizer() : data_begin_(0), data_end_(0) {}
+  explicit StdVectorRandomizer(const NnetDataRandomizerOptions& conf) : data_begin_(0), data_end_(0) { Init(conf); }
   void Init(const NnetDataRandomizerOptions& conf) { conf_ = conf; }
   void AddData(const std::vector<T>& v) {
     if (data_.size() == 0) data_.resize(conf_.randomizer_size);
@@ -130,6 +133,30 @@ class StdVectorRandomizer {
   NnetDataRandomizerOptions conf_;
 };
 typedef StdVectorRandomizer<std::vector<std::pair<int32, BaseFloat>>> PosteriorRandomizer;
+typedef StdVectorRandomizer<int32> Int32VectorRandomizer;
+
+// per-frame weights (nnet-randomizer.h:105-138): the same begin / end arithmetic on a Vector<BaseFloat>
+class VectorRandomizer {
+ public:
+  VectorRandomizer() {}
+  explicit VectorRandomizer(const NnetDataRandomizerOptions& conf) : r_(conf) {}
+  void Init(const NnetDataRandomizerOptions& conf) { r_.Init(conf); }
+  void AddData(const Vector<BaseFloat>& v) { r_.AddData(std::vector<BaseFloat>(v.Data(), v.Data() + v.Dim())); }
+  bool IsFull() const { return r_.IsFull(); }
+  int32 NumFrames() const { return r_.NumFrames(); }
+  void Randomize(const std::vector<int32>& mask) { r_.Randomize(mask); }
+  bool Done() const { return r_.Done(); }
+  void Next() { r_.Next(); }
+  const Vector<BaseFloat>& Value() {
+    const std::vector<BaseFloat>& m = r_.Value();
+    minibatch_.Resize(static_cast<int32>(m.size()), kUndefined);
+    for (size_t i = 0; i < m.size(); ++i) minibatch_(static_cast<int32>(i)) = m[i];
+    return minibatch_;
+  }
+ private:
+  StdVectorRandomizer<BaseFloat> r_;
+  Vector<BaseFloat> minibatch_;
+};
 
 // features + frame targets -> shuffled minibatches (data-reader.cc:62-182)
 // The begin / end arithmetic of MatrixRandomizer / StdVectorRandomizer without the data (nnet-randomizer.cc:60-134): which

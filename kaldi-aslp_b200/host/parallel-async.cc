@@ -136,6 +136,7 @@ void IServer::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
 EasgdWorker::EasgdWorker(const char id[128], int nranks, int rank, float alpha) : IWorker(id, nranks, rank), alpha_(alpha), ctrl_(nullptr) {
   KALDI_ASSERT(rank != 0);
 }
+EasgdWorker::EasgdWorker(float alpha) : IWorker(WorkerBootstrap()), alpha_(alpha), ctrl_(nullptr) { KALDI_ASSERT(Rank() != 0); }
 EasgdWorker::~EasgdWorker() { delete ctrl_; }
 void EasgdWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
   IWorker::InitParam(params);
@@ -190,6 +191,7 @@ void EasgdServer::Update(int worker_rank) {
 
 // ---------------------------------------------------------------- ASGD / MASGD
 AsgdWorker::AsgdWorker(const char id[128], int nranks, int rank) : IWorker(id, nranks, rank), ctrl_(nullptr) { KALDI_ASSERT(rank != 0); }
+AsgdWorker::AsgdWorker() : IWorker(WorkerBootstrap()), ctrl_(nullptr) { KALDI_ASSERT(Rank() != 0); }
 AsgdWorker::~AsgdWorker() { delete ctrl_; }
 void AsgdWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
   IWorker::InitParam(params);

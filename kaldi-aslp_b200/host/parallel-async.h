@@ -59,6 +59,7 @@ class IServer : public NcclNode {             // itf.h:38-43
 class EasgdWorker : public IWorker {
  public:
   EasgdWorker(const char id[128], int nranks, int rank, float alpha = 0.5f);
+  explicit EasgdWorker(float alpha);                           // easgd-worker.h: environment bootstrap (see IWorker)
   ~EasgdWorker();
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);        // always true (easgd-worker.cc:66)
@@ -81,6 +82,7 @@ class EasgdServer : public IServer {
 class AsgdWorker : public IWorker {
  public:
   AsgdWorker(const char id[128], int nranks, int rank);
+  AsgdWorker();                                                // asgd-worker.h
   ~AsgdWorker();
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);

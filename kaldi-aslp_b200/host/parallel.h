@@ -29,9 +29,21 @@ class NcclNode {
   int rank_, nranks_;
 };
 
+// Process-launch bootstrap for the worker mains (what mpirun + MPI_Init did in the reference): rank and world size
+// from RANK / WORLD_SIZE (torchrun's variables; OMPI_COMM_WORLD_RANK / _SIZE are honoured too), the ncclUniqueId
+// through a file named by ASLP_NCCL_ID_FILE (rank 0 writes it atomically, the others wait for it).
+struct WorkerBootstrap {
+  char id[128];
+  int rank, nranks;
+  WorkerBootstrap();
+};
+
 class IWorker : public NcclNode {
  public:
   IWorker(const char id[128], int nranks, int rank) : NcclNode(id, nranks, rank), table_dev_(nullptr), total_(0) {}
+  // the reference's workers take no launch arguments (MpiNode's constructor calls MPI_Init, mpi-node.h:21-27): bootstrap from the
+  // environment instead, so that `new BspWorker()` / `new BmufWorker(momentum, learn_rate)` in an unmodified main keep working
+  explicit IWorker(const WorkerBootstrap& b) : NcclNode(b.id, b.nranks, b.rank), table_dev_(nullptr), total_(0) {}
   virtual ~IWorker();
   virtual void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   virtual bool Synchronize(int num_worker_samples) = 0;   // false when every rank is out of data
@@ -49,6 +61,7 @@ class IWorker : public NcclNode {
 class BspWorker : public IWorker {
  public:
   BspWorker(const char id[128], int nranks, int rank) : IWorker(id, nranks, rank) {}
+  BspWorker() : IWorker(WorkerBootstrap()) {}                                  // bsp-worker.h:21
   bool Synchronize(int num_worker_samples);
 };
 
@@ -56,20 +69,13 @@ class BmufWorker : public IWorker {
  public:
   BmufWorker(const char id[128], int nranks, int rank, float momentum = 0.9f, float learn_rate = 1.0f)
       : IWorker(id, nranks, rank), momentum_(momentum), learn_rate_(learn_rate) {}
+  // the reference's own signature and argument ORDER (bmuf-worker.h:31: learn rate first)
+  explicit BmufWorker(float learn_rate = 1.0f, float momentum = 0.9f) : IWorker(WorkerBootstrap()), momentum_(momentum), learn_rate_(learn_rate) {}
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);
  private:
   float momentum_, learn_rate_;
   CuVector<BaseFloat> w_prev_, delta_prev_;
-};
-
-// Process-launch bootstrap for the worker mains (what mpirun + MPI_Init did in the reference): rank and world size
-// from RANK / WORLD_SIZE (torchrun's variables; OMPI_COMM_WORLD_RANK / _SIZE are honoured too), the ncclUniqueId
-// through a file named by ASLP_NCCL_ID_FILE (rank 0 writes it atomically, the others wait for it).
-struct WorkerBootstrap {
-  char id[128];
-  int rank, nranks;
-  WorkerBootstrap();
 };
 
 struct OptimizerOption {
@@ -93,6 +99,7 @@ struct OptimizerOption {
 class SodWorker : public IWorker {
  public:
   SodWorker(const char id[128], int nranks, int rank, const OptimizerOption& config) : IWorker(id, nranks, rank), config_(config), step_(1) {}
+  explicit SodWorker(const OptimizerOption& config) : IWorker(WorkerBootstrap()), config_(config), step_(1) {}              // sod-worker.h
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);
  private:

@@ -143,15 +143,19 @@ class Nnet:
 
 
 class Xent:
-    def __init__(self):
+    """a frame-level objective (LossItf): Xent by default, Loss("mse") / Loss("multitask,...") for the others"""
+    def __init__(self, objective="xent"):
         self.h = P()
-        _ck(host_lib().aslp_xent_create(ctypes.byref(self.h)))
+        _ck(host_lib().aslp_loss_create(objective.encode(), ctypes.byref(self.h)))
 
     def report(self):
         buf = ctypes.create_string_buffer(4096)
         st = (ctypes.c_double * 5)()
         _ck(host_lib().aslp_xent_report(self.h, buf, len(buf), st))
         return buf.value.decode(), list(st)
+
+
+Loss = Xent
 
 
 class WarpCtc:

@@ -100,6 +100,38 @@ CASES = {
                "<AffineTransform> <InputDim> 20 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
                "<Softmax> <InputDim> 8 <OutputDim> 8"],
         dim=12, rows=32, loss="xent", spec=dict(learn_rate=0.05, momentum=0.9, iters=2, dump_components=1)),
+    "zoo_pnorm_lengthnorm": dict(      # Pnorm (p = 2 and a general p), LengthNorm, Copy as a front end
+        proto=["<Copy> <InputDim> 10 <OutputDim> 12 <BuildVector> 1:10 3 7 </BuildVector>",
+               "<AffineTransform> <InputDim> 12 <OutputDim> 24 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.3",
+               "<Pnorm> <InputDim> 24 <OutputDim> 8 <P> 2",
+               "<LengthNormComponent> <InputDim> 8 <OutputDim> 8",
+               "<AffineTransform> <InputDim> 8 <OutputDim> 18 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.4",
+               "<Pnorm> <InputDim> 18 <OutputDim> 6 <P> 3",
+               "<AffineTransform> <InputDim> 6 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
+               "<Softmax> <InputDim> 8 <OutputDim> 8"],
+        dim=10, rows=21, loss="xent", spec=dict(learn_rate=0.05, momentum=0.9, iters=2, dump_components=1)),
+    "zoo_blocksoftmax_mse": dict(      # BlockSoftmax over blocks of 5 + 3 outputs, trained with the Mse objective
+        proto=["<AffineTransform> <InputDim> 9 <OutputDim> 14 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.3",
+               "<Tanh> <InputDim> 14 <OutputDim> 14",
+               "<AffineTransform> <InputDim> 14 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
+               "<BlockSoftmax> <InputDim> 8 <OutputDim> 8 <BlockDims> 5:3"],
+        dim=9, rows=17, loss="mse", spec=dict(learn_rate=0.05, momentum=0.9, iters=2, dump_components=1)),
+    "zoo_blocksoftmax_xent": dict(     # the backward rule that zeroes the block without the target
+        proto=["<AffineTransform> <InputDim> 9 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.3",
+               "<BlockSoftmax> <InputDim> 8 <OutputDim> 8 <BlockDims> 5:3"],
+        dim=9, rows=16, loss="xent", spec=dict(learn_rate=0.05, momentum=0.5, iters=2, dump_components=1)),
+    "zoo_dropout": dict(               # masks drawn from rand() in the reference CPU order (ASLP_DROPOUT_HOST_RAND=1 on our side)
+        proto=["<AffineTransform> <InputDim> 10 <OutputDim> 16 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.3",
+               "<Sigmoid> <InputDim> 16 <OutputDim> 16",
+               "<Dropout> <InputDim> 16 <OutputDim> 16",                       # the reference cannot parse <DropoutRetention> from a proto line (ReadToken fails at the line end): default 0.5
+               "<AffineTransform> <InputDim> 16 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
+               "<Softmax> <InputDim> 8 <OutputDim> 8"],
+        dim=10, rows=19, loss="xent", spec=dict(learn_rate=0.05, momentum=0.9, iters=3, srand=4321, dump_components=1)),
+    "lstm_cifg_xent": dict(            # coupled input-forget gate, state carried over the iterations, one stream restarted
+        proto=["<LstmCifgProjectedStreams> <InputDim> 10 <OutputDim> 12 <CellDim> 16 <ClipGradient> 5 <ParamScale> 0.2",
+               "<AffineTransform> <InputDim> 12 <OutputDim> 8 <BiasMean> 0 <BiasRange> 0 <ParamStddev> 0.3",
+               "<Softmax> <InputDim> 8 <OutputDim> 8"],
+        dim=10, rows=6 * 3, loss="xent", spec=dict(learn_rate=0.05, momentum=0.9, iters=3, reset_flags="1,0,0", dump_components=1)),
     "splice_rowconv": dict(
         proto=["<Splice> <InputDim> 6 <OutputDim> 18 <BuildVector> -1:1 </BuildVector>",
                "<AffineTransform> <InputDim> 18 <OutputDim> 12 <BiasMean> 0 <BiasRange> 0.5 <ParamStddev> 0.3",
@@ -132,7 +164,7 @@ def main():
         spec = dict(c["spec"])
         spec["input"] = "input.mat"
         spec["loss"] = c["loss"]
-        if c["loss"] == "xent":
+        if c["loss"] in ("xent", "mse"):
             np.savetxt(os.path.join(d, "targets.txt"), rng.integers(0, out_dim, c["rows"]), fmt="%d")
             spec["targets"] = "targets.txt"
             if "mask_tail" in c:

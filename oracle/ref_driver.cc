@@ -10,7 +10,8 @@
 // spec-file: one `key value` per line
 //   input <kaldi matrix file>          features [rows, dim], stream-interleaved for recurrent nets
 //   out_diff <kaldi matrix file>       explicit d(loss)/d(output)            (loss none)
-//   loss none|xent|ctc
+//   loss none|xent|mse|ctc                mse: Mse::Eval on the same posterior targets as xent
+//   srand n                            std::srand(n) before the first iteration (Dropout draws its masks from rand())
 //   targets <file>                     xent: one int per row (text, whitespace separated)
 //   frame_mask <file>                  xent: one float per row (optional)
 //   labels <file>                      ctc: one utterance per line, ints
@@ -118,7 +119,7 @@ int main(int argc, char** argv) {
     Posterior post;
     Vector<BaseFloat> frame_mask;
     std::vector<std::vector<int32> > labels;
-    if (loss == "xent") {
+    if (loss == "xent" || loss == "mse") {
       std::ifstream ts(sp["targets"].c_str());
       int t;
       while (ts >> t) { post.push_back(std::vector<std::pair<int32, BaseFloat> >(1, std::make_pair(t, 1.0f))); }
@@ -131,11 +132,13 @@ int main(int argc, char** argv) {
       while (std::getline(ls, line)) { if (line.find_first_not_of(" \t\r") != std::string::npos) labels.push_back(Ints(line)); }
     }
     Xent xent;
+    Mse mse;
     WarpCtc ctc;
     ctc.SetUseGpu(false);
     std::vector<std::string> keys;
     for (size_t i = 0; i < seq_lengths.size(); ++i) { std::ostringstream k; k << "utt" << i; keys.push_back(k.str()); }
 
+    if (sp.count("srand")) std::srand(atoi(sp["srand"].c_str()));
     CuMatrix<BaseFloat> in(in_h), out, diff, in_diff;
     Timer timer;
     double frames_done = 0;
@@ -157,6 +160,7 @@ int main(int argc, char** argv) {
       }
       nnet.Propagate(in, &out);
       if (loss == "xent") xent.Eval(frame_mask, out, post, &diff);
+      else if (loss == "mse") mse.Eval(frame_mask, out, post, &diff);
       else if (loss == "ctc") ctc.Eval(keys, seq_lengths, out, labels, &diff);
       else diff = CuMatrix<BaseFloat>(od_h);
       nnet.Backpropagate(diff, &in_diff);
@@ -189,6 +193,7 @@ int main(int argc, char** argv) {
     } else {
       std::ofstream rep((outdir + "/report.txt").c_str());
       if (loss == "xent") rep << xent.Report();
+      if (loss == "mse") rep << mse.Report();
       if (loss == "ctc") rep << ctc.Report() << "\n";
     }
     return 0;
