@@ -62,6 +62,8 @@ int aslp_device_sync(void);
 int aslp_event_record(aslp_stream_t s, void** event);
 int aslp_event_elapsed_ms(void* a, void* b, float* ms);
 int aslp_stream_wait_event(aslp_stream_t s, void* event);   /* later work on s starts after `event` (recorded on another stream) */
+int aslp_event_destroy(void* event);                        /* NULL is fine */
+int aslp_scratch_release(aslp_stream_t s);                  /* frees the library's per-stream scratch arena before a stream is destroyed */
 int aslp_event_sync(void* event);                           /* the host waits for `event` (a pinned staging slot is free again) */
 
 /* ---- dense contraction: CuMatrixBase::AddMatMat (cu-matrix.cc:1027-1062) ----

@@ -3,6 +3,7 @@
 // repeated, mask 0 for the look-ahead rows) and log lines as src/aslp-nnetbin/aslp-nnet-train-blstm-streams-lc.cc:35-394.
 // With --worker-type it is the worker of src/aslp-parallelbin/aslp-nnet-train-lc-blstm-streams-worker.cc:176-330
 // (one process per GPU; that binary spells the look-ahead flag --right_splice: '-' and '_' are interchangeable here).
+#include <memory>
 #include "batch-feeder.h"
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
@@ -10,6 +11,7 @@
 #include "nnet-trnopts.h"
 #include "parallel-async.h"
 #include "parse-options.h"
+#include "worker-opts.h"
 #include "table.h"
 
 int main(int argc, char* argv[]) {
@@ -71,7 +73,6 @@ int main(int argc, char* argv[]) {
     std::string target_model_filename;
     if (!crossvalidate) target_model_filename = po.GetArg(4);
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
-    if (objective_function != "xent") KALDI_ERR << "Unknown objective function code : " << objective_function;
     if (!worker_type.empty()) {
       const char* lr = std::getenv("LOCAL_RANK");
       if (lr != nullptr) ASLP_OK(aslp_set_device(std::atoi(lr)));
@@ -101,7 +102,11 @@ int main(int argc, char* argv[]) {
     long long total_frames = 0;
     SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
     RandomAccessPosteriorReader target_reader(targets_rspecifier);
-    Xent xent;
+    std::unique_ptr<LossItf> loss_holder;                  // LossItf* as in the reference's worker mains (xent | mse)
+    if (objective_function == "xent") loss_holder.reset(new Xent);
+    else if (objective_function == "mse") loss_holder.reset(new Mse);
+    else KALDI_ERR << "Unsupported objective function: " << objective_function;
+    LossItf& xent = *loss_holder;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0, num_sentence = 0, num_frames_since_sync = 0;
@@ -228,13 +233,7 @@ int main(int argc, char* argv[]) {
       }
     }
     feeder.Join();
-    if (worker) {
-      if (!worker->IsAsync()) {
-        if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);
-        while (worker->Synchronize(0)) {}
-      }
-      worker->Stop();         // async modes: kMsgFinished to the server, which writes the model
-    }
+    if (worker) FinishWorker(worker.get(), &nnet);        // Stop(), then the BatchNorm statistics of all ranks (worker-opts.h)
     if (!crossvalidate && (!worker || worker->IsMainNode())) nnet.Write(target_model_filename, binary);
     KALDI_LOG << "Done " << num_done << " files, " << num_no_tgt_mat << " with no tgt_mats, " << num_other_error << " with other errors. "
               << "[" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", " << (randomize ? "RANDOMIZED" : "NOT-RANDOMIZED") << ", "

@@ -1,6 +1,7 @@
 // aslp-nnet-train-frame -- frame-shuffled minibatch training, same command line, bookkeeping and log lines as
 // src/aslp-nnetbin/aslp-nnet-train-frame.cc:22-153.  --use-gpu=no is refused: this build has no CPU path.
 // With --worker-type it is the worker of src/aslp-parallelbin/aslp-nnet-train-frame-worker.cc (bin/worker-opts.h).
+#include <memory>
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
@@ -47,14 +48,19 @@ int main(int argc, char* argv[]) {
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
     if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));
     else wopts.SelectDevice();
-    if (objective_function != "xent") KALDI_ERR << "Unsupported objective function: " << objective_function;
-    if (dropout_retention > 0.0) KALDI_ERR << "--dropout-retention: Dropout is not part of this build";
 
     Nnet nnet;
     nnet.Read(model_filename);
     nnet.SetTrainOptions(trn_opts);
+    // aslp-nnet-train-frame.cc:82-88: dropout retention from the command line while training, switched off (1.0) for cross-validation
+    if (dropout_retention > 0.0) nnet.SetDropoutRetention(dropout_retention);
+    if (crossvalidate) nnet.SetDropoutRetention(1.0);
     wopts.Create(&nnet, crossvalidate);
-    Xent loss;
+    std::unique_ptr<LossItf> loss_holder;                  // aslp-nnet-train-frame.cc:90-98
+    if (objective_function == "xent") loss_holder.reset(new Xent);
+    else if (objective_function == "mse") loss_holder.reset(new Mse);
+    else KALDI_ERR << "Unsupported objective function: " << objective_function;
+    LossItf& loss = *loss_holder;
     Timer time;
     long long total_frames = 0, report_frames = 0;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";

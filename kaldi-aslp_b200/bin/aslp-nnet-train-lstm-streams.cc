@@ -1,6 +1,7 @@
 // aslp-nnet-train-lstm-streams -- multi-stream truncated-BPTT training of (projected) LSTMs with delayed targets, same
 // command line, batching (SequenceDataReader), bookkeeping and log lines as
 // src/aslp-nnetbin/aslp-nnet-train-lstm-streams.cc:24-240 (BASELINE config 2).
+#include <memory>
 #include "batch-feeder.h"
 #include "nnet-nnet.h"
 #include "nnet-loss.h"
@@ -54,7 +55,6 @@ int main(int argc, char* argv[]) {
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
     if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));
     else wopts.SelectDevice();
-    if (objective_function != "xent") KALDI_ERR << "Unsupported objective function: " << objective_function;
 
     Nnet nnet;
     nnet.Read(model_filename);
@@ -62,7 +62,11 @@ int main(int argc, char* argv[]) {
     wopts.Create(&nnet, crossvalidate);
     long long total_frames = 0;
     int32 num_done = 0, num_sentence = 0;
-    Xent loss;
+    std::unique_ptr<LossItf> loss_holder;                  // LossItf* as in the reference's worker mains (xent | mse)
+    if (objective_function == "xent") loss_holder.reset(new Xent);
+    else if (objective_function == "mse") loss_holder.reset(new Mse);
+    else KALDI_ERR << "Unsupported objective function: " << objective_function;
+    LossItf& loss = *loss_holder;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     SequenceDataReader reader(feature_rspecifier, targets_rspecifier, read_opts);

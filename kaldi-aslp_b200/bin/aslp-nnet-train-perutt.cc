@@ -1,6 +1,7 @@
 // aslp-nnet-train-perutt -- one utterance per update (the FSMN / whole-sentence trainer, BASELINE config 4), same command
 // line, length-tolerance rule, learn-rate quirk (learn_rate = norm_lr / 1024 for every utterance, :201) and log lines as
 // src/aslp-nnetbin/aslp-nnet-train-perutt.cc:30-300.  --frame-weights is not served (not on the BASELINE configs).
+#include <memory>
 #include <algorithm>
 #include "batch-feeder.h"
 #include "nnet-nnet.h"
@@ -55,7 +56,6 @@ int main(int argc, char* argv[]) {
     if (!crossvalidate) target_model_filename = po.GetArg(4);
     if (use_gpu == "no") KALDI_ERR << "--use-gpu=no: this build has no CPU path";
     if (gpu_id >= 0) ASLP_OK(aslp_set_device(gpu_id));
-    if (objective_function != "xent") KALDI_ERR << "Unknown objective function code : " << objective_function;
     if (frame_weights != "") KALDI_ERR << "--frame-weights is not supported by this build";
 
     Nnet nnet_transf;
@@ -67,7 +67,11 @@ int main(int argc, char* argv[]) {
     long long total_frames = 0, report_frames = 0;
     SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
     RandomAccessPosteriorReader targets_reader(targets_rspecifier);
-    Xent xent;
+    std::unique_ptr<LossItf> loss_holder;                  // LossItf* as in the reference's worker mains (xent | mse)
+    if (objective_function == "xent") loss_holder.reset(new Xent);
+    else if (objective_function == "mse") loss_holder.reset(new Mse);
+    else KALDI_ERR << "Unsupported objective function: " << objective_function;
+    LossItf& xent = *loss_holder;
     CuMatrix<BaseFloat> feats, feats_transf, nnet_out, obj_diff;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";

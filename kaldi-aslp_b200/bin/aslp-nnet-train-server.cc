@@ -56,6 +56,12 @@ int main(int argc, char* argv[]) {
     server->InitParam(params);
     KALDI_LOG << "Mpi cluster info total " << server->NumNodes() << " server rank " << server->Rank();
     server->Run();          // until every worker has finished
+    {                       // aslp-nnet-train-server.cc:93-97: the collective the worker mains enter after Stop()
+      std::vector<double*> acc_params;
+      std::vector<std::pair<double*, int>> data_params;
+      nnet.GetAccStats(&acc_params, &data_params);
+      server->ReduceAccStat(acc_params, data_params);
+    }
     nnet.Write(target_model_filename, binary);
     return 0;
   } catch (const std::exception& e) {

@@ -14,6 +14,7 @@
 #include "nnet-trnopts.h"
 #include "parallel-async.h"
 #include "parse-options.h"
+#include "worker-opts.h"
 #include "table.h"
 
 namespace kaldi {
@@ -196,14 +197,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
       if (last) break;
     }
     feeder.Join();
-    if (worker) {
-      // last partial period, then zero-frame syncs until every rank is out of data (termination protocol)
-      if (!worker->IsAsync()) {
-        if (num_frames_since_sync > 0) worker->Synchronize(num_frames_since_sync);
-        while (worker->Synchronize(0)) {}
-      }
-      worker->Stop();         // async modes: kMsgFinished to the server, which writes the model
-    }
+    if (worker) FinishWorker(worker.get(), &net);        // Stop(), then the BatchNorm statistics of all ranks (worker-opts.h)
     if (!crossvalidate) KALDI_LOG << net.InfoGradient();
     if (!crossvalidate && (!worker || worker->IsMainNode())) net.Write(target_model_filename, binary);
     KALDI_LOG << "Done " << num_done << " files, " << num_no_tgt_mat << " with no targets, " << num_other_error << " with other errors. "

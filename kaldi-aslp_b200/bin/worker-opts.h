@@ -13,6 +13,19 @@
 
 namespace kaldi {
 
+// End of a rank's data, as in the reference worker mains (aslp-nnet-train-frame-worker.cc:171-178): Stop() -- synchronous workers
+// answer zero-frame syncs until every rank is out of data (bsp-worker.cc:60-65; frames trained since the last sync are NOT
+// flushed first, as in the reference), asynchronous ones tell the server they are finished -- then the BatchNorm frame counters and
+// fp64 running sums are all-reduced on EVERY rank (the server main joins the same collective), so that the model rank 0 writes
+// carries the statistics of all shards.
+inline void FinishWorker(IWorker* worker, aslp_nnet::Nnet* nnet) {
+  worker->Stop();
+  std::vector<double*> acc_params;
+  std::vector<std::pair<double*, int>> data_params;
+  nnet->GetAccStats(&acc_params, &data_params);
+  worker->ReduceAccStat(acc_params, data_params);
+}
+
 struct WorkerOptions {
   std::string worker_type;
   float alpha, bmuf_momentum, bmuf_learn_rate;
@@ -20,6 +33,7 @@ struct WorkerOptions {
   OptimizerOption optimizer_opts;
   std::unique_ptr<IWorker> worker;
   int32 frames_since_sync;
+  aslp_nnet::Nnet* nnet_ = nullptr;
   WorkerOptions() : alpha(0.5f), bmuf_momentum(0.9f), bmuf_learn_rate(1.0f), sync_period(25600), frames_since_sync(0) {}
   void Register(ParseOptions* po) {
     po->Register("worker-type", &worker_type, "Worker type(bsp | bmuf | sod | easgd | asgd); empty: single process");
@@ -36,6 +50,7 @@ struct WorkerOptions {
   }
   void Create(aslp_nnet::Nnet* nnet, bool crossvalidate) {
     if (worker_type.empty() || crossvalidate) return;
+    nnet_ = nnet;
     WorkerBootstrap boot;
     if (worker_type == "bsp") worker.reset(new BspWorker(boot.id, boot.nranks, boot.rank));
     else if (worker_type == "bmuf") worker.reset(new BmufWorker(boot.id, boot.nranks, boot.rank, bmuf_momentum, bmuf_learn_rate));
@@ -57,16 +72,7 @@ struct WorkerOptions {
       frames_since_sync = 0;
     }
   }
-  // end of data: synchronous workers flush their last frames and answer zero-frame syncs until every rank is done
-  // (bsp-worker.cc:60-65); asynchronous ones tell the server they are finished
-  void Finish() {
-    if (!worker) return;
-    if (!worker->IsAsync()) {
-      if (frames_since_sync > 0) worker->Synchronize(frames_since_sync);
-      while (worker->Synchronize(0)) {}
-    }
-    worker->Stop();
-  }
+  void Finish() { if (worker) FinishWorker(worker.get(), nnet_); }
   bool WritesModel() const { return !worker || worker->IsMainNode(); }
 };
 

@@ -86,6 +86,10 @@ int aslp_event_sync(void* event) {
   ASLP_CUDA(cudaEventSynchronize((cudaEvent_t)event));
   return 0;
 }
+int aslp_event_destroy(void* event) {
+  if (event != nullptr) ASLP_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
 int aslp_event_elapsed_ms(void* a, void* b, float* ms) {
   ASLP_CUDA(cudaEventSynchronize((cudaEvent_t)b));
   ASLP_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
@@ -118,4 +122,14 @@ void* aslp_scratch(cudaStream_t stream, size_t bytes) {
     b.bytes = cap;
   }
   return static_cast<char*>(b.ptr) + ASLP_SCRATCH_RESERVED;
+}
+
+// a helper thread's stream is going away (CuThreadDetach): drop its scratch arena
+extern "C" int aslp_scratch_release(aslp_stream_t s) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = g_scratch.find(std::make_pair(dev, (cudaStream_t)s));
+  if (it != g_scratch.end()) { if (it->second.ptr != nullptr) cudaFree(it->second.ptr); g_scratch.erase(it); }
+  return 0;
 }

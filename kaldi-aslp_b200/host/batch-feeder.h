@@ -38,7 +38,10 @@ class BatchFeeder {
       thread_ = std::thread([this] { Run(); });
     }
   }
-  ~BatchFeeder() { Join(); }
+  ~BatchFeeder() {
+    Join();
+    for (auto& s : slots_) if (s->copied != nullptr) { aslp_event_destroy(s->copied); s->copied = nullptr; }
+  }
   // stops the feeder thread (after the fill() it may be in); what fill() wrote through captured references -- e.g. the
   // skipped-utterance counters, which also count utterances skipped after the last delivered minibatch -- is then safe to read
   void Join() {
@@ -102,6 +105,7 @@ class BatchFeeder {
   void Run() {
     try {
       if (attach_) CuThreadAttach();
+      else if (track_) CuThreadUseDevice();      // pinned allocations and event waits of this thread belong to the process's GPU
       for (;;) {
         Slot* s = nullptr;
         {

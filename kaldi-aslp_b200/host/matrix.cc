@@ -34,9 +34,13 @@ void CuThreadAttach() {
   ASLP_OK(aslp_stream_create(&t_current));
   t_helper = true;
 }
+void CuThreadUseDevice() { if (g_stream_made) ASLP_OK(aslp_set_device(g_device)); }
+void CuWorkspaceRelease(aslp_stream_t st);
 void CuThreadDetach() {
   if (!t_helper) return;
   aslp_stream_sync(t_current);
+  CuWorkspaceRelease(t_current);                           // the stream handle is about to die: drop what was keyed by it
+  aslp_scratch_release(t_current);
   aslp_stream_destroy(t_current);
   t_current = nullptr;
   t_helper = false;
@@ -187,6 +191,43 @@ void Matrix<Real>::Read(std::istream& is, bool binary) {
   if (binary) {
     std::string tok;
     ReadToken(is, binary, &tok);
+    if (tok == "CM" || tok == "CM2") {
+      // CompressedMatrix (src/matrix/compressed-matrix.{h,cc}:128-143, 438-483, 486-530): what copy-feats --compress=true writes.
+      // Header after the token: min_value, range (float), num_rows, num_cols (int32).  CM: per column four uint16 percentiles,
+      // then one byte per element COLUMN by column, piecewise linear between the percentiles; CM2: uint16 per element, row-major.
+      struct { float min_value, range; int32 num_rows, num_cols; } h;
+      is.read(reinterpret_cast<char*>(&h), sizeof(h));
+      if (is.fail()) KALDI_ERR << "Failed to read header";
+      if (h.num_rows < 0 || h.num_cols < 0) KALDI_ERR << "Matrix::Read, negative dimension in a compressed matrix";
+      Resize(h.num_cols == 0 ? 0 : h.num_rows, h.num_cols, kUndefined);
+      if (h.num_cols == 0) return;
+      auto u16 = [&](uint16_t v) { return h.min_value + h.range * 1.52590218966964e-05F * v; };
+      if (tok == "CM") {
+        std::vector<uint16_t> pc(static_cast<size_t>(h.num_cols) * 4);
+        is.read(reinterpret_cast<char*>(pc.data()), pc.size() * 2);
+        std::vector<unsigned char> col(h.num_rows);
+        for (int32 j = 0; j < h.num_cols; ++j) {
+          const float p0 = u16(pc[4 * j]), p25 = u16(pc[4 * j + 1]), p75 = u16(pc[4 * j + 2]), p100 = u16(pc[4 * j + 3]);
+          is.read(reinterpret_cast<char*>(col.data()), h.num_rows);
+          for (int32 i = 0; i < h.num_rows; ++i) {
+            const unsigned char v = col[i];
+            float f;
+            if (v <= 64) f = p0 + (p25 - p0) * v * (1 / 64.0);
+            else if (v <= 192) f = p25 + (p75 - p25) * (v - 64) * (1 / 128.0);
+            else f = p75 + (p100 - p75) * (v - 192) * (1 / 63.0);
+            (*this)(i, j) = static_cast<Real>(f);
+          }
+        }
+      } else {
+        std::vector<uint16_t> row(h.num_cols);
+        for (int32 i = 0; i < h.num_rows; ++i) {
+          is.read(reinterpret_cast<char*>(row.data()), static_cast<size_t>(h.num_cols) * 2);
+          for (int32 j = 0; j < h.num_cols; ++j) (*this)(i, j) = static_cast<Real>(u16(row[j]));
+        }
+      }
+      if (is.fail()) KALDI_ERR << "Failed to read data.";
+      return;
+    }
     int32 rows = 0, cols = 0;
     ReadBasicType(is, binary, &rows);
     ReadBasicType(is, binary, &cols);
@@ -202,7 +243,7 @@ void Matrix<Real>::Read(std::istream& is, bool binary) {
       std::vector<double> tmp(n); is.read(reinterpret_cast<char*>(tmp.data()), 8 * n);
       for (size_t i = 0; i < n; ++i) d_[i] = static_cast<Real>(tmp[i]);
     } else {
-      KALDI_ERR << "Matrix::Read, expected token FM or DM, got " << tok << " (compressed matrices are not on this path)";
+      KALDI_ERR << "Matrix::Read, expected token FM, DM, CM or CM2, got " << tok;
     }
   } else {
     std::string s;
@@ -436,6 +477,11 @@ namespace {
 struct Ws { void* p = nullptr; size_t bytes = 0; };
 std::map<aslp_stream_t, Ws> g_ws;
 std::mutex g_ws_mu;
+}
+void CuWorkspaceRelease(aslp_stream_t st) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  auto it = g_ws.find(st);
+  if (it != g_ws.end()) { if (it->second.p != nullptr) aslp_free(it->second.p); g_ws.erase(it); }
 }
 void* CuWorkspace(size_t bytes) {
   const aslp_stream_t st = CuStream();

@@ -28,6 +28,9 @@ aslp_stream_t CuSideStream();
 // workspace) and CuSync() waits for it alone.  CuThreadDetach() drains and destroys the stream.
 void CuThreadAttach();
 void CuThreadDetach();
+// a helper thread that only touches page-locked memory and events (no stream of its own) still has per-thread device state: without
+// this call its runtime calls land on device 0 and create a context there on every rank.  No-op before the first device operation.
+void CuThreadUseDevice();
 bool CuAsyncEnabled();
 void CuFork();
 void CuJoin();

@@ -10,6 +10,9 @@ namespace kaldi {
 NcclNode::NcclNode(const char nccl_id[128], int nranks, int rank) : comm_(nullptr), rank_(rank), nranks_(nranks) {
   CuStream();      // device selected + stream before the communicator is created
   ASLP_OK(aslp_comm_init(&comm_, nccl_id, nranks, rank));
+  // ncclCommInitRank is collective: once it returns on rank 0 every rank has read the id, so the rendezvous file can go -- a later
+  // launch that reuses the path (the schedulers start one job per epoch) must never find this job's id
+  if (rank == 0) if (const char* file = std::getenv("ASLP_NCCL_ID_FILE")) std::remove(file);
 }
 NcclNode::~NcclNode() { if (comm_ != nullptr) aslp_comm_destroy(comm_); }
 void NcclNode::Barrier() { ASLP_OK(aslp_comm_barrier(comm_, CuStream())); }
@@ -137,18 +140,39 @@ WorkerBootstrap::WorkerBootstrap() : rank(0), nranks(1) {
   KALDI_ASSERT(nranks >= 1 && rank >= 0 && rank < nranks);
   const char* file = std::getenv("ASLP_NCCL_ID_FILE");
   if (nranks > 1 && file == nullptr) KALDI_ERR << "WORLD_SIZE > 1 needs ASLP_NCCL_ID_FILE (a path every rank can reach) to pass the NCCL id";
+  // A file left behind by an earlier launch (a job that died before its communicator was up) must not be taken for this one's:
+  // the file carries a job nonce after the id -- ASLP_JOB_NONCE, else torchrun's TORCHELASTIC_RUN_ID, else MASTER_ADDR:MASTER_PORT,
+  // which every rank of one launch shares -- and a rank keeps waiting while the nonce on disk is not its own.  Rank 0 removes the
+  // file before writing and again once the communicator is up (NcclNode).  Without any of those variables only the removals
+  // protect a reused path: give every launch its own path then.
+  char nonce[64];
+  std::memset(nonce, 0, sizeof(nonce));
+  {
+    std::string n;
+    if (const char* v = std::getenv("ASLP_JOB_NONCE")) n = v;
+    else if (const char* v = std::getenv("TORCHELASTIC_RUN_ID")) n = v;
+    else if (const char* v = std::getenv("MASTER_PORT")) { const char* a = std::getenv("MASTER_ADDR"); n = std::string(a ? a : "") + ":" + v; }
+    std::strncpy(nonce, n.c_str(), sizeof(nonce) - 1);
+  }
   if (rank == 0) {
     ASLP_OK(aslp_comm_unique_id(id));
     if (file != nullptr) {
+      std::remove(file);
       const std::string tmp = std::string(file) + ".tmp";
-      { std::ofstream os(tmp, std::ios::binary); os.write(id, sizeof(id)); if (!os.good()) KALDI_ERR << "Cannot write " << tmp; }
+      { std::ofstream os(tmp, std::ios::binary); os.write(id, sizeof(id)); os.write(nonce, sizeof(nonce)); if (!os.good()) KALDI_ERR << "Cannot write " << tmp; }
       if (std::rename(tmp.c_str(), file) != 0) KALDI_ERR << "Cannot publish " << file;
     }
   } else {
     for (int tries = 0;; ++tries) {
       std::ifstream is(file, std::ios::binary);
-      if (is.good()) { is.read(id, sizeof(id)); if (is.gcount() == static_cast<std::streamsize>(sizeof(id))) break; }
-      if (tries > 1200) KALDI_ERR << "Timed out waiting for " << file;
+      if (is.good()) {
+        char got[64];
+        is.read(id, sizeof(id));
+        const bool have_id = is.gcount() == static_cast<std::streamsize>(sizeof(id));
+        is.read(got, sizeof(got));
+        if (have_id && is.gcount() == static_cast<std::streamsize>(sizeof(got)) && std::memcmp(got, nonce, sizeof(nonce)) == 0) break;
+      }
+      if (tries > 1200) KALDI_ERR << "Timed out waiting for " << file << " (a file with another launch's nonce does not count)";
       std::this_thread::sleep_for(std::chrono::milliseconds(100));
     }
   }

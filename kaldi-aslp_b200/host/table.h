@@ -3,10 +3,14 @@
 //   RandomAccessPosteriorReader       Posterior archives  (src/hmm/posterior.cc:29-99 on-disk format)
 //   RandomAccessInt32VectorReader     std::vector<int32> archives (CTC label sequences)
 //   BaseFloatMatrixWriter             "ark:file", "ark,t:file"
-// Option letters after the type ("ark,s,cs:") are accepted and ignored; piped commands ("cmd |") and "-" are not
-// supported here (the recipes' feature pipes run upstream of the trainers).
+// Option letters after the type ("ark,s,cs:") are accepted and ignored.  Sources and sinks are Kaldi's extended file names
+// (src/util/kaldi-io.h:60-93): a path, "-" (standard input / output), "cmd |" (read from a command, e.g. the recipes'
+// "ark:copy-feats scp:... ark:- | apply-cmvn ... |") and "| cmd" (write into one); scp entries may be pipes too.
+// Compressed feature matrices (CM / CM2, the default of copy-feats --compress) are decoded by Matrix::Read.
 #ifndef ASLP_HOST_TABLE_H_
 #define ASLP_HOST_TABLE_H_
+#include <cstdio>
+#include <ext/stdio_filebuf.h>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -31,9 +35,81 @@ inline TableSpec ParseSpecifier(const std::string& spec) {
     else if (o == "t") t.text = true;
   }
   if (!have_type) KALDI_ERR << "Invalid table specifier " << spec << " (expected ark: or scp:)";
-  if (t.file.empty() || t.file == "-" || t.file.back() == '|') KALDI_ERR << "Unsupported table source '" << t.file << "' (files only)";
+  while (!t.file.empty() && (t.file.back() == ' ' || t.file.back() == '\t')) t.file.pop_back();
+  if (t.file.empty()) KALDI_ERR << "Invalid table specifier " << spec << " (empty file name)";
   return t;
 }
+
+// rxfilename: path | "-" | "command |"   (Input, src/util/kaldi-io.cc)
+class InputStream {
+ public:
+  explicit InputStream(const std::string& rx) : pipe_(nullptr), is_(nullptr), name_(rx) {
+    if (rx == "-") { is_ = &std::cin; return; }
+    if (!rx.empty() && rx.back() == '|') {
+      const std::string cmd = rx.substr(0, rx.size() - 1);
+      pipe_ = popen(cmd.c_str(), "r");
+      if (pipe_ == nullptr) KALDI_ERR << "Failed opening pipe for reading, command is: " << cmd;
+      buf_.reset(new __gnu_cxx::stdio_filebuf<char>(pipe_, std::ios::in | std::ios::binary));
+      pis_.reset(new std::istream(buf_.get()));
+      is_ = pis_.get();
+      return;
+    }
+    file_.open(rx, std::ios::in | std::ios::binary);
+    if (!file_.is_open()) KALDI_ERR << "Cannot open " << rx;
+    is_ = &file_;
+  }
+  ~InputStream() {
+    pis_.reset();
+    buf_.reset();
+    if (pipe_ != nullptr) { const int rc = pclose(pipe_); if (rc != 0) KALDI_WARN << "Pipe " << name_ << " had nonzero return status " << rc; }
+  }
+  InputStream(const InputStream&) = delete;
+  InputStream& operator=(const InputStream&) = delete;
+  std::istream& Stream() { return *is_; }
+  bool IsFile() const { return is_ == &file_; }
+ private:
+  std::ifstream file_;
+  FILE* pipe_;
+  std::unique_ptr<__gnu_cxx::stdio_filebuf<char>> buf_;
+  std::unique_ptr<std::istream> pis_;
+  std::istream* is_;
+  std::string name_;
+};
+// wxfilename: path | "-" | "| command"   (Output)
+class OutputStream {
+ public:
+  explicit OutputStream(const std::string& wx) : pipe_(nullptr), os_(nullptr), name_(wx) {
+    if (wx == "-") { os_ = &std::cout; return; }
+    if (!wx.empty() && wx[0] == '|') {
+      const std::string cmd = wx.substr(1);
+      pipe_ = popen(cmd.c_str(), "w");
+      if (pipe_ == nullptr) KALDI_ERR << "Failed opening pipe for writing, command is: " << cmd;
+      buf_.reset(new __gnu_cxx::stdio_filebuf<char>(pipe_, std::ios::out | std::ios::binary));
+      pos_.reset(new std::ostream(buf_.get()));
+      os_ = pos_.get();
+      return;
+    }
+    file_.open(wx, std::ios::out | std::ios::binary);
+    if (!file_.is_open()) KALDI_ERR << "Cannot open " << wx << " for writing";
+    os_ = &file_;
+  }
+  ~OutputStream() {
+    if (os_ != nullptr) os_->flush();
+    pos_.reset();
+    buf_.reset();
+    if (pipe_ != nullptr) pclose(pipe_);
+  }
+  OutputStream(const OutputStream&) = delete;
+  OutputStream& operator=(const OutputStream&) = delete;
+  std::ostream& Stream() { return *os_; }
+ private:
+  std::ofstream file_;
+  FILE* pipe_;
+  std::unique_ptr<__gnu_cxx::stdio_filebuf<char>> buf_;
+  std::unique_ptr<std::ostream> pos_;
+  std::ostream* os_;
+  std::string name_;
+};
 
 // reads the next whitespace-terminated key of an archive; false at end of file
 inline bool ReadArchiveKey(std::istream& is, std::string* key) {
@@ -109,9 +185,7 @@ template <class Holder>
 class SequentialTableReader {
  public:
   typedef typename Holder::T T;
-  explicit SequentialTableReader(const std::string& rspecifier) : spec_(ParseSpecifier(rspecifier)), done_(false) {
-    main_.open(spec_.file, std::ios::in | std::ios::binary);
-    if (!main_.is_open()) KALDI_ERR << "Cannot open " << spec_.file;
+  explicit SequentialTableReader(const std::string& rspecifier) : spec_(ParseSpecifier(rspecifier)), in_(spec_.file), main_(in_.Stream()), done_(false) {
     Next();
   }
   bool Done() const { return done_; }
@@ -125,29 +199,32 @@ class SequentialTableReader {
     }
     std::string line;
     while (std::getline(main_, line)) {
-      std::vector<std::string> f;
-      SplitStringToVector(line, " \t\r", true, &f);
-      if (f.empty()) continue;
-      if (f.size() != 2) KALDI_ERR << "Invalid scp line: " << line;
-      key_ = f[0];
-      std::string path = f[1];
+      // "key rxfilename": the rxfilename is the rest of the line (it contains spaces when it is a command)
+      const size_t k0 = line.find_first_not_of(" \t\r");
+      if (k0 == std::string::npos) continue;
+      const size_t k1 = line.find_first_of(" \t", k0);
+      if (k1 == std::string::npos) KALDI_ERR << "Invalid scp line: " << line;
+      key_ = line.substr(k0, k1 - k0);
+      size_t p0 = line.find_first_not_of(" \t", k1), p1 = line.find_last_not_of(" \t\r");
+      if (p0 == std::string::npos) KALDI_ERR << "Invalid scp line: " << line;
+      std::string path = line.substr(p0, p1 - p0 + 1);
       long long off = -1;
       const size_t c = path.rfind(':');
       if (c != std::string::npos && c + 1 < path.size() && path.find_first_not_of("0123456789", c + 1) == std::string::npos) {
         off = std::atoll(path.c_str() + c + 1);
         path = path.substr(0, c);
       }
-      std::ifstream obj(path, std::ios::in | std::ios::binary);
-      if (!obj.is_open()) KALDI_ERR << "Cannot open " << path << " (scp entry " << key_ << ")";
-      if (off >= 0) obj.seekg(off);
-      Holder::Read(obj, &value_);
+      InputStream obj(path);                    // a path, or "command |" (then the line's second field runs to the end of the line)
+      if (off >= 0) obj.Stream().seekg(off);
+      Holder::Read(obj.Stream(), &value_);
       return;
     }
     done_ = true;
   }
  private:
   TableSpec spec_;
-  std::ifstream main_;
+  InputStream in_;
+  std::istream& main_;
   bool done_;
   std::string key_;
   T value_;
@@ -179,17 +256,17 @@ class BaseFloatMatrixWriter {
  public:
   explicit BaseFloatMatrixWriter(const std::string& wspecifier) : spec_(ParseSpecifier(wspecifier)) {
     if (spec_.scp) KALDI_ERR << "scp output is not supported: " << wspecifier;
-    os_.open(spec_.file, std::ios::out | std::ios::binary);
-    if (!os_.is_open()) KALDI_ERR << "Cannot open " << spec_.file << " for writing";
+    out_.reset(new OutputStream(spec_.file));
   }
   void Write(const std::string& key, const Matrix<BaseFloat>& m) {
+    std::ostream& os_ = out_->Stream();
     os_ << key << ' ';
     if (!spec_.text) { os_.put('\0'); os_.put('B'); }
     m.Write(os_, !spec_.text);
   }
  private:
   TableSpec spec_;
-  std::ofstream os_;
+  std::unique_ptr<OutputStream> out_;
 };
 
 }  // namespace kaldi

@@ -70,6 +70,18 @@ def frame_case():
     open(os.path.join(d, "args.txt"), "w").write("--minibatch-size=32 --randomizer-size=200 --randomizer-seed=777 --learn-rate=0.02 --momentum=0.9 --l2-penalty=0.0001\n")
 
 
+def frame_mse_case():
+    """--objective-function=mse on the cli_frame inputs (Mse through the LossItf pointer of the trainer, nnet-loss.cc:205-290)"""
+    src = os.path.join(GOLD, "cli_frame")
+    d = os.path.join(GOLD, "cli_frame_mse")
+    os.makedirs(d, exist_ok=True)
+    flags = "--objective-function=mse --minibatch-size=32 --randomizer-size=200 --randomizer-seed=777 --learn-rate=0.05 --momentum=0.9"
+    args = ["--use-gpu=no"] + flags.split() + ["ark:" + os.path.join(src, "feats.ark"), "ark:" + os.path.join(src, "post.ark"),
+                                                os.path.join(src, "init.nnet"), os.path.join(d, "ref_out.nnet")]
+    run([os.path.join(REF, "aslp-nnet-train-frame")] + args, os.path.join(d, "ref_train.log"))
+    open(os.path.join(d, "args.txt"), "w").write(flags + "\n")
+
+
 def ctc_case():
     d = os.path.join(GOLD, "cli_ctc")
     os.makedirs(d, exist_ok=True)
@@ -218,7 +230,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "forward":
         forward_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "frame_mse":
+        frame_mse_case()
+        sys.exit(0)
     frame_case()
+    frame_mse_case()
     ctc_case()
     lc_case()
     lstm_case()

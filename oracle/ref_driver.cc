@@ -6,6 +6,7 @@
 //   ref_driver init  <proto> <model-out> <seed> <binary 0|1>
 //   ref_driver step  <model-in> <spec-file> <out-dir>
 //   ref_driver bench <model-in> <spec-file>            (times `iters` training minibatches, prints one JSON line)
+//   ref_driver compress <matrix-in> <archive-out> <key> <1|2>   (the reference's CompressedMatrix writer, format CM or CM2: fixtures for the I/O tests)
 //
 // spec-file: one `key value` per line
 //   input <kaldi matrix file>          features [rows, dim], stream-interleaved for recurrent nets
@@ -46,6 +47,7 @@
 #include "aslp-nnet/nnet-loss.h"
 #include "aslp-nnet/warp-ctc.h"
 #include "base/timer.h"
+#include "matrix/compressed-matrix.h"
 
 using namespace kaldi;
 using namespace kaldi::aslp_nnet;
@@ -88,6 +90,24 @@ int main(int argc, char** argv) {
       Nnet nnet;
       nnet.Init(argv[2]);
       nnet.Write(argv[3], atoi(argv[5]) != 0);
+      return 0;
+    }
+    if (cmd == "compress") {
+      if (argc != 6) { std::cerr << "ref_driver compress <matrix-in> <archive-out> <key> <1|2>\n"; return 1; }
+      Matrix<BaseFloat> m;
+      ReadMat(argv[2], &m);
+      CompressedMatrix cm;
+      if (atoi(argv[5]) == 2) {                 // format 2 has no public selector in this version: it is what a matrix with fewer than 8 rows gets
+        KALDI_ASSERT(m.NumRows() < 8);
+      }
+      cm.CopyFromMat(m);
+      Output ko(argv[3], true, false);          // binary, no header: an archive entry "key \0B<matrix>"
+      ko.Stream() << argv[4] << ' ';
+      ko.Stream().put('\0'); ko.Stream().put('B');
+      cm.Write(ko.Stream(), true);
+      Matrix<BaseFloat> back(cm.NumRows(), cm.NumCols());
+      cm.CopyToMat(&back);
+      WriteMat(std::string(argv[3]) + ".decoded", back);
       return 0;
     }
     if (cmd != "step" && cmd != "bench") { std::cerr << "unknown command " << cmd << "\n"; return 1; }
