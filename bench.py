@@ -121,14 +121,18 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference(args, rank, world, threads=None):
-    """The reference's own CPU implementation of the path on the host cores (oracle/_ref)."""
+def run_reference(args, rank, world, threads=None, t_sample=T):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref): the unmodified Nnet / WarpCtc classes,
+    one step = the same 16 x t_sample-frame minibatch as our arm (t_sample = T = 1000 for the --impl reference line, so that both
+    arms take the same branch of the reference's 3000-cost loss guard; the in-line cpu_baseline of our arm uses a shorter sample)."""
     if rank != 0:
         return None
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     cores = threads or os.cpu_count() or 1
-    t_sample = 200                                  # frames per utterance in one reference step (bounded sample: 1/5 of T)
     cfg = workload_config(args.gpus)
+    cfg["reference_frames_per_utterance"] = t_sample
+    if args.gpus > 1:
+        cfg["reference_note"] = "ONE CPU process on rank 0's host cores whatever N is (the reference's CPU path does not shard): only the N = 1 ratio compares like with like"
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg}
     if not os.path.exists(drv):
@@ -147,36 +151,40 @@ def run_reference(args, rank, world, threads=None):
         with open(os.path.join(td, "spec.txt"), "w") as f:
             f.write("input input.mat\nloss ctc\nlabels labels.txt\nseq_lengths %s\nmomentum %g\nnorm_learn_rate %g\niters %d\nwarmup %d\n"
                     % (",".join([str(t_sample)] * S), MOMENTUM, NORM_LR * t_sample / T, args.steps + args.warmup, args.warmup))
-        out = subprocess.check_output([drv, "bench", "model.bin", "spec.txt"], cwd=td, env=env, stderr=subprocess.DEVNULL)
-    r = json.loads(out.decode().strip().splitlines()[-1])
+        pr = subprocess.run([drv, "bench", "model.bin", "spec.txt"], cwd=td, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    r = json.loads(pr.stdout.decode().strip().splitlines()[-1])
     fps = r["frames_per_sec"]
-    sample = "%d steps of 16 utts x %d frames (1/%d of the minibatch length), OpenBLAS threads=%d" % (args.steps, t_sample, T // t_sample, cores)
+    rejected = pr.stderr.decode(errors="replace").count("obj is abnormal")
+    sample = "%d timed steps of 16 utts x %d frames%s, OpenBLAS threads=%d" % (
+        args.steps, t_sample, "" if t_sample == T else " (1/%d of the minibatch length)" % (T // t_sample), cores)
     line.update({"value": fps, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps),
+                 "guard_rejected_utts": rejected,
                  "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
                  "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     return line
 
 
 def cpu_baseline_leg():
-    """Bounded CPU sample for our arm's JSON line (rank 0, N=1): one warm-up + one timed reference step at T=50."""
+    """Bounded CPU sample for our arm's JSON line (rank 0, N = 1): 1 warm-up + 5 timed reference steps of 16 utts x 200 frames with all
+    host threads (about 10 s), and 2 steps single-threaded (SURVEY 8d asks for both)."""
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     cores = os.cpu_count() or 1
     if not os.path.exists(drv):
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "unavailable: oracle/_ref not built"}
 
     class A:
-        gpus, steps, warmup = 1, 2, 1
-    r = run_reference(A, 0, 1)
+        gpus, steps, warmup = 1, 5, 1
+    r = run_reference(A, 0, 1, t_sample=200)
     cb = r["cpu_baseline"]
-    # SURVEY 8(d): also with OPENBLAS_NUM_THREADS=1 (the reference's pointwise code and its warp-ctc call are single-threaded anyway)
+
     class B:
-        gpus, steps, warmup = 1, 1, 1
+        gpus, steps, warmup = 1, 2, 1
     try:
-        cb["single_thread"] = {"value": run_reference(B, 0, 1, threads=1)["cpu_baseline"]["value"], "unit": UNIT, "cores": 1}
+        cb["single_thread"] = {"value": run_reference(B, 0, 1, threads=1, t_sample=200)["cpu_baseline"]["value"], "unit": UNIT, "cores": 1,
+                               "sample": "2 timed steps of 16 utts x 200 frames"}
     except Exception as e:  # the baseline is a reported figure: never fail the bench line over it
         cb["single_thread"] = {"value": None, "error": str(e)[:200]}
     return cb
-
 
 
 def secondary_metrics(lib, torch):
@@ -229,6 +237,95 @@ def secondary_metrics(lib, torch):
             "useful_TFLOPs": tf, "ms": ms, "tensor_pipe_frac": issued / (tf_peak / 2.0) if tf_peak else None,
             "peak": "TF32 dense = sustained bf16 / 2 = %.0f TFLOP/s; 3xTF32 issues 3 MMAs per useful one" % (tf_peak / 2.0)}
     return out
+
+
+def multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, host_lib, bmuf_worker):
+    """N > 1 numerics in front of the driver (the 2-GPU pytest cases are skipped on a 1-GPU box): after the timed region replay
+    real parameter synchronisations on the N ranks and compare what they leave in the replicas with the reference's formulas,
+    restated here from src/aslp-parallel/bsp-worker.cc:33-58 and bmuf-worker.cc:37-68:
+        BSP :  w <- SUM_r (frames_r / SUM_r frames_r) * w_r
+        BMUF:  G = SUM_r (w_r - w_prev);  d = m * d_prev + (1 - m) * lr * G;  w <- w_prev + d;  w_prev <- w;  d_prev <- d
+    Every rank trains one minibatch of its own shard between syncs, so the w_r really differ.  Also a BSP-every-minibatch timing
+    line (the synchronous gradient-level reading of north_star's "BSP allreduce")."""
+    import zlib
+
+    def new_worker(kind, **kw):
+        ids = [NN.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        w = NN.Worker(kind, ids[0], world, rank, **kw)
+        w.init_param(net)
+        return w
+
+    def gather(vec):
+        t = torch.from_numpy(np.ascontiguousarray(vec))
+        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, out, dst=0)
+        return [o.numpy().astype(np.float64) for o in out] if rank == 0 else None
+
+    def identical():
+        crc = torch.tensor([zlib.crc32(net.get_params().tobytes())], dtype=torch.int64)
+        allc = [torch.zeros_like(crc) for _ in range(world)]
+        dist.all_gather(allc, crc)
+        return len({int(c.item()) for c in allc}) == 1
+
+    def rel(got, want):
+        return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
+
+    res = {"ranks": world}
+    bmuf_worker.synchronize(S * T)                         # bring the replicas together first
+    res["replicas_bit_identical_after_bmuf"] = identical()
+    # ---- BSP with unequal frame counts
+    bsp = new_worker("bsp")
+    step_plain()
+    w_r = gather(net.get_params())
+    frames_r = 1000 * (rank + 1)
+    bsp.synchronize(frames_r)
+    got = net.get_params().astype(np.float64)
+    res["replicas_bit_identical_after_bsp"] = identical()
+    if rank == 0:
+        tot = sum(1000 * (r + 1) for r in range(world))
+        want = sum((np.float32(1000 * (r + 1)) / np.float32(tot)).astype(np.float64) * w_r[r] for r in range(world))
+        res["bsp_max_rel_err_vs_formula"] = rel(got, want)
+    # ---- BMUF, two rounds (the second one exercises the block momentum)
+    m, lr = 1.0 - 1.0 / world, 1.0
+    bm = new_worker("bmuf", bmuf_momentum=m, bmuf_learn_rate=lr)
+    w_prev = net.get_params().astype(np.float64)
+    d_prev = np.zeros_like(w_prev)
+    errs = []
+    for _ in range(2):
+        step_plain()
+        w_r = gather(net.get_params())
+        bm.synchronize(S * T)
+        got = net.get_params().astype(np.float64)
+        if rank == 0:
+            G = sum(w - w_prev for w in w_r)
+            d = m * d_prev + (1.0 - m) * lr * G
+            want = w_prev + d
+            errs.append(rel(got - w_prev, want - w_prev))     # on the UPDATE, not on the weights it is added to
+            d_prev = d
+        w_prev = got
+    res["replicas_bit_identical_after_bmuf_rounds"] = identical()
+    if rank == 0:
+        res["bmuf_max_rel_err_of_update_vs_formula"] = max(errs)
+        res["max_rel_err_vs_formula"] = max(res["bsp_max_rel_err_vs_formula"], max(errs))
+    res["replicas_bit_identical"] = bool(res["replicas_bit_identical_after_bmuf"] and res["replicas_bit_identical_after_bsp"] and res["replicas_bit_identical_after_bmuf_rounds"])
+    # ---- BSP after EVERY minibatch, timed like the main loop
+    NN.device_sync(); dist.barrier()
+    for _ in range(2):
+        step_plain(); bsp.synchronize(S * T)
+    NN.device_sync(); dist.barrier()
+    host_lib().aslp_nnet_event_record(0)
+    for _ in range(args.steps):
+        step_plain(); bsp.synchronize(S * T)
+    host_lib().aslp_nnet_event_record(1)
+    ms = ctypes.c_float(0)
+    assert host_lib().aslp_nnet_event_elapsed_ms(0, 1, ctypes.byref(ms)) == 0
+    NN.device_sync()
+    t = torch.tensor([ms.value], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    bsp_line = {"ms_per_step": float(t.item()) / args.steps, "frames_per_s": S * T * args.steps * world / (float(t.item()) * 1e-3),
+                "what": "BspWorker::Synchronize after every minibatch (one ncclAllReduce of the 26 MB arena per 16000 frames per rank)"}
+    return res, bsp_line
 
 
 def main():
@@ -299,6 +396,9 @@ def main():
             state["since_sync"] = 0
         return costs
 
+    def step_plain():
+        return NN.train_step_ctc(net, ctc, dev_ptr, lens, None, norm_learn_rate=NORM_LR, on_device=True, rows=T * S, cols=D, flat=flat)
+
     def barrier():
         NN.device_sync()
         if world > 1:
@@ -354,6 +454,9 @@ def main():
         sync_info = {"ms_per_sync": float(t.item()), "params": int(nparams),
                      "bus_GBps": 2.0 * (world - 1) / world * 4.0 * nparams / (float(t.item()) * 1e-3) / 1e9,
                      "what": "pack + ONE ncclAllReduce(sum) of the fp32 arena + BMUF filter apply; bus bytes = 2(N-1)/N * 4P (SURVEY 8d)"}
+    sync_check, bsp_line = None, None
+    if worker is not None:
+        sync_check, bsp_line = multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, host_lib, worker)
     secondary = secondary_metrics(lib, torch) if (rank == 0 and world == 1 and not args.no_secondary) else None
     if secondary is not None and args.precision == "3xtf32":
         # the same step with single-pass TF32 chunk GEMMs (north_star's "stated looser bound" mode, parity bound 5e-3 in
@@ -408,6 +511,11 @@ def main():
             line["secondary"] = secondary
         if sync_info is not None:
             line["sync"] = sync_info
+        if sync_check is not None:
+            line["sync_check"] = sync_check
+        if bsp_line is not None:
+            line["bsp_every_minibatch"] = bsp_line
+        line["guard_rejected_utts"] = NN.warpctc_rejected(ctc)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)

@@ -71,11 +71,16 @@ int aslp_event_sync(void* event);                           /* the host waits fo
  * then, if clip > 0, C = min(max(C, -clip), clip)  (ApplyFloor/ApplyCeiling on *_corr_,
  * src/aslp-nnet/nnet-blstm-projected-streams-lc.h:1002-1017 fused into the epilogue).
  * trans_a: A is stored [K,M]; trans_b: B is stored [N,K] (Kaldi kTrans).
- * precision: ASLP_GEMM_3XTF32 = fp32-grade split-TF32 (3 tcgen05 MMAs per k-step),
+ * precision: ASLP_GEMM_3XTF32 = fp32-grade (default): chunk-sized products run as ASLP_GEMM_F16X3, smaller ones split tf32 hi / lo in the main loop
+ *                               (3 tcgen05 MMAs per k-step either way),
+ *            ASLP_GEMM_F16X3  = fp32-grade: operands split once into fp16 hi / lo planes (row-wise power-of-two scaling), 3 kind::f16 passes,
  *            ASLP_GEMM_TF32   = single-pass TF32 (looser bound),
  *            ASLP_GEMM_FP32   = CUDA-core fp32 FMA (exact-order-free fp32; small/odd shapes).
  * workspace: used only for split-K; aslp_gemm_workspace_bytes() gives the size (may be 0). */
-enum { ASLP_GEMM_3XTF32 = 0, ASLP_GEMM_TF32 = 1, ASLP_GEMM_FP32 = 2 };
+enum { ASLP_GEMM_3XTF32 = 0, ASLP_GEMM_TF32 = 1, ASLP_GEMM_FP32 = 2, ASLP_GEMM_F16X3 = 3 };
+/* caps the persistent grid of the tensor-core GEMMs launched by the CALLING THREAD (0 = one CTA per SM): weight-gradient products
+ * issued on a side stream leave SMs free for the persistent recurrence kernel they are meant to overlap with */
+int aslp_gemm_set_cta_limit(int max_ctas);
 size_t aslp_gemm_workspace_bytes(int M, int N, int K);
 int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
               float alpha, const float* A, int lda, const float* B, int ldb,

@@ -63,6 +63,7 @@ int aslp_xent_report(aslp_xent_t x, char* buf, size_t buf_bytes, double stats5[5
 int aslp_warpctc_create(aslp_warpctc_t* out);
 int aslp_warpctc_destroy(aslp_warpctc_t c);
 int aslp_warpctc_report(aslp_warpctc_t c, char* buf, size_t buf_bytes);
+int aslp_warpctc_rejected(aslp_warpctc_t c, int* n);   /* utterances rejected so far by the loss guard (StatAndAverageLossCheck, warp-ctc.cc:288-365) */
 
 /* ---- one training minibatch, the loop body of the reference trainers ----
  * frame CE (aslp-nnet-train-frame.cc:110-124, -lstm-streams, -blstm-streams-lc):

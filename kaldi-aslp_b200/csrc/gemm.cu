@@ -19,6 +19,10 @@
 #include <stdlib.h>
 #include "scratch.cuh"
 
+// persistent-grid cap of the calling thread (aslp_gemm_set_cta_limit): work issued on a side stream leaves SMs to a concurrently
+// running persistent kernel instead of taking one CTA per SM
+static thread_local int t_cta_limit = 0;
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;           // BK floats = 128 B = one swizzle row
@@ -27,6 +31,15 @@ constexpr uint32_t SPIN_LIMIT = 1u << 18;
 constexpr int STG_PITCH = 36;                        // epilogue staging tile pitch (floats)
 constexpr int BAR_REGION = 256;                      // mbarriers + the TMEM slot, after the stage buffers
 constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;    // one 32 x 32 chunk per epilogue warp
+#ifndef ASLP_SPLIT_WARPS
+#define ASLP_SPLIT_WARPS 4                           // hi/lo splitter warps of the 3xTF32 kernel
+#endif
+#ifndef ASLP_SPLIT_UNROLL
+#define ASLP_SPLIT_UNROLL 4                          // float4 loads a splitter thread keeps in flight
+#endif
+constexpr int SPLIT_THREADS = 32 * ASLP_SPLIT_WARPS;
+constexpr int SPLIT_UNROLL = ASLP_SPLIT_UNROLL;
+constexpr int NT3 = 192 + SPLIT_THREADS;             // threads of the 3-pass kernel
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -56,6 +69,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// one lane of a CONVERGED warp; unlike `if (lane == 0)` the compiler knows the branch is taken by a single thread and emits the
+// uniform-datapath instructions (UTCHMMA, UTMALDG) back to back instead of wrapping each in an ELECT / BRA.U.ANY loop -- measured
+// 19 vs 46 cycles per tcgen05.mma issued (profiles/r02_umma_dsmem_probe.txt)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -111,7 +132,7 @@ struct EpiParams {
 
 // ------------------------------------------------------------------ the kernel
 template <bool A_MN, bool B_MN, int PASSES>
-__global__ void __launch_bounds__(PASSES == 1 ? 192 : 320, 1)
+__global__ void __launch_bounds__(PASSES == 1 ? 192 : NT3, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p) {
   constexpr int STAGES = (PASSES == 1) ? 6 : 3;
   constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
@@ -148,7 +169,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), 128);
+      mbar_init(split_bar(s), SPLIT_THREADS);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,8 +185,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (the warp stays converged; one elected lane issues) =====================
+    {
       int s = 0; uint32_t ph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int z, m0, n0, kb_begin, kb_end;
@@ -174,26 +195,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + TILE_BYTES;
-          mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
-          if (!A_MN) {
-            tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);              // box {32 k, 128 rows}
-          } else {
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);              // box {32 k, 128 rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, full_bar(s), m0 + 32 * j, kb * BK);  // box {32 m, 32 k}
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmB, full_bar(s), kb * BK, n0);
-          } else {
+              for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, full_bar(s), m0 + 32 * j, kb * BK);  // box {32 m, 32 k}
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tmB, full_bar(s), kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, full_bar(s), n0 + 32 * j, kb * BK);
+              for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, full_bar(s), n0 + 32 * j, kb * BK);
+            }
           }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the warp stays converged; one elected lane issues) =====================
+    {
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=F32, a=b=TF32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -217,25 +241,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t da = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t db = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
-            const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
-            if (PASSES == 1) {
-              tc_mma_tf32(tmem_d, da, db, idesc, acc);
-            } else {
-              const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, a_sbo, a_lay);
-              const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, b_sbo, b_lay);
-              tc_mma_tf32(tmem_d, da_lo, db, idesc, acc);     // small terms first
-              tc_mma_tf32(tmem_d, da, db_lo, idesc, 1u);
-              tc_mma_tf32(tmem_d, da, db, idesc, 1u);
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t da = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
+              const uint64_t db = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
+              const uint32_t acc = (kb > kb_begin || k > 0) ? 1u : 0u;
+              if (PASSES == 1) {
+                tc_mma_tf32(tmem_d, da, db, idesc, acc);
+              } else {
+                const uint64_t da_lo = make_desc(sa + 2 * TILE_BYTES + k * a_step, a_lbo, a_sbo, a_lay);
+                const uint64_t db_lo = make_desc(sb + 2 * TILE_BYTES + k * b_step, b_lbo, b_sbo, b_lay);
+                tc_mma_tf32(tmem_d, da_lo, db, idesc, acc);     // small terms first
+                tc_mma_tf32(tmem_d, da, db_lo, idesc, 1u);
+                tc_mma_tf32(tmem_d, da, db, idesc, 1u);
+              }
             }
+            tc_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
           }
-          tc_commit(empty_bar(s));            // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        tc_commit(tmem_full_bar(acc_idx));    // accumulator complete (fires at once for an empty k range)
+        if (elect_one()) tc_commit(tmem_full_bar(acc_idx));    // accumulator complete (fires at once for an empty k range)
+        __syncwarp();
         if (++acc_idx == 2) { acc_idx = 0; acc_ph ^= 1u; }
       }
     }
@@ -332,9 +360,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(full_bar(s), ph);
           float4* hi4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES);                   // A then B, 32 KB
           float4* lo4 = reinterpret_cast<float4*>(smem_gen + s * STAGE_BYTES + 2 * TILE_BYTES);  // A_lo then B_lo
-#pragma unroll 4
-          for (int i = 0; i < (2 * TILE_BYTES / 16) / 128; ++i) {
-            const int idx = t + i * 128;
+#pragma unroll (SPLIT_UNROLL)
+          for (int i = 0; i < (2 * TILE_BYTES / 16) / SPLIT_THREADS; ++i) {
+            const int idx = t + i * SPLIT_THREADS;
             // the tensor core reads a TF32 operand as the top 19 bits of the fp32 word, so the raw tile already IS the
             // "hi" operand; only the residual has to be written (one third less shared-memory traffic per stage)
             const float4 x = hi4[idx];
@@ -384,6 +412,8 @@ __global__ void splitk_reduce_kernel(float* C, int ldc, const float* partial, in
     }
   }
 }
+
+#include "gemm_f16x3.cuh"
 
 // ------------------------------------------------------------------ CUDA-core fp32 GEMM (odd shapes / exact fp32)
 template <bool TA, bool TB>
@@ -488,9 +518,99 @@ int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, con
   p.tiles_m = aslp_div_up(p.M, BM); p.tiles_n = aslp_div_up(p.N, BN); p.splits = splits;
   // persistent: one CTA per SM walks the (split, tile) work items with a stride of the grid size
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
-  const int grid = (int)(items < aslp_num_sms() ? items : aslp_num_sms());
-  gemm_tf32_kernel<A_MN, B_MN, PASSES><<<grid, PASSES == 1 ? 192 : 320, SMEM, st>>>(ta, tb, p);
+  const int sm_cap = (t_cta_limit > 0 && t_cta_limit < aslp_num_sms()) ? t_cta_limit : aslp_num_sms();
+  const int grid = (int)(items < sm_cap ? items : sm_cap);
+  gemm_tf32_kernel<A_MN, B_MN, PASSES><<<grid, PASSES == 1 ? 192 : NT3, SMEM, st>>>(ta, tb, p);
   ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
+// fp16 plane stored [rows][ldp] with K (extent k) contiguous; box = {64 halves, 128 rows}, 128-byte swizzle
+bool make_tmap_h(CUtensorMap* tm, const __half* base, int k_extent, int rows, int ldp) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ldp * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)HK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// splits op(X) [R rows of the product, K] into K-major fp16 planes; `mn_major`: X is stored [K][R]
+int presplit_operand(cudaStream_t st, const float* X, int ld, int R, int K, bool mn_major, __half* hi, __half* lo, int ldp, float* inv, unsigned* cmax) {
+  if (!mn_major) {
+    int blocks = aslp_div_up(R, 8);
+    if (blocks > aslp_num_sms() * 16) blocks = aslp_num_sms() * 16;
+    presplit_rows_kernel<<<blocks, 256, 0, st>>>(X, ld, R, K, hi, lo, ldp, inv);
+    ASLP_CHECK_LAUNCH();
+    return 0;
+  }
+  ASLP_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned) * R, st));
+  int gy = aslp_div_up(K, 8 * 16);
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  presplit_colmax_kernel<<<dim3(aslp_div_up(R, 32), gy), 256, 0, st>>>(X, ld, K, R, cmax);
+  ASLP_CHECK_LAUNCH();
+  presplit_transpose_kernel<<<dim3(aslp_div_up(R, 32), aslp_div_up(K, 64)), 256, 0, st>>>(X, ld, K, R, cmax, hi, lo, ldp, inv);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
+int pick_splits_h(int M, int N, int K);
+
+// the whole fp16-split product: two operand splits + the three-pass kernel (+ split-K reduce)
+int gemm_f16x3(cudaStream_t st, bool a_mn, bool b_mn, const EpiParams& p_in, const float* A, int lda, const float* B, int ldb, void* workspace,
+               size_t workspace_bytes) {
+  const int M = p_in.M, N = p_in.N, K = p_in.K;
+  const int ldp = (K + 7) / 8 * 8;
+  const size_t plane_a = (size_t)M * ldp, plane_b = (size_t)N * ldp;
+  const size_t bytes = 2 * (plane_a + plane_b) * sizeof(__half) + ((size_t)M + N) * 2 * sizeof(float) + 64;
+  char* scr = (char*)aslp_scratch(st, bytes);
+  if (scr == nullptr) { aslp_set_last_error_msg("scratch allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
+  __half* a_hi = (__half*)scr; __half* a_lo = a_hi + plane_a;
+  __half* b_hi = a_lo + plane_a; __half* b_lo = b_hi + plane_b;
+  float* inv_a = (float*)(((uintptr_t)(b_lo + plane_b) + 15) & ~(uintptr_t)15);
+  float* inv_b = inv_a + M;
+  unsigned* cmax = (unsigned*)(inv_b + N);                // max(M, N) words are enough; M + N are reserved
+  int rc = presplit_operand(st, A, lda, M, K, a_mn, a_hi, a_lo, ldp, inv_a, cmax);
+  if (rc != 0) return rc;
+  rc = presplit_operand(st, B, ldb, N, K, b_mn, b_hi, b_lo, ldp, inv_b, cmax);
+  if (rc != 0) return rc;
+  CUtensorMap tah, tal, tbh, tbl;
+  if (!(make_tmap_h(&tah, a_hi, K, M, ldp) && make_tmap_h(&tal, a_lo, K, M, ldp) && make_tmap_h(&tbh, b_hi, K, N, ldp) && make_tmap_h(&tbl, b_lo, K, N, ldp))) {
+    aslp_set_last_error_msg("cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    return ASLP_STATUS_EXECUTION_FAILED;
+  }
+  constexpr int SMEM = HSTAGES * HSTAGE_BYTES + 1024 + BAR_REGION + STG_BYTES;
+  static_assert(8 * (2 * HSTAGES + 4) + 16 <= BAR_REGION, "barrier region too small");
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASLP_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  EpiParams p = p_in;
+  int splits = pick_splits_h(M, N, K);
+  const size_t ldpart = ((size_t)N + 3) / 4 * 4;
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * ldpart * sizeof(float))) splits = 1;
+  const int num_kb = aslp_div_up(K, HK);
+  p.partial = splits > 1 ? (float*)workspace : nullptr;
+  p.ldp = (int)ldpart;
+  p.kb_per_split = aslp_div_up(num_kb, splits);
+  p.tiles_m = aslp_div_up(M, BM); p.tiles_n = aslp_div_up(N, BN); p.splits = splits;
+  const long long items = (long long)p.tiles_m * p.tiles_n * splits;
+  const int sm_cap = (t_cta_limit > 0 && t_cta_limit < aslp_num_sms()) ? t_cta_limit : aslp_num_sms();
+  const int grid = (int)(items < sm_cap ? items : sm_cap);
+  gemm_f16x3_kernel<<<grid, 192, SMEM, st>>>(tah, tal, tbh, tbl, p, inv_a, inv_b);
+  ASLP_CHECK_LAUNCH();
+  if (splits > 1) {
+    const long long total = (long long)M * ((N + 3) / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > aslp_num_sms() * 8) blocks = aslp_num_sms() * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.C, p.ldc, (const float*)workspace, (int)ldpart, splits, M, N, p.alpha, p.beta, p.bias, p.clip);
+    ASLP_CHECK_LAUNCH();
+  }
   return 0;
 }
 
@@ -513,9 +633,21 @@ int pick_splits(int M, int N, int K) {
   return aslp_div_up(num_kb, per);
 }
 
+// k-blocks are 64 wide here; the split count never exceeds pick_splits' (the workspace the caller sized with aslp_gemm_workspace_bytes)
+int pick_splits_h(int M, int N, int K) {
+  int splits = pick_splits(M, N, K);
+  const int num_kb = aslp_div_up(K, HK);
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  const int per = aslp_div_up(num_kb, splits);
+  return aslp_div_up(num_kb, per);
+}
+
 }  // namespace
 
 extern "C" {
+
+int aslp_gemm_set_cta_limit(int max_ctas) { t_cta_limit = max_ctas; return 0; }
 
 size_t aslp_gemm_workspace_bytes(int M, int N, int K) {
   const int splits = pick_splits(M, N, K);
@@ -554,6 +686,23 @@ int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, fl
     if (a_mn) { int rc = aslp_transpose(s, scr, (int)lda_t, A, lda, K, M); if (rc) return rc; A = scr; lda = (int)lda_t; scr += (size_t)M * lda_t; a_mn = false; }
     if (b_mn) { int rc = aslp_transpose(s, scr, (int)ldb_t, B, ldb, K, N); if (rc) return rc; B = scr; ldb = (int)ldb_t; b_mn = false; }
   }
+  // default fp32-grade mode: operands split once into fp16 hi / lo planes, three kind::f16 passes (gemm_f16x3.cuh).  The two split
+  // launches only pay off on chunk-sized products; ASLP_GEMM_SPLIT=tf32 keeps the in-loop 3xTF32 split for every shape (A/B runs).
+  static const char* split_env = getenv("ASLP_GEMM_SPLIT");
+  static const bool force_tf32_split = split_env != nullptr && split_env[0] == 't';
+  // Measured (profiles/r02_gemm_ab.jsonl, times include the split launches): 16000x1280x640 NT 0.148 -> 0.107 ms, 16000x640x1280 NN
+  // 0.151 -> 0.123 ms, 4096^3 0.644 -> 0.389 ms; but 16000x320x320 0.033 -> 0.043 ms (the split of A costs more than it saves) and
+  // the TN weight gradient 1280x640x16000 0.157 -> 0.221 ms (two large TRANSPOSING splits: a column-maximum pass plus a tile
+  // transpose each).  So: chunk-sized products only, and only when every MN-major operand is small (a weight matrix).
+  static const double f16_min_work = getenv("ASLP_GEMM_F16_MIN_WORK") ? atof(getenv("ASLP_GEMM_F16_MIN_WORK")) : 3.0e9;
+  const bool cheap_split = (!a_mn || (long long)M * K <= (1ll << 22)) && (!b_mn || (long long)N * K <= (1ll << 22));
+  if (precision == ASLP_GEMM_F16X3 ||
+      (precision == ASLP_GEMM_3XTF32 && !force_tf32_split && cheap_split && (double)M * N * K >= f16_min_work && K >= 2 * HK)) {
+    EpiParams pe;
+    pe.C = C; pe.ldc = ldc; pe.M = M; pe.N = N; pe.K = K; pe.alpha = alpha; pe.beta = beta; pe.bias = bias; pe.clip = clip;
+    pe.partial = nullptr; pe.ldp = 0; pe.kb_per_split = 0; pe.tiles_m = pe.tiles_n = pe.splits = 0;
+    return gemm_f16x3(st, a_mn, b_mn, pe, A, lda, B, ldb, workspace, workspace_bytes);
+  }
   CUtensorMap ta, tb;
   bool ok = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK, true) : make_tmap(&ta, A, K, M, lda, BK, BM, false);
   ok = ok && (b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK, true) : make_tmap(&tb, B, K, N, ldb, BK, BN, false));
@@ -568,7 +717,7 @@ int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, fl
   p.partial = splits > 1 ? (float*)workspace : nullptr;
   p.ldp = (int)ldp;
   p.kb_per_split = aslp_div_up(num_kb, splits);
-  const bool one_pass = precision == ASLP_GEMM_TF32;
+  const bool one_pass = precision == ASLP_GEMM_TF32;      // ASLP_GEMM_3XTF32 below the fp16-split threshold: the in-loop split
   int rc;
 #define ASLP_DISPATCH(AM, BMN)                                             \
   rc = one_pass ? launch_tc<AM, BMN, 1>(st, ta, tb, p, splits) : launch_tc<AM, BMN, 3>(st, ta, tb, p, splits)

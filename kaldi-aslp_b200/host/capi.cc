@@ -140,6 +140,7 @@ int aslp_xent_report(aslp_xent_t x, char* buf, size_t bytes, double stats5[5]) {
 }
 int aslp_warpctc_create(aslp_warpctc_t* out) { CAPI_BEGIN *out = new WarpCtc(); CAPI_END }
 int aslp_warpctc_destroy(aslp_warpctc_t c) { CAPI_BEGIN delete static_cast<WarpCtc*>(c); CAPI_END }
+int aslp_warpctc_rejected(aslp_warpctc_t c, int* n) { CAPI_BEGIN *n = static_cast<WarpCtc*>(c)->NumRejected(); CAPI_END }
 int aslp_warpctc_report(aslp_warpctc_t c, char* buf, size_t bytes) { CAPI_BEGIN CopyOut(static_cast<WarpCtc*>(c)->Report(), buf, bytes); CAPI_END }
 
 static const CuMatrixBase<BaseFloat>& StageFeatures(const float* features, int on_device, int rows, int cols, CuSubMatrix<BaseFloat>* view) {

@@ -67,8 +67,23 @@ void CuJoin() {
   ASLP_OK(aslp_stream_wait_event(g_stream, g_ev_join));
   g_side_pending = false;
 }
-CuStreamScope::CuStreamScope(aslp_stream_t s) { CuStream(); saved_ = t_current; t_current = s; }
-CuStreamScope::~CuStreamScope() { t_current = saved_; }
+// GEMMs issued inside a side-stream scope can run on a capped grid (ASLP_SIDE_GEMM_CTAS = n; default 0 = one CTA per SM): they are
+// the weight-gradient products that run under the next layer's persistent backward recurrence (80 co-resident CTAs).  Measured on
+// one box (profiles/r02_ab_side_ctas.jsonl): 17.91 ms per cfg3 step uncapped, 17.95 at 68, 17.98 at 60, 18.28 at 40 -- the cap
+// does not help (the recurrence gets its SMs either way), so it stays off.
+static int SideGemmCtas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ASLP_SIDE_GEMM_CTAS"); v = e != nullptr ? atoi(e) : 0; }
+  return v;
+}
+CuStreamScope::CuStreamScope(aslp_stream_t s) {
+  CuStream(); saved_ = t_current; t_current = s;
+  if (s == g_side && g_side != nullptr) aslp_gemm_set_cta_limit(SideGemmCtas());
+}
+CuStreamScope::~CuStreamScope() {
+  if (t_current == g_side && g_side != nullptr) aslp_gemm_set_cta_limit(0);
+  t_current = saved_;
+}
 void CuSync() {
   CuStream();
   if (t_helper) { ASLP_OK(aslp_stream_sync(t_current)); return; }     // a helper thread owns nothing but its stream

@@ -312,6 +312,7 @@ void WarpCtc::StatAndAverageLossCheck(const std::vector<std::string>& utt, const
       } else {
         KALDI_WARN << "Sequences " << utt[s] << " obj is abnormal(sum " << pzx_host[s] << " per_frame " << loss_per_frame << " mean "
                    << loss_sum_ / normal_num_ << " sigma " << loss_square_sum_ / normal_num_ << "), drop it's diff and stat";
+        ++rejected_num_;
         // rows t*num_sequence + s, t < frames: one strided zero fill instead of a host loop of per-row SetZero
         ASLP_OK(aslp_memset2d(CuStream(), diff->Data() + static_cast<size_t>(s) * diff->Stride(), sizeof(float) * diff->Stride() * num_sequence, 0,
                               sizeof(float) * diff->NumCols(), frame_num_utt[s]));

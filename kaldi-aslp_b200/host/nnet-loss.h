@@ -113,6 +113,7 @@ class WarpCtc {
   int32 NumRefTokens() const { return ref_num_; }
   void SetUseGpu(bool use_gpu);       // only true is served: there is no CPU path
   const std::vector<float>& LastCosts() const { return costs_; }
+  int32 NumRejected() const { return rejected_num_; }      // utterances whose diff the loss guard zeroed so far (warp-ctc.cc:318-330)
  private:
   void StatAndAverageLossCheck(const std::vector<std::string>& utt, const std::vector<int32>& frame_num_utt,
                                const std::vector<float>& pzx_host, CuMatrix<BaseFloat>* diff);
@@ -127,6 +128,7 @@ class WarpCtc {
   double loss_sum_, loss_square_sum_, loss_sum_bak_, loss_square_sum_bak_;
   int32 normal_num_, stat_period_;
   std::vector<float> costs_;
+  int32 rejected_num_ = 0;
   CuArrayInt maxid_;
 };
 

@@ -169,6 +169,13 @@ class WarpCtc:
         return buf.value.decode()
 
 
+def warpctc_rejected(ctc):
+    """utterances whose derivative the 6-sigma / (0, 3000) loss guard has zeroed so far"""
+    n = ctypes.c_int(0)
+    _ck(host_lib().aslp_warpctc_rejected(ctc.h, ctypes.byref(n)))
+    return n.value
+
+
 class EesenCtc:
     """kaldi::aslp_nnet::Ctc (src/aslp-nnet/ctc-loss.h): CTC on the softmax outputs, error back-propagated through the softmax."""
 

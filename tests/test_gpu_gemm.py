@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 #   3xTF32 (default): fp32-grade, the north_star's 1e-4 bound (we assert 2e-5)
 #   TF32 single pass: stated looser bound 5e-3 (10-bit mantissa operands, truncated)
 #   FP32 CUDA cores : 2e-5
-TOL = {0: 2e-5, 1: 5e-3, 2: 2e-5}
+TOL = {0: 2e-5, 1: 5e-3, 2: 2e-5, 3: 2e-5}      # 3: fp16 hi / lo planes + three kind::f16 passes (what 0 runs on chunk-sized products)
 
 SHAPES = [
     # (M, N, K)
@@ -53,7 +53,7 @@ def run_gemm(M, N, K, ta, tb, prec, alpha=1.0, beta=0.0, bias=False, clip=0.0, s
     return err, err_oracle, got, dC
 
 
-@pytest.mark.parametrize("prec", [2, 1, 0], ids=["fp32", "tf32", "x3tf32"])
+@pytest.mark.parametrize("prec", [2, 1, 0, 3], ids=["fp32", "tf32", "x3tf32", "f16x3"])
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)], ids=["NT", "NN", "TN", "TT"])
 @pytest.mark.parametrize("shape", SHAPES, ids=["s%d" % i for i in range(len(SHAPES))])
 def test_gemm_all_layouts(shape, ta, tb, prec):
@@ -62,7 +62,7 @@ def test_gemm_all_layouts(shape, ta, tb, prec):
     assert err < TOL[prec], (shape, ta, tb, prec, err, err_oracle)
 
 
-@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("prec", [0, 1, 3])
 def test_gemm_epilogue_alpha_beta_bias_clip(prec):
     err, _, _, _ = run_gemm(300, 200, 96, False, True, prec, alpha=0.5, beta=0.9, bias=True)
     assert err < TOL[prec]
@@ -71,11 +71,11 @@ def test_gemm_epilogue_alpha_beta_bias_clip(prec):
     assert np.abs(got).max() <= 5.0
 
 
-@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("prec", [0, 1, 3])
 def test_gemm_wgrad_split_k(prec):
     # chunk weight gradient: [4C, D] = DGIFO^T [4C, T*S] * X [T*S, D] with momentum and clip (lc.h:981-1017)
-    # long contractions: the bound is the north_star's 1e-4 (fp32-grade path), the TF32 bound otherwise
-    tol = 1e-4 if prec == 0 else TOL[prec]
+    # long contractions: the bound is the north_star's 1e-4 (fp32-grade paths), the TF32 bound otherwise
+    tol = 1e-4 if prec in (0, 3) else TOL[prec]
     err, _, _, _ = run_gemm(1280, 640, 4000, True, False, prec, alpha=1.0, beta=0.9, clip=50.0)
     assert err < tol, err
     err, _, _, _ = run_gemm(320, 40, 4000, True, False, prec, alpha=1.0, beta=0.9)
@@ -96,3 +96,25 @@ def test_gemm_padded_strides_do_not_leak():
 def test_gemm_empty():
     from tests.gpu_utils import lib, ok, stream, P
     ok(lib().aslp_gemm(stream(), 0, 1, 0, 16, 16, 1.0, P(0), 16, P(0), 16, 0.0, P(0), 16, P(0), 0.0, 0, P(0), 0))
+
+
+def test_gemm_f16x3_rows_of_very_different_magnitude():
+    """the fp16-split path scales every row of op(A) and every column of op(B) by its own power of two: rows 2^-60 .. 2^40 apart must
+    all come out fp32-grade RELATIVE TO THEIR OWN magnitude (a single global scale would flush the small rows to zero)"""
+    from tests.gpu_utils import DMat, lib, ok, ptr, stream, sync, P
+    import torch
+    rng = np.random.default_rng(7)
+    M, N, K = 300, 200, 256
+    A = rng.standard_normal((M, K)).astype(np.float32) * np.exp2(rng.integers(-60, 40, size=(M, 1))).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32) * np.exp2(rng.integers(-30, 30, size=(N, 1))).astype(np.float32)
+    dA, dB, dC = DMat(A), DMat(B), DMat(np.zeros((M, N), np.float32))
+    L = lib()
+    wsb = L.aslp_gemm_workspace_bytes(M, N, K)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device="cuda")
+    ok(L.aslp_gemm(stream(), 0, 1, M, N, K, 1.0, dA.ptr, dA.ld, dB.ptr, dB.ld, 0.0, dC.ptr, dC.ld, P(0), 0.0, 3, ptr(ws), wsb))
+    sync()
+    got = dC.np().astype(np.float64)
+    exact = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A.astype(np.float64)).max(axis=1)[:, None] * np.abs(B.astype(np.float64)).max(axis=1)[None, :] * np.sqrt(K)
+    assert np.all(np.isfinite(got))
+    assert (np.abs(got - exact) / scale).max() < 2e-5
