@@ -20,6 +20,9 @@ constexpr int TR = 4;                    // ring slots of the partial-sum exchan
 #ifndef ASLP_BWD_T_DELAY_NS
 #define ASLP_BWD_T_DELAY_NS 0
 #endif
+#ifndef ASLP_PIPE_BWD_GAP_NS
+#define ASLP_PIPE_BWD_GAP_NS 0   // extra spacing before the last gather round of a step (pipelined polling)
+#endif
 #ifndef ASLP_BWD_T_FP16
 #define ASLP_BWD_T_FP16 1        // 1: fp16 two-term split with per-stream power-of-two scaling of dgifo (8-stream form); 0: 3xTF32
 #endif
@@ -202,14 +205,36 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   const size_t chain_off = (size_t)cta.pg * nblk * nblk * 128;
   auto own_block = [&](int slot) { return X + (size_t)slot * slot_stride + chain_off + (size_t)cta.blk * nblk * 128; };   // [producer][16][8]
   const int items = nblk * 32;                           // float4 items of the own block
+  constexpr int PR = ASLP_PIPE_ROUNDS;                   // gather rounds in flight per step (pipelined polling, recur.cuh)
   auto issue_gather = [&](int slot) {
     const float* src = own_block(slot);
     for (int i = threadIdx.x; i < items; i += NT) cp_async16(Psm + i * 4, src + i * 4);
+    if (PR > 1) cp_async_commit();
   };
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // debug phase clocks (aslp_lstm_debug_timing), thread 0
+  auto gather_clean = [&]() {
+    unsigned bad = 0;
+    for (int i = threadIdx.x; i < items; i += NT) bad |= sentinel_in(*reinterpret_cast<const float4*>(Psm + i * 4));
+    return bad == 0;
+  };
   auto complete_gather = [&](int slot) {
     const float* src = own_block(slot);
     unsigned rounds = 0;
+    if (PR > 1) {
+      // the PR rounds were issued during the previous step: leave on the first one that shows no sentinel
+      bool ok = false;
+      if (PR >= 3) { cp_async_wait_group<2>(); if (L.timing != nullptr && threadIdx.x == 0) tacc[5] += 1; ok = gather_clean(); }
+      if (!ok) { cp_async_wait_group<1>(); if (L.timing != nullptr && threadIdx.x == 0) tacc[5] += 1; ok = gather_clean(); }
+      if (!ok) { cp_async_wait_group<0>(); if (L.timing != nullptr && threadIdx.x == 0) tacc[5] += 1; ok = gather_clean(); }
+      while (!ok) {
+        for (int i = threadIdx.x; i < items; i += NT) cp_async16(Psm + i * 4, src + i * 4);
+        cp_async_wait_all();
+        if (L.timing != nullptr && threadIdx.x == 0) tacc[5] += 1;
+        ok = gather_clean();
+        if (++rounds > POLL_LIMIT) __trap();
+      }
+      return;
+    }
     for (;;) {
       cp_async_wait_all();
       if (L.timing != nullptr && threadIdx.x == 0) tacc[5] += 1;
@@ -245,6 +270,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
   };
   warm(0); warm(1);
   issue_gather(0);
+  if (PR > 1) { for (int r = 1; r < PR; ++r) cp_async_commit(); }     // slot 0 is the boundary: one real round, PR groups
 
   for (int it = 0; it < T; ++it) {
     const int slot = it % TR;
@@ -266,8 +292,14 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
     float dg = 0.f, di = 0.f, df = 0.f, dout = 0.f, dc = 0.f, dh = 0.f, dm = 0.f;
     if (fin) {
       if (live) {
-        float sum = 0.f;
-        for (int p = 0; p < nblk; ++p) sum += Psm[p * 128 + cl * 8 + s_local];      // fixed order: deterministic
+        // fixed order (deterministic): four interleaved partial chains, so the nblk shared-memory loads are in flight
+        // together instead of one load-add round trip per producer
+        const float* pp = Psm + cl * 8 + s_local;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p = 0;
+        for (; p + 4 <= nblk; p += 4) { s0 += pp[p * 128]; s1 += pp[(p + 1) * 128]; s2 += pp[(p + 2) * 128]; s3 += pp[(p + 3) * 128]; }
+        for (; p < nblk; ++p) s0 += pp[p * 128];
+        const float sum = (s0 + s1) + (s2 + s3);
         const int si = cl * 8 + s_local;
         const float yg = yv[0], yi = yv[1], yf = yv[2], yo = yv[3], yh = yv[4], c_prev = yv[5], yf_next = yv[6];
         dm = sum + od;
@@ -293,6 +325,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
       __threadfence();                                   // the re-arm stores of the previous step (below) precede this step's publish
     }
     RECUR_TICK(k3);
+    if (PR > 1) cp_async_wait_all();                     // this step's stale gather rounds are done before the slot is re-armed / Psm reused
     __syncthreads();                                     // Bsm complete, re-arm fenced
     RECUR_TICK(k4);
     if (it + 1 < T) {
@@ -314,21 +347,29 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
     // ---- off the chain: re-arm the slot consumed at the top of this step, start the next gather, and only then write the
     // bookkeeping of this step (they overlap the gather's round trip).  The re-arm and the prefetch address arithmetic put
     // about one store-to-L2 latency between the publish and the gather, so its first round usually finds the data.
+    const bool more = it + 1 < T;
+    if (PR > 1 && more) issue_gather((it + 1) % TR);     // round 0 right behind the publish (Psm is free: its readers passed the barrier)
     if (!fin) {
       float* blk = own_block(slot);
       const float4 sent = make_float4(__uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL), __uint_as_float(SENTINEL));
       for (int i = threadIdx.x - 128; i < items; i += NT - 128) *reinterpret_cast<float4*>(blk + i * 4) = sent;
     }
-    if (it + 1 < T) {
+    if (more) {
       warm(it + 2);
 #if ASLP_BWD_T_DELAY_NS > 0
       __nanosleep(ASLP_BWD_T_DELAY_NS);
 #endif
-      issue_gather((it + 1) % TR);                       // Psm is free: its readers passed the barrier above
+      if (PR == 1 || PR >= 3) issue_gather((it + 1) % TR);   // single-round form: Psm is free, its readers passed the barrier above
     }
     if (live) {
       float* d = dbuf + ((size_t)t * S + s) * lddb + cc;
       d[0] = dg; d[C] = di; d[2 * C] = df; d[3 * C] = dout; d[4 * C] = dc; d[5 * C] = dh; d[6 * C] = dm;
+    }
+    if (PR >= 2 && more) {
+#if ASLP_PIPE_BWD_GAP_NS > 0
+      __nanosleep(ASLP_PIPE_BWD_GAP_NS);
+#endif
+      issue_gather((it + 1) % TR);
     }
     if (L.timing != nullptr && threadIdx.x == 0) {
       const long long k6 = clock64();
@@ -550,8 +591,13 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_tn_kernel(Launch L) {
       if (item < ITEMS) {
         const int cl = item / SW;
         if (live[r]) {
-          float sum = 0.f;
-          for (int p = 0; p < nblk; ++p) sum += Psm[(size_t)p * ITEMS + item];      // fixed order: deterministic
+          // fixed order (deterministic), four interleaved chains: the nblk loads are in flight together
+          const float* pp = Psm + item;
+          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+          int p = 0;
+          for (; p + 4 <= nblk; p += 4) { q0 += pp[(size_t)p * ITEMS]; q1 += pp[(size_t)(p + 1) * ITEMS]; q2 += pp[(size_t)(p + 2) * ITEMS]; q3 += pp[(size_t)(p + 3) * ITEMS]; }
+          for (; p < nblk; ++p) q0 += pp[(size_t)p * ITEMS];
+          const float sum = (q0 + q1) + (q2 + q3);
           const float pi = pst[cl], pf = pst[16 + cl], po = pst[32 + cl];
           const float yg = yv[r][0], yi = yv[r][1], yf = yv[r][2], yo = yv[r][3], yh = yv[r][4], c_prev = yv[r][5], yf_next = yv[r][6];
           const float dm = sum + od[r];

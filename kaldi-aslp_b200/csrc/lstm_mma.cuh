@@ -399,7 +399,21 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
   };
   if (ASLP_WARM_AHEAD > 0) { for (int w = 0; w < ASLP_WARM_AHEAD; ++w) warm(w); }
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (hoisted) stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? T + 1 : 0) * slot);
+  constexpr int PR = ASLP_PIPE_ROUNDS;                   // staging rounds in flight per step (recur.cuh)
+  if (hoisted) {
+    stage_issue<SB>(sd, xT, xa + (size_t)(reverse ? T + 1 : 0) * slot);
+    if (PR > 1) { for (int r = 0; r < PR; ++r) cp_async_commit(); }          // the boundary slot is there: one real round
+  }
+  // warps none of whose threads finishes an item have nothing to do between the contraction and the next exchange wait:
+  // they sleep towards the publish of the finishing warps before their staging rounds (warp-uniform)
+  const bool warp_fin = __any_sync(0xffffffffu, owner && s_local < min(SG, cta.send - cta.sbeg));
+  auto pipe_round = [&](int it, int t, int idle_ns) {
+    if (PR > 1 && hoisted && it + 1 < nitems) {
+      if (!warp_fin && idle_ns > 0) __nanosleep(idle_ns);
+      stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+      cp_async_commit();
+    }
+  };
 
   for (int it = 0; it < nitems; ++it) {
     int t, s0; item_row(it, t, s0);
@@ -407,7 +421,10 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
     const int nstr = min(SG, cta.send - s0);             // streams of this staging group
     RECUR_TICK(k0);
     long long* dbg = (L.timing != nullptr && threadIdx.x == 0) ? &tacc[5] : nullptr;
-    if (hoisted) stage_complete<SB>(sd, xT, xa + (size_t)tp * slot, dbg);     // copies were issued at the end of the previous step
+    if (hoisted) {                                       // copies were issued at the end of the previous step
+      if (PR > 1) stage_complete_pipe<SB, PR>(sd, xT, xa + (size_t)tp * slot, dbg);
+      else stage_complete<SB>(sd, xT, xa + (size_t)tp * slot, dbg);
+    }
     else stage_poll<8>(xT, SP, xa + (size_t)tp * slot, K, SX, s0, (min(s0 + SG, SX) - s0) >> 2, dbg);
     float pre[4] = {0.f, 0.f, 0.f, 0.f};
     {
@@ -423,46 +440,52 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_mma_kernel(Launch L) {
     mma_contract<MT_, KT_>(wa, xT, SP, kt0 * 8, K, (nstr + 7) >> 3, part + (size_t)warp * SG * NPP, lane);
 #endif
     RECUR_TICK(k3);
+    if (PR > 1 && hoisted) cp_async_wait_all();          // stale rounds of this step (identical values) are done before xT is released
     __syncthreads();
     RECUR_TICK(k4);
     const int s = s0 + s_local;
-    if (owner && s_local < nstr) {
+    const bool fin_item = owner && s_local < nstr;
+    float yg = 0.f, yi = 0.f, yf = 0.f, yo = 0.f, yc = 0.f, yh = 0.f, ym = 0.f;
+    if (fin_item) {
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
         const float4 p = *reinterpret_cast<const float4*>(part + ((size_t)w * SG + s_local) * NPP + cl * 4);
         sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
       }
-      const size_t row = (size_t)t * S + s;
       const int ci = cl * L.SGP + (s - cta.sbeg);
       const float cprev = cst[ci];
-      float yg = pre[0] + sum.x;
-      float yi = pre[1] + sum.y + cprev * pi;
-      float yf = pre[2] + sum.z + cprev * pf;
-      float yo = pre[3] + sum.w;
+      yg = pre[0] + sum.x;
+      yi = pre[1] + sum.y + cprev * pi;
+      yf = pre[2] + sum.z + cprev * pf;
+      yo = pre[3] + sum.w;
       yi = ref_sigmoid(yi); yf = ref_sigmoid(yf); yg = ref_tanh(yg);
-      float yc = yg * yi + cprev * yf;
+      yc = yg * yi + cprev * yf;
       yc = fminf(fmaxf(yc, -clip), clip);
-      float yh = ref_tanh(yc);
+      yh = ref_tanh(yc);
       yo = ref_sigmoid(yo + yc * po);
-      float ym = yh * yo;
+      ym = yh * yo;
       if (seq_len != nullptr && t > seq_len[s]) { yg = yi = yf = yo = yc = yh = ym = 0.f; }
       st_pub(xa + ((size_t)t * C + c0 + cl) * SX + s, ym);       // publish m(t) first: it is what the other SMs wait for
       if (L.timing != nullptr && threadIdx.x == 0) tacc[7] += clock64() - k4;
-      if (ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
-      float* o = buf + row * ldb + c0 + cl;
-      o[0] = yg; o[C] = yi; o[2 * C] = yf; o[3 * C] = yo; o[4 * C] = yc; o[5 * C] = yh; o[6 * C] = ym;
       cst[ci] = yc;
-    } else if (ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) {
-      stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
     }
-    // next step's exchange copies: after the bookkeeping stores (about one store-to-L2 latency after the publish, so
-    // the first round usually finds the data), before the prefetch address arithmetic; xT is free (contraction done).
-    // ASLP_ISSUE_EARLY = 1 issues them right after the publish instead (A/B variant, tools/gpu_ab_fwd.sh).
+    // next step's exchange copies; xT is free (contraction done).  Pipelined form: first round right after the publish,
+    // the others behind the bookkeeping stores and the prefetch arithmetic.  Single-round form (ASLP_PIPE_ROUNDS = 1):
+    // after the bookkeeping stores (about one store-to-L2 latency after the publish, so the round usually finds the data);
+    // ASLP_ISSUE_EARLY = 1 issues it right after the publish instead (A/B variant, tools/gpu_ab_fwd.sh).
+    pipe_round(it, t, ASLP_PIPE_IDLE_NS0);
+    if (PR == 1 && ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    if (fin_item) {
+      float* o = buf + ((size_t)t * S + s) * ldb + c0 + cl;
+      o[0] = yg; o[C] = yi; o[2 * C] = yf; o[3 * C] = yo; o[4 * C] = yc; o[5 * C] = yh; o[6 * C] = ym;
+    }
     RECUR_TICK(e0);
-    if (!ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
+    if (PR >= 3) pipe_round(it, t, ASLP_PIPE_IDLE_NS);
+    if (PR == 1 && !ASLP_ISSUE_EARLY && hoisted && it + 1 < nitems) stage_issue<SB>(sd, xT, xa + (size_t)t * slot);
     RECUR_TICK(e1);
     if (ASLP_WARM_AHEAD > 0) warm(it + ASLP_WARM_AHEAD);
+    if (PR >= 2) pipe_round(it, t, ASLP_PIPE_IDLE_NS);
     if (L.timing != nullptr && threadIdx.x == 0) { tacc[8] += e0 - k4; tacc[9] += e1 - e0; tacc[10] += clock64() - e1; }
     if (L.timing != nullptr && threadIdx.x == 0) {
       const long long k5 = clock64();

@@ -36,6 +36,29 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Pipelined polling (ASLP_PIPE_ROUNDS = R > 1).  A staging round samples L2 about half a round trip after it is issued and
+// lands half a round trip later (~700 cycles in all); issued once and early it misses the slowest producer and pays a
+// second full round trip, issued late it idles -- so R rounds are issued a few hundred cycles apart, each its own
+// cp.async group, all into the same shared-memory destination.  Exchange words only ever change from the sentinel to
+// their final value, so overlapping rounds are monotonic: the consumer waits for the groups in order and leaves on the
+// first round that shows no sentinel; later rounds rewrite identical values.  A thread drains its stale rounds
+// (cp_async_wait_all, long complete by then) before the barrier that releases the destination / the source slot.
+// MEASURED AND NOT ADOPTED (profiles/r02_ab_pipe_polling.jsonl, cfg3 geometry, same box): R = 3 is 9 % slower forward
+// (2.17 vs 1.99 us per step) and 8 % slower backward (2.65 vs 2.45), R = 2 in between -- issuing a round costs the
+// finishing threads ~170 cycles of LSU issue each (forward finish phase 971 -> 1412 cycles) and the single well-timed
+// round already samples L2 just as the slowest producer's store lands (rounds = 1.0 in the phase timing).  Default 1.
+#ifndef ASLP_PIPE_ROUNDS
+#define ASLP_PIPE_ROUNDS 1
+#endif
+#ifndef ASLP_PIPE_IDLE_NS0
+#define ASLP_PIPE_IDLE_NS0 200     // idle (non-finishing) warps: sleep before their first round ...
+#endif
+#ifndef ASLP_PIPE_IDLE_NS
+#define ASLP_PIPE_IDLE_NS 100      // ... and between rounds
+#endif
 
 template <int BATCH>
 __device__ __forceinline__ void stage_poll(float* xT, int SP, const float* g, int K, int SX, int s0, int sg4,
@@ -150,6 +173,34 @@ __device__ __forceinline__ void stage_complete(const StageDesc& d, float* xT, co
 #pragma unroll
     for (int j = 0; j < BATCH; ++j)
       if ((still >> j) & 1u) cp_async16(dst0 + j * d.dstride, src0 + (size_t)j * d.sstride);
+    if (++rounds > POLL_LIMIT) __trap();
+  }
+}
+// pipelined form: the R rounds were issued (stage_issue + cp_async_commit each) by the caller; inspect them in order
+template <int BATCH, int R>
+__device__ __forceinline__ void stage_complete_pipe(const StageDesc& d, float* xT, const float* g, long long* dbg = nullptr) {
+  float* dst0 = xT + d.dst_off;
+  auto clean = [&]() {
+    unsigned still = 0;
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const bool live = (d.mask >> j) & 1u;
+      const float4 v = *reinterpret_cast<const float4*>(live ? dst0 + j * d.dstride : dst0);
+      still |= (live ? sentinel_in(v) : 0u) << j;
+    }
+    return still == 0;
+  };
+  const long long tq0 = dbg != nullptr ? clock64() : 0;
+  bool ok = false;
+  if (R >= 3) { cp_async_wait_group<2>(); if (dbg != nullptr) { dbg[1] += clock64() - tq0; dbg[0] += 1; } ok = clean(); }
+  if (R >= 2 && !ok) { cp_async_wait_group<1>(); if (dbg != nullptr) dbg[0] += 1; ok = clean(); }
+  if (!ok) { cp_async_wait_group<0>(); if (dbg != nullptr) dbg[0] += 1; ok = clean(); }
+  unsigned rounds = 0;
+  while (!ok) {
+    stage_issue<BATCH>(d, xT, g);
+    cp_async_wait_all();
+    if (dbg != nullptr) dbg[0] += 1;
+    ok = clean();
     if (++rounds > POLL_LIMIT) __trap();
   }
 }
