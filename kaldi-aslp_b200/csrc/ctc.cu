@@ -4,7 +4,9 @@
 // cost_and_grad :369-428, log_plus (detail/ctc_helper.h:55-68).  The reference's GPU path
 // (gpu_ctc_kernels.h) is not followed: it does not compile for sm_70+.
 //
-// Four launches per minibatch, labels uploaded once:
+// Up to 256 states, 128 classes and ~4 utterances per SM: ONE launch (ctc_fused.cuh -- softmax rows in shared memory, both
+// sweeps meeting in the middle, gradient formed from the half-spilled rows; 1.13 x the algorithmic HBM bytes).
+// Otherwise four launches per minibatch, labels uploaded once:
 //   0. ctc_csr_kernel     : per utterance, the states of every label (for the per-label sums of pass 3);
 //   1. ctc_softmax_kernel : warp per (t, n) row: probabilities and the per-state log-probabilities lp[n][t][i]
 //                           into the workspace (HBM-bound);
@@ -547,6 +549,19 @@ __global__ void __launch_bounds__(256) ctc_grad_staged_kernel(float* __restrict_
   }
 }
 
+#include "ctc_fused.cuh"
+
+template <int G, int HW>
+int launch_fused(cudaStream_t st, int mb, const float* acts, float* grads, float* spill, float* costs, int* valid, const int* flat,
+                 const int* off, const int* llen, const int* ilen, int K, int maxT, int maxS) {
+  const int SP = (maxS + 3) & ~3;
+  const size_t smem = CfSmem{SP, K}.bytes(HW);
+  ASLP_CUDA(cudaFuncSetAttribute(ctc_fused_kernel<G, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_fused_kernel<G, HW><<<mb, 2 * G + 32 * HW, smem, st>>>(acts, grads, spill, costs, valid, flat, off, llen, ilen, K, mb, maxT, maxS, SP);
+  ASLP_CHECK_LAUNCH();
+  return 0;
+}
+
 struct Sizes { size_t alphas, betas, lp, probs, costs, valid, meta, csr, total; int maxT, maxL, maxS, sumL; };
 Sizes ctc_sizes(const int* label_lengths, const int* input_lengths, int K, int mb) {
   Sizes z; memset(&z, 0, sizeof(z));
@@ -654,6 +669,26 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
   const int* d_llen = meta; const int* d_ilen = meta + mb; const int* d_off = meta + 2 * mb; const int* d_flat = meta + 3 * mb;
 
   if (z.maxS > 4 * 1024) return CTC_STATUS_INVALID_VALUE;          // more than 2047 labels in one utterance
+  const char* sweep_env = getenv("ASLP_CTC_SWEEP");                // fused (default where it applies) | warp | block
+  const bool fused_fits = z.maxS <= 256 && K <= CF_KMAX;
+  const bool want_fused = fused_fits && (sweep_env != nullptr ? strcmp(sweep_env, "fused") == 0 : mb <= 4 * aslp_num_sms());
+  if (want_fused) {
+    // one launch: softmax rows, both sweeps and the gradient per utterance (ctc_fused.cuh); `alphas` is the [T][S] spill.
+    // 16 helper warps while the minibatch leaves SMs idle (the helpers must keep up with one sweep step every ~300
+    // cycles), 8 once utterances queue per SM
+    const bool wide = mb < 2 * aslp_num_sms();
+    int rc;
+#define ASLP_FUSED(Gv) (wide ? launch_fused<Gv, 16>(st, mb, activations, gradients, alphas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, K, z.maxT, z.maxS) \
+                             : launch_fused<Gv, 8>(st, mb, activations, gradients, alphas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, K, z.maxT, z.maxS))
+    if (z.maxS <= 64) rc = ASLP_FUSED(64);
+    else if (z.maxS <= 128) rc = ASLP_FUSED(128);
+    else rc = ASLP_FUSED(256);
+#undef ASLP_FUSED
+    if (rc != 0) return CTC_STATUS_EXECUTION_FAILED;
+    if (cudaMemcpyAsync(costs, costs_dev, mb * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) return CTC_STATUS_MEMOPS_FAILED;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
+    return CTC_STATUS_SUCCESS;
+  }
   {
     ctc_csr_kernel<<<mb, 128, (K + 1) * sizeof(int), st>>>(cls_start, cls_list, d_flat, d_off, d_llen, K, z.maxS);
     ++g_aslp_launches;
@@ -685,7 +720,6 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
     // Which sweep kernel: the CTA form (one state per thread) has the shorter step -- 0.53 ms against 0.90 ms for the 16
     // utterances of a cfg3 minibatch -- and the warp-per-sweep form the higher throughput once the minibatch alone fills
     // the chip (2048 utterances: 6.93 ms against 7.33 ms).  ASLP_CTC_SWEEP=warp|block forces one (the tests run both).
-    const char* sweep_env = getenv("ASLP_CTC_SWEEP");
     const bool force_warp = sweep_env != nullptr && strcmp(sweep_env, "warp") == 0;
     const bool force_block = sweep_env != nullptr && strcmp(sweep_env, "block") == 0;
     const bool want_warp = z.maxS <= 256 && !force_block && (force_warp || mb >= aslp_num_sms() * 8);

@@ -1,0 +1,345 @@
+// ctc_fused.cuh -- one-launch CTC forward-backward at its algorithmic HBM traffic (included by ctc.cu inside its anonymous
+// namespace, after log_plus).  Same arithmetic as the four-launch path (cpu_ctc.h:158-179 softmax, :217-262 alphas,
+// :269-367 betas + gradient), but nothing that is not algorithmically necessary touches HBM:
+//   * no per-state log-probability rows and no probability matrix in the workspace: helper warps of the CTA turn the
+//     activation rows of the next TB time steps into log-softmax rows in shared memory (ring of three blocks) while the
+//     sweeps run on the current block; a sweep thread gathers log p[t][label(i)] from that row;
+//   * the alpha sweep and the beta sweep of an utterance run concurrently in ONE CTA (G threads each, one state per
+//     thread, one named barrier per step and direction) and meet in the middle: whichever sweep reaches a time row FIRST
+//     spills it ([T][S] floats in all: alpha rows for the first half of the utterance, beta rows for the second), the
+//     sweep that reaches the row SECOND leaves it in shared memory, where the helper warps combine it with the spilled
+//     counterpart into the per-label sums and the gradient row one block later.  beta is never stored for the first
+//     half, alpha never for the second, and the whole utterance takes T steps instead of 2 T;
+//   * because the gradient of the rows the sweeps reach second is formed before either sweep has finished, the
+//     normaliser log Z is taken where the sweeps meet: log Z = logsumexp_i (alpha_t[i] + beta_t[i] - log p_t[label(i)]) at
+//     the middle row (both recursions include the emission of their own row, cpu_ctc.h:252,329).  It equals the
+//     reference's log-likelihood (the last alpha row, :255-261 -- which is still what `costs` returns) up to fp32 rounding
+//     of sums of magnitude |cost|, the same resolution the alpha-beta products themselves have.
+// HBM per utterance: activations read twice (once per direction) + [T][S] spill written and read once + gradient written
+// = (2 K + 2 S + K) * 4 T bytes against SURVEY 8(d)'s (K + K + 2 S) * 4 T: 1.13 x at cfg3 (K = 72, S = 201).
+// Limits: S <= 256 states, K <= 128 classes; anything else takes the four-launch path in ctc.cu.
+// What bounds it (B200, cfg3 geometry, T = 1000; profiles/r02_ctc_fused.jsonl): not HBM but instruction issue and the
+// T-step chain -- sweeps alone 0.23 ms, helper warps alone 0.22 ms, together 0.37 ms + 0.08 ms of setup / launch / cost
+// read-back for the 16 utterances of a minibatch (0.45 ms against 0.53 ms for the four launches; 256 utterances 0.88 ms
+// against 1.24 ms).  Past ~4 utterances per SM the warp-per-sweep form of the four-launch path issues fewer instructions
+// per state (no barrier, no idle lanes) and stays ahead (2048 utterances: 6.3 ms against 7.7 ms), so the dispatch in
+// compute_ctc_loss keeps it there.
+#pragma once
+
+constexpr int CF_TB = 16;                // time steps per block (helper warps work one block ahead / behind)
+constexpr int CF_KMAX = 128;
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+// log(exp(a) + exp(b)) with the SFU forms spelled out (ex2.approx.ftz / lg2.approx.ftz: the same two instructions __expf /
+// __logf issue, without their denormal-range fix-up -- exp(-d) below 2^-126 adds nothing to 1 anyway).  Both arguments at
+// -inf make the difference NaN; the final select returns -inf for that case, so no operand needs guarding.
+__device__ __forceinline__ float log_plus_sfu(float p1, float p2) {
+  const float m = fmaxf(p1, p2);
+  const float d = fabsf(p1 - p2) * -1.4426950408889634f;
+  float e, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+  const float r = fmaf(l, 0.6931471805599453f, m);
+  return (m == neg_inf()) ? neg_inf() : r;
+}
+
+struct CfSmem {
+  int SP, K;
+  __host__ __device__ size_t ints() const { return (size_t)4 * SP + (K + 1) + 8; }   // lab, ps, pe, cls_list, cls_start, scalars
+  __host__ __device__ size_t floats(int hw) const {
+    return (size_t)2 * 2 * (SP + 4) + (size_t)3 * 2 * CF_TB * K + (size_t)2 * 2 * CF_TB * SP + (size_t)hw * SP + 32;
+  }
+  __host__ __device__ size_t bytes(int hw) const { return (ints() + floats(hw)) * 4; }
+};
+
+// G: sweep threads per direction (>= number of states); HW: helper warps (>= 2)
+template <int G, int HW>
+__global__ void __launch_bounds__(2 * G + 32 * HW, 1)
+ctc_fused_kernel(const float* __restrict__ acts, float* __restrict__ grads, float* __restrict__ spill_all, float* costs_dev,
+                 int* valid_dev, const int* flat_labels, const int* label_off, const int* label_len, const int* in_len,
+                 int K, int mb, int maxT, int maxS, int SP) {
+  extern __shared__ __align__(16) int cf_smem[];
+  const int n = blockIdx.x;
+  const int T = in_len[n], L = label_len[n], S = 2 * L + 1;
+  const int tid = threadIdx.x;
+  int* lab = cf_smem;                      // [SP] labels with blanks
+  int* s_inc = lab + SP;                   // [SP] prefix sums of the reference's s_inc (L + repeats + 1 entries <= 2 L <= SP)
+  int* e_inc = s_inc + SP;                 // [SP] prefix sums of e_inc
+  int* cls_list = e_inc + SP;              // [SP] non-blank states grouped by label, ascending state order
+  int* cls_start = cls_list + SP;          // [K + 1]
+  int* scal = cls_start + (K + 1);         // [0] repeats
+  float* prevbuf = reinterpret_cast<float*>(scal + 8);   // [2 dirs][2][SP + 4]: state i at index i + 2, two -inf guards on either side
+  float* ring = prevbuf + 2 * 2 * (SP + 4);          // [3][2][TB][K] log-softmax rows
+  float* rows = ring + (size_t)3 * 2 * CF_TB * K;    // [2][2][TB][SP] sweep rows of the current / previous block
+  float* abst = rows + (size_t)2 * 2 * CF_TB * SP;   // [HW][SP] helper staging
+  float* red = abst + (size_t)HW * SP;               // [32]
+
+  const int* labels = flat_labels + label_off[n];
+  // ---- setup (cpu_ctc.h:119-155): s_inc / e_inc / repeats sequentially, labels with blanks, per-label state lists
+  // The reference walks its valid-state window with the increments s_inc / e_inc (cpu_ctc.h:119-155, used at :235-243 and
+  // :287-303).  Here the increments are kept as PREFIX SUMS ps[j] = s_inc[0] + .. + s_inc[j-1], pe[j] likewise, so that the
+  // window of any time step is two table reads instead of a walk (see window_alpha / window_beta below).
+  if (tid == 0) {
+    int e_counter = 0, s_counter = 0, repeats = 0, ssum = 0, esum = 0;
+    s_inc[0] = 0; e_inc[0] = 0;
+    ssum += 1; s_inc[++s_counter] = ssum;
+    for (int i = 1; i < L; ++i) {
+      if (labels[i - 1] == labels[i]) {
+        ssum += 1; s_inc[++s_counter] = ssum; ssum += 1; s_inc[++s_counter] = ssum;
+        esum += 1; e_inc[++e_counter] = esum; esum += 1; e_inc[++e_counter] = esum;
+        ++repeats;
+      } else {
+        ssum += 2; s_inc[++s_counter] = ssum;
+        esum += 2; e_inc[++e_counter] = esum;
+      }
+    }
+    esum += 1; e_inc[++e_counter] = esum;
+    scal[0] = repeats;
+  }
+  for (int i = tid; i < S; i += blockDim.x) lab[i] = (i & 1) ? labels[i >> 1] : 0;
+  for (int k = tid; k <= K; k += blockDim.x) cls_start[k] = 0;
+  for (int i = tid; i < 2 * 2 * (SP + 4); i += blockDim.x) prevbuf[i] = neg_inf();
+  __syncthreads();
+  for (int i = tid; i < L; i += blockDim.x) atomicAdd(&cls_start[labels[i] + 1], 1);
+  __syncthreads();
+  if (tid == 0) for (int k = 0; k < K; ++k) cls_start[k + 1] += cls_start[k];
+  __syncthreads();
+  for (int i = tid; i < L; i += blockDim.x) {            // position among equal labels = number of earlier equal labels
+    const int l = labels[i];
+    int rank = 0;
+    for (int j = 0; j < i; ++j) rank += (labels[j] == l);
+    cls_list[cls_start[l] + rank] = 2 * i + 1;
+  }
+  __syncthreads();
+  const int repeats = scal[0];
+  if (L + repeats > T) {                   // cpu_ctc.h:193-195: cost 0, gradient untouched
+    if (tid == 0) { costs_dev[n] = 0.f; valid_dev[n] = 0; }
+    return;
+  }
+
+  float* spill = spill_all + (size_t)n * maxT * maxS;
+  const int nblocks = (T + CF_TB - 1) / CF_TB;
+  const int role = tid < G ? 0 : (tid < 2 * G ? 1 : 2);  // alpha sweep, beta sweep, helper
+  // row r is reached by alpha at step r and by beta at step T-1-r: alpha is first (and spills it) iff r <= t_sp
+  const int t_sp = (T - 1) / 2;
+
+  // ---- sweep state
+  const int i = role == 0 ? tid : tid - G;               // state of a sweep thread
+  const bool st_live = role < 2 && i < S;
+  const int il = st_live ? i : 0;                        // threads past the last state compute on state 0 and store nothing
+  const int lab_i = lab[il];
+  bool skip = false;                                     // third term: across a blank between two DIFFERENT labels
+  if (st_live && (i & 1)) {
+    if (role == 0) skip = i >= 3 && lab_i != lab[i - 2];
+    else skip = i + 2 < S && lab_i != lab[i + 2];
+  }
+  float* prev = prevbuf + (size_t)(role == 1 ? 2 : 0) * (SP + 4) + 2 + il;   // this thread's own state in the row
+  float* cur = prev + (SP + 4);
+
+  // ---- helper state
+  const int hw = (tid - 2 * G) >> 5, lane = tid & 31;
+  float logZ = 0.f;
+  bool have_logZ = false;
+  const int kstar = T - 1 - t_sp;          // the normaliser is taken at row t_sp: the first row beta reaches second (step kstar)
+  constexpr int KS = CF_KMAX / 32;
+  constexpr int IPW = (2 * CF_TB + HW - 1) / HW;         // (direction, step) items per helper warp and block
+  // valid-state windows [start, end) in closed form.  With R0 = S/2 + repeats - T (<= 0) and cap = S/2 + repeats:
+  //   alpha (:235-243): start(t) = ps[max(0, R0 + t + 1)],  end(t) = end0 + pe[min(t, cap)]
+  //   beta  (:287-303): start(t) = start0 - (ps[cap] - ps[max(0, R0 + t + 1)]),  end(t) = end0 - (pe[min(cap, T - 1)] - pe[min(cap, t)])
+  const int R0 = (S / 2) + repeats - T, cap = (S / 2) + repeats;
+  const int a_end0 = S > 1 ? 2 : 1;
+  const int b_start0 = (S > 1 ? (S - 2) : 0) - s_inc[cap];
+  const int b_end0 = ((T > cap) ? S : S - 1) - e_inc[min(cap, T - 1)];
+  for (int p = 0; p <= nblocks + 1; ++p) {
+    if (role == 2) {
+      if (p < nblocks) {
+        // ---- (i) log-softmax rows of block p for both directions
+        float xv[IPW][KS];
+#pragma unroll
+        for (int u = 0; u < IPW; ++u) {                  // all loads of the warp's rows first: one HBM latency per block
+          const int item = hw + u * HW, kk = item >> 1, dir = item & 1, k = p * CF_TB + kk;
+          const bool on = item < 2 * CF_TB && k < T;
+          const int r = dir == 0 ? k : T - 1 - k;
+          const float* x = acts + ((size_t)(on ? r : 0) * mb + n) * K;
+#pragma unroll
+          for (int q = 0; q < KS; ++q) { const int c = lane + 32 * q; xv[u][q] = (on && c < K) ? __ldg(x + c) : neg_inf(); }
+        }
+#pragma unroll
+        for (int u = 0; u < IPW; ++u) {
+          const int item = hw + u * HW, kk = item >> 1, dir = item & 1, k = p * CF_TB + kk;
+          if (item < 2 * CF_TB && k < T) {               // warp-uniform
+            float mx = neg_inf();
+#pragma unroll
+            for (int q = 0; q < KS; ++q) mx = fmaxf(mx, xv[u][q]);
+            mx = warp_max(mx);
+            float den = 0.f;
+            float ex[KS];
+#pragma unroll
+            for (int q = 0; q < KS; ++q) { ex[q] = expf(xv[u][q] - mx); den += ex[q]; }      // exp(-inf) = 0 for the padding classes
+            den = warp_sum(den);
+            const float lden = logf(den);
+            float* out = ring + ((size_t)((p % 3) * 2 + dir) * CF_TB + kk) * K;
+            // log p = (x - max) - log(sum); a probability that underflows to 0 has log p = -inf, as log(probs) in the reference
+#pragma unroll
+            for (int q = 0; q < KS; ++q) { const int c = lane + 32 * q; if (c < K) out[c] = ex[q] == 0.f ? neg_inf() : (xv[u][q] - mx) - lden; }
+          }
+        }
+      }
+      // ---- (ii) gradient rows of block p - 2: the rows a sweep reached second, combined with the spilled counterpart
+      if (p >= 2) {
+        const int q0 = p - 2;
+        float* wst = abst + (size_t)hw * SP;
+        if (!have_logZ && kstar / CF_TB == q0) {
+          // log Z at the middle row t_sp: beta row from shared memory, alpha row from the spill
+          const int kk = kstar - q0 * CF_TB;
+          const float* own = rows + ((size_t)((q0 & 1) * 2 + 1) * CF_TB + kk) * SP;
+          const float* lpr = ring + ((size_t)((q0 % 3) * 2 + 1) * CF_TB + kk) * K;
+          const float* oth = spill + (size_t)t_sp * maxS;
+          float tv[8];
+          float mx = neg_inf();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int s = lane + 32 * j;
+            float v = neg_inf();
+            if (s < S) {
+              const float a = __ldcg(oth + s), b = own[s];
+              if (a != neg_inf() && b != neg_inf()) v = a + b - lpr[lab[s]];
+            }
+            tv[j] = v; mx = fmaxf(mx, v);
+          }
+          mx = warp_max(mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum += (tv[j] == neg_inf()) ? 0.f : expf(tv[j] - mx);
+          sum = warp_sum(sum);
+          logZ = (mx == neg_inf()) ? neg_inf() : mx + logf(sum);
+          have_logZ = true;
+        }
+        for (int u = 0; u < IPW; ++u) {
+          const int item = hw + u * HW, kk = item >> 1, dir = item & 1, k = q0 * CF_TB + kk;
+          if (item >= 2 * CF_TB || k >= T) continue;     // warp-uniform
+          const int r = dir == 0 ? k : T - 1 - k;
+          if ((dir == 0) == (r <= t_sp)) continue;       // this sweep was first on the row: it only spilled it
+          const float* own = rows + ((size_t)((q0 & 1) * 2 + dir) * CF_TB + kk) * SP;
+          const float* oth = spill + (size_t)r * maxS;
+          const float* lpr = ring + ((size_t)((q0 % 3) * 2 + dir) * CF_TB + kk) * K;
+          // per-label sums of alpha * beta (cpu_ctc.h:296-301) as max-shifted sums: w[i] = exp(alpha_i + beta_i - M) into
+          // the staging row, then o[c] = M + log(sum of w over the states of label c); a state more than ~87 below the
+          // row's maximum adds nothing (its posterior is below 1e-38)
+          float tv[8];
+          float M = neg_inf();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int s = lane + 32 * j;
+            tv[j] = s < S ? __ldcg(oth + s) + own[s] : neg_inf();
+            M = fmaxf(M, tv[j]);
+          }
+          M = warp_max(M);
+          float bs = 0.f;                                // blank: all even states; they sit in the even lanes
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int s = lane + 32 * j;
+            const float w = (tv[j] == neg_inf()) ? 0.f : __expf(tv[j] - M);
+            if (s < S) wst[s] = w;
+            bs += (lane & 1) ? 0.f : w;
+          }
+          bs = warp_sum(bs);
+          __syncwarp();
+          float* g = grads + ((size_t)r * mb + n) * K;
+#pragma unroll
+          for (int q = 0; q < KS; ++q) {
+            const int c = lane + 32 * q;
+            if (c < K) {
+              float sum = (c == 0) ? bs : 0.f;
+              const int e1 = cls_start[c + 1];
+              for (int e = cls_start[c]; e < e1; ++e) sum += wst[cls_list[e]];
+              const float o = (sum > 0.f && M != neg_inf()) ? M + __logf(sum) : neg_inf();
+              const float lpk = lpr[c];
+              const float pk = expf(lpk);
+              g[c] = (o == 0.0f || o == neg_inf() || pk == 0.0f) ? pk : pk - __expf(o - lpk - logZ);
+            }
+          }
+          __syncwarp();                                  // the staging row is rewritten by the warp's next item
+        }
+      }
+    } else if (p >= 1 && p <= nblocks) {
+      // ---- sweeps over block p - 1: one state per thread, one named barrier per step
+      const int q0 = p - 1;
+      const float* lpp = ring + ((size_t)((q0 % 3) * 2 + role) * CF_TB) * K + lab_i;
+      float* rowp = rows + ((size_t)((q0 & 1) * 2 + role) * CF_TB) * SP + il;
+      const int kend = min(CF_TB, T - q0 * CF_TB);
+      int kk = 0;
+      if (role == 0) {
+        float* spp = spill + (size_t)q0 * CF_TB * maxS + il;
+        if (q0 == 0) {                                   // t = 0: the window states start at their emission
+          const int wx = s_inc[max(0, R0 + 1)], wy = a_end0;
+          const float v = (i >= wx && i < wy) ? lpp[0] : neg_inf();
+          if (st_live) { cur[0] = v; rowp[0] = v; spp[0] = v; }
+          named_bar_sync(1, G);
+          float* tmp = prev; prev = cur; cur = tmp;
+          kk = 1;
+        }
+        for (; kk < kend; ++kk) {
+          const int t = q0 * CF_TB + kk;
+          const int wx = s_inc[max(0, R0 + t + 1)], wy = a_end0 + e_inc[min(t, cap)];
+          const float a = prev[0], b = prev[-1], c = prev[-2];
+          const float s3 = log_plus_sfu(log_plus_sfu(a, b), skip ? c : neg_inf());
+          const float v = (i >= wx && i < wy) ? s3 + lpp[kk * K] : neg_inf();
+          if (st_live) {
+            cur[0] = v;
+            rowp[kk * SP] = v;
+            if (t <= t_sp) spp[(size_t)kk * maxS] = v;
+          }
+          named_bar_sync(1, G);
+          float* tmp = prev; prev = cur; cur = tmp;
+        }
+        if (p == nblocks) {
+          // log-likelihood over the final window (the reference adds in ascending i; the tree covers the same terms)
+          const int wx = s_inc[max(0, R0 + T)], wy = a_end0 + e_inc[min(T - 1, cap)];
+          float ll = (st_live && i >= wx && i < wy) ? prev[0] : neg_inf();
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ll = log_plus(ll, __shfl_xor_sync(0xffffffffu, ll, o));
+          if ((tid & 31) == 0) red[tid >> 5] = ll;
+          named_bar_sync(1, G);
+          if (tid == 0) {
+            float r0 = red[0];
+            for (int w2 = 1; w2 < G / 32; ++w2) r0 = log_plus(r0, red[w2]);
+            costs_dev[n] = -r0; valid_dev[n] = 1;
+          }
+        }
+      } else {
+        const int t0 = T - 1 - q0 * CF_TB;                 // row of step kk = 0 of this block; rows descend
+        float* spp = spill + (size_t)t0 * maxS + il;
+        if (q0 == 0) {                                   // t = T - 1
+          const int wx = b_start0 + s_inc[max(0, R0 + T)], wy = b_end0 + e_inc[min(cap, T - 1)];
+          const float v = (i >= wx && i < wy) ? lpp[0] : neg_inf();
+          if (st_live) { cur[0] = v; rowp[0] = v; if (t0 > t_sp) spp[0] = v; }
+          named_bar_sync(2, G);
+          float* tmp = prev; prev = cur; cur = tmp;
+          kk = 1;
+        }
+        for (; kk < kend; ++kk) {
+          const int t = t0 - kk;
+          const int wx = b_start0 + s_inc[max(0, R0 + t + 1)], wy = b_end0 + e_inc[min(cap, t)];
+          const int endloop = (wy == S) ? wy - 1 : wy;
+          const float a = prev[0], n1 = prev[1], n2 = prev[2];
+          const bool in_loop = i >= wx && i < endloop;
+          const bool in_last = wy == S && i == S - 1;
+          // outside the window the reference leaves the old value in place; the last state only adds the emission
+          const float s2 = log_plus_sfu(a, in_loop ? n1 : neg_inf());
+          const float s3 = log_plus_sfu(s2, (in_loop && skip) ? n2 : neg_inf());
+          const float v = (in_loop || in_last) ? s3 + lpp[kk * K] : a;
+          const float masked = (in_loop || in_last) ? v : neg_inf();
+          if (st_live) {
+            cur[0] = v;
+            rowp[kk * SP] = masked;
+            if (t > t_sp) *(spp - (size_t)kk * maxS) = masked;
+          }
+          named_bar_sync(2, G);
+          float* tmp = prev; prev = cur; cur = tmp;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
