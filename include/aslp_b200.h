@@ -65,6 +65,23 @@ int aslp_stream_wait_event(aslp_stream_t s, void* event);   /* later work on s s
 int aslp_event_destroy(void* event);                        /* NULL is fine */
 int aslp_scratch_release(aslp_stream_t s);                  /* frees the library's per-stream scratch arena before a stream is destroyed */
 int aslp_event_sync(void* event);                           /* the host waits for `event` (a pinned staging slot is free again) */
+/* Static-shape step replay.  The reference enqueues every kernel of every minibatch from the host and device-syncs after
+ * most of them (CU_SAFE_CALL, src/aslp-cudamatrix/cu-common.h:38-45); at a 256-frame DNN minibatch (BASELINE cfg1) the
+ * step is then bound by host enqueue time, not by the device.  A step whose shapes, pointers and scalars repeat is
+ * captured once from the stream it is enqueued on and replayed as one executable graph.
+ *   aslp_graph_begin(s)                   later work enqueued on s (and on streams that join it through events) is recorded, not run
+ *   aslp_graph_end(s, &exec, &kernels)    ends the recording and instantiates it; non-zero (exec = NULL) when the recording
+ *                                         was invalidated -- nothing ran, the caller enqueues the step again without recording
+ *   aslp_graph_launch(exec, s), aslp_graph_destroy(exec)
+ *   aslp_alloc_epoch()                    changes whenever device memory has been released (aslp_free, scratch regrowth): a
+ *                                         recording is only valid while the epoch it was made in lasts
+ *   aslp_count_launches(n)                adds the kernels of a replay to the launch counter (aslp_launch_count) */
+int aslp_graph_begin(aslp_stream_t s);
+int aslp_graph_end(aslp_stream_t s, void** exec, int* kernel_nodes);
+int aslp_graph_launch(void* exec, aslp_stream_t s);
+int aslp_graph_destroy(void* exec);
+unsigned long long aslp_alloc_epoch(void);
+int aslp_count_launches(unsigned long long n);
 
 /* ---- dense contraction: CuMatrixBase::AddMatMat (cu-matrix.cc:1027-1062) ----
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C  (+ bias[n] broadcast over rows)
@@ -87,6 +104,25 @@ int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
               float beta, float* C, int ldc, const float* bias, float clip,
               int precision, void* workspace, size_t workspace_bytes);
 
+/* aslp_gemm with what the components do to the product right afterwards folded in (SURVEY 2.4's fusion targets):
+ *   act         0 none, 1 + ASLP_ACT_* : C = f(C)            Affine followed by Sigmoid / Tanh / ReLU (nnet-activation.h:153-199, 275-303)
+ *   dact_y      C = f'(y) * C with y the activation's OUTPUT  the DiffSigmoid / DiffTanh / ReLU mask the activation's Backpropagate
+ *                                                             applies to what the next layer's backward product delivers
+ *   update_w    W -= update_lr * C after C = beta*C + alpha*AB the SGD apply behind the weight-gradient product, C = *_corr_
+ *                                                             (nnet-affine-transform.h:210,237)
+ * order: product, beta, bias, clip, act, dact, store, update.  Folded into the split-K reduce pass when the product takes it (the
+ * few-tile shapes of 256- to 1000-frame minibatches, where every saved launch counts); otherwise the same steps run as
+ * launches of their own behind the product, so the result does not depend on the path. */
+typedef struct {
+  int act;
+  const float* dact_y; int dact_ldy; int dact_kind;      /* ASLP_ACT_* of the activation whose derivative is applied; y may not alias C */
+  float* update_w; int update_ldw; float update_lr;
+} aslp_gemm_epilogue_t;
+int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
+                 float alpha, const float* A, int lda, const float* B, int ldb,
+                 float beta, float* C, int ldc, const float* bias, float clip,
+                 int precision, void* workspace, size_t workspace_bytes, const aslp_gemm_epilogue_t* epi);
+
 /* ---- pointwise / reductions (cu-kernels.cu:1802-1858, 700-760, 416-437, 1346-1505) ---- */
 enum { ASLP_ACT_SIGMOID = 0, ASLP_ACT_TANH = 1, ASLP_ACT_RELU = 2 };
 /* Sigmoid/Tanh/ReLU::PropagateFnc (src/aslp-nnet/nnet-activation.h:153-199,276-298) */
@@ -105,6 +141,9 @@ int aslp_axpby(aslp_stream_t s, float* dst, int ldd, const float* src, int lds, 
 int aslp_add_vec_to_rows(aslp_stream_t s, float* dst, int ldd, int rows, int cols, const float* vec, float alpha, float beta);
 /* vec[c] = alpha * sum_r mat[r,c] + beta*vec[c], then optional clip (CuVector::AddRowSumMat, cu-vector.cc:1145-1166) */
 int aslp_col_sum(aslp_stream_t s, float* vec, const float* mat, int ldm, int rows, int cols, float alpha, float beta, float clip);
+/* bias gradient and bias update of an affine layer in one launch (nnet-affine-transform.h:211,237-238):
+ * corr[c] = momentum * corr[c] + sum_r diff[r,c];  bias[c] -= lr * corr[c] */
+int aslp_bias_grad_update(aslp_stream_t s, float* bias, float* corr, const float* diff, int ldd, int rows, int cols, float momentum, float lr);
 /* vec[c] = alpha * sum_r a[r,c]*b[r,c] + beta*vec[c], optional clip (AddDiagMatMat(kTrans,kNoTrans), cu-kernels.cu:992; peephole grads) */
 int aslp_col_dot(aslp_stream_t s, float* vec, const float* a, int lda, const float* b, int ldb, int rows, int cols, float alpha, float beta, float clip);
 /* clamp to [lo, hi] (ApplyFloor + ApplyCeiling) */

@@ -23,6 +23,8 @@ int aslp_nnet_srand(int seed);                        /* std::srand(seed) before
 int aslp_nnet_set_gemm_precision(int precision);      /* ASLP_GEMM_3XTF32 (default) / ASLP_GEMM_TF32 / ASLP_GEMM_FP32 */
 int aslp_nnet_device_sync(void);
 unsigned long long aslp_nnet_launch_count(void);
+/* training steps of aslp_train_step_xent that ran as a replayed recording (host/nnet-train-step.h) since the library was loaded */
+long long aslp_nnet_step_replays(void);
 /* CUDA events on the host layer's compute stream (the stream every kernel of this library is launched on) */
 int aslp_nnet_event_record(int slot);                 /* slot in [0, 16) */
 int aslp_nnet_event_elapsed_ms(int slot_a, int slot_b, float* ms);   /* synchronises on slot_b */

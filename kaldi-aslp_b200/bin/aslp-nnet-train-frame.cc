@@ -3,6 +3,7 @@
 // With --worker-type it is the worker of src/aslp-parallelbin/aslp-nnet-train-frame-worker.cc (bin/worker-opts.h).
 #include <memory>
 #include "nnet-nnet.h"
+#include "nnet-train-step.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
 #include "nnet-trnopts.h"
@@ -68,12 +69,20 @@ int main(int argc, char* argv[]) {
     const CuMatrixBase<BaseFloat>* nnet_in = nullptr;
     const Posterior* nnet_tgt = nullptr;
     CuMatrix<BaseFloat> nnet_out, obj_diff;
+    XentTrainStep train_step;                              // the same three calls; a repeating minibatch shape is recorded once and replayed
+    Xent* xent = dynamic_cast<Xent*>(loss_holder.get());
+    Vector<BaseFloat> ones;
     while (!reader.Done()) {
       if (!reader.ReadData(&nnet_in, &nnet_tgt)) continue;
-      if (!crossvalidate) nnet.Propagate(*nnet_in, &nnet_out);
-      else nnet.Feedforward(*nnet_in, &nnet_out);
-      loss.Eval(nnet_out, *nnet_tgt, &obj_diff);
-      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      if (!crossvalidate && xent != nullptr) {
+        if (ones.Dim() != nnet_in->NumRows()) { ones.Resize(nnet_in->NumRows()); for (int32 r = 0; r < ones.Dim(); ++r) ones(r) = 1.0f; }   // LossItf::Eval's unit frame weights
+        train_step.Run(&nnet, xent, *nnet_in, ones, *nnet_tgt);
+      } else {
+        if (!crossvalidate) nnet.Propagate(*nnet_in, &nnet_out);
+        else nnet.Feedforward(*nnet_in, &nnet_out);
+        loss.Eval(nnet_out, *nnet_tgt, &obj_diff);
+        if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      }
       total_frames += nnet_in->NumRows();
       report_frames += nnet_in->NumRows();
       wopts.Progress(nnet_in->NumRows());

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include "batch-feeder.h"
 #include "nnet-nnet.h"
+#include "nnet-train-step.h"
 #include "nnet-loss.h"
 #include "nnet-randomizer.h"
 #include "nnet-trnopts.h"
@@ -114,6 +115,8 @@ int main(int argc, char* argv[]) {
       }
       return false;
     };
+    XentTrainStep train_step;
+    Xent* xent_impl = dynamic_cast<Xent*>(loss_holder.get());
     BatchFeeder<UttBatch> feeder(fill, /*attach_device=*/false);
     while (UttBatch* b = feeder.Next()) {
       feats.Resize(b->mat.NumRows(), b->mat.NumCols(), kUndefined);
@@ -122,11 +125,17 @@ int main(int argc, char* argv[]) {
       if (nnet_transf.NumComponents() > 0) { nnet_transf.Feedforward(feats, &feats_transf); net_in = &feats_transf; }
       trn_opts.learn_rate = norm_lr / 1024.0;             // quirk (:201): a fixed divisor, not the utterance length
       nnet.SetTrainOptions(trn_opts);
-      if (!crossvalidate) nnet.Propagate(*net_in, &nnet_out);
-      else nnet.Feedforward(*net_in, &nnet_out);
-      xent.Eval(b->weights, nnet_out, b->targets, &obj_diff);
-      feeder.Release(b);                                  // Xent::Eval has uploaded weights and targets
-      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      if (!crossvalidate && xent_impl != nullptr) {
+        // Propagate + Xent::Eval + Backpropagate; a step shape that repeats is recorded once and replayed (nnet-train-step.h)
+        train_step.Run(&nnet, xent_impl, *net_in, b->weights, b->targets);
+        feeder.Release(b);                                // weights and targets are staged
+      } else {
+        if (!crossvalidate) nnet.Propagate(*net_in, &nnet_out);
+        else nnet.Feedforward(*net_in, &nnet_out);
+        xent.Eval(b->weights, nnet_out, b->targets, &obj_diff);
+        feeder.Release(b);                                // the loss has uploaded weights and targets
+        if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      }
       num_done++;
       total_frames += net_in->NumRows();
       report_frames += net_in->NumRows();

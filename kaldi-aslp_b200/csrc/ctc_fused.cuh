@@ -13,17 +13,18 @@
 //   * because the gradient of the rows the sweeps reach second is formed before either sweep has finished, the
 //     normaliser log Z is taken where the sweeps meet: log Z = logsumexp_i (alpha_t[i] + beta_t[i] - log p_t[label(i)]) at
 //     the middle row (both recursions include the emission of their own row, cpu_ctc.h:252,329).  It equals the
-//     reference's log-likelihood (the last alpha row, :255-261 -- which is still what `costs` returns) up to fp32 rounding
-//     of sums of magnitude |cost|, the same resolution the alpha-beta products themselves have.
-// HBM per utterance: activations read twice (once per direction) + [T][S] spill written and read once + gradient written
-// = (2 K + 2 S + K) * 4 T bytes against SURVEY 8(d)'s (K + K + 2 S) * 4 T: 1.13 x at cfg3 (K = 72, S = 201).
+//     reference's log-likelihood (the last alpha row, :255-261 -- which is what `costs` returns) up to fp32 rounding of
+//     sums of magnitude |cost|; a closing pass rescales every row to the reference's normaliser once it is known.
+// HBM per utterance: activations read three times (once per direction, once in the closing pass) + [T][S] spill written and
+// read once + gradient written, re-read and re-written = (3 K + 2 S + 3 K) * 4 T bytes against SURVEY 8(d)'s
+// (K + K + 2 S) * 4 T: 1.53 x at cfg3 (K = 72, S = 201) -- against 3 x for the four launches.
 // Limits: S <= 256 states, K <= 128 classes; anything else takes the four-launch path in ctc.cu.
 // What bounds it (B200, cfg3 geometry, T = 1000; profiles/r02_ctc_fused.jsonl): not HBM but instruction issue and the
-// T-step chain -- sweeps alone 0.23 ms, helper warps alone 0.22 ms, together 0.37 ms + 0.08 ms of setup / launch / cost
-// read-back for the 16 utterances of a minibatch (0.45 ms against 0.53 ms for the four launches; 256 utterances 0.88 ms
-// against 1.24 ms).  Past ~4 utterances per SM the warp-per-sweep form of the four-launch path issues fewer instructions
-// per state (no barrier, no idle lanes) and stays ahead (2048 utterances: 6.3 ms against 7.7 ms), so the dispatch in
-// compute_ctc_loss keeps it there.
+// T-step chain -- sweeps alone 0.23 ms, helper warps alone 0.22 ms, together 0.37 ms + 0.03 ms closing pass + 0.08 ms of
+// setup / launch / cost read-back for the 16 utterances of a minibatch (0.48 ms against 0.53 ms for the four launches; 256
+// utterances 0.94 ms against 1.24 ms).  Past ~4 utterances per SM the warp-per-sweep form of the four-launch path issues
+// fewer instructions per state (no barrier, no idle lanes) and stays ahead (2048 utterances: 6.3 ms against 8.3 ms), so the
+// dispatch in compute_ctc_loss keeps it there.
 #pragma once
 
 constexpr int CF_TB = 16;                // time steps per block (helper warps work one block ahead / behind)
@@ -214,6 +215,7 @@ ctc_fused_kernel(const float* __restrict__ acts, float* __restrict__ grads, floa
           sum = warp_sum(sum);
           logZ = (mx == neg_inf()) ? neg_inf() : mx + logf(sum);
           have_logZ = true;
+          if (hw == 0 && lane == 0) red[16] = logZ;
         }
         for (int u = 0; u < IPW; ++u) {
           const int item = hw + u * HW, kk = item >> 1, dir = item & 1, k = q0 * CF_TB + kk;
@@ -305,6 +307,7 @@ ctc_fused_kernel(const float* __restrict__ acts, float* __restrict__ grads, floa
             float r0 = red[0];
             for (int w2 = 1; w2 < G / 32; ++w2) r0 = log_plus(r0, red[w2]);
             costs_dev[n] = -r0; valid_dev[n] = 1;
+            red[17] = r0;                                 // the reference's normaliser, for the closing pass below
           }
         }
       } else {
@@ -341,5 +344,48 @@ ctc_fused_kernel(const float* __restrict__ acts, float* __restrict__ grads, floa
       }
     }
     __syncthreads();
+  }
+
+  // ---- closing pass: the gradient rows were formed with the normaliser of the middle row, log Z_mid; the reference divides
+  // by the likelihood of the LAST alpha row (cpu_ctc.h:255-261, :305), log Z_end.  The two are the same number up to the fp32
+  // rounding accumulated by T/2 recursion steps -- a few ulp(|cost|), i.e. up to ~3e-3 relative on the posteriors at
+  // T = 1000 -- and the reference's posteriors carry exactly the rounding of ITS normaliser.  To stay within the parity
+  // bound of the four-launch path every row is therefore rescaled once both sweeps are done:
+  //     grad = p - post * exp(log Z_mid - log Z_end) = grad_mid * c + p * (1 - c),   c = exp(log Z_mid - log Z_end)
+  // with p recomputed from the activation row (all warps of the CTA, one row per warp and pass).
+  {
+    const float lz_mid = red[16], lz_end = red[17];
+    const bool finite = lz_mid > -3.0e38f && lz_mid < 3.0e38f && lz_end > -3.0e38f && lz_end < 3.0e38f;
+    if (finite && lz_mid != lz_end) {
+      const float c = expf(lz_mid - lz_end), omc = 1.0f - c;
+      const int nwarps = (2 * G + 32 * HW) >> 5, wid = tid >> 5, ln = tid & 31;
+      for (int t0 = wid * 2; t0 < T; t0 += nwarps * 2) {   // two rows per warp and pass: their loads overlap
+        float xv[2][KS], gv[2][KS];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int t = t0 + u;
+          const float* x = acts + ((size_t)(t < T ? t : t0) * mb + n) * K;
+          const float* g = grads + ((size_t)(t < T ? t : t0) * mb + n) * K;
+#pragma unroll
+          for (int q = 0; q < KS; ++q) { const int k = ln + 32 * q; xv[u][q] = k < K ? __ldg(x + k) : neg_inf(); gv[u][q] = k < K ? g[k] : 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int t = t0 + u;
+          if (t >= T) break;                             // warp-uniform
+          float mx = neg_inf();
+#pragma unroll
+          for (int q = 0; q < KS; ++q) mx = fmaxf(mx, xv[u][q]);
+          mx = warp_max(mx);
+          float ex[KS], den = 0.f;
+#pragma unroll
+          for (int q = 0; q < KS; ++q) { ex[q] = expf(xv[u][q] - mx); den += ex[q]; }
+          den = warp_sum(den);
+          float* g = grads + ((size_t)t * mb + n) * K;
+#pragma unroll
+          for (int q = 0; q < KS; ++q) { const int k = ln + 32 * q; if (k < K) g[k] = gv[u][q] * c + (ex[q] / den) * omc; }
+        }
+      }
+    }
   }
 }

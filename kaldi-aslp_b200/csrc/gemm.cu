@@ -297,6 +297,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           const int col = nb + sub_c;
           const int nvalid = p.N - col;         // > 0: columns col .. col+3 that exist
+          // beta: the old C values of the whole chunk are fetched first, all eight loads in flight together.  Loaded one by
+          // one inside the store loop below they serialise behind the stores (the compiler cannot prove that `dst` of one row
+          // is not the next row's source): 32 dependent HBM round trips per tile, which made the momentum weight-gradient
+          // product of a 256-frame minibatch take 30 us instead of 14.
+          float4 oldc[8];
+          const bool pre_beta = p.partial == nullptr && p.beta != 0.f && nvalid >= 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = m0 + q * 32 + it * 4 + sub_r;
+            oldc[it] = (pre_beta && row < p.M) ? *reinterpret_cast<const float4*>(p.C + (size_t)row * p.ldc + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + sub_r;
@@ -312,7 +323,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o.x *= p.alpha; o.y *= p.alpha; o.z *= p.alpha; o.w *= p.alpha;
                 if (nvalid >= 4) {
                   if (p.beta != 0.f) {
-                    const float4 old = *reinterpret_cast<const float4*>(dst);
+                    const float4 old = oldc[it];
                     o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
                   }
                   if (p.bias != nullptr) {
@@ -389,9 +400,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// split-K second phase: C = alpha * sum_z partial[z] + beta*C + bias, clip
+// extended epilogue of aslp_gemm_ex (include/aslp_b200.h): activation of the result, multiplication by the derivative of
+// an activation at its output y, and the SGD apply W -= lr * C -- each otherwise a launch of its own after the product
+struct EpiExt { int act; const float* dy; int ldy; int dkind; float* w; int ldw; float lr; };
+__device__ __forceinline__ float epi_act(int kind, float x) {        // kind - 1 = ASLP_ACT_*
+  if (kind == 1 + ASLP_ACT_SIGMOID) return ref_sigmoid(x);
+  if (kind == 1 + ASLP_ACT_TANH) return ref_tanh(x);
+  return fmaxf(x, 0.f);
+}
+__device__ __forceinline__ float epi_dact(int kind, float y, float e) {   // as act_bwd_kernel (pointwise.cu)
+  if (kind == ASLP_ACT_SIGMOID) return y * (1.0f - y) * e;
+  if (kind == ASLP_ACT_TANH) return (1.0f - y * y) * e;
+  return y > 0.f ? e : 0.f;
+}
+
+// split-K second phase: C = alpha * sum_z partial[z] + beta*C + bias, clip, then the extended epilogue
 __global__ void splitk_reduce_kernel(float* C, int ldc, const float* partial, int ldp, int splits, int M, int N,
-                                     float alpha, float beta, const float* bias, float clip) {
+                                     float alpha, float beta, const float* bias, float clip, EpiExt x) {
   const int n4 = (N + 3) / 4;
   const long long total = (long long)M * n4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -408,7 +433,10 @@ __global__ void splitk_reduce_kernel(float* C, int ldc, const float* partial, in
       if (beta != 0.f) v += beta * dst[j];
       if (bias != nullptr) v += bias[c + j];
       if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+      if (x.act != 0) v = epi_act(x.act, v);
+      if (x.dy != nullptr) v = epi_dact(x.dkind, x.dy[(size_t)r * x.ldy + c + j], v);
       dst[j] = v;
+      if (x.w != nullptr) { float* wp = x.w + (size_t)r * x.ldw + c + j; *wp = *wp + (-x.lr) * v; }
     }
   }
 }
@@ -608,7 +636,7 @@ int gemm_f16x3(cudaStream_t st, bool a_mn, bool b_mn, const EpiParams& p_in, con
     const long long total = (long long)M * ((N + 3) / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > aslp_num_sms() * 8) blocks = aslp_num_sms() * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.C, p.ldc, (const float*)workspace, (int)ldpart, splits, M, N, p.alpha, p.beta, p.bias, p.clip);
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.C, p.ldc, (const float*)workspace, (int)ldpart, splits, M, N, p.alpha, p.beta, p.bias, p.clip, EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f});
     ASLP_CHECK_LAUNCH();
   }
   return 0;
@@ -622,11 +650,14 @@ int pick_splits(int M, int N, int K) {
   const int tiles = aslp_div_up(M, BM) * aslp_div_up(N, BN);
   const int num_kb = aslp_div_up(K, BK);
   const int sms = aslp_num_sms();
-  if (tiles >= sms || num_kb < 16) return 1;
+  // (c) short K with few tiles (the products of a 256-frame minibatch: 16 .. 64 tiles, 8 .. 14 k-blocks): still split, down to
+  // two k-blocks per item -- unsplit they leave 84 .. 132 SMs idle and a tile's whole k chain on one SM
+  if (tiles >= sms || num_kb < 4) return 1;
   int splits = aslp_div_up(2 * sms, tiles);
   const int by_chain = aslp_div_up(num_kb, 32);
   if (by_chain > splits) splits = by_chain;
-  if (splits > num_kb / 4) splits = num_kb / 4;
+  const int by_kb = num_kb >= 16 ? num_kb / 4 : num_kb / 2;
+  if (splits > by_kb) splits = by_kb;
   if (splits > 32) splits = 32;
   if (splits < 1) splits = 1;
   const int per = aslp_div_up(num_kb, splits);     // make every split non-empty
@@ -656,10 +687,12 @@ size_t aslp_gemm_workspace_bytes(int M, int N, int K) {
   return (size_t)splits * M * ldp * sizeof(float);
 }
 
-int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
-              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
-              void* workspace, size_t workspace_bytes) {
+// `ext` != NULL: fold the extended epilogue into the split-K reduce when the product takes that path (*ext_done = true)
+static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
+                     const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
+                     void* workspace, size_t workspace_bytes, const EpiExt* ext, bool* ext_done) {
   cudaStream_t st = (cudaStream_t)s;
+  if (ext_done != nullptr) *ext_done = false;
   ASLP_REQUIRE(M >= 0 && N >= 0 && K >= 0);
   if (M == 0 || N == 0) return 0;
   ASLP_REQUIRE(A != nullptr && B != nullptr && C != nullptr);
@@ -731,9 +764,35 @@ int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, fl
     const long long total = (long long)M * ((N + 3) / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > aslp_num_sms() * 8) blocks = aslp_num_sms() * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(C, ldc, (const float*)workspace, (int)ldp, splits, M, N, alpha, beta, bias, clip);
+    const EpiExt none{0, nullptr, 0, 0, nullptr, 0, 0.f};
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(C, ldc, (const float*)workspace, (int)ldp, splits, M, N, alpha, beta, bias, clip, ext != nullptr ? *ext : none);
     ASLP_CHECK_LAUNCH();
+    if (ext != nullptr && ext_done != nullptr) *ext_done = true;
   }
+  return 0;
+}
+
+int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
+              void* workspace, size_t workspace_bytes) {
+  return gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, nullptr, nullptr);
+}
+
+int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
+                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
+                 void* workspace, size_t workspace_bytes, const aslp_gemm_epilogue_t* epi) {
+  if (epi == nullptr) return aslp_gemm(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes);
+  ASLP_REQUIRE(epi->act >= 0 && epi->act <= 3);
+  ASLP_REQUIRE(epi->dact_y == nullptr || (epi->dact_kind >= 0 && epi->dact_kind <= 2));
+  if (M == 0 || N == 0) return 0;
+  EpiExt x{epi->act, epi->dact_y, epi->dact_ldy, epi->dact_kind, epi->update_w, epi->update_ldw, epi->update_lr};
+  bool done = false;
+  int rc = gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, &x, &done);
+  if (rc != 0 || done) return rc;
+  // the product did not go through the split-K reduce (large or odd shapes): the same steps as launches of their own
+  if (x.act != 0) { rc = aslp_act_fwd(s, x.act - 1, C, ldc, C, ldc, M, N); if (rc != 0) return rc; }
+  if (x.dy != nullptr) { rc = aslp_act_bwd(s, x.dkind, C, ldc, x.dy, x.ldy, C, ldc, M, N); if (rc != 0) return rc; }
+  if (x.w != nullptr) { rc = aslp_axpby(s, x.w, x.ldw, C, ldc, M, N, -x.lr, 1.0f); if (rc != 0) return rc; }
   return 0;
 }
 

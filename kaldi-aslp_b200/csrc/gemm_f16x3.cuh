@@ -247,6 +247,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           float cs[4] = {0.f, 0.f, 0.f, 0.f};                // 2^-e of the four columns of this lane
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) if (jj < nvalid) cs[jj] = inv_b[col + jj];
+          float4 oldc[8];                                    // beta operands of the chunk, all in flight together (see gemm.cu)
+          const bool pre_beta = p.partial == nullptr && p.beta != 0.f && nvalid >= 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = m0 + q * 32 + it * 4 + sub_r;
+            oldc[it] = (pre_beta && row < p.M) ? *reinterpret_cast<const float4*>(p.C + (size_t)row * p.ldc + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + sub_r;
@@ -263,7 +270,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 o.x *= p.alpha; o.y *= p.alpha; o.z *= p.alpha; o.w *= p.alpha;
                 if (nvalid >= 4) {
                   if (p.beta != 0.f) {
-                    const float4 old = *reinterpret_cast<const float4*>(dst);
+                    const float4 old = oldc[it];
                     o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
                   }
                   if (p.bias != nullptr) {

@@ -273,6 +273,34 @@ int col_reduce(cudaStream_t st, bool dot, float* vec, const float* a, int lda, c
   return 0;
 }
 
+// corr = momentum * corr + column sums of diff; bias -= lr * corr.  One CTA per 32 columns: 8 row lanes x 32 columns, four
+// independent accumulators per thread, a fixed-order shared-memory reduction over the row lanes (deterministic).
+__global__ void __launch_bounds__(256) bias_grad_update_kernel(float* bias, float* corr, const float* __restrict__ diff, int ldd, int rows, int cols,
+                                                               float momentum, float lr) {
+  __shared__ float part[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    int r = rl;
+    for (; r + 24 < rows; r += 32) {
+      a0 += diff[(size_t)r * ldd + c]; a1 += diff[(size_t)(r + 8) * ldd + c];
+      a2 += diff[(size_t)(r + 16) * ldd + c]; a3 += diff[(size_t)(r + 24) * ldd + c];
+    }
+    for (; r < rows; r += 8) a0 += diff[(size_t)r * ldd + c];
+  }
+  part[rl][cl] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += part[k][cl];
+    const float g = momentum * corr[c] + sum;
+    corr[c] = g;
+    bias[c] = bias[c] + (-lr) * g;
+  }
+}
+
 // dst[r, :] = src[idx[r], :]  (idx < 0 -> zeros), 128-bit lanes along the row
 __global__ void copy_rows_kernel(float* dst, int ldd, const float* src, int lds, const int* idx, int rows, int cols) {
   const int c4 = (cols + 3) >> 2;
@@ -393,6 +421,19 @@ int aslp_add_vec_to_rows(aslp_stream_t s, float* dst, int ldd, int rows, int col
 int aslp_col_sum(aslp_stream_t s, float* vec, const float* mat, int ldm, int rows, int cols, float alpha, float beta, float clip) {
   ASLP_REQUIRE(ldm % 4 == 0);
   return col_reduce((cudaStream_t)s, false, vec, mat, ldm, nullptr, 0, rows, cols, alpha, beta, clip);
+}
+int aslp_bias_grad_update(aslp_stream_t s, float* bias, float* corr, const float* diff, int ldd, int rows, int cols, float momentum, float lr) {
+  if (cols == 0) return 0;
+  ASLP_REQUIRE(bias != nullptr && corr != nullptr && diff != nullptr && ldd >= cols);
+  if (rows > 4096) {                                      // long chunks: the chunked two-pass column sum fills the chip better
+    int rc = col_reduce((cudaStream_t)s, false, corr, diff, ldd, nullptr, 0, rows, cols, 1.0f, momentum, 0.0f);
+    if (rc != 0) return rc;
+    const int ld = (cols + 3) / 4 * 4;
+    return aslp_axpby(s, bias, ld, corr, ld, 1, cols, -lr, 1.0f);
+  }
+  bias_grad_update_kernel<<<aslp_div_up(cols, 32), 256, 0, (cudaStream_t)s>>>(bias, corr, diff, ldd, rows, cols, momentum, lr);
+  ASLP_CHECK_LAUNCH();
+  return 0;
 }
 int aslp_col_dot(aslp_stream_t s, float* vec, const float* a, int lda, const float* b, int ldb, int rows, int cols, float alpha, float beta, float clip) {
   ASLP_REQUIRE(lda % 4 == 0 && ldb % 4 == 0);

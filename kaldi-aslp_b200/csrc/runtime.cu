@@ -5,6 +5,9 @@
 #include <string.h>
 
 unsigned long long g_aslp_launches = 0;
+// bumped whenever this library or its caller (through aslp_free) releases device memory: a captured step graph holds raw
+// pointers, so it is only replayed while no allocation it may have seen has gone away (aslp_alloc_epoch)
+static unsigned long long g_alloc_epoch = 0;
 static thread_local char g_err[512] = "";
 
 void aslp_set_last_error(cudaError_t e, const char* file, int line) {
@@ -38,7 +41,55 @@ int aslp_malloc(void** p, size_t bytes) {
   if (e != cudaSuccess) { aslp_set_last_error(e, __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
   return 0;
 }
-int aslp_free(void* p) { ASLP_CUDA(cudaFree(p)); return 0; }
+int aslp_free(void* p) { ++g_alloc_epoch; ASLP_CUDA(cudaFree(p)); return 0; }
+unsigned long long aslp_alloc_epoch(void) { return g_alloc_epoch; }
+int aslp_count_launches(unsigned long long n) { g_aslp_launches += n; return 0; }
+
+// ---- static-shape step replay: stream capture -> executable graph (host/matrix.h CuStepGraph) ----
+int aslp_graph_begin(aslp_stream_t s) {
+  ASLP_CUDA(cudaStreamBeginCapture((cudaStream_t)s, cudaStreamCaptureModeRelaxed));
+  return 0;
+}
+int aslp_graph_end(aslp_stream_t s, void** exec, int* kernel_nodes) {
+  ASLP_REQUIRE(exec != nullptr);
+  *exec = nullptr;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)s, &g);
+  if (e != cudaSuccess || g == nullptr) {
+    cudaGetLastError();                                   // a failed capture leaves a sticky-looking error behind: clear it
+    aslp_set_last_error(e == cudaSuccess ? cudaErrorUnknown : e, __FILE__, __LINE__);
+    if (g != nullptr) cudaGraphDestroy(g);
+    return ASLP_STATUS_EXECUTION_FAILED;
+  }
+  if (kernel_nodes != nullptr) {
+    size_t n = 0;
+    *kernel_nodes = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n) == cudaSuccess && n > 0) {
+      cudaGraphNode_t* nodes = new cudaGraphNode_t[n];
+      if (cudaGraphGetNodes(g, nodes, &n) == cudaSuccess)
+        for (size_t i = 0; i < n; ++i) {
+          cudaGraphNodeType t;
+          if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++*kernel_nodes;
+        }
+      delete[] nodes;
+    }
+  }
+  cudaGraphExec_t x = nullptr;
+  e = cudaGraphInstantiate(&x, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { cudaGetLastError(); aslp_set_last_error(e, __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; }
+  *exec = (void*)x;
+  return 0;
+}
+int aslp_graph_launch(void* exec, aslp_stream_t s) {
+  ASLP_REQUIRE(exec != nullptr);
+  ASLP_CUDA(cudaGraphLaunch((cudaGraphExec_t)exec, (cudaStream_t)s));
+  return 0;
+}
+int aslp_graph_destroy(void* exec) {
+  if (exec != nullptr) ASLP_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)exec));
+  return 0;
+}
 int aslp_malloc_host(void** p, size_t bytes) {
   cudaError_t e = cudaMallocHost(p, bytes ? bytes : 16);
   if (e != cudaSuccess) { aslp_set_last_error(e, __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
@@ -115,7 +166,7 @@ void* aslp_scratch(cudaStream_t stream, size_t bytes) {
   ScratchBuf& b = g_scratch[std::make_pair(dev, stream)];
   const size_t want = bytes + ASLP_SCRATCH_RESERVED;
   if (b.ptr == nullptr || b.bytes < want) {
-    if (b.ptr != nullptr) { cudaStreamSynchronize(stream); cudaFree(b.ptr); b.ptr = nullptr; }
+    if (b.ptr != nullptr) { cudaStreamSynchronize(stream); cudaFree(b.ptr); b.ptr = nullptr; ++g_alloc_epoch; }
     size_t cap = want < (8u << 20) ? (8u << 20) : want * 2;
     if (cudaMalloc(&b.ptr, cap) != cudaSuccess) { b.ptr = nullptr; b.bytes = 0; return nullptr; }
     cudaMemsetAsync(b.ptr, 0, ASLP_SCRATCH_RESERVED, stream);
@@ -130,6 +181,6 @@ extern "C" int aslp_scratch_release(aslp_stream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   auto it = g_scratch.find(std::make_pair(dev, (cudaStream_t)s));
-  if (it != g_scratch.end()) { if (it->second.ptr != nullptr) cudaFree(it->second.ptr); g_scratch.erase(it); }
+  if (it != g_scratch.end()) { if (it->second.ptr != nullptr) { cudaFree(it->second.ptr); ++g_alloc_epoch; } g_scratch.erase(it); }
   return 0;
 }

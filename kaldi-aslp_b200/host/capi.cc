@@ -4,6 +4,7 @@
 #include "cu-workspace.h"
 #include "nnet-loss.h"
 #include "nnet-nnet.h"
+#include "nnet-train-step.h"
 #include "parallel.h"
 #include "parallel-async.h"
 
@@ -29,6 +30,8 @@ static void CopyOut(const std::string& s, char* buf, size_t bytes) {
 
 // reusable device staging for host inputs / outputs
 static CuMatrix<BaseFloat> g_in, g_out, g_diff, g_indiff, g_loss_diff;
+static XentTrainStep g_xent_step;
+long long aslp_nnet_step_replays(void) { return g_xent_step.Replays(); }
 
 extern "C" {
 
@@ -38,6 +41,7 @@ int aslp_nnet_srand(int seed) { srand(seed); return 0; }
 int aslp_nnet_set_gemm_precision(int precision) { SetGemmPrecision(precision); return 0; }
 int aslp_nnet_device_sync(void) { CAPI_BEGIN CuSync(); CAPI_END }
 unsigned long long aslp_nnet_launch_count(void) { return aslp_launch_count(); }
+long long aslp_nnet_step_replays(void);
 static void* g_events[16] = {nullptr};
 int aslp_nnet_event_record(int slot) {
   CAPI_BEGIN
@@ -155,12 +159,17 @@ int aslp_train_step_xent(aslp_nnet_t n, aslp_xent_t x, const float* features, in
   CAPI_BEGIN
   CuSubMatrix<BaseFloat> view(nullptr, 0, 0, 0);
   const CuMatrixBase<BaseFloat>& in = StageFeatures(features, on_device, rows, cols, &view);
-  N(n)->Propagate(in, &g_out);
   Posterior post(rows);
   Vector<BaseFloat> fw(rows);
   for (int r = 0; r < rows; ++r) { post[r].push_back(std::make_pair(targets[r], 1.0f)); fw(r) = frame_mask ? frame_mask[r] : 1.0f; }
-  static_cast<LossItf*>(x)->Eval(fw, g_out, post, &g_loss_diff);
-  N(n)->Backpropagate(g_loss_diff, NULL);
+  Xent* xent = dynamic_cast<Xent*>(static_cast<LossItf*>(x));
+  if (xent != nullptr) {                                // the trainers' step (nnet-train-step.h): recorded and replayed when it repeats
+    g_xent_step.Run(N(n), xent, in, fw, post);
+  } else {
+    N(n)->Propagate(in, &g_out);
+    static_cast<LossItf*>(x)->Eval(fw, g_out, post, &g_loss_diff);
+    N(n)->Backpropagate(g_loss_diff, NULL);
+  }
   CAPI_END
 }
 

@@ -67,6 +67,76 @@ void CuJoin() {
   ASLP_OK(aslp_stream_wait_event(g_stream, g_ev_join));
   g_side_pending = false;
 }
+// ------------------------------------------------------------------ step replay
+bool CuStepGraph::Enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ASLP_STEP_GRAPH"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+CuStepGraph::CuStepGraph() : recording_(false), epoch_(0), clock_(0), replays_(0), recordings_(0) {}
+CuStepGraph::~CuStepGraph() { DropAll(); }
+void CuStepGraph::DropAll() {
+  for (auto& kv : cache_) if (kv.second.exec != nullptr) aslp_graph_destroy(kv.second.exec);
+  cache_.clear();
+}
+bool CuStepGraph::Begin(const std::string& key) {
+  KALDI_ASSERT(!recording_);
+  if (!Enabled() || t_helper) return true;
+  const unsigned long long epoch = aslp_alloc_epoch();
+  if (epoch != epoch_) {                                  // some device allocation went away: every recording may hold a dead pointer
+    for (auto& kv : cache_) if (kv.second.exec != nullptr) { aslp_graph_destroy(kv.second.exec); kv.second.exec = nullptr; kv.second.seen = 0; }
+    epoch_ = epoch;
+  }
+  auto it = cache_.find(key);
+  if (it == cache_.end()) {
+    if (static_cast<int>(cache_.size()) >= kMaxGraphs) {  // least recently used out
+      auto victim = cache_.begin();
+      for (auto jt = cache_.begin(); jt != cache_.end(); ++jt) if (jt->second.stamp < victim->second.stamp) victim = jt;
+      if (victim->second.exec != nullptr) aslp_graph_destroy(victim->second.exec);
+      cache_.erase(victim);
+    }
+    Entry e; e.exec = nullptr; e.kernels = 0; e.seen = 0; e.bad = false; e.stamp = 0;
+    it = cache_.insert(std::make_pair(key, e)).first;
+  }
+  Entry& e = it->second;
+  e.stamp = ++clock_;
+  if (e.exec != nullptr) {
+    ASLP_OK(aslp_graph_launch(e.exec, g_stream));
+    aslp_count_launches(e.kernels);
+    ++replays_;
+    return false;
+  }
+  if (e.bad || e.seen < 2) { ++e.seen; return true; }     // warm-up passes run as they are
+  CuStream();
+  if (aslp_graph_begin(g_stream) != 0) { e.bad = true; return true; }
+  recording_ = true;
+  recording_key_ = key;
+  return true;
+}
+bool CuStepGraph::End() {
+  if (!recording_) return true;
+  recording_ = false;
+  Entry& e = cache_[recording_key_];
+  void* exec = nullptr;
+  int kernels = 0;
+  if (aslp_graph_end(g_stream, &exec, &kernels) != 0 || exec == nullptr) {
+    g_side_pending = false;                                // a fork recorded into the dead capture never happened
+    e.bad = true;
+    KALDI_WARN << "step recording failed (" << aslp_last_error() << "); this step shape keeps running unrecorded";
+    return false;
+  }
+  if (aslp_alloc_epoch() != epoch_) {                      // something was freed while recording: the graph may point at it
+    aslp_graph_destroy(exec);
+    epoch_ = aslp_alloc_epoch();
+    e.seen = 0;
+    return false;
+  }
+  e.exec = exec; e.kernels = kernels;
+  ++recordings_;
+  ASLP_OK(aslp_graph_launch(e.exec, g_stream));            // recording does not execute: run the step now
+  return true;
+}
+
 // GEMMs issued inside a side-stream scope can run on a capped grid (ASLP_SIDE_GEMM_CTAS = n; default 0 = one CTA per SM): they are
 // the weight-gradient products that run under the next layer's persistent backward recurrence (80 co-resident CTAs).  Measured on
 // one box (profiles/r02_ab_side_ctas.jsonl): 17.91 ms per cfg3 step uncapped, 17.95 at 68, 17.98 at 60, 18.28 at 40 -- the cap

@@ -8,6 +8,8 @@
 #include "aslp_b200.h"
 #include "base.h"
 #include "io.h"
+#include <map>
+#include <string>
 
 namespace kaldi {
 
@@ -34,6 +36,38 @@ void CuThreadUseDevice();
 bool CuAsyncEnabled();
 void CuFork();
 void CuJoin();
+
+// Static-shape step replay (include/aslp_b200.h, aslp_graph_*).  A trainer whose minibatch has the same shapes, buffers
+// and hyper-parameters step after step records the device work of one step from the compute stream and replays it as ONE
+// graph launch: the host cost of a step drops from one enqueue per kernel (4-14 us each -- the whole step time of the
+// launch-bound configurations) to one call.
+//     if (g.Begin(key)) { <enqueue the step on CuStream()>;  if (!g.End()) <enqueue it again>; }
+// Begin() returns false when it replayed a recording for `key`; true when the caller has to enqueue the step: the first
+// two times a key is seen (allocations settle), while recording (third time), when recording is switched off
+// (ASLP_STEP_GRAPH=0) or failed for this key before.  End() returns false only when a recording was invalidated: nothing
+// ran and the caller enqueues the step once more, unrecorded.  Everything between Begin and End must be device work on
+// the library's streams -- host-side bookkeeping of the step belongs outside, it is not re-executed by a replay.
+// Recordings hold raw device pointers: they are dropped as soon as the allocation epoch moves (any device free anywhere),
+// and at most kMaxGraphs of them are kept (least recently used out first).
+class CuStepGraph {
+ public:
+  CuStepGraph();
+  ~CuStepGraph();
+  bool Begin(const std::string& key);
+  bool End();
+  long long Replays() const { return replays_; }
+  long long Recordings() const { return recordings_; }
+  static bool Enabled();
+ private:
+  struct Entry { void* exec; int kernels; int seen; bool bad; unsigned long long stamp; };
+  void DropAll();
+  static const int kMaxGraphs = 32;
+  std::map<std::string, Entry> cache_;
+  std::string recording_key_;
+  bool recording_;
+  unsigned long long epoch_, clock_;
+  long long replays_, recordings_;
+};
 class CuStreamScope {
  public:
   explicit CuStreamScope(aslp_stream_t s);

@@ -32,7 +32,9 @@ class PointwiseActivation : public Component {
     ASLP_OK(aslp_act_fwd(CuStream(), KIND, out->Data(), out->Stride(), in.Data(), in.Stride(), in.NumRows(), in.NumCols()));
   }
   void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
-    const CuMatrixBase<BaseFloat>& ref = (KIND == ASLP_ACT_RELU) ? in : out;     // sigmoid/tanh use y, ReLU uses Heaviside(x)
+    // sigmoid / tanh use y; the ReLU mask Heaviside(x) is taken from y as well (y = max(x, 0) is positive exactly where x is), so
+    // that no activation needs its input again -- Nnet may have folded the forward pass into the producing Affine's epilogue
+    const CuMatrixBase<BaseFloat>& ref = out;
     ASLP_OK(aslp_act_bwd(CuStream(), KIND, in_diff->Data(), in_diff->Stride(), ref.Data(), ref.Stride(), out_diff.Data(), out_diff.Stride(),
                          out_diff.NumRows(), out_diff.NumCols()));
   }

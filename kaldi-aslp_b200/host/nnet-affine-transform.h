@@ -94,13 +94,41 @@ class AffineTransform : public UpdatableComponent {
            (has_bias_ ? "\n  bias_grad" + MomentStatistics(bias_corr_) + ", lr-coef " + ToString(bias_learn_rate_coef_) : "");
   }
 
+  // (split-K workspace also for the forward / backward products: at a 256-frame minibatch the output has 16 tiles, i.e.
+  // 16 of 148 SMs busy for the whole K chain -- 29 us per 256 x 1024 x 1024 product measured -- unless K is split)
   void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
+    const size_t wsb = aslp_gemm_workspace_bytes(in.NumRows(), output_dim_, input_dim_);
     ASLP_OK(aslp_gemm(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
-                      0.0f, out->Data(), out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+                      0.0f, out->Data(), out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
   }
   void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
+    const size_t wsb = aslp_gemm_workspace_bytes(out_diff.NumRows(), input_dim_, output_dim_);
     ASLP_OK(aslp_gemm(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
-                      linearity_.Stride(), 0.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), nullptr, 0));
+                      linearity_.Stride(), 0.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
+  }
+  // Forward with the following Sigmoid / Tanh / ReLU applied in the product's epilogue (Nnet::Propagate pairs the two
+  // components when the product takes the split-K reduce pass; the pre-activation is then never written)
+  void PropagateFused(const CuMatrixBase<BaseFloat>& in, int act_kind, CuMatrixBase<BaseFloat>* act_out) {
+    const size_t wsb = aslp_gemm_workspace_bytes(in.NumRows(), output_dim_, input_dim_);
+    aslp_gemm_epilogue_t epi = {};
+    epi.act = 1 + act_kind;
+    ASLP_OK(aslp_gemm_ex(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
+                         0.0f, act_out->Data(), act_out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
+  }
+  // Backward with the derivative of the PRECEDING activation (output y) applied in the epilogue: what this component and the
+  // activation in front of it would write in two passes, d(loss)/d(input of the activation), in one
+  void BackpropagateFused(const CuMatrixBase<BaseFloat>& out_diff, const CuMatrixBase<BaseFloat>& act_y, int act_kind, CuMatrixBase<BaseFloat>* act_in_diff) {
+    const size_t wsb = aslp_gemm_workspace_bytes(out_diff.NumRows(), input_dim_, output_dim_);
+    aslp_gemm_epilogue_t epi = {};
+    epi.dact_y = act_y.Data(); epi.dact_ldy = act_y.Stride(); epi.dact_kind = act_kind;
+    ASLP_OK(aslp_gemm_ex(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
+                         linearity_.Stride(), 0.0f, act_in_diff->Data(), act_in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
+  }
+  // true when a product of this layer at `rows` frames goes through the split-K reduce pass, i.e. when folding a neighbouring
+  // pointwise step into it costs nothing (few-tile shapes: the launch-bound minibatches)
+  bool SmallBatchShape(int32 rows, bool backward) const {
+    const int32 n = backward ? input_dim_ : output_dim_, k = backward ? output_dim_ : input_dim_;
+    return static_cast<long long>(rows) * n * k >= (1ll << 18) && rows % 4 == 0 && aslp_gemm_workspace_bytes(rows, n, k) > 0;
   }
   void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     aslp_stream_t st = CuStream();
@@ -108,16 +136,23 @@ class AffineTransform : public UpdatableComponent {
     const BaseFloat mmt = opts_.momentum, l2 = opts_.l2_penalty, l1 = opts_.l1_penalty;
     const int32 num_frames = input.NumRows();
     const size_t wsb = aslp_gemm_workspace_bytes(output_dim_, input_dim_, num_frames);
-    ASLP_OK(aslp_gemm(st, 1, 0, output_dim_, input_dim_, num_frames, 1.0f, diff.Data(), diff.Stride(), input.Data(), input.Stride(), mmt,
-                      linearity_corr_.Data(), linearity_corr_.Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
-    if (has_bias_) ASLP_OK(aslp_col_sum(st, bias_corr_.Data(), diff.Data(), diff.Stride(), num_frames, output_dim_, 1.0f, mmt, 0.0f));
-    // (LinearTransform regularises with the bare learn rate, nnet-linear-transform.h:140-155)
-    const BaseFloat lr_reg = has_bias_ ? lr : opts_.learn_rate;
-    if (l2 != 0.0) linearity_.Scale(1.0f - lr_reg * l2 * num_frames);                // W += (-lr*l2*N) * W
-    if (l1 != 0.0) ASLP_OK(aslp_regularize_l1(st, linearity_.Data(), linearity_.Stride(), linearity_corr_.Data(), linearity_corr_.Stride(),
-                                              output_dim_, input_dim_, lr_reg * l1 * num_frames, lr_reg));
-    linearity_.AddMat(-lr, linearity_corr_);
-    if (has_bias_) ASLP_OK(aslp_axpby(st, bias_.Data(), (output_dim_ + 3) / 4 * 4, bias_corr_.Data(), (output_dim_ + 3) / 4 * 4, 1, output_dim_, -lr_bias, 1.0f));
+    // without weight decay the SGD apply W -= lr * W_corr rides in the weight-gradient product's epilogue (the decay terms
+    // below act on W between the two, so with them the apply stays a pass of its own)
+    const bool fused_apply = (l2 == 0.0 && l1 == 0.0);
+    aslp_gemm_epilogue_t epi = {};
+    if (fused_apply) { epi.update_w = linearity_.Data(); epi.update_ldw = linearity_.Stride(); epi.update_lr = lr; }
+    ASLP_OK(aslp_gemm_ex(st, 1, 0, output_dim_, input_dim_, num_frames, 1.0f, diff.Data(), diff.Stride(), input.Data(), input.Stride(), mmt,
+                         linearity_corr_.Data(), linearity_corr_.Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
+    // bias_corr = mmt * bias_corr + column sums of diff; bias -= lr_bias * bias_corr: one launch
+    if (has_bias_) ASLP_OK(aslp_bias_grad_update(st, bias_.Data(), bias_corr_.Data(), diff.Data(), diff.Stride(), num_frames, output_dim_, mmt, lr_bias));
+    if (!fused_apply) {
+      // (LinearTransform regularises with the bare learn rate, nnet-linear-transform.h:140-155)
+      const BaseFloat lr_reg = has_bias_ ? lr : opts_.learn_rate;
+      if (l2 != 0.0) linearity_.Scale(1.0f - lr_reg * l2 * num_frames);                // W += (-lr*l2*N) * W
+      if (l1 != 0.0) ASLP_OK(aslp_regularize_l1(st, linearity_.Data(), linearity_.Stride(), linearity_corr_.Data(), linearity_corr_.Stride(),
+                                                output_dim_, input_dim_, lr_reg * l1 * num_frames, lr_reg));
+      linearity_.AddMat(-lr, linearity_corr_);
+    }
     if (max_norm_ > 0.0) ASLP_OK(aslp_max_norm_rows(st, linearity_.Data(), linearity_.Stride(), output_dim_, input_dim_, max_norm_));
   }
 

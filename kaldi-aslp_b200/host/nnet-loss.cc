@@ -7,10 +7,18 @@ namespace kaldi {
 namespace aslp_nnet {
 
 // ------------------------------------------------------------------ Xent
-Xent::Xent() : stats_dev_(nullptr), frames_(0), correct_(0), loss_(0), entropy_(0), likelyhood_(0), frames_progress_(0) {
+Xent::Xent() : stats_dev_(nullptr), frames_(0), correct_(0), loss_(0), entropy_(0), likelyhood_(0), frames_progress_(0),
+               stage_rows_(0), stage_pad_(0), stage_next_(0) {
   for (double& b : base_) b = 0;
+  for (int i = 0; i < kStageSlots; ++i) { stage_host_[i] = nullptr; stage_event_[i] = nullptr; stage_cap_[i] = 0; }
 }
-Xent::~Xent() { if (stats_dev_ != nullptr) aslp_free(stats_dev_); }
+Xent::~Xent() {
+  if (stats_dev_ != nullptr) aslp_free(stats_dev_);
+  for (int i = 0; i < kStageSlots; ++i) {
+    if (stage_event_[i] != nullptr) { aslp_event_sync(stage_event_[i]); aslp_event_destroy(stage_event_[i]); }
+    if (stage_host_[i] != nullptr) aslp_free_host(stage_host_[i]);
+  }
+}
 
 static void EnsureStats(double** p) {
   if (*p == nullptr) {
@@ -63,26 +71,57 @@ void Xent::Eval(const VectorBase<BaseFloat>& frame_weights, const CuMatrixBase<B
     Eval(frame_weights, net_out, tgt_mat_, diff);
     return;
   }
+  const double nf = StageSparse(frame_weights, post, num_pdf);
+  KALDI_ASSERT(nf >= 0.0);
+  LaunchSparse(net_out, diff);
+  Progress(nf);
+}
+
+double Xent::StageSparse(const VectorBase<BaseFloat>& frame_weights, const Posterior& post, int32 num_pdf) {
+  const int32 num_frames = static_cast<int32>(post.size());
+  KALDI_ASSERT(num_frames == frame_weights.Dim());
+  for (const auto& f : post) if (f.size() > 1) return -1.0;
   EnsureStats(&stats_dev_);
-  std::vector<int32> idx(num_frames, 0);
-  Vector<BaseFloat> w(num_frames);
+  const int32 pad = (num_frames + 3) / 4 * 4;
+  // a ring of page-locked slots: the upload is asynchronous, so the slot of step n is written again only after the copy
+  // of step n - kStageSlots has finished (its event) -- which also bounds how far the host runs ahead of the device
+  const int slot = static_cast<int>(stage_next_++ % kStageSlots);
+  if (stage_event_[slot] != nullptr) ASLP_OK(aslp_event_sync(stage_event_[slot]));
+  if (stage_cap_[slot] < static_cast<size_t>(3) * pad) {
+    if (stage_host_[slot] != nullptr) ASLP_OK(aslp_free_host(stage_host_[slot]));
+    void* p = nullptr;
+    ASLP_OK(aslp_malloc_host(&p, sizeof(float) * 3 * pad));
+    stage_host_[slot] = static_cast<float*>(p);
+    stage_cap_[slot] = static_cast<size_t>(3) * pad;
+  }
+  float* h = stage_host_[slot];
+  int32* hi = reinterpret_cast<int32*>(h);
   double nf = 0;
   for (int32 t = 0; t < num_frames; ++t) {
+    int32 id = 0;
+    float w = 0.f;
     if (!post[t].empty()) {
       if (post[t][0].first >= num_pdf) KALDI_ERR << "Posterior has pdf-id " << post[t][0].first << " but the net has " << num_pdf << " outputs";
-      idx[t] = post[t][0].first;
-      w(t) = post[t][0].second;
+      id = post[t][0].first;
+      w = post[t][0].second;
     }
-    nf += frame_weights(t) * w(t);
+    hi[t] = id; h[pad + t] = w; h[2 * pad + t] = frame_weights(t);
+    nf += frame_weights(t) * w;
   }
-  KALDI_ASSERT(nf >= 0.0);
-  tgt_idx_dev_ = idx;
-  tgt_w_dev_ = w;
-  frame_w_dev_ = frame_weights;
+  for (int32 t = num_frames; t < pad; ++t) { hi[t] = 0; h[pad + t] = 0.f; h[2 * pad + t] = 0.f; }
+  if (stage_dev_.Dim() != 3 * pad) stage_dev_.Resize(3 * pad, kUndefined);
+  stage_rows_ = num_frames; stage_pad_ = pad;
+  ASLP_OK(aslp_memcpy_h2d(CuStream(), stage_dev_.Data(), h, sizeof(float) * 3 * pad));
+  ASLP_OK(aslp_event_record(CuStream(), &stage_event_[slot]));
+  return nf;
+}
+
+void Xent::LaunchSparse(const CuMatrixBase<BaseFloat>& net_out, CuMatrix<BaseFloat>* diff) {
+  const int32 num_frames = net_out.NumRows(), num_pdf = net_out.NumCols();
+  KALDI_ASSERT(num_frames == stage_rows_);
   diff->Resize(num_frames, num_pdf, kUndefined);
-  ASLP_OK(aslp_xent_sparse(CuStream(), diff->Data(), diff->Stride(), net_out.Data(), net_out.Stride(), num_frames, num_pdf, tgt_idx_dev_.Data(),
-                           tgt_w_dev_.Data(), frame_w_dev_.Data(), stats_dev_));
-  Progress(nf);
+  ASLP_OK(aslp_xent_sparse(CuStream(), diff->Data(), diff->Stride(), net_out.Data(), net_out.Stride(), num_frames, num_pdf,
+                           reinterpret_cast<const int32*>(stage_dev_.Data()), stage_dev_.Data() + stage_pad_, stage_dev_.Data() + 2 * stage_pad_, stats_dev_));
 }
 
 BaseFloat Xent::AvgLoss() { Fetch(); return (loss_ - entropy_) / frames_; }

@@ -48,15 +48,28 @@ class Xent : public LossItf {
   BaseFloat AvgLoss();
   double Frames() { Fetch(); return frames_; }
   double Correct() { Fetch(); return correct_; }
+  // The sparse Eval in three parts, so that the device part can sit inside a recorded step (CuStepGraph) while the host
+  // parts run every step: StageSparse packs target index, target weight and frame weight of every frame into one
+  // page-locked slot and uploads them with ONE asynchronous copy into a fixed device buffer (returns the weighted frame
+  // count, or -1 when some frame has more than one target -- the caller then takes the dense Eval); LaunchSparse is the
+  // kernel alone; Progress is the host-side bookkeeping.
+  double StageSparse(const VectorBase<BaseFloat>& frame_weights, const Posterior& post, int32 num_pdf);
+  void LaunchSparse(const CuMatrixBase<BaseFloat>& net_out, CuMatrix<BaseFloat>* diff);
+  void Progress(double num_frames);
  private:
   void Fetch();                 // device accumulators -> host (synchronises)
-  void Progress(double num_frames);
   double* stats_dev_;           // [ce, entropy, likelihood, correct, frames] accumulated on the device
   double frames_, correct_, loss_, entropy_, likelyhood_;
   double frames_progress_, base_[5];
   CuMatrix<BaseFloat> tgt_mat_;
-  CuVector<BaseFloat> frame_w_dev_, tgt_w_dev_;
-  CuArrayInt tgt_idx_dev_;
+  CuVector<BaseFloat> frame_w_dev_;
+  static const int kStageSlots = 8;
+  float* stage_host_[kStageSlots];          // page-locked [3][rows_pad]: index bits, target weight, frame weight
+  void* stage_event_[kStageSlots];
+  size_t stage_cap_[kStageSlots];
+  CuVector<BaseFloat> stage_dev_;           // the same three rows on the device (fixed address while the minibatch size repeats)
+  int32 stage_rows_, stage_pad_;
+  unsigned stage_next_;
 };
 
 // mean square error (nnet-loss.h:133-171, nnet-loss.cc:205-290): diff = w (y - t); one fused pass, the loss stays on the device

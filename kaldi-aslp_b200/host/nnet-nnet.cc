@@ -1,6 +1,7 @@
 #include "nnet-nnet.h"
 #include <map>
 #include "nnet-activation.h"
+#include "nnet-affine-transform.h"
 #include "nnet-gru-streams.h"
 #include "nnet-lstm-family.h"
 #include "nnet-misc-components.h"
@@ -37,6 +38,35 @@ static bool DirectInput(const std::vector<Component*>& comps, int32 i) {
   return consumers == 1;
 }
 
+// Epilogue fusion across component pairs.  Forward: Affine / Linear i followed by a Sigmoid / Tanh / ReLU that is
+// its only consumer -> one product with the activation in its epilogue; the Affine's own output buffer is not written.
+// Backward: the same kind of activation a in front of an Affine b -> b's backward product applies f'(y_a) in its epilogue
+// and writes d(loss)/d(input of a); a's own out-diff buffer is not written.  Only for the few-tile shapes whose products
+// take the split-K reduce pass (AffineTransform::SmallBatchShape), which is where a step is launch-bound and where the
+// golden-net comparisons of every per-component buffer do not reach.  ASLP_FUSE_EPILOGUE=0 switches it off.
+static bool FusionEnabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ASLP_FUSE_EPILOGUE"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+static int ActKind(const Component* c) {
+  switch (c->GetType()) {
+    case Component::kSigmoid: return ASLP_ACT_SIGMOID;
+    case Component::kTanh: return ASLP_ACT_TANH;
+    case Component::kReLU: return ASLP_ACT_RELU;
+    default: return -1;
+  }
+}
+static bool IsAffine(const Component* c) { return c->GetType() == Component::kAffineTransform || c->GetType() == Component::kLinearTransform; }
+// activation `a` reads, in place, the whole output of an Affine that nobody else reads
+static bool ActBehindAffine(const std::vector<Component*>& comps, const std::vector<int32>& outputs, int32 a) {
+  if (a < 1 || a >= static_cast<int32>(comps.size()) || ActKind(comps[a]) < 0 || !DirectInput(comps, a)) return false;
+  const int32 p = comps[a]->GetInput()[0];
+  if (!IsAffine(comps[p])) return false;
+  for (int32 o : outputs) if (o == p) return false;      // the pre-activation is a net output: it has to exist
+  return true;
+}
+
 void Nnet::Propagate(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std::vector<CuMatrix<BaseFloat>*>* out) {
   KALDI_ASSERT(NULL != out);
   KALDI_ASSERT(in.size() == input_.size());
@@ -65,6 +95,18 @@ void Nnet::Propagate(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std:
       }
     }
     Timer tim;
+    // Affine + activation in one product (the activation must be the next component in execution order)
+    if (FusionEnabled() && IsAffine(c) && i + 1 < NumComponents() && ActBehindAffine(components_, output_, i + 1) &&
+        components_[i + 1]->GetInput()[0] == i && static_cast<AffineTransform*>(c)->SmallBatchShape(num_frame, false)) {
+      output_buf_[i].Resize(num_frame, c->OutputDim(), kUndefined);          // keeps its shape (Backpropagate checks it); never written
+      output_buf_[i + 1].Resize(num_frame, components_[i + 1]->OutputDim(), kUndefined);
+      static_cast<AffineTransform*>(c)->PropagateFused(*src, ActKind(components_[i + 1]), &output_buf_[i + 1]);
+      propagate_time_[i].first = Component::TypeToMarker(c->GetType());
+      propagate_time_[i].second += tim.Elapsed();
+      propagate_time_[i + 1].first = Component::TypeToMarker(components_[i + 1]->GetType());
+      ++i;
+      continue;
+    }
     c->Propagate(*src, &output_buf_[i]);
     propagate_time_[i].first = Component::TypeToMarker(c->GetType());
     propagate_time_[i].second += tim.Elapsed();
@@ -75,7 +117,7 @@ void Nnet::Propagate(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std:
 void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_diff, std::vector<CuMatrix<BaseFloat>*>* in_diff) {
   KALDI_ASSERT(out_diff.size() == output_.size());
   const int32 num_frame = out_diff[0]->NumRows();
-  std::vector<char> direct(NumComponents(), 0), fed_direct(NumComponents(), 0);
+  std::vector<char> direct(NumComponents(), 0), fed_direct(NumComponents(), 0), skip_bwd(NumComponents(), 0);
   for (int32 i = 0; i < NumComponents(); i++) {
     direct[i] = DirectInput(components_, i);
     if (direct[i]) fed_direct[components_[i]->GetInput()[0]] = 1;
@@ -88,7 +130,20 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_
     const CuMatrixBase<BaseFloat>& cin = direct[i] ? static_cast<const CuMatrixBase<BaseFloat>&>(output_buf_[c->GetInput()[0]]) : input_buf_[i];
     CuMatrix<BaseFloat>* target = direct[i] ? &output_diff_buf_[c->GetInput()[0]] : &input_diff_buf_[i];
     Timer tim;
-    c->Backpropagate(cin, output_buf_[i], output_diff_buf_[i], target);
+    if (skip_bwd[i]) continue;                            // an activation whose derivative the Affine behind it has applied
+    // Affine whose input is an activation that reads an Affine in place: d(loss)/d(pre-activation) straight from this product
+    const int32 a = direct[i] ? c->GetInput()[0] : -1;
+    bool a_is_output = false;
+    for (int32 o : output_) if (o == a) a_is_output = true;
+    if (FusionEnabled() && IsAffine(c) && a >= 0 && a == i - 1 && direct[a] && !a_is_output && ActKind(components_[a]) >= 0 &&
+        static_cast<AffineTransform*>(c)->SmallBatchShape(num_frame, true)) {
+      CuMatrix<BaseFloat>* pre = &output_diff_buf_[components_[a]->GetInput()[0]];
+      pre->Resize(num_frame, components_[a]->InputDim(), kUndefined);
+      static_cast<AffineTransform*>(c)->BackpropagateFused(output_diff_buf_[i], output_buf_[a], ActKind(components_[a]), pre);
+      skip_bwd[a] = 1;
+    } else {
+      c->Backpropagate(cin, output_buf_[i], output_diff_buf_[i], target);
+    }
     if (c->IsUpdatable()) dynamic_cast<UpdatableComponent*>(c)->Update(cin, output_diff_buf_[i]);   // update inside backprop (:126-129)
     back_propagate_time_[i].first = Component::TypeToMarker(c->GetType());
     back_propagate_time_[i].second += tim.Elapsed();
@@ -106,6 +161,21 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_
   if (NULL == in_diff) return;
   for (size_t i = 0; i < input_.size(); i++)
     if ((*in_diff)[i] != NULL) *((*in_diff)[i]) = input_diff_buf_[input_[i]];
+}
+
+bool Nnet::StepReplayable() const {
+  if (input_.size() != 1 || output_.size() != 1) return false;
+  for (const Component* c : components_) {
+    switch (c->GetType()) {
+      case Component::kAffineTransform: case Component::kLinearTransform: case Component::kSigmoid: case Component::kTanh:
+      case Component::kReLU: case Component::kSoftmax: case Component::kCompactFsmn: case Component::kSplice:
+      case Component::kAddShift: case Component::kRescale: case Component::kInputLayer: case Component::kOutputLayer:
+        break;
+      default:
+        return false;
+    }
+  }
+  return true;
 }
 
 void Nnet::Feedforward(const std::vector<const CuMatrixBase<BaseFloat>*>& in, std::vector<CuMatrix<BaseFloat>*>* out) {

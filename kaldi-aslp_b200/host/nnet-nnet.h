@@ -66,6 +66,10 @@ class Nnet {
   void Check() const;
   void Destroy();
 
+  // true when a training step of this net is pure device work that depends on nothing but its input buffers: every
+  // component is of a kind that keeps no per-step state on the host (no stream-reset flags, sequence lengths, random
+  // masks, running statistics) -- what XentTrainStep needs to record the step once and replay it (nnet-train-step.h)
+  bool StepReplayable() const;
   void SetTrainOptions(const NnetTrainOptions& opts);
   const NnetTrainOptions& GetTrainOptions() const { return opts_; }
   void AutoComplete();

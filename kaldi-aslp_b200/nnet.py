@@ -42,6 +42,11 @@ def launch_count():
     return int(host_lib().aslp_nnet_launch_count())
 
 
+def step_replays():
+    """train_step_xent calls that ran as a replayed recording (CuStepGraph) so far"""
+    return int(host_lib().aslp_nnet_step_replays())
+
+
 class Nnet:
     """kaldi::aslp_nnet::Nnet (src/aslp-nnet/nnet-nnet.h:38-193)."""
 

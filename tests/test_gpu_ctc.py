@@ -20,16 +20,13 @@ def sweep_form(request, monkeypatch):
 
 
 def grad_tol(costs, base=1e-4):
-    """Gradient bound against the oracle.  Costs are held to 1e-4 relative in every form.  Posteriors are
-    exp(alpha + beta - log p - log Z), a difference of fp32 numbers of magnitude |cost|, so they carry a few ulp(|cost|)
-    of absolute error in the reference itself.  The four-launch forms repeat the reference's operation order (their
-    rounding noise is largely the reference's own); the fused form takes log Z where its two sweeps meet instead of
-    from the last alpha row (ctc_fused.cuh) -- an equally good estimate of the same quantity whose rounding is
-    independent of the reference's, so its stated bound is max(1e-4, 8 ulp(|cost|)), the bound tests/test_gpu_fullsize.py
-    already states for the full-size step."""
+    """Gradient bound against the oracle: 1e-4, or 4 ulp(|cost|) where that is larger -- posteriors are
+    exp(alpha + beta - log p - log Z), a difference of fp32 numbers of magnitude |cost|, so they carry a few ulp(|cost|) of
+    absolute error in the reference itself.  The same bound for all three forms: the fused form rescales its rows to the
+    reference's normaliser (the last alpha row) in its closing pass."""
     finite = np.abs(costs[np.isfinite(costs)])
     big = float(finite.max()) if finite.size else 1.0
-    return max(base, 8 * float(np.spacing(np.float32(big))))
+    return max(base, 4 * float(np.spacing(np.float32(big))))
 
 
 def gpu_ctc(acts, labels, ilen):

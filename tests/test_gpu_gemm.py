@@ -118,3 +118,80 @@ def test_gemm_f16x3_rows_of_very_different_magnitude():
     scale = np.abs(A.astype(np.float64)).max(axis=1)[:, None] * np.abs(B.astype(np.float64)).max(axis=1)[None, :] * np.sqrt(K)
     assert np.all(np.isfinite(got))
     assert (np.abs(got - exact) / scale).max() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(256, 1024, 1024, 0, 1), (256, 1024, 1024, 0, 0), (1024, 440, 256, 1, 0), (1000, 512, 1024, 0, 1),
+                                          (4096, 2048, 512, 0, 1), (24, 36, 20, 0, 1)])
+def test_gemm_ex_epilogue_matches_the_separate_steps(M, N, K, ta, tb):
+    """aslp_gemm_ex: activation of the result, derivative of an activation at its output, SGD apply -- against fp64, for shapes
+    that take the split-K reduce pass (folded), a large shape (separate launches behind the product) and a CUDA-core shape."""
+    import ctypes
+    import torch
+    import kaldi_aslp_b200 as KK
+    from tests.gpu_utils import lib, ptr, stream, sync
+    L = lib()
+
+    class Epi(ctypes.Structure):
+        _fields_ = [("act", ctypes.c_int), ("dact_y", ctypes.c_void_p), ("dact_ldy", ctypes.c_int), ("dact_kind", ctypes.c_int),
+                    ("update_w", ctypes.c_void_p), ("update_ldw", ctypes.c_int), ("update_lr", ctypes.c_float)]
+    rng = np.random.default_rng(M + N)
+    A = (rng.standard_normal((K, M) if ta else (M, K)) * 0.1).astype(np.float32)
+    B = (rng.standard_normal((N, K) if tb else (K, N)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    prod = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+    ld = (N + 3) // 4 * 4
+    f = ctypes.c_float
+    dA, dB, dbias = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(bias).cuda()
+    ws = torch.zeros(L.aslp_gemm_workspace_bytes(M, N, K) + 256, dtype=torch.uint8, device="cuda")
+
+    def run(C0, epi, with_bias, beta):
+        dC = torch.zeros((M, ld), device="cuda"); dC[:, :N] = torch.from_numpy(C0).cuda()
+        rc = L.aslp_gemm_ex(stream(), ta, tb, M, N, K, f(1.0), ptr(dA), A.shape[1], ptr(dB), B.shape[1], f(beta), ptr(dC), ld,
+                            ptr(dbias) if with_bias else None, f(0.0), 0, ptr(ws), ctypes.c_size_t(ws.numel() - 256), ctypes.byref(epi))
+        assert rc == 0, L.aslp_last_error()
+        sync()
+        return dC[:, :N].cpu().numpy()
+    zero = np.zeros((M, N), np.float32)
+    tol = 2e-5
+    # (1) forward: sigmoid / tanh / relu of product + bias
+    for kind, fn in ((0, lambda x: 1 / (1 + np.exp(-x))), (1, np.tanh), (2, lambda x: np.maximum(x, 0))):
+        got = run(zero, Epi(1 + kind, None, 0, 0, None, 0, 0.0), True, 0.0)
+        want = fn(prod + bias)
+        assert np.abs(got - want).max() < tol * max(1.0, np.abs(want).max()), kind
+    # (2) backward: product times f'(y)
+    y = rng.uniform(0.05, 0.95, size=(M, N)).astype(np.float32)
+    dy = torch.zeros((M, ld), device="cuda"); dy[:, :N] = torch.from_numpy(y).cuda()
+    for kind, fn in ((0, lambda yy: yy * (1 - yy)), (1, lambda yy: 1 - yy * yy), (2, lambda yy: (yy > 0).astype(np.float64))):
+        got = run(zero, Epi(0, dy.data_ptr(), ld, kind, None, 0, 0.0), False, 0.0)
+        want = fn(y.astype(np.float64)) * prod
+        assert np.abs(got - want).max() < tol * max(1.0, np.abs(want).max()), kind
+    # (3) weight gradient with momentum + SGD apply
+    corr0 = rng.standard_normal((M, N)).astype(np.float32)
+    W0 = rng.standard_normal((M, N)).astype(np.float32)
+    dW = torch.zeros((M, ld), device="cuda"); dW[:, :N] = torch.from_numpy(W0).cuda()
+    got_corr = run(corr0, Epi(0, None, 0, 0, dW.data_ptr(), ld, 0.01), False, 0.9)
+    want_corr = 0.9 * corr0 + prod
+    assert np.abs(got_corr - want_corr).max() < tol * np.abs(want_corr).max()
+    got_W = dW[:, :N].cpu().numpy()
+    assert np.abs(got_W - (W0 - 0.01 * want_corr)).max() < tol * np.abs(W0).max()
+
+
+@pytest.mark.parametrize("rows,cols", [(256, 1024), (1000, 1500), (7, 33), (5000, 512)])
+def test_bias_grad_update(rows, cols):
+    import ctypes
+    import torch
+    from tests.gpu_utils import lib, ptr, stream, sync
+    L = lib()
+    rng = np.random.default_rng(rows)
+    ld = (cols + 3) // 4 * 4
+    d = rng.standard_normal((rows, cols)).astype(np.float32)
+    b0, c0 = rng.standard_normal(cols).astype(np.float32), rng.standard_normal(cols).astype(np.float32)
+    dd = torch.zeros((rows, ld), device="cuda"); dd[:, :cols] = torch.from_numpy(d).cuda()
+    db, dc = torch.zeros(ld, device="cuda"), torch.zeros(ld, device="cuda")
+    db[:cols] = torch.from_numpy(b0).cuda(); dc[:cols] = torch.from_numpy(c0).cuda()
+    f = ctypes.c_float
+    assert L.aslp_bias_grad_update(stream(), ptr(db), ptr(dc), ptr(dd), ld, rows, cols, f(0.9), f(0.05)) == 0
+    sync()
+    want_c = 0.9 * c0.astype(np.float64) + d.astype(np.float64).sum(axis=0)
+    assert np.abs(dc[:cols].cpu().numpy() - want_c).max() < 1e-5 * max(1.0, np.abs(want_c).max())
+    assert np.abs(db[:cols].cpu().numpy() - (b0 - 0.05 * want_c)).max() < 1e-5 * max(1.0, np.abs(want_c).max())

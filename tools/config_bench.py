@@ -33,7 +33,10 @@ CFG = {
 
 if __name__ == "__main__":
     NN.select_device(0)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for name, c in CFG.items():
+        if only and not name.startswith(only):
+            continue
         with tempfile.TemporaryDirectory() as td:
             p = os.path.join(td, "proto.txt")
             open(p, "w").write("<NnetProto>\n" + c["proto"] + "</NnetProto>\n")
@@ -59,4 +62,11 @@ if __name__ == "__main__":
             NN.device_sync(); a.record(); step(); NN.device_sync(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         ms = float(np.median(ts))
-        print(json.dumps({"config": name, "ms_per_minibatch": round(ms, 3), "frames_per_s": round(c["rows"] / ms * 1e3), "params": net.num_params}), flush=True)
+        import time
+        NN.device_sync(); h0 = time.perf_counter()
+        for _ in range(20):
+            step()
+        h1 = time.perf_counter(); NN.device_sync(); h2 = time.perf_counter()
+        host_ms, total_ms = (h1 - h0) / 20 * 1e3, (h2 - h0) / 20 * 1e3
+        print(json.dumps({"config": name, "ms_per_minibatch": round(ms, 3), "frames_per_s": round(c["rows"] / ms * 1e3), "params": net.num_params,
+                          "host_enqueue_ms": round(host_ms, 3), "ms_back_to_back": round(total_ms, 3)}), flush=True)
