@@ -131,8 +131,14 @@ class AffineTransform : public UpdatableComponent {
     return static_cast<long long>(rows) * n * k >= (1ll << 18) && rows % 4 == 0 && aslp_gemm_workspace_bytes(rows, n, k) > 0;
   }
   void Update(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
+    UpdateLinearity(input, diff);
+    UpdateBias(diff);
+  }
+  // The two halves of Update touch disjoint state (W, W_corr / bias, bias_corr), so Nnet::Backpropagate may run the weight
+  // half on the side stream, under the backward products of the layers below (nnet-nnet.cc).
+  void UpdateLinearity(const CuMatrixBase<BaseFloat>& input, const CuMatrixBase<BaseFloat>& diff) {
     aslp_stream_t st = CuStream();
-    const BaseFloat lr = opts_.learn_rate * learn_rate_coef_, lr_bias = opts_.learn_rate * bias_learn_rate_coef_;
+    const BaseFloat lr = opts_.learn_rate * learn_rate_coef_;
     const BaseFloat mmt = opts_.momentum, l2 = opts_.l2_penalty, l1 = opts_.l1_penalty;
     const int32 num_frames = input.NumRows();
     const size_t wsb = aslp_gemm_workspace_bytes(output_dim_, input_dim_, num_frames);
@@ -143,8 +149,6 @@ class AffineTransform : public UpdatableComponent {
     if (fused_apply) { epi.update_w = linearity_.Data(); epi.update_ldw = linearity_.Stride(); epi.update_lr = lr; }
     ASLP_OK(aslp_gemm_ex(st, 1, 0, output_dim_, input_dim_, num_frames, 1.0f, diff.Data(), diff.Stride(), input.Data(), input.Stride(), mmt,
                          linearity_corr_.Data(), linearity_corr_.Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
-    // bias_corr = mmt * bias_corr + column sums of diff; bias -= lr_bias * bias_corr: one launch
-    if (has_bias_) ASLP_OK(aslp_bias_grad_update(st, bias_.Data(), bias_corr_.Data(), diff.Data(), diff.Stride(), num_frames, output_dim_, mmt, lr_bias));
     if (!fused_apply) {
       // (LinearTransform regularises with the bare learn rate, nnet-linear-transform.h:140-155)
       const BaseFloat lr_reg = has_bias_ ? lr : opts_.learn_rate;
@@ -154,6 +158,11 @@ class AffineTransform : public UpdatableComponent {
       linearity_.AddMat(-lr, linearity_corr_);
     }
     if (max_norm_ > 0.0) ASLP_OK(aslp_max_norm_rows(st, linearity_.Data(), linearity_.Stride(), output_dim_, input_dim_, max_norm_));
+  }
+  void UpdateBias(const CuMatrixBase<BaseFloat>& diff) {
+    // bias_corr = mmt * bias_corr + column sums of diff; bias -= lr_bias * bias_corr: one launch
+    if (has_bias_) ASLP_OK(aslp_bias_grad_update(CuStream(), bias_.Data(), bias_corr_.Data(), diff.Data(), diff.Stride(), diff.NumRows(), output_dim_,
+                                                 opts_.momentum, opts_.learn_rate * bias_learn_rate_coef_));
   }
 
   const CuVector<BaseFloat>& GetBias() const { return bias_; }

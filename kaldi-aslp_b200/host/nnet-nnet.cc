@@ -144,7 +144,10 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_
     } else {
       c->Backpropagate(cin, output_buf_[i], output_diff_buf_[i], target);
     }
-    if (c->IsUpdatable()) dynamic_cast<UpdatableComponent*>(c)->Update(cin, output_diff_buf_[i]);   // update inside backprop (:126-129)
+    // update inside backprop (:126-129).  (Running an Affine's weight half on the side stream under the next layer's backward
+    // product was measured and dropped: cfg1 0.329 ms with it, 0.321 without -- a tcgen05 GEMM CTA takes a whole SM's shared
+    // memory, so two products never share the chip; profiles/r02_config_bench.jsonl)
+    if (c->IsUpdatable()) dynamic_cast<UpdatableComponent*>(c)->Update(cin, output_diff_buf_[i]);
     back_propagate_time_[i].first = Component::TypeToMarker(c->GetType());
     back_propagate_time_[i].second += tim.Elapsed();
     if (c->GetType() != Component::kInputLayer && !direct[i]) {
