@@ -22,6 +22,8 @@ typedef float BaseFloat;
 typedef int32 MatrixIndexT;
 
 extern int g_kaldi_verbose_level;
+inline void SetVerboseLevel(int i) { g_kaldi_verbose_level = i; }      // src/base/kaldi-error.h:61-64
+inline int GetVerboseLevel() { return g_kaldi_verbose_level; }
 
 class MessageLogger {
  public:

@@ -1,4 +1,5 @@
 #include "matrix.h"
+#include "cu-workspace.h"
 #include <cstring>
 
 namespace kaldi {
@@ -458,6 +459,63 @@ void CuMatrix<float>::Write(std::ostream& os, bool binary) const {
   CopyToMat(&tmp);
   tmp.Write(os, binary);
 }
+
+// ---- forwarder vocabulary: min / max / scalar add / log through the one-pass posterior kernel (aslp_posterior_finalize)
+static void MinMax(const CuMatrixBase<float>& m, float* mn, float* mx) {
+  if (m.NumRows() == 0 || m.NumCols() == 0) { *mn = 0.f; *mx = 0.f; return; }
+  float* stats = static_cast<float*>(CuWorkspace(8 * sizeof(float)));
+  // no log, no shift, no priors: the pass rewrites every element with itself and leaves min / max of the input in stats[0..1]
+  ASLP_OK(aslp_posterior_finalize(CuStream(), const_cast<float*>(m.Data()), m.Stride(), m.NumRows(), m.NumCols(), 0, 0.f, 0.f, nullptr, 0.f, stats));
+  float h[5];
+  ASLP_OK(aslp_memcpy_d2h(CuStream(), h, stats, sizeof(h)));
+  CuSync();
+  *mn = h[0]; *mx = h[1];
+}
+float CuMatrixBase<float>::Min() const { float a, b; MinMax(*this, &a, &b); return a; }
+float CuMatrixBase<float>::Max() const { float a, b; MinMax(*this, &a, &b); return b; }
+void CuMatrixBase<float>::Set(float value) {
+  if (rows_ == 0 || cols_ == 0) return;
+  CuVector<float> v(cols_, kUndefined);
+  v.Set(value);
+  ASLP_OK(aslp_add_vec_to_rows(CuStream(), data_, stride_, rows_, cols_, v.Data(), 1.0f, 0.0f));
+  CuSync();                                                 // `v` is released when we return
+}
+void CuMatrixBase<float>::Add(float value) {
+  if (rows_ == 0 || cols_ == 0) return;
+  CuVector<float> v(cols_, kUndefined);
+  v.Set(value);
+  ASLP_OK(aslp_add_vec_to_rows(CuStream(), data_, stride_, rows_, cols_, v.Data(), 1.0f, 1.0f));
+  CuSync();
+}
+void CuMatrixBase<float>::ApplySoftMaxPerRow(const CuMatrixBase<float>& src) {
+  KALDI_ASSERT(src.NumRows() == rows_ && src.NumCols() == cols_);
+  ASLP_OK(aslp_softmax_rows(CuStream(), data_, stride_, src.Data(), src.Stride(), rows_, cols_));
+}
+void CuMatrixBase<float>::ApplyLog() {
+  if (rows_ == 0 || cols_ == 0) return;
+  float* stats = static_cast<float*>(CuWorkspace(8 * sizeof(float)));
+  ASLP_OK(aslp_posterior_finalize(CuStream(), data_, stride_, rows_, cols_, 1, 0.f, 0.f, nullptr, 0.f, stats));
+}
+
+// ---- CuSubVector
+template <typename Real> void CuSubVector<Real>::CopyFromVec(const CuSubVector<Real>& src) {
+  KALDI_ASSERT(src.Dim() == dim_);
+  if (dim_ > 0) ASLP_OK(aslp_memcpy_d2d(CuStream(), data_, src.Data(), sizeof(Real) * dim_));
+}
+template <typename Real> void CuSubVector<Real>::CopyFromVec(const CuVector<Real>& src) {
+  KALDI_ASSERT(src.Dim() == dim_);
+  if (dim_ > 0) ASLP_OK(aslp_memcpy_d2d(CuStream(), data_, src.Data(), sizeof(Real) * dim_));
+}
+template <typename Real> void CuSubVector<Real>::CopyFromVec(const VectorBase<Real>& src) {
+  KALDI_ASSERT(src.Dim() == dim_);
+  if (dim_ > 0) { ASLP_OK(aslp_memcpy_h2d(CuStream(), data_, src.Data(), sizeof(Real) * dim_)); CuSync(); }
+}
+template <typename Real> void CuSubVector<Real>::CopyToVec(VectorBase<Real>* dst) const {
+  KALDI_ASSERT(dst->Dim() == dim_);
+  if (dim_ > 0) { ASLP_OK(aslp_memcpy_d2h(CuStream(), dst->Data(), data_, sizeof(Real) * dim_)); CuSync(); }
+}
+template <typename Real> void CuSubVector<Real>::SetZero() { if (dim_ > 0) ASLP_OK(aslp_memset(CuStream(), data_, 0, sizeof(Real) * dim_)); }
+template class CuSubVector<float>;
 
 // ------------------------------------------------------------------ device vectors
 template <typename Real> CuVector<Real>::~CuVector() { if (data_ != nullptr) aslp_free(data_); }

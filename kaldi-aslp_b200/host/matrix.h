@@ -133,6 +133,7 @@ class Vector : public VectorBase<Real> {
   std::vector<Real> d_;
 };
 
+template <typename Real> class SubMatrix;
 template <typename Real>
 class MatrixBase {
  public:
@@ -156,6 +157,7 @@ class MatrixBase {
     for (int32 r = 0; r < r_; ++r) for (int32 c = 0; c < c_; ++c) (*this)(r, c) = m(r, c);
   }
   void CopyRowFromVec(const VectorBase<Real>& v, int32 row) { Row(row).CopyFromVec(v); }
+  SubMatrix<Real> RowRange(int32 r0, int32 n) const;     // kaldi-matrix.h:202: a view, rows r0 .. r0 + n - 1
   void Write(std::ostream& os, bool binary) const;
  protected:
   MatrixBase() : data_(nullptr), r_(0), c_(0), stride_(0) {}
@@ -170,6 +172,9 @@ class SubMatrix : public MatrixBase<Real> {
   SubMatrix(const MatrixBase<Real>& m, int32 r0, int32 nr, int32 c0, int32 nc)
       : MatrixBase<Real>(const_cast<Real*>(m.RowData(r0)) + c0, nr, nc, m.Stride()) { KALDI_ASSERT(r0 + nr <= m.NumRows() && c0 + nc <= m.NumCols()); }
 };
+
+template <typename Real>
+inline SubMatrix<Real> MatrixBase<Real>::RowRange(int32 r0, int32 n) const { return SubMatrix<Real>(*this, r0, n, 0, c_); }
 
 template <typename Real>
 class Matrix : public MatrixBase<Real> {
@@ -221,6 +226,26 @@ class PinnedMatrix {
 template <typename Real> class CuMatrixBase;
 template <typename Real> class CuSubMatrix;
 template <typename Real> class CuMatrix;
+template <typename Real> class CuVector;
+
+// one row of a device matrix (CuMatrixBase::Row, src/aslp-cudamatrix/cu-matrix.h:575-590): what the forwarders' frame-skipping
+// loops copy row by row (aslp-nnet-forward.cc:163-179)
+template <typename Real>
+class CuSubVector {
+ public:
+  CuSubVector(Real* d, int32 n) : data_(d), dim_(n) {}
+  int32 Dim() const { return dim_; }
+  Real* Data() { return data_; }
+  const Real* Data() const { return data_; }
+  void CopyFromVec(const CuSubVector<Real>& src);            // device -> device
+  void CopyFromVec(const CuVector<Real>& src);
+  void CopyFromVec(const VectorBase<Real>& src);             // host -> device
+  void CopyToVec(VectorBase<Real>* dst) const;               // device -> host (synchronises)
+  void SetZero();
+ private:
+  Real* data_;
+  int32 dim_;
+};
 
 template <>
 class CuMatrixBase<float> {
@@ -242,6 +267,15 @@ class CuMatrixBase<float> {
   void AddMat(float alpha, const CuMatrixBase<float>& A);           // this += alpha * A
   void Scale(float alpha);
   double Sum() const;                                        // synchronises
+  CuSubVector<float> Row(int32 r) { KALDI_ASSERT(r >= 0 && r < rows_); return CuSubVector<float>(data_ + static_cast<size_t>(r) * stride_, cols_); }
+  const CuSubVector<float> Row(int32 r) const { KALDI_ASSERT(r >= 0 && r < rows_); return CuSubVector<float>(data_ + static_cast<size_t>(r) * stride_, cols_); }
+  // the forwarders' post-processing vocabulary (aslp-nnet-forward.cc:184-207); Min / Max synchronise
+  float Min() const;
+  float Max() const;
+  void Add(float value);
+  void ApplyLog();
+  void Set(float value);
+  void ApplySoftMaxPerRow(const CuMatrixBase<float>& src);   // cu-matrix.cc:1346-1380 (--add-softmax of the forwarders)
  protected:
   CuMatrixBase() : data_(nullptr), rows_(0), cols_(0), stride_(0) {}
   CuMatrixBase(float* d, int32 r, int32 c, int32 s) : data_(d), rows_(r), cols_(c), stride_(s) {}

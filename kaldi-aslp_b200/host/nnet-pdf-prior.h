@@ -57,6 +57,11 @@ class PdfPrior {
   }
   int32 Dim() const { return log_priors_.Dim(); }
   BaseFloat PriorScale() const { return prior_scale_; }
+  // nnet-pdf-prior.cc:75-86, for code written against the reference class: llk -= prior_scale * log_priors on every row
+  void SubtractOnLogpost(CuMatrixBase<BaseFloat>* llk) {
+    const float* lp = DeviceLogPriors(llk->NumCols());
+    ASLP_OK(aslp_add_vec_to_rows(CuStream(), llk->Data(), llk->Stride(), llk->NumRows(), llk->NumCols(), lp, -prior_scale_, 1.0f));
+  }
   // device pointer for aslp_posterior_finalize; same two errors as PdfPrior::SubtractOnLogpost (:73-84)
   const float* DeviceLogPriors(int32 num_cols) const {
     if (log_priors_.Dim() == 0) KALDI_ERR << "--class-frame-counts is empty: Cannot initialize priors without the counts.";

@@ -140,6 +140,20 @@ struct Int32VectorHolder {
     if (!SplitStringToIntegers(line, " \t\r", true, v)) KALDI_ERR << "Invalid integer vector line: " << line;
   }
 };
+// Vector<BaseFloat> ("FV" binary or "[ ... ]" text) and plain BaseFloat values: the per-frame / per-utterance weight tables of
+// the trainers (--frame-weights, --utt-weights; src/util/kaldi-holder.h KaldiObjectHolder / BasicHolder)
+struct BaseFloatVectorHolder {
+  typedef Vector<BaseFloat> T;
+  static void Read(std::istream& is, T* v) { const bool b = ReadBinaryFlag(is); v->Read(is, b); }
+};
+struct BaseFloatHolder {
+  typedef BaseFloat T;
+  static void Read(std::istream& is, T* v) {
+    const bool b = ReadBinaryFlag(is);
+    ReadBasicType(is, b, v);
+    if (!b) { std::string rest; std::getline(is, rest); }   // a text archive holds one value per line
+  }
+};
 struct PosteriorHolder {
   typedef Posterior T;
   // src/hmm/posterior.cc:57-99
@@ -235,9 +249,16 @@ template <class Holder>
 class RandomAccessTableReader {
  public:
   typedef typename Holder::T T;
-  explicit RandomAccessTableReader(const std::string& rspecifier) {
+  RandomAccessTableReader() : open_(false) {}
+  explicit RandomAccessTableReader(const std::string& rspecifier) : open_(false) { Open(rspecifier); }
+  bool Open(const std::string& rspecifier) {
+    map_.clear();
     for (SequentialTableReader<Holder> r(rspecifier); !r.Done(); r.Next()) map_[r.Key()] = r.Value();
+    open_ = true;
+    return true;
   }
+  bool IsOpen() const { return open_; }
+  bool Close() { map_.clear(); open_ = false; return true; }
   bool HasKey(const std::string& k) const { return map_.count(k) != 0; }
   const T& Value(const std::string& k) const {
     auto it = map_.find(k);
@@ -246,8 +267,12 @@ class RandomAccessTableReader {
   }
  private:
   std::map<std::string, T> map_;
+  bool open_;
 };
 
+typedef RandomAccessTableReader<BaseFloatVectorHolder> RandomAccessBaseFloatVectorReader;
+typedef RandomAccessTableReader<BaseFloatHolder> RandomAccessBaseFloatReader;
+typedef RandomAccessTableReader<MatrixHolder> RandomAccessBaseFloatMatrixReader;
 typedef SequentialTableReader<MatrixHolder> SequentialBaseFloatMatrixReader;
 typedef RandomAccessTableReader<PosteriorHolder> RandomAccessPosteriorReader;
 typedef RandomAccessTableReader<Int32VectorHolder> RandomAccessInt32VectorReader;

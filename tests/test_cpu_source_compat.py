@@ -19,6 +19,16 @@ MAINS = [
     "aslp-nnetbin/aslp-nnet-train-ctc-streams.cc",
     "aslp-nnetbin/aslp-nnet-train-blstm-parallel.cc",
     "aslp-nnetbin/aslp-nnet-info.cc",
+    "aslp-nnetbin/aslp-nnet-copy.cc",
+    "aslp-nnetbin/aslp-nnet-init.cc",
+    "aslp-nnetbin/aslp-nnet-train-perutt.cc",
+    "aslp-nnetbin/aslp-nnet-train-mse.cc",
+    "aslp-nnetbin/aslp-nnet-train-blstm-streams.cc",
+    "aslp-nnetbin/aslp-nnet-train-lstm-streams-skip.cc",
+    "aslp-nnetbin/aslp-nnet-forward.cc",
+    "aslp-nnetbin/aslp-nnet-forward-skip.cc",
+    "aslp-nnetbin/aslp-nnet-forward-blstm-lc.cc",
+    "aslp-nnetbin/aslp-nnet-forward-mimo.cc",
     "aslp-parallelbin/aslp-nnet-train-lc-blstm-streams-worker.cc",
     "aslp-parallelbin/aslp-nnet-train-frame-worker.cc",
     "aslp-parallelbin/aslp-nnet-train-lstm-stream-worker.cc",

@@ -70,3 +70,60 @@ def test_unmodified_reference_worker_main_single_rank(tmp_path):
 def test_unmodified_reference_info_main():
     log = run("aslp-nnet-info", [os.path.join(GOLD, "cli_lc", "init.nnet")])
     assert "BLstmProjectedStreamsLC" in log and "num-components" in log
+
+
+@needs_dropin
+def test_unmodified_reference_perutt_main_on_our_library(tmp_path):
+    """aslp-nnet-train-perutt (BASELINE cfg4's trainer): frame-weight / utterance-weight table readers, length tolerance, the
+    learn_rate / 1024 quirk -- the reference's own main() on our classes, against the model its CPU build wrote"""
+    d = os.path.join(GOLD, "cli_fsmn")
+    out = str(tmp_path / "out.nnet")
+    flags = open(os.path.join(d, "args.txt")).read().split()
+    log = run("aslp-nnet-train-perutt", flags + ["ark:" + os.path.join(d, "feats.ark"), "ark:" + os.path.join(d, "post.ark"),
+                                                 os.path.join(d, "init.nnet"), out])
+    ref_log = open(os.path.join(d, "ref_train.log")).read()
+    done = lambda s: re.findall(r"Done (\d+) files, (\d+) with no tgt_mats, (\d+) with other errors", s)[-1]
+    assert done(log) == done(ref_log)
+    check_model(out, "cli_fsmn")
+
+
+def _fwd_cases():
+    from tests.test_gpu_cli import fwd_cases
+    return fwd_cases()
+
+
+@needs_dropin
+@pytest.mark.parametrize("name,exe,case,flags", _fwd_cases(), ids=[c[0] for c in _fwd_cases()])
+def test_unmodified_reference_forwarders_on_our_library(name, exe, case, flags, tmp_path):
+    """the reference's forwarder mains (CuMatrix::Row / Min / Max / Add / ApplyLog / ApplySoftMaxPerRow, PdfPrior::SubtractOnLogpost,
+    Matrix::RowRange ...) on our library, against the archives their own CPU build wrote (tests/golden/cli_fwd)"""
+    from tests.test_gpu_cli import read_feats_ark
+    if not os.path.exists(os.path.join(DROPIN, exe)):
+        pytest.skip(exe + " not built")
+    d = os.path.join(GOLD, "cli_fwd")
+    out = str(tmp_path / "out.ark")
+    args = flags.replace("@GOLD@", d).split()
+    run(exe, args + [os.path.join(GOLD, case, "ref_out.nnet"), "ark:" + os.path.join(GOLD, case, "feats.ark"), "ark:" + out])
+    want, got = read_feats_ark(os.path.join(d, name + ".ark")), read_feats_ark(out)
+    assert list(got) == list(want)
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        big = np.abs(want[k]) >= 1e18
+        assert np.array_equal(big, np.abs(got[k]) >= 1e18), k
+        scale = max(1.0, float(np.max(np.abs(want[k][~big]))))
+        assert np.max(np.abs(got[k][~big] - want[k][~big])) / scale < RTOL, (k, np.max(np.abs(got[k][~big] - want[k][~big])))
+
+
+@needs_dropin
+def test_unmodified_reference_init_and_copy_mains(tmp_path):
+    """aslp-nnet-init --seed=777 must write the reference's initial model; aslp-nnet-copy must round-trip it byte for byte"""
+    d = os.path.join(GOLD, "cli_frame")
+    if not os.path.exists(os.path.join(d, "proto.txt")) or not os.path.exists(os.path.join(DROPIN, "aslp-nnet-init")):
+        pytest.skip("fixture or binary missing")
+    out = str(tmp_path / "init.nnet")
+    run("aslp-nnet-init", ["--seed=777", "--binary=true", os.path.join(d, "proto.txt"), out])
+    got, want = params(out), params(os.path.join(d, "init.nnet"))
+    assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-6 * np.max(np.abs(want))
+    cp = str(tmp_path / "copy.nnet")
+    run("aslp-nnet-copy", ["--binary=true", os.path.join(d, "init.nnet"), cp])
+    assert open(cp, "rb").read() == open(os.path.join(d, "init.nnet"), "rb").read()
