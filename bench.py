@@ -232,10 +232,16 @@ def secondary_metrics(lib, torch):
             assert lib.aslp_gemm(P(st), 0, 1, M, N, Kd, 1.0, P(A.data_ptr()), Kd, P(B.data_ptr()), Kd, 0.0, P(Cm.data_ptr()), N, None, 0.0, prec, None, 0) == 0
         ms = med(fn)
         tf = 2.0 * M * N * Kd / ms / 1e9
-        issued = tf * (3 if prec == 0 else 1)
+        # fractions on USEFUL flops (2 M N K).  The fp32-grade mode issues three kind::f16 tensor-core passes per useful product
+        # (fp16 hi / lo planes, gemm_f16x3.cuh: the operand split launches are inside `ms`), the TF32 mode one kind::tf32 pass.
+        tf32_peak, f16_peak = (tf_peak / 2.0, tf_peak) if tf_peak else (None, None)
         out["gemm_%dx%dx%d_%s" % (M, N, Kd, name)] = {
-            "useful_TFLOPs": tf, "ms": ms, "tensor_pipe_frac": issued / (tf_peak / 2.0) if tf_peak else None,
-            "peak": "TF32 dense = sustained bf16 / 2 = %.0f TFLOP/s; 3xTF32 issues 3 MMAs per useful one" % (tf_peak / 2.0)}
+            "useful_TFLOPs": tf, "ms": ms,
+            "tensor_pipe_frac": tf / tf32_peak if tf32_peak else None,
+            "issued_frac_of_its_pipe": (3.0 * tf / f16_peak if prec == 0 else tf / tf32_peak) if tf_peak else None,
+            "peak": "tensor_pipe_frac = useful TFLOP/s over the dense TF32 peak (sustained bf16 / 2 = %.0f TFLOP/s, MEASURED_PEAKS.json); "
+                    "issued_frac_of_its_pipe counts the MMAs actually issued (3 fp16 passes against the %.0f TFLOP/s fp16 / bf16 peak for "
+                    "3xtf32 mode, 1 TF32 pass for tf32 mode)" % (tf_peak / 2.0, tf_peak)}
     return out
 
 
