@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(NT, 1) lstm_bwd_t_kernel(Launch L) {
 #if ASLP_BWD_T_FP16
       // largest |dgifo| of every stream column over this warp's four cells (lanes with equal lane & 7)
       float m4 = fmaxf(fmaxf(fabsf(dg), fabsf(di)), fmaxf(fabsf(df), fabsf(dout)));
-      m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, 8));
-      m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, 16));
+      m4 = fmaxf(m4, ::__shfl_xor_sync(0xffffffffu, m4, 8));      // (global overload: <cuda_fp16.h> sits inside this namespace and its __half shuffles would hide the float one)
+      m4 = fmaxf(m4, ::__shfl_xor_sync(0xffffffffu, m4, 16));
       if (lane < 8) cmx[warp * 8 + lane] = m4;
 #endif
     } else {

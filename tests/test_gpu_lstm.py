@@ -36,7 +36,7 @@ def make_dir(rng, T, S, C, R, D, scale=None):
     return p
 
 
-def run_case(T, S, C, R, ndirs, seed=0, with_state=True, seq_len=None, reverse_first=False):
+def run_case(T, S, C, R, ndirs, seed=0, with_state=True, seq_len=None, reverse_first=False, od_scale=None):
     import torch
     import kaldi_aslp_b200 as K
     from tests.gpu_utils import DMat, dvec, lib, ok, ptr, stream, sync, P
@@ -93,6 +93,8 @@ def run_case(T, S, C, R, ndirs, seed=0, with_state=True, seq_len=None, reverse_f
     for di in range(ndirs):
         p, want, reverse, _ = dirs_np[di]
         od = rng.standard_normal((T * S, R if R > 0 else C)).astype(np.float32)
+        if od_scale is not None:                         # per-(frame, cell) magnitudes spread over many decades
+            od = (od * od_scale(rng, od.shape)).astype(np.float32)
         dwant = O.lstm_dir_bwd(want, od, p["w_r"], p.get("w_rm"), (p["pi"], p["pf"], p["po"]), T, S, C, R, reverse=reverse)
         d0 = np.zeros(((T + 2) * S, W), np.float32)
         oc = slice(7 * C, 7 * C + R) if R > 0 else slice(6 * C, 7 * C)
@@ -171,3 +173,17 @@ def test_backward_recurrence_forms(T, S, C, ndirs, form, monkeypatch):
     errs, berrs = run_case(T, S, C, 0, ndirs, seed=11)
     assert max(errs) < RTOL, errs
     assert max(berrs) < (5 * RTOL if T >= 300 else RTOL), berrs
+
+
+@pytest.mark.parametrize("T,S,C", [(24, 16, 320), (12, 8, 64)])
+def test_backward_tiny_and_widely_spread_derivatives(T, S, C, monkeypatch):
+    """The transposed backward kernel scales every stream column of its fp16-split operand by a power of two taken from the
+    column's largest |dgifo| over the CTA's 64 rows.  Late in a long utterance those derivatives are tiny (1e-9 is ordinary) and
+    differ by many decades between neighbouring cells; the column maximum has to be exact in fp32 for that -- a maximum
+    that went through fp16 on its way across lanes (flushes below 6e-8) picks a scale that overflows the real maximum.
+    Output derivatives between 1e-13 and 1e-7 here: no Inf / NaN, and the usual bound relative to the largest value."""
+    monkeypatch.setenv("ASLP_LSTM_KERNEL", "mma")
+    monkeypatch.setenv("ASLP_LSTM_BWD_T", "1")
+    spread = lambda rng, shape: 10.0 ** rng.uniform(-13.0, -7.0, size=shape)
+    errs, berrs = run_case(T, S, C, 0, 2, seed=5, od_scale=spread)
+    assert np.all(np.isfinite(berrs)) and max(berrs) < RTOL, berrs

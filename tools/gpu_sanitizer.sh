@@ -13,15 +13,28 @@ echo "# compute-sanitizer $(compute-sanitizer --version | head -2 | tail -1) on 
 run() {
   local tool=$1 name=$2 file=$3 sel=$4
   echo "## --tool $tool: pytest $file -k \"$sel\"" >> $OUT
-  timeout -s KILL 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 python -m pytest $file -q -m gpu -p no:cacheprovider -x -k "$sel" > gpurun_out/san_$name.log 2>&1
+  timeout -s KILL 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 python -m pytest $file -q -m gpu -p no:cacheprovider -k "$sel" > gpurun_out/san_$name.log 2>&1
   echo "exit code $? (99 = the sanitizer reported errors, 137 = timed out)" >> $OUT
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Error:|Race reported|Invalid|hazard" gpurun_out/san_$name.log | sort | uniq -c | head -20 >> $OUT
 }
-run memcheck mem_lstm tests/test_gpu_lstm.py "$LSTM"
-run memcheck mem_bwd tests/test_gpu_lstm.py "$BWD"
-run memcheck mem_ctc tests/test_gpu_ctc.py "$CTC"
-run memcheck mem_gemm tests/test_gpu_gemm.py "$GEMM"
-run racecheck race_lstm tests/test_gpu_lstm.py "$LSTM"
-run racecheck race_bwd tests/test_gpu_lstm.py "$BWD"
-run racecheck race_ctc tests/test_gpu_ctc.py "$CTC"
+if [ "$1" == "all" ]; then          # whole test files (about ten minutes)
+  ALL='not full_size and not many_utts'
+  run memcheck mem_lstm_all tests/test_gpu_lstm.py "$ALL"
+  run memcheck mem_ctc_all tests/test_gpu_ctc.py "$ALL"
+  run memcheck mem_eesen_all tests/test_gpu_ctc_eesen.py "$ALL"
+  run memcheck mem_gemm_all tests/test_gpu_gemm.py "$ALL"
+  run memcheck mem_pointwise_all tests/test_gpu_pointwise.py "$ALL"
+  run racecheck race_lstm_all tests/test_gpu_lstm.py "$ALL"
+  run racecheck race_ctc_all tests/test_gpu_ctc.py "$ALL"
+  run racecheck race_eesen_all tests/test_gpu_ctc_eesen.py "$ALL"
+  run racecheck race_pointwise_all tests/test_gpu_pointwise.py "$ALL"
+else
+  run memcheck mem_lstm tests/test_gpu_lstm.py "$LSTM"
+  run memcheck mem_bwd tests/test_gpu_lstm.py "$BWD"
+  run memcheck mem_ctc tests/test_gpu_ctc.py "$CTC"
+  run memcheck mem_gemm tests/test_gpu_gemm.py "$GEMM"
+  run racecheck race_lstm tests/test_gpu_lstm.py "$LSTM"
+  run racecheck race_bwd tests/test_gpu_lstm.py "$BWD"
+  run racecheck race_ctc tests/test_gpu_ctc.py "$CTC"
+fi
 cat $OUT
