@@ -8,8 +8,9 @@
 // sweeps meeting in the middle, gradient formed from the half-spilled rows; 1.13 x the algorithmic HBM bytes).
 // Otherwise four launches per minibatch, labels uploaded once:
 //   0. ctc_csr_kernel     : per utterance, the states of every label (for the per-label sums of pass 3);
-//   1. ctc_softmax_kernel : warp per (t, n) row: probabilities and the per-state log-probabilities lp[n][t][i]
-//                           into the workspace (HBM-bound);
+//   1. ctc_softmax_kernel : warp per (t, n) row: the log-softmax row (K floats) into the workspace (HBM-bound); the sweeps
+//                           gather log p[t][label(i)] from it, the gradient takes p = exp(log p) from it -- round 1 also
+//                           wrote the probabilities and a per-state row lp[n][t][i], 3.8 x the bytes;
 //   2. ctc_sweep_kernel   : the alpha sweep and the beta sweep of an utterance are two CTAs running concurrently; one
 //                           state per thread, one barrier per time step, lp rows prefetched a step ahead -- the
 //                           recurrence is latency-bound, so nothing that is not recurrent stays in the loop.  Exactly
@@ -29,10 +30,21 @@ __device__ __forceinline__ float neg_inf() { return -INFINITY; }
 // select.  Without branches the independent states a thread owns overlap their SFU latencies.
 __device__ __forceinline__ float log_plus(float p1, float p2) {
   const float m = fmaxf(p1, p2);
+#ifdef ASLP_PRECISE_MATH
   const float d = (m == neg_inf()) ? 0.f : fabsf(p1 - p2);
-  // SFU forms (common.cuh): the absolute error (< 4e-7) is three orders below one ulp of the alpha / beta values this is
-  // added to on utterances of the BASELINE size (|alpha| ~ 3e3, ulp 2.4e-4); a fifth of the instructions of log1pf(expf())
   const float r = aslp_log1p_of_exp_neg(d) + m;
+#else
+  // SFU forms spelled out: ex2.approx.ftz / lg2.approx.ftz, the two instructions __expf / __logf issue, without their
+  // denormal-range fix-up (exp(-d) below 2^-126 adds nothing to 1 anyway): 10 instructions instead of 16 on the recurrent chain
+  // of every sweep.  The argument of the log lies in (1, 2], where lg2.approx has an absolute error < 4e-7 -- three orders below
+  // one ulp of the alpha / beta values this is added to on utterances of the BASELINE size (|alpha| ~ 3e3, ulp 2.4e-4).  Both
+  // arguments at -inf make the difference NaN; the final select returns -inf for that case, so no operand needs guarding.
+  const float d = fabsf(p1 - p2) * -1.4426950408889634f;
+  float e, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+  const float r = fmaf(l, 0.6931471805599453f, m);
+#endif
   return (m == neg_inf()) ? neg_inf() : r;
 }
 
@@ -60,29 +72,24 @@ __global__ void ctc_csr_kernel(int* cls_start_all, int* cls_list_all, const int*
   }
 }
 
-// ---- 1. softmax of every valid (t, n) row, plus the per-state log-probabilities lp[n][t][i] = log p[t][lab_n(i)] that
-// the two sweeps consume (contiguous, prefetchable rows instead of a dependent gather on the recurrent chain)
-__global__ void ctc_softmax_kernel(float* probs, float* lp_all, const float* acts, const int* in_len, const int* flat_labels,
-                                   const int* label_off, const int* label_len, int K, int mb, int maxT, int maxS) {
+// ---- 1. log-softmax of every valid (t, n) row (the sweeps prefetch their per-state gather from it two steps ahead)
+__global__ void ctc_softmax_kernel(float* logp_all, const float* acts, const int* in_len, int K, int mb, int maxT) {
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long rows = (long long)maxT * mb;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
     const int n = (int)(row % mb), t = (int)(row / mb);
     if (t >= in_len[n]) continue;
     const float* x = acts + row * K;
-    float* p = probs + row * K;
+    float* lp = logp_all + row * K;
     float mx = -INFINITY;
     for (int k = lane; k < K; k += 32) mx = fmaxf(mx, x[k]);
     mx = warp_max(mx);
     float den = 0.f;
     for (int k = lane; k < K; k += 32) den += expf(x[k] - mx);
     den = warp_sum(den);
-    for (int k = lane; k < K; k += 32) p[k] = expf(x[k] - mx) / den;
-    __syncwarp();                                      // the row just written is re-read by other lanes below
-    const int L = label_len[n], S = 2 * L + 1;
-    const int* labels = flat_labels + label_off[n];
-    float* lp = lp_all + ((size_t)n * maxT + t) * maxS;
-    for (int i = lane; i < S; i += 32) lp[i] = logf(p[(i & 1) ? labels[i >> 1] : 0]);
+    const float lden = logf(den);
+    // log p = (x - max) - log(sum); a probability that underflows to 0 has log p = -inf, as log(probs) in the reference
+    for (int k = lane; k < K; k += 32) lp[k] = expf(x[k] - mx) == 0.f ? neg_inf() : (x[k] - mx) - lden;
   }
 }
 
@@ -91,9 +98,8 @@ __global__ void ctc_softmax_kernel(float* probs, float* lp_all, const float* act
 // is a shuffle from the owning lane instead of a re-read of the row just written.  The first version was instruction-bound
 // (ncu: 677 warp instructions per row, SM throughput 52 %): two expf per class, 2L+1 logf per row, 64-bit index division.
 template <int KS>
-__global__ void __launch_bounds__(256) ctc_softmax_reg_kernel(float* __restrict__ probs, float* __restrict__ lp_all,
-                                                              const float* __restrict__ acts, const int* in_len, const int* flat_labels,
-                                                              const int* label_off, const int* label_len, int K, int mb, int maxT, int maxS) {
+__global__ void __launch_bounds__(256) ctc_softmax_reg_kernel(float* __restrict__ logp_all, const float* __restrict__ acts, const int* in_len,
+                                                              int K, int mb, int maxT) {
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
   const unsigned rows = (unsigned)maxT * (unsigned)mb;
   for (unsigned row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
@@ -105,29 +111,16 @@ __global__ void __launch_bounds__(256) ctc_softmax_reg_kernel(float* __restrict_
 #pragma unroll
     for (int q = 0; q < KS; ++q) { const int k = lane + 32 * q; v[q] = k < K ? x[k] : -INFINITY; mx = fmaxf(mx, v[q]); }
     mx = warp_max(mx);
-    float den = 0.f;
+    float den = 0.f, ex[KS];
 #pragma unroll
-    for (int q = 0; q < KS; ++q) { v[q] = expf(v[q] - mx); den += v[q]; }      // exp(-inf) = 0 for the padding classes
+    for (int q = 0; q < KS; ++q) { ex[q] = expf(v[q] - mx); den += ex[q]; }      // exp(-inf) = 0 for the padding classes
     den = warp_sum(den);
-    float* p = probs + (size_t)row * K;
-    float lg[KS];
+    const float lden = logf(den);
+    float* lp = logp_all + (size_t)row * K;
 #pragma unroll
     for (int q = 0; q < KS; ++q) {
       const int k = lane + 32 * q;
-      v[q] = v[q] / den;
-      if (k < K) p[k] = v[q];
-      lg[q] = logf(v[q]);
-    }
-    const int S = 2 * label_len[n] + 1;
-    const int* labels = flat_labels + label_off[n];
-    float* lp = lp_all + ((size_t)n * maxT + t) * maxS;
-    for (int ib = 0; ib < S; ib += 32) {               // warp-uniform trip count: every lane takes part in the shuffles
-      const int i = ib + lane;
-      const int c = (i < S && (i & 1)) ? labels[i >> 1] : 0;
-      float r = 0.f;
-#pragma unroll
-      for (int q = 0; q < KS; ++q) { const float g = __shfl_sync(0xffffffffu, lg[q], c & 31); if ((c >> 5) == q) r = g; }
-      if (i < S) lp[i] = r;
+      if (k < K) lp[k] = ex[q] == 0.f ? neg_inf() : (v[q] - mx) - lden;
     }
   }
 }
@@ -153,9 +146,9 @@ __device__ __forceinline__ float block_log_plus(float v, float* red) {
 // keep their previous value) are reproduced exactly.  alpha rows go to alphas_ws; beta rows, masked to the window,
 // to betas_ws; the per-label sums and the gradient are a separate, fully parallel pass.
 template <int G>
-__global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float* alphas_ws, float* betas_ws, float* costs_dev,
+__global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* logp_all, float* alphas_ws, float* betas_ws, float* costs_dev,
                                                       int* valid_dev, const int* flat_labels, const int* label_off,
-                                                      const int* label_len, const int* in_len, int maxT, int maxS) {
+                                                      const int* label_len, const int* in_len, int maxT, int maxS, int K, int mb) {
   extern __shared__ int smem_i[];
   const int n = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
@@ -193,8 +186,14 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
     if (tid == 0 && !is_beta) { costs_dev[n] = 0.f; valid_dev[n] = 0; }
     return;
   }
-  const float* lp = lp_all + (size_t)n * maxT * maxS;
+  // log p of row t, state i: gathered from the log-softmax row of (t, n) (K floats) by the state's class -- the per-state
+  // rows lp[t][i] that used to be materialised for this were 2.8 x the bytes of the row they were gathered from
+  const float* logp = logp_all + (size_t)n * K;
+  const size_t rstride = (size_t)mb * K;
   constexpr int MAXI = 4;                 // states per thread (S <= 4 G), kept in registers
+  int labv[MAXI];
+#pragma unroll
+  for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; labv[j] = i < S ? lab[i] : 0; }
   float* prev = rowA;
   float* cur = rowB;
 
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
     int end = S > 1 ? 2 : 1;
     float lpn[MAXI];
 #pragma unroll
-    for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[i] : 0.f; }
+    for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? logp[labv[j]] : 0.f; }
 #pragma unroll
     for (int j = 0; j < MAXI; ++j) {
       const int i = j * G + tid;
@@ -217,7 +216,7 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
     }
     if (T > 1) {
 #pragma unroll
-      for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)maxS + i] : 0.f; }
+      for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? logp[rstride + labv[j]] : 0.f; }
     }
     __syncthreads();
     for (int t = 1; t < T; ++t) {
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
       for (int j = 0; j < MAXI; ++j) lpc[j] = lpn[j];
       if (t + 1 < T) {
 #pragma unroll
-        for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(t + 1) * maxS + i] : 0.f; }
+        for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? logp[(size_t)(t + 1) * rstride + labv[j]] : 0.f; }
       }
 #pragma unroll
       for (int j = 0; j < MAXI; ++j) {
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
   int end = (T > (S / 2) + repeats) ? S : S - 1;
   float lpn[MAXI];
 #pragma unroll
-  for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(T - 1) * maxS + i] : 0.f; }
+  for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? logp[(size_t)(T - 1) * rstride + labv[j]] : 0.f; }
 #pragma unroll
   for (int j = 0; j < MAXI; ++j) {
     const int i = j * G + tid;
@@ -280,7 +279,7 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
   if (tid < 2) { prev[S + tid] = neg_inf(); cur[S + tid] = neg_inf(); }   // guards for the i+1 / i+2 reads
   if (T > 1) {
 #pragma unroll
-    for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(T - 2) * maxS + i] : 0.f; }
+    for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? logp[(size_t)(T - 2) * rstride + labv[j]] : 0.f; }
   }
   __syncthreads();
   for (int t = T - 2; t >= 0; --t) {
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
     for (int j = 0; j < MAXI; ++j) lpc[j] = lpn[j];
     if (t > 0) {
 #pragma unroll
-      for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? lp[(size_t)(t - 1) * maxS + i] : 0.f; }
+      for (int j = 0; j < MAXI; ++j) { const int i = j * G + tid; lpn[j] = i < S ? logp[(size_t)(t - 1) * rstride + labv[j]] : 0.f; }
     }
 #pragma unroll
     for (int j = 0; j < MAXI; ++j) {
@@ -326,10 +325,10 @@ __global__ void __launch_bounds__(G) ctc_sweep_kernel(const float* lp_all, float
 // two steps ahead.  Same recurrences, window arithmetic and in-place beta semantics as ctc_sweep_kernel above
 // (cpu_ctc.h:217-262, :269-367).  Used once the minibatch alone fills the chip (see the dispatch in compute_ctc_loss).
 template <int NS>
-__global__ void __launch_bounds__(64) ctc_sweep_warp_kernel(const float* __restrict__ lp_all, float* __restrict__ alphas_ws,
+__global__ void __launch_bounds__(64) ctc_sweep_warp_kernel(const float* __restrict__ logp_all, float* __restrict__ alphas_ws,
                                                             float* __restrict__ betas_ws, float* costs_dev, int* valid_dev,
                                                             const int* flat_labels, const int* label_off, const int* label_len,
-                                                            const int* in_len, int maxT, int maxS) {
+                                                            const int* in_len, int maxT, int maxS, int K, int mb) {
   extern __shared__ int smem_i[];
   const int n = blockIdx.x;
   const int T = in_len[n], L = label_len[n], S = 2 * L + 1;
@@ -361,7 +360,11 @@ __global__ void __launch_bounds__(64) ctc_sweep_warp_kernel(const float* __restr
     if (tid == 0) { costs_dev[n] = 0.f; valid_dev[n] = 0; }
     return;
   }
-  const float* lp = lp_all + (size_t)n * maxT * maxS;
+  const float* logp = logp_all + (size_t)n * K;           // log-softmax rows of this utterance, mb * K floats apart
+  const size_t rstride = (size_t)mb * K;
+  int labv[NS];                                           // class of the lane's states: the lp gather
+#pragma unroll
+  for (int j = 0; j < NS; ++j) { const int i = j * 32 + lane; labv[j] = (i < S && (i & 1)) ? labels[i >> 1] : 0; }
   // third-term flags: alpha may come from i-2 / beta from i+2 only across a blank between two DIFFERENT labels
   bool skip_a[NS], skip_b[NS];
 #pragma unroll
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(64) ctc_sweep_warp_kernel(const float* __restr
   float prev[NS], lp1[NS], lp2[NS];       // lp rows of the next step and the one after
   auto load_row = [&](float (&dst)[NS], int t) {
 #pragma unroll
-    for (int j = 0; j < NS; ++j) { const int i = j * 32 + lane; dst[j] = (t >= 0 && t < T && i < S) ? lp[(size_t)t * maxS + i] : 0.f; }
+    for (int j = 0; j < NS; ++j) { const int i = j * 32 + lane; dst[j] = (t >= 0 && t < T && i < S) ? logp[(size_t)t * rstride + labv[j]] : 0.f; }
   };
 
   if (!is_beta) {
@@ -499,8 +502,8 @@ __global__ void ctc_grad_kernel(float* grads, const float* probs, const float* a
     for (int k = lane; k < K; k += 32) {
       float o = (k == 0) ? bl : neg_inf();
       for (int q = cls_start[k]; q < cls_start[k + 1]; ++q) { const int i = cls_list[q]; o = log_plus(al[i] + be[i], o); }
-      const float pk = p[k];
-      g[k] = (o == 0.0f || o == -INFINITY || pk == 0.0f) ? pk : pk - expf(o - logf(pk) - log_partition);
+      const float lpk = p[k], pk = expf(lpk);          // `probs` holds log-softmax rows: p = exp(log p)
+      g[k] = (o == 0.0f || o == -INFINITY || pk == 0.0f) ? pk : pk - expf(o - lpk - log_partition);
     }
   }
 }
@@ -523,15 +526,31 @@ __global__ void __launch_bounds__(256) ctc_grad_staged_kernel(float* __restrict_
     const int S = 2 * label_len[n] + 1;
     const float* al = alphas_ws + ((size_t)n * maxT + t) * maxS;
     const float* be = betas_ws + ((size_t)n * maxT + t) * maxS;
-    float bl = neg_inf();                              // blank: all even states (even lanes hold them), then a tree
+    // per-label sums of alpha * beta (cpu_ctc.h:296-301) as max-shifted sums: w[i] = exp(alpha_i + beta_i - M) into the staging
+    // row (one exponential per STATE), then o[k] = M + log(sum of w over the states of label k) (one logarithm per CLASS); the
+    // per-state log-add chains this replaces (two SFU operations and eight ALU operations per state on a dependent chain)
+    // made the kernel instruction-bound at 70 % SM throughput.  A state more than ~87 below the row's maximum adds nothing
+    // (its posterior is below 1e-38).
+    float M = neg_inf();
     for (int ib = 0; ib < S; ib += 32) {
       const int i = ib + lane;
       const float v = i < S ? al[i] + be[i] : neg_inf();
       if (i < S) ab[i] = v;
-      bl = log_plus((i & 1) ? neg_inf() : v, bl);
+      M = fmaxf(M, v);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bl = log_plus(bl, __shfl_xor_sync(0xffffffffu, bl, o));
+    M = warp_max(M);
+    __syncwarp();
+    float bs = 0.f;                                    // blank: all even states; they sit in the even lanes
+    for (int ib = 0; ib < S; ib += 32) {
+      const int i = ib + lane;
+      if (i < S) {
+        const float v = ab[i];
+        const float w = (v == neg_inf()) ? 0.f : aslp_exp(v - M);
+        ab[i] = w;
+        bs += (i & 1) ? 0.f : w;
+      }
+    }
+    bs = warp_sum(bs);
     __syncwarp();
     const int* cls_start = cls_start_all + (size_t)n * (K + 1);
     const int* cls_list = cls_list_all + (size_t)n * maxS;
@@ -539,11 +558,12 @@ __global__ void __launch_bounds__(256) ctc_grad_staged_kernel(float* __restrict_
     const float* p = probs + (size_t)row * K;
     float* g = grads + (size_t)row * K;
     for (int k = lane; k < K; k += 32) {
-      float o = (k == 0) ? bl : neg_inf();
+      float sum = (k == 0) ? bs : 0.f;
       const int q1 = cls_start[k + 1];
-      for (int q = cls_start[k]; q < q1; ++q) o = log_plus(ab[cls_list[q]], o);
-      const float pk = p[k];
-      g[k] = (o == 0.0f || o == -INFINITY || pk == 0.0f) ? pk : pk - aslp_exp(o - __logf(pk) - log_partition);
+      for (int q = cls_start[k]; q < q1; ++q) sum += ab[cls_list[q]];
+      const float o = (sum > 0.f && M != neg_inf()) ? M + __logf(sum) : neg_inf();
+      const float lpk = p[k], pk = expf(lpk);          // `probs` holds log-softmax rows: p = exp(log p)
+      g[k] = (o == 0.0f || o == -INFINITY || pk == 0.0f) ? pk : pk - aslp_exp(o - lpk - log_partition);
     }
     __syncwarp();                                      // the staging row is rewritten by the next row of this warp
   }
@@ -577,7 +597,7 @@ Sizes ctc_sizes(const int* label_lengths, const int* input_lengths, int K, int m
   z.costs = al((size_t)mb * sizeof(float));
   z.valid = al((size_t)mb * sizeof(int));
   z.betas = z.alphas;
-  z.lp = z.alphas;
+  z.lp = 0;                                              // (round 1 kept a per-state log-probability matrix here)
   z.meta = al((size_t)(3 * mb + z.sumL + 4) * sizeof(int));
   z.csr = al(((size_t)mb * (K + 1) + (size_t)mb * z.maxS) * sizeof(int));
   z.total = z.alphas + z.betas + z.lp + z.probs + z.costs + z.valid + z.meta + z.csr;
@@ -586,17 +606,17 @@ Sizes ctc_sizes(const int* label_lengths, const int* input_lengths, int K, int m
 
 template <int G>
 int launch_sweep(cudaStream_t st, int mb, size_t smem, const float* lp, float* alphas, float* betas, float* costs, int* valid,
-                 const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS) {
+                 const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS, int K) {
   ASLP_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ctc_sweep_kernel<G><<<dim3(mb, 2), G, smem, st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS);
+  ctc_sweep_kernel<G><<<dim3(mb, 2), G, smem, st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS, K, mb);
   ASLP_CHECK_LAUNCH();
   return 0;
 }
 
 template <int NS>
 int launch_sweep_warp(cudaStream_t st, int mb, const float* lp, float* alphas, float* betas, float* costs, int* valid,
-                      const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS) {
-  ctc_sweep_warp_kernel<NS><<<mb, 64, (size_t)2 * maxS * sizeof(int), st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS);
+                      const int* flat, const int* off, const int* llen, const int* ilen, int maxT, int maxS, int K) {
+  ctc_sweep_warp_kernel<NS><<<mb, 64, (size_t)2 * maxS * sizeof(int), st>>>(lp, alphas, betas, costs, valid, flat, off, llen, ilen, maxT, maxS, K, mb);
   ASLP_CHECK_LAUNCH();
   return 0;
 }
@@ -638,8 +658,8 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
   char* ws = (char*)workspace;
   float* alphas = (float*)ws;                      ws += z.alphas;
   float* betas = (float*)ws;                       ws += z.betas;
-  float* lp = (float*)ws;                          ws += z.lp;
-  float* probs = (float*)ws;                       ws += z.probs;
+  ws += z.lp;
+  float* probs = (float*)ws;                       ws += z.probs;      // log-softmax rows [maxT][mb][K]
   float* costs_dev = (float*)ws;                   ws += z.costs;
   int* valid_dev = (int*)ws;                       ws += z.valid;
   int* meta = (int*)ws;                            ws += z.meta;
@@ -700,11 +720,11 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
   if (row_blocks < 1) row_blocks = 1;
   {
     const bool small_rows = rows < (1ll << 31);
-    if (K <= 32 && small_rows) ctc_softmax_reg_kernel<1><<<row_blocks, 256, 0, st>>>(probs, lp, activations, d_ilen, d_flat, d_off, d_llen, K, mb, z.maxT, z.maxS);
-    else if (K <= 64 && small_rows) ctc_softmax_reg_kernel<2><<<row_blocks, 256, 0, st>>>(probs, lp, activations, d_ilen, d_flat, d_off, d_llen, K, mb, z.maxT, z.maxS);
-    else if (K <= 96 && small_rows) ctc_softmax_reg_kernel<3><<<row_blocks, 256, 0, st>>>(probs, lp, activations, d_ilen, d_flat, d_off, d_llen, K, mb, z.maxT, z.maxS);
-    else if (K <= 128 && small_rows) ctc_softmax_reg_kernel<4><<<row_blocks, 256, 0, st>>>(probs, lp, activations, d_ilen, d_flat, d_off, d_llen, K, mb, z.maxT, z.maxS);
-    else ctc_softmax_kernel<<<row_blocks, 256, 0, st>>>(probs, lp, activations, d_ilen, d_flat, d_off, d_llen, K, mb, z.maxT, z.maxS);
+    if (K <= 32 && small_rows) ctc_softmax_reg_kernel<1><<<row_blocks, 256, 0, st>>>(probs, activations, d_ilen, K, mb, z.maxT);
+    else if (K <= 64 && small_rows) ctc_softmax_reg_kernel<2><<<row_blocks, 256, 0, st>>>(probs, activations, d_ilen, K, mb, z.maxT);
+    else if (K <= 96 && small_rows) ctc_softmax_reg_kernel<3><<<row_blocks, 256, 0, st>>>(probs, activations, d_ilen, K, mb, z.maxT);
+    else if (K <= 128 && small_rows) ctc_softmax_reg_kernel<4><<<row_blocks, 256, 0, st>>>(probs, activations, d_ilen, K, mb, z.maxT);
+    else ctc_softmax_kernel<<<row_blocks, 256, 0, st>>>(probs, activations, d_ilen, K, mb, z.maxT);
     ++g_aslp_launches;
     if (cudaGetLastError() != cudaSuccess) return CTC_STATUS_EXECUTION_FAILED;
   }
@@ -725,7 +745,7 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
     const bool want_warp = z.maxS <= 256 && !force_block && (force_warp || mb >= aslp_num_sms() * 8);
     if (want_warp) {
       const int ns = (z.maxS + 31) / 32;
-#define ASLP_SWEEP_WARP(NSv) rc = launch_sweep_warp<NSv>(st, mb, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS)
+#define ASLP_SWEEP_WARP(NSv) rc = launch_sweep_warp<NSv>(st, mb, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K)
       switch (ns) {
         case 1: ASLP_SWEEP_WARP(1); break; case 2: ASLP_SWEEP_WARP(2); break; case 3: ASLP_SWEEP_WARP(3); break; case 4: ASLP_SWEEP_WARP(4); break;
         case 5: ASLP_SWEEP_WARP(5); break; case 6: ASLP_SWEEP_WARP(6); break; case 7: ASLP_SWEEP_WARP(7); break; default: ASLP_SWEEP_WARP(8); break;
@@ -733,12 +753,12 @@ ctcStatus_t compute_ctc_loss(const float* const activations, float* gradients, c
 #undef ASLP_SWEEP_WARP
     } else
     switch (G) {
-      case 32: rc = launch_sweep<32>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
-      case 64: rc = launch_sweep<64>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
-      case 128: rc = launch_sweep<128>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
-      case 256: rc = launch_sweep<256>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
-      case 512: rc = launch_sweep<512>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
-      default: rc = launch_sweep<1024>(st, mb, smem, lp, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS); break;
+      case 32: rc = launch_sweep<32>(st, mb, smem, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K); break;
+      case 64: rc = launch_sweep<64>(st, mb, smem, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K); break;
+      case 128: rc = launch_sweep<128>(st, mb, smem, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K); break;
+      case 256: rc = launch_sweep<256>(st, mb, smem, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K); break;
+      case 512: rc = launch_sweep<512>(st, mb, smem, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K); break;
+      default: rc = launch_sweep<1024>(st, mb, smem, probs, alphas, betas, costs_dev, valid_dev, d_flat, d_off, d_llen, d_ilen, z.maxT, z.maxS, K); break;
     }
     if (rc != 0) return CTC_STATUS_EXECUTION_FAILED;
   }

@@ -31,19 +31,6 @@ constexpr int CF_TB = 16;                // time steps per block (helper warps w
 constexpr int CF_KMAX = 128;
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-// log(exp(a) + exp(b)) with the SFU forms spelled out (ex2.approx.ftz / lg2.approx.ftz: the same two instructions __expf /
-// __logf issue, without their denormal-range fix-up -- exp(-d) below 2^-126 adds nothing to 1 anyway).  Both arguments at
-// -inf make the difference NaN; the final select returns -inf for that case, so no operand needs guarding.
-__device__ __forceinline__ float log_plus_sfu(float p1, float p2) {
-  const float m = fmaxf(p1, p2);
-  const float d = fabsf(p1 - p2) * -1.4426950408889634f;
-  float e, l;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d));
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-  const float r = fmaf(l, 0.6931471805599453f, m);
-  return (m == neg_inf()) ? neg_inf() : r;
-}
-
 struct CfSmem {
   int SP, K;
   __host__ __device__ size_t ints() const { return (size_t)4 * SP + (K + 1) + 8; }   // lab, ps, pe, cls_list, cls_start, scalars
@@ -285,7 +272,7 @@ ctc_fused_kernel(const float* __restrict__ acts, float* __restrict__ grads, floa
           const int t = q0 * CF_TB + kk;
           const int wx = s_inc[max(0, R0 + t + 1)], wy = a_end0 + e_inc[min(t, cap)];
           const float a = prev[0], b = prev[-1], c = prev[-2];
-          const float s3 = log_plus_sfu(log_plus_sfu(a, b), skip ? c : neg_inf());
+          const float s3 = log_plus(log_plus(a, b), skip ? c : neg_inf());
           const float v = (i >= wx && i < wy) ? s3 + lpp[kk * K] : neg_inf();
           if (st_live) {
             cur[0] = v;
@@ -329,8 +316,8 @@ ctc_fused_kernel(const float* __restrict__ acts, float* __restrict__ grads, floa
           const bool in_loop = i >= wx && i < endloop;
           const bool in_last = wy == S && i == S - 1;
           // outside the window the reference leaves the old value in place; the last state only adds the emission
-          const float s2 = log_plus_sfu(a, in_loop ? n1 : neg_inf());
-          const float s3 = log_plus_sfu(s2, (in_loop && skip) ? n2 : neg_inf());
+          const float s2 = log_plus(a, in_loop ? n1 : neg_inf());
+          const float s3 = log_plus(s2, (in_loop && skip) ? n2 : neg_inf());
           const float v = (in_loop || in_last) ? s3 + lpp[kk * K] : a;
           const float masked = (in_loop || in_last) ? v : neg_inf();
           if (st_live) {
