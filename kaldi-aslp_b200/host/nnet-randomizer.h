@@ -174,9 +174,9 @@ struct RandomizerReplay {
   void ConsumeMinibatches() { while (end - begin >= minibatch_size) begin += minibatch_size; }     // Done() / Next() until used up
 };
 
-class FrameDataReader {
+class FrameDataReaderSingle {
  public:
-  FrameDataReader(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const NnetDataRandomizerOptions& rand_opts)
+  FrameDataReaderSingle(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const NnetDataRandomizerOptions& rand_opts)
       : feature_reader_(feature_rspecifier), targets_reader_(targets_rspecifier), read_done_(false), sim_(rand_opts.randomizer_size, rand_opts.minibatch_size),
         sim_read_done_(false), feeder_([this](Block* b) { return FillBlock(b); }, /*attach_device=*/false) {
     feature_randomizer_.Init(rand_opts);
@@ -269,6 +269,107 @@ class FrameDataReader {
   bool sim_read_done_;
   CuMatrix<BaseFloat> block_dev_;
   BatchFeeder<Block> feeder_;              // last member: its thread uses everything above
+};
+
+// Several feature streams and several target streams shuffled by ONE mask (the multi-input / multi-output nets of
+// aslp-nnet-train-frame-mimo.cc; data-reader.cc:18-125): every stream has its own table and randomizer, the utterances must
+// come in the same order in every feature table, an utterance needs targets in every target table, and all streams of an
+// utterance must have the same number of frames.  Reads utterance by utterance on the calling thread (no feeder).
+class FrameDataReaderMulti {
+ public:
+  FrameDataReaderMulti(const std::vector<std::string>& feature_rspecifiers, const std::vector<std::string>& targets_rspecifiers,
+                       const NnetDataRandomizerOptions& rand_opts) : read_done_(false) {
+    KALDI_ASSERT(!feature_rspecifiers.empty() && !targets_rspecifiers.empty());
+    for (const std::string& r : feature_rspecifiers) {
+      feature_readers_.emplace_back(new SequentialBaseFloatMatrixReader(r));
+      feature_randomizers_.emplace_back(new MatrixRandomizer());
+      feature_randomizers_.back()->Init(rand_opts);
+    }
+    for (const std::string& r : targets_rspecifiers) {
+      targets_readers_.emplace_back(new RandomAccessPosteriorReader(r));
+      targets_randomizers_.emplace_back(new PosteriorRandomizer());
+      targets_randomizers_.back()->Init(rand_opts);
+    }
+    randomizer_mask_.Init(rand_opts);
+  }
+  bool Done() { return read_done_ && feature_randomizers_[0]->Done(); }
+  void ReadData(std::vector<const CuMatrixBase<BaseFloat>*>* input, std::vector<const Posterior*>* output) {
+    if (Done()) KALDI_ERR << "Already read done";
+    if (feature_randomizers_[0]->Done()) FillRandomizer();
+    input->resize(feature_randomizers_.size());
+    output->resize(targets_randomizers_.size());
+    for (size_t i = 0; i < feature_randomizers_.size(); ++i) { (*input)[i] = &feature_randomizers_[i]->Value(); feature_randomizers_[i]->Next(); }
+    for (size_t i = 0; i < targets_randomizers_.size(); ++i) { (*output)[i] = &targets_randomizers_[i]->Value(); targets_randomizers_[i]->Next(); }
+  }
+ private:
+  void FillRandomizer() {
+    while (true) {
+      if (feature_randomizers_[0]->IsFull()) break;
+      if (feature_readers_[0]->Done()) {
+        for (size_t i = 1; i < feature_readers_.size(); ++i) KALDI_ASSERT(feature_readers_[i]->Done());
+        read_done_ = true;
+        break;
+      }
+      const std::string utt = feature_readers_[0]->Key();
+      for (size_t i = 1; i < feature_readers_.size(); ++i)
+        if (utt != feature_readers_[i]->Key())
+          KALDI_ERR << "all feature not in the same order[0] " << utt << "[" << i << "] " << feature_readers_[i]->Key();
+      bool all_have_target = true;
+      for (auto& tr : targets_readers_)
+        if (!tr->HasKey(utt)) { KALDI_WARN << utt << ", missing targets"; all_have_target = false; }
+      if (all_have_target) {
+        int32 num_frame = 0;
+        for (size_t i = 0; i < feature_readers_.size(); ++i) {
+          const Matrix<BaseFloat>& mat = feature_readers_[i]->Value();
+          if (i == 0) num_frame = mat.NumRows();
+          else if (mat.NumRows() != num_frame) KALDI_ERR << "all feature dim not equal";
+          feature_randomizers_[i]->AddData(CuMatrix<BaseFloat>(mat));
+        }
+        for (size_t i = 0; i < targets_readers_.size(); ++i) {
+          const Posterior& targets = targets_readers_[i]->Value(utt);
+          if (static_cast<int32>(targets.size()) != num_frame) KALDI_ERR << "feature and target dim must match";
+          targets_randomizers_[i]->AddData(targets);
+        }
+      }
+      for (auto& fr : feature_readers_) fr->Next();
+    }
+    const std::vector<int32>& mask = randomizer_mask_.Generate(feature_randomizers_[0]->NumFrames());
+    for (auto& r : feature_randomizers_) r->Randomize(mask);
+    for (auto& r : targets_randomizers_) r->Randomize(mask);
+  }
+  std::vector<std::unique_ptr<SequentialBaseFloatMatrixReader>> feature_readers_;
+  std::vector<std::unique_ptr<RandomAccessPosteriorReader>> targets_readers_;
+  std::vector<std::unique_ptr<MatrixRandomizer>> feature_randomizers_;
+  std::vector<std::unique_ptr<PosteriorRandomizer>> targets_randomizers_;
+  RandomizerMask randomizer_mask_;
+  bool read_done_;
+};
+
+// The reference's one class with both constructors (data-reader.h:24-47): a single feature / target pair takes the
+// feeder-backed reader above, lists take the multi-stream one.
+class FrameDataReader {
+ public:
+  FrameDataReader(const std::string& feature_rspecifier, const std::string& targets_rspecifier, const NnetDataRandomizerOptions& rand_opts)
+      : single_(new FrameDataReaderSingle(feature_rspecifier, targets_rspecifier, rand_opts)) {}
+  FrameDataReader(const std::vector<std::string>& feature_rspecifiers, const std::vector<std::string>& targets_rspecifiers,
+                  const NnetDataRandomizerOptions& rand_opts) : multi_(new FrameDataReaderMulti(feature_rspecifiers, targets_rspecifiers, rand_opts)) {}
+  bool Done() { return single_ ? single_->Done() : multi_->Done(); }
+  bool ReadData(const CuMatrixBase<BaseFloat>** feat, const Posterior** targets) {
+    if (single_) return single_->ReadData(feat, targets);
+    std::vector<const CuMatrixBase<BaseFloat>*> in;
+    std::vector<const Posterior*> out;
+    multi_->ReadData(&in, &out);
+    *feat = in[0]; *targets = out[0];
+    return true;
+  }
+  void ReadData(std::vector<const CuMatrixBase<BaseFloat>*>* input, std::vector<const Posterior*>* output) {
+    if (multi_) { multi_->ReadData(input, output); return; }
+    input->resize(1); output->resize(1);
+    if (!single_->ReadData(&(*input)[0], &(*output)[0])) KALDI_ERR << "Already read done";
+  }
+ private:
+  std::unique_ptr<FrameDataReaderSingle> single_;
+  std::unique_ptr<FrameDataReaderMulti> multi_;
 };
 
 

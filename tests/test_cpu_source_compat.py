@@ -29,6 +29,7 @@ MAINS = [
     "aslp-nnetbin/aslp-nnet-forward-skip.cc",
     "aslp-nnetbin/aslp-nnet-forward-blstm-lc.cc",
     "aslp-nnetbin/aslp-nnet-forward-mimo.cc",
+    "aslp-nnetbin/aslp-nnet-train-frame-mimo.cc",
     "aslp-parallelbin/aslp-nnet-train-lc-blstm-streams-worker.cc",
     "aslp-parallelbin/aslp-nnet-train-frame-worker.cc",
     "aslp-parallelbin/aslp-nnet-train-lstm-stream-worker.cc",

@@ -127,3 +127,18 @@ def test_unmodified_reference_init_and_copy_mains(tmp_path):
     cp = str(tmp_path / "copy.nnet")
     run("aslp-nnet-copy", ["--binary=true", os.path.join(d, "init.nnet"), cp])
     assert open(cp, "rb").read() == open(os.path.join(d, "init.nnet"), "rb").read()
+
+
+@needs_dropin
+def test_unmodified_reference_mimo_frame_trainer_with_one_stream(tmp_path):
+    """aslp-nnet-train-frame-mimo (the multi-stream FrameDataReader, vector Propagate / Backpropagate, one loss per output) on a
+    net with one input and one output: the same shuffle mask, minibatches and updates as the plain frame trainer, so it must
+    write the model the reference's aslp-nnet-train-frame wrote for the fixture"""
+    if not os.path.exists(os.path.join(DROPIN, "aslp-nnet-train-frame-mimo")):
+        pytest.skip("aslp-nnet-train-frame-mimo not built")
+    d = os.path.join(GOLD, "cli_frame")
+    out = str(tmp_path / "out.nnet")
+    flags = open(os.path.join(d, "args.txt")).read().split()
+    run("aslp-nnet-train-frame-mimo", flags + ["ark:" + os.path.join(d, "feats.ark"), "ark:" + os.path.join(d, "post.ark"),
+                                               os.path.join(d, "init.nnet"), out])
+    check_model(out, "cli_frame")
