@@ -215,8 +215,9 @@ void LstmFamily::PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<Ba
     if (i == 0 && tr_.carry_state) d.prop.RowRange(0, S).CopyFromMat(prev_state_);
     // x -> g,i,f,o for the whole chunk, bias fused in the epilogue (lc.h:552-555, :632-645)
     CuSubMatrix<BaseFloat> gifo = d.prop.Range(S, T * S, 0, 4 * C);
+    const size_t wsb = aslp_gemm_workspace_bytes(T * S, 4 * C, input_dim_);      // few-tile shapes (short BPTT chunks) split K
     ASLP_OK(aslp_gemm(st, 0, 1, T * S, 4 * C, input_dim_, 1.0f, in.Data(), in.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(), 0.0f,
-                      gifo.Data(), gifo.Stride(), d.bias.Data(), 0.0f, GemmPrecision(), nullptr, 0));
+                      gifo.Data(), gifo.Stride(), d.bias.Data(), 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
   }
   const bool fold = FoldProjection();
   if (fold) {
@@ -301,8 +302,9 @@ void LstmFamily::BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMat
     Dir& d = d_[i];
     CuSubMatrix<BaseFloat> dgifo = d.back.Range(S, T * S, 0, 4 * C);
     // g,i,f,o -> x (lc.h:963-965): second direction accumulates
+    const size_t wsb = aslp_gemm_workspace_bytes(T * S, input_dim_, 4 * C);
     ASLP_OK(aslp_gemm(st, 0, 0, T * S, input_dim_, 4 * C, 1.0f, dgifo.Data(), dgifo.Stride(), d.w_gifo_x.Data(), d.w_gifo_x.Stride(),
-                      i == 0 ? 0.0f : 1.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, prec, nullptr, 0));
+                      i == 0 ? 0.0f : 1.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, prec, wsb ? CuWorkspace(wsb) : nullptr, wsb));
   }
   if (skip_wgrad_) { async_tail_ = false; return; }
   // Everything below (weight gradients, then Update) is off the critical path of the backward pass: nothing downstream reads
