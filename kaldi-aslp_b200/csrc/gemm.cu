@@ -642,7 +642,7 @@ int gemm_f16x3(cudaStream_t st, bool a_mn, bool b_mn, const EpiParams& p_in, con
   return 0;
 }
 
-// Split-K policy.  (a) fill the chip: aim for ~2 CTAs per SM when the output has few tiles (wgrad shapes);
+// Split-K policy.  (a) fill the chip: one work item per SM when the output has few tiles (wgrad shapes, small minibatches);
 // (b) bound the length of one TMEM accumulation chain to 32 k-blocks (K = 1024): the tensor core's fp32
 // accumulate truncates, so its error grows with the chain length, while the split partials are summed with
 // IEEE round-to-nearest adds in the reduce kernel.  Large square GEMMs (many tiles) are left unsplit.
@@ -653,7 +653,11 @@ int pick_splits(int M, int N, int K) {
   // (c) short K with few tiles (the products of a 256-frame minibatch: 16 .. 64 tiles, 8 .. 14 k-blocks): still split, down to
   // two k-blocks per item -- unsplit they leave 84 .. 132 SMs idle and a tile's whole k chain on one SM
   if (tiles >= sms || num_kb < 4) return 1;
-  int splits = aslp_div_up(2 * sms, tiles);
+  // one wave of work items (floor(sms / tiles) splits), not two: the k-loops of these products are a handful of blocks either
+  // way, while every extra split is another M x N partial for the reduce pass to read -- cfg1 0.304 -> 0.278 ms per minibatch,
+  // cfg4 1.018 -> 0.976 ms (ASLP_GEMM_SPLIT_WAVES=2 restores the old count)
+  static const int waves = getenv("ASLP_GEMM_SPLIT_WAVES") ? atoi(getenv("ASLP_GEMM_SPLIT_WAVES")) : 1;
+  int splits = waves >= 2 ? aslp_div_up(waves * sms, tiles) : (sms / tiles > 0 ? sms / tiles : 1);
   const int by_chain = aslp_div_up(num_kb, 32);
   if (by_chain > splits) splits = by_chain;
   const int by_kb = num_kb >= 16 ? num_kb / 4 : num_kb / 2;
