@@ -110,13 +110,18 @@ int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
  *                                                             applies to what the next layer's backward product delivers
  *   update_w    W -= update_lr * C after C = beta*C + alpha*AB the SGD apply behind the weight-gradient product, C = *_corr_
  *                                                             (nnet-affine-transform.h:210,237)
- * order: product, beta, bias, clip, act, dact, store, update.  Folded into the split-K reduce pass when the product takes it (the
+ * order: product, beta, bias, clip, act, dact, store, update.  Folded into the split-K reduction when the product takes it (the
  * few-tile shapes of 256- to 1000-frame minibatches, where every saved launch counts); otherwise the same steps run as
  * launches of their own behind the product, so the result does not depend on the path. */
 typedef struct {
   int act;
   const float* dact_y; int dact_ldy; int dact_kind;      /* ASLP_ACT_* of the activation whose derivative is applied; y may not alias C */
   float* update_w; int update_ldw; float update_lr;
+  int reduce_in_launch;   /* non-zero: a split-K product may reduce its partial tiles inside the launch (the CTAs of a tile wait for
+                           * each other) instead of in a second pass.  Only for products enqueued where nothing else competes for
+                           * SMs -- all work items must be resident together; the library falls back to the second pass when the
+                           * items do not fit one wave.  Same summation order, bit-identical results.  Measured slower than the second
+                           * pass on B200 (profiles/r02_gemm_in_launch_reduce.txt); the host layer leaves it 0. */
 } aslp_gemm_epilogue_t;
 int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
                  float alpha, const float* A, int lda, const float* B, int ldb,

@@ -17,6 +17,9 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "scratch.cuh"
 
 // persistent-grid cap of the calling thread (aslp_gemm_set_cta_limit): work issued on a side stream leaves SMs to a concurrently
@@ -118,6 +121,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// extended epilogue of aslp_gemm_ex (include/aslp_b200.h): activation of the result, multiplication by the derivative of
+// an activation at its output y, and the SGD apply W -= lr * C -- each otherwise a launch of its own after the product
+struct EpiExt { int act; const float* dy; int ldy; int dkind; float* w; int ldw; float lr; };
+__device__ __forceinline__ float epi_act(int kind, float x) {        // kind - 1 = ASLP_ACT_*
+  if (kind == 1 + ASLP_ACT_SIGMOID) return ref_sigmoid(x);
+  if (kind == 1 + ASLP_ACT_TANH) return ref_tanh(x);
+  return fmaxf(x, 0.f);
+}
+__device__ __forceinline__ float epi_dact(int kind, float y, float e) {   // as act_bwd_kernel (pointwise.cu)
+  if (kind == ASLP_ACT_SIGMOID) return y * (1.0f - y) * e;
+  if (kind == ASLP_ACT_TANH) return (1.0f - y * y) * e;
+  return y > 0.f ? e : 0.f;
+}
+
+#ifdef ASLP_GEMM_DEBUG_TIMES
+__device__ unsigned long long g_dbg_t[148 * 8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DBG_T(slot) do { if ((threadIdx.x & 31) == 0 && threadIdx.x == 64) g_dbg_t[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+#else
+#define DBG_T(slot) do {} while (0)
+#endif
 struct EpiParams {
   float* C; int ldc;
   int M, N, K;
@@ -128,11 +152,20 @@ struct EpiParams {
   int ldp;
   int kb_per_split;
   int tiles_m, tiles_n, splits;   // persistent scheduling: work item = (split z, tile row, tile column), z slowest
+  // split-K reduced INSIDE the launch (one work item per CTA, all of them resident): after writing its partial tile a CTA
+  // counts itself in on counters[tile], waits for the other splits of the tile, and reduces its own 1/splits of the tile's
+  // rows over all partials (ascending z: the same order and rounding as splitk_reduce_kernel) with the full epilogue.
+  // Opt-in (aslp_gemm_epilogue_t::reduce_in_launch), and the host layer leaves it off: measured with the stamps below
+  // (-DASLP_GEMM_DEBUG_TIMES, tools/gemm_in_launch_probe.py; profiles/r02_gemm_in_launch_reduce.txt), the 128 threads per SM
+  // that are left to reduce pull their 73 KB of partials out of L2 in 8 us (19 us with the C / W read-modify-write of a
+  // weight gradient), where the separate pass with 256K threads takes 4.6 us INCLUDING its launch.
+  int* counters;       // [2 * tiles]: arrivals, then finished reducers (the last one re-arms both); NULL = separate reduce pass
+  EpiExt ext;
 };
 
 // ------------------------------------------------------------------ the kernel
-template <bool A_MN, bool B_MN, int PASSES>
-__global__ void __launch_bounds__(PASSES == 1 ? 192 : NT3, 1)
+template <bool A_MN, bool B_MN, int PASSES, bool INL>     // INL: with the in-launch split-K reduction (its own instantiation:
+__global__ void __launch_bounds__(PASSES == 1 ? 192 : NT3, 1)   // the default kernel stays at its register count and code size)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p) {
   constexpr int STAGES = (PASSES == 1) ? 6 : 3;
   constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
@@ -181,6 +214,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  DBG_T(0);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -275,6 +309,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int z, m0, n0, kb_begin, kb_end;
       item_coords(item, z, m0, n0, kb_begin, kb_end);
       mbar_wait(tmem_full_bar(acc_idx), acc_ph);
+      DBG_T(4);
       tc_fence_after();
       const bool has_work = kb_end > kb_begin;
       // Coalesced epilogue.  tcgen05.ld hands lane r the 32 columns of accumulator row r; storing that straight to HBM makes
@@ -358,6 +393,123 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc_idx));
       if (++acc_idx == 2) { acc_idx = 0; acc_ph ^= 1u; }
+      if constexpr (INL) if (p.partial != nullptr && p.counters != nullptr) {
+        // ---- in-launch reduction (grid == number of work items: every split of this tile is running on some SM right now)
+        const int et = threadIdx.x - 64;                  // 0..127 over the four epilogue warps
+        const int tile = item - z * tiles_mn;
+        DBG_T(1);
+        // The 128 partial-tile writers meet at the CTA barrier and ONE thread publishes for all of them: its gpu-scope release
+        // is cumulative over what the barrier ordered before it.
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          asm volatile("red.release.gpu.global.add.s32 [%0], 1;" :: "l"(p.counters + tile) : "memory");
+          int seen;
+          unsigned spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
+            if (seen < p.splits) { __nanosleep(40); if (++spins > (1u << 26)) __trap(); }      // seconds: an error, never a hang
+          } while (seen < p.splits);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        DBG_T(2);
+        const int rp = (BM + p.splits - 1) / p.splits;    // rows of the tile this split reduces
+        const int c4 = (et & 31) << 2;                    // 4 columns per thread, 32 threads span the tile's 128 columns
+        const int col = n0 + c4;
+        if (col < p.N) {
+          // A thread owns the rows (et >> 5) + 4 i of the slice and needs `splits` partials of each (32 loads in all, whatever
+          // the split count) plus the old C / y / W values of the epilogue.  Only 128 threads per SM are left to do this, so
+          // nothing may wait for one load at a time: a batch of rows has ALL its loads issued (up to 16 partials and the
+          // epilogue operands) before the first add, and only then the adds, in ascending z, and the stores.
+          const int iters = (rp + 3) >> 2;
+          const int nb = p.splits <= 4 ? 4 : (p.splits <= 8 ? 2 : 1);          // rows per batch: nb * splits <= 16, or one row
+          auto row_of = [&](int i, bool& ok) {
+            const int rr = (et >> 5) + 4 * i, row = m0 + z * rp + rr;
+            ok = i < iters && rr < rp && z * rp + rr < BM && row < p.M;
+            return row;
+          };
+          float bia[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bia[j] = (p.bias != nullptr && col + j < p.N) ? p.bias[col + j] : 0.f;
+          for (int i0 = 0; i0 < iters; i0 += nb) {
+            float ad[4][4], aw[4][4], ay[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              bool ok;
+              const int row = row_of(i0 + r, ok);
+              ok = ok && r < nb;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool okj = ok && col + j < p.N;
+                ad[r][j] = (okj && p.beta != 0.f) ? p.C[(size_t)row * p.ldc + col + j] : 0.f;
+                ay[r][j] = (okj && p.ext.dy != nullptr) ? p.ext.dy[(size_t)row * p.ext.ldy + col + j] : 0.f;
+                aw[r][j] = (okj && p.ext.w != nullptr) ? p.ext.w[(size_t)row * p.ext.ldw + col + j] : 0.f;
+              }
+            }
+            float4 accs[4];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nb > 1) {
+              float4 v[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const int r = u / p.splits, zz = u - r * p.splits;
+                bool ok;
+                const int row = row_of(i0 + r, ok);
+                v[u] = (ok && r < nb) ? __ldcg(reinterpret_cast<const float4*>(p.partial + ((size_t)zz * p.M + row) * p.ldp + col))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const int r = u / p.splits, zz = u - r * p.splits;
+                if (zz == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q == r && zz == p.splits - 1) accs[q] = acc;
+              }
+            } else {
+              bool ok;
+              const int row = row_of(i0, ok);
+              for (int z0 = 0; z0 < p.splits; z0 += 16) {
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  v[u] = (ok && z0 + u < p.splits) ? __ldcg(reinterpret_cast<const float4*>(p.partial + ((size_t)(z0 + u) * p.M + row) * p.ldp + col))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                  if (z0 + u < p.splits) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+              }
+              accs[0] = acc;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              bool ok;
+              const int row = row_of(i0 + r, ok);
+              if (ok && r < nb) {
+                const float o[4] = {accs[r].x, accs[r].y, accs[r].z, accs[r].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (col + j < p.N) {
+                    float v = p.alpha * o[j];
+                    if (p.beta != 0.f) v += p.beta * ad[r][j];
+                    if (p.bias != nullptr) v += bia[j];
+                    if (p.clip > 0.f) v = fminf(fmaxf(v, -p.clip), p.clip);
+                    if (p.ext.act != 0) v = epi_act(p.ext.act, v);
+                    if (p.ext.dy != nullptr) v = epi_dact(p.ext.dkind, ay[r][j], v);
+                    p.C[(size_t)row * p.ldc + col + j] = v;
+                    if (p.ext.w != nullptr) p.ext.w[(size_t)row * p.ext.ldw + col + j] = aw[r][j] + (-p.ext.lr) * v;
+                  }
+                }
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        DBG_T(3);
+        if (et == 0) {                                    // the last reducer of the tile re-arms its counters for the next launch
+          const int done = atomicAdd(p.counters + tiles_mn + tile, 1);
+          if (done == p.splits - 1) { p.counters[tile] = 0; p.counters[tiles_mn + tile] = 0; }
+        }
+      }
     }
   } else {
     // ===================== hi/lo splitter (3xTF32) =====================
@@ -398,20 +550,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem_base) : "memory");
   }
-}
-
-// extended epilogue of aslp_gemm_ex (include/aslp_b200.h): activation of the result, multiplication by the derivative of
-// an activation at its output y, and the SGD apply W -= lr * C -- each otherwise a launch of its own after the product
-struct EpiExt { int act; const float* dy; int ldy; int dkind; float* w; int ldw; float lr; };
-__device__ __forceinline__ float epi_act(int kind, float x) {        // kind - 1 = ASLP_ACT_*
-  if (kind == 1 + ASLP_ACT_SIGMOID) return ref_sigmoid(x);
-  if (kind == 1 + ASLP_ACT_TANH) return ref_tanh(x);
-  return fmaxf(x, 0.f);
-}
-__device__ __forceinline__ float epi_dact(int kind, float y, float e) {   // as act_bwd_kernel (pointwise.cu)
-  if (kind == ASLP_ACT_SIGMOID) return y * (1.0f - y) * e;
-  if (kind == ASLP_ACT_TANH) return (1.0f - y * y) * e;
-  return y > 0.f ? e : 0.f;
 }
 
 // split-K second phase: C = alpha * sum_z partial[z] + beta*C + bias, clip, then the extended epilogue
@@ -531,7 +669,7 @@ bool make_tmap(CUtensorMap* tm, const float* base, int inner_extent, int outer_e
   return r == CUDA_SUCCESS;
 }
 
-template <bool A_MN, bool B_MN, int PASSES>
+template <bool A_MN, bool B_MN, int PASSES, bool INL>
 int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p_in, int splits) {
   constexpr int STAGES = (PASSES == 1) ? 6 : 3;
   constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
@@ -539,7 +677,7 @@ int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, con
   static_assert(8 * (3 * STAGES + 4) + 16 <= BAR_REGION, "barrier region too small");
   static bool attr_set = false;
   if (!attr_set) {
-    ASLP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    ASLP_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, PASSES, INL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   EpiParams p = p_in;
@@ -548,7 +686,7 @@ int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, con
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int sm_cap = (t_cta_limit > 0 && t_cta_limit < aslp_num_sms()) ? t_cta_limit : aslp_num_sms();
   const int grid = (int)(items < sm_cap ? items : sm_cap);
-  gemm_tf32_kernel<A_MN, B_MN, PASSES><<<grid, PASSES == 1 ? 192 : NT3, SMEM, st>>>(ta, tb, p);
+  gemm_tf32_kernel<A_MN, B_MN, PASSES, INL><<<grid, PASSES == 1 ? 192 : NT3, SMEM, st>>>(ta, tb, p);
   ASLP_CHECK_LAUNCH();
   return 0;
 }
@@ -678,9 +816,29 @@ int pick_splits_h(int M, int N, int K) {
   return aslp_div_up(num_kb, per);
 }
 
+// per-(device, stream) arrival / completion counters of the in-launch split-K reduction: zeroed once, re-armed by the kernels
+constexpr int GEMM_COUNTERS = 4096;
+struct CounterBuf { int* ptr; };
+std::map<std::pair<int, cudaStream_t>, CounterBuf> g_counters;
+std::mutex g_counters_mu;
+int* gemm_counters(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_counters_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CounterBuf& b = g_counters[std::make_pair(dev, st)];
+  if (b.ptr == nullptr) {
+    if (cudaMalloc((void**)&b.ptr, GEMM_COUNTERS * sizeof(int)) != cudaSuccess) { b.ptr = nullptr; return nullptr; }
+    cudaMemsetAsync(b.ptr, 0, GEMM_COUNTERS * sizeof(int), st);
+  }
+  return b.ptr;
+}
+
 }  // namespace
 
 extern "C" {
+#ifdef ASLP_GEMM_DEBUG_TIMES
+int aslp_gemm_debug_times(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_dbg_t, sizeof(unsigned long long) * 148 * 8); }
+#endif
 
 int aslp_gemm_set_cta_limit(int max_ctas) { t_cta_limit = max_ctas; return 0; }
 
@@ -694,7 +852,7 @@ size_t aslp_gemm_workspace_bytes(int M, int N, int K) {
 // `ext` != NULL: fold the extended epilogue into the split-K reduce when the product takes that path (*ext_done = true)
 static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
                      const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
-                     void* workspace, size_t workspace_bytes, const EpiExt* ext, bool* ext_done) {
+                     void* workspace, size_t workspace_bytes, const EpiExt* ext, bool* ext_done, bool reduce_in_launch) {
   cudaStream_t st = (cudaStream_t)s;
   if (ext_done != nullptr) *ext_done = false;
   ASLP_REQUIRE(M >= 0 && N >= 0 && K >= 0);
@@ -738,6 +896,7 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
     EpiParams pe;
     pe.C = C; pe.ldc = ldc; pe.M = M; pe.N = N; pe.K = K; pe.alpha = alpha; pe.beta = beta; pe.bias = bias; pe.clip = clip;
     pe.partial = nullptr; pe.ldp = 0; pe.kb_per_split = 0; pe.tiles_m = pe.tiles_n = pe.splits = 0;
+    pe.counters = nullptr; pe.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
     return gemm_f16x3(st, a_mn, b_mn, pe, A, lda, B, ldb, workspace, workspace_bytes);
   }
   CUtensorMap ta, tb;
@@ -754,16 +913,30 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
   p.partial = splits > 1 ? (float*)workspace : nullptr;
   p.ldp = (int)ldp;
   p.kb_per_split = aslp_div_up(num_kb, splits);
+  p.counters = nullptr; p.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
+  // In-launch reduction: only when the caller asked for it (aslp_gemm_ex, reduce_in_launch) and every work item gets a CTA of
+  // its own (items <= SMs, no grid cap), so that all splits of a tile are resident together and may wait for each other.
+  const long long items_ll = (long long)aslp_div_up(M, BM) * aslp_div_up(N, BN) * splits;
+  const bool in_launch = splits > 1 && reduce_in_launch && precision != ASLP_GEMM_TF32 && items_ll <= aslp_num_sms() && (t_cta_limit <= 0 || t_cta_limit >= aslp_num_sms()) &&
+                         2 * aslp_div_up(M, BM) * aslp_div_up(N, BN) <= GEMM_COUNTERS;
+  if (in_launch) {
+    p.counters = gemm_counters(st);
+    if (p.counters == nullptr) { aslp_set_last_error_msg("counter allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
+    if (ext != nullptr) p.ext = *ext;
+  }
   const bool one_pass = precision == ASLP_GEMM_TF32;      // ASLP_GEMM_3XTF32 below the fp16-split threshold: the in-loop split
   int rc;
 #define ASLP_DISPATCH(AM, BMN)                                             \
-  rc = one_pass ? launch_tc<AM, BMN, 1>(st, ta, tb, p, splits) : launch_tc<AM, BMN, 3>(st, ta, tb, p, splits)
+  rc = one_pass ? launch_tc<AM, BMN, 1, false>(st, ta, tb, p, splits)       \
+     : in_launch ? launch_tc<AM, BMN, 3, true>(st, ta, tb, p, splits)      \
+                 : launch_tc<AM, BMN, 3, false>(st, ta, tb, p, splits)
   if (!a_mn && !b_mn) { ASLP_DISPATCH(false, false); }
   else if (!a_mn && b_mn) { ASLP_DISPATCH(false, true); }
   else if (a_mn && !b_mn) { ASLP_DISPATCH(true, false); }
   else { ASLP_DISPATCH(true, true); }
 #undef ASLP_DISPATCH
   if (rc != 0) return rc;
+  if (in_launch) { if (ext != nullptr && ext_done != nullptr) *ext_done = true; return 0; }
   if (splits > 1) {
     const long long total = (long long)M * ((N + 3) / 4);
     int blocks = (int)((total + 255) / 256);
@@ -779,7 +952,7 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
 int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
               void* workspace, size_t workspace_bytes) {
-  return gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, nullptr, nullptr);
+  return gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, nullptr, nullptr, false);
 }
 
 int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
@@ -791,7 +964,9 @@ int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
   if (M == 0 || N == 0) return 0;
   EpiExt x{epi->act, epi->dact_y, epi->dact_ldy, epi->dact_kind, epi->update_w, epi->update_ldw, epi->update_lr};
   bool done = false;
-  int rc = gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, &x, &done);
+  static const bool allow_in_launch = getenv("ASLP_GEMM_REDUCE_IN_LAUNCH") == nullptr || getenv("ASLP_GEMM_REDUCE_IN_LAUNCH")[0] != '0';
+  int rc = gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, &x, &done,
+                     epi->reduce_in_launch != 0 && allow_in_launch);
   if (rc != 0 || done) return rc;
   // the product did not go through the split-K reduce (large or odd shapes): the same steps as launches of their own
   if (x.act != 0) { rc = aslp_act_fwd(s, x.act - 1, C, ldc, C, ldc, M, N); if (rc != 0) return rc; }

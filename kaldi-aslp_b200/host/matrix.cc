@@ -51,6 +51,7 @@ aslp_stream_t CuSideStream() {
   if (g_side == nullptr) ASLP_OK(aslp_stream_create(&g_side));
   return g_side;
 }
+bool CuOnComputeStream() { return t_current == nullptr && !t_helper; }
 bool CuAsyncEnabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("ASLP_ASYNC_WGRAD"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }

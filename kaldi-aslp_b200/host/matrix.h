@@ -34,6 +34,8 @@ void CuThreadDetach();
 // this call its runtime calls land on device 0 and create a context there on every rank.  No-op before the first device operation.
 void CuThreadUseDevice();
 bool CuAsyncEnabled();
+// true when CuStream() is the process-wide compute stream itself: no side-stream scope, not a helper thread's stream
+bool CuOnComputeStream();
 void CuFork();
 void CuJoin();
 

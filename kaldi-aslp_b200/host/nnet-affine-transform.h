@@ -6,6 +6,7 @@
 //           optional L2 / L1 / max-norm, W -= lr W_corr
 #ifndef ASLP_HOST_NNET_AFFINE_TRANSFORM_H_
 #define ASLP_HOST_NNET_AFFINE_TRANSFORM_H_
+#include <stdlib.h>
 #include "cu-workspace.h"
 #include "nnet-component.h"
 
@@ -98,20 +99,24 @@ class AffineTransform : public UpdatableComponent {
   // 16 of 148 SMs busy for the whole K chain -- 29 us per 256 x 1024 x 1024 product measured -- unless K is split)
   void PropagateFnc(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out) {
     const size_t wsb = aslp_gemm_workspace_bytes(in.NumRows(), output_dim_, input_dim_);
-    ASLP_OK(aslp_gemm(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
-                      0.0f, out->Data(), out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
+    aslp_gemm_epilogue_t epi = {};
+    epi.reduce_in_launch = ReduceInLaunch();
+    ASLP_OK(aslp_gemm_ex(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
+                         0.0f, out->Data(), out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
   }
   void BackpropagateFnc(const CuMatrixBase<BaseFloat>& in, const CuMatrixBase<BaseFloat>& out, const CuMatrixBase<BaseFloat>& out_diff, CuMatrixBase<BaseFloat>* in_diff) {
     const size_t wsb = aslp_gemm_workspace_bytes(out_diff.NumRows(), input_dim_, output_dim_);
-    ASLP_OK(aslp_gemm(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
-                      linearity_.Stride(), 0.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb));
+    aslp_gemm_epilogue_t epi = {};
+    epi.reduce_in_launch = ReduceInLaunch();
+    ASLP_OK(aslp_gemm_ex(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
+                         linearity_.Stride(), 0.0f, in_diff->Data(), in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
   }
   // Forward with the following Sigmoid / Tanh / ReLU applied in the product's epilogue (Nnet::Propagate pairs the two
   // components when the product takes the split-K reduce pass; the pre-activation is then never written)
   void PropagateFused(const CuMatrixBase<BaseFloat>& in, int act_kind, CuMatrixBase<BaseFloat>* act_out) {
     const size_t wsb = aslp_gemm_workspace_bytes(in.NumRows(), output_dim_, input_dim_);
     aslp_gemm_epilogue_t epi = {};
-    epi.act = 1 + act_kind;
+    epi.act = 1 + act_kind; epi.reduce_in_launch = ReduceInLaunch();
     ASLP_OK(aslp_gemm_ex(CuStream(), 0, 1, in.NumRows(), output_dim_, input_dim_, 1.0f, in.Data(), in.Stride(), linearity_.Data(), linearity_.Stride(),
                          0.0f, act_out->Data(), act_out->Stride(), has_bias_ ? bias_.Data() : nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
   }
@@ -120,9 +125,18 @@ class AffineTransform : public UpdatableComponent {
   void BackpropagateFused(const CuMatrixBase<BaseFloat>& out_diff, const CuMatrixBase<BaseFloat>& act_y, int act_kind, CuMatrixBase<BaseFloat>* act_in_diff) {
     const size_t wsb = aslp_gemm_workspace_bytes(out_diff.NumRows(), input_dim_, output_dim_);
     aslp_gemm_epilogue_t epi = {};
-    epi.dact_y = act_y.Data(); epi.dact_ldy = act_y.Stride(); epi.dact_kind = act_kind;
+    epi.dact_y = act_y.Data(); epi.dact_ldy = act_y.Stride(); epi.dact_kind = act_kind; epi.reduce_in_launch = ReduceInLaunch();
     ASLP_OK(aslp_gemm_ex(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
                          linearity_.Stride(), 0.0f, act_in_diff->Data(), act_in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
+  }
+  // The split-K reduction inside the launch makes the CTAs of a tile wait for each other, so all work items of the product must
+  // become resident without depending on another waiting product: products of the process-wide compute stream are serialised
+  // among themselves and qualify; anything on the side stream or on a helper thread's stream (which may run beside them) does not.
+  // OFF unless ASLP_GEMM_REDUCE_IN_LAUNCH=1: measured slower than the separate reduce pass (cfg1 0.40 vs 0.28 ms per
+  // minibatch, cfg4 1.39 vs 0.97 ms; profiles/r02_gemm_in_launch_reduce.txt).
+  static int ReduceInLaunch() {
+    static const bool on = getenv("ASLP_GEMM_REDUCE_IN_LAUNCH") != nullptr && getenv("ASLP_GEMM_REDUCE_IN_LAUNCH")[0] == '1';
+    return on && CuOnComputeStream() ? 1 : 0;
   }
   // true when a product of this layer at `rows` frames goes through the split-K reduce pass, i.e. when folding a neighbouring
   // pointwise step into it costs nothing (few-tile shapes: the launch-bound minibatches)
@@ -147,6 +161,7 @@ class AffineTransform : public UpdatableComponent {
     const bool fused_apply = (l2 == 0.0 && l1 == 0.0);
     aslp_gemm_epilogue_t epi = {};
     if (fused_apply) { epi.update_w = linearity_.Data(); epi.update_ldw = linearity_.Stride(); epi.update_lr = lr; }
+    epi.reduce_in_launch = ReduceInLaunch();
     ASLP_OK(aslp_gemm_ex(st, 1, 0, output_dim_, input_dim_, num_frames, 1.0f, diff.Data(), diff.Stride(), input.Data(), input.Stride(), mmt,
                          linearity_corr_.Data(), linearity_corr_.Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
     if (!fused_apply) {

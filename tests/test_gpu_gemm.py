@@ -121,6 +121,7 @@ def test_gemm_f16x3_rows_of_very_different_magnitude():
 
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [(256, 1024, 1024, 0, 1), (256, 1024, 1024, 0, 0), (1024, 440, 256, 1, 0), (1000, 512, 1024, 0, 1),
+                                          (1000, 1500, 512, 0, 1), (1024, 1024, 1000, 1, 0), (250, 1022, 440, 0, 1),
                                           (4096, 2048, 512, 0, 1), (24, 36, 20, 0, 1)])
 def test_gemm_ex_epilogue_matches_the_separate_steps(M, N, K, ta, tb):
     """aslp_gemm_ex: activation of the result, derivative of an activation at its output, SGD apply -- against fp64, for shapes
@@ -133,7 +134,7 @@ def test_gemm_ex_epilogue_matches_the_separate_steps(M, N, K, ta, tb):
 
     class Epi(ctypes.Structure):
         _fields_ = [("act", ctypes.c_int), ("dact_y", ctypes.c_void_p), ("dact_ldy", ctypes.c_int), ("dact_kind", ctypes.c_int),
-                    ("update_w", ctypes.c_void_p), ("update_ldw", ctypes.c_int), ("update_lr", ctypes.c_float)]
+                    ("update_w", ctypes.c_void_p), ("update_ldw", ctypes.c_int), ("update_lr", ctypes.c_float), ("reduce_in_launch", ctypes.c_int)]
     rng = np.random.default_rng(M + N)
     A = (rng.standard_normal((K, M) if ta else (M, K)) * 0.1).astype(np.float32)
     B = (rng.standard_normal((N, K) if tb else (K, N)) * 0.1).astype(np.float32)
@@ -153,27 +154,36 @@ def test_gemm_ex_epilogue_matches_the_separate_steps(M, N, K, ta, tb):
         return dC[:, :N].cpu().numpy()
     zero = np.zeros((M, N), np.float32)
     tol = 2e-5
+    # every case twice: split-K reduced by the second pass, and inside the launch (reduce_in_launch; a no-op for shapes that
+    # do not split or do not fit one wave) -- the two must agree bit for bit (same summation order)
     # (1) forward: sigmoid / tanh / relu of product + bias
     for kind, fn in ((0, lambda x: 1 / (1 + np.exp(-x))), (1, np.tanh), (2, lambda x: np.maximum(x, 0))):
-        got = run(zero, Epi(1 + kind, None, 0, 0, None, 0, 0.0), True, 0.0)
+        got = run(zero, Epi(1 + kind, None, 0, 0, None, 0, 0.0, 0), True, 0.0)
         want = fn(prod + bias)
         assert np.abs(got - want).max() < tol * max(1.0, np.abs(want).max()), kind
+        assert np.array_equal(run(zero, Epi(1 + kind, None, 0, 0, None, 0, 0.0, 1), True, 0.0), got), kind
     # (2) backward: product times f'(y)
     y = rng.uniform(0.05, 0.95, size=(M, N)).astype(np.float32)
     dy = torch.zeros((M, ld), device="cuda"); dy[:, :N] = torch.from_numpy(y).cuda()
     for kind, fn in ((0, lambda yy: yy * (1 - yy)), (1, lambda yy: 1 - yy * yy), (2, lambda yy: (yy > 0).astype(np.float64))):
-        got = run(zero, Epi(0, dy.data_ptr(), ld, kind, None, 0, 0.0), False, 0.0)
+        got = run(zero, Epi(0, dy.data_ptr(), ld, kind, None, 0, 0.0, 0), False, 0.0)
         want = fn(y.astype(np.float64)) * prod
         assert np.abs(got - want).max() < tol * max(1.0, np.abs(want).max()), kind
+        assert np.array_equal(run(zero, Epi(0, dy.data_ptr(), ld, kind, None, 0, 0.0, 1), False, 0.0), got), kind
     # (3) weight gradient with momentum + SGD apply
     corr0 = rng.standard_normal((M, N)).astype(np.float32)
     W0 = rng.standard_normal((M, N)).astype(np.float32)
-    dW = torch.zeros((M, ld), device="cuda"); dW[:, :N] = torch.from_numpy(W0).cuda()
-    got_corr = run(corr0, Epi(0, None, 0, 0, dW.data_ptr(), ld, 0.01), False, 0.9)
-    want_corr = 0.9 * corr0 + prod
-    assert np.abs(got_corr - want_corr).max() < tol * np.abs(want_corr).max()
-    got_W = dW[:, :N].cpu().numpy()
-    assert np.abs(got_W - (W0 - 0.01 * want_corr)).max() < tol * np.abs(W0).max()
+    results = []
+    for ril in (0, 1, 1):                                  # in-launch twice: the counters re-arm themselves
+        dW = torch.zeros((M, ld), device="cuda"); dW[:, :N] = torch.from_numpy(W0).cuda()
+        got_corr = run(corr0, Epi(0, None, 0, 0, dW.data_ptr(), ld, 0.01, ril), False, 0.9)
+        want_corr = 0.9 * corr0 + prod
+        assert np.abs(got_corr - want_corr).max() < tol * np.abs(want_corr).max()
+        got_W = dW[:, :N].cpu().numpy()
+        assert np.abs(got_W - (W0 - 0.01 * want_corr)).max() < tol * np.abs(W0).max()
+        results.append((got_corr, got_W))
+    for gc, gw in results[1:]:
+        assert np.array_equal(gc, results[0][0]) and np.array_equal(gw, results[0][1])
 
 
 @pytest.mark.parametrize("rows,cols", [(256, 1024), (1000, 1500), (7, 33), (5000, 512)])
