@@ -47,12 +47,12 @@ METRIC = "train frames/sec (LC-BLSTM-CTC)"
 UNIT = "frames/s"
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, sync_form="pipelined by layer under Backpropagate"):
     return {
         "workload": "cfg3: 3x BLstmProjectedStreamsLC(cell 320, out 640) + Affine 640->72 + Softmax, warp-ctc CTC; "
                     "minibatch 16 utts x 1000 frames x 40-dim, 100 labels/utt, K=72",
         "frames_per_step_per_gpu": S * T,
-        "parallelism": "dp%d-bmuf(sync-period %d frames)" % (n_gpus, SYNC_PERIOD) if n_gpus > 1 else "single",
+        "parallelism": "dp%d-bmuf(sync-period %d frames, exchange %s)" % (n_gpus, SYNC_PERIOD, sync_form) if n_gpus > 1 else "single",
         "l2_policy": "working set per step (6 LSTM buffers of 184 MB + exchange workspaces) >> 126 MB L2; no explicit flush needed",
     }
 
@@ -259,7 +259,7 @@ def multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, h
         ids = [NN.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         w = NN.Worker(kind, ids[0], world, rank, **kw)
-        w.init_param(net)
+        w.init_param_by_component(net)
         return w
 
     def gather(vec):
@@ -311,10 +311,21 @@ def multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, h
             d_prev = d
         w_prev = got
     res["replicas_bit_identical_after_bmuf_rounds"] = identical()
+    # ---- the same worker, one more round with the exchange pipelined by layer (BeginSynchronize / EndSynchronize).  The model
+    # before the exchange is not observable here, so the check is on what must hold afterwards: every replica carries the SAME
+    # model although each trained its own minibatch (an Update that ran behind its layer's exchange, or a tensor left out of it,
+    # would break that).  tests/test_gpu_workers.py compares the pipelined form with the blocking one bit for bit on a small net.
+    bm.begin_synchronize(S * T)
+    step_plain()
+    bm.end_synchronize()
+    res["replicas_bit_identical_after_pipelined_bmuf"] = identical()
+    w_after = net.get_params().astype(np.float64)
+    res["pipelined_bmuf_moved_the_model"] = bool(np.abs(w_after - w_prev).max() > 0)
     if rank == 0:
         res["bmuf_max_rel_err_of_update_vs_formula"] = max(errs)
         res["max_rel_err_vs_formula"] = max(res["bsp_max_rel_err_vs_formula"], max(errs))
-    res["replicas_bit_identical"] = bool(res["replicas_bit_identical_after_bmuf"] and res["replicas_bit_identical_after_bsp"] and res["replicas_bit_identical_after_bmuf_rounds"])
+    res["replicas_bit_identical"] = bool(res["replicas_bit_identical_after_bmuf"] and res["replicas_bit_identical_after_bsp"] and res["replicas_bit_identical_after_bmuf_rounds"] and
+                                         res["replicas_bit_identical_after_pipelined_bmuf"])
     # ---- BSP after EVERY minibatch, timed like the main loop
     NN.device_sync(); dist.barrier()
     for _ in range(2):
@@ -342,6 +353,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocking-sync", action="store_true", help="N > 1: BmufWorker::Synchronize after the minibatch, as the reference calls it, instead of the exchange pipelined by layer")
     ap.add_argument("--no-secondary", action="store_true", help="skip the CTC / GEMM / TF32-mode side measurements (profiling runs: keeps the launch list to the training steps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -401,18 +413,27 @@ def main():
         ids = [NN.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         worker = NN.Worker("bmuf", ids[0], world, rank, bmuf_momentum=1.0 - 1.0 / world, bmuf_learn_rate=1.0)
-        worker.init_param(net)
+        worker.init_param_by_component(net)        # exchanges go component by component: they can ride under Backpropagate
 
+    overlap = worker is not None and not args.blocking_sync
     state = {"since_sync": 0}
 
     def step(on_device):
+        # A synchronisation is due after this minibatch: with the pipelined exchange the worker is told BEFORE it, so that every
+        # layer's tensors go out behind that layer's Update while the layers below still back-propagate (IWorker::BeginSynchronize)
+        due = worker is not None and state["since_sync"] + S * T > SYNC_PERIOD
+        if due and overlap:
+            worker.begin_synchronize(state["since_sync"] + S * T)
         if on_device:
             costs = NN.train_step_ctc(net, current_ctc(), dev_ptr, lens, None, norm_learn_rate=NORM_LR, on_device=True, rows=T * S, cols=D, flat=flat)
         else:
             costs = NN.train_step_ctc(net, current_ctc(), pinned, lens, None, norm_learn_rate=NORM_LR, flat=flat)
         state["since_sync"] += S * T
-        if worker is not None and state["since_sync"] > SYNC_PERIOD:
-            worker.synchronize(state["since_sync"])
+        if due:
+            if overlap:
+                worker.end_synchronize()
+            else:
+                worker.synchronize(state["since_sync"])
             state["since_sync"] = 0
         return costs
 
@@ -526,7 +547,7 @@ def main():
             "metric": METRIC, "value": frames / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else ("f32 (chunk GEMMs: 3xTF32 split; recurrences: fp16 hi/lo split, backward operand scaled per stream by an exact power of two; all fp32-grade, fp32 accumulate)" if args.precision == "3xtf32" else "f32 (GEMMs: TF32)"),
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": workload_config(world, "pipelined by layer under Backpropagate" if overlap else "blocking after the minibatch"),
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(feats.nbytes), "d2h_bytes_per_step": int(4 * S)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

@@ -100,6 +100,15 @@ int aslp_worker_create(const char* type, const char nccl_id[128], int nranks, in
                        const char* sod_solver, aslp_worker_t* out);
 int aslp_worker_init_param(aslp_worker_t w, aslp_nnet_t n);                       /* IWorker::InitParam(GetGpuParams) */
 int aslp_worker_synchronize(aslp_worker_t w, int num_frames, int* keep_going);    /* IWorker::Synchronize */
+/* The exchange pipelined by layer (not in the reference, same arithmetic per tensor): register the tensors with
+ * aslp_worker_init_param_by_component on EVERY rank (synchronize then exchanges component by component, top layer first); a
+ * trainer that knows a synchronisation is due after the coming minibatch calls begin_synchronize(frames) before the minibatch
+ * and end_synchronize after it instead of synchronize(frames): each component's tensors are exchanged on the worker's own stream as
+ * soon as its Update is enqueued, while the layers below still back-propagate.  bmuf and sod only (can_overlap). */
+int aslp_worker_init_param_by_component(aslp_worker_t w, aslp_nnet_t n);
+int aslp_worker_can_overlap(aslp_worker_t w, int* yes);
+int aslp_worker_begin_synchronize(aslp_worker_t w, int num_frames);
+int aslp_worker_end_synchronize(aslp_worker_t w, int* keep_going);
 int aslp_worker_stop(aslp_worker_t w);                                            /* IWorker::Stop */
 int aslp_worker_reduce_acc_stat(aslp_worker_t w, aslp_nnet_t n);                  /* MpiNode::ReduceAccStat (mpi-node.h:76-91) */
 int aslp_worker_destroy(aslp_worker_t w);

@@ -61,6 +61,9 @@ int main(int argc, char* argv[]) {
     po.Register("alpha", &alpha, "Moving rate alpha for easgd worker");
     int32 sync_period = 25600;
     po.Register("sync-period", &sync_period, "number of frames for one sync with other workers");
+    bool pipeline_sync = true;
+    po.Register("pipeline-sync", &pipeline_sync, "bmuf | sod: exchange each layer's tensors behind its Update, under the backward pass "
+                "(same result as the blocking exchange after the minibatch; every rank must use the same setting)");
     float bmuf_momentum = 0.9f, bmuf_learn_rate = 1.0f;
     po.Register("bmuf-momentum", &bmuf_momentum, "bmuf block momentum");
     po.Register("bmuf-learn-rate", &bmuf_learn_rate, "bmuf block learning rate");
@@ -86,6 +89,7 @@ int main(int argc, char* argv[]) {
     nnet.SetChunkSize(chunk_size);
 
     std::unique_ptr<IWorker> worker;
+    SyncCounter sync;                                      // worker-opts.h: frame counter + Synchronize, blocking or pipelined by layer
     if (!worker_type.empty() && !crossvalidate) {
       WorkerBootstrap boot;
       if (worker_type == "bsp") worker.reset(new BspWorker(boot.id, boot.nranks, boot.rank));
@@ -94,9 +98,7 @@ int main(int argc, char* argv[]) {
       else if (worker_type == "easgd") worker.reset(new EasgdWorker(boot.id, boot.nranks, boot.rank, alpha));     // rank 0 runs aslp-nnet-train-server
       else if (worker_type == "asgd") worker.reset(new AsgdWorker(boot.id, boot.nranks, boot.rank));
       else KALDI_ERR << "Unsupported worker type: " << worker_type;
-      std::vector<std::pair<BaseFloat*, int>> params;
-      nnet.GetGpuParams(&params);
-      worker->InitParam(params);
+      sync.Attach(worker.get(), &nnet, sync_period, pipeline_sync);
     }
 
     long long total_frames = 0;
@@ -109,7 +111,7 @@ int main(int argc, char* argv[]) {
     LossItf& xent = *loss_holder;
     Timer time;
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
-    int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0, num_sentence = 0, num_frames_since_sync = 0;
+    int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0, num_sentence = 0;
 
     std::vector<std::string> keys(num_stream);
     std::vector<Matrix<BaseFloat>> feats(num_stream);
@@ -210,7 +212,7 @@ int main(int argc, char* argv[]) {
       int num_done_progress = 0;
       for (size_t i = 0; i < b->new_utt_flags.size(); i++) num_done_progress += b->new_utt_flags[i];
       feeder.Release(b);                              // Xent::Eval has uploaded mask and targets (pageable: staged at the call)
-      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      if (!crossvalidate) { sync.BeforeBackpropagate(frame_progress); nnet.Backpropagate(obj_diff, nullptr); }
 
       total_frames += frame_progress;
       num_done += num_done_progress;
@@ -219,13 +221,7 @@ int main(int argc, char* argv[]) {
         KALDI_LOG << xent.Report();
         num_sentence -= report_period;
       }
-      if (worker) {
-        num_frames_since_sync += frame_progress;
-        if (num_frames_since_sync > sync_period) {
-          worker->Synchronize(num_frames_since_sync);
-          num_frames_since_sync = 0;
-        }
-      }
+      sync.Progress(frame_progress);
       if (dump_interval > 0 && (num_done - num_done_progress) / dump_interval != (num_done / dump_interval) && !crossvalidate) {
         char nnet_name[512];
         snprintf(nnet_name, sizeof(nnet_name), "%s_utt%d", target_model_filename.c_str(), num_done);

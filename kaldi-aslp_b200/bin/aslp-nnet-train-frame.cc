@@ -74,6 +74,7 @@ int main(int argc, char* argv[]) {
     Vector<BaseFloat> ones;
     while (!reader.Done()) {
       if (!reader.ReadData(&nnet_in, &nnet_tgt)) continue;
+      if (!crossvalidate) wopts.BeforeBackpropagate(nnet_in->NumRows());      // a synchronisation due after this minibatch rides under it
       if (!crossvalidate && xent != nullptr) {
         if (ones.Dim() != nnet_in->NumRows()) { ones.Resize(nnet_in->NumRows()); for (int32 r = 0; r < ones.Dim(); ++r) ones(r) = 1.0f; }   // LossItf::Eval's unit frame weights
         train_step.Run(&nnet, xent, *nnet_in, ones, *nnet_tgt);

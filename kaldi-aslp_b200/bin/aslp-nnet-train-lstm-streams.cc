@@ -99,7 +99,7 @@ int main(int argc, char* argv[]) {
       int frame_progress = 0;
       for (int32 i = 0; i < b->frame_mask.Dim(); i++) frame_progress += static_cast<int>(b->frame_mask(i));
       feeder.Release(b);                              // Xent::Eval has uploaded mask and targets
-      if (!crossvalidate) nnet.Backpropagate(obj_diff, nullptr);
+      if (!crossvalidate) { wopts.BeforeBackpropagate(frame_progress); nnet.Backpropagate(obj_diff, nullptr); }
       total_frames += frame_progress;
       wopts.Progress(frame_progress);
       int num_done_progress = 0;

@@ -55,6 +55,9 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     po.Register("alpha", &alpha, "Moving rate alpha for easgd worker");
     int32 sync_period = 25600;
     po.Register("sync-period", &sync_period, "number of frames for one sync with other workers");
+    bool pipeline_sync = true;
+    po.Register("pipeline-sync", &pipeline_sync, "bmuf | sod: exchange each layer's tensors behind its Update, under the backward pass "
+                "(same result as the blocking exchange after the minibatch; every rank must use the same setting)");
     float bmuf_momentum = 0.9f, bmuf_learn_rate = 1.0f;
     po.Register("bmuf-momentum", &bmuf_momentum, "bmuf block momentum");
     po.Register("bmuf-learn-rate", &bmuf_learn_rate, "bmuf block learning rate");
@@ -75,6 +78,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     const float norm_lr = trn_opts.learn_rate;
 
     std::unique_ptr<IWorker> worker;
+    SyncCounter sync;                                      // worker-opts.h: frame counter + Synchronize, blocking or pipelined by layer
     if (!worker_type.empty() && !crossvalidate) {
       WorkerBootstrap boot;
       if (worker_type == "bsp") worker.reset(new BspWorker(boot.id, boot.nranks, boot.rank));
@@ -82,9 +86,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
       else if (worker_type == "easgd") worker.reset(new EasgdWorker(boot.id, boot.nranks, boot.rank, alpha));     // rank 0 runs aslp-nnet-train-server
       else if (worker_type == "asgd") worker.reset(new AsgdWorker(boot.id, boot.nranks, boot.rank));
       else KALDI_ERR << "Unsupported worker type: " << worker_type;
-      std::vector<std::pair<BaseFloat*, int>> params;
-      net.GetGpuParams(&params);
-      worker->InitParam(params);
+      sync.Attach(worker.get(), &net, sync_period, pipeline_sync);
     }
 
     long long total_frames = 0;
@@ -97,7 +99,6 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
     const int32 feat_dim = net.InputDim();
     int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0, num_sentence = 0;
-    int32 num_frames_since_sync = 0;
     CuMatrix<BaseFloat> feat_mat_dev;
 
     // One group of utterances, read / filtered / packed by the feeder thread exactly as the reference's loop does it
@@ -179,7 +180,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
       else net.Feedforward(feat_mat_dev, &net_out);
       ctc.Eval(keys, frame_num_utt, net_out, labels, &obj_diff);
       ctc.ErrorRate(frame_num_utt, net_out, labels);
-      if (!crossvalidate) net.Backpropagate(obj_diff, nullptr);
+      if (!crossvalidate) { sync.BeforeBackpropagate(num_valid_frame); net.Backpropagate(obj_diff, nullptr); }
       num_done += cur_sequence_num;
       total_frames += batch_rows;
       num_sentence += cur_sequence_num;
@@ -187,13 +188,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
         KALDI_LOG << ctc.Report();
         num_sentence -= report_period;
       }
-      if (worker) {
-        num_frames_since_sync += num_valid_frame;
-        if (num_frames_since_sync > sync_period) {
-          worker->Synchronize(num_frames_since_sync);
-          num_frames_since_sync = 0;
-        }
-      }
+      sync.Progress(num_valid_frame);
       if (last) break;
     }
     feeder.Join();

@@ -276,6 +276,10 @@ int aslp_worker_init_param(aslp_worker_t w, aslp_nnet_t n) {
   static_cast<IWorker*>(w)->InitParam(params);
   CAPI_END
 }
+int aslp_worker_init_param_by_component(aslp_worker_t w, aslp_nnet_t n) { CAPI_BEGIN static_cast<IWorker*>(w)->InitParam(N(n)); CAPI_END }
+int aslp_worker_can_overlap(aslp_worker_t w, int* yes) { CAPI_BEGIN *yes = static_cast<IWorker*>(w)->CanOverlap() ? 1 : 0; CAPI_END }
+int aslp_worker_begin_synchronize(aslp_worker_t w, int num_frames) { CAPI_BEGIN static_cast<IWorker*>(w)->BeginSynchronize(num_frames); CAPI_END }
+int aslp_worker_end_synchronize(aslp_worker_t w, int* keep_going) { CAPI_BEGIN const bool k = static_cast<IWorker*>(w)->EndSynchronize(); if (keep_going) *keep_going = k ? 1 : 0; CAPI_END }
 int aslp_worker_synchronize(aslp_worker_t w, int num_frames, int* keep_going) { CAPI_BEGIN const bool k = static_cast<IWorker*>(w)->Synchronize(num_frames); if (keep_going) *keep_going = k ? 1 : 0; CAPI_END }
 int aslp_worker_stop(aslp_worker_t w) { CAPI_BEGIN static_cast<IWorker*>(w)->Stop(); CAPI_END }
 int aslp_worker_reduce_acc_stat(aslp_worker_t w, aslp_nnet_t n) {

@@ -147,7 +147,10 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_
     // update inside backprop (:126-129).  (Running an Affine's weight half on the side stream under the next layer's backward
     // product was measured and dropped: cfg1 0.329 ms with it, 0.321 without -- a tcgen05 GEMM CTA takes a whole SM's shared
     // memory, so two products never share the chip; profiles/r02_config_bench.jsonl)
-    if (c->IsUpdatable()) dynamic_cast<UpdatableComponent*>(c)->Update(cin, output_diff_buf_[i]);
+    if (c->IsUpdatable()) {
+      dynamic_cast<UpdatableComponent*>(c)->Update(cin, output_diff_buf_[i]);
+      if (update_observer_) update_observer_(i);
+    }
     back_propagate_time_[i].first = Component::TypeToMarker(c->GetType());
     back_propagate_time_[i].second += tim.Elapsed();
     if (c->GetType() != Component::kInputLayer && !direct[i]) {
@@ -167,7 +170,7 @@ void Nnet::Backpropagate(const std::vector<const CuMatrixBase<BaseFloat>*>& out_
 }
 
 bool Nnet::StepReplayable() const {
-  if (input_.size() != 1 || output_.size() != 1) return false;
+  if (input_.size() != 1 || output_.size() != 1 || update_observer_) return false;
   for (const Component* c : components_) {
     switch (c->GetType()) {
       case Component::kAffineTransform: case Component::kLinearTransform: case Component::kSigmoid: case Component::kTanh:

@@ -3,6 +3,7 @@
 // (nnet-nnet.cc:70-154), with Update() applied right after each component's Backpropagate (:126-129).
 #ifndef ASLP_HOST_NNET_NNET_H_
 #define ASLP_HOST_NNET_NNET_H_
+#include <functional>
 #include "nnet-component.h"
 
 namespace kaldi {
@@ -70,6 +71,11 @@ class Nnet {
   // component is of a kind that keeps no per-step state on the host (no stream-reset flags, sequence lengths, random
   // masks, running statistics) -- what XentTrainStep needs to record the step once and replay it (nnet-train-step.h)
   bool StepReplayable() const;
+  // called by Backpropagate with a component's index right after that component's Update has been enqueued (its parameters
+  // are final for this minibatch once the compute and side streams reach this point): the parallel workers start exchanging
+  // the component's tensors while the layers below are still back-propagating (parallel.h, IWorker::BeginSynchronize).
+  // A net with an observer is not step-replayable.  NULL removes it.
+  void SetUpdateObserver(std::function<void(int32)> f) { update_observer_ = f; }
   void SetTrainOptions(const NnetTrainOptions& opts);
   const NnetTrainOptions& GetTrainOptions() const { return opts_; }
   void AutoComplete();
@@ -83,6 +89,7 @@ class Nnet {
   std::vector<std::pair<std::string, BaseFloat>> propagate_time_, back_propagate_time_;
   std::vector<CuMatrix<BaseFloat>> input_buf_, output_buf_, input_diff_buf_, output_diff_buf_;
   NnetTrainOptions opts_;
+  std::function<void(int32)> update_observer_;
 };
 
 }  // namespace aslp_nnet

@@ -1,4 +1,5 @@
 #include "parallel.h"
+#include "nnet-nnet.h"
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -46,7 +47,18 @@ void NcclNode::ReduceAccStat(const std::vector<double*>& acc_params, const std::
   CuSync();
 }
 
-IWorker::~IWorker() { if (table_dev_ != nullptr) aslp_free(table_dev_); }
+void IWorker::Reset() {
+  table_dev_ = nullptr; ntensors_ = 0; total_ = 0; nnet_ = nullptr; comm_stream_ = nullptr;
+  ev_compute_ = ev_side_ = ev_done_ = ev_count_ = nullptr; count_host_ = nullptr; count_dev_ = nullptr; armed_ = false;
+}
+IWorker::~IWorker() {
+  if (armed_ && nnet_ != nullptr) nnet_->SetUpdateObserver(nullptr);
+  if (comm_stream_ != nullptr) { aslp_stream_sync(comm_stream_); aslp_stream_destroy(comm_stream_); }
+  aslp_event_destroy(ev_compute_); aslp_event_destroy(ev_side_); aslp_event_destroy(ev_done_); aslp_event_destroy(ev_count_);
+  if (count_host_ != nullptr) aslp_free_host(count_host_);
+  if (count_dev_ != nullptr) aslp_free(count_dev_);
+  if (table_dev_ != nullptr) aslp_free(table_dev_);
+}
 
 void IWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
   std::vector<aslp_tensor_ref_t> table(params.size());
@@ -59,11 +71,38 @@ void IWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
   }
   ntensors_ = static_cast<int>(params.size());
   total_ = off;
+  segments_.clear();
   if (table_dev_ != nullptr) aslp_free(table_dev_);
   ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&table_dev_), sizeof(aslp_tensor_ref_t) * (table.size() + 1)));
   ASLP_OK(aslp_memcpy_h2d(CuStream(), table_dev_, table.data(), sizeof(aslp_tensor_ref_t) * table.size()));
   CuSync();
   arena_.Resize(static_cast<int32>(total_), kSetZero);
+}
+
+// the net's tensors in Nnet::GetGpuParams order, plus the component each run of them belongs to
+void IWorker::InitParam(aslp_nnet::Nnet* nnet) {
+  using aslp_nnet::Component; using aslp_nnet::UpdatableComponent;
+  KALDI_ASSERT(nnet != nullptr);
+  std::vector<std::pair<BaseFloat*, int>> params;
+  std::vector<Segment> segs;
+  size_t off = 0;
+  for (int32 c = 0; c < nnet->NumComponents(); ++c) {
+    Component& comp = nnet->GetComponent(c);
+    if (!comp.IsUpdatable()) continue;
+    std::vector<std::pair<BaseFloat*, int>> cp;
+    dynamic_cast<UpdatableComponent&>(comp).GetGpuParams(&cp);
+    if (cp.empty()) continue;
+    Segment s;
+    s.component = c; s.first = static_cast<int>(params.size()); s.count = static_cast<int>(cp.size()); s.offset = off;
+    for (const auto& t : cp) off += (static_cast<size_t>(t.second) + 3) / 4 * 4;
+    s.length = off - s.offset;
+    segs.push_back(s);
+    params.insert(params.end(), cp.begin(), cp.end());
+  }
+  InitParam(params);                 // the worker's own (virtual) registration: arena, previous model, optimizer state
+  KALDI_ASSERT(off == total_);
+  segments_ = segs;
+  nnet_ = nnet;
 }
 
 bool IWorker::AllFinished(int num_worker_samples, int* num_all) {
@@ -73,16 +112,88 @@ bool IWorker::AllFinished(int num_worker_samples, int* num_all) {
   return false;
 }
 
+void IWorker::ExchangeAll() {
+  if (segments_.empty()) {
+    Segment all; all.component = -1; all.first = 0; all.count = ntensors_; all.offset = 0; all.length = total_;
+    ExchangeSegment(CuStream(), all);
+  } else {
+    for (size_t i = segments_.size(); i-- > 0;) ExchangeSegment(CuStream(), segments_[i]);
+  }
+  AfterExchange();
+}
+
+void IWorker::BeginSynchronize(int num_worker_samples) {
+  KALDI_ASSERT(CanOverlap() && nnet_ != nullptr && !segments_.empty() && !armed_);
+  KALDI_ASSERT(num_worker_samples > 0);        // a rank inside a minibatch has frames: the job's total cannot be "all finished"
+  if (comm_stream_ == nullptr) {
+    ASLP_OK(aslp_stream_create(&comm_stream_));
+    ASLP_OK(aslp_malloc_host(reinterpret_cast<void**>(&count_host_), 64));
+    ASLP_OK(aslp_malloc(reinterpret_cast<void**>(&count_dev_), 64));
+  }
+  // the frame-count exchange of the termination protocol, as Synchronize issues it first -- here without the host waiting
+  ASLP_OK(aslp_event_record(CuStream(), &ev_compute_));
+  ASLP_OK(aslp_stream_wait_event(comm_stream_, ev_compute_));    // behind whatever an earlier (blocking) exchange left on the compute stream
+  count_host_[0] = num_worker_samples;
+  ASLP_OK(aslp_memcpy_h2d(comm_stream_, count_dev_, count_host_, sizeof(int)));
+  ASLP_OK(aslp_comm_allreduce_sum_i32(comm_, comm_stream_, count_dev_, 1));
+  ASLP_OK(aslp_memcpy_d2h(comm_stream_, count_host_ + 1, count_dev_, sizeof(int)));
+  ASLP_OK(aslp_event_record(comm_stream_, &ev_count_));
+  exchanged_.assign(segments_.size(), 0);
+  armed_ = true;
+  nnet_->SetUpdateObserver([this](int component) { OnComponentUpdated(component); });
+}
+
+void IWorker::OnComponentUpdated(int component) {
+  if (!armed_) return;
+  for (size_t i = 0; i < segments_.size(); ++i) {
+    if (segments_[i].component != component || exchanged_[i]) continue;
+    // Collectives must be issued in the same order on every rank: top component first, none skipped.
+    for (size_t j = segments_.size(); j-- > i + 1;) KALDI_ASSERT(exchanged_[j]);
+    // the Update may sit on the compute stream, on the side stream (weight-gradient tail of the recurrent layers), or both
+    ASLP_OK(aslp_event_record(CuStream(), &ev_compute_));
+    ASLP_OK(aslp_stream_wait_event(comm_stream_, ev_compute_));
+    ASLP_OK(aslp_event_record(CuSideStream(), &ev_side_));
+    ASLP_OK(aslp_stream_wait_event(comm_stream_, ev_side_));
+    ExchangeSegment(comm_stream_, segments_[i]);
+    exchanged_[i] = 1;
+  }
+}
+
+bool IWorker::EndSynchronize() {
+  KALDI_ASSERT(armed_);
+  nnet_->SetUpdateObserver(nullptr);
+  armed_ = false;
+  // components whose Update was not reported (a net driven without Nnet::Backpropagate): exchange them now, in order
+  for (size_t i = segments_.size(); i-- > 0;) {
+    if (exchanged_[i]) continue;
+    ASLP_OK(aslp_event_record(CuStream(), &ev_compute_));
+    ASLP_OK(aslp_stream_wait_event(comm_stream_, ev_compute_));
+    ASLP_OK(aslp_event_record(CuSideStream(), &ev_side_));
+    ASLP_OK(aslp_stream_wait_event(comm_stream_, ev_side_));
+    ExchangeSegment(comm_stream_, segments_[i]);
+    exchanged_[i] = 1;
+  }
+  AfterExchange();
+  ASLP_OK(aslp_event_record(comm_stream_, &ev_done_));
+  ASLP_OK(aslp_stream_wait_event(CuStream(), ev_done_));         // the next Propagate reads the exchanged model
+  ASLP_OK(aslp_stream_wait_event(CuSideStream(), ev_done_));
+  ASLP_OK(aslp_event_sync(ev_count_));                            // long complete: it was issued before the minibatch
+  return count_host_[1] > 0;
+}
+
 // frame-weighted MODEL average (bsp-worker.cc:33-58): w <- sum_r (frames_r / frames_all) * w_r
 bool BspWorker::Synchronize(int num_worker_samples) {
   int num_all = 0;
   if (AllFinished(num_worker_samples, &num_all)) return false;
-  const float factor = static_cast<float>(num_worker_samples) / num_all;
-  KALDI_ASSERT(factor >= 0.0 && factor <= 1.0);
-  ASLP_OK(aslp_sync_pack(CuStream(), arena_.Data(), table_dev_, ntensors_, factor));
-  AllReduceDevice(arena_.Data(), total_);
-  ASLP_OK(aslp_sync_unpack(CuStream(), arena_.Data(), table_dev_, ntensors_));
+  factor_ = static_cast<float>(num_worker_samples) / num_all;
+  KALDI_ASSERT(factor_ >= 0.0 && factor_ <= 1.0);
+  ExchangeAll();
   return true;
+}
+void BspWorker::ExchangeSegment(aslp_stream_t st, const Segment& seg) {
+  ASLP_OK(aslp_sync_pack(st, arena_.Data(), table_dev_ + seg.first, seg.count, factor_));
+  ASLP_OK(aslp_comm_allreduce_sum_f32(comm_, st, arena_.Data() + seg.offset, seg.length));
+  ASLP_OK(aslp_sync_unpack(st, arena_.Data(), table_dev_ + seg.first, seg.count));
 }
 
 void BmufWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
@@ -96,10 +207,13 @@ void BmufWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params
 bool BmufWorker::Synchronize(int num_worker_samples) {
   int num_all = 0;
   if (AllFinished(num_worker_samples, &num_all)) return false;
-  ASLP_OK(aslp_sync_pack_diff(CuStream(), arena_.Data(), table_dev_, ntensors_, w_prev_.Data(), 1.0f));
-  AllReduceDevice(arena_.Data(), total_);
-  ASLP_OK(aslp_sync_bmuf_apply_packed(CuStream(), table_dev_, ntensors_, w_prev_.Data(), delta_prev_.Data(), arena_.Data(), momentum_, learn_rate_));
+  ExchangeAll();
   return true;
+}
+void BmufWorker::ExchangeSegment(aslp_stream_t st, const Segment& seg) {
+  ASLP_OK(aslp_sync_pack_diff(st, arena_.Data(), table_dev_ + seg.first, seg.count, w_prev_.Data(), 1.0f));
+  ASLP_OK(aslp_comm_allreduce_sum_f32(comm_, st, arena_.Data() + seg.offset, seg.length));
+  ASLP_OK(aslp_sync_bmuf_apply_packed(st, table_dev_ + seg.first, seg.count, w_prev_.Data(), delta_prev_.Data(), arena_.Data(), momentum_, learn_rate_));
 }
 
 void SodWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params) {
@@ -113,19 +227,21 @@ void SodWorker::InitParam(const std::vector<std::pair<BaseFloat*, int>>& params)
 bool SodWorker::Synchronize(int num_worker_samples) {
   int num_all = 0;
   if (AllFinished(num_worker_samples, &num_all)) return false;
-  ASLP_OK(aslp_sync_pack_diff(CuStream(), arena_.Data(), table_dev_, ntensors_, w_prev_.Data(), -1.0f));
-  AllReduceDevice(arena_.Data(), total_);
-  int opt; float lr = config_.lr, p1 = 0.f, p2 = 0.f;
+  ExchangeAll();
+  return true;
+}
+void SodWorker::ExchangeSegment(aslp_stream_t st, const Segment& seg) {
+  ASLP_OK(aslp_sync_pack_diff(st, arena_.Data(), table_dev_ + seg.first, seg.count, w_prev_.Data(), -1.0f));
+  ASLP_OK(aslp_comm_allreduce_sum_f32(comm_, st, arena_.Data() + seg.offset, seg.length));
+  int opt = ASLP_OPT_SGD; float lr = config_.lr, p1 = 0.f, p2 = 0.f;
   if (config_.solver == "sgd") { opt = ASLP_OPT_SGD; }
   else if (config_.solver == "momentum") { opt = ASLP_OPT_MOMENTUM; p1 = config_.momentum; }
   else if (config_.solver == "adagrad") { opt = ASLP_OPT_ADAGRAD; lr = config_.adagrad_lr; }
   else if (config_.solver == "rmsprop") { opt = ASLP_OPT_RMSPROP; lr = config_.rmsprop_lr; }
   else if (config_.solver == "adadelta") { opt = ASLP_OPT_ADADELTA; p1 = config_.adadelta_gamma; }
   else if (config_.solver == "adam") { opt = ASLP_OPT_ADAM; lr = config_.adam_lr; p1 = config_.adam_beta1; p2 = config_.adam_beta2; }
-  else { KALDI_ERR << "Unknown solver type " << config_.solver; return false; }
-  ASLP_OK(aslp_sync_sod_apply_packed(CuStream(), opt, table_dev_, ntensors_, arena_.Data(), s1_.Data(), s2_.Data(), w_prev_.Data(), lr, p1, p2, 1e-8f, step_));
-  ++step_;
-  return true;
+  else { KALDI_ERR << "Unknown solver type " << config_.solver; }
+  ASLP_OK(aslp_sync_sod_apply_packed(st, opt, table_dev_ + seg.first, seg.count, arena_.Data(), s1_.Data(), s2_.Data(), w_prev_.Data(), lr, p1, p2, 1e-8f, step_));
 }
 
 WorkerBootstrap::WorkerBootstrap() : rank(0), nranks(1) {

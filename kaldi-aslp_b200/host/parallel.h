@@ -38,24 +38,55 @@ struct WorkerBootstrap {
   WorkerBootstrap();
 };
 
+namespace aslp_nnet { class Nnet; }
+
 class IWorker : public NcclNode {
  public:
-  IWorker(const char id[128], int nranks, int rank) : NcclNode(id, nranks, rank), table_dev_(nullptr), total_(0) {}
+  IWorker(const char id[128], int nranks, int rank) : NcclNode(id, nranks, rank) { Reset(); }
   // the reference's workers take no launch arguments (MpiNode's constructor calls MPI_Init, mpi-node.h:21-27): bootstrap from the
   // environment instead, so that `new BspWorker()` / `new BmufWorker(momentum, learn_rate)` in an unmodified main keep working
-  explicit IWorker(const WorkerBootstrap& b) : NcclNode(b.id, b.nranks, b.rank), table_dev_(nullptr), total_(0) {}
+  explicit IWorker(const WorkerBootstrap& b) : NcclNode(b.id, b.nranks, b.rank) { Reset(); }
   virtual ~IWorker();
   virtual void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   virtual bool Synchronize(int num_worker_samples) = 0;   // false when every rank is out of data
   virtual bool IsAsync() const { return false; }          // true: a parameter-server worker (Synchronize never says "all done")
   // a rank that has finished its shard keeps answering with zero frames so collectives stay matched (bsp-worker.cc:60-65)
   virtual void Stop() { KALDI_LOG << "Worker " << Rank() << "finished, waitting for others"; while (Synchronize(0)) {} }
+
+  // ---- the exchange pipelined by layer (not in the reference, whose Synchronize blocks after the minibatch: same arithmetic,
+  // same result per tensor).  InitParam(nnet) registers the net's tensors as InitParam(params) does and remembers which belong
+  // to which component; every Synchronize then exchanges component by component, top layer first -- on EVERY rank, so all
+  // ranks of a job must use the same form of InitParam.  A trainer that knows a synchronisation is due after the coming
+  // minibatch calls BeginSynchronize(n) before it instead of Synchronize(n) after it: the frame counts are exchanged at once,
+  // and each component's tensors as soon as Nnet::Backpropagate has enqueued its Update -- on the worker's own stream, while
+  // the layers below are still back-propagating.  EndSynchronize() after the minibatch makes the compute stream wait for
+  // the last exchange and returns what Synchronize(n) would have.  Only workers whose exchange does not need the global
+  // frame count up front can do this (CanOverlap(): BMUF and SOD; BSP weighs its model by frames_r / frames_all).
+  virtual bool CanOverlap() const { return false; }
+  void InitParam(aslp_nnet::Nnet* nnet);
+  void BeginSynchronize(int num_worker_samples);
+  bool EndSynchronize();
  protected:
+  struct Segment { int component, first, count; size_t offset, length; };   // tensors [first, first + count) = arena [offset, offset + length)
+  void Reset();
   bool AllFinished(int num_worker_samples, int* num_all);
+  // pack, all-reduce and apply the tensors of one segment on stream `st` (the whole exchange when there are no segments)
+  virtual void ExchangeSegment(aslp_stream_t st, const Segment& seg) { KALDI_ERR << "this worker has no segmented exchange"; }
+  void ExchangeAll();                               // every segment on the compute stream, top component first
+  virtual void AfterExchange() {}                   // once per synchronisation (SOD's step counter)
+  void OnComponentUpdated(int component);
   aslp_tensor_ref_t* table_dev_;
   int ntensors_;
   size_t total_;            // packed arena length
   CuVector<BaseFloat> arena_;          // the all-reduce buffer
+  std::vector<Segment> segments_;      // in component order; empty: one exchange of everything
+  aslp_nnet::Nnet* nnet_;
+  aslp_stream_t comm_stream_;
+  void *ev_compute_, *ev_side_, *ev_done_, *ev_count_;
+  int* count_host_;                    // page-locked: this rank's frame count in, the job's total out
+  int* count_dev_;
+  bool armed_;
+  std::vector<char> exchanged_;
 };
 
 class BspWorker : public IWorker {
@@ -63,6 +94,10 @@ class BspWorker : public IWorker {
   BspWorker(const char id[128], int nranks, int rank) : IWorker(id, nranks, rank) {}
   BspWorker() : IWorker(WorkerBootstrap()) {}                                  // bsp-worker.h:21
   bool Synchronize(int num_worker_samples);
+ protected:
+  void ExchangeSegment(aslp_stream_t st, const Segment& seg);
+ private:
+  float factor_;
 };
 
 class BmufWorker : public IWorker {
@@ -71,8 +106,12 @@ class BmufWorker : public IWorker {
       : IWorker(id, nranks, rank), momentum_(momentum), learn_rate_(learn_rate) {}
   // the reference's own signature and argument ORDER (bmuf-worker.h:31: learn rate first)
   explicit BmufWorker(float learn_rate = 1.0f, float momentum = 0.9f) : IWorker(WorkerBootstrap()), momentum_(momentum), learn_rate_(learn_rate) {}
+  using IWorker::InitParam;
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);
+  bool CanOverlap() const { return true; }
+ protected:
+  void ExchangeSegment(aslp_stream_t st, const Segment& seg);
  private:
   float momentum_, learn_rate_;
   CuVector<BaseFloat> w_prev_, delta_prev_;
@@ -100,8 +139,13 @@ class SodWorker : public IWorker {
  public:
   SodWorker(const char id[128], int nranks, int rank, const OptimizerOption& config) : IWorker(id, nranks, rank), config_(config), step_(1) {}
   explicit SodWorker(const OptimizerOption& config) : IWorker(WorkerBootstrap()), config_(config), step_(1) {}              // sod-worker.h
+  using IWorker::InitParam;
   void InitParam(const std::vector<std::pair<BaseFloat*, int>>& params);
   bool Synchronize(int num_worker_samples);
+  bool CanOverlap() const { return true; }
+ protected:
+  void ExchangeSegment(aslp_stream_t st, const Segment& seg);
+  void AfterExchange() { ++step_; }
  private:
   OptimizerOption config_;
   int step_;

@@ -261,9 +261,28 @@ class Worker:
     def init_param(self, nnet):
         _ck(host_lib().aslp_worker_init_param(self.h, nnet.h))
 
+    def init_param_by_component(self, nnet):
+        """As init_param, remembering which tensors belong to which component: every synchronisation then goes component by
+        component (all ranks must register the same way), and begin_synchronize / end_synchronize can pipeline it by layer."""
+        _ck(host_lib().aslp_worker_init_param_by_component(self.h, nnet.h))
+
+    def can_overlap(self):
+        y = ctypes.c_int(0)
+        _ck(host_lib().aslp_worker_can_overlap(self.h, ctypes.byref(y)))
+        return bool(y.value)
+
     def synchronize(self, num_frames):
         k = ctypes.c_int(0)
         _ck(host_lib().aslp_worker_synchronize(self.h, int(num_frames), ctypes.byref(k)))
+        return bool(k.value)
+
+    def begin_synchronize(self, num_frames):
+        """Before the minibatch after which synchronize(num_frames) would have been called (IWorker::BeginSynchronize)."""
+        _ck(host_lib().aslp_worker_begin_synchronize(self.h, int(num_frames)))
+
+    def end_synchronize(self):
+        k = ctypes.c_int(0)
+        _ck(host_lib().aslp_worker_end_synchronize(self.h, ctypes.byref(k)))
         return bool(k.value)
 
     def stop(self):

@@ -25,7 +25,7 @@ def local_step(NN, net, rank):
     NN.train_step_xent(net, NN.Xent(), x, t)
 
 
-def rank_main(rank, world, kind, id_file, out_dir):
+def rank_main(rank, world, kind, id_file, out_dir, mode="blocking"):
     import kaldi_aslp_b200 as K
     from kaldi_aslp_b200 import nnet as NN
     NN.select_device(rank)
@@ -43,9 +43,24 @@ def rank_main(rank, world, kind, id_file, out_dir):
     net = NN.Nnet.read(os.path.join(GOLD, "model.bin"))
     w0 = net.get_params()
     worker = NN.Worker(kind, ident, world, rank, bmuf_momentum=0.5, bmuf_learn_rate=1.0, sod_solver="momentum")
-    worker.init_param(net)
+    # blocking: the reference's form.  segmented: tensors registered by component, every exchange goes component by component.
+    # overlapped: begin_synchronize before the minibatch, each component exchanged behind its Update, end_synchronize after.
+    if mode == "blocking":
+        worker.init_param(net)
+    else:
+        worker.init_param_by_component(net)
+    if mode == "overlapped":
+        assert worker.can_overlap()
     trace = [w0]
     for step in range(2):
+        # one rank falls back to the blocking call in the second round: the collectives of the two forms must pair up
+        if mode == "overlapped" and not (step == 1 and rank == world - 1 and world > 1):
+            worker.begin_synchronize(FRAMES[rank])
+            local_step(NN, net, rank + 10 * step)
+            assert worker.end_synchronize() is True
+            trace.append(net.get_params())             # the model before the exchange is never visible here: run_world compares
+            trace.append(net.get_params())             # the result with the blocking run's
+            continue
         local_step(NN, net, rank + 10 * step)
         trace.append(net.get_params())                 # before the sync
         assert worker.synchronize(FRAMES[rank]) is True
@@ -87,18 +102,25 @@ def expected(kind, traces):
     return out
 
 
-def run_world(world, kind):
+def run_world(world, kind, mode="blocking"):
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as d:
         id_file = os.path.join(d, "nccl_id")
         ctx = mp.get_context("spawn")
-        procs = [ctx.Process(target=rank_main, args=(r, world, kind, id_file, d)) for r in range(world)]
+        procs = [ctx.Process(target=rank_main, args=(r, world, kind, id_file, d, mode)) for r in range(world)]
         for p in procs:
             p.start()
         for p in procs:
             p.join(300)
-            assert p.exitcode == 0, (kind, p.exitcode)
+            assert p.exitcode == 0, (kind, mode, p.exitcode)
         traces = [np.load(os.path.join(d, "rank%d.npy" % r)) for r in range(world)]
+    if mode == "overlapped":
+        # steps are deterministic and a two-term sum does not depend on how the all-reduce is cut up: bit-identical to blocking
+        ref = run_world(world, kind, "blocking")
+        for step in range(2):
+            for r in range(world):
+                assert np.array_equal(traces[r][2 + 2 * step], ref[r][2 + 2 * step]), (kind, step, r)
+        return traces
     want = expected(kind, traces)
     for step in range(2):
         for r in range(world):
@@ -107,6 +129,7 @@ def run_world(world, kind):
             assert err < 1e-6, (kind, step, r, err)
         if world > 1 and kind != "sod":      # replicas agree bit for bit after a BSP / BMUF sync
             assert np.array_equal(traces[0][2 + 2 * step], traces[1][2 + 2 * step]), (kind, step)
+    return traces
 
 
 @pytest.mark.parametrize("kind", ["bsp", "bmuf", "sod"])
@@ -120,3 +143,17 @@ def test_two_rank_worker_matches_replica_simulation(kind):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     run_world(2, kind)
+
+
+@pytest.mark.parametrize("kind,mode", [("bsp", "segmented"), ("bmuf", "segmented"), ("bmuf", "overlapped"), ("sod", "overlapped")])
+def test_single_rank_exchange_by_component(kind, mode):
+    """IWorker::InitParam(nnet) / BeginSynchronize / EndSynchronize: the exchange pipelined by layer gives what the blocking one does"""
+    run_world(1, kind, mode)
+
+
+@pytest.mark.parametrize("kind,mode", [("bsp", "segmented"), ("bmuf", "overlapped"), ("sod", "overlapped")])
+def test_two_rank_exchange_by_component(kind, mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_world(2, kind, mode)
