@@ -218,7 +218,9 @@ int aslp_bn_bwd(aslp_stream_t s, float* in_diff, int ldd, const float* in, int l
  * nnet-max-pooling-component.h:100-156) ----
  * gather : patches[(b*num_patches + p)*ldp + s*patch_dim + d] = in[b*ldi + p*patch_step + s*patch_stride + d]
  *          (replaces column_map + CopyCols; with this layout the per-patch AddMatMat loop is ONE aslp_gemm:
- *          [rows*num_patches, filter_dim] x filters^T -> out viewed as [rows*num_patches, num_filters])
+ *          [rows*num_patches, filter_dim] x filters^T -> out viewed as [rows*num_patches, num_filters]);
+ *          when ldp is filter_dim rounded up to a multiple of 4 the rounding columns are written too (zeros), otherwise
+ *          columns beyond filter_dim are left alone
  * scatter: in_diff[b, c] = sum over the patch positions that read column c, in ascending p (replaces ReverseIndexes /
  *          RearrangeIndexes / AddCols); in_diff is overwritten
  * maxpool fwd: out[b, q*S + j] = max(-1e20, max_{r<pool_size} in[b, (q*pool_step + r)*S + j]),  S = pool_stride

@@ -332,7 +332,8 @@ def test_posterior_finalize(rows, cols, apply_log, blank, prior):
     assert s[4] == 0
 
 
-@pytest.mark.parametrize("rows,ns,stride,pd,step,nf", [(256, 11, 40, 9, 1, 128), (37, 3, 11, 4, 1, 6), (50, 2, 12, 4, 2, 5), (9, 1, 8, 8, 1, 3)])
+@pytest.mark.parametrize("rows,ns,stride,pd,step,nf", [(256, 11, 40, 9, 1, 128), (37, 3, 11, 4, 1, 6), (50, 2, 12, 4, 2, 5), (9, 1, 8, 8, 1, 3),
+                                                         (8000, 11, 40, 9, 1, 8), (300, 20, 64, 8, 1, 4)])
 def test_conv_gather_gemm_scatter(rows, ns, stride, pd, step, nf):
     """ConvolutionalComponent device side (nnet-convolutional-component.h:263-421): im2col into [frames*P, filter_dim], ONE GEMM
     into the [frames, P*num_filters] output, and the inverse gather-sum; the first shape is the recipes' 40 x 11 input."""
@@ -364,7 +365,7 @@ def test_conv_gather_gemm_scatter(rows, ns, stride, pd, step, nf):
     assert np.array_equal(din.np(), want_in)                                           # same summation order: bit-exact
 
 
-@pytest.mark.parametrize("rows,patches,size,step,ps", [(256, 32, 4, 4, 128), (40, 8, 4, 2, 6), (13, 7, 3, 2, 5), (5, 4, 4, 1, 3)])
+@pytest.mark.parametrize("rows,patches,size,step,ps", [(256, 32, 4, 4, 128), (40, 8, 4, 2, 6), (13, 7, 3, 2, 5), (5, 4, 4, 1, 3), (300, 9, 3, 2, 16)])
 def test_maxpool_fwd_bwd(rows, patches, size, step, ps):
     """MaxPoolingComponent (nnet-max-pooling-component.h:100-156), overlapping pools and ties included."""
     from tests.gpu_utils import DMat, lib, ok, stream, sync
