@@ -17,9 +17,6 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include <map>
-#include <mutex>
-#include <utility>
 #include "scratch.cuh"
 
 // persistent-grid cap of the calling thread (aslp_gemm_set_cta_limit): work issued on a side stream leaves SMs to a concurrently
@@ -142,6 +139,20 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #else
 #define DBG_T(slot) do {} while (0)
 #endif
+constexpr int TB_PITCH = 132;                             // floats per row of a CTA's raw tile in shared memory (cluster reduction)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 struct EpiParams {
   float* C; int ldc;
   int M, N, K;
@@ -152,14 +163,13 @@ struct EpiParams {
   int ldp;
   int kb_per_split;
   int tiles_m, tiles_n, splits;   // persistent scheduling: work item = (split z, tile row, tile column), z slowest
-  // split-K reduced INSIDE the launch (one work item per CTA, all of them resident): after writing its partial tile a CTA
-  // counts itself in on counters[tile], waits for the other splits of the tile, and reduces its own 1/splits of the tile's
-  // rows over all partials (ascending z: the same order and rounding as splitk_reduce_kernel) with the full epilogue.
-  // Opt-in (aslp_gemm_epilogue_t::reduce_in_launch), and the host layer leaves it off: measured with the stamps below
-  // (-DASLP_GEMM_DEBUG_TIMES, tools/gemm_in_launch_probe.py; profiles/r02_gemm_in_launch_reduce.txt), the 128 threads per SM
-  // that are left to reduce pull their 73 KB of partials out of L2 in 8 us (19 us with the C / W read-modify-write of a
-  // weight gradient), where the separate pass with 256K threads takes 4.6 us INCLUDING its launch.
-  int* counters;       // [2 * tiles]: arrivals, then finished reducers (the last one re-arms both); NULL = separate reduce pass
+  // split-K reduced INSIDE the launch: the `splits` CTAs of a tile form a thread-block cluster (blockIdx = tile * splits + z,
+  // cluster rank = z); each leaves its raw accumulator tile in its OWN shared memory (the operand stages are free by then),
+  // the cluster meets, and CTA z reduces rows [z, z+1) * 128 / splits of the tile over all peers through distributed shared
+  // memory in ascending z (the order and rounding of splitk_reduce_kernel) with the full epilogue.  No partial tile goes to
+  // global memory, no second launch.  (The first form of this -- partials in global memory, arrival counters, 128 threads
+  // per SM pulling 73 KB out of L2 -- took 8-19 us for the reduction alone: profiles/r02_gemm_in_launch_reduce.txt.)
+  int cluster;         // non-zero: launched with cluster dimension = splits (<= 8), one work item per CTA
   EpiExt ext;
 };
 
@@ -190,8 +200,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // item -> (z, m0, n0, k-block range); consecutive items walk the tile columns of one row, so CTAs running at the same
   // time share the A rows in L2
   auto item_coords = [&](int item, int& z, int& m0, int& n0, int& kb_begin, int& kb_end) {
-    z = item / tiles_mn;
-    const int t = item - z * tiles_mn;
+    z = (INL && p.cluster) ? item % p.splits : item / tiles_mn;
+    const int t = (INL && p.cluster) ? item / p.splits : item - z * tiles_mn;
     const int tm = t / p.tiles_n;
     m0 = tm * BM; n0 = (t - tm * p.tiles_n) * BN;
     kb_begin = z * p.kb_per_split;
@@ -324,7 +334,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_idx * BN + c * 32), v);
         const int nb = n0 + c * 32;
-        if (nb < p.N) {                         // warp-uniform
+        if (INL && p.cluster) {                 // raw accumulator chunk -> this CTA's tile buffer (row = TMEM lane, pitch 132: conflict-free)
+          float* tb = reinterpret_cast<float*>(smem_gen) + (size_t)(q * 32 + lane) * TB_PITCH + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tb + j) = has_work ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (nb < p.N) {                  // warp-uniform
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) =
@@ -393,38 +409,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc_idx));
       if (++acc_idx == 2) { acc_idx = 0; acc_ph ^= 1u; }
-      if constexpr (INL) if (p.partial != nullptr && p.counters != nullptr) {
-        // ---- in-launch reduction (grid == number of work items: every split of this tile is running on some SM right now)
+      if constexpr (INL) if (p.cluster) {
+        // ---- in-launch reduction over the cluster
         const int et = threadIdx.x - 64;                  // 0..127 over the four epilogue warps
-        const int tile = item - z * tiles_mn;
         DBG_T(1);
-        // The 128 partial-tile writers meet at the CTA barrier and ONE thread publishes for all of them: its gpu-scope release
-        // is cumulative over what the barrier ordered before it.
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          asm volatile("red.release.gpu.global.add.s32 [%0], 1;" :: "l"(p.counters + tile) : "memory");
-          int seen;
-          unsigned spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory");
-            if (seen < p.splits) { __nanosleep(40); if (++spins > (1u << 26)) __trap(); }      // seconds: an error, never a hang
-          } while (seen < p.splits);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cluster_sync_all();                               // every split's tile is in its CTA's shared memory
         DBG_T(2);
         const int rp = (BM + p.splits - 1) / p.splits;    // rows of the tile this split reduces
         const int c4 = (et & 31) << 2;                    // 4 columns per thread, 32 threads span the tile's 128 columns
         const int col = n0 + c4;
         if (col < p.N) {
           // A thread owns the rows (et >> 5) + 4 i of the slice and needs `splits` partials of each (32 loads in all, whatever
-          // the split count) plus the old C / y / W values of the epilogue.  Only 128 threads per SM are left to do this, so
-          // nothing may wait for one load at a time: a batch of rows has ALL its loads issued (up to 16 partials and the
-          // epilogue operands) before the first add, and only then the adds, in ascending z, and the stores.
+          // the split count) plus the old C / y / W values of the epilogue: a batch of rows has ALL its loads issued (up to
+          // 16 partials and the epilogue operands) before the first add, then the adds in ascending z, then the stores.
           const int iters = (rp + 3) >> 2;
-          const int nb = p.splits <= 4 ? 4 : (p.splits <= 8 ? 2 : 1);          // rows per batch: nb * splits <= 16, or one row
-          auto row_of = [&](int i, bool& ok) {
-            const int rr = (et >> 5) + 4 * i, row = m0 + z * rp + rr;
-            ok = i < iters && rr < rp && z * rp + rr < BM && row < p.M;
+          const int nb = p.splits <= 4 ? 4 : 2;                                // rows per batch: nb * splits <= 16
+          const uint32_t tb_local = smem_base + (uint32_t)c4 * 4u;
+          auto row_of = [&](int i, bool& ok, int& rt) {
+            const int rr = (et >> 5) + 4 * i;
+            rt = z * rp + rr;
+            const int row = m0 + rt;
+            ok = i < iters && rr < rp && rt < BM && row < p.M;
             return row;
           };
           float bia[4];
@@ -434,8 +439,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float ad[4][4], aw[4][4], ay[4][4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              bool ok;
-              const int row = row_of(i0 + r, ok);
+              bool ok; int rt;
+              const int row = row_of(i0 + r, ok, rt);
               ok = ok && r < nb;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -447,68 +452,47 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             float4 accs[4];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (nb > 1) {
-              float4 v[16];
+            float4 v[16];
 #pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const int r = u / p.splits, zz = u - r * p.splits;
-                bool ok;
-                const int row = row_of(i0 + r, ok);
-                v[u] = (ok && r < nb) ? __ldcg(reinterpret_cast<const float4*>(p.partial + ((size_t)zz * p.M + row) * p.ldp + col))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
+            for (int u = 0; u < 16; ++u) {
+              const int r = u / p.splits, zz = u - r * p.splits;
+              bool ok; int rt;
+              row_of(i0 + r, ok, rt);
+              v[u] = (ok && r < nb) ? ld_dsmem_v4(mapa_u32(tb_local + (uint32_t)rt * (TB_PITCH * 4u), (uint32_t)zz)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const int r = u / p.splits, zz = u - r * p.splits;
-                if (zz == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            for (int u = 0; u < 16; ++u) {
+              const int r = u / p.splits, zz = u - r * p.splits;
+              if (zz == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (q == r && zz == p.splits - 1) accs[q] = acc;
-              }
-            } else {
-              bool ok;
-              const int row = row_of(i0, ok);
-              for (int z0 = 0; z0 < p.splits; z0 += 16) {
-                float4 v[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u)
-                  v[u] = (ok && z0 + u < p.splits) ? __ldcg(reinterpret_cast<const float4*>(p.partial + ((size_t)(z0 + u) * p.M + row) * p.ldp + col))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 16; ++u)
-                  if (z0 + u < p.splits) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
-              }
-              accs[0] = acc;
+              for (int qq = 0; qq < 4; ++qq) if (qq == r && zz == p.splits - 1) accs[qq] = acc;
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              bool ok;
-              const int row = row_of(i0 + r, ok);
+              bool ok; int rt;
+              const int row = row_of(i0 + r, ok, rt);
               if (ok && r < nb) {
                 const float o[4] = {accs[r].x, accs[r].y, accs[r].z, accs[r].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   if (col + j < p.N) {
-                    float v = p.alpha * o[j];
-                    if (p.beta != 0.f) v += p.beta * ad[r][j];
-                    if (p.bias != nullptr) v += bia[j];
-                    if (p.clip > 0.f) v = fminf(fmaxf(v, -p.clip), p.clip);
-                    if (p.ext.act != 0) v = epi_act(p.ext.act, v);
-                    if (p.ext.dy != nullptr) v = epi_dact(p.ext.dkind, ay[r][j], v);
-                    p.C[(size_t)row * p.ldc + col + j] = v;
-                    if (p.ext.w != nullptr) p.ext.w[(size_t)row * p.ext.ldw + col + j] = aw[r][j] + (-p.ext.lr) * v;
+                    float vv = p.alpha * o[j];
+                    if (p.beta != 0.f) vv += p.beta * ad[r][j];
+                    if (p.bias != nullptr) vv += bia[j];
+                    if (p.clip > 0.f) vv = fminf(fmaxf(vv, -p.clip), p.clip);
+                    if (p.ext.act != 0) vv = epi_act(p.ext.act, vv);
+                    if (p.ext.dy != nullptr) vv = epi_dact(p.ext.dkind, ay[r][j], vv);
+                    p.C[(size_t)row * p.ldc + col + j] = vv;
+                    if (p.ext.w != nullptr) p.ext.w[(size_t)row * p.ext.ldw + col + j] = aw[r][j] + (-p.ext.lr) * vv;
                   }
                 }
               }
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         DBG_T(3);
-        if (et == 0) {                                    // the last reducer of the tile re-arms its counters for the next launch
-          const int done = atomicAdd(p.counters + tiles_mn + tile, 1);
-          if (done == p.splits - 1) { p.counters[tile] = 0; p.counters[tiles_mn + tile] = 0; }
-        }
+        cluster_sync_all();                               // nobody leaves (and frees its shared memory) while a peer still reads its tile
       }
     }
   } else {
@@ -544,6 +528,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  if constexpr (INL) if (p.cluster && (warp < 2 || warp >= 6)) { cluster_sync_all(); cluster_sync_all(); }   // the epilogue warps' two meetings
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -686,6 +671,20 @@ int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, con
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int sm_cap = (t_cta_limit > 0 && t_cta_limit < aslp_num_sms()) ? t_cta_limit : aslp_num_sms();
   const int grid = (int)(items < sm_cap ? items : sm_cap);
+  if (INL && p.cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)items, 1, 1);            // one work item per CTA; blockIdx = tile * splits + z
+    cfg.blockDim = dim3(PASSES == 1 ? 192 : NT3, 1, 1);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)splits; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ASLP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, PASSES, INL>, ta, tb, p));
+    ASLP_COUNT_LAUNCH();
+    return 0;
+  }
   gemm_tf32_kernel<A_MN, B_MN, PASSES, INL><<<grid, PASSES == 1 ? 192 : NT3, SMEM, st>>>(ta, tb, p);
   ASLP_CHECK_LAUNCH();
   return 0;
@@ -816,23 +815,6 @@ int pick_splits_h(int M, int N, int K) {
   return aslp_div_up(num_kb, per);
 }
 
-// per-(device, stream) arrival / completion counters of the in-launch split-K reduction: zeroed once, re-armed by the kernels
-constexpr int GEMM_COUNTERS = 4096;
-struct CounterBuf { int* ptr; };
-std::map<std::pair<int, cudaStream_t>, CounterBuf> g_counters;
-std::mutex g_counters_mu;
-int* gemm_counters(cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_counters_mu);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  CounterBuf& b = g_counters[std::make_pair(dev, st)];
-  if (b.ptr == nullptr) {
-    if (cudaMalloc((void**)&b.ptr, GEMM_COUNTERS * sizeof(int)) != cudaSuccess) { b.ptr = nullptr; return nullptr; }
-    cudaMemsetAsync(b.ptr, 0, GEMM_COUNTERS * sizeof(int), st);
-  }
-  return b.ptr;
-}
-
 }  // namespace
 
 extern "C" {
@@ -852,7 +834,7 @@ size_t aslp_gemm_workspace_bytes(int M, int N, int K) {
 // `ext` != NULL: fold the extended epilogue into the split-K reduce when the product takes that path (*ext_done = true)
 static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
                      const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
-                     void* workspace, size_t workspace_bytes, const EpiExt* ext, bool* ext_done, bool reduce_in_launch) {
+                     void* workspace, size_t workspace_bytes, const EpiExt* ext, bool* ext_done, bool reduce_in_launch, int max_splits) {
   cudaStream_t st = (cudaStream_t)s;
   if (ext_done != nullptr) *ext_done = false;
   ASLP_REQUIRE(M >= 0 && N >= 0 && K >= 0);
@@ -896,7 +878,7 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
     EpiParams pe;
     pe.C = C; pe.ldc = ldc; pe.M = M; pe.N = N; pe.K = K; pe.alpha = alpha; pe.beta = beta; pe.bias = bias; pe.clip = clip;
     pe.partial = nullptr; pe.ldp = 0; pe.kb_per_split = 0; pe.tiles_m = pe.tiles_n = pe.splits = 0;
-    pe.counters = nullptr; pe.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
+    pe.cluster = 0; pe.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
     return gemm_f16x3(st, a_mn, b_mn, pe, A, lda, B, ldb, workspace, workspace_bytes);
   }
   CUtensorMap ta, tb;
@@ -905,6 +887,7 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
   if (!ok) { aslp_set_last_error_msg("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; }
 
   int splits = pick_splits(M, N, K);
+  if (max_splits > 0 && splits > max_splits) splits = max_splits;       // aslp_gemm_ex: the same split count with and without the cluster reduction
   const size_t ldp = ((size_t)N + 3) / 4 * 4;
   if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * ldp * sizeof(float))) splits = 1;   // caller gave no room: single pass
   const int num_kb = aslp_div_up(K, BK);
@@ -913,15 +896,13 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
   p.partial = splits > 1 ? (float*)workspace : nullptr;
   p.ldp = (int)ldp;
   p.kb_per_split = aslp_div_up(num_kb, splits);
-  p.counters = nullptr; p.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
-  // In-launch reduction: only when the caller asked for it (aslp_gemm_ex, reduce_in_launch) and every work item gets a CTA of
-  // its own (items <= SMs, no grid cap), so that all splits of a tile are resident together and may wait for each other.
-  const long long items_ll = (long long)aslp_div_up(M, BM) * aslp_div_up(N, BN) * splits;
-  const bool in_launch = splits > 1 && reduce_in_launch && precision != ASLP_GEMM_TF32 && items_ll <= aslp_num_sms() && (t_cta_limit <= 0 || t_cta_limit >= aslp_num_sms()) &&
-                         2 * aslp_div_up(M, BM) * aslp_div_up(N, BN) <= GEMM_COUNTERS;
+  p.cluster = 0; p.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
+  // In-launch reduction: when the caller asked for it (aslp_gemm_ex, reduce_in_launch) and the splits of a tile fit one
+  // thread-block cluster (portable size: 8).  Clusters are co-scheduled by the hardware, so nothing else about the launch matters.
+  const bool in_launch = splits > 1 && splits <= 8 && reduce_in_launch && precision != ASLP_GEMM_TF32 && (t_cta_limit <= 0 || t_cta_limit >= aslp_num_sms());
   if (in_launch) {
-    p.counters = gemm_counters(st);
-    if (p.counters == nullptr) { aslp_set_last_error_msg("counter allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
+    p.cluster = 1;
+    p.partial = nullptr;
     if (ext != nullptr) p.ext = *ext;
   }
   const bool one_pass = precision == ASLP_GEMM_TF32;      // ASLP_GEMM_3XTF32 below the fp16-split threshold: the in-loop split
@@ -952,7 +933,7 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
 int aslp_gemm(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias, float clip, int precision,
               void* workspace, size_t workspace_bytes) {
-  return gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, nullptr, nullptr, false);
+  return gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, nullptr, nullptr, false, 0);
 }
 
 int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int lda,
@@ -966,7 +947,7 @@ int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
   bool done = false;
   static const bool allow_in_launch = getenv("ASLP_GEMM_REDUCE_IN_LAUNCH") == nullptr || getenv("ASLP_GEMM_REDUCE_IN_LAUNCH")[0] != '0';
   int rc = gemm_impl(s, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, clip, precision, workspace, workspace_bytes, &x, &done,
-                     epi->reduce_in_launch != 0 && allow_in_launch);
+                     epi->reduce_in_launch != 0 && allow_in_launch, 8);
   if (rc != 0 || done) return rc;
   // the product did not go through the split-K reduce (large or odd shapes): the same steps as launches of their own
   if (x.act != 0) { rc = aslp_act_fwd(s, x.act - 1, C, ldc, C, ldc, M, N); if (rc != 0) return rc; }
