@@ -117,12 +117,15 @@ typedef struct {
   int act;
   const float* dact_y; int dact_ldy; int dact_kind;      /* ASLP_ACT_* of the activation whose derivative is applied; y may not alias C */
   float* update_w; int update_ldw; float update_lr;
-  int reduce_in_launch;   /* non-zero: a split-K product may reduce its partial tiles inside the launch (the CTAs of a tile wait for
-                           * each other) instead of in a second pass.  Only for products enqueued where nothing else competes for
-                           * SMs -- all work items must be resident together; the library falls back to the second pass when the
-                           * items do not fit one wave.  Same summation order, bit-identical results.  Measured slower than the second
-                           * pass on B200 (profiles/r02_gemm_in_launch_reduce.txt); the host layer leaves it 0. */
+  int reduce_in_launch;   /* non-zero: a split-K product may reduce its partial tiles inside the launch -- the splits of a tile run as
+                           * a thread-block cluster and add their tiles through distributed shared memory -- instead of in a
+                           * second pass; the library falls back to the second pass when the clusters of the product do not all
+                           * fit the device.  Same summation order, bit-identical results; at par with the second pass on B200
+                           * (profiles/r02_gemm_in_launch_reduce.txt), the host layer leaves it 0. */
 } aslp_gemm_epilogue_t;
+/* diagnostic: clusters of `cluster_size` (2..8) CTAs of the split-K kernel the device runs at once; aslp_gemm_ex only reduces inside
+ * the launch when all the clusters of a product fit */
+int aslp_gemm_cluster_fit(int cluster_size);
 int aslp_gemm_ex(aslp_stream_t s, int trans_a, int trans_b, int M, int N, int K,
                  float alpha, const float* A, int lda, const float* B, int ldb,
                  float beta, float* C, int ldc, const float* bias, float clip,

@@ -208,6 +208,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     kb_end = min(num_kb, kb_begin + p.kb_per_split);
   };
 
+  if (threadIdx.x == 64) {      // descriptor fetch under the barrier / TMEM set-up instead of in front of the first load
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -409,91 +413,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc_idx));
       if (++acc_idx == 2) { acc_idx = 0; acc_ph ^= 1u; }
-      if constexpr (INL) if (p.cluster) {
-        // ---- in-launch reduction over the cluster
-        const int et = threadIdx.x - 64;                  // 0..127 over the four epilogue warps
-        DBG_T(1);
-        cluster_sync_all();                               // every split's tile is in its CTA's shared memory
-        DBG_T(2);
-        const int rp = (BM + p.splits - 1) / p.splits;    // rows of the tile this split reduces
-        const int c4 = (et & 31) << 2;                    // 4 columns per thread, 32 threads span the tile's 128 columns
-        const int col = n0 + c4;
-        if (col < p.N) {
-          // A thread owns the rows (et >> 5) + 4 i of the slice and needs `splits` partials of each (32 loads in all, whatever
-          // the split count) plus the old C / y / W values of the epilogue: a batch of rows has ALL its loads issued (up to
-          // 16 partials and the epilogue operands) before the first add, then the adds in ascending z, then the stores.
-          const int iters = (rp + 3) >> 2;
-          const int nb = p.splits <= 4 ? 4 : 2;                                // rows per batch: nb * splits <= 16
-          const uint32_t tb_local = smem_base + (uint32_t)c4 * 4u;
-          auto row_of = [&](int i, bool& ok, int& rt) {
-            const int rr = (et >> 5) + 4 * i;
-            rt = z * rp + rr;
-            const int row = m0 + rt;
-            ok = i < iters && rr < rp && rt < BM && row < p.M;
-            return row;
-          };
-          float bia[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bia[j] = (p.bias != nullptr && col + j < p.N) ? p.bias[col + j] : 0.f;
-          for (int i0 = 0; i0 < iters; i0 += nb) {
-            float ad[4][4], aw[4][4], ay[4][4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              bool ok; int rt;
-              const int row = row_of(i0 + r, ok, rt);
-              ok = ok && r < nb;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const bool okj = ok && col + j < p.N;
-                ad[r][j] = (okj && p.beta != 0.f) ? p.C[(size_t)row * p.ldc + col + j] : 0.f;
-                ay[r][j] = (okj && p.ext.dy != nullptr) ? p.ext.dy[(size_t)row * p.ext.ldy + col + j] : 0.f;
-                aw[r][j] = (okj && p.ext.w != nullptr) ? p.ext.w[(size_t)row * p.ext.ldw + col + j] : 0.f;
-              }
-            }
-            float4 accs[4];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const int r = u / p.splits, zz = u - r * p.splits;
-              bool ok; int rt;
-              row_of(i0 + r, ok, rt);
-              v[u] = (ok && r < nb) ? ld_dsmem_v4(mapa_u32(tb_local + (uint32_t)rt * (TB_PITCH * 4u), (uint32_t)zz)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const int r = u / p.splits, zz = u - r * p.splits;
-              if (zz == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) if (qq == r && zz == p.splits - 1) accs[qq] = acc;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              bool ok; int rt;
-              const int row = row_of(i0 + r, ok, rt);
-              if (ok && r < nb) {
-                const float o[4] = {accs[r].x, accs[r].y, accs[r].z, accs[r].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (col + j < p.N) {
-                    float vv = p.alpha * o[j];
-                    if (p.beta != 0.f) vv += p.beta * ad[r][j];
-                    if (p.bias != nullptr) vv += bia[j];
-                    if (p.clip > 0.f) vv = fminf(fmaxf(vv, -p.clip), p.clip);
-                    if (p.ext.act != 0) vv = epi_act(p.ext.act, vv);
-                    if (p.ext.dy != nullptr) vv = epi_dact(p.ext.dkind, ay[r][j], vv);
-                    p.C[(size_t)row * p.ldc + col + j] = vv;
-                    if (p.ext.w != nullptr) p.ext.w[(size_t)row * p.ext.ldw + col + j] = aw[r][j] + (-p.ext.lr) * vv;
-                  }
-                }
-              }
-            }
-          }
-        }
-        DBG_T(3);
-        cluster_sync_all();                               // nobody leaves (and frees its shared memory) while a peer still reads its tile
-      }
     }
   } else {
     // ===================== hi/lo splitter (3xTF32) =====================
@@ -528,7 +447,55 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
-  if constexpr (INL) if (p.cluster && (warp < 2 || warp >= 6)) { cluster_sync_all(); cluster_sync_all(); }   // the epilogue warps' two meetings
+  if constexpr (INL) if (p.cluster) {
+    // ---- in-launch reduction over the cluster, by ALL warps of the CTA.  (Left to the four epilogue warps -- one warp per
+    // scheduler, ~2000 dependent instructions each -- this phase took 7-16 us whatever the partials were read from; the work
+    // is instruction latency, not bytes: profiles/r02_gemm_in_launch_reduce.txt.)
+    int z, m0, n0, kb_begin, kb_end;
+    item_coords(blockIdx.x, z, m0, n0, kb_begin, kb_end);
+    DBG_T(1);
+    cluster_sync_all();                                   // every split's raw tile is in its CTA's shared memory
+    DBG_T(2);
+    const int rp = (BM + p.splits - 1) / p.splits;        // CTA z reduces rows [z * rp, (z + 1) * rp) of the tile
+    for (int it = threadIdx.x; it < rp * 32; it += blockDim.x) {
+      const int rr = it >> 5, c4 = (it & 31) << 2;        // a thread: 4 columns of one row, over all splits in ascending z
+      const int rt = z * rp + rr, row = m0 + rt, col = n0 + c4;
+      if (rt >= BM || row >= p.M || col >= p.N) continue;
+      const uint32_t laddr = smem_base + (uint32_t)(rt * TB_PITCH + c4) * 4u;
+      float4 v[8];
+#pragma unroll
+      for (int zz = 0; zz < 8; ++zz) v[zz] = zz < p.splits ? ld_dsmem_v4(mapa_u32(laddr, (uint32_t)zz)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float ad[4], ay[4], aw[4], bia[4];                  // the epilogue's operands, in flight with the partials
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool okj = col + j < p.N;
+        ad[j] = (okj && p.beta != 0.f) ? p.C[(size_t)row * p.ldc + col + j] : 0.f;
+        ay[j] = (okj && p.ext.dy != nullptr) ? p.ext.dy[(size_t)row * p.ext.ldy + col + j] : 0.f;
+        aw[j] = (okj && p.ext.w != nullptr) ? p.ext.w[(size_t)row * p.ext.ldw + col + j] : 0.f;
+        bia[j] = (okj && p.bias != nullptr) ? p.bias[col + j] : 0.f;
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int zz = 0; zz < 8; ++zz)
+        if (zz < p.splits) { acc.x += v[zz].x; acc.y += v[zz].y; acc.z += v[zz].z; acc.w += v[zz].w; }
+      const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col + j < p.N) {
+          float vv = p.alpha * o[j];
+          if (p.beta != 0.f) vv += p.beta * ad[j];
+          if (p.bias != nullptr) vv += bia[j];
+          if (p.clip > 0.f) vv = fminf(fmaxf(vv, -p.clip), p.clip);
+          if (p.ext.act != 0) vv = epi_act(p.ext.act, vv);
+          if (p.ext.dy != nullptr) vv = epi_dact(p.ext.dkind, ay[j], vv);
+          p.C[(size_t)row * p.ldc + col + j] = vv;
+          if (p.ext.w != nullptr) p.ext.w[(size_t)row * p.ext.ldw + col + j] = aw[j] + (-p.ext.lr) * vv;
+        }
+      }
+    }
+    DBG_T(3);
+    cluster_sync_all();                                   // nobody leaves (and frees its shared memory) while a peer still reads its tile
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -815,9 +782,32 @@ int pick_splits_h(int M, int N, int K) {
   return aslp_div_up(num_kb, per);
 }
 
+// How many clusters of `cs` CTAs of the 3-pass kernel the device runs at once (each CTA owns a whole SM's shared memory and a
+// cluster must sit inside one GPC: 16 clusters of 8 do NOT fit a B200, and a second wave doubles the launch).  Queried once.
+int cluster_fit(int cs) {
+  static int fit[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  if (cs < 2 || cs > 8) return 0;
+  if (fit[cs] >= 0) return fit[cs];
+  constexpr int SMEM3 = 3 * 4 * TILE_BYTES + 1024 + BAR_REGION + STG_BYTES;
+  auto kern = gemm_tf32_kernel<false, false, 3, true>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3) != cudaSuccess) { cudaGetLastError(); return fit[cs] = 0; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(cs * aslp_num_sms()), 1, 1);
+  cfg.blockDim = dim3(NT3, 1, 1);
+  cfg.dynamicSmemBytes = SMEM3;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return fit[cs] = n;
+}
+
 }  // namespace
 
 extern "C" {
+int aslp_gemm_cluster_fit(int cluster_size) { return cluster_fit(cluster_size); }
 #ifdef ASLP_GEMM_DEBUG_TIMES
 int aslp_gemm_debug_times(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_dbg_t, sizeof(unsigned long long) * 148 * 8); }
 #endif
@@ -887,7 +877,15 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
   if (!ok) { aslp_set_last_error_msg("cuTensorMapEncodeTiled failed", __FILE__, __LINE__); return ASLP_STATUS_EXECUTION_FAILED; }
 
   int splits = pick_splits(M, N, K);
-  if (max_splits > 0 && splits > max_splits) splits = max_splits;       // aslp_gemm_ex: the same split count with and without the cluster reduction
+  // aslp_gemm_ex (max_splits > 0): the split count is one whose clusters all run at once -- tiles <= cluster_fit(splits) -- whether
+  // or not this call reduces inside the launch, so that the two forms add the same partial sums in the same order
+  bool cluster_ok = false;
+  if (max_splits > 0 && splits > 1 && precision != ASLP_GEMM_TF32) {
+    const int tiles = aslp_div_up(M, BM) * aslp_div_up(N, BN);
+    int cs = splits < max_splits ? splits : max_splits;
+    while (cs > 1 && tiles > cluster_fit(cs)) --cs;
+    if (cs > 1) { splits = cs; cluster_ok = true; }
+  }
   const size_t ldp = ((size_t)N + 3) / 4 * 4;
   if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * ldp * sizeof(float))) splits = 1;   // caller gave no room: single pass
   const int num_kb = aslp_div_up(K, BK);
@@ -899,7 +897,7 @@ static int gemm_impl(aslp_stream_t s, int trans_a, int trans_b, int M, int N, in
   p.cluster = 0; p.ext = EpiExt{0, nullptr, 0, 0, nullptr, 0, 0.f};
   // In-launch reduction: when the caller asked for it (aslp_gemm_ex, reduce_in_launch) and the splits of a tile fit one
   // thread-block cluster (portable size: 8).  Clusters are co-scheduled by the hardware, so nothing else about the launch matters.
-  const bool in_launch = splits > 1 && splits <= 8 && reduce_in_launch && precision != ASLP_GEMM_TF32 && (t_cta_limit <= 0 || t_cta_limit >= aslp_num_sms());
+  const bool in_launch = cluster_ok && reduce_in_launch && (t_cta_limit <= 0 || t_cta_limit >= aslp_num_sms());
   if (in_launch) {
     p.cluster = 1;
     p.partial = nullptr;

@@ -152,6 +152,12 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     kb_end = min(num_kb, kb_begin + p.kb_per_split);
   };
 
+  if (threadIdx.x == 64) {      // descriptor fetch under the barrier / TMEM set-up instead of in front of the first load
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmAh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmAl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmBh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < HSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 128); }

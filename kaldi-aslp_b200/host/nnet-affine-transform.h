@@ -129,11 +129,9 @@ class AffineTransform : public UpdatableComponent {
     ASLP_OK(aslp_gemm_ex(CuStream(), 0, 0, out_diff.NumRows(), input_dim_, output_dim_, 1.0f, out_diff.Data(), out_diff.Stride(), linearity_.Data(),
                          linearity_.Stride(), 0.0f, act_in_diff->Data(), act_in_diff->Stride(), nullptr, 0.0f, GemmPrecision(), wsb ? CuWorkspace(wsb) : nullptr, wsb, &epi));
   }
-  // The split-K reduction inside the launch makes the CTAs of a tile wait for each other, so all work items of the product must
-  // become resident without depending on another waiting product: products of the process-wide compute stream are serialised
-  // among themselves and qualify; anything on the side stream or on a helper thread's stream (which may run beside them) does not.
-  // OFF unless ASLP_GEMM_REDUCE_IN_LAUNCH=1: measured slower than the separate reduce pass (cfg1 0.40 vs 0.28 ms per
-  // minibatch, cfg4 1.39 vs 0.97 ms; profiles/r02_gemm_in_launch_reduce.txt).
+  // Split-K reduced inside the launch (the splits of a tile as a thread-block cluster, aslp_gemm_epilogue_t::reduce_in_launch).
+  // OFF unless ASLP_GEMM_REDUCE_IN_LAUNCH=1: at par with the separate reduce pass (cfg1 0.276 ms either way, cfg4 0.956 vs
+  // 0.976 ms per minibatch; profiles/r02_gemm_in_launch_reduce.txt).
   static int ReduceInLaunch() {
     static const bool on = getenv("ASLP_GEMM_REDUCE_IN_LAUNCH") != nullptr && getenv("ASLP_GEMM_REDUCE_IN_LAUNCH")[0] == '1';
     return on && CuOnComputeStream() ? 1 : 0;

@@ -9,6 +9,7 @@ class Epi(ctypes.Structure):
     _fields_ = [("act", ctypes.c_int), ("dact_y", ctypes.c_void_p), ("dact_ldy", ctypes.c_int), ("dact_kind", ctypes.c_int),
                 ("update_w", ctypes.c_void_p), ("update_ldw", ctypes.c_int), ("update_lr", ctypes.c_float), ("reduce_in_launch", ctypes.c_int)]
 f = ctypes.c_float
+print("clusters that fit at once, by size:", {cs: L.aslp_gemm_cluster_fit(cs) for cs in range(2, 9)})
 for (M, N, K, ta, tb) in [(256, 1024, 1024, 0, 1), (1024, 1024, 256, 1, 0)]:
     A = torch.randn((K, M) if ta else (M, K), device="cuda") * 0.1
     B = torch.randn((N, K) if tb else (K, N), device="cuda") * 0.1
