@@ -17,7 +17,15 @@ run() {
   echo "exit code $? (99 = the sanitizer reported errors, 137 = timed out)" >> $OUT
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Error:|Race reported|Invalid|hazard" gpurun_out/san_$name.log | sort | uniq -c | head -20 >> $OUT
 }
-if [ "$1" == "all" ]; then          # whole test files (about ten minutes)
+if [ "$1" == "late" ]; then         # kernels added after the "all" pass of the round: conv / pool row kernels, cluster split-K reduce
+  OUT=gpurun_out/sanitizer_late.txt
+  echo "# compute-sanitizer $(compute-sanitizer --version | head -2 | tail -1) on $(nvidia-smi --query-gpu=name --format=csv,noheader | head -1)" > $OUT
+  run memcheck mem_gemm_late tests/test_gpu_gemm.py "not full_size"
+  run memcheck mem_pointwise_late tests/test_gpu_pointwise.py "conv or maxpool"
+  run racecheck race_pointwise_late tests/test_gpu_pointwise.py "conv or maxpool"
+  run racecheck race_gemm_ex_late tests/test_gpu_gemm.py "test_gemm_ex_epilogue_matches_the_separate_steps and (256-1024-1024-0-1 or 1024-440-256 or 24-36-20)"
+  run memcheck mem_workers_late tests/test_gpu_workers.py "single_rank"
+elif [ "$1" == "all" ]; then          # whole test files (about ten minutes)
   ALL='not full_size and not many_utts'
   run memcheck mem_lstm_all tests/test_gpu_lstm.py "$ALL"
   run memcheck mem_ctc_all tests/test_gpu_ctc.py "$ALL"
