@@ -494,7 +494,9 @@ def main():
         nparams = net.num_params
         sync_info = {"ms_per_sync": float(t.item()), "params": int(nparams),
                      "bus_GBps": 2.0 * (world - 1) / world * 4.0 * nparams / (float(t.item()) * 1e-3) / 1e9,
-                     "what": "pack + ONE ncclAllReduce(sum) of the fp32 arena + BMUF filter apply; bus bytes = 2(N-1)/N * 4P (SURVEY 8d)"}
+                     "what": "the exchange ALONE and blocking (in the timed loop it rides under Backpropagate, layer by layer): per component "
+                             "pack + ncclAllReduce(sum) of its slice of the fp32 arena + BMUF filter apply, 4 latency-bound collectives; "
+                             "bus bytes = 2(N-1)/N * 4P (SURVEY 8d)"}
     sync_check, bsp_line = None, None
     if worker is not None:
         sync_check, bsp_line = multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, host_lib, worker)
