@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(PASSES == 1 ? 192 : NT3, 1)   // the default k
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p) {
   constexpr int STAGES = (PASSES == 1) ? 6 : 3;
   constexpr int STAGE_BYTES = (PASSES == 1) ? 2 * TILE_BYTES : 4 * TILE_BYTES;
+  DBG_T(5);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B wants 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));

@@ -35,5 +35,6 @@ for (M, N, K, ta, tb) in [(256, 1024, 1024, 0, 1), (1024, 1024, 256, 1, 0)]:
             t = np.array(buf[:], dtype=np.int64).reshape(148, 8)
             t = t[t[:, 0] > 0]
             base = t[:, 0].min()
+            print(" kernel entry -> set-up done (barriers, TMEM, block sync), ns, median / max:", np.median(t[:, 0] - t[:, 5]), (t[:, 0] - t[:, 5]).max())
             d = t[:, [0, 4, 1, 2, 3]] - base
             print(" ctas", len(t), "start/tmem_full/partial_done/spin_done/reduce_done ns: median", np.median(d, 0), "max", d.max(0), "min", d.min(0))
