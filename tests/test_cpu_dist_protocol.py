@@ -34,6 +34,68 @@ def all_finished(frames):
     return int(t.item()) == 0, int(t.item())
 
 
+SEGMENTS = [(0, 2), (2, 4)]                  # tensors of "component" 0 and 1 (IWorker::InitParam(nnet) remembers these runs)
+
+
+def seg_slices():
+    sizes = [int(np.prod(s)) for s in SHAPES]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    return [slice(int(offs[a]), int(offs[b])) for a, b in SEGMENTS]
+
+
+def bmuf_apply(w, w_prev, delta_prev, g, sl):
+    delta = np.float32(0.5) * delta_prev[sl] + np.float32(0.5) * np.float32(1.0) * g
+    w[sl] = (w_prev[sl] + delta).astype(np.float32)
+    w_prev[sl] = w[sl]
+    delta_prev[sl] = delta.astype(np.float32)
+
+
+def worker_pipelined(rank, world, port, out):
+    """The exchange pipelined by component (IWorker::BeginSynchronize / EndSynchronize, host/parallel.cc): a rank with data sends
+    its frame count first WITHOUT waiting for it, then each component's slice right behind that component's update, top
+    component first, and waits for everything at the end; a rank that is out of data answers with the blocking form, cut into
+    the same slices in the same order.  The collectives of the two forms must pair up and give the blocking result."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = pack(make_params(0, 0))
+        w_prev, delta_prev = w.copy(), np.zeros_like(w)
+        trace, step = [], 0
+        my = PERIODS[rank]
+        sls = seg_slices()
+        while True:
+            frames = my[step] if step < len(my) else 0
+            if frames > 0:
+                cnt = torch.tensor([frames], dtype=torch.int64)
+                h_cnt = dist.all_reduce(cnt, async_op=True)            # BeginSynchronize: nobody waits for the count yet
+                upd = 0.01 * pack(make_params(rank + 1, step + 1))
+                pending = []
+                for sl in reversed(sls):                                # Backpropagate: top component's Update first ...
+                    w[sl] = w[sl] + upd[sl]
+                    arena = torch.from_numpy((w[sl] - w_prev[sl]).astype(np.float32))
+                    pending.append((sl, arena, dist.all_reduce(arena, async_op=True)))   # ... its exchange right behind it
+                h_cnt.wait()                                            # EndSynchronize
+                total = int(cnt.item())
+                assert total > 0
+                for sl, arena, h in pending:
+                    h.wait()
+                    bmuf_apply(w, w_prev, delta_prev, arena.numpy(), sl)
+            else:
+                done, total = all_finished(0)                           # Synchronize(0), blocking, cut the same way
+                if done:
+                    break
+                for sl in reversed(sls):
+                    arena = torch.from_numpy((w[sl] - w_prev[sl]).astype(np.float32))
+                    dist.all_reduce(arena)
+                    bmuf_apply(w, w_prev, delta_prev, arena.numpy(), sl)
+            trace.append((frames, total, w.copy()))
+            step += 1
+        out[rank] = trace
+    finally:
+        dist.destroy_process_group()
+
+
 def worker(rank, world, port, kind, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -123,4 +185,26 @@ def test_two_rank_sync_matches_replica_simulation(kind):
             np.testing.assert_allclose(w, w_want, rtol=1e-6, atol=1e-7)
     # replicas are bit-identical to each other after a sync (same allreduce result, same filter)
     for step in range(len(want)):
+        assert np.array_equal(got[0][step][2], got[1][step][2])
+
+
+def test_two_rank_pipelined_exchange_pairs_with_the_blocking_form():
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        port = free_port()
+        procs = [ctx.Process(target=worker_pipelined, args=(r, 2, port, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0, p.exitcode
+        got = {r: list(out[r]) for r in range(2)}
+    want = simulate("bmuf")
+    assert len(got[0]) == len(got[1]) == len(want) == 3
+    for step, (frames, w_want) in enumerate(want):
+        for r in range(2):
+            f, total, w = got[r][step]
+            assert f == frames[r] and total == sum(frames)
+            np.testing.assert_allclose(w, w_want, rtol=1e-6, atol=1e-7)
         assert np.array_equal(got[0][step][2], got[1][step][2])
