@@ -444,9 +444,11 @@ def sod_optimize(opt, w, g, s1, s2, lr, p1, p2, step, floor=1e-8):
     return w.astype(F), s1.astype(F), s2.astype(F)
 
 
-# ---------------------------------------------------------------- Eesen CTC on probabilities (PARITY UNPINNED: the
-# reference implementation is GPU-only and has no tests; this follows the kernel sources line by line and the GPU tests
-# additionally cross-check it against warp-ctc, whose CPU path is pinned by its own known-answer tests)
+# ---------------------------------------------------------------- Eesen CTC on probabilities.  The reference implementation
+# is GPU-only and has no tests; this follows the kernel sources line by line.  PINNED on the GPU box: tests/test_gpu_ctc_eesen.py
+# runs the reference's own kernels (cu-kernels.cu compiled for sm_100a into oracle/_ref/libref_cukernels.so) and compares this
+# restatement -- and aslp_ctc_eesen -- with them; it is also cross-checked against warp-ctc, whose CPU path is pinned by its own
+# known-answer tests.
 _LZ, _LINF, _EXPLIM, _FMAX = F(-1e30), F(1e30), F(88.722839), F(3.4028235e38)
 
 

@@ -1,0 +1,25 @@
+/* Test infrastructure (oracle/): a stand-in for <mpi.h> that lets the reference's OWN worker classes
+ * (src/aslp-parallel/{bsp,bmuf,sod}-worker.cc over mpi-node.h) run N ranks as N threads of one process, so that their results can
+ * pin the restated formulas (oracle/aslp_oracle.py) without an MPI installation.  Only what mpi-node.h:18-101 touches is declared;
+ * the definitions live in oracle/ref_worker_driver.cc.  MPI_Allreduce adds the ranks' buffers in rank order, in the element type. */
+#ifndef ASLP_ORACLE_STUB_MPI_H_
+#define ASLP_ORACLE_STUB_MPI_H_
+typedef int MPI_Comm;
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+#define MPI_COMM_WORLD 0
+#define MPI_IN_PLACE ((void*)1)
+#define MPI_SUM 0
+#define MPI_CHAR 1
+#define MPI_INT 2
+#define MPI_FLOAT 3
+#define MPI_DOUBLE 4
+#define MPI_UNSIGNED 5
+#define MPI_LONG_LONG_INT 6
+int MPI_Init(int* argc, char*** argv);
+int MPI_Finalize();
+int MPI_Comm_rank(MPI_Comm comm, int* rank);
+int MPI_Comm_size(MPI_Comm comm, int* size);
+int MPI_Barrier(MPI_Comm comm);
+int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
+#endif

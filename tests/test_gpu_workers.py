@@ -1,6 +1,7 @@
 """IWorker parity (BSP / BMUF / SOD over NCCL, kaldi-aslp_b200/host/parallel.cc) against the N-replica restatement of
-src/aslp-parallel/{bsp,bmuf,sod}-worker.cc in oracle/aslp_oracle.py (the reference has no tests for these and needs MPI:
-"parity unpinned" beyond that restatement).  One rank on any GPU box; two ranks when the box has two GPUs."""
+src/aslp-parallel/{bsp,bmuf,sod}-worker.cc in oracle/aslp_oracle.py (the reference has no tests for these and needs MPI; the
+restatement itself is pinned against the reference's own worker classes run over a stand-in for mpi.h,
+tests/test_cpu_oracle_pinning.py::test_worker_restatements_match_the_reference_workers).  One rank on any GPU box; two ranks when the box has two GPUs."""
 import os
 import tempfile
 import time
