@@ -453,8 +453,9 @@ _LZ, _LINF, _EXPLIM, _FMAX = F(-1e30), F(1e30), F(88.722839), F(3.4028235e38)
 
 
 # ---------------------------------------------------------------- async parameter-server modes (aslp-parallel)
-# UNPINNED like the synchronous workers: the reference has no tests for them and needs MPI.  One call = what the server and
-# the worker do for ONE kMsgSynchronize, in the order the server receives the messages.
+# The reference has no tests for them and needs MPI; pinned, like the synchronous workers, against the reference's own server and
+# worker classes run over oracle/stub/mpi.h (tests/test_cpu_oracle_pinning.py::test_async_restatements_match_the_reference_servers).
+# One call = what the server and the worker do for ONE kMsgSynchronize, in the order the server receives the messages.
 
 def easgd_exchange(w_worker, w_server, alpha):
     """easgd-worker.cc:58-62 and easgd-server.cc:78-83: both sides move towards the OTHER side's pre-update model."""

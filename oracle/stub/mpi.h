@@ -22,4 +22,14 @@ int MPI_Comm_rank(MPI_Comm comm, int* rank);
 int MPI_Comm_size(MPI_Comm comm, int* size);
 int MPI_Barrier(MPI_Comm comm);
 int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
+/* point to point, for the parameter-server modes ({easgd,asgd,masgd}-{server,worker}.cc): buffered sends into a per-rank
+ * mailbox; a receive takes the first queued message that matches (source or MPI_ANY_SOURCE, tag or MPI_ANY_TAG), so messages
+ * of one source are matched in the order they were sent, as MPI guarantees */
+#define MPI_ANY_SOURCE (-1)
+#define MPI_ANY_TAG (-1)
+typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR; } MPI_Status;
+int MPI_Send(const void* buf, int count, MPI_Datatype type, int dest, int tag, MPI_Comm comm);
+int MPI_Recv(void* buf, int count, MPI_Datatype type, int source, int tag, MPI_Comm comm, MPI_Status* status);
+int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, int dest, int sendtag, void* recvbuf, int recvcount,
+                 MPI_Datatype recvtype, int source, int recvtag, MPI_Comm comm, MPI_Status* status);
 #endif

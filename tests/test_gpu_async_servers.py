@@ -1,7 +1,8 @@
 """Async parameter-server modes (EASGD / ASGD / MASGD, kaldi-aslp_b200/host/parallel-async.cc) over NCCL send / recv: rank 0
 serves, rank 1 trains.  With one worker the arrival order is fixed, so the run replays exactly against the restated formulas
-of oracle/aslp_oracle.py (easgd-*.cc, asgd-*.cc, masgd-server.cc; the reference has no tests for these and needs MPI:
-"parity unpinned" beyond the restatement).  Needs two GPUs (NCCL does not put two ranks on one device)."""
+of oracle/aslp_oracle.py (easgd-*.cc, asgd-*.cc, masgd-server.cc; the reference has no tests for these and needs MPI -- the
+restatement itself is pinned against the reference's own server and worker classes run over a stand-in for mpi.h,
+tests/test_cpu_oracle_pinning.py::test_async_restatements_match_the_reference_servers).  Needs two GPUs (NCCL does not put two ranks on one device)."""
 import os
 import tempfile
 import time
