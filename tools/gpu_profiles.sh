@@ -18,6 +18,10 @@ python tools/ncu_summary.py gpurun_out/prof_ctc4.ncu-rep > gpurun_out/ctc_four_l
 python tools/ncu_summary.py gpurun_out/prof_ctc.ncu-rep > gpurun_out/ctc_ncu_summary.txt; rm -f gpurun_out/prof_ctc.ncu-rep
 timeout -s KILL 600 ncu --set full --clock-control none -k regex:'act_|softmax_reg|xent_reg|bn_|splice|fsmn|axpby|col_reduce' -c 60 -f -o gpurun_out/prof_hbm python tools/kernel_bench.py --once "" > gpurun_out/t_ncu_hbm.log 2>&1
 python tools/ncu_summary.py gpurun_out/prof_hbm.ncu-rep > gpurun_out/hbm_ncu_summary.txt; rm -f gpurun_out/prof_hbm.ncu-rep
+# the CNN front end's kernels (rewritten late in round 2): their own ncu summary
+timeout -s KILL 600 ncu --set full --clock-control none -k regex:'conv_|maxpool_' -c 8 -f -o gpurun_out/prof_conv python tools/kernel_bench.py --once conv > gpurun_out/t_ncu_conv.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none -k regex:'conv_|maxpool_' -c 8 -f -o gpurun_out/prof_pool python tools/kernel_bench.py --once maxpool > gpurun_out/t_ncu_pool.log 2>&1
+(python tools/ncu_summary.py gpurun_out/prof_conv.ncu-rep; python tools/ncu_summary.py gpurun_out/prof_pool.ncu-rep) > gpurun_out/conv_pool_ncu_summary.txt; rm -f gpurun_out/prof_conv.ncu-rep gpurun_out/prof_pool.ncu-rep
 # launch lists of one minibatch of the launch-bound configurations (enqueued, not replayed, so that every kernel is listed)
 ASLP_STEP_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 3000 --csv --log-file gpurun_out/launches_cfg1.csv python tools/config_bench.py cfg1 > gpurun_out/t_ncu_cfg1.log 2>&1
 ASLP_STEP_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 5000 --csv --log-file gpurun_out/launches_cfg4.csv python tools/config_bench.py cfg4 > gpurun_out/t_ncu_cfg4.log 2>&1
