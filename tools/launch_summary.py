@@ -4,7 +4,7 @@ import collections
 import csv
 import sys
 
-fn, nsteps = sys.argv[1], int(sys.argv[2])
+fn, nsteps = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 4
 lines = [l for l in open(fn) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 n = len(rows) // nsteps
