@@ -9,11 +9,13 @@ lines = [l for l in open(fn) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 n = len(rows) // nsteps
 # the training steps are identical: their period is the spacing of a kernel that runs once per step (the CTC label CSR
-# build); the last step is the last `period` launches of the run (profiling runs use --no-secondary, nothing follows it)
-marks = [i for i, x in enumerate(rows) if "ctc_csr_kernel" in x["Kernel Name"]]
+# build, or the one-launch CTC kernel); the summary covers the last whole period of the run (profiling runs use --no-secondary, nothing follows it)
+marks = [i for i, x in enumerate(rows) if "ctc_csr_kernel" in x["Kernel Name"] or "ctc_fused_kernel" in x["Kernel Name"]]
 if len(marks) >= 2:
     n = marks[-1] - marks[-2]
-last = rows[-n:]
+    last = rows[marks[-2] + 1:marks[-1] + 1]           # one whole period: from behind one CTC launch up to and including the next
+else:
+    last = rows[-n:]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for x in last:
     k = x["Kernel Name"]
