@@ -327,13 +327,18 @@ def multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, h
     res["replicas_bit_identical"] = bool(res["replicas_bit_identical_after_bmuf"] and res["replicas_bit_identical_after_bsp"] and res["replicas_bit_identical_after_bmuf_rounds"] and
                                          res["replicas_bit_identical_after_pipelined_bmuf"])
     # ---- BSP after EVERY minibatch, timed like the main loop
+    def bsp_step():
+        if args.blocking_sync:
+            step_plain(); bsp.synchronize(S * T)
+        else:                                              # the exchange rides under Backpropagate, layer by layer
+            bsp.begin_synchronize(S * T); step_plain(); bsp.end_synchronize()
     NN.device_sync(); dist.barrier()
     for _ in range(2):
-        step_plain(); bsp.synchronize(S * T)
+        bsp_step()
     NN.device_sync(); dist.barrier()
     host_lib().aslp_nnet_event_record(0)
     for _ in range(args.steps):
-        step_plain(); bsp.synchronize(S * T)
+        bsp_step()
     host_lib().aslp_nnet_event_record(1)
     ms = ctypes.c_float(0)
     assert host_lib().aslp_nnet_event_elapsed_ms(0, 1, ctypes.byref(ms)) == 0
@@ -341,7 +346,8 @@ def multi_gpu_checks(NN, net, ctc, world, rank, dist, torch, step_plain, args, h
     t = torch.tensor([ms.value], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     bsp_line = {"ms_per_step": float(t.item()) / args.steps, "frames_per_s": S * T * args.steps * world / (float(t.item()) * 1e-3),
-                "what": "BspWorker::Synchronize after every minibatch (one ncclAllReduce of the 26 MB arena per 16000 frames per rank)"}
+                "what": "BSP after every minibatch (the 26 MB model exchanged per 16000 frames per rank), " +
+                        ("BspWorker::Synchronize blocking after the minibatch" if args.blocking_sync else "the exchange pipelined by layer under Backpropagate")}
     return res, bsp_line
 
 

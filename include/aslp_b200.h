@@ -346,6 +346,9 @@ int aslp_sync_sod_apply(aslp_stream_t s, int opt, float* w, const float* g, floa
  * counts including row padding); `table_dev` is a DEVICE array of {ptr, offset into the packed arena, n}.  One launch each. */
 typedef struct { float* ptr; size_t offset; size_t n; } aslp_tensor_ref_t;
 int aslp_sync_pack(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, float factor);           /* arena = w * factor (BSP) */
+/* arena = w * (float(frames) / float(*frames_all_dev)): the BSP weight of bsp-worker.cc:44 with the job's frame total still on the
+ * device (behind its all-reduce on the same stream), so that a pipelined exchange needs no host round trip for it */
+int aslp_sync_pack_weighted(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, int frames, const int* frames_all_dev);
 int aslp_sync_pack_diff(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, const float* w_prev_arena, float sign);  /* arena = sign*(w - w_prev) */
 int aslp_sync_unpack(aslp_stream_t s, const float* arena, const aslp_tensor_ref_t* table_dev, int ntensors);                 /* w = arena */
 int aslp_sync_bmuf_apply_packed(aslp_stream_t s, const aslp_tensor_ref_t* table_dev, int ntensors, float* w_prev_arena, float* delta_prev_arena,

@@ -104,7 +104,7 @@ int aslp_worker_synchronize(aslp_worker_t w, int num_frames, int* keep_going);  
  * aslp_worker_init_param_by_component on EVERY rank (synchronize then exchanges component by component, top layer first); a
  * trainer that knows a synchronisation is due after the coming minibatch calls begin_synchronize(frames) before the minibatch
  * and end_synchronize after it instead of synchronize(frames): each component's tensors are exchanged on the worker's own stream as
- * soon as its Update is enqueued, while the layers below still back-propagate.  bmuf and sod only (can_overlap). */
+ * soon as its Update is enqueued, while the layers below still back-propagate.  bsp, bmuf and sod (can_overlap). */
 int aslp_worker_init_param_by_component(aslp_worker_t w, aslp_nnet_t n);
 int aslp_worker_can_overlap(aslp_worker_t w, int* yes);
 int aslp_worker_begin_synchronize(aslp_worker_t w, int num_frames);

@@ -56,7 +56,7 @@ int CtcStreamsMain(int argc, char* argv[], const char* usage) {
     int32 sync_period = 25600;
     po.Register("sync-period", &sync_period, "number of frames for one sync with other workers");
     bool pipeline_sync = true;
-    po.Register("pipeline-sync", &pipeline_sync, "bmuf | sod: exchange each layer's tensors behind its Update, under the backward pass "
+    po.Register("pipeline-sync", &pipeline_sync, "bsp | bmuf | sod: exchange each layer's tensors behind its Update, under the backward pass "
                 "(same result as the blocking exchange after the minibatch; every rank must use the same setting)");
     float bmuf_momentum = 0.9f, bmuf_learn_rate = 1.0f;
     po.Register("bmuf-momentum", &bmuf_momentum, "bmuf block momentum");

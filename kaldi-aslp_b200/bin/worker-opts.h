@@ -27,7 +27,7 @@ inline void FinishWorker(IWorker* worker, aslp_nnet::Nnet* nnet) {
 }
 
 // The per-minibatch frame counter with its synchronisation (frame-worker.cc:150-156), in two forms: the reference's -- count,
-// then Synchronize once the period is exceeded -- and, for workers that can (IWorker::CanOverlap: bmuf, sod) and were
+// then Synchronize once the period is exceeded -- and, for workers that can (IWorker::CanOverlap: bsp, bmuf, sod) and were
 // registered with InitParam(nnet), the exchange pipelined by layer: the trainer says BEFORE Backpropagate how many frames the
 // minibatch has, a synchronisation that this minibatch makes due is begun there and rides under the backward pass.
 // Same moments of synchronisation, same arithmetic, same model afterwards.
@@ -85,7 +85,7 @@ struct WorkerOptions {
     po->Register("sync-period", &sync_period, "number frames for every synchronization");
     po->Register("bmuf-momentum", &bmuf_momentum, "bmuf block momentum");
     po->Register("bmuf-learn-rate", &bmuf_learn_rate, "bmuf block learning rate");
-    po->Register("pipeline-sync", &pipeline_sync, "bmuf | sod: exchange each layer's tensors behind its Update, under the backward pass "
+    po->Register("pipeline-sync", &pipeline_sync, "bsp | bmuf | sod: exchange each layer's tensors behind its Update, under the backward pass "
                  "(same result as the blocking exchange after the minibatch; every rank must use the same setting)");
     optimizer_opts.Register(po);
   }

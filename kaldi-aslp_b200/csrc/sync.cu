@@ -64,7 +64,7 @@ __global__ void sod_kernel(int opt, float* w, const float* g, float* s1, float* 
 // ---- multi-tensor forms: the model's parameter tensors stay where the components own them (GetGpuParams views);
 // a device table {ptr, arena offset, n} lets ONE launch gather / scatter all of them against a packed arena.
 // blockIdx.y = tensor, blockIdx.x strides over its elements.
-enum { MT_PACK_SCALE = 0, MT_PACK_DIFF = 1, MT_UNPACK = 2, MT_BMUF = 3, MT_SOD = 4 };
+enum { MT_PACK_SCALE = 0, MT_PACK_DIFF = 1, MT_UNPACK = 2, MT_BMUF = 3, MT_SOD = 4, MT_PACK_WEIGHTED = 5 };
 struct MtArgs {
   const aslp_tensor_ref_t* table;
   float* arena;            // PACK_*: destination; UNPACK: source; BMUF/SOD: the all-reduced g
@@ -72,13 +72,17 @@ struct MtArgs {
   float* s1; float* s2;    // BMUF: s1 = delta_prev ; SOD: optimizer states
   float a, b, p1, p2, eps; // PACK_SCALE: a = factor; PACK_DIFF: a = sign; BMUF: a = momentum, b = learn rate; SOD: a = lr
   int opt, step;
+  const int* count;        // PACK_WEIGHTED: the job's frame total, on the device (a = this rank's frames)
 };
 template <int MODE>
 __global__ void multi_tensor_kernel(MtArgs A) {
   const aslp_tensor_ref_t t = A.table[blockIdx.y];
+  // bsp-worker.cc:44: float factor = float(num_worker_samples) / num_all_samples -- the same fp32 division, taken on the device
+  const float weight = MODE == MT_PACK_WEIGHTED ? A.a / (float)(*A.count) : 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < t.n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t j = t.offset + i;
     if (MODE == MT_PACK_SCALE) A.arena[j] = t.ptr[i] * A.a;
+    else if (MODE == MT_PACK_WEIGHTED) A.arena[j] = t.ptr[i] * weight;
     else if (MODE == MT_PACK_DIFF) A.arena[j] = A.a * (t.ptr[i] - A.w_prev[j]);
     else if (MODE == MT_UNPACK) t.ptr[i] = A.arena[j];
     else if (MODE == MT_BMUF) {
@@ -165,6 +169,11 @@ int aslp_sync_sod_apply(aslp_stream_t s, int opt, float* w, const float* g, floa
 int aslp_sync_pack(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, float factor) {
   MtArgs A = {}; A.table = table_dev; A.arena = arena; A.a = factor;
   return launch_mt<MT_PACK_SCALE>(s, A, ntensors);
+}
+int aslp_sync_pack_weighted(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, int frames, const int* frames_all_dev) {
+  ASLP_REQUIRE(frames_all_dev != nullptr && frames >= 0);
+  MtArgs A = {}; A.table = table_dev; A.arena = arena; A.a = (float)frames; A.count = frames_all_dev;
+  return launch_mt<MT_PACK_WEIGHTED>(s, A, ntensors);
 }
 int aslp_sync_pack_diff(aslp_stream_t s, float* arena, const aslp_tensor_ref_t* table_dev, int ntensors, const float* w_prev_arena, float sign) {
   MtArgs A = {}; A.table = table_dev; A.arena = arena; A.w_prev = const_cast<float*>(w_prev_arena); A.a = sign;

@@ -49,7 +49,7 @@ void NcclNode::ReduceAccStat(const std::vector<double*>& acc_params, const std::
 
 void IWorker::Reset() {
   table_dev_ = nullptr; ntensors_ = 0; total_ = 0; nnet_ = nullptr; comm_stream_ = nullptr;
-  ev_compute_ = ev_side_ = ev_done_ = ev_count_ = nullptr; count_host_ = nullptr; count_dev_ = nullptr; armed_ = false;
+  ev_compute_ = ev_side_ = ev_done_ = ev_count_ = nullptr; count_host_ = nullptr; count_dev_ = nullptr; armed_ = false; begin_samples_ = 0;
 }
 IWorker::~IWorker() {
   if (armed_ && nnet_ != nullptr) nnet_->SetUpdateObserver(nullptr);
@@ -140,6 +140,7 @@ void IWorker::BeginSynchronize(int num_worker_samples) {
   ASLP_OK(aslp_event_record(comm_stream_, &ev_count_));
   exchanged_.assign(segments_.size(), 0);
   armed_ = true;
+  begin_samples_ = num_worker_samples;
   nnet_->SetUpdateObserver([this](int component) { OnComponentUpdated(component); });
 }
 
@@ -162,7 +163,6 @@ void IWorker::OnComponentUpdated(int component) {
 bool IWorker::EndSynchronize() {
   KALDI_ASSERT(armed_);
   nnet_->SetUpdateObserver(nullptr);
-  armed_ = false;
   // components whose Update was not reported (a net driven without Nnet::Backpropagate): exchange them now, in order
   for (size_t i = segments_.size(); i-- > 0;) {
     if (exchanged_[i]) continue;
@@ -173,6 +173,7 @@ bool IWorker::EndSynchronize() {
     ExchangeSegment(comm_stream_, segments_[i]);
     exchanged_[i] = 1;
   }
+  armed_ = false;
   AfterExchange();
   ASLP_OK(aslp_event_record(comm_stream_, &ev_done_));
   ASLP_OK(aslp_stream_wait_event(CuStream(), ev_done_));         // the next Propagate reads the exchanged model
@@ -191,7 +192,10 @@ bool BspWorker::Synchronize(int num_worker_samples) {
   return true;
 }
 void BspWorker::ExchangeSegment(aslp_stream_t st, const Segment& seg) {
-  ASLP_OK(aslp_sync_pack(st, arena_.Data(), table_dev_ + seg.first, seg.count, factor_));
+  // pipelined: the job's frame total is still on the device, behind its all-reduce on this stream; the weight is the same
+  // fp32 division either way, so the two forms give the same bits
+  if (armed_) ASLP_OK(aslp_sync_pack_weighted(st, arena_.Data(), table_dev_ + seg.first, seg.count, begin_samples_, count_dev_));
+  else ASLP_OK(aslp_sync_pack(st, arena_.Data(), table_dev_ + seg.first, seg.count, factor_));
   ASLP_OK(aslp_comm_allreduce_sum_f32(comm_, st, arena_.Data() + seg.offset, seg.length));
   ASLP_OK(aslp_sync_unpack(st, arena_.Data(), table_dev_ + seg.first, seg.count));
 }

@@ -61,7 +61,8 @@ class IWorker : public NcclNode {
   // and each component's tensors as soon as Nnet::Backpropagate has enqueued its Update -- on the worker's own stream, while
   // the layers below are still back-propagating.  EndSynchronize() after the minibatch makes the compute stream wait for
   // the last exchange and returns what Synchronize(n) would have.  Only workers whose exchange does not need the global
-  // frame count up front can do this (CanOverlap(): BMUF and SOD; BSP weighs its model by frames_r / frames_all).
+  // frame count on the HOST up front can do this (CanOverlap(): BSP -- whose weight frames_r / frames_all is taken on the
+  // device behind the count's all-reduce --, BMUF and SOD).
   virtual bool CanOverlap() const { return false; }
   void InitParam(aslp_nnet::Nnet* nnet);
   void BeginSynchronize(int num_worker_samples);
@@ -86,6 +87,7 @@ class IWorker : public NcclNode {
   int* count_host_;                    // page-locked: this rank's frame count in, the job's total out
   int* count_dev_;
   bool armed_;
+  int begin_samples_;                  // the frame count BeginSynchronize was given
   std::vector<char> exchanged_;
 };
 
@@ -94,6 +96,7 @@ class BspWorker : public IWorker {
   BspWorker(const char id[128], int nranks, int rank) : IWorker(id, nranks, rank) {}
   BspWorker() : IWorker(WorkerBootstrap()) {}                                  // bsp-worker.h:21
   bool Synchronize(int num_worker_samples);
+  bool CanOverlap() const { return true; }
  protected:
   void ExchangeSegment(aslp_stream_t st, const Segment& seg);
  private:

@@ -146,13 +146,13 @@ def test_two_rank_worker_matches_replica_simulation(kind):
     run_world(2, kind)
 
 
-@pytest.mark.parametrize("kind,mode", [("bsp", "segmented"), ("bmuf", "segmented"), ("bmuf", "overlapped"), ("sod", "overlapped")])
+@pytest.mark.parametrize("kind,mode", [("bsp", "segmented"), ("bsp", "overlapped"), ("bmuf", "segmented"), ("bmuf", "overlapped"), ("sod", "overlapped")])
 def test_single_rank_exchange_by_component(kind, mode):
     """IWorker::InitParam(nnet) / BeginSynchronize / EndSynchronize: the exchange pipelined by layer gives what the blocking one does"""
     run_world(1, kind, mode)
 
 
-@pytest.mark.parametrize("kind,mode", [("bsp", "segmented"), ("bmuf", "overlapped"), ("sod", "overlapped")])
+@pytest.mark.parametrize("kind,mode", [("bsp", "segmented"), ("bsp", "overlapped"), ("bmuf", "overlapped"), ("sod", "overlapped")])
 def test_two_rank_exchange_by_component(kind, mode):
     import torch
     if torch.cuda.device_count() < 2:
