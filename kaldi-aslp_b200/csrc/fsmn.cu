@@ -151,7 +151,11 @@ int filter(cudaStream_t st, float* y, int ldy, const float* x, int ldx, int T, i
     aslp_set_last_error_msg("FSMN operands must be 16-byte aligned with strides that are multiples of 4 floats", __FILE__, __LINE__);
     return ASLP_STATUS_INVALID_VALUE;
   }
-  ASLP_CUDA(cudaFuncSetAttribute(fsmn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_allowed = 0;                      // raised when a wider context comes along, not on every launch
+  if (smem > smem_allowed) {
+    ASLP_CUDA(cudaFuncSetAttribute(fsmn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_allowed = smem;
+  }
   dim3 grid(aslp_div_up(D, COLS), aslp_div_up(T, TT));
   fsmn_filter_kernel<<<grid, TT / TB * 32, smem, st>>>(y, ldy, x, ldx, T, D, coef, ldc, P, C, rev);
   ASLP_CHECK_LAUNCH();
@@ -187,7 +191,11 @@ int aslp_fsmn_coef_grad(aslp_stream_t s, float* coef_corr, int ldc, const float*
   if (partial == nullptr) { aslp_set_last_error_msg("scratch allocation failed", __FILE__, __LINE__); return ASLP_STATUS_MEMOPS_FAILED; }
   const size_t smem = ((size_t)(TT + C - 1 + 2 * TB) + TT) * COLS * sizeof(float);
   if (smem > 220 * 1024) { aslp_set_last_error_msg("FSMN context too large for one shared-memory tile", __FILE__, __LINE__); return ASLP_STATUS_INVALID_VALUE; }
-  ASLP_CUDA(cudaFuncSetAttribute(fsmn_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_allowed = 0;
+  if (smem > smem_allowed) {
+    ASLP_CUDA(cudaFuncSetAttribute(fsmn_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_allowed = smem;
+  }
   dim3 grid(aslp_div_up(D, COLS), chunks);
   fsmn_grad_partial_kernel<<<grid, warps * 32, smem, st>>>(partial, in, ldi, out_diff, ldo, T, D, past, C, Dpad);
   ASLP_CHECK_LAUNCH();
